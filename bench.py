@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the B200 filtering hot path on BASELINE.json's metric.
+
+    python bench.py --gpus N --steps K --warmup W [--config c2] [--impl reference]
+
+Default workload (BASELINE.json configs[1], "c2"): FftFilter, 4097-tap low-pass,
+2^28 synthetic c32 samples, single stream per GPU.  One "step" = one pass of the
+hot path over one such batch.  With N > 1 (torchrun, one rank per GPU) every
+rank filters its own independent 2^28-sample capture (weak scaling, no
+data-path collective).  Other configs (c1 FIR, c3 channelizer, c4 resampler)
+are selectable with --config for the per-kernel numbers in DESIGN.md.
+
+Prints ONE JSON line on rank 0 (contract in the task statement):
+  value     = input Msamples/s, inputs resident in HBM (CUDA events, max over ranks)
+  e2e       = same metric through the C ABI's *_run_host entry point with
+              pinned HOST buffers (H2D + kernel + D2H inside the timed region)
+  roofline  = algorithmic bytes of the dominant kernel / its measured duration
+              against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline = oracle port (restated CPU reference) timed on this host
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SEED = 0x5EED0000
+
+
+# ----------------------------------------------------------------- configs --
+def cfg_c1():
+    return dict(name="c1", op="fir", ntaps=64, deci=1, n=1 << 24, cutoff=0.1, dtype="c32",
+                desc="FirFilter c32 low-pass 64 taps, deci 1, 2^24 samples")
+
+
+def cfg_c2():
+    return dict(name="c2", op="fftfilt", ntaps=4097, n=1 << 28, cutoff=0.05, dtype="c32",
+                desc="FftFilter 4097-tap low-pass, 2^28 c32 samples, single stream per GPU")
+
+
+def cfg_c3():
+    return dict(name="c3", op="fir_demod", ntaps=255, deci=10, nchan=1024, n=240_000, dtype="c32",
+                desc="rtl_fm channelizer: 1024 ch x 240000 c32 (0.1 s @2.4 Msps), 255-tap /10 FIR + QuadratureDemod fused")
+
+
+def cfg_c4():
+    return dict(name="c4", op="resample", interp=147, deci=160, n=1 << 30, dtype="f32",
+                desc="RationalResampler 147/160 on 2^30 f32 samples")
+
+
+CONFIGS = {"c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4}
+
+
+def low_pass_taps(ntaps: int, cutoff: float) -> np.ndarray:
+    """Hamming (a0 = 25/46) windowed-sinc low-pass of an exact length, cutoff as a fraction of fs
+    (the rustradio low_pass formula, src/fir.rs:631-655, for an explicit ntaps).  Host-side, one-off."""
+    a0 = np.float32(25.0 / 46.0)
+    k = np.arange(ntaps, dtype=np.float32)
+    win = a0 - (np.float32(1) - a0) * np.cos(np.float32(2 * np.pi) * k / np.float32(max(ntaps - 1, 1)))
+    m = (ntaps - 1) // 2
+    nn = (np.arange(ntaps) - m).astype(np.float32)
+    w0 = np.float32(2 * np.pi * cutoff)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.where(nn == 0, w0 / np.float32(np.pi), np.sin(nn * w0) / (nn * np.float32(np.pi))).astype(np.float32) * win
+    gain = t[m] + 2 * t[m + 1:m + 1 + m].sum(dtype=np.float32)
+    return (t / gain).astype(np.float32)
+
+
+def taps_for(cfg):
+    if cfg["op"] == "fir_demod":
+        return low_pass_taps(cfg["ntaps"], 100e3 / 2.4e6).astype(np.complex64)
+    return low_pass_taps(cfg["ntaps"], cfg["cutoff"]).astype(np.complex64)
+
+
+def alg_bytes(cfg, n_in, n_out):
+    """algorithmic bytes per step."""
+    if cfg["op"] in ("fir", "fftfilt"):
+        return 8 * n_in + 8 * n_out
+    if cfg["op"] == "fir_demod":
+        return 8 * n_in + 4 * n_out
+    if cfg["op"] == "resample":
+        return 4 * (n_in + n_out)
+    raise ValueError(cfg["op"])
+
+
+# ---------------------------------------------------------------- clocks ----
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [c.strip() for c in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------ GPU arm -------
+def run_gpu(args):
+    import torch
+    import rustradio_b200 as R
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = local
+    cfg = CONFIGS[args.config]()
+    stream = torch.cuda.current_stream().cuda_stream
+    seed = SEED + int(cfg["name"][1]) + 1000 * rank      # every rank filters its own capture
+
+    # ---- build the op and its device-resident input ----
+    op = cfg["op"]
+    if op == "fftfilt":
+        n = cfg["n"]
+        f = R.FftFilt(taps_for(cfg), device=dev)
+        n_in = (n // f.nsamples) * f.nsamples            # reference count rule (whole blocks)
+        n_out = n_in
+        din = torch.empty(2 * n, dtype=torch.float32, device=f"cuda:{dev}")
+        dout = torch.empty(2 * n_out, dtype=torch.float32, device=f"cuda:{dev}")
+        R.synth_f32(din, seed, 0, 2 * n, dev, stream)
+
+        def step():
+            f.run(din, n_in, dout, stream)
+        launches_per_step = 2
+        units = n_in
+    elif op == "fir":
+        n = cfg["n"]
+        f = R.Fir(taps_for(cfg), deci=cfg["deci"], device=dev)
+        n_out = f.out_count(n)
+        n_in = n
+        din = torch.empty(2 * n, dtype=torch.float32, device=f"cuda:{dev}")
+        dout = torch.empty(2 * n_out, dtype=torch.float32, device=f"cuda:{dev}")
+        R.synth_f32(din, seed, 0, 2 * n, dev, stream)
+
+        def step():
+            f.run(din, n, dout, n_out, stream)
+        launches_per_step = 1
+        units = n_in
+    elif op == "fir_demod":
+        n, nchan = cfg["n"], cfg["nchan"] // (1 if world == 1 else 1)
+        f = R.Fir(taps_for(cfg), deci=cfg["deci"], device=dev)
+        out_n = f.out_count(n)
+        need = (out_n - 1) * cfg["deci"] + cfg["ntaps"]
+        din = torch.empty(2 * n * nchan, dtype=torch.float32, device=f"cuda:{dev}")
+        dout = torch.empty((out_n - 1) * nchan, dtype=torch.float32, device=f"cuda:{dev}")
+        R.synth_f32(din, seed, 0, 2 * n * nchan, dev, stream)
+
+        def step():
+            f.demod_run_batch(din, n, need, 1.0, dout, out_n - 1, out_n, nchan, stream)
+        launches_per_step = 1
+        n_in, n_out = n * nchan, (out_n - 1) * nchan
+        units = n_in
+    elif op == "resample":
+        n = cfg["n"]
+        f = R.Resampler(4, cfg["interp"], cfg["deci"], device=dev)
+        n_out = (n * cfg["interp"] + cfg["deci"] - 1) // cfg["deci"]
+        n_in = n
+        din = torch.empty(n, dtype=torch.float32, device=f"cuda:{dev}")
+        dout = torch.empty(n_out + 16, dtype=torch.float32, device=f"cuda:{dev}")
+        R.synth_f32(din, seed, 0, n, dev, stream)
+
+        def step():
+            f.reset()
+            c, p, w = f.run(din, n, dout, n_out + 16, stream)
+            assert (c, p) == (n, n_out)
+        launches_per_step = 1
+        units = n_in
+    else:
+        raise SystemExit(f"unknown op {op}")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    l0 = R.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = R.launch_count() - l0
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{dev}")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = units * world / (ms_per_step * 1e-3) / 1e6      # Msamples/s, whole job
+
+    # ---- end to end: host buffers through *_run_host ----
+    e2e = None
+    if not args.no_e2e and op in ("fftfilt", "fir"):
+        hin = R.PinnedBuffer(np.complex64, cfg["n"])
+        hout = R.PinnedBuffer(np.complex64, n_out)
+        R.lib().rrc_memcpy_d2h(dev, hin.ptr, din.data_ptr(), cfg["n"] * 8, stream)
+        torch.cuda.synchronize()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(2):
+            f.reset() if op == "fftfilt" else None
+            f.run_host(hin, hout)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            if op == "fftfilt":
+                f.reset()
+            got = f.run_host(hin, hout)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{dev}")
+        if dist:
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": units * world / (dt / e2e_steps) / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(8 * (n_in if op == "fftfilt" else cfg["n"])), "d2h_bytes_per_step": int(8 * len(got)),
+               "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3, "timer": "host wall clock around rrc_*_run_host (returns after D2H completes)"}
+        hin.free(); hout.free()
+
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = json.loads(peaks_path.read_text())["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    ab = alg_bytes(cfg, n_in, n_out)
+    achieved = ab / (ms_per_step * 1e-3) / 1e9
+    traffic_path = ROOT / "profiles" / "traffic.json"
+    traffic = None
+    if traffic_path.exists():
+        traffic = json.loads(traffic_path.read_text()).get(cfg["name"])
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                "kernel": {"fftfilt": "fftfilt_kernel", "fir": "fir_poly_kernel", "fir_demod": "fir_poly_kernel<DEMOD>", "resample": "resample_kernel"}[op],
+                "duration_ms": ms_per_step,
+                "note": "duration = CUDA-event time of the whole step on the launching stream / steps; the step is this one kernel"
+                        + (" plus a <3 us history-update kernel" if op == "fftfilt" else "")}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(cfg, threads=1, budget_s=args.cpu_budget)
+
+    line = {
+        "metric": "Msamples/s (c32) FIR/FftFilter/resampler at 1/2/4/8 B200; % of roofline",
+        "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if cfg["dtype"] == "f32" else "c32 (complex f32)", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "name": cfg["name"], "samples_per_gpu_per_step": int(units),
+                   "outputs_per_gpu_per_step": int(n_out), "parallelism": f"independent stream per GPU x{world}",
+                   "l2_policy": "inputs larger than L2 (>= 0.5 GiB per step vs 126 MB L2)" if ab > 4e8 else "input 128 MiB ~ L2 size; see DESIGN.md",
+                   "timer": "torch.cuda.Event on the launching stream, max over ranks"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------ CPU reference arm ---
+def cpu_baseline(cfg, threads: int, budget_s: float):
+    """Times the oracle port (oracle/rr_oracle.c, -O3 AVX2 build, no FMA contraction like rustc)
+    on a bounded sample of the same workload.  This is the ONLY place bench.py executes oracle/."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as O
+    op = cfg["op"]
+    taps = taps_for(cfg) if op != "resample" else None
+    if op == "fftfilt":
+        per = 1 << 21
+        x = O.synth_c32(SEED + 2, 0, per)
+        objs = [O.FftFilt(taps, fast=True) for _ in range(threads)]
+        fn = lambda i: len(objs[i].run(x))
+        sample = f"{threads} x 2^21 c32 samples per repetition, overlap-add with F=16384 like the reference"
+    elif op == "fir":
+        per = 1 << 19
+        x = O.synth_c32(SEED + 1, 0, per)
+        fn = lambda i: len(O.fir(x, taps, cfg["deci"], fast=True))
+        sample = f"{threads} x 2^19 c32 samples per repetition"
+    elif op == "fir_demod":
+        per = 240_000
+        x = O.synth_c32(SEED + 3, 0, per)
+        fn = lambda i: len(O.quad_demod(O.fir(x, taps, cfg["deci"], fast=True), fast=True))
+        sample = f"{threads} channels x 240000 c32 samples per repetition"
+    else:
+        per = 1 << 24
+        x = O.synth_f32(SEED + 4, 0, per)
+        fn = lambda i: len(O.resample(x, cfg["interp"], cfg["deci"]))
+        sample = f"{threads} x 2^24 f32 samples per repetition"
+    fn(0)  # warm-up
+    reps, t0 = 0, time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        while True:
+            list(ex.map(fn, range(threads)))
+            reps += 1
+            if time.perf_counter() - t0 >= budget_s or reps >= 64:
+                break
+    dt = time.perf_counter() - t0
+    return {"value": per * threads * reps / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
+            "sample": f"{sample}, {reps} repetitions, {dt:.1f} s",
+            "note": "restated CPU baseline (oracle port), not rustradio itself: no Rust toolchain in the image; "
+                    "the port's scalar radix-4 FFT is slower than rustfft's AVX planner"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; rustradio
+    cannot be compiled here).  One rustradio block processes one stream on one thread
+    (FftFilter::work has no threading, src/fft_filter.rs:291), so threads = streams = --gpus."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.config]()
+    streams = max(1, args.gpus)
+    threads = min(streams, os.cpu_count() or 1)
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    res = cpu_baseline(cfg, threads=threads, budget_s=max(5.0, min(60.0, 3.0 * steps)))
+    line = {
+        "impl": "reference",
+        "metric": "Msamples/s (c32) FIR/FftFilter/resampler at 1/2/4/8 B200; % of roofline",
+        "value": res["value"], "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if cfg["dtype"] == "f32" else "c32 (complex f32)", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "name": cfg["name"], "parallelism": f"{threads} host thread(s), one stream each"},
+        "cpu_baseline": res,
+        "e2e": {"value": res["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,213 @@
+/*
+ * rustradio_cuda.h — C ABI of the B200 filtering hot path for rustradio.
+ *
+ * This is the whole drop-in boundary: `extern "C"`, plain pointers and
+ * sizes, no C++/torch/Rust types.  rustradio has no FFI today (it is pure
+ * Rust); these are the entry points the `rustradio-cuda` crate's FFI binds
+ * (see INTEGRATION.md and rustradio_b200/rust/rustradio-cuda/src/ffi.rs).
+ * Each group cites the reference code it replaces (paths relative to the
+ * rustradio v0.18.2 source tree).
+ *
+ * Conventions
+ *   - Every function returns an `int` status: RRC_OK (0) or a negative
+ *     RRC_ERR_*; the text of the last error on the calling thread is
+ *     rrc_last_error().  Nothing unwinds across the boundary.
+ *   - Complex<f32> samples/taps are interleaved (re, im) floats, i.e.
+ *     num_complex::Complex<f32>'s #[repr(C)] layout; `float*` arguments that
+ *     carry c32 data have 2 floats per sample and sizes count SAMPLES.
+ *   - "dev" pointers are device pointers on the handle's device; "host"
+ *     pointers are host memory (pinned memory makes the copies asynchronous).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's device
+ *     default stream).  Kernel-level *_run calls only enqueue; they do not
+ *     synchronise.  *_run_host calls return after the result is in host memory.
+ *   - Every entry point selects the handle's device itself (rustradio's
+ *     AsyncGraph may call work() from different threads, src/agraph.rs:64-97).
+ *   - There is no CPU fallback anywhere behind this ABI: without a CUDA
+ *     device every compute entry point fails with RRC_ERR_CUDA.
+ */
+#ifndef RUSTRADIO_CUDA_H
+#define RUSTRADIO_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRC_OK            0
+#define RRC_ERR_INVALID  (-1)   /* bad argument (the reference would assert!/Err) */
+#define RRC_ERR_CUDA     (-2)   /* CUDA runtime/driver failure -> Error::DeviceError (src/lib.rs:288-294) */
+#define RRC_ERR_NOMEM    (-3)
+#define RRC_ERR_STATE    (-4)   /* call made in the wrong state */
+#define RRC_ERR_UNSUPPORTED (-5)
+
+#define RRC_ABI_VERSION 1
+
+/* ------------------------------------------------------------ runtime --- */
+int         rrc_abi_version(void);
+const char* rrc_last_error(void);
+int rrc_device_count(int* count);
+int rrc_device_name(int device, char* buf, size_t buflen);
+int rrc_device_sm_count(int device, int* sms);
+
+/* Device / pinned memory and copies, so the host language needs no cudart. */
+int rrc_malloc_device(int device, size_t bytes, void** dev_ptr);
+int rrc_free_device(int device, void* dev_ptr);
+int rrc_malloc_pinned(size_t bytes, void** host_ptr);
+int rrc_free_pinned(void* host_ptr);
+int rrc_host_register(void* host_ptr, size_t bytes);      /* pin caller memory */
+int rrc_host_unregister(void* host_ptr);
+int rrc_memset_device(int device, void* dev_ptr, int value, size_t bytes, void* stream);
+int rrc_memcpy_h2d(int device, void* dev_dst, const void* host_src, size_t bytes, void* stream);
+int rrc_memcpy_d2h(int device, void* host_dst, const void* dev_src, size_t bytes, void* stream);
+int rrc_memcpy_d2d(int device, void* dev_dst, const void* dev_src, size_t bytes, void* stream);
+int rrc_stream_create(int device, void** stream);
+int rrc_stream_destroy(int device, void* stream);
+int rrc_stream_sync(int device, void* stream);
+int rrc_device_sync(int device);
+/* CUDA-event timing on a stream (used by bench.py; torch.cuda.Event only sees torch's stream). */
+int rrc_event_create(int device, void** event);
+int rrc_event_destroy(int device, void* event);
+int rrc_event_record(int device, void* event, void* stream);
+int rrc_event_sync(int device, void* event);
+int rrc_event_elapsed_ms(int device, void* start, void* stop, float* ms);
+/* Fill a device buffer with the deterministic synthetic signal used by the
+ * tests and bench (same splitmix64 counter generator as oracle/rr_oracle.c:
+ * float index i -> U(-1,1)); n_floats floats starting at float index first. */
+int rrc_synth_f32(int device, uint64_t seed, uint64_t first_index, float* dev_out, size_t n_floats, void* stream);
+/* Number of kernels this library has launched on the calling process so far. */
+int rrc_launch_count(uint64_t* launches);
+
+/* ---------------------------------------------------------------- FIR --- */
+/*
+ * Replaces Fir<T>::new / filter / filter_n_inplace (src/fir.rs:156-197) and the
+ * compute step of FirFilter<T>::work (src/fir.rs:526-531) for T = Complex and
+ * T = Float.  out[i] = sum_{j<ntaps} in[i*deci + j] * taps[ntaps-1-j].
+ * The host computes n/need/out_n exactly as src/fir.rs:496-525 (see
+ * rrc_fir_plan) and calls run with need = (out_n-1)*deci + ntaps valid inputs.
+ */
+typedef struct rrc_fir rrc_fir_t;
+
+/* flags */
+#define RRC_FIR_NO_REAL_TAP_FASTPATH 1u  /* always do the full complex*complex MAC even if every tap has im == 0 */
+#define RRC_FIR_FORCE_GENERIC        2u  /* use the one-thread-per-output fallback kernel (testing) */
+
+int rrc_fir_c32_create(int device, const float* taps_c32, size_t ntaps, size_t deci, unsigned flags, rrc_fir_t** out);
+int rrc_fir_f32_create(int device, const float* taps, size_t ntaps, size_t deci, unsigned flags, rrc_fir_t** out);
+/* FirFilterBuilder::translate (src/fir.rs:476-486) + new_translator (:427-462):
+ * rotates the taps (same f32 recurrence) and arms the per-output rotator.
+ * The rotator phase is evaluated per output from the exact f64 angle instead
+ * of the reference's drifting f32 recurrence (:464-473).
+ * freq == 0 is a no-op like the reference (:438-440).  c32 only. */
+int rrc_fir_set_translate(rrc_fir_t* h, float samp_rate, float freq);
+int rrc_fir_destroy(rrc_fir_t* h);
+int rrc_fir_ntaps(const rrc_fir_t* h, size_t* ntaps);
+int rrc_fir_deci(const rrc_fir_t* h, size_t* deci);
+/* 1 if the real-tap fast path (2 FMA per tap instead of 4) is active. */
+int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes);
+/* Restart the translate rotator's output counter (new stream). */
+int rrc_fir_reset(rrc_fir_t* h);
+
+/* The integer part of FirFilter::work (src/fir.rs:496-525): given the input
+ * window length and the free output space, how many samples to consume, how
+ * many inputs the kernel must see and how many outputs it produces.
+ * consume == 0 means WaitForStream: *wait_need is the sample count to wait
+ * for and *wait_on_output says which stream (0 = src, 1 = dst). */
+int rrc_fir_plan(size_t ntaps, size_t deci, size_t in_len, size_t out_free,
+                 size_t* consume, size_t* need, size_t* out_n, size_t* wait_need, int* wait_on_output);
+
+int rrc_fir_run(rrc_fir_t* h, const void* in_dev, size_t need, void* out_dev, size_t out_n, void* stream);
+/* nchan independent channels with the same taps: channel c reads
+ * in_dev + c*in_stride samples and writes out_dev + c*out_stride samples. */
+int rrc_fir_run_batch(rrc_fir_t* h, const void* in_dev, size_t in_stride, size_t need,
+                      void* out_dev, size_t out_stride, size_t out_n, size_t nchan, void* stream);
+/* Fused FirFilter<Complex> -> QuadratureDemod (the rtl_fm shape,
+ * rustradio-ui/examples/rtlsdr-fm/src/worker.rs:85-90): produces out_n-1
+ * floats per channel, equal to running the two blocks back to back.  c32 only. */
+int rrc_fir_c32_demod_run_batch(rrc_fir_t* h, const void* in_dev, size_t in_stride, size_t need,
+                                float gain, float* out_dev, size_t out_stride, size_t out_n,
+                                size_t nchan, void* stream);
+/* Host-buffer form: H2D -> kernel -> D2H, chunked and double-buffered, for a
+ * whole stream of n_in samples; writes floor((n_in-ntaps+1)/deci) outputs
+ * (0 if n_in < ntaps+deci-1) and returns the count in *n_out. */
+int rrc_fir_run_host(rrc_fir_t* h, const void* in_host, size_t n_in, void* out_host, size_t* n_out);
+
+/* ---------------------------------------------------------- FftFilter --- */
+/*
+ * Replaces RustFftEngine::new / Engine::run / sum_vec and the overlap
+ * handling of FftFilter::work (src/fft_filter.rs:144-176, 281-287, 331-348).
+ * The device computes the same linear convolution y[n] = sum_k h[k] x[n-k]
+ * (zero initial state, src/fft_filter.rs:270) by overlap-SAVE with its own
+ * FFT size; state carried between calls is the last ntaps-1 inputs.
+ * run() accepts any n and produces exactly n outputs; the reference's count
+ * rule (whole blocks of nsamples = 2*nextpow2(ntaps) - ntaps, trailing
+ * partial block never flushed, :306-327) is applied by the caller / by
+ * rrc_fftfilt_plan.
+ */
+typedef struct rrc_fftfilt rrc_fftfilt_t;
+
+int rrc_fftfilt_c32_create(int device, const float* taps_c32, size_t ntaps, rrc_fftfilt_t** out);
+int rrc_fftfilt_destroy(rrc_fftfilt_t* h);
+int rrc_fftfilt_reset(rrc_fftfilt_t* h, void* stream);          /* zero the carried history */
+/* calc_fft_size and nsamples exactly as the reference (src/fft_filter.rs:36-42,262-263). */
+int rrc_fftfilt_ref_fft_size(size_t ntaps, size_t* fft_size, size_t* nsamples);
+/* Device-side geometry actually used (FFT size, valid outputs per block). */
+int rrc_fftfilt_geometry(const rrc_fftfilt_t* h, size_t* fft_size, size_t* valid_per_block);
+/* Integer part of FftFilter::work's loop (src/fft_filter.rs:293-327) for one
+ * call: with `buffered` samples already accumulated (< nsamples), an input
+ * window of in_len and out_free output space, how many whole reference
+ * blocks can run now (*blocks), how many input samples are taken (*consume,
+ * including a final partial accumulation) and the WaitForStream that ends
+ * the loop. */
+int rrc_fftfilt_plan(size_t ntaps, size_t buffered, size_t in_len, size_t out_free,
+                     size_t* blocks, size_t* consume, size_t* buffered_after,
+                     size_t* wait_need, int* wait_on_output);
+int rrc_fftfilt_run(rrc_fftfilt_t* h, const float* in_dev, size_t n, float* out_dev, void* stream);
+/* Fused FftFilter -> RationalResampler(1, deci) (BASELINE config 5): writes
+ * y[k*deci - phase] style decimated output without materialising y.
+ * `skip` = number of filter outputs to drop before the first kept one
+ * (carries the resampler counter between calls); produces
+ * ceil((n - skip)/deci) outputs for n > skip. */
+int rrc_fftfilt_decim_run(rrc_fftfilt_t* h, const float* in_dev, size_t n, size_t deci, size_t skip,
+                          float* out_dev, size_t* n_out, void* stream);
+/* Host-buffer form for a whole stream: n_in samples in, floor(n_in/nsamples)*nsamples out. */
+int rrc_fftfilt_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, float* out_host, size_t* n_out);
+
+/* -------------------------------------------------- RationalResampler --- */
+/*
+ * Replaces RationalResampler::new / work (src/rational_resampler.rs:125-206):
+ * counter-driven sample-and-hold/drop, out[k] = in[floor((k*deci - c0)/interp)].
+ * No filtering, no floating point; bit-exact for any element size.
+ */
+typedef struct rrc_resampler rrc_resampler_t;
+
+/* elem_size in {1,2,4,8,16}.  interp == 0 or deci == 0 -> RRC_ERR_INVALID
+ * (the reference returns Err, :130-135).  gcd-reduced like :136-138. */
+int rrc_resampler_create(int device, size_t elem_size, size_t interp, size_t deci, rrc_resampler_t** out);
+int rrc_resampler_destroy(rrc_resampler_t* h);
+int rrc_resampler_reset(rrc_resampler_t* h);
+/* State inspection (counter <= 0 between calls unless a sample is pending). */
+int rrc_resampler_state(const rrc_resampler_t* h, int64_t* interp, int64_t* deci, int64_t* counter, int* has_pending);
+/* One work() call on an input window of n_in and an output window of out_cap
+ * samples.  *wait_on_output: 1 = WaitForStream(dst,1), 0 = WaitForStream(src,1). */
+int rrc_resampler_run(rrc_resampler_t* h, const void* in_dev, size_t n_in, void* out_dev, size_t out_cap,
+                      size_t* consumed, size_t* produced, int* wait_on_output, void* stream);
+int rrc_resampler_run_host(rrc_resampler_t* h, const void* in_host, size_t n_in, void* out_host, size_t out_cap,
+                           size_t* consumed, size_t* produced);
+
+/* ---------------------------------------------------- QuadratureDemod --- */
+/*
+ * Replaces the compute of QuadratureDemod::work (src/quadrature_demod.rs:56-111,
+ * libm branch): out[t] = gain * atan2(Im, Re) of conj(in[t]) * in[t+1],
+ * t < n_in - 1.  The caller keeps the 1-sample history by consuming n_in - 1.
+ */
+int rrc_quad_demod_run(int device, const float* in_dev_c32, size_t n_in, float gain, float* out_dev, void* stream);
+int rrc_quad_demod_run_batch(int device, const float* in_dev_c32, size_t in_stride, size_t n_in, float gain,
+                             float* out_dev, size_t out_stride, size_t nchan, void* stream);
+int rrc_quad_demod_run_host(int device, const float* in_host_c32, size_t n_in, float gain, float* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUSTRADIO_CUDA_H */

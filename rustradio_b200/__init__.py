@@ -1,0 +1,15 @@
+"""rustradio_b200 — B200-native filtering hot path for rustradio.
+
+The product is the C-ABI shared library `librustradio_cuda.so`
+(include/rustradio_cuda.h; sources in rustradio_b200/csrc).  This Python
+package is only a ctypes binding of that ABI for the test-suite and bench.py;
+it contains no compute and no CPU fallback: every call goes to the CUDA
+library and raises `RrcError` if the library or a CUDA device is missing.
+"""
+from .api import (  # noqa: F401
+    RrcError, lib, library_path, build_library, device_count,
+    DeviceBuffer, PinnedBuffer, Fir, FftFilt, Resampler, quad_demod, quad_demod_host,
+    synth_f32, launch_count, fir_plan, fftfilt_plan, fftfilt_ref_fft_size,
+    Event, stream_sync, device_sync,
+    RRC_FIR_NO_REAL_TAP_FASTPATH, RRC_FIR_FORCE_GENERIC,
+)

@@ -1,0 +1,102 @@
+// fft_regs.cuh — compile-time-unrolled in-register DFTs (N = 2..32) for the
+// shared-memory FFT used by the overlap-save FftFilter kernel.
+//
+// dif<N, DIR>(v): decimation-in-frequency radix-2 recursion on v[0..N).
+//   natural-order input, BIT-REVERSED output: X[k] ends up in v[bitrev<N>(k)].
+//   DIR = +1: forward (W = e^{-2 pi i / N}); DIR = -1: inverse (conjugate), unnormalised.
+// All twiddles are compile-time constants; multiplications by 1, -i and
+// (+-1 +- i)/sqrt(2) are special-cased.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace rrc { namespace fftr {
+
+#if defined(__CUDACC__)
+#define RRC_HD __host__ __device__ __forceinline__
+#else
+#define RRC_HD inline
+#endif
+
+// cos(2*pi*i/64), i = 0..16 (first quadrant in 1/64-turn steps).
+RRC_HD constexpr double cos64_q(int i) {
+    constexpr double t[17] = {
+        1.0,
+        0.99518472667219688624, 0.98078528040323044913, 0.95694033573220886494,
+        0.92387953251128675613, 0.88192126434835502971, 0.83146961230254523708,
+        0.77301045336273696081, 0.70710678118654752440, 0.63439328416364549822,
+        0.55557023301960222474, 0.47139673682599764856, 0.38268343236508977173,
+        0.29028467725446236764, 0.19509032201612826785, 0.09801714032956060199,
+        0.0};
+    return t[i];
+}
+// cos / sin of 2*pi*num/64 for any integer num.
+RRC_HD constexpr double cos64(int num) {
+    num = ((num % 64) + 64) % 64;
+    if (num <= 16) return cos64_q(num);
+    if (num <= 32) return -cos64_q(32 - num);
+    if (num <= 48) return -cos64_q(num - 32);
+    return cos64_q(64 - num);
+}
+RRC_HD constexpr double sin64(int num) { return cos64(num - 16); }
+
+RRC_HD constexpr int bitrev(int x, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+RRC_HD constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
+
+RRC_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+RRC_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+RRC_HD float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
+}
+RRC_HD float2 cmul_conj(float2 a, float2 b) {   // a * conj(b)
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -(a.x * b.y)));
+}
+RRC_HD float2 csqr(float2 a) { return make_float2(fmaf(a.x, a.x, -(a.y * a.y)), 2.0f * a.x * a.y); }
+
+// d * exp(-DIR * 2*pi*i * NUM/DEN), NUM/DEN in [0, 1/2), DEN | 64.
+template <int NUM, int DEN, int DIR>
+RRC_HD float2 mul_w(float2 d) {
+    constexpr int n64 = NUM * (64 / DEN);          // angle in 1/64 turns
+    if constexpr (n64 == 0) {
+        return d;
+    } else if constexpr (n64 == 16) {              // -i (fwd) / +i (inv)
+        return DIR > 0 ? make_float2(d.y, -d.x) : make_float2(-d.y, d.x);
+    } else if constexpr (n64 == 8) {               // (1 -+ i)/sqrt2
+        constexpr float c = (float)0.70710678118654752440;
+        return DIR > 0 ? make_float2(c * (d.x + d.y), c * (d.y - d.x))
+                       : make_float2(c * (d.x - d.y), c * (d.y + d.x));
+    } else if constexpr (n64 == 24) {              // (-1 -+ i)/sqrt2
+        constexpr float c = (float)0.70710678118654752440;
+        return DIR > 0 ? make_float2(c * (d.y - d.x), -c * (d.x + d.y))
+                       : make_float2(-c * (d.x + d.y), c * (d.x - d.y));
+    } else {
+        constexpr float wr = (float)cos64(n64);
+        constexpr float wi = (float)(-DIR * sin64(n64));
+        return make_float2(fmaf(d.x, wr, -(d.y * wi)), fmaf(d.x, wi, d.y * wr));
+    }
+}
+
+template <int N, int DIR, int I>
+struct DifLevel {
+    static RRC_HD void run(float2* v) {
+        const float2 a = v[I], b = v[I + N / 2];
+        v[I] = cadd(a, b);
+        v[I + N / 2] = mul_w<I, N, DIR>(csub(a, b));
+        if constexpr (I + 1 < N / 2) DifLevel<N, DIR, I + 1>::run(v);
+    }
+};
+
+template <int N, int DIR>
+RRC_HD void dif(float2* v) {
+    static_assert(N >= 1 && N <= 64 && (N & (N - 1)) == 0, "N must be a power of two <= 64");
+    if constexpr (N >= 2) {
+        DifLevel<N, DIR, 0>::run(v);
+        dif<N / 2, DIR>(v);
+        dif<N / 2, DIR>(v + N / 2);
+    }
+}
+
+}}  // namespace rrc::fftr

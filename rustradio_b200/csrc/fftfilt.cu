@@ -1,0 +1,248 @@
+// fftfilt.cu — FftFilter (FFT block convolution) for Complex<f32> on sm_100a.
+//
+// Replaces rustradio's RustFftEngine::new / Engine::run / sum_vec and the
+// overlap handling of FftFilter::work (src/fft_filter.rs:144-176, 281-287,
+// 331-348).  The reference does overlap-ADD with F = 2*nextpow2(ntaps)
+// (SURVEY F1); this kernel computes the same linear convolution
+//   y[n] = sum_k h[k] x[n-k],  x[n<0] = 0 (src/fft_filter.rs:270)
+// by overlap-SAVE with a fixed 16384-point transform held entirely in one
+// CTA's shared memory: one HBM read of the input, one HBM write of the
+// output, forward FFT, spectrum multiply and inverse FFT fused in between
+// (fftfilt_core.cuh).  State carried across calls: the last ntaps-1 inputs.
+//
+// Roofline: per 16384-point block, V = 16384-(ntaps-1) outputs; bytes
+// 8*(N_in + N_out); ~116 FP32 instructions per transformed point (issue bound
+// before HBM bound for ntaps > ~2048).
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <vector>
+
+#include "common.cuh"
+#include "fftfilt_core.cuh"
+#include "fftfilt_tables.hpp"
+#include "pipeline.cuh"
+
+namespace rrc {
+
+using fftk::BlockIO;
+
+constexpr size_t FFTFILT_SMEM = (size_t)(fftk::N + 512 + 512) * sizeof(float2);
+
+__global__ void __launch_bounds__(fftk::NT, 1)
+fftfilt_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __restrict__ tw1g,
+               const float2* __restrict__ tw2g, long long nblocks) {
+    extern __shared__ __align__(16) float2 sm[];
+    float2* s_tw2 = sm + fftk::N;
+    float2* s_tw1 = s_tw2 + 512;
+    const int tid = threadIdx.x;
+    s_tw2[tid] = tw2g[tid];
+    s_tw1[tid] = tw1g[tid];
+    __syncthreads();
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        fftk::phase_a(tid, blk, io, s_tw1, sm);
+        __syncthreads();
+        fftk::phase_b(tid, s_tw2, sm);
+        __syncthreads();
+        fftk::phase_c(tid, Hp, sm);
+        __syncthreads();
+        fftk::phase_bi(tid, s_tw2, sm);
+        __syncthreads();
+        fftk::phase_ai(tid, blk, io, s_tw1, sm);
+        // no barrier: the next phase_a writes exactly the words this thread just read
+    }
+}
+
+// hist_next[i] = x[n - T1 + i] over the concatenation (hist_cur ++ in).
+__global__ void fftfilt_hist_kernel(const float2* __restrict__ hist_cur, const float2* __restrict__ in,
+                                    long long n, int T1, float2* __restrict__ hist_next) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T1; i += gridDim.x * blockDim.x) {
+        const long long s = n - T1 + i;
+        hist_next[i] = s >= 0 ? in[s] : hist_cur[s + T1];
+    }
+}
+
+}  // namespace rrc
+
+using namespace rrc;
+
+struct rrc_fftfilt {
+    int device = 0;
+    size_t ntaps = 0;
+    int T1 = 0, V = 0;
+    float2* Hp = nullptr;
+    float2* tw1 = nullptr;
+    float2* tw2 = nullptr;
+    float2* hist[2] = {nullptr, nullptr};
+    int cur = 0;
+    Pipe pipe;
+};
+
+namespace {
+
+size_t ref_fft_size(size_t ntaps) {   // calc_fft_size, src/fft_filter.rs:36-42
+    size_t n = 1;
+    while (n < ntaps) n <<= 1;
+    return 2 * n;
+}
+
+int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, size_t deci, size_t skip, cudaStream_t st) {
+    BlockIO io;
+    io.in = reinterpret_cast<const float2*>(in);
+    io.hist = h->hist[h->cur];
+    io.out = reinterpret_cast<float2*>(out);
+    io.n_in = (long long)n;
+    io.n_out = (long long)n_out;
+    io.T1 = h->T1;
+    io.V = h->V;
+    io.deci = (int)deci;
+    io.skip = (long long)skip;
+    const long long nblocks = ((long long)n + h->V - 1) / h->V;
+    const int grid = (int)std::min<long long>(nblocks, sm_count(h->device));
+    static bool attr_set[64] = {false};
+    if (!attr_set[h->device]) {
+        RRC_CUDA(cudaFuncSetAttribute(fftfilt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_SMEM));
+        attr_set[h->device] = true;
+    }
+    fftfilt_kernel<<<grid, fftk::NT, FFTFILT_SMEM, st>>>(io, h->Hp, h->tw1, h->tw2, nblocks);
+    RRC_CHECK_LAUNCH();
+    count_launch();
+    if (h->T1 > 0) {
+        fftfilt_hist_kernel<<<(h->T1 + 255) / 256, 256, 0, st>>>(h->hist[h->cur], io.in, (long long)n, h->T1, h->hist[h->cur ^ 1]);
+        RRC_CHECK_LAUNCH();
+        count_launch();
+        h->cur ^= 1;
+    }
+    return RRC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rrc_fftfilt_ref_fft_size(size_t ntaps, size_t* fft_size, size_t* nsamples) {
+    if (ntaps == 0) return fail(RRC_ERR_INVALID, "FftFilter needs at least one tap (src/fft_filter.rs:146)");
+    const size_t f = ref_fft_size(ntaps);
+    if (fft_size) *fft_size = f;
+    if (nsamples) *nsamples = f - ntaps;
+    return RRC_OK;
+}
+
+int rrc_fftfilt_plan(size_t ntaps, size_t buffered, size_t in_len, size_t out_free,
+                     size_t* blocks, size_t* consume, size_t* buffered_after, size_t* wait_need, int* wait_on_output) {
+    if (!blocks || !consume || !buffered_after || !wait_need || !wait_on_output) return fail(RRC_ERR_INVALID, "NULL argument");
+    if (ntaps == 0) return fail(RRC_ERR_INVALID, "ntaps must be nonzero");
+    const size_t S = ref_fft_size(ntaps) - ntaps;      // nsamples, src/fft_filter.rs:262-263
+    if (buffered >= S) return fail(RRC_ERR_INVALID, "buffered %zu >= nsamples %zu", buffered, S);
+    size_t nb = 0, used = 0, b = buffered, avail = in_len, space = out_free;
+    for (;;) {
+        if (S > space) { *wait_need = S; *wait_on_output = 1; break; }            // :293-303
+        const size_t add = std::min(avail, S - b);                                 // :306
+        b += add; avail -= add; used += add;                                       // :308,314
+        if (b < S) { *wait_need = S - b; *wait_on_output = 0; break; }             // :315-327
+        ++nb; space -= S; b = 0;                                                   // :331-352
+    }
+    *blocks = nb; *consume = used; *buffered_after = b;
+    return RRC_OK;
+}
+
+int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftfilt_t** out) {
+    if (!out) return fail(RRC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!taps || ntaps == 0) return fail(RRC_ERR_INVALID, "FftFilter needs at least one tap (src/fft_filter.rs:146)");
+    if (ntaps > (size_t)fftk::N - 4096 + 1)
+        return fail(RRC_ERR_UNSUPPORTED, "ntaps %zu > %d: the single-CTA 16384-point kernel needs ntaps <= 12289", ntaps, fftk::N - 4096 + 1);
+    RRC_CUDA(cudaSetDevice(device));
+    auto* h = new rrc_fftfilt();
+    h->device = device; h->ntaps = ntaps;
+    h->T1 = (int)ntaps - 1;
+    h->V = fftk::N - h->T1;
+
+    std::vector<float2> Hp, tw1, tw2;
+    fftk::build_tables(taps, ntaps, Hp, tw1, tw2);
+    auto cleanup = [&](int s) { rrc_fftfilt_destroy(h); return s; };
+    auto up = [&](float2** d, const std::vector<float2>& v) -> cudaError_t {
+        cudaError_t e = cudaMalloc((void**)d, v.size() * sizeof(float2));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*d, v.data(), v.size() * sizeof(float2), cudaMemcpyHostToDevice);
+    };
+    cudaError_t e;
+    if ((e = up(&h->Hp, Hp)) != cudaSuccess || (e = up(&h->tw1, tw1)) != cudaSuccess || (e = up(&h->tw2, tw2)) != cudaSuccess)
+        return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
+    for (int i = 0; i < 2; ++i) {
+        const size_t bytes = std::max<size_t>(1, (size_t)h->T1) * sizeof(float2);
+        if ((e = cudaMalloc((void**)&h->hist[i], bytes)) != cudaSuccess || (e = cudaMemset(h->hist[i], 0, bytes)) != cudaSuccess)
+            return cleanup(fail(RRC_ERR_CUDA, "FftFilter history alloc failed: %s", cudaGetErrorString(e)));
+    }
+    *out = h;
+    return RRC_OK;
+}
+
+int rrc_fftfilt_destroy(rrc_fftfilt_t* h) {
+    if (!h) return RRC_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->Hp); cudaFree(h->tw1); cudaFree(h->tw2); cudaFree(h->hist[0]); cudaFree(h->hist[1]);
+    h->pipe.destroy();
+    delete h;
+    return RRC_OK;
+}
+
+int rrc_fftfilt_reset(rrc_fftfilt_t* h, void* stream) {
+    if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
+    RRC_CUDA(cudaSetDevice(h->device));
+    if (h->T1 > 0) RRC_CUDA(cudaMemsetAsync(h->hist[h->cur], 0, (size_t)h->T1 * sizeof(float2), as_stream(stream)));
+    return RRC_OK;
+}
+
+int rrc_fftfilt_geometry(const rrc_fftfilt_t* h, size_t* fft_size, size_t* valid) {
+    if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
+    if (fft_size) *fft_size = fftk::N;
+    if (valid) *valid = (size_t)h->V;
+    return RRC_OK;
+}
+
+int rrc_fftfilt_run(rrc_fftfilt_t* h, const float* in, size_t n, float* out, void* stream) {
+    if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
+    if (n == 0) return RRC_OK;
+    if (!in || !out) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    RRC_CUDA(cudaSetDevice(h->device));
+    return launch(h, in, n, out, n, 1, 0, as_stream(stream));
+}
+
+int rrc_fftfilt_decim_run(rrc_fftfilt_t* h, const float* in, size_t n, size_t deci, size_t skip,
+                          float* out, size_t* n_out, void* stream) {
+    if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
+    if (deci == 0) return fail(RRC_ERR_INVALID, "deci must be nonzero");
+    const size_t cnt = n > skip ? (n - skip + deci - 1) / deci : 0;
+    if (n_out) *n_out = cnt;
+    if (n == 0) return RRC_OK;
+    if (!in || (!out && cnt)) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    RRC_CUDA(cudaSetDevice(h->device));
+    // deci == 1 && skip == 0 degenerates to the plain path; otherwise the store
+    // predicate in phase A' keeps y[skip + k*deci].
+    if (deci == 1 && skip == 0) return launch(h, in, n, out, n, 1, 0, as_stream(stream));
+    return launch(h, in, n, out, cnt, deci, skip, as_stream(stream));
+}
+
+int rrc_fftfilt_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, float* out_host, size_t* n_out) {
+    if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
+    // Reference count rule: whole blocks of nsamples only (src/fft_filter.rs:315-327).
+    const size_t S = ref_fft_size(h->ntaps) - h->ntaps;
+    const size_t total = (n_in / S) * S;
+    if (n_out) *n_out = total;
+    if (total == 0) return RRC_OK;
+    if (!in_host || !out_host) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    RRC_TRY(h->pipe.init(h->device));
+    const size_t chunk = PIPE_CHUNK_SAMPLES;
+    RRC_TRY(h->pipe.reserve(std::min(chunk, total) * sizeof(float2), std::min(chunk, total) * sizeof(float2)));
+    int i = 0;
+    for (size_t off = 0; off < total; off += chunk, ++i) {
+        const size_t n = std::min(chunk, total - off);
+        RRC_TRY(h->pipe.stage_in(i, in_host + 2 * off, n * sizeof(float2)));
+        RRC_TRY(launch(h, (const float*)h->pipe.d_in[i & 1], n, (float*)h->pipe.d_out[i & 1], n, 1, 0, h->pipe.s_comp));
+        RRC_TRY(h->pipe.drain_out(i, out_host + 2 * off, n * sizeof(float2)));
+    }
+    return h->pipe.finish();
+}
+
+}  // extern "C"

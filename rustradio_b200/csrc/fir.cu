@@ -1,0 +1,568 @@
+// fir.cu — decimating FIR for Complex<f32> and f32 streams on sm_100a.
+//
+// Replaces rustradio's Fir<T>::filter / filter_n_inplace (src/fir.rs:166-197)
+// and the compute step of FirFilter<T>::work (src/fir.rs:526-531).
+//
+//   out[i] = sum_{j<T} in[i*D + j] * h'[j],   h'[j] = taps[T-1-j]
+//
+// Kernel design (polyphase register-blocked FIR):
+//   j = q*D + p  =>  out[i] = sum_p sum_q in[(i+q)*D + p] * h'[q*D + p].
+//   For one phase p this is a NON-decimated FIR over the sub-sequence
+//   x_p[n] = in[n*D + p], so a thread that owns R consecutive outputs can
+//   slide a register window over x_p and reuse every tap for R outputs and
+//   every input for R taps (R*R MACs per R window loads + R tap loads).
+//   A CTA stages the input span of its NT*R outputs in shared memory once
+//   (coalesced global reads, HBM traffic = algorithmic bytes), padded by one
+//   element per thread segment (S = R*D elements, R even => S+1 odd) so the
+//   thread-strided window reads are bank-conflict free.  Taps live in shared
+//   memory phase-major and are read as warp-uniform broadcasts.
+//   Outputs are transposed through shared memory for coalesced stores; the
+//   fused QuadratureDemod epilogue (rtl_fm shape) reads y[i], y[i+1] there.
+//
+// Roofline: FP32-FMA bound.  MACs per output: 4*T FFMA (complex taps),
+// 2*T (complex data, real taps), T (f32).  Bytes: 8*(N_in + N_out) c32.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "pipeline.cuh"
+
+namespace rrc {
+
+constexpr int FIR_R = 8;          // outputs per thread (must be even)
+constexpr int FIR_MAX_NT = 256;
+
+struct FirArgs {
+    const void* in;
+    void* out;
+    const void* taps;             // poly: phase-major padded; generic: reversed flat
+    long long in_stride, out_stride;
+    long long need, out_n;
+    int ntaps, deci, qpad, nchunks, S, nseg;
+    float gain;
+    int translate;
+    double ratio;                 // freq / samp_rate
+    unsigned long long out_base;  // absolute index of out[0] (translate rotator)
+};
+
+__device__ __forceinline__ void mac(float2& acc, float2 h, float2 x) {
+    acc.x = fmaf(h.x, x.x, acc.x);
+    acc.x = fmaf(-h.y, x.y, acc.x);
+    acc.y = fmaf(h.x, x.y, acc.y);
+    acc.y = fmaf(h.y, x.x, acc.y);
+}
+__device__ __forceinline__ void mac(float2& acc, float h, float2 x) {
+    acc.x = fmaf(h, x.x, acc.x);
+    acc.y = fmaf(h, x.y, acc.y);
+}
+__device__ __forceinline__ void mac(float& acc, float h, float x) { acc = fmaf(h, x, acc); }
+__device__ __forceinline__ void zero(float2& v) { v = make_float2(0.f, 0.f); }
+__device__ __forceinline__ void zero(float& v) { v = 0.f; }
+
+// exp(-j*2*pi*ratio*k) evaluated from the exact f64 angle.
+__device__ __forceinline__ float2 rotator(double ratio, unsigned long long k) {
+    double r = ratio * (double)k;
+    r -= rint(r);
+    double s, c;
+    sincospi(-2.0 * r, &s, &c);
+    return make_float2((float)c, (float)s);
+}
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// FirFilter translate epilogue: y[i] *= phi_i, phi_i = exp(-j*theta*((T-1) + i*D))
+// (src/fir.rs:453-462 closed form of the :464-473 recurrence).
+__device__ __forceinline__ float2 apply_translate(const FirArgs& a, float2 y, long long gi) {
+    unsigned long long k = (unsigned long long)(a.ntaps - 1) + (a.out_base + (unsigned long long)gi) * (unsigned long long)a.deci;
+    return cmulf(y, rotator(a.ratio, k));
+}
+__device__ __forceinline__ float apply_translate(const FirArgs&, float y, long long) { return y; }
+
+__device__ __forceinline__ float demod_pair(float2 a, float2 b, float gain) {
+    // conj(a) * b, then gain * atan2(im, re)  (src/quadrature_demod.rs:71-73,106-108)
+    float re = fmaf(a.x, b.x, a.y * b.y);
+    float im = fmaf(a.x, b.y, -(a.y * b.x));
+    return gain * atan2f(im, re);
+}
+
+template <typename TT, int R>
+__device__ __forceinline__ void load_taps(const TT* tp, TT (&h)[R]);
+template <>
+__device__ __forceinline__ void load_taps<float2, FIR_R>(const float2* tp, float2 (&h)[FIR_R]) {
+#pragma unroll
+    for (int k = 0; k < FIR_R; k += 2) {
+        float4 v = *reinterpret_cast<const float4*>(tp + k);
+        h[k] = make_float2(v.x, v.y);
+        h[k + 1] = make_float2(v.z, v.w);
+    }
+}
+template <>
+__device__ __forceinline__ void load_taps<float, FIR_R>(const float* tp, float (&h)[FIR_R]) {
+#pragma unroll
+    for (int k = 0; k < FIR_R; k += 4) {
+        float4 v = *reinterpret_cast<const float4*>(tp + k);
+        h[k] = v.x; h[k + 1] = v.y; h[k + 2] = v.z; h[k + 3] = v.w;
+    }
+}
+
+// ST: sample type (float2 / float); TT: tap type; DECI1: compile-time deci == 1;
+// DEMOD: fused conj-multiply + atan2 epilogue (ST must be float2).
+template <typename ST, typename TT, bool DECI1, bool DEMOD>
+__global__ void __launch_bounds__(FIR_MAX_NT) fir_poly_kernel(const FirArgs a) {
+    constexpr int R = FIR_R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int deci = DECI1 ? 1 : a.deci;
+    const int S = DECI1 ? R : a.S;
+    const int S1 = S + 1;
+    const int NT = blockDim.x, t = threadIdx.x;
+    const int BT = NT * R;
+    const int ntap_tab = deci * a.qpad;
+    TT* s_taps = reinterpret_cast<TT*>(smem_raw);
+    ST* s_tile = reinterpret_cast<ST*>(smem_raw + (((size_t)ntap_tab * sizeof(TT) + 15) & ~(size_t)15));
+
+    const long long ob = (long long)blockIdx.x * (DEMOD ? BT - 1 : BT);
+    const ST* __restrict__ in = reinterpret_cast<const ST*>(a.in) + (long long)blockIdx.y * a.in_stride;
+
+    {   // taps -> smem (phase-major, zero padded to qpad per phase)
+        const TT* __restrict__ gt = reinterpret_cast<const TT*>(a.taps);
+        for (int i = t; i < ntap_tab; i += NT) s_taps[i] = gt[i];
+    }
+    {   // input span -> smem, one pad element after every S elements
+        const int L = a.nseg * S;
+        const long long g0 = ob * deci;
+        int seg = t / S, rem = t - seg * S;
+        const int dseg = NT / S, drem = NT - dseg * S;
+        for (int e = t; e < L; e += NT) {
+            const long long g = g0 + e;
+            ST v; zero(v);
+            if (g < a.need) v = in[g];
+            s_tile[seg * S1 + rem] = v;
+            seg += dseg; rem += drem;
+            if (rem >= S) { rem -= S; ++seg; }
+        }
+    }
+    __syncthreads();
+
+    ST acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) zero(acc[r]);
+
+    const ST* base_t = s_tile + t * S1;
+    for (int p = 0; p < deci; ++p) {
+        const ST* bp = base_t + p;
+        const TT* tp = s_taps + p * a.qpad;
+        ST w[2 * R - 1];
+#pragma unroll
+        for (int u = 0; u < R - 1; ++u) w[u] = bp[u * deci];
+        for (int c = 0; c < a.nchunks; ++c) {
+#pragma unroll
+            for (int u = R - 1; u < 2 * R - 1; ++u) w[u] = bp[u * deci + (u >= R ? 1 : 0)];
+            TT h[R];
+            load_taps<TT, R>(tp, h);
+#pragma unroll
+            for (int k = 0; k < R; ++k)
+#pragma unroll
+                for (int r = 0; r < R; ++r) mac(acc[r], h[k], w[r + k]);
+#pragma unroll
+            for (int u = 0; u < R - 1; ++u) w[u] = w[u + R];
+            bp += S1;
+            tp += R;
+        }
+    }
+
+    __syncthreads();                 // everyone is done with the input tile
+    ST* s_out = s_tile;              // reuse: BT + NT entries <= tile size
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        ST y = acc[r];
+        if (a.translate) y = apply_translate(a, y, ob + (long long)t * R + r);
+        s_out[t * (R + 1) + r] = y;
+    }
+    __syncthreads();
+
+    if constexpr (!DEMOD) {
+        ST* __restrict__ out = reinterpret_cast<ST*>(a.out) + (long long)blockIdx.y * a.out_stride;
+        for (int o = t; o < BT; o += NT) {
+            const long long gi = ob + o;
+            if (gi < a.out_n) out[gi] = s_out[o + o / R];
+        }
+    } else {
+        float* __restrict__ out = reinterpret_cast<float*>(a.out) + (long long)blockIdx.y * a.out_stride;
+        for (int o = t; o < BT - 1; o += NT) {
+            const long long gi = ob + o;
+            if (gi < a.out_n - 1) {
+                const float2 ya = s_out[o + o / R];
+                const float2 yb = s_out[(o + 1) + (o + 1) / R];
+                out[gi] = demod_pair(ya, yb, a.gain);
+            }
+        }
+    }
+}
+
+// Fallback for geometries whose tile does not fit shared memory (very large
+// deci*R or tap tables): one thread per output, taps and inputs through L1/L2.
+template <typename ST, typename TT>
+__global__ void fir_generic_kernel(const FirArgs a) {
+    const ST* __restrict__ in = reinterpret_cast<const ST*>(a.in) + (long long)blockIdx.y * a.in_stride;
+    ST* __restrict__ out = reinterpret_cast<ST*>(a.out) + (long long)blockIdx.y * a.out_stride;
+    const TT* __restrict__ taps = reinterpret_cast<const TT*>(a.taps);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.out_n; i += stride) {
+        const ST* x = in + i * a.deci;
+        ST acc; zero(acc);
+        for (int j = 0; j < a.ntaps; ++j) mac(acc, taps[j], x[j]);
+        if (a.translate) acc = apply_translate(a, acc, i);
+        out[i] = acc;
+    }
+}
+
+__global__ void quad_demod_kernel(const float2* __restrict__ in, long long in_stride, long long n_in,
+                                  float gain, float* __restrict__ out, long long out_stride) {
+    in += (long long)blockIdx.y * in_stride;
+    out += (long long)blockIdx.y * out_stride;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t + 1 < n_in; t += stride)
+        out[t] = demod_pair(in[t], in[t + 1], gain);
+}
+
+}  // namespace rrc
+
+using namespace rrc;
+
+struct rrc_fir {
+    int device = 0;
+    bool cplx = false;        // samples are Complex<f32>
+    bool real_taps = false;   // tap table holds floats (f32 FIR or c32 real-tap fast path)
+    unsigned flags = 0;
+    size_t ntaps = 0, deci = 1;
+    std::vector<float> taps_host;   // caller order, interleaved if cplx
+    void* taps_poly = nullptr;
+    void* taps_rev = nullptr;
+    int qpad = 0, nchunks = 0, nt = 0;
+    size_t smem = 0;
+    bool use_poly = false;
+    bool translate = false;
+    double ratio = 0.0;
+    unsigned long long out_counter = 0;
+    Pipe pipe;
+};
+
+namespace {
+
+size_t tap_elem(const rrc_fir* h) { return h->real_taps ? sizeof(float) : sizeof(float2); }
+size_t samp_elem(const rrc_fir* h) { return h->cplx ? sizeof(float2) : sizeof(float); }
+
+// (Re)build the device tap tables from taps_host and pick the launch geometry.
+int upload_taps(rrc_fir* h) {
+    const size_t T = h->ntaps, D = h->deci;
+    RRC_CUDA(cudaSetDevice(h->device));
+    if (h->taps_poly) { cudaFree(h->taps_poly); h->taps_poly = nullptr; }
+    if (h->taps_rev) { cudaFree(h->taps_rev); h->taps_rev = nullptr; }
+
+    bool all_real = true;
+    if (h->cplx)
+        for (size_t k = 0; k < T; ++k)
+            if (h->taps_host[2 * k + 1] != 0.0f) { all_real = false; break; }
+    h->real_taps = !h->cplx || (all_real && !(h->flags & RRC_FIR_NO_REAL_TAP_FASTPATH));
+    const size_t te = h->real_taps ? 1 : 2;   // floats per tap in the device tables
+
+    const size_t Q = (T + D - 1) / D;
+    h->qpad = (int)((Q + FIR_R - 1) / FIR_R * FIR_R);
+    h->nchunks = h->qpad / FIR_R;
+
+    auto tap_at = [&](size_t j, float* dst) {   // h'[j] = taps[T-1-j]
+        const size_t k = T - 1 - j;
+        if (h->cplx) {
+            dst[0] = h->taps_host[2 * k];
+            if (te == 2) dst[1] = h->taps_host[2 * k + 1];
+        } else {
+            dst[0] = h->taps_host[k];
+        }
+    };
+    std::vector<float> rev(T * te), poly((size_t)D * h->qpad * te, 0.0f);
+    for (size_t j = 0; j < T; ++j) {
+        tap_at(j, &rev[j * te]);
+        const size_t q = j / D, p = j % D;
+        tap_at(j, &poly[(p * h->qpad + q) * te]);
+    }
+    RRC_CUDA(cudaMalloc(&h->taps_rev, rev.size() * sizeof(float)));
+    RRC_CUDA(cudaMemcpy(h->taps_rev, rev.data(), rev.size() * sizeof(float), cudaMemcpyHostToDevice));
+    RRC_CUDA(cudaMalloc(&h->taps_poly, poly.size() * sizeof(float)));
+    RRC_CUDA(cudaMemcpy(h->taps_poly, poly.data(), poly.size() * sizeof(float), cudaMemcpyHostToDevice));
+
+    // Geometry: largest CTA whose tile fits; prefer <= 100 KB so two CTAs share an SM.
+    h->use_poly = false;
+    if (!(h->flags & RRC_FIR_FORCE_GENERIC) && D <= (1u << 20)) {
+        const size_t S1 = FIR_R * D + 1;
+        const size_t tap_bytes = ((size_t)D * h->qpad * tap_elem(h) + 15) & ~(size_t)15;
+        const size_t limit_hi = (size_t)max_smem_optin(h->device);
+        const size_t limits[2] = {100 * 1024, limit_hi};
+        for (int pass = 0; pass < 2 && !h->use_poly; ++pass) {
+            for (int nt = FIR_MAX_NT; nt >= 32; nt >>= 1) {
+                const size_t bytes = tap_bytes + (size_t)(nt + h->nchunks) * S1 * samp_elem(h);
+                if (bytes <= limits[pass]) {
+                    h->nt = nt; h->smem = bytes; h->use_poly = true;
+                    break;
+                }
+            }
+        }
+    }
+    return RRC_OK;
+}
+
+template <typename ST, typename TT, bool DEMOD>
+int launch_poly(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
+    if (h->deci == 1) {
+        auto k = fir_poly_kernel<ST, TT, true, DEMOD>;
+        RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        k<<<grid, h->nt, h->smem, st>>>(a);
+    } else {
+        auto k = fir_poly_kernel<ST, TT, false, DEMOD>;
+        RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        k<<<grid, h->nt, h->smem, st>>>(a);
+    }
+    RRC_CHECK_LAUNCH();
+    count_launch();
+    return RRC_OK;
+}
+
+int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* out, size_t out_stride,
+             size_t out_n, size_t nchan, bool demod, float gain, void* stream) {
+    if (!h) return fail(RRC_ERR_INVALID, "fir handle is NULL");
+    if (out_n == 0 || nchan == 0) return RRC_OK;
+    if (!in || !out) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    if (need < (out_n - 1) * h->deci + h->ntaps)
+        return fail(RRC_ERR_INVALID, "fir: need %zu < (out_n-1)*deci+ntaps = %zu", need, (out_n - 1) * h->deci + h->ntaps);
+    if (nchan > 65535) return fail(RRC_ERR_INVALID, "fir: nchan %zu > 65535", nchan);
+    if (demod && !h->cplx) return fail(RRC_ERR_INVALID, "fused demod needs a c32 FIR");
+    RRC_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = as_stream(stream);
+
+    FirArgs a{};
+    a.in = in; a.out = out;
+    a.in_stride = (long long)in_stride; a.out_stride = (long long)out_stride;
+    a.need = (long long)need; a.out_n = (long long)out_n;
+    a.ntaps = (int)h->ntaps; a.deci = (int)h->deci;
+    a.qpad = h->qpad; a.nchunks = h->nchunks;
+    a.S = FIR_R * (int)h->deci; a.nseg = h->nt + h->nchunks;
+    a.gain = gain;
+    a.translate = h->translate ? 1 : 0;
+    a.ratio = h->ratio;
+    a.out_base = h->out_counter;
+
+    if (h->use_poly) {
+        a.taps = h->taps_poly;
+        const size_t bt = (size_t)h->nt * FIR_R;
+        const size_t per = demod ? bt - 1 : bt;
+        const size_t work = demod ? (out_n > 1 ? out_n - 1 : 0) : out_n;
+        if (work == 0) return RRC_OK;
+        dim3 grid((unsigned)((work + per - 1) / per), (unsigned)nchan);
+        int s;
+        if (h->cplx && !h->real_taps)
+            s = demod ? launch_poly<float2, float2, true>(h, a, grid, st) : launch_poly<float2, float2, false>(h, a, grid, st);
+        else if (h->cplx)
+            s = demod ? launch_poly<float2, float, true>(h, a, grid, st) : launch_poly<float2, float, false>(h, a, grid, st);
+        else
+            s = launch_poly<float, float, false>(h, a, grid, st);
+        RRC_TRY(s);
+    } else {
+        a.taps = h->taps_rev;
+        void* fir_out = out;
+        size_t fir_stride = out_stride;
+        float2* tmp = nullptr;
+        if (demod) {   // unfused fallback: FIR into scratch, then demod
+            RRC_CUDA(cudaMallocAsync((void**)&tmp, sizeof(float2) * out_n * nchan, st));
+            fir_out = tmp; fir_stride = out_n;
+            a.out = tmp; a.out_stride = (long long)out_n;
+        }
+        unsigned gx = (unsigned)std::min<size_t>((out_n + 255) / 256, (size_t)sm_count(h->device) * 8);
+        dim3 grid(gx, (unsigned)nchan);
+        if (h->cplx && !h->real_taps) fir_generic_kernel<float2, float2><<<grid, 256, 0, st>>>(a);
+        else if (h->cplx) fir_generic_kernel<float2, float><<<grid, 256, 0, st>>>(a);
+        else fir_generic_kernel<float, float><<<grid, 256, 0, st>>>(a);
+        RRC_CHECK_LAUNCH();
+        count_launch();
+        if (demod) {
+            if (out_n > 1) {
+                unsigned dx = (unsigned)std::min<size_t>((out_n + 255) / 256, (size_t)sm_count(h->device) * 8);
+                quad_demod_kernel<<<dim3(dx, (unsigned)nchan), 256, 0, st>>>((const float2*)fir_out, (long long)fir_stride,
+                                                                           (long long)out_n, gain, (float*)out, (long long)out_stride);
+                RRC_CHECK_LAUNCH();
+                count_launch();
+            }
+            RRC_CUDA(cudaFreeAsync(tmp, st));
+        }
+    }
+    if (h->translate) h->out_counter += out_n;
+    return RRC_OK;
+}
+
+int create_impl(int device, const float* taps, size_t ntaps, size_t deci, unsigned flags, bool cplx, rrc_fir_t** out) {
+    if (!out) return fail(RRC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!taps || ntaps == 0) return fail(RRC_ERR_INVALID, "FirFilter needs at least one tap (src/fir.rs:158,372)");
+    if (deci == 0) return fail(RRC_ERR_INVALID, "FirFilter deci must be nonzero (src/fir.rs:319)");
+    if (ntaps > (1u << 30) || deci > (1u << 30)) return fail(RRC_ERR_INVALID, "ntaps/deci too large");
+    auto* h = new rrc_fir();
+    h->device = device; h->cplx = cplx; h->flags = flags; h->ntaps = ntaps; h->deci = deci;
+    h->taps_host.assign(taps, taps + ntaps * (cplx ? 2 : 1));
+    int s = upload_taps(h);
+    if (s != RRC_OK) { rrc_fir_destroy(h); return s; }
+    *out = h;
+    return RRC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rrc_fir_c32_create(int device, const float* taps, size_t ntaps, size_t deci, unsigned flags, rrc_fir_t** out) {
+    return create_impl(device, taps, ntaps, deci, flags, true, out);
+}
+int rrc_fir_f32_create(int device, const float* taps, size_t ntaps, size_t deci, unsigned flags, rrc_fir_t** out) {
+    return create_impl(device, taps, ntaps, deci, flags, false, out);
+}
+
+int rrc_fir_set_translate(rrc_fir_t* h, float samp_rate, float freq) {
+    if (!h) return fail(RRC_ERR_INVALID, "fir handle is NULL");
+    if (!h->cplx) return fail(RRC_ERR_INVALID, "translate() exists only on FirFilterBuilder<Complex> (src/fir.rs:476)");
+    if (!(samp_rate > 0.0f)) return fail(RRC_ERR_INVALID, "samp_rate must be > 0 (src/fir.rs:435)");
+    if (h->translate) return fail(RRC_ERR_STATE, "translate already set");
+    if (freq == 0.0f) return RRC_OK;   // src/fir.rs:438-440
+    // Pre-rotate taps by the same f32 recurrence as src/fir.rs:441-449.
+    const double input_step = 2.0 * M_PI * (double)freq / (double)samp_rate;
+    const float sr = (float)std::cos(input_step), si = (float)std::sin(input_step);
+    float pr = 1.0f, pi = 0.0f;
+    for (size_t k = 0; k < h->ntaps; ++k) {
+        float tr = h->taps_host[2 * k], ti = h->taps_host[2 * k + 1];
+        h->taps_host[2 * k] = tr * pr - ti * pi;
+        h->taps_host[2 * k + 1] = tr * pi + ti * pr;
+        float nr = pr * sr - pi * si, ni = pr * si + pi * sr;
+        pr = nr; pi = ni;
+    }
+    h->translate = true;
+    h->ratio = (double)freq / (double)samp_rate;
+    h->out_counter = 0;
+    return upload_taps(h);
+}
+
+int rrc_fir_destroy(rrc_fir_t* h) {
+    if (!h) return RRC_OK;
+    cudaSetDevice(h->device);
+    if (h->taps_poly) cudaFree(h->taps_poly);
+    if (h->taps_rev) cudaFree(h->taps_rev);
+    h->pipe.destroy();
+    delete h;
+    return RRC_OK;
+}
+int rrc_fir_ntaps(const rrc_fir_t* h, size_t* n) {
+    if (!h || !n) return fail(RRC_ERR_INVALID, "NULL argument");
+    *n = h->ntaps;
+    return RRC_OK;
+}
+int rrc_fir_deci(const rrc_fir_t* h, size_t* d) {
+    if (!h || !d) return fail(RRC_ERR_INVALID, "NULL argument");
+    *d = h->deci;
+    return RRC_OK;
+}
+int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes) {
+    if (!h || !yes) return fail(RRC_ERR_INVALID, "NULL argument");
+    *yes = (h->cplx && h->real_taps) ? 1 : 0;
+    return RRC_OK;
+}
+int rrc_fir_reset(rrc_fir_t* h) {
+    if (!h) return fail(RRC_ERR_INVALID, "fir handle is NULL");
+    h->out_counter = 0;
+    return RRC_OK;
+}
+
+int rrc_fir_plan(size_t ntaps, size_t deci, size_t in_len, size_t out_free,
+                 size_t* consume, size_t* need, size_t* out_n, size_t* wait_need, int* wait_on_output) {
+    if (!consume || !need || !out_n || !wait_need || !wait_on_output) return fail(RRC_ERR_INVALID, "NULL argument");
+    if (ntaps == 0 || deci == 0) return fail(RRC_ERR_INVALID, "ntaps/deci must be nonzero");
+    *consume = *need = *out_n = *wait_need = 0;
+    *wait_on_output = 0;
+    const size_t absolute_minimum = ntaps + deci - 1;                 // src/fir.rs:497
+    if (in_len < absolute_minimum) { *wait_need = absolute_minimum; return RRC_OK; }   // :498-500
+    size_t n = deci * ((in_len - ntaps + 1) / deci);                  // :502
+    if (out_free < 1) { *wait_need = 1; *wait_on_output = 1; return RRC_OK; }          // :511-515
+    n = std::min(n, out_free * deci);                                 // :518
+    *consume = n;
+    *out_n = n / deci;                                                // :525
+    *need = n + ntaps - 1;                                            // :507
+    return RRC_OK;
+}
+
+int rrc_fir_run(rrc_fir_t* h, const void* in, size_t need, void* out, size_t out_n, void* stream) {
+    return run_impl(h, in, 0, need, out, 0, out_n, 1, false, 0.f, stream);
+}
+int rrc_fir_run_batch(rrc_fir_t* h, const void* in, size_t in_stride, size_t need, void* out, size_t out_stride,
+                      size_t out_n, size_t nchan, void* stream) {
+    return run_impl(h, in, in_stride, need, out, out_stride, out_n, nchan, false, 0.f, stream);
+}
+int rrc_fir_c32_demod_run_batch(rrc_fir_t* h, const void* in, size_t in_stride, size_t need, float gain,
+                                float* out, size_t out_stride, size_t out_n, size_t nchan, void* stream) {
+    return run_impl(h, in, in_stride, need, out, out_stride, out_n, nchan, true, gain, stream);
+}
+
+int rrc_fir_run_host(rrc_fir_t* h, const void* in_host, size_t n_in, void* out_host, size_t* n_out) {
+    if (!h) return fail(RRC_ERR_INVALID, "fir handle is NULL");
+    const size_t T = h->ntaps, D = h->deci, es = samp_elem(h);
+    const size_t total = n_in < T + D - 1 ? 0 : (n_in - T + 1) / D;     // src/fir.rs:496-525 to exhaustion
+    if (n_out) *n_out = total;
+    if (total == 0) return RRC_OK;
+    if (!in_host || !out_host) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    RRC_TRY(h->pipe.init(h->device));
+    const size_t chunk_out = std::max<size_t>(1, PIPE_CHUNK_SAMPLES / D);
+    const size_t max_out = std::min(chunk_out, total);
+    RRC_TRY(h->pipe.reserve(((max_out - 1) * D + T) * es, max_out * es));
+    int i = 0;
+    for (size_t o = 0; o < total; o += chunk_out, ++i) {
+        const size_t no = std::min(chunk_out, total - o);
+        const size_t need = (no - 1) * D + T;                              // halo = ntaps-1 re-copied per chunk
+        RRC_TRY(h->pipe.stage_in(i, (const char*)in_host + o * D * es, need * es));
+        RRC_TRY(run_impl(h, h->pipe.d_in[i & 1], 0, need, h->pipe.d_out[i & 1], 0, no, 1, false, 0.f, h->pipe.s_comp));
+        RRC_TRY(h->pipe.drain_out(i, (char*)out_host + o * es, no * es));
+    }
+    return h->pipe.finish();
+}
+
+int rrc_quad_demod_run_host(int device, const float* in_host, size_t n_in, float gain, float* out_host) {
+    if (n_in < 2) return RRC_OK;
+    if (!in_host || !out_host) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    RRC_CUDA(cudaSetDevice(device));
+    Pipe pipe;
+    RRC_TRY(pipe.init(device));
+    const size_t chunk = PIPE_CHUNK_SAMPLES;
+    int s = pipe.reserve((std::min(chunk, n_in - 1) + 1) * sizeof(float2), std::min(chunk, n_in - 1) * sizeof(float));
+    int i = 0;
+    for (size_t o = 0; s == RRC_OK && o < n_in - 1; o += chunk, ++i) {
+        const size_t no = std::min(chunk, n_in - 1 - o);
+        s = pipe.stage_in(i, in_host + 2 * o, (no + 1) * sizeof(float2));
+        if (s == RRC_OK) s = rrc_quad_demod_run(device, (const float*)pipe.d_in[i & 1], no + 1, gain, (float*)pipe.d_out[i & 1], pipe.s_comp);
+        if (s == RRC_OK) s = pipe.drain_out(i, out_host + o, no * sizeof(float));
+    }
+    if (s == RRC_OK) s = pipe.finish();
+    pipe.destroy();
+    return s;
+}
+
+int rrc_quad_demod_run_batch(int device, const float* in, size_t in_stride, size_t n_in, float gain,
+                             float* out, size_t out_stride, size_t nchan, void* stream) {
+    if (n_in < 2 || nchan == 0) return RRC_OK;
+    if (!in || !out) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    if (nchan > 65535) return fail(RRC_ERR_INVALID, "nchan > 65535");
+    RRC_CUDA(cudaSetDevice(device));
+    unsigned gx = (unsigned)std::min<size_t>((n_in + 255) / 256, (size_t)sm_count(device) * 16);
+    quad_demod_kernel<<<dim3(gx, (unsigned)nchan), 256, 0, as_stream(stream)>>>(
+        (const float2*)in, (long long)in_stride, (long long)n_in, gain, out, (long long)out_stride);
+    RRC_CHECK_LAUNCH();
+    count_launch();
+    return RRC_OK;
+}
+int rrc_quad_demod_run(int device, const float* in, size_t n_in, float gain, float* out, void* stream) {
+    return rrc_quad_demod_run_batch(device, in, 0, n_in, gain, out, 0, 1, stream);
+}
+
+}  // extern "C"

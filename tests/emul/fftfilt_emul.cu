@@ -1,0 +1,36 @@
+// CPU emulation of the FftFilter CUDA kernel's five phases (fftfilt_core.cuh):
+// every "thread" of the 512-thread CTA is run in a loop, phase by phase, with
+// a plain array standing in for shared memory.  Lets the index math, swizzle
+// and twiddle logic be checked against the oracle without a GPU.
+// Built by tests/test_emul.py with `nvcc -x cu` (host code only).
+#include <cstring>
+#include <vector>
+
+#include "../../rustradio_b200/csrc/fftfilt_tables.hpp"
+
+using namespace rrc::fftk;
+
+extern "C" int emul_fftfilt(const float* taps, long long ntaps, const float* in, long long n,
+                            const float* hist /* (ntaps-1) c32 or NULL = zeros */, float* out,
+                            long long deci, long long skip, long long n_out) {
+    std::vector<float2> Hp, tw1, tw2;
+    build_tables(taps, (size_t)ntaps, Hp, tw1, tw2);
+    const int T1 = (int)ntaps - 1;
+    std::vector<float2> h(T1 > 0 ? T1 : 1, make_float2(0.f, 0.f));
+    if (hist && T1 > 0) memcpy(h.data(), hist, sizeof(float2) * T1);
+    BlockIO io;
+    io.in = reinterpret_cast<const float2*>(in);
+    io.hist = h.data();
+    io.out = reinterpret_cast<float2*>(out);
+    io.n_in = n; io.n_out = n_out; io.T1 = T1; io.V = N - T1; io.deci = (int)deci; io.skip = skip;
+    std::vector<float2> sm(N);
+    const long long nblocks = (n + io.V - 1) / io.V;
+    for (long long blk = 0; blk < nblocks; ++blk) {
+        for (int t = 0; t < NT; ++t) phase_a(t, blk, io, tw1.data(), sm.data());
+        for (int t = 0; t < NT; ++t) phase_b(t, tw2.data(), sm.data());
+        for (int t = 0; t < NT; ++t) phase_c(t, Hp.data(), sm.data());
+        for (int t = 0; t < NT; ++t) phase_bi(t, tw2.data(), sm.data());
+        for (int t = 0; t < NT; ++t) phase_ai(t, blk, io, tw1.data(), sm.data());
+    }
+    return 0;
+}

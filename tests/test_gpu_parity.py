@@ -1,0 +1,345 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star): FIR / FftFilter rel-RMS <= 1e-5 against the
+f64 truth of the same f32 inputs; resampler bit-exact; demod <= 1e-4 rad;
+sample counts exactly the reference's.  The bit-faithful f32 oracle error is
+printed next to ours as a second opinion.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL_RMS_BAR = 1e-5
+DEMOD_BAR = 1e-4
+
+
+@pytest.fixture(scope="module")
+def R():
+    import rustradio_b200 as R
+    assert R.device_count() >= 1
+    return R
+
+
+def cplx_taps(n, seed=1):
+    r = np.random.default_rng(seed)
+    return ((r.standard_normal(n) + 1j * r.standard_normal(n)) / np.sqrt(n)).astype(np.complex64)
+
+
+# ------------------------------------------------------------------ FIR ---
+def test_fir_kat_test_complex(R):
+    """reference src/fir.rs:921-950"""
+    x = np.array([1, 2, 3 + .2j, 4.1, 5, 6 + .2j], np.complex64)
+    taps = np.array([.1, 1, .2j], np.complex64)
+    assert np.allclose(R.Fir(taps).filter(x), [2.3 + .22j, 3.41 + .6j, 4.56 + .6j, 5.6 + .84j], atol=1e-6)
+    assert np.allclose(R.Fir(taps, deci=2).filter(x), [2.3 + .22j, 4.56 + .6j], atol=1e-6)
+
+
+@pytest.mark.parametrize("ntaps,deci,n", [
+    (1, 1, 1000), (2, 1, 5000), (3, 2, 4099), (64, 1, 100_000), (247, 1, 512_000), (255, 10, 240_000),
+    (33, 7, 50_001), (100, 100, 30_000), (5, 64, 100_000), (1025, 3, 70_000), (64, 1, 63), (64, 2, 64)])
+@pytest.mark.parametrize("kind", ["c32_ctaps", "c32_rtaps", "f32"])
+def test_fir_matches_oracle(R, ntaps, deci, n, kind):
+    if kind == "f32":
+        x = O.synth_f32(11, 0, n)
+        taps = np.random.default_rng(ntaps).standard_normal(ntaps).astype(np.float32) / np.sqrt(ntaps)
+    else:
+        x = O.synth_c32(12, 0, n)
+        taps = cplx_taps(ntaps, ntaps) if kind == "c32_ctaps" else O.low_pass_n(1.0, 0.1, ntaps).astype(np.complex64)
+    f = R.Fir(taps, deci=deci)
+    assert f.uses_real_taps == (kind == "c32_rtaps")
+    y = f.filter(x)
+    truth = O.fir(x, taps, deci, f64=True)
+    assert len(y) == len(truth) == O.fir_out_count(n, ntaps, deci)
+    if len(y):
+        e = O.rel_rms(y, truth)
+        e_ref = O.rel_rms(O.fir(x, taps, deci), truth)
+        print(f"fir {kind} T={ntaps} D={deci}: gpu {e:.2e}  f32-oracle {e_ref:.2e}")
+        assert e <= REL_RMS_BAR
+
+
+@pytest.mark.parametrize("flags_name", ["RRC_FIR_FORCE_GENERIC", "RRC_FIR_NO_REAL_TAP_FASTPATH"])
+def test_fir_alternate_paths(R, flags_name):
+    x = O.synth_c32(13, 0, 20_000)
+    taps = O.low_pass_n(1.0, 0.1, 101).astype(np.complex64)
+    f = R.Fir(taps, deci=3, flags=getattr(R, flags_name))
+    assert not (flags_name == "RRC_FIR_NO_REAL_TAP_FASTPATH" and f.uses_real_taps)
+    assert O.rel_rms(f.filter(x), O.fir(x, taps, 3, f64=True)) <= REL_RMS_BAR
+
+
+def test_fir_huge_deci_falls_back(R):
+    """deci so large that the smem tile cannot hold R*deci samples per thread."""
+    x = O.synth_c32(14, 0, 400_000)
+    taps = cplx_taps(300, 3)
+    y = R.Fir(taps, deci=5000).filter(x)
+    truth = O.fir(x, taps, 5000, f64=True)
+    assert len(y) == len(truth) and O.rel_rms(y, truth) <= REL_RMS_BAR
+
+
+def test_fir_batch_and_fused_demod(R):
+    """rtl_fm shape: nchan channels, 255-tap decimate-by-10 FIR, then QuadratureDemod."""
+    nchan, n, ntaps, deci = 7, 30_000, 255, 10
+    taps = O.low_pass_n(2.4e6, 100e3, ntaps).astype(np.complex64)
+    xs = np.stack([O.synth_c32(100 + c, 0, n) * 0.3 + np.exp(2j * np.pi * 0.01 * (c + 1) * np.arange(n)).astype(np.complex64)
+                   for c in range(nchan)])
+    f = R.Fir(taps, deci=deci)
+    out_n = f.out_count(n)
+    need = (out_n - 1) * deci + ntaps
+    din = R.DeviceBuffer.from_numpy(xs)
+    dy = R.DeviceBuffer(nchan * out_n * 8)
+    f.run_batch(din, n, need, dy, out_n, out_n, nchan)
+    y = dy.download(np.complex64, nchan * out_n).reshape(nchan, out_n)
+    dd = R.DeviceBuffer(nchan * (out_n - 1) * 4)
+    f.demod_run_batch(din, n, need, 1.5, dd, out_n - 1, out_n, nchan)
+    d = dd.download(np.float32, nchan * (out_n - 1)).reshape(nchan, out_n - 1)
+    for c in range(nchan):
+        truth = O.fir(xs[c], taps, deci, f64=True)
+        assert O.rel_rms(y[c], truth) <= REL_RMS_BAR
+        # fused == FirFilter -> QuadratureDemod chain (oracle demod of the f64-truth FIR output)
+        want = 1.5 * np.angle(truth[1:] * np.conj(truth[:-1]))
+        assert O.max_angle_err(d[c] / 1.5, want / 1.5) <= DEMOD_BAR
+
+
+def test_fir_translate_matches_reference_kat(R):
+    """reference src/fir.rs:744-789 (translate + deci 3 == manual mix then filter)."""
+    inp = np.array([complex(i, i * 0.25) for i in range(32)], np.complex64)
+    taps = np.array([.5 - .1j, 1 + .2j, -.25 + .05j, .125 - .3j], np.complex64)
+    f = R.Fir(taps, deci=3)
+    f.set_translate(8.0, 2.0)
+    got = f.filter(inp)
+    rt, ph, st = O.fir_new_translator(taps, 8.0, 2.0, 3)
+    want = O.fir(inp, rt, 3)
+    O.fir_translate_output(want, ph, st)
+    assert len(got) == len(want) == 9
+    assert np.max(np.abs(got - want)) < 1e-3       # the reference's own tolerance
+    # longer run: the exact-phase rotator stays within the f32 recurrence's early behaviour
+    x = O.synth_c32(15, 0, 4096)
+    t2 = O.low_pass_complex(1024.0, 20.0, 10.0)
+    f2 = R.Fir(t2)
+    f2.set_translate(1024.0, 60.0)
+    got2 = f2.filter(x)
+    rt2, ph2, st2 = O.fir_new_translator(t2, 1024.0, 60.0, 1)
+    want2 = O.fir(x, rt2, 1)
+    O.fir_translate_output(want2, ph2, st2)
+    assert O.rel_rms(got2, want2) < 1e-4
+
+
+def test_fir_run_host_count_rule(R):
+    x = O.synth_c32(16, 0, 300_000)
+    taps = O.low_pass_n(1.0, 0.1, 64).astype(np.complex64)
+    y = R.Fir(taps, deci=4).run_host(x)
+    truth = O.fir(x, taps, 4, f64=True)
+    assert len(y) == len(truth) and O.rel_rms(y, truth) <= REL_RMS_BAR
+    assert len(R.Fir(taps, deci=4).run_host(x[:66])) == 0      # < ntaps + deci - 1 -> WaitForStream, nothing out
+
+
+# ----------------------------------------------------------- FFT filter ---
+@pytest.mark.parametrize("ntaps,n", [(1, 5000), (2, 40_000), (193, 8000), (4097, 100_000), (8193, 50_000), (12289, 30_000), (64, 16384 * 3 + 17)])
+def test_fftfilt_matches_f64_convolution(R, ntaps, n):
+    taps = (O.low_pass_n(1.0, 0.05, ntaps).astype(np.complex64) * (1 + 0.5j)) if ntaps > 2 else cplx_taps(ntaps)
+    x = O.synth_c32(21, 0, n)
+    y = R.FftFilt(taps).filter(x)
+    truth = O.conv_full_f64_fft(x, taps, n)
+    e = O.rel_rms(y, truth)
+    S = O.calc_fft_size(ntaps) - ntaps
+    e_ref = O.rel_rms(O.fftfilt(x, taps), truth[:(n // S) * S]) if n >= S else float("nan")
+    print(f"fftfilt T={ntaps}: gpu {e:.2e}  f32-oracle(overlap-add) {e_ref:.2e}")
+    assert e <= REL_RMS_BAR
+
+
+def test_fftfilt_streaming_state_and_reset(R):
+    taps = O.low_pass_n(1.0, 0.1, 301).astype(np.complex64)
+    x = O.synth_c32(22, 0, 60_000)
+    f = R.FftFilt(taps)
+    cuts = [0, 1, 150, 12_345, 12_400, 45_000, 60_000]
+    y = np.concatenate([f.filter(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    truth = O.conv_full_f64_fft(x, taps, len(x))
+    assert O.rel_rms(y, truth) <= REL_RMS_BAR
+    f.reset()
+    assert O.rel_rms(f.filter(x[:5000]), truth[:5000]) <= REL_RMS_BAR
+
+
+def test_fftfilt_run_host_reference_count_rule(R):
+    """floor(N/nsamples)*nsamples outputs, trailing partial block never flushed (src/fft_filter.rs:315-327)."""
+    taps = O.low_pass_complex(8000.0, 1000.0, 100.0)        # 193 taps -> fft 512, block 319
+    sig, _ = O.signal_source_complex(8000.0, 3000.0, 1.0, 8000)
+    f = R.FftFilt(taps)
+    assert (f.ref_fft_size, f.nsamples) == (512, 319)
+    y = f.run_host(sig)
+    assert len(y) == 7975 == O.fftfilt_out_count(8000, 193)
+    # reference test filter_a_signal (src/fft_filter.rs:502-549): stop band < 2e-4 after the transient
+    assert np.max(np.abs(y[193:])) < 2e-4
+    assert O.rel_rms(y, O.conv_full_f64(sig, taps, 7975)) <= REL_RMS_BAR
+
+
+def test_fftfilt_fused_decimation(R):
+    taps = O.low_pass_n(1.0, 0.05, 1025).astype(np.complex64)
+    x = O.synth_c32(23, 0, 90_000)
+    truth = O.conv_full_f64_fft(x, taps, len(x))
+    for deci, skip in ((8, 0), (8, 5), (3, 2), (1, 4)):
+        f = R.FftFilt(taps)
+        din = R.DeviceBuffer.from_numpy(x)
+        dout = R.DeviceBuffer(len(x) * 8)
+        n = f.decim_run(din, len(x), deci, skip, dout)
+        want = truth[skip::deci]
+        assert n == len(want)
+        assert O.rel_rms(dout.download(np.complex64, n), want) <= REL_RMS_BAR
+
+
+def test_fftfilt_too_many_taps_is_an_error_not_a_fallback(R):
+    with pytest.raises(R.RrcError):
+        R.FftFilt(np.ones(20_000, np.complex64))
+
+
+# ------------------------------------------------------------ resampler ---
+@pytest.mark.parametrize("interp,deci", [(1, 1), (1, 2), (2, 1), (2, 3), (3, 2), (25, 64), (25, 128), (147, 160),
+                                          (200000, 1024000), (1, 8), (160, 147), (7, 1000), (1000, 7)])
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint32, np.complex64])
+def test_resampler_bit_exact(R, interp, deci, dtype):
+    n = 100_003
+    if dtype == np.complex64:
+        x = O.synth_c32(31, 0, n)
+    else:
+        x = (np.arange(n) * 2654435761 % (np.iinfo(dtype).max + 1)).astype(dtype)
+    want = O.resample(x, interp, deci)
+    r = R.Resampler(x.dtype.itemsize, interp, deci)
+    w, consumed, got = r.work(x, len(want) + 10)
+    assert w == 0 and consumed == n                     # WaitForStream(src, 1)
+    assert got.tobytes() == want.tobytes()
+    assert len(got) == O.resample_out_count(n, interp, deci)
+
+
+def test_resampler_kat_example64(R):
+    """reference src/rational_resampler.rs:248-262"""
+    r = R.Resampler(4, 25, 64)
+    _, _, got = r.work(np.arange(50, dtype=np.uint32), 100)
+    assert list(got) == [0, 2, 5, 7, 10, 12, 15, 17, 20, 23, 25, 28, 30, 33, 35, 38, 40, 43, 46, 48]
+
+
+def test_resampler_work_sequence_matches_oracle_state(R):
+    """Random input/output window sizes: consumed/produced/wait/counter/pending equal the restated work()."""
+    rng = np.random.default_rng(5)
+    for interp, deci in ((3, 1), (7, 3), (147, 160), (1, 9), (11, 2)):
+        x = (np.arange(40_000) * 7919 % 65521).astype(np.uint32)
+        g, o = R.Resampler(4, interp, deci), O.Resampler(4, interp, deci)
+        pos = 0
+        outs_g, outs_o = [], []
+        for _ in range(400):
+            n_in = int(rng.integers(0, 300))
+            cap = int(rng.integers(0, 200))
+            win = x[pos:pos + n_in]
+            ro, co, yo = o.work(win, cap)
+            wg, cg, yg = g.work(win, cap)
+            assert (cg, len(yg)) == (co, len(yo))
+            assert yg.tobytes() == yo.tobytes()
+            assert wg == (1 if ro == O.Resampler.WAIT_DST else 0)
+            gi, gd, gc, gp = g.state()
+            assert gp == o.has_pending
+            assert gc == o.counter
+            pos += cg
+            outs_g.append(yg)
+        assert pos > 0
+
+
+def test_resampler_interpolation_survives_full_output_buffer(R):
+    """reference src/rational_resampler.rs:278-299"""
+    cap = 4_096_000 // 4
+    boundary = cap // 3
+    x = np.arange(boundary + 1, dtype=np.uint32)
+    r = R.Resampler(4, 3, 1)
+    w, consumed, first = r.work(x, cap)
+    assert w == 1 and len(first) == cap and first[-1] == boundary and consumed == boundary + 1
+    assert r.state()[3]                                  # pending sample
+    w, consumed, second = r.work(np.empty(0, np.uint32), cap)
+    assert w == 0 and list(second) == [boundary, boundary] and not r.state()[3]
+
+
+def test_resampler_zero_is_error(R):
+    for i, d in ((0, 1), (1, 0)):
+        with pytest.raises(R.RrcError):
+            R.Resampler(4, i, d)
+
+
+def test_resampler_run_host(R):
+    x = O.synth_f32(33, 0, 1_000_000)
+    want = O.resample(x, 147, 160)
+    r = R.Resampler(4, 147, 160)
+    consumed, got = r.run_host(x, len(want) + 5)
+    assert consumed == len(x) and got.tobytes() == want.tobytes()
+
+
+# ---------------------------------------------------------------- demod ---
+def test_quad_demod(R):
+    n = 200_000
+    x = (np.exp(2j * np.pi * np.cumsum(0.05 * np.sin(2 * np.pi * 1e-3 * np.arange(n)))) * (1 + 0.1 * O.synth_f32(41, 0, n))).astype(np.complex64)
+    got = R.quad_demod_host(x, 0.7)
+    want = O.quad_demod(x, 0.7, f64=True)
+    assert len(got) == n - 1
+    assert O.max_angle_err(got / 0.7, want / 0.7) <= DEMOD_BAR
+    print("demod max err rad:", O.max_angle_err(got / 0.7, want / 0.7), " f32 oracle:", O.max_angle_err(O.quad_demod(x, 0.7) / 0.7, want / 0.7))
+    # reference KATs src/quadrature_demod.rs:211-264
+    assert list(R.quad_demod_host(np.zeros(4, np.complex64))) == [0.0, 0.0, 0.0]
+    cw = R.quad_demod_host(np.array([1, 0.707 - 0.707j, -1j, -1], np.complex64))
+    assert np.allclose(cw, [-np.pi / 4, -np.pi / 4, -np.pi / 2], atol=1e-3)
+    # white noise input: angles all over (-pi, pi]
+    z = O.synth_c32(42, 0, 100_000)
+    assert O.max_angle_err(R.quad_demod_host(z), O.quad_demod(z, f64=True)) <= DEMOD_BAR
+
+
+# ----------------------------------------- BASELINE-size spot checks -------
+def _spot_check_fir(R, x_dev, y_dev, n_out, taps, deci, seed, n_in, npts=400):
+    """Random outputs of a device-resident run against f64 dot products of the
+    regenerated synthetic input (the input never has to exist on the host)."""
+    rng = np.random.default_rng(0)
+    idx = np.unique(np.concatenate([[0, 1, n_out - 1], rng.integers(0, n_out, npts)]))
+    T = len(taps)
+    got = np.array([y_dev.download(np.complex64, 1, int(i) * 8)[0] for i in idx])
+    want = np.empty(len(idx), np.complex128)
+    rev = taps[::-1].astype(np.complex128)
+    for k, i in enumerate(idx):
+        w = O.synth_c32(seed, int(i) * deci, T).astype(np.complex128)
+        want[k] = np.dot(w, rev)
+    return O.rel_rms(got, want)
+
+
+def test_fir_config1_full_size(R):
+    """BASELINE config 1: 64-tap c32 low-pass, no decimation, 2^24 samples."""
+    n, seed = 1 << 24, 0x5EED0001
+    taps = O.low_pass_n(1.0, 0.1, 64).astype(np.complex64)
+    f = R.Fir(taps)
+    din = R.DeviceBuffer(n * 8)
+    R.synth_f32(din, seed, 0, 2 * n)
+    n_out = f.out_count(n)
+    assert n_out == 16_777_153
+    dout = R.DeviceBuffer(n_out * 8)
+    f.run(din, n, dout, n_out)
+    assert _spot_check_fir(R, din, dout, n_out, taps, 1, seed, n) <= REL_RMS_BAR
+    # the device generator and the oracle generator are the same function
+    h = din.download(np.complex64, 4096)
+    assert np.array_equal(h, O.synth_c32(seed, 0, 4096))
+
+
+def test_fftfilt_config2_full_size(R):
+    """BASELINE config 2: 4097-tap FftFilter over 2^28 c32 samples (device-resident)."""
+    n, seed, T = 1 << 28, 0x5EED0002, 4097
+    taps = O.low_pass_n(1.0, 0.05, T).astype(np.complex64)
+    f = R.FftFilt(taps)
+    din = R.DeviceBuffer(n * 8)
+    R.synth_f32(din, seed, 0, 2 * n)
+    n_out = O.fftfilt_out_count(n, T)
+    assert n_out == 268_434_089
+    dout = R.DeviceBuffer(n * 8)
+    f.run(din, n_out, dout)
+    rng = np.random.default_rng(1)
+    idx = np.unique(np.concatenate([[0, 1, T - 2, T - 1, T, 12287, 12288, n_out - 1], rng.integers(0, n_out, 300)]))
+    got = np.array([dout.download(np.complex64, 1, int(i) * 8)[0] for i in idx])
+    want = np.empty(len(idx), np.complex128)
+    h64 = taps.astype(np.complex128)
+    for k, i in enumerate(idx):
+        i = int(i)
+        lo = max(0, i - T + 1)
+        w = O.synth_c32(seed, lo, i - lo + 1).astype(np.complex128)     # x[lo..i]
+        want[k] = np.dot(w[::-1], h64[:len(w)])                          # sum_k h[k] x[i-k]
+    assert O.rel_rms(got, want) <= REL_RMS_BAR
