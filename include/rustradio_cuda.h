@@ -207,6 +207,84 @@ int rrc_quad_demod_run_batch(int device, const float* in_dev_c32, size_t in_stri
                              float* out_dev, size_t out_stride, size_t nchan, void* stream);
 int rrc_quad_demod_run_host(int device, const float* in_host_c32, size_t n_in, float gain, float* out_host);
 
+/* ------------------------------------------- block-level contract (rrb_) --- */
+/*
+ * rustradio's Block / ReadStream / WriteStream / Tag contract (src/block.rs:12-126,
+ * src/stream.rs:48-339, src/nowasm/circular_buffer.rs:340-616) restated over the
+ * kernels above, so a host language without the `rustradio-cuda` Rust crate can
+ * still drive the blocks exactly as the reference's tests drive its own:
+ * constructors take ownership of the input ReadStream and hand back the block
+ * plus the output ReadStream; work() reports Again / WaitForStream(stream, need)
+ * / EOF; tags travel with the samples.  Streams are double-mapped rings in
+ * pageable host memory (residency 0) or in device memory (residency 1, CUDA
+ * VMM) with a configurable size (the reference's is fixed at 4,096,000 bytes).
+ */
+typedef struct rrb_rstream rrb_rstream_t;     /* ReadStream<T> */
+typedef struct rrb_wstream rrb_wstream_t;     /* WriteStream<T> */
+typedef struct rrb_block rrb_block_t;         /* Box<dyn Block> */
+
+#define RRB_TAG_STRING 0
+#define RRB_TAG_FLOAT  1
+#define RRB_TAG_BOOL   2
+#define RRB_TAG_U64    3
+#define RRB_TAG_I64    4
+typedef struct {
+    uint64_t pos;          /* relative to the window, like Tag::pos() */
+    const char* key;
+    int kind;              /* RRB_TAG_* (TagValue variant, src/stream.rs:17-34) */
+    const char* s;
+    float f;
+    int b;
+    uint64_t u;
+    int64_t i;
+} rrb_tag_t;
+
+#define RRB_RET_AGAIN   0
+#define RRB_RET_PENDING 1
+#define RRB_RET_WAIT    2   /* WaitForStream(stream_id, need) */
+#define RRB_RET_EOF     3
+
+#define RRB_HOST   0
+#define RRB_DEVICE 1
+#define RRB_DEFAULT_STREAM_SIZE 4096000
+
+int rrb_stream_new(size_t elem_size, size_t bytes, int residency, int device, rrb_wstream_t** w, rrb_rstream_t** r);
+/* write_buf() + fill_from_slice + produce(n, tags): writes min(n, free) samples. */
+int rrb_wstream_write(rrb_wstream_t* w, const void* host_data, size_t n, const rrb_tag_t* tags, size_t ntags, size_t* written);
+int rrb_wstream_free(rrb_wstream_t* w, size_t* free_samples);
+int rrb_wstream_id(rrb_wstream_t* w, size_t* id);
+int rrb_wstream_drop(rrb_wstream_t* w);                         /* dropping the writer is how EOF propagates */
+/* read_buf(): copies up to max samples of the current window to host_out (no consume) and
+ * snapshots the window's tags for rrb_rstream_tag(). */
+int rrb_rstream_read(rrb_rstream_t* r, void* host_out, size_t max, size_t* window_len, size_t* ntags);
+int rrb_rstream_tag(rrb_rstream_t* r, size_t index, rrb_tag_t* tag);   /* pointers valid until the next read */
+int rrb_rstream_consume(rrb_rstream_t* r, size_t n);
+int rrb_rstream_id(rrb_rstream_t* r, size_t* id);
+int rrb_rstream_capacity(rrb_rstream_t* r, size_t* samples);
+int rrb_rstream_eof(rrb_rstream_t* r, int* eof);
+int rrb_rstream_drop(rrb_rstream_t* r);
+
+/* Constructors: `src` is consumed.  out_bytes/out_residency/device configure the output stream. */
+int rrb_vector_source_new(const void* data, size_t n, size_t elem_size, uint64_t repeat,
+                          size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+int rrb_fir_filter_new(rrb_rstream_t* src, int cplx, const float* taps, size_t ntaps, size_t deci,
+                       int translate, float samp_rate, float freq, unsigned flags,
+                       size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+int rrb_fft_filter_new(rrb_rstream_t* src, const float* taps_c32, size_t ntaps,
+                       size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+int rrb_fft_filter_float_new(rrb_rstream_t* src, const float* taps, size_t ntaps,
+                             size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+int rrb_rational_resampler_new(rrb_rstream_t* src, size_t interp, size_t deci,
+                               size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+int rrb_quadrature_demod_new(rrb_rstream_t* src, float gain,
+                             size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+int rrb_block_work(rrb_block_t* b, int* kind, size_t* stream_id, size_t* need);
+int rrb_block_eof(rrb_block_t* b, int* eof);
+const char* rrb_block_name(rrb_block_t* b);
+int rrb_block_drop(rrb_block_t* b);
+/* Graph::run (src/graph.rs:99-173) over the given blocks, single threaded, round robin. */
+int rrb_graph_run(rrb_block_t** blocks, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,622 @@
+// blocks.cu — implementation of blocks.hpp (host-side Block/Stream contract over the C ABI)
+// plus the rrb_* C entry points used by the block-level parity tests.
+#include "blocks.hpp"
+
+#include <cuda.h>          // driver-API TYPES only; entry points are resolved at run time
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace rr {
+
+using rrc::fail;
+
+// ------------------------------------------------------------ driver API (VMM) ----
+// libcuda is NOT linked (the library must load on machines without a driver); the few
+// driver entry points the double-mapped device ring needs are fetched through the runtime.
+namespace drv {
+typedef CUresult (*pfn_cuMemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+typedef CUresult (*pfn_cuMemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+typedef CUresult (*pfn_cuMemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+typedef CUresult (*pfn_cuMemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+typedef CUresult (*pfn_cuMemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+typedef CUresult (*pfn_cuMemUnmap)(CUdeviceptr, size_t);
+typedef CUresult (*pfn_cuMemRelease)(CUmemGenericAllocationHandle);
+typedef CUresult (*pfn_cuMemAddressFree)(CUdeviceptr, size_t);
+
+struct Api {
+    pfn_cuMemGetAllocationGranularity granularity = nullptr;
+    pfn_cuMemAddressReserve reserve = nullptr;
+    pfn_cuMemCreate create = nullptr;
+    pfn_cuMemMap map = nullptr;
+    pfn_cuMemSetAccess set_access = nullptr;
+    pfn_cuMemUnmap unmap = nullptr;
+    pfn_cuMemRelease release = nullptr;
+    pfn_cuMemAddressFree addr_free = nullptr;
+    bool ok = false;
+};
+
+static const Api& api() {
+    static Api a = [] {
+        Api x;
+        auto get = [](const char* name, void** fn) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+        };
+        x.ok = get("cuMemGetAllocationGranularity", (void**)&x.granularity) && get("cuMemAddressReserve", (void**)&x.reserve) &&
+               get("cuMemCreate", (void**)&x.create) && get("cuMemMap", (void**)&x.map) &&
+               get("cuMemSetAccess", (void**)&x.set_access) && get("cuMemUnmap", (void**)&x.unmap) &&
+               get("cuMemRelease", (void**)&x.release) && get("cuMemAddressFree", (void**)&x.addr_free);
+        return x;
+    }();
+    return a;
+}
+}  // namespace drv
+
+static std::atomic<size_t> g_next_stream_id{1};    // NEXT_STREAM_ID, src/lib.rs:273-274
+
+void* graph_stream(int device) {
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {nullptr};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64) return nullptr;
+    if (!streams[device]) {
+        cudaSetDevice(device);
+        cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking);
+    }
+    return streams[device];
+}
+
+// --------------------------------------------------------------------- Buffer -----
+std::shared_ptr<Buffer> Buffer::create(size_t elem_size, size_t bytes, Residency res, int device, std::string* err) {
+    auto set_err = [&](const std::string& m) { if (err) *err = m; return std::shared_ptr<Buffer>(); };
+    if (elem_size == 0 || bytes < elem_size) return set_err("stream size too small");
+    std::shared_ptr<Buffer> b(new Buffer());
+    b->id_ = g_next_stream_id.fetch_add(1);
+    b->elem_ = elem_size; b->res_ = res; b->device_ = device;
+    if (res == Residency::Host) {
+        const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+        if (bytes % page) return set_err("host stream size must be a multiple of the page size (src/stream.rs:96)");
+        if (bytes % elem_size) return set_err("stream size must be a multiple of the element size");
+        int fd = memfd_create("rrb_stream", 0);
+        if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0) { if (fd >= 0) close(fd); return set_err("memfd_create/ftruncate failed"); }
+        void* base = mmap(nullptr, 2 * bytes, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (base == MAP_FAILED) { close(fd); return set_err("mmap reserve failed"); }
+        void* m1 = mmap(base, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, fd, 0);
+        void* m2 = mmap((char*)base + bytes, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, fd, 0);
+        close(fd);
+        if (m1 == MAP_FAILED || m2 == MAP_FAILED) { munmap(base, 2 * bytes); return set_err("double mmap failed"); }
+        b->base_ = (char*)base; b->map_bytes_ = bytes;
+        b->cap_ = bytes / elem_size;
+    } else {
+        const auto& d = drv::api();
+        if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) return set_err("no CUDA device for a device-resident stream");
+        if (!d.ok) return set_err("CUDA VMM driver entry points unavailable");
+        CUmemAllocationProp prop{};
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = device;
+        size_t gran = 0;
+        if (d.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0) return set_err("cuMemGetAllocationGranularity failed");
+        // capacity: round up to the VMM granularity AND to a whole number of elements
+        size_t sz = (bytes + gran - 1) / gran * gran;
+        while (sz % elem_size) sz += gran;
+        CUdeviceptr va = 0;
+        if (d.reserve(&va, 2 * sz, gran, 0, 0) != CUDA_SUCCESS) return set_err("cuMemAddressReserve failed");
+        CUmemGenericAllocationHandle h = 0;
+        if (d.create(&h, sz, &prop, 0) != CUDA_SUCCESS) { d.addr_free(va, 2 * sz); return set_err("cuMemCreate failed"); }
+        CUmemAccessDesc acc{};
+        acc.location = prop.location;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        if (d.map(va, sz, 0, h, 0) != CUDA_SUCCESS || d.map(va + sz, sz, 0, h, 0) != CUDA_SUCCESS ||
+            d.set_access(va, 2 * sz, &acc, 1) != CUDA_SUCCESS) {
+            d.unmap(va, 2 * sz); d.release(h); d.addr_free(va, 2 * sz);
+            return set_err("cuMemMap/cuMemSetAccess failed");
+        }
+        b->base_ = (char*)va; b->map_bytes_ = sz; b->vmm_handle_ = h; b->vmm_va_ = va;
+        b->cap_ = sz / elem_size;
+        cudaMemset((void*)va, 0, sz);          // zero-initialised like the reference's tempfile (Appendix B.8)
+    }
+    return b;
+}
+
+Buffer::~Buffer() {
+    if (!base_) return;
+    if (res_ == Residency::Host) {
+        munmap(base_, 2 * map_bytes_);
+    } else {
+        const auto& d = drv::api();
+        cudaSetDevice(device_);
+        cudaDeviceSynchronize();
+        d.unmap((CUdeviceptr)vmm_va_, 2 * map_bytes_);
+        d.release((CUmemGenericAllocationHandle)vmm_handle_);
+        d.addr_free((CUdeviceptr)vmm_va_, 2 * map_bytes_);
+    }
+}
+
+size_t Buffer::used() { std::lock_guard<std::mutex> lk(mu_); return used_; }
+size_t Buffer::free_space() { std::lock_guard<std::mutex> lk(mu_); return cap_ - used_; }
+
+void Buffer::write_window(char** ptr, size_t* len) {
+    std::lock_guard<std::mutex> lk(mu_);
+    *ptr = base_ + wpos_ * elem_;
+    *len = cap_ - used_;
+}
+
+void Buffer::produce(size_t n, const std::vector<Tag>& tags) {
+    if (n == 0) return;                                       // tags on an empty produce are dropped (:528-533)
+    std::lock_guard<std::mutex> lk(mu_);
+    for (const Tag& t : tags) {
+        const size_t pos = (t.pos + wpos_) % cap_;
+        Tag c = t; c.pos = pos;
+        tags_[pos].push_back(std::move(c));
+    }
+    wpos_ = (wpos_ + n) % cap_;
+    used_ += n;
+    cv_.notify_all();
+}
+
+void Buffer::read_window(const char** ptr, size_t* len, std::vector<Tag>* tags) {
+    std::lock_guard<std::mutex> lk(mu_);
+    const size_t start = rpos_, end = rpos_ + used_;
+    *ptr = base_ + rpos_ * elem_;
+    *len = used_;
+    if (!tags) return;
+    tags->clear();
+    for (const auto& kv : tags_) {
+        const size_t m = kv.first % cap_;
+        if (end < cap_ && start < cap_) {
+            if (m < start || m >= end) continue;
+        } else {
+            if (m >= (end % cap_) && m < start) continue;
+        }
+        for (const Tag& t : kv.second) {
+            Tag c = t; c.pos = (t.pos + cap_ - start) % cap_;
+            tags->push_back(std::move(c));
+        }
+    }
+    std::stable_sort(tags->begin(), tags->end(), [](const Tag& a, const Tag& b) { return a.pos < b.pos; });
+}
+
+void Buffer::consume(size_t n) {
+    if (n == 0) return;
+    std::lock_guard<std::mutex> lk(mu_);
+    const size_t newpos = (rpos_ + n) % cap_;
+    if (newpos > rpos_) {
+        tags_.erase(tags_.lower_bound(rpos_), tags_.lower_bound(newpos));
+    } else {
+        tags_.erase(tags_.lower_bound(rpos_), tags_.end());
+        tags_.erase(tags_.begin(), tags_.lower_bound(newpos));
+    }
+    rpos_ = newpos;
+    used_ -= n;
+    cv_.notify_all();
+}
+
+size_t Buffer::wait_for_read(size_t need) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait_for(lk, std::chrono::milliseconds(100), [&] { return used_ >= need; });
+    return used_;
+}
+size_t Buffer::wait_for_write(size_t need) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait_for(lk, std::chrono::milliseconds(100), [&] { return cap_ - used_ >= need; });
+    return cap_ - used_;
+}
+void Buffer::writer_dropped() { std::lock_guard<std::mutex> lk(mu_); writer_alive_ = false; cv_.notify_all(); }
+void Buffer::reader_dropped() { std::lock_guard<std::mutex> lk(mu_); reader_alive_ = false; cv_.notify_all(); }
+bool Buffer::writer_alive() { std::lock_guard<std::mutex> lk(mu_); return writer_alive_; }
+bool Buffer::reader_alive() { std::lock_guard<std::mutex> lk(mu_); return reader_alive_; }
+
+StreamPair new_stream(size_t elem_size, size_t bytes, Residency res, int device, std::string* err) {
+    StreamPair p;
+    auto b = Buffer::create(elem_size, bytes, res, device, err);
+    if (!b) return p;
+    p.w.reset(new WriteStream(b));
+    p.r.reset(new ReadStream(b));
+    return p;
+}
+
+// -------------------------------------------------------------------- Scratch -----
+Scratch::~Scratch() { if (ptr) { cudaSetDevice(device_); cudaFree(ptr); } }
+int Scratch::reserve(int device, size_t bytes) {
+    if (bytes <= cap_) return RRC_OK;
+    if (ptr) { RRC_CUDA(cudaSetDevice(device_)); RRC_CUDA(cudaFree(ptr)); ptr = nullptr; cap_ = 0; }
+    device_ = device;
+    RRC_CUDA(cudaSetDevice(device));
+    RRC_CUDA(cudaMalloc((void**)&ptr, bytes));
+    cap_ = bytes;
+    return RRC_OK;
+}
+
+// Device view of an input window: the ring itself if it is device resident, else an H2D copy.
+static int stage_input(Buffer& b, const char* win, size_t bytes, Scratch& s, int device, const char** dev) {
+    if (b.residency() == Residency::Device) { *dev = win; return RRC_OK; }
+    RRC_TRY(s.reserve(device, std::max<size_t>(bytes, 16)));
+    RRC_CUDA(cudaMemcpyAsync(s.ptr, win, bytes, cudaMemcpyHostToDevice, (cudaStream_t)graph_stream(device)));
+    *dev = s.ptr;
+    return RRC_OK;
+}
+// Device view of an output window; finish_output() copies back and synchronises for host rings
+// (a CPU consumer must see the data before produce(), SURVEY section 7 "Hard parts").
+static int stage_output(Buffer& b, char* win, size_t bytes, Scratch& s, int device, char** dev) {
+    if (b.residency() == Residency::Device) { *dev = win; return RRC_OK; }
+    RRC_TRY(s.reserve(device, std::max<size_t>(bytes, 16)));
+    *dev = s.ptr;
+    return RRC_OK;
+}
+static int finish_output(Buffer& b, char* win, size_t bytes, Scratch& s, int device) {
+    if (b.residency() == Residency::Device) return RRC_OK;
+    cudaStream_t st = (cudaStream_t)graph_stream(device);
+    if (bytes) RRC_CUDA(cudaMemcpyAsync(win, s.ptr, bytes, cudaMemcpyDeviceToHost, st));
+    RRC_CUDA(cudaStreamSynchronize(st));
+    return RRC_OK;
+}
+
+static int make_output(size_t elem, const StreamOpts& o, std::unique_ptr<WriteStream>* w, std::unique_ptr<ReadStream>* r) {
+    std::string err;
+    StreamPair p = new_stream(elem, o.bytes, o.res, o.device, &err);
+    if (!p.w) return fail(RRC_ERR_CUDA, "new_stream failed: %s", err.c_str());
+    *w = std::move(p.w); *r = std::move(p.r);
+    return RRC_OK;
+}
+
+// ------------------------------------------------------------------ FirFilter -----
+int FirFilter::create(std::unique_ptr<ReadStream> src, bool cplx, const float* taps, size_t ntaps, size_t deci,
+                      bool translate, float samp_rate, float freq, unsigned flags, const StreamOpts& o,
+                      std::unique_ptr<FirFilter>* out) {
+    if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    std::unique_ptr<FirFilter> b(new FirFilter());
+    b->cplx_ = cplx; b->ntaps_ = ntaps; b->deci_ = deci; b->elem_ = cplx ? 8 : 4; b->device_ = o.device;
+    if (src->buffer().elem() != b->elem_) return fail(RRC_ERR_INVALID, "FirFilter: stream element size mismatch");
+    RRC_TRY(cplx ? rrc_fir_c32_create(o.device, taps, ntaps, deci, flags, &b->h_)
+                 : rrc_fir_f32_create(o.device, taps, ntaps, deci, flags, &b->h_));
+    if (translate) RRC_TRY(rrc_fir_set_translate(b->h_, samp_rate, freq));
+    b->src_ = std::move(src);
+    RRC_TRY(make_output(b->elem_, o, &b->dst_, &b->out_r_));
+    *out = std::move(b);
+    return RRC_OK;
+}
+FirFilter::~FirFilter() { rrc_fir_destroy(h_); }
+
+int FirFilter::work(BlockRet* ret) {          // src/fir.rs:492-550
+    const char* in; size_t in_len; std::vector<Tag> tags;
+    src_->buffer().read_window(&in, &in_len, &tags);
+    char* outp; size_t out_free;
+    dst_->buffer().write_window(&outp, &out_free);
+    size_t n, need, out_n, wait_need; int wait_out;
+    RRC_TRY(rrc_fir_plan(ntaps_, deci_, in_len, out_free, &n, &need, &out_n, &wait_need, &wait_out));
+    if (n == 0) {
+        *ret = BlockRet::wait(wait_out ? (const StreamWait*)dst_.get() : (const StreamWait*)src_.get(), wait_need);
+        return RRC_OK;
+    }
+    const char* din; char* dout;
+    RRC_TRY(stage_input(src_->buffer(), in, need * elem_, sin_, device_, &din));
+    RRC_TRY(stage_output(dst_->buffer(), outp, out_n * elem_, sout_, device_, &dout));
+    RRC_TRY(rrc_fir_run(h_, din, need, dout, out_n, graph_stream(device_)));
+    RRC_TRY(finish_output(dst_->buffer(), outp, out_n * elem_, sout_, device_));
+    tags.erase(std::remove_if(tags.begin(), tags.end(), [&](const Tag& t) { return t.pos >= n; }), tags.end());   // :536
+    src_->buffer().consume(n);                                                                                   // :537
+    if (deci_ != 1) for (Tag& t : tags) t.pos /= deci_;                                                          // :541-543
+    dst_->buffer().produce(out_n, tags);
+    *ret = BlockRet::again();                                                                                    // :549
+    return RRC_OK;
+}
+
+// ------------------------------------------------------------------ FftFilter -----
+int FftFilter::create(std::unique_ptr<ReadStream> src, const float* taps, size_t ntaps, const StreamOpts& o,
+                      std::unique_ptr<FftFilter>* out) {
+    if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    if (src->buffer().elem() != 8) return fail(RRC_ERR_INVALID, "FftFilter: stream must carry Complex<f32>");
+    std::unique_ptr<FftFilter> b(new FftFilter());
+    b->device_ = o.device; b->ntaps_ = ntaps;
+    RRC_TRY(rrc_fftfilt_c32_create(o.device, taps, ntaps, &b->h_));
+    size_t fft_size;
+    RRC_TRY(rrc_fftfilt_ref_fft_size(ntaps, &fft_size, &b->nsamples_));
+    RRC_CUDA(cudaSetDevice(o.device));
+    RRC_CUDA(cudaMalloc((void**)&b->partial_, b->nsamples_ * 8));
+    b->src_ = std::move(src);
+    RRC_TRY(make_output(8, o, &b->dst_, &b->out_r_));
+    *out = std::move(b);
+    return RRC_OK;
+}
+FftFilter::~FftFilter() {
+    rrc_fftfilt_destroy(h_);
+    if (partial_) { cudaSetDevice(device_); cudaFree(partial_); }
+}
+
+int FftFilter::work(BlockRet* ret) {          // src/fft_filter.rs:290-354, whole loop in one pass
+    const size_t S = nsamples_;
+    cudaStream_t st = (cudaStream_t)graph_stream(device_);
+    char* outp; size_t out_free;
+    dst_->buffer().write_window(&outp, &out_free);
+    const char* in; size_t in_len; std::vector<Tag> tags;
+    src_->buffer().read_window(&in, &in_len, &tags);
+    size_t blocks, consume, buffered_after, wait_need; int wait_out;
+    RRC_TRY(rrc_fftfilt_plan(ntaps_, buffered_, in_len, out_free, &blocks, &consume, &buffered_after, &wait_need, &wait_out));
+    const bool host_in = src_->buffer().residency() == Residency::Host;
+    const cudaMemcpyKind in_kind = host_in ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    RRC_CUDA(cudaSetDevice(device_));
+    char* dout = nullptr;
+    if (blocks) RRC_TRY(stage_output(dst_->buffer(), outp, blocks * S * 8, sout_, device_, &dout));
+    size_t ipos = 0;       // input samples handed to the filter so far
+    size_t done = 0;       // blocks done
+    if (blocks && buffered_ > 0) {            // complete the block that was being accumulated (:306-308)
+        const size_t add = S - buffered_;
+        RRC_CUDA(cudaMemcpyAsync(partial_ + buffered_ * 8, in, add * 8, in_kind, st));
+        RRC_TRY(rrc_fftfilt_run(h_, (const float*)partial_, S, (float*)dout, st));
+        ipos = add; done = 1;
+    }
+    if (blocks > done) {                      // whole blocks straight from the input window
+        const size_t nb = blocks - done;
+        const char* din;
+        if (host_in) {
+            RRC_TRY(sin_.reserve(device_, nb * S * 8));
+            RRC_CUDA(cudaMemcpyAsync(sin_.ptr, in + ipos * 8, nb * S * 8, cudaMemcpyHostToDevice, st));
+            din = sin_.ptr;
+        } else {
+            din = in + ipos * 8;
+        }
+        RRC_TRY(rrc_fftfilt_run(h_, (const float*)din, nb * S, (float*)(dout + done * S * 8), st));
+        ipos += nb * S;
+    }
+    // trailing partial accumulation (:306-327): buf keeps `buffered_after` samples
+    const size_t base = blocks ? 0 : buffered_;
+    if (consume > ipos) RRC_CUDA(cudaMemcpyAsync(partial_ + base * 8, in + ipos * 8, (consume - ipos) * 8, in_kind, st));
+    if (host_in) RRC_CUDA(cudaStreamSynchronize(st));          // the host window is released by consume()
+    if (blocks) RRC_TRY(finish_output(dst_->buffer(), outp, blocks * S * 8, sout_, device_));
+
+    // tags (:309-313): absolute position in (buf ++ input) = buffered + pos; emitted with their block.
+    std::vector<Tag> out_tags = std::move(pending_tags_);
+    pending_tags_.clear();
+    for (Tag& t : tags) {
+        if (t.pos >= consume) continue;
+        t.pos += buffered_;
+        out_tags.push_back(std::move(t));
+    }
+    std::vector<Tag> emit;
+    for (Tag& t : out_tags) {
+        if (t.pos < blocks * S) emit.push_back(std::move(t));
+        else { t.pos -= blocks * S; pending_tags_.push_back(std::move(t)); }
+    }
+    src_->buffer().consume(consume);
+    dst_->buffer().produce(blocks * S, emit);
+    buffered_ = buffered_after;
+    *ret = BlockRet::wait(wait_out ? (const StreamWait*)dst_.get() : (const StreamWait*)src_.get(), wait_need);
+    return RRC_OK;
+}
+
+// ------------------------------------------------------------- FftFilterFloat -----
+__global__ void widen_kernel(const float* __restrict__ in, float2* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = make_float2(in[i], 0.f);
+}
+__global__ void real_part_kernel(const float2* __restrict__ in, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = in[i].x;
+}
+
+int FftFilterFloat::create(std::unique_ptr<ReadStream> src, const float* taps, size_t ntaps, const StreamOpts& o,
+                           std::unique_ptr<FftFilterFloat>* out) {
+    if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    if (src->buffer().elem() != 4) return fail(RRC_ERR_INVALID, "FftFilterFloat: stream must carry f32");
+    if (!taps || ntaps == 0) return fail(RRC_ERR_INVALID, "FftFilterFloat needs at least one tap");
+    std::unique_ptr<FftFilterFloat> b(new FftFilterFloat());
+    b->device_ = o.device;
+    std::vector<float> ct(2 * ntaps, 0.f);                    // taps -> Complex::new(f, 0.0) (:404)
+    for (size_t i = 0; i < ntaps; ++i) ct[2 * i] = taps[i];
+    StreamOpts inner = o;
+    inner.res = Residency::Device;                            // inner streams never leave the device
+    std::string err;
+    StreamPair p = new_stream(8, inner.bytes, inner.res, inner.device, &err);
+    if (!p.w) return fail(RRC_ERR_CUDA, "new_stream failed: %s", err.c_str());
+    b->inner_in_ = std::move(p.w);
+    b->inner_in_id_ = b->inner_in_->id();
+    RRC_TRY(FftFilter::create(std::move(p.r), ct.data(), ntaps, inner, &b->complex_));
+    b->inner_out_ = b->complex_->take_output();
+    b->src_ = std::move(src);
+    RRC_TRY(make_output(4, o, &b->dst_, &b->out_r_));
+    *out = std::move(b);
+    return RRC_OK;
+}
+
+int FftFilterFloat::work(BlockRet* ret) {     // src/fft_filter.rs:428-490
+    cudaStream_t st = (cudaStream_t)graph_stream(device_);
+    RRC_CUDA(cudaSetDevice(device_));
+    {   // Convert input to Complex (:430-445)
+        const char* in; size_t in_len; std::vector<Tag> tags;
+        src_->buffer().read_window(&in, &in_len, &tags);
+        char* to; size_t to_len;
+        inner_in_->buffer().write_window(&to, &to_len);
+        const size_t n = std::min(in_len, to_len);
+        if (n) {
+            const char* din;
+            RRC_TRY(stage_input(src_->buffer(), in, n * 4, sin_, device_, &din));
+            widen_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, st>>>((const float*)din, (float2*)to, n);
+            RRC_CHECK_LAUNCH();
+            rrc::count_launch();
+            if (src_->buffer().residency() == Residency::Host) RRC_CUDA(cudaStreamSynchronize(st));
+        }
+        tags.erase(std::remove_if(tags.begin(), tags.end(), [&](const Tag& t) { return t.pos >= n; }), tags.end());
+        inner_in_->buffer().produce(n, tags);
+        src_->buffer().consume(n);
+    }
+    BlockRet inner;
+    RRC_TRY(complex_->work(&inner));          // :450
+    {   // Replicate stream write (:453-470)
+        const char* from; size_t from_len; std::vector<Tag> tags;
+        inner_out_->buffer().read_window(&from, &from_len, &tags);
+        char* to; size_t to_len;
+        dst_->buffer().write_window(&to, &to_len);
+        const size_t n = std::min(from_len, to_len);
+        if (n == 0 && from_len != 0) { *ret = BlockRet::wait(dst_.get(), 1); return RRC_OK; }
+        if (n) {
+            char* dout;
+            RRC_TRY(stage_output(dst_->buffer(), to, n * 4, sout_, device_, &dout));
+            real_part_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, st>>>((const float2*)from, (float*)dout, n);
+            RRC_CHECK_LAUNCH();
+            rrc::count_launch();
+            RRC_TRY(finish_output(dst_->buffer(), to, n * 4, sout_, device_));
+        }
+        tags.erase(std::remove_if(tags.begin(), tags.end(), [&](const Tag& t) { return t.pos >= n; }), tags.end());
+        inner_out_->buffer().consume(n);
+        dst_->buffer().produce(n, tags);
+    }
+    if (inner.kind == RetKind::WaitForStream) {               // :474-489
+        if (inner.stream->id() == inner_in_id_) *ret = BlockRet::wait(src_.get(), inner.need);
+        else *ret = BlockRet::wait(dst_.get(), inner.need);
+    } else {
+        *ret = inner;
+    }
+    return RRC_OK;
+}
+
+// ---------------------------------------------------------- RationalResampler -----
+int RationalResampler::create(std::unique_ptr<ReadStream> src, size_t interp, size_t deci, const StreamOpts& o,
+                              std::unique_ptr<RationalResampler>* out) {
+    if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    std::unique_ptr<RationalResampler> b(new RationalResampler());
+    b->device_ = o.device; b->elem_ = src->buffer().elem();
+    RRC_TRY(rrc_resampler_create(o.device, b->elem_, interp, deci, &b->h_));   // Err on 0 (:130-135)
+    b->src_ = std::move(src);
+    RRC_TRY(make_output(b->elem_, o, &b->dst_, &b->out_r_));
+    *out = std::move(b);
+    return RRC_OK;
+}
+RationalResampler::~RationalResampler() { rrc_resampler_destroy(h_); }
+
+bool RationalResampler::eof() {
+    int pending = 0;
+    rrc_resampler_state(h_, nullptr, nullptr, nullptr, &pending);
+    return !pending && src_->eof();
+}
+
+int RationalResampler::work(BlockRet* ret) {  // src/rational_resampler.rs:155-206
+    char* outp; size_t cap;
+    dst_->buffer().write_window(&outp, &cap);
+    if (cap == 0) { *ret = BlockRet::wait(dst_.get(), 1); return RRC_OK; }
+    const char* in; size_t in_len;
+    src_->buffer().read_window(&in, &in_len, nullptr);        // tags dropped (:156,200)
+    const char* din = in; char* dout;
+    if (in_len) RRC_TRY(stage_input(src_->buffer(), in, in_len * elem_, sin_, device_, &din));
+    RRC_TRY(stage_output(dst_->buffer(), outp, cap * elem_, sout_, device_, &dout));
+    size_t consumed, produced; int wait_out;
+    RRC_TRY(rrc_resampler_run(h_, din, in_len, dout, cap, &consumed, &produced, &wait_out, graph_stream(device_)));
+    RRC_TRY(finish_output(dst_->buffer(), outp, produced * elem_, sout_, device_));
+    if (src_->buffer().residency() == Residency::Host) RRC_CUDA(cudaStreamSynchronize((cudaStream_t)graph_stream(device_)));
+    src_->buffer().consume(consumed);
+    dst_->buffer().produce(produced, {});
+    *ret = BlockRet::wait(wait_out ? (const StreamWait*)dst_.get() : (const StreamWait*)src_.get(), 1);
+    return RRC_OK;
+}
+
+// ------------------------------------------------------------ QuadratureDemod -----
+int QuadratureDemod::create(std::unique_ptr<ReadStream> src, float gain, const StreamOpts& o,
+                            std::unique_ptr<QuadratureDemod>* out) {
+    if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    if (src->buffer().elem() != 8) return fail(RRC_ERR_INVALID, "QuadratureDemod: stream must carry Complex<f32>");
+    std::unique_ptr<QuadratureDemod> b(new QuadratureDemod());
+    b->device_ = o.device; b->gain_ = gain;
+    b->src_ = std::move(src);
+    RRC_TRY(make_output(4, o, &b->dst_, &b->out_r_));
+    *out = std::move(b);
+    return RRC_OK;
+}
+
+int QuadratureDemod::work(BlockRet* ret) {    // src/quadrature_demod.rs:46-113
+    for (;;) {
+        const char* in; size_t in_len;
+        src_->buffer().read_window(&in, &in_len, nullptr);    // tags dropped (:111)
+        if (in_len < 2) { *ret = BlockRet::wait(src_.get(), 2); return RRC_OK; }
+        char* outp; size_t cap;
+        dst_->buffer().write_window(&outp, &cap);
+        if (cap == 0) { *ret = BlockRet::wait(dst_.get(), 1); return RRC_OK; }
+        const size_t n1 = std::min(in_len - 1, cap);
+        const char* din; char* dout;
+        RRC_TRY(stage_input(src_->buffer(), in, (n1 + 1) * 8, sin_, device_, &din));
+        RRC_TRY(stage_output(dst_->buffer(), outp, n1 * 4, sout_, device_, &dout));
+        RRC_TRY(rrc_quad_demod_run(device_, (const float*)din, n1 + 1, gain_, (float*)dout, graph_stream(device_)));
+        RRC_TRY(finish_output(dst_->buffer(), outp, n1 * 4, sout_, device_));
+        if (src_->buffer().residency() == Residency::Host) RRC_CUDA(cudaStreamSynchronize((cudaStream_t)graph_stream(device_)));
+        src_->buffer().consume(n1);                           // keeps the last sample as history (:110)
+        dst_->buffer().produce(n1, {});
+    }
+}
+
+// --------------------------------------------------------------- VectorSource -----
+int VectorSource::create(const void* data, size_t n, size_t elem_size, uint64_t repeat, const StreamOpts& o,
+                         std::unique_ptr<VectorSource>* out) {
+    std::unique_ptr<VectorSource> b(new VectorSource());
+    b->elem_ = elem_size; b->n_ = n; b->repeat_ = repeat; b->device_ = o.device;
+    b->data_.assign((const char*)data, (const char*)data + n * elem_size);
+    RRC_TRY(make_output(elem_size, o, &b->dst_, &b->out_r_));
+    *out = std::move(b);
+    return RRC_OK;
+}
+
+static Tag mk_tag_bool(size_t pos, const char* key, bool v) { Tag t; t.pos = pos; t.key = key; t.val.kind = TagKind::Bool; t.val.b = v; return t; }
+static Tag mk_tag_u64(size_t pos, const char* key, uint64_t v) { Tag t; t.pos = pos; t.key = key; t.val.kind = TagKind::U64; t.val.u = v; return t; }
+
+int VectorSource::work(BlockRet* ret) {       // src/vector_source.rs:101-143
+    if (n_ == 0 || count_ >= repeat_) { *ret = BlockRet::eof(); return RRC_OK; }
+    if (!dst_) return fail(RRC_ERR_STATE, "VectorSource output dropped");
+    std::vector<Tag> tags;
+    if (pos_ == 0) {
+        tags.push_back(mk_tag_bool(0, "VectorSource::start", true));
+        tags.push_back(mk_tag_u64(0, "VectorSource::repeat", count_));
+        if (count_ == 0) tags.push_back(mk_tag_bool(0, "VectorSource::first", true));
+    }
+    char* outp; size_t cap;
+    dst_->buffer().write_window(&outp, &cap);
+    if (cap == 0) { *ret = BlockRet::wait(dst_.get(), 1); return RRC_OK; }
+    const size_t n = std::min(cap, n_ - pos_);
+    if (dst_->buffer().residency() == Residency::Device) {
+        RRC_CUDA(cudaSetDevice(device_));
+        RRC_CUDA(cudaMemcpyAsync(outp, data_.data() + pos_ * elem_, n * elem_, cudaMemcpyHostToDevice, (cudaStream_t)graph_stream(device_)));
+        RRC_CUDA(cudaStreamSynchronize((cudaStream_t)graph_stream(device_)));
+    } else {
+        memcpy(outp, data_.data() + pos_ * elem_, n * elem_);
+    }
+    dst_->buffer().produce(n, tags);
+    pos_ += n;
+    if (pos_ == n_) {
+        ++count_;
+        if (!(count_ < repeat_)) { *ret = BlockRet::eof(); return RRC_OK; }
+        pos_ = 0;
+    }
+    *ret = BlockRet::again();
+    return RRC_OK;
+}
+
+// ---------------------------------------------------------------------- Graph -----
+int Graph::run() {                            // src/graph.rs:99-160
+    std::vector<bool> eof(blocks_.size(), false);
+    for (;;) {
+        bool done = true, all_idle = true;
+        for (size_t i = 0; i < blocks_.size(); ++i) {
+            if (eof[i]) continue;
+            BlockRet r;
+            RRC_TRY(blocks_[i]->work(&r));
+            switch (r.kind) {
+            case RetKind::Again: done = false; all_idle = false; break;
+            case RetKind::Pending: done = false; break;
+            case RetKind::WaitForStream:
+                if (blocks_[i]->eof() || (r.stream && r.stream->closed())) eof[i] = true;
+                break;
+            case RetKind::EOF_: eof[i] = true; break;
+            }
+        }
+        if (done) break;
+        if (all_idle) std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    }
+    return RRC_OK;
+}
+
+}  // namespace rr

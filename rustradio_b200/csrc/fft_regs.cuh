@@ -99,4 +99,63 @@ RRC_HD void dif(float2* v) {
     }
 }
 
+// ---- decimation-in-time with FMA-fused butterflies --------------------------------
+// bfly<NUM, DEN, DIR>(a, b):  a <- a + w*b,  b <- a - w*b,  w = exp(-DIR*2*pi*i*NUM/DEN).
+// General twiddle: 6 FFMA (sum by two FMA chains, difference as 2a - sum) instead of the
+// 2 FMUL + 2 FFMA + 4 FADD of the textbook form; +-(1 -+ i)/sqrt2 twiddles: 2 FADD + 4 FFMA.
+template <int NUM, int DEN, int DIR>
+RRC_HD void bfly(float2& a, float2& b) {
+    constexpr int n64 = NUM * (64 / DEN);
+    if constexpr (n64 == 0) {
+        const float2 s = cadd(a, b), d = csub(a, b);
+        a = s; b = d;
+    } else if constexpr (n64 == 16) {              // w = -i (fwd): w*b = (b.y, -b.x); +i (inv): (-b.y, b.x)
+        const float2 t = DIR > 0 ? make_float2(b.y, -b.x) : make_float2(-b.y, b.x);
+        const float2 s = cadd(a, t), d = csub(a, t);
+        a = s; b = d;
+    } else if constexpr (n64 == 8 || n64 == 24) {
+        constexpr float c = (float)0.70710678118654752440;
+        // n64 == 8 : w = c(1 - i) fwd, c(1 + i) inv ; n64 == 24: w = c(-1 - i) fwd, c(-1 + i) inv
+        // w*b = cr*(p) + i*cr*(q) with p, q = +-b.x +- b.y
+        float p, q;
+        if constexpr (n64 == 8) {
+            p = DIR > 0 ? b.x + b.y : b.x - b.y;
+            q = DIR > 0 ? b.y - b.x : b.y + b.x;
+        } else {
+            p = DIR > 0 ? b.y - b.x : -(b.x + b.y);
+            q = DIR > 0 ? -(b.x + b.y) : b.x - b.y;
+        }
+        const float2 s = make_float2(fmaf(c, p, a.x), fmaf(c, q, a.y));
+        const float2 d = make_float2(fmaf(-c, p, a.x), fmaf(-c, q, a.y));
+        a = s; b = d;
+    } else {
+        constexpr float wr = (float)cos64(n64);
+        constexpr float wi = (float)(-DIR * sin64(n64));
+        float2 s;
+        s.x = fmaf(-wi, b.y, fmaf(wr, b.x, a.x));
+        s.y = fmaf(wi, b.x, fmaf(wr, b.y, a.y));
+        const float2 d = make_float2(fmaf(2.0f, a.x, -s.x), fmaf(2.0f, a.y, -s.y));
+        a = s; b = d;
+    }
+}
+
+template <int N, int DIR, int I>
+struct DitLevel {
+    static RRC_HD void run(float2* v) {
+        bfly<I, N, DIR>(v[I], v[I + N / 2]);
+        if constexpr (I + 1 < N / 2) DitLevel<N, DIR, I + 1>::run(v);
+    }
+};
+
+// dit<N, DIR>(v): BIT-REVERSED input (v[bitrev<N>(n)] = x[n]), natural-order output (v[k] = X[k]).
+template <int N, int DIR>
+RRC_HD void dit(float2* v) {
+    static_assert(N >= 1 && N <= 64 && (N & (N - 1)) == 0, "N must be a power of two <= 64");
+    if constexpr (N >= 2) {
+        dit<N / 2, DIR>(v);
+        dit<N / 2, DIR>(v + N / 2);
+        DitLevel<N, DIR, 0>::run(v);
+    }
+}
+
 }}  // namespace rrc::fftr

@@ -27,28 +27,36 @@ namespace rrc {
 
 using fftk::BlockIO;
 
-constexpr size_t FFTFILT_SMEM = (size_t)(fftk::N + 512 + 512) * sizeof(float2);
+constexpr size_t FFTFILT_SMEM = (size_t)(fftk::SMEM_ELEMS + 512 + 512 + fftk::HRES_ELEMS) * sizeof(float2);
 
+template <bool DECIM>
 __global__ void __launch_bounds__(fftk::NT, 1)
 fftfilt_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __restrict__ tw1g,
                const float2* __restrict__ tw2g, long long nblocks) {
     extern __shared__ __align__(16) float2 sm[];
-    float2* s_tw2 = sm + fftk::N;
+    float2* s_tw2 = sm + fftk::SMEM_ELEMS;
     float2* s_tw1 = s_tw2 + 512;
+    float2* s_hres = s_tw1 + 512;
     const int tid = threadIdx.x;
     s_tw2[tid] = tw2g[tid];
     s_tw1[tid] = tw1g[tid];
+    fftk::load_hres(tid, Hp, s_hres);
     __syncthreads();
     for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         fftk::phase_a(tid, blk, io, s_tw1, sm);
         __syncthreads();
-        fftk::phase_b(tid, s_tw2, sm);
+        {   // Pull the NEXT block's input segment into L2 while this block computes, so the
+            // next phase A's loads are L2 hits: one 8 KiB bulk prefetch per warp (16 x 8 KiB = segment).
+            const long long nb = blk + gridDim.x;
+            const long long seg0 = nb * (long long)io.V - io.T1 + (long long)(tid >> 5) * 1024;
+            if ((tid & 31) == 0 && nb < nblocks && seg0 >= 0 && seg0 + 1024 <= io.n_in) {
+                const unsigned long long a = (reinterpret_cast<unsigned long long>(io.in + seg0) + 15ull) & ~15ull;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(8192 - 16) : "memory");
+            }
+        }
+        fftk::phase_mid(tid, s_tw2, Hp, s_hres, sm);      // half-warp local exchanges: __syncwarp only
         __syncthreads();
-        fftk::phase_c(tid, Hp, sm);
-        __syncthreads();
-        fftk::phase_bi(tid, s_tw2, sm);
-        __syncthreads();
-        fftk::phase_ai(tid, blk, io, s_tw1, sm);
+        fftk::phase_ai<DECIM>(tid, blk, io, s_tw1, sm);
         // no barrier: the next phase_a writes exactly the words this thread just read
     }
 }
@@ -99,12 +107,10 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
     io.skip = (long long)skip;
     const long long nblocks = ((long long)n + h->V - 1) / h->V;
     const int grid = (int)std::min<long long>(nblocks, sm_count(h->device));
-    static bool attr_set[64] = {false};
-    if (!attr_set[h->device]) {
-        RRC_CUDA(cudaFuncSetAttribute(fftfilt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_SMEM));
-        attr_set[h->device] = true;
-    }
-    fftfilt_kernel<<<grid, fftk::NT, FFTFILT_SMEM, st>>>(io, h->Hp, h->tw1, h->tw2, nblocks);
+    const bool decim = !(deci == 1 && skip == 0);
+    auto kern = decim ? fftfilt_kernel<true> : fftfilt_kernel<false>;
+    RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_SMEM));
+    kern<<<grid, fftk::NT, FFTFILT_SMEM, st>>>(io, h->Hp, h->tw1, h->tw2, nblocks);
     RRC_CHECK_LAUNCH();
     count_launch();
     if (h->T1 > 0) {

@@ -1,6 +1,6 @@
 // fftfilt_tables.hpp — host-side tables for the 16384-point FftFilter kernel:
 // the tap spectrum H (f64 FFT, scaled by 1/N like rustradio
-// src/fft_filter.rs:151-162, permuted to phase C's register order) and the two
+// src/fft_filter.rs:151-162, laid out in phase C's row order) and the two
 // twiddle tables.  Shared by fftfilt.cu and the CPU emulator (tests/emul).
 #pragma once
 #include <cmath>
@@ -33,7 +33,7 @@ inline void fft_host(std::vector<std::complex<double>>& a) {
     }
 }
 
-// taps: ntaps interleaved c32.  Hp[P*16 + j] = H[k1 + 32*k2 + 1024*bitrev4(j)] / N,
+// taps: ntaps interleaved c32.  Hp[P*16 + k3] = H[k1 + 32*k2 + 1024*k3] / N,
 // P = k1*32 + k2.  tw1[t] = W_N^t (t < 512).  tw2[k2*16 + n3] = W_512^{n3*k2}.
 inline void build_tables(const float* taps, size_t ntaps, std::vector<float2>& Hp,
                          std::vector<float2>& tw1, std::vector<float2>& tw2) {
@@ -44,7 +44,7 @@ inline void build_tables(const float* taps, size_t ntaps, std::vector<float2>& H
     for (int P = 0; P < 1024; ++P) {
         const int k1 = P >> 5, k2 = P & 31;
         for (int j = 0; j < 16; ++j) {
-            const int k = k1 + 32 * k2 + 1024 * fftr::bitrev(j, 4);
+            const int k = k1 + 32 * k2 + 1024 * j;
             const auto v = H[k] / (double)N;
             Hp[(size_t)P * 16 + j] = make_float2((float)v.real(), (float)v.imag());
         }

@@ -23,14 +23,19 @@ extern "C" int emul_fftfilt(const float* taps, long long ntaps, const float* in,
     io.hist = h.data();
     io.out = reinterpret_cast<float2*>(out);
     io.n_in = n; io.n_out = n_out; io.T1 = T1; io.V = N - T1; io.deci = (int)deci; io.skip = skip;
-    std::vector<float2> sm(N);
+    std::vector<float2> sm(SMEM_ELEMS), hres(HRES_ELEMS);
+    for (int t = 0; t < NT; ++t) load_hres(t, Hp.data(), hres.data());
     const long long nblocks = (n + io.V - 1) / io.V;
+    const bool decim = !(deci == 1 && skip == 0);
     for (long long blk = 0; blk < nblocks; ++blk) {
         for (int t = 0; t < NT; ++t) phase_a(t, blk, io, tw1.data(), sm.data());
-        for (int t = 0; t < NT; ++t) phase_b(t, tw2.data(), sm.data());
-        for (int t = 0; t < NT; ++t) phase_c(t, Hp.data(), sm.data());
-        for (int t = 0; t < NT; ++t) phase_bi(t, tw2.data(), sm.data());
-        for (int t = 0; t < NT; ++t) phase_ai(t, blk, io, tw1.data(), sm.data());
+        for (int t = 0; t < NT; ++t) phase_mid_b(t, tw2.data(), sm.data());
+        for (int t = 0; t < NT; ++t) phase_mid_c(t, Hp.data(), hres.data(), sm.data());
+        for (int t = 0; t < NT; ++t) phase_mid_bi(t, tw2.data(), sm.data());
+        for (int t = 0; t < NT; ++t) {
+            if (decim) phase_ai<true>(t, blk, io, tw1.data(), sm.data());
+            else phase_ai<false>(t, blk, io, tw1.data(), sm.data());
+        }
     }
     return 0;
 }

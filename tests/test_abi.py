@@ -19,7 +19,7 @@ HEADER = (ROOT / "include" / "rustradio_cuda.h").read_text()
 
 
 def declared_symbols():
-    return sorted(set(re.findall(r"\b(rrc_[a-z0-9_]+)\s*\(", HEADER)))
+    return sorted(set(re.findall(r"\b(rr[cb]_[a-z0-9_]+)\s*\(", HEADER)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -29,8 +29,8 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in rustradio_cuda.h but not exported"
     # and the Python binding covers the same set
-    from rustradio_b200 import api
-    assert set(api.exported_symbols()) == set(names)
+    from rustradio_b200 import api, blocks
+    assert set(api.exported_symbols()) | set(blocks.exported_symbols()) == set(names)
 
 
 def test_header_cites_reference_for_each_group():

@@ -1,0 +1,64 @@
+"""CPU emulation of the FftFilter CUDA kernel (tests/emul/fftfilt_emul.cu): the
+kernel's phase functions are __host__ __device__, so the exact index math,
+shared-memory layout and twiddle logic run here thread-by-thread on the CPU and
+are checked against the oracle.  This is a test of the kernel SOURCE without a
+GPU; it is not a product path (nothing in rustradio_b200 can reach it)."""
+import ctypes as C
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+HERE = Path(__file__).resolve().parent / "emul"
+SO = HERE / "_fftfilt_emul.so"
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if shutil.which("nvcc") is None and not Path("/usr/local/cuda/bin/nvcc").exists():
+        pytest.skip("nvcc not available")
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    src = HERE / "fftfilt_emul.cu"
+    deps = [src] + list((HERE.parent.parent / "rustradio_b200" / "csrc").glob("fft*"))
+    if not SO.exists() or SO.stat().st_mtime < max(d.stat().st_mtime for d in deps):
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
+                        "-o", str(SO), str(src)], check=True)
+    L = C.CDLL(str(SO))
+    L.emul_fftfilt.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                               C.c_longlong, C.c_longlong, C.c_longlong]
+
+    def run(taps, x, hist=None, deci=1, skip=0):
+        taps = np.ascontiguousarray(taps, np.complex64)
+        x = np.ascontiguousarray(x, np.complex64)
+        n = len(x)
+        n_out = n if (deci == 1 and skip == 0) else ((n - skip + deci - 1) // deci if n > skip else 0)
+        out = np.zeros(n_out, np.complex64)
+        L.emul_fftfilt(taps.ctypes.data, len(taps), x.ctypes.data, n,
+                       hist.ctypes.data if hist is not None else None, out.ctypes.data, deci, skip, n_out)
+        return out
+    return run
+
+
+@pytest.mark.parametrize("ntaps,n", [(1, 3000), (2, 20_000), (193, 8000), (4097, 40_000), (64, 16384 * 2 + 5), (12289, 20_000)])
+def test_emulated_kernel_matches_f64_convolution(emul, ntaps, n):
+    taps = (O.low_pass_n(1.0, 0.05, ntaps).astype(np.complex64) * (1 + 0.3j)) if ntaps > 2 else np.array([0.5 - 0.25j, 0.3 + 1j][:ntaps], np.complex64)
+    x = O.synth_c32(5, 0, n)
+    assert O.rel_rms(emul(taps, x), O.conv_full_f64_fft(x, taps, n)) <= 1e-5
+
+
+def test_emulated_kernel_history_and_decimation(emul):
+    taps = O.low_pass_n(1.0, 0.1, 301).astype(np.complex64)
+    x = O.synth_c32(6, 0, 40_000)
+    truth = O.conv_full_f64_fft(x, taps, len(x))
+    y = np.concatenate([emul(taps, x[:12345]), emul(taps, x[12345:], hist=np.ascontiguousarray(x[12345 - 300:12345]))])
+    assert O.rel_rms(y, truth) <= 1e-5
+    for deci, skip in ((8, 3), (3, 0), (1, 7), (1000, 999), (700, 40_001)):
+        yd = emul(taps, x, deci=deci, skip=skip)
+        want = truth[skip::deci]
+        assert len(yd) == len(want)
+        if len(want):
+            assert O.rel_rms(yd, want) <= 1e-5

@@ -171,7 +171,11 @@ def test_fftfilt_run_host_reference_count_rule(R):
     assert len(y) == 7975 == O.fftfilt_out_count(8000, 193)
     # reference test filter_a_signal (src/fft_filter.rs:502-549): stop band < 2e-4 after the transient
     assert np.max(np.abs(y[193:])) < 2e-4
-    assert O.rel_rms(y, O.conv_full_f64(sig, taps, 7975)) <= REL_RMS_BAR
+    # The tone sits in the stop band, so |y| ~ 1e-4 |x|: judge the error against the INPUT scale
+    # (relative to the almost-cancelled output it would be pure f32 rounding noise of either side).
+    truth = O.conv_full_f64(sig, taps, 7975)
+    assert np.max(np.abs(y - truth)) <= 1e-5 * np.max(np.abs(sig))
+    assert np.max(np.abs(y - truth)) <= 1e-6       # f32 noise floor of a 16384-point transform at unit input
 
 
 def test_fftfilt_fused_decimation(R):
