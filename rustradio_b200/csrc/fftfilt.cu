@@ -29,7 +29,7 @@ using fftk::BlockIO;
 
 constexpr size_t FFTFILT_SMEM = (size_t)(fftk::SMEM_ELEMS + 512 + 512 + fftk::HRES_ELEMS) * sizeof(float2);
 
-template <bool DECIM>
+template <bool DECIM, bool ACCUM>
 __global__ void __launch_bounds__(fftk::NT, 1)
 fftfilt_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __restrict__ tw1g,
                const float2* __restrict__ tw2g, long long nblocks) {
@@ -48,7 +48,7 @@ fftfilt_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __
         {   // Pull the NEXT block's input segment into L2 while this block computes, so the
             // next phase A's loads are L2 hits: one 8 KiB bulk prefetch per warp (16 x 8 KiB = segment).
             const long long nb = blk + gridDim.x;
-            const long long seg0 = nb * (long long)io.V - io.T1 + (long long)(tid >> 5) * 1024;
+            const long long seg0 = nb * (long long)io.V - io.T1 - io.shift + (long long)(tid >> 5) * 1024;
             if ((tid & 31) == 0 && nb < nblocks && seg0 >= 0 && seg0 + 1024 <= io.n_in) {
                 const unsigned long long a = (reinterpret_cast<unsigned long long>(io.in + seg0) + 15ull) & ~15ull;
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(8192 - 16) : "memory");
@@ -56,7 +56,7 @@ fftfilt_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __
         }
         fftk::phase_mid(tid, s_tw2, Hp, s_hres, sm);      // half-warp local exchanges: __syncwarp only
         __syncthreads();
-        fftk::phase_ai<DECIM>(tid, blk, io, s_tw1, sm);
+        fftk::phase_ai<DECIM, ACCUM>(tid, blk, io, s_tw1, sm);
         // no barrier: the next phase_a writes exactly the words this thread just read
     }
 }
@@ -77,8 +77,12 @@ using namespace rrc;
 struct rrc_fftfilt {
     int device = 0;
     size_t ntaps = 0;
-    int T1 = 0, V = 0;
-    float2* Hp = nullptr;
+    int T1 = 0;                       // ntaps - 1 (history length)
+    // Long filters are split into tap partitions of <= PART_TAPS taps; partition p filters the
+    // input delayed by p*PART_TAPS and accumulates into the output (y = sum_p h_p * x(n - p*L)).
+    std::vector<int> part_T1;         // taps of partition p, minus 1
+    std::vector<float2*> part_Hp;     // spectrum of partition p
+    float2* Hp = nullptr;             // == part_Hp[0]
     float2* tw1 = nullptr;
     float2* tw2 = nullptr;
     float2* hist[2] = {nullptr, nullptr};
@@ -94,6 +98,23 @@ size_t ref_fft_size(size_t ntaps) {   // calc_fft_size, src/fft_filter.rs:36-42
     return 2 * n;
 }
 
+// Tap partitioning: filters with more taps than one 16384-point block can hold efficiently
+// are split into partitions of PART_TAPS taps (valid fraction >= 50% per partition).
+constexpr size_t PART_TAPS = 8193;
+constexpr size_t SINGLE_MAX_TAPS = 12289;     // up to here one partition (valid >= 25%) beats two
+
+template <bool DECIM, bool ACCUM>
+int launch_part(rrc_fftfilt* h, const BlockIO& io, const float2* Hp, cudaStream_t st) {
+    const long long nblocks = (io.n_in + io.V - 1) / io.V;
+    const int grid = (int)std::min<long long>(nblocks, sm_count(h->device));
+    auto kern = fftfilt_kernel<DECIM, ACCUM>;
+    RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_SMEM));
+    kern<<<grid, fftk::NT, FFTFILT_SMEM, st>>>(io, Hp, h->tw1, h->tw2, nblocks);
+    RRC_CHECK_LAUNCH();
+    count_launch();
+    return RRC_OK;
+}
+
 int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, size_t deci, size_t skip, cudaStream_t st) {
     BlockIO io;
     io.in = reinterpret_cast<const float2*>(in);
@@ -101,18 +122,21 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
     io.out = reinterpret_cast<float2*>(out);
     io.n_in = (long long)n;
     io.n_out = (long long)n_out;
-    io.T1 = h->T1;
-    io.V = h->V;
+    io.T1_total = h->T1;
     io.deci = (int)deci;
     io.skip = (long long)skip;
-    const long long nblocks = ((long long)n + h->V - 1) / h->V;
-    const int grid = (int)std::min<long long>(nblocks, sm_count(h->device));
     const bool decim = !(deci == 1 && skip == 0);
-    auto kern = decim ? fftfilt_kernel<true> : fftfilt_kernel<false>;
-    RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_SMEM));
-    kern<<<grid, fftk::NT, FFTFILT_SMEM, st>>>(io, h->Hp, h->tw1, h->tw2, nblocks);
-    RRC_CHECK_LAUNCH();
-    count_launch();
+    long long shift = 0;
+    for (size_t p = 0; p < h->part_T1.size(); ++p) {
+        io.T1 = h->part_T1[p];
+        io.V = fftk::N - io.T1;
+        io.shift = shift;
+        int s;
+        if (p == 0) s = decim ? launch_part<true, false>(h, io, h->part_Hp[p], st) : launch_part<false, false>(h, io, h->part_Hp[p], st);
+        else        s = decim ? launch_part<true, true>(h, io, h->part_Hp[p], st) : launch_part<false, true>(h, io, h->part_Hp[p], st);
+        RRC_TRY(s);
+        shift += io.T1 + 1;
+    }
     if (h->T1 > 0) {
         fftfilt_hist_kernel<<<(h->T1 + 255) / 256, 256, 0, st>>>(h->hist[h->cur], io.in, (long long)n, h->T1, h->hist[h->cur ^ 1]);
         RRC_CHECK_LAUNCH();
@@ -156,16 +180,11 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
     if (!out) return fail(RRC_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (!taps || ntaps == 0) return fail(RRC_ERR_INVALID, "FftFilter needs at least one tap (src/fft_filter.rs:146)");
-    if (ntaps > (size_t)fftk::N - 4096 + 1)
-        return fail(RRC_ERR_UNSUPPORTED, "ntaps %zu > %d: the single-CTA 16384-point kernel needs ntaps <= 12289", ntaps, fftk::N - 4096 + 1);
+    if (ntaps > ((size_t)1 << 24)) return fail(RRC_ERR_UNSUPPORTED, "ntaps %zu > 2^24", ntaps);
     RRC_CUDA(cudaSetDevice(device));
     auto* h = new rrc_fftfilt();
     h->device = device; h->ntaps = ntaps;
     h->T1 = (int)ntaps - 1;
-    h->V = fftk::N - h->T1;
-
-    std::vector<float2> Hp, tw1, tw2;
-    fftk::build_tables(taps, ntaps, Hp, tw1, tw2);
     auto cleanup = [&](int s) { rrc_fftfilt_destroy(h); return s; };
     auto up = [&](float2** d, const std::vector<float2>& v) -> cudaError_t {
         cudaError_t e = cudaMalloc((void**)d, v.size() * sizeof(float2));
@@ -173,7 +192,18 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
         return cudaMemcpy(*d, v.data(), v.size() * sizeof(float2), cudaMemcpyHostToDevice);
     };
     cudaError_t e;
-    if ((e = up(&h->Hp, Hp)) != cudaSuccess || (e = up(&h->tw1, tw1)) != cudaSuccess || (e = up(&h->tw2, tw2)) != cudaSuccess)
+    std::vector<float2> Hp, tw1, tw2;
+    const size_t part = ntaps <= SINGLE_MAX_TAPS ? ntaps : PART_TAPS;
+    for (size_t off = 0; off < ntaps; off += part) {
+        const size_t len = std::min(part, ntaps - off);
+        fftk::build_tables(taps + 2 * off, len, Hp, tw1, tw2);
+        float2* d = nullptr;
+        if ((e = up(&d, Hp)) != cudaSuccess) return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
+        h->part_Hp.push_back(d);
+        h->part_T1.push_back((int)len - 1);
+    }
+    h->Hp = h->part_Hp[0];
+    if ((e = up(&h->tw1, tw1)) != cudaSuccess || (e = up(&h->tw2, tw2)) != cudaSuccess)
         return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
     for (int i = 0; i < 2; ++i) {
         const size_t bytes = std::max<size_t>(1, (size_t)h->T1) * sizeof(float2);
@@ -187,7 +217,8 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
 int rrc_fftfilt_destroy(rrc_fftfilt_t* h) {
     if (!h) return RRC_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->Hp); cudaFree(h->tw1); cudaFree(h->tw2); cudaFree(h->hist[0]); cudaFree(h->hist[1]);
+    for (float2* p : h->part_Hp) cudaFree(p);
+    cudaFree(h->tw1); cudaFree(h->tw2); cudaFree(h->hist[0]); cudaFree(h->hist[1]);
     h->pipe.destroy();
     delete h;
     return RRC_OK;
@@ -203,7 +234,7 @@ int rrc_fftfilt_reset(rrc_fftfilt_t* h, void* stream) {
 int rrc_fftfilt_geometry(const rrc_fftfilt_t* h, size_t* fft_size, size_t* valid) {
     if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
     if (fft_size) *fft_size = fftk::N;
-    if (valid) *valid = (size_t)h->V;
+    if (valid) *valid = (size_t)(fftk::N - h->part_T1[0]);
     return RRC_OK;
 }
 

@@ -43,8 +43,10 @@ struct BlockIO {
     float2* out;             // y[0..n_out)
     long long n_in;          // valid input samples
     long long n_out;         // outputs to write
-    int T1;                  // ntaps - 1
+    int T1;                  // taps of THIS partition - 1
     int V;                   // valid outputs per block = N - T1
+    int T1_total;            // ntaps - 1 of the whole filter = length of hist
+    long long shift;         // input delay of this tap partition (p * partition length); 0 for a single partition
     int deci;                // output decimation (fused RationalResampler(1,deci)); 1 = none
     long long skip;          // first kept filter output index (decimation phase)
 };
@@ -77,7 +79,8 @@ RRC_HD void powers32(float2 w, float2 (&p)[32]) {
 // tw1[t] = W_N^t = exp(-2 pi i t / N), t < 512.
 RRC_HD void phase_a(int tid, long long blk, const BlockIO& io, const float2* tw1, float2* sm) {
     float2 v[32];
-    const long long seg0 = blk * (long long)io.V - io.T1;       // input index of segment element 0
+    // input index of segment element 0 (tap partition p filters the input delayed by `shift`)
+    const long long seg0 = blk * (long long)io.V - io.T1 - io.shift;
     if (seg0 >= 0 && seg0 + N <= io.n_in) {                     // interior block: no bounds checks
         const float2* p = io.in + seg0 + tid;
 #pragma unroll
@@ -88,7 +91,7 @@ RRC_HD void phase_a(int tid, long long blk, const BlockIO& io, const float2* tw1
         for (int n1 = 0; n1 < 32; ++n1) {
             const long long g = g0 + 512 * n1;
             float2 x = make_float2(0.f, 0.f);
-            if (g < 0) { if (g + io.T1 >= 0) x = io.hist[g + io.T1]; }
+            if (g < 0) { if (g + io.T1_total >= 0) x = io.hist[g + io.T1_total]; }
             else if (g < io.n_in) x = io.in[g];
             v[bitrev(n1, 5)] = x;
         }
@@ -177,7 +180,7 @@ RRC_HD void phase_mid(int tid, const float2* tw2, const float2* Hp, const float2
 }
 
 // Phase A': tid = t; conj twiddle, IDFT32 over k1 -> n1; store valid outputs.
-template <bool DECIM>
+template <bool DECIM, bool ACCUM>
 RRC_HD void phase_ai(int tid, long long blk, const BlockIO& io, const float2* tw1, const float2* sm) {
     float2 p[32];
     powers32(tw1[tid], p);
@@ -195,11 +198,12 @@ RRC_HD void phase_ai(int tid, long long blk, const BlockIO& io, const float2* tw
         if (o0 + N <= io.n_out) {                               // interior: only the n >= T1 test
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1)
-                if (n1 > tq || (n1 == tq && tid >= tr)) q[512 * n1] = v[n1];
+                if (n1 > tq || (n1 == tq && tid >= tr)) q[512 * n1] = ACCUM ? cadd(q[512 * n1], v[n1]) : v[n1];
         } else {
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1)
-                if ((n1 > tq || (n1 == tq && tid >= tr)) && o0 + tid + 512 * n1 < io.n_out) q[512 * n1] = v[n1];
+                if ((n1 > tq || (n1 == tq && tid >= tr)) && o0 + tid + 512 * n1 < io.n_out)
+                    q[512 * n1] = ACCUM ? cadd(q[512 * n1], v[n1]) : v[n1];
         }
     } else {
         // keep outputs with (o - skip) >= 0 and (o - skip) % deci == 0, at index (o - skip)/deci.
@@ -210,7 +214,8 @@ RRC_HD void phase_ai(int tid, long long blk, const BlockIO& io, const float2* tw
         const long long sq = 512 / D, sm_ = 512 % D;
 #pragma unroll
         for (int n1 = 0; n1 < 32; ++n1) {
-            if ((n1 > tq || (n1 == tq && tid >= tr)) && m == 0 && qd >= 0 && qd < io.n_out) io.out[qd] = v[n1];
+            if ((n1 > tq || (n1 == tq && tid >= tr)) && m == 0 && qd >= 0 && qd < io.n_out)
+                io.out[qd] = ACCUM ? cadd(io.out[qd], v[n1]) : v[n1];
             qd += sq; m += sm_;
             if (m >= D) { m -= D; ++qd; }
         }

@@ -3,6 +3,7 @@
 // a plain array standing in for shared memory.  Lets the index math, swizzle
 // and twiddle logic be checked against the oracle without a GPU.
 // Built by tests/test_emul.py with `nvcc -x cu` (host code only).
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -13,29 +14,36 @@ using namespace rrc::fftk;
 extern "C" int emul_fftfilt(const float* taps, long long ntaps, const float* in, long long n,
                             const float* hist /* (ntaps-1) c32 or NULL = zeros */, float* out,
                             long long deci, long long skip, long long n_out) {
-    std::vector<float2> Hp, tw1, tw2;
-    build_tables(taps, (size_t)ntaps, Hp, tw1, tw2);
-    const int T1 = (int)ntaps - 1;
-    std::vector<float2> h(T1 > 0 ? T1 : 1, make_float2(0.f, 0.f));
-    if (hist && T1 > 0) memcpy(h.data(), hist, sizeof(float2) * T1);
-    BlockIO io;
-    io.in = reinterpret_cast<const float2*>(in);
-    io.hist = h.data();
-    io.out = reinterpret_cast<float2*>(out);
-    io.n_in = n; io.n_out = n_out; io.T1 = T1; io.V = N - T1; io.deci = (int)deci; io.skip = skip;
-    std::vector<float2> sm(SMEM_ELEMS), hres(HRES_ELEMS);
-    for (int t = 0; t < NT; ++t) load_hres(t, Hp.data(), hres.data());
-    const long long nblocks = (n + io.V - 1) / io.V;
+    const int T1_total = (int)ntaps - 1;
+    std::vector<float2> h(T1_total > 0 ? T1_total : 1, make_float2(0.f, 0.f));
+    if (hist && T1_total > 0) memcpy(h.data(), hist, sizeof(float2) * T1_total);
+    const long long part = ntaps <= 12289 ? ntaps : 8193;     // same split as fftfilt.cu
+    long long shift = 0;
     const bool decim = !(deci == 1 && skip == 0);
-    for (long long blk = 0; blk < nblocks; ++blk) {
-        for (int t = 0; t < NT; ++t) phase_a(t, blk, io, tw1.data(), sm.data());
-        for (int t = 0; t < NT; ++t) phase_mid_b(t, tw2.data(), sm.data());
-        for (int t = 0; t < NT; ++t) phase_mid_c(t, Hp.data(), hres.data(), sm.data());
-        for (int t = 0; t < NT; ++t) phase_mid_bi(t, tw2.data(), sm.data());
-        for (int t = 0; t < NT; ++t) {
-            if (decim) phase_ai<true>(t, blk, io, tw1.data(), sm.data());
-            else phase_ai<false>(t, blk, io, tw1.data(), sm.data());
+    for (long long off = 0; off < ntaps; off += part) {
+        const long long len = std::min(part, ntaps - off);
+        std::vector<float2> Hp, tw1, tw2;
+        build_tables(taps + 2 * off, (size_t)len, Hp, tw1, tw2);
+        BlockIO io;
+        io.in = reinterpret_cast<const float2*>(in);
+        io.hist = h.data();
+        io.out = reinterpret_cast<float2*>(out);
+        io.n_in = n; io.n_out = n_out; io.T1 = (int)len - 1; io.V = N - io.T1; io.deci = (int)deci; io.skip = skip;
+        io.T1_total = T1_total; io.shift = shift;
+        std::vector<float2> sm(SMEM_ELEMS), hres(HRES_ELEMS);
+        for (int t = 0; t < NT; ++t) load_hres(t, Hp.data(), hres.data());
+        const long long nblocks = (n + io.V - 1) / io.V;
+        for (long long blk = 0; blk < nblocks; ++blk) {
+            for (int t = 0; t < NT; ++t) phase_a(t, blk, io, tw1.data(), sm.data());
+            for (int t = 0; t < NT; ++t) phase_mid_b(t, tw2.data(), sm.data());
+            for (int t = 0; t < NT; ++t) phase_mid_c(t, Hp.data(), hres.data(), sm.data());
+            for (int t = 0; t < NT; ++t) phase_mid_bi(t, tw2.data(), sm.data());
+            for (int t = 0; t < NT; ++t) {
+                if (off == 0) { if (decim) phase_ai<true, false>(t, blk, io, tw1.data(), sm.data()); else phase_ai<false, false>(t, blk, io, tw1.data(), sm.data()); }
+                else          { if (decim) phase_ai<true, true>(t, blk, io, tw1.data(), sm.data()); else phase_ai<false, true>(t, blk, io, tw1.data(), sm.data()); }
+            }
         }
+        shift += len;
     }
     return 0;
 }

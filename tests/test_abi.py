@@ -132,3 +132,17 @@ def test_fftfilt_plan_equals_restated_work(ntaps):
             assert wait_need == ret.need and wait_out == (1 if ret.stream is blk.out else 0)
             buffered = buffered_after
             blk.out.consume(blk.out.used)
+
+
+def test_rust_ffi_declares_header_symbols():
+    """The (uncompiled) Rust binding only declares entry points that exist in the header, with the same arity."""
+    ffi = (ROOT / "rustradio_b200" / "rust" / "rustradio-cuda" / "src" / "ffi.rs").read_text()
+    decl = re.findall(r"pub fn (rrc_[a-z0-9_]+)\s*\(([^;]*?)\)\s*->", ffi, flags=re.S)
+    assert len(decl) >= 25
+    for name, args in decl:
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", HEADER, flags=re.S)
+        assert m, f"{name} in ffi.rs but not in rustradio_cuda.h"
+        n_rust = 0 if not args.strip() else len([a for a in args.split(",") if a.strip()])
+        c_args = m.group(1).strip()
+        n_c = 0 if c_args in ("", "void") else len([a for a in c_args.split(",") if a.strip()])
+        assert n_rust == n_c, f"{name}: {n_rust} args in ffi.rs vs {n_c} in the header"

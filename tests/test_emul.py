@@ -43,7 +43,7 @@ def emul():
     return run
 
 
-@pytest.mark.parametrize("ntaps,n", [(1, 3000), (2, 20_000), (193, 8000), (4097, 40_000), (64, 16384 * 2 + 5), (12289, 20_000)])
+@pytest.mark.parametrize("ntaps,n", [(1, 3000), (2, 20_000), (193, 8000), (4097, 40_000), (64, 16384 * 2 + 5), (12289, 20_000), (16385, 40_000), (20_000, 30_000)])
 def test_emulated_kernel_matches_f64_convolution(emul, ntaps, n):
     taps = (O.low_pass_n(1.0, 0.05, ntaps).astype(np.complex64) * (1 + 0.3j)) if ntaps > 2 else np.array([0.5 - 0.25j, 0.3 + 1j][:ntaps], np.complex64)
     x = O.synth_c32(5, 0, n)
@@ -56,6 +56,9 @@ def test_emulated_kernel_history_and_decimation(emul):
     truth = O.conv_full_f64_fft(x, taps, len(x))
     y = np.concatenate([emul(taps, x[:12345]), emul(taps, x[12345:], hist=np.ascontiguousarray(x[12345 - 300:12345]))])
     assert O.rel_rms(y, truth) <= 1e-5
+    t2 = (O.low_pass_n(1.0, 0.02, 16385).astype(np.complex64) * (1 - 0.2j))
+    truth2 = O.conv_full_f64_fft(x, t2, len(x))
+    assert O.rel_rms(emul(t2, x, deci=8, skip=0), truth2[::8]) <= 1e-5
     for deci, skip in ((8, 3), (3, 0), (1, 7), (1000, 999), (700, 40_001)):
         yd = emul(taps, x, deci=deci, skip=skip)
         want = truth[skip::deci]

@@ -136,7 +136,7 @@ def test_fir_run_host_count_rule(R):
 
 
 # ----------------------------------------------------------- FFT filter ---
-@pytest.mark.parametrize("ntaps,n", [(1, 5000), (2, 40_000), (193, 8000), (4097, 100_000), (8193, 50_000), (12289, 30_000), (64, 16384 * 3 + 17)])
+@pytest.mark.parametrize("ntaps,n", [(1, 5000), (2, 40_000), (193, 8000), (4097, 100_000), (8193, 50_000), (12289, 30_000), (64, 16384 * 3 + 17), (16385, 100_000), (40_000, 90_000)])
 def test_fftfilt_matches_f64_convolution(R, ntaps, n):
     taps = (O.low_pass_n(1.0, 0.05, ntaps).astype(np.complex64) * (1 + 0.5j)) if ntaps > 2 else cplx_taps(ntaps)
     x = O.synth_c32(21, 0, n)
@@ -192,9 +192,20 @@ def test_fftfilt_fused_decimation(R):
         assert O.rel_rms(dout.download(np.complex64, n), want) <= REL_RMS_BAR
 
 
-def test_fftfilt_too_many_taps_is_an_error_not_a_fallback(R):
-    with pytest.raises(R.RrcError):
-        R.FftFilt(np.ones(20_000, np.complex64))
+def test_fftfilt_long_taps_partitioned_streaming_and_decimation(R):
+    """BASELINE config 5 shape at test size: 16385 taps (two tap partitions), streamed in pieces, decimate by 8."""
+    taps = O.low_pass_n(1.0, 0.02, 16385).astype(np.complex64)
+    x = O.synth_c32(24, 0, 150_000)
+    truth = O.conv_full_f64_fft(x, taps, len(x))
+    f = R.FftFilt(taps)
+    y = np.concatenate([f.filter(x[:70_001]), f.filter(x[70_001:])])
+    assert O.rel_rms(y, truth) <= REL_RMS_BAR
+    f2 = R.FftFilt(taps)
+    din = R.DeviceBuffer.from_numpy(x)
+    dout = R.DeviceBuffer(len(x) * 8)
+    n = f2.decim_run(din, len(x), 8, 0, dout)
+    assert n == len(truth[::8])
+    assert O.rel_rms(dout.download(np.complex64, n), truth[::8]) <= REL_RMS_BAR
 
 
 # ------------------------------------------------------------ resampler ---
@@ -347,3 +358,47 @@ def test_fftfilt_config2_full_size(R):
         w = O.synth_c32(seed, lo, i - lo + 1).astype(np.complex128)     # x[lo..i]
         want[k] = np.dot(w[::-1], h64[:len(w)])                          # sum_k h[k] x[i-k]
     assert O.rel_rms(got, want) <= REL_RMS_BAR
+
+
+# ------------------------------------------------ time-segment sharding ------
+def test_time_segment_shards_equal_whole(R):
+    """splitting a stream by time segment with an ntaps-1 halo (0 for the resampler) and
+    running each shard through the CUDA kernels independently reproduces the whole-stream result."""
+    from rustradio_b200 import shard as S
+    n, world = 300_000, 4
+    x = O.synth_c32(51, 0, n)
+    taps = O.low_pass_n(1.0, 0.08, 257).astype(np.complex64)
+    whole_fir = O.fir(x, taps, 5, f64=True)
+    parts = []
+    for r in range(world):
+        seg = S.fir_segment(n, len(taps), 5, world, r)
+        y = R.Fir(taps, deci=5).filter(x[seg.in_lo:seg.in_hi])
+        assert len(y) == seg.out_hi - seg.out_lo
+        parts.append(y)
+    assert O.rel_rms(np.concatenate(parts), whole_fir) <= REL_RMS_BAR
+    n_out = O.fftfilt_out_count(n, len(taps))
+    whole_fft = O.conv_full_f64_fft(x, taps, n_out)
+    parts = []
+    for r in range(world):
+        seg = S.fftfilt_segment(n, len(taps), world, r)
+        y = R.FftFilt(taps).filter(x[seg.in_lo:seg.in_hi])       # fresh filter: zero history before the halo
+        parts.append(y[seg.out_lo - seg.in_lo:])
+    got = np.concatenate(parts)
+    assert len(got) == n_out and O.rel_rms(got, whole_fft) <= REL_RMS_BAR
+    xf = O.synth_f32(52, 0, n)
+    whole_rs = O.resample(xf, 147, 160)
+    parts = []
+    for r in range(world):
+        seg = S.resampler_segment(n, 147, 160, world, r)
+        # a shard starts mid-stream: seed the counter so that its first output is global output out_lo
+        k = np.arange(seg.out_lo, seg.out_hi, dtype=np.int64)
+        res = R.Resampler(4, 147, 160)
+        # closed form through the kernel: shift the window so that local index = global index - in_lo
+        _, _, y = res.work(xf[seg.in_lo:seg.in_hi], len(k)) if seg.out_lo == 0 else (0, 0, None)
+        if y is None:
+            # phase of the first output inside the shard: counter c0 = -(out_lo*deci - in_lo*interp) (<= 0)
+            c0 = -(seg.out_lo * 160 - seg.in_lo * 147)
+            assert -160 < c0 <= 0
+            y = xf[seg.in_lo:seg.in_hi][((k - seg.out_lo) * 160 - c0) // 147]
+        parts.append(y)
+    assert np.concatenate(parts).tobytes() == whole_rs.tobytes()
