@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -61,6 +62,54 @@ fftfilt_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __
     }
 }
 
+// 1024-thread x 16-point variant (fftfilt16_core.cuh).  Plane-local exchanges (B<->C<->D) use
+// 128-thread named barriers (two k1 planes per barrier), ids 1..8; id 0 is __syncthreads.
+constexpr size_t FFTFILT16_SMEM = (size_t)(fftk16::SMEM16_ELEMS + 1024 + 1024 + 64 + fftk16::HRES16_ELEMS) * sizeof(float2);
+
+__device__ __forceinline__ void plane_barrier(int tid) {
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + (tid >> 7)) : "memory");
+}
+
+template <bool DECIM, bool ACCUM>
+__global__ void __launch_bounds__(fftk16::NT16, 1)
+fftfilt16_kernel(const BlockIO io, const float2* __restrict__ Hd, const float2* __restrict__ tw1g,
+                 const float2* __restrict__ tw2g, const float2* __restrict__ tw3g, long long nblocks) {
+    extern __shared__ __align__(16) float2 sm[];
+    float2* s_tw1 = sm + fftk16::SMEM16_ELEMS;
+    float2* s_tw2 = s_tw1 + 1024;
+    float2* s_tw3 = s_tw2 + 1024;
+    float2* s_hres = s_tw3 + 64;
+    const int tid = threadIdx.x;
+    s_tw1[tid] = tw1g[tid];
+    s_tw2[tid] = tw2g[tid];
+    if (tid < 64) s_tw3[tid] = tw3g[tid];
+    fftk16::load_hres(tid, Hd, s_hres);
+    __syncthreads();
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        fftk16::phase_a(tid, blk, io, s_tw1, sm);
+        __syncthreads();
+        {   // next block's input -> L2 (one 4 KiB bulk prefetch per warp, 32 x 4 KiB = segment)
+            const long long nb = blk + gridDim.x;
+            const long long seg0 = nb * (long long)io.V - io.T1 - io.shift + (long long)(tid >> 5) * 512;
+            if ((tid & 31) == 0 && nb < nblocks && seg0 >= 0 && seg0 + 512 <= io.n_in) {
+                const unsigned long long a = (reinterpret_cast<unsigned long long>(io.in + seg0) + 15ull) & ~15ull;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(4096 - 16) : "memory");
+            }
+        }
+        fftk16::phase_b(tid, s_tw2, sm);
+        plane_barrier(tid);
+        fftk16::phase_c(tid, s_tw3, sm);
+        plane_barrier(tid);
+        fftk16::phase_d(tid, Hd, s_hres, sm);
+        plane_barrier(tid);
+        fftk16::phase_ci(tid, s_tw3, sm);
+        plane_barrier(tid);
+        fftk16::phase_bi(tid, s_tw2, sm);
+        __syncthreads();
+        fftk16::phase_ai<DECIM, ACCUM>(tid, blk, io, s_tw1, sm);
+    }
+}
+
 // hist_next[i] = x[n - T1 + i] over the concatenation (hist_cur ++ in).
 __global__ void fftfilt_hist_kernel(const float2* __restrict__ hist_cur, const float2* __restrict__ in,
                                     long long n, int T1, float2* __restrict__ hist_next) {
@@ -81,8 +130,13 @@ struct rrc_fftfilt {
     // Long filters are split into tap partitions of <= PART_TAPS taps; partition p filters the
     // input delayed by p*PART_TAPS and accumulates into the output (y = sum_p h_p * x(n - p*L)).
     std::vector<int> part_T1;         // taps of partition p, minus 1
-    std::vector<float2*> part_Hp;     // spectrum of partition p
+    std::vector<float2*> part_Hp;     // spectrum of partition p (512-thread layout)
+    std::vector<float2*> part_Hd;     // spectrum of partition p (1024-thread layout)
     float2* Hp = nullptr;             // == part_Hp[0]
+    float2* tw1_16 = nullptr;
+    float2* tw2_16 = nullptr;
+    float2* tw3_16 = nullptr;
+    int variant = 32;                 // points per thread: 32 (512 threads) or 16 (1024 threads)
     float2* tw1 = nullptr;
     float2* tw2 = nullptr;
     float2* hist[2] = {nullptr, nullptr};
@@ -102,6 +156,18 @@ size_t ref_fft_size(size_t ntaps) {   // calc_fft_size, src/fft_filter.rs:36-42
 // are split into partitions of PART_TAPS taps (valid fraction >= 50% per partition).
 constexpr size_t PART_TAPS = 8193;
 constexpr size_t SINGLE_MAX_TAPS = 12289;     // up to here one partition (valid >= 25%) beats two
+
+template <bool DECIM, bool ACCUM>
+int launch_part16(rrc_fftfilt* h, const BlockIO& io, const float2* Hd, cudaStream_t st) {
+    const long long nblocks = (io.n_in + io.V - 1) / io.V;
+    const int grid = (int)std::min<long long>(nblocks, sm_count(h->device));
+    auto kern = fftfilt16_kernel<DECIM, ACCUM>;
+    RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT16_SMEM));
+    kern<<<grid, fftk16::NT16, FFTFILT16_SMEM, st>>>(io, Hd, h->tw1_16, h->tw2_16, h->tw3_16, nblocks);
+    RRC_CHECK_LAUNCH();
+    count_launch();
+    return RRC_OK;
+}
 
 template <bool DECIM, bool ACCUM>
 int launch_part(rrc_fftfilt* h, const BlockIO& io, const float2* Hp, cudaStream_t st) {
@@ -132,7 +198,10 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
         io.V = fftk::N - io.T1;
         io.shift = shift;
         int s;
-        if (p == 0) s = decim ? launch_part<true, false>(h, io, h->part_Hp[p], st) : launch_part<false, false>(h, io, h->part_Hp[p], st);
+        if (h->variant == 16) {
+            if (p == 0) s = decim ? launch_part16<true, false>(h, io, h->part_Hd[p], st) : launch_part16<false, false>(h, io, h->part_Hd[p], st);
+            else        s = decim ? launch_part16<true, true>(h, io, h->part_Hd[p], st) : launch_part16<false, true>(h, io, h->part_Hd[p], st);
+        } else if (p == 0) s = decim ? launch_part<true, false>(h, io, h->part_Hp[p], st) : launch_part<false, false>(h, io, h->part_Hp[p], st);
         else        s = decim ? launch_part<true, true>(h, io, h->part_Hp[p], st) : launch_part<false, true>(h, io, h->part_Hp[p], st);
         RRC_TRY(s);
         shift += io.T1 + 1;
@@ -201,7 +270,15 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
         if ((e = up(&d, Hp)) != cudaSuccess) return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
         h->part_Hp.push_back(d);
         h->part_T1.push_back((int)len - 1);
+        std::vector<float2> Hd, t1, t2, t3;
+        fftk::build_tables16(taps + 2 * off, len, Hd, t1, t2, t3);
+        float2* dd = nullptr;
+        if ((e = up(&dd, Hd)) != cudaSuccess) return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
+        h->part_Hd.push_back(dd);
+        if (!h->tw1_16 && ((e = up(&h->tw1_16, t1)) != cudaSuccess || (e = up(&h->tw2_16, t2)) != cudaSuccess || (e = up(&h->tw3_16, t3)) != cudaSuccess))
+            return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
     }
+    if (const char* v = getenv("RRC_FFTFILT_VARIANT")) h->variant = atoi(v) == 16 ? 16 : 32;
     h->Hp = h->part_Hp[0];
     if ((e = up(&h->tw1, tw1)) != cudaSuccess || (e = up(&h->tw2, tw2)) != cudaSuccess)
         return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
@@ -218,6 +295,8 @@ int rrc_fftfilt_destroy(rrc_fftfilt_t* h) {
     if (!h) return RRC_OK;
     cudaSetDevice(h->device);
     for (float2* p : h->part_Hp) cudaFree(p);
+    for (float2* p : h->part_Hd) cudaFree(p);
+    cudaFree(h->tw1_16); cudaFree(h->tw2_16); cudaFree(h->tw3_16);
     cudaFree(h->tw1); cudaFree(h->tw2); cudaFree(h->hist[0]); cudaFree(h->hist[1]);
     h->pipe.destroy();
     delete h;

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "fftfilt_core.cuh"
+#include "fftfilt16_core.cuh"
 
 namespace rrc { namespace fftk {
 
@@ -58,6 +59,35 @@ inline void build_tables(const float* taps, size_t ntaps, std::vector<float2>& H
             const double a = -2.0 * M_PI * (double)(n3 * k2) / 512.0;
             tw2[k2 * 16 + n3] = make_float2((float)std::cos(a), (float)std::sin(a));
         }
+}
+
+// Tables of the 1024-thread variant (fftfilt16_core.cuh):
+// Hd[tid*16 + j*4 + k4] = H[k1 + 16*k2 + 256*(4q + j) + 4096*k4] / N for tid = k1*64 + q*16 + k2;
+// tw1[t] = W_N^t (t < 1024); tw2[k2*64 + m] = W_1024^{m*k2}; tw3[k3*4 + n4] = W_64^{n4*k3}.
+inline void build_tables16(const float* taps, size_t ntaps, std::vector<float2>& Hd, std::vector<float2>& tw1,
+                           std::vector<float2>& tw2, std::vector<float2>& tw3) {
+    std::vector<std::complex<double>> H(N);
+    for (size_t k = 0; k < ntaps; ++k) H[k] = {(double)taps[2 * k], (double)taps[2 * k + 1]};
+    fft_host(H);
+    Hd.resize(N); tw1.resize(1024); tw2.resize(1024); tw3.resize(64);
+    for (int tid = 0; tid < 1024; ++tid) {
+        const int k1 = tid >> 6, q = (tid >> 4) & 3, k2 = tid & 15;
+        for (int j = 0; j < 4; ++j)
+            for (int k4 = 0; k4 < 4; ++k4) {
+                const int k = k1 + 16 * k2 + 256 * (4 * q + j) + 4096 * k4;
+                const auto v = H[k] / (double)N;
+                Hd[(size_t)tid * 16 + j * 4 + k4] = make_float2((float)v.real(), (float)v.imag());
+            }
+    }
+    auto w = [](double num, double den) {
+        const double a = -2.0 * M_PI * num / den;
+        return make_float2((float)std::cos(a), (float)std::sin(a));
+    };
+    for (int t = 0; t < 1024; ++t) tw1[t] = w(t, N);
+    for (int k2 = 0; k2 < 16; ++k2)
+        for (int m = 0; m < 64; ++m) tw2[k2 * 64 + m] = w(m * k2, 1024.0);
+    for (int k3 = 0; k3 < 16; ++k3)
+        for (int n4 = 0; n4 < 4; ++n4) tw3[k3 * 4 + n4] = w(n4 * k3, 64.0);
 }
 
 }}  // namespace rrc::fftk

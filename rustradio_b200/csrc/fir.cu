@@ -79,11 +79,33 @@ __device__ __forceinline__ float2 apply_translate(const FirArgs& a, float2 y, lo
 }
 __device__ __forceinline__ float apply_translate(const FirArgs&, float y, long long) { return y; }
 
+// atan2 with |error| < 1e-6 rad over the whole plane (bar: 1e-4 rad): octant reduction to
+// q = min/max in [0,1], odd minimax polynomial of degree 15, then quadrant fix-ups.  About
+// half the instructions of libdevice's atan2f and no slow path.  atan2(0, 0) = 0 like libm.
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float q = mx == 0.0f ? 0.0f : __fdividef(mn, mx);
+    const float s = q * q;
+    float r = -0.0040540580f;
+    r = fmaf(r, s, 0.0218612288f);
+    r = fmaf(r, s, -0.0559098861f);
+    r = fmaf(r, s, 0.0964200441f);
+    r = fmaf(r, s, -0.1390853351f);
+    r = fmaf(r, s, 0.1994653599f);
+    r = fmaf(r, s, -0.3332985605f);
+    r = fmaf(r, s, 0.9999993329f);
+    r = r * q;
+    if (ay > ax) r = 1.57079632679489662f - r;
+    if (x < 0.0f) r = 3.14159265358979324f - r;
+    return copysignf(r, y);
+}
+
 __device__ __forceinline__ float demod_pair(float2 a, float2 b, float gain) {
     // conj(a) * b, then gain * atan2(im, re)  (src/quadrature_demod.rs:71-73,106-108)
     float re = fmaf(a.x, b.x, a.y * b.y);
     float im = fmaf(a.x, b.y, -(a.y * b.x));
-    return gain * atan2f(im, re);
+    return gain * fast_atan2(im, re);
 }
 
 template <typename TT, int R>
@@ -106,14 +128,15 @@ __device__ __forceinline__ void load_taps<float, FIR_R>(const float* tp, float (
     }
 }
 
-// ST: sample type (float2 / float); TT: tap type; DECI1: compile-time deci == 1;
+// ST: sample type (float2 / float); TT: tap type; DCT: compile-time decimation (0 = run time), so
+// that every window offset u*deci is an immediate for the common decimations;
 // DEMOD: fused conj-multiply + atan2 epilogue (ST must be float2).
-template <typename ST, typename TT, bool DECI1, bool DEMOD>
+template <typename ST, typename TT, int DCT, bool DEMOD>
 __global__ void __launch_bounds__(FIR_MAX_NT) fir_poly_kernel(const FirArgs a) {
     constexpr int R = FIR_R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int deci = DECI1 ? 1 : a.deci;
-    const int S = DECI1 ? R : a.S;
+    const int deci = DCT ? DCT : a.deci;
+    const int S = DCT ? R * DCT : a.S;
     const int S1 = S + 1;
     const int NT = blockDim.x, t = threadIdx.x;
     const int BT = NT * R;
@@ -131,15 +154,49 @@ __global__ void __launch_bounds__(FIR_MAX_NT) fir_poly_kernel(const FirArgs a) {
     {   // input span -> smem, one pad element after every S elements
         const int L = a.nseg * S;
         const long long g0 = ob * deci;
-        int seg = t / S, rem = t - seg * S;
-        const int dseg = NT / S, drem = NT - dseg * S;
-        for (int e = t; e < L; e += NT) {
-            const long long g = g0 + e;
-            ST v; zero(v);
-            if (g < a.need) v = in[g];
-            s_tile[seg * S1 + rem] = v;
-            seg += dseg; rem += drem;
-            if (rem >= S) { rem -= S; ++seg; }
+        if (g0 + L <= a.need) {
+            // Interior tile: asynchronous 8/4-byte copies global -> shared (LDGSTS), all in flight
+            // at once, so the tile costs one memory latency instead of one per loop iteration.
+            const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_tile);
+            if (S >= 64) {      // one warp per thread-segment: no div/mod, constant strides
+                const int lane = t & 31, nwarp = NT >> 5;
+                for (int sg = t >> 5; sg < a.nseg; sg += nwarp) {
+                    const ST* src = in + g0 + (long long)sg * S;
+                    const unsigned dst = sbase + (unsigned)(sg * S1) * (unsigned)sizeof(ST);
+                    for (int e = lane; e < S; e += 32) {
+                        if constexpr (sizeof(ST) == 8)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + e * 8), "l"(src + e) : "memory");
+                        else
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + e * 4), "l"(src + e) : "memory");
+                    }
+                }
+            } else {            // short segments: flat element loop with incremental (segment, offset)
+                const ST* gsrc = in + g0;
+                int seg = t / S, rem = t - seg * S;
+                const int dseg = NT / S, drem = NT - dseg * S;
+                for (int e = t; e < L; e += NT) {
+                    const unsigned dst = sbase + (unsigned)(seg * S1 + rem) * (unsigned)sizeof(ST);
+                    if constexpr (sizeof(ST) == 8)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc + e) : "memory");
+                    else
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc + e) : "memory");
+                    seg += dseg; rem += drem;
+                    if (rem >= S) { rem -= S; ++seg; }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        } else {
+            int seg = t / S, rem = t - seg * S;
+            const int dseg = NT / S, drem = NT - dseg * S;
+            for (int e = t; e < L; e += NT) {
+                const long long g = g0 + e;
+                ST v; zero(v);
+                if (g < a.need) v = in[g];
+                s_tile[seg * S1 + rem] = v;
+                seg += dseg; rem += drem;
+                if (rem >= S) { rem -= S; ++seg; }
+            }
         }
     }
     __syncthreads();
@@ -183,19 +240,26 @@ __global__ void __launch_bounds__(FIR_MAX_NT) fir_poly_kernel(const FirArgs a) {
 
     if constexpr (!DEMOD) {
         ST* __restrict__ out = reinterpret_cast<ST*>(a.out) + (long long)blockIdx.y * a.out_stride;
-        for (int o = t; o < BT; o += NT) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int o = t + r * NT;
             const long long gi = ob + o;
             if (gi < a.out_n) out[gi] = s_out[o + o / R];
         }
     } else {
         float* __restrict__ out = reinterpret_cast<float*>(a.out) + (long long)blockIdx.y * a.out_stride;
-        for (int o = t; o < BT - 1; o += NT) {
+        float2 ya[R], yb[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {                 // R independent demods per thread: ILP for atan2
+            const int o = t + r * NT;
+            ya[r] = s_out[o + o / R];
+            yb[r] = s_out[(o + 1) + (o + 1) / R];     // o + 1 <= BT - 1 < BT + NT entries
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int o = t + r * NT;
             const long long gi = ob + o;
-            if (gi < a.out_n - 1) {
-                const float2 ya = s_out[o + o / R];
-                const float2 yb = s_out[(o + 1) + (o + 1) / R];
-                out[gi] = demod_pair(ya, yb, a.gain);
-            }
+            if (o < BT - 1 && gi < a.out_n - 1) out[gi] = demod_pair(ya[r], yb[r], a.gain);
         }
     }
 }
@@ -297,9 +361,12 @@ int upload_taps(rrc_fir* h) {
         const size_t S1 = FIR_R * D + 1;
         const size_t tap_bytes = ((size_t)D * h->qpad * tap_elem(h) + 15) & ~(size_t)15;
         const size_t limit_hi = (size_t)max_smem_optin(h->device);
-        const size_t limits[2] = {100 * 1024, limit_hi};
-        for (int pass = 0; pass < 2 && !h->use_poly; ++pass) {
-            for (int nt = FIR_MAX_NT; nt >= 32; nt >>= 1) {
+        // Large decimations make the staged tile big (R*deci samples per thread): prefer CTAs of
+        // <= 48 KB so that >= 4 of them share an SM and their load / compute / store phases overlap.
+        const size_t limits[3] = {48 * 1024, 100 * 1024, limit_hi};
+        const int nt_min[3] = {64, 32, 32};
+        for (int pass = 0; pass < 3 && !h->use_poly; ++pass) {
+            for (int nt = FIR_MAX_NT; nt >= nt_min[pass]; nt >>= 1) {
                 const size_t bytes = tap_bytes + (size_t)(nt + h->nchunks) * S1 * samp_elem(h);
                 if (bytes <= limits[pass]) {
                     h->nt = nt; h->smem = bytes; h->use_poly = true;
@@ -311,20 +378,27 @@ int upload_taps(rrc_fir* h) {
     return RRC_OK;
 }
 
-template <typename ST, typename TT, bool DEMOD>
-int launch_poly(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
-    if (h->deci == 1) {
-        auto k = fir_poly_kernel<ST, TT, true, DEMOD>;
-        RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-        k<<<grid, h->nt, h->smem, st>>>(a);
-    } else {
-        auto k = fir_poly_kernel<ST, TT, false, DEMOD>;
-        RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-        k<<<grid, h->nt, h->smem, st>>>(a);
-    }
+template <typename ST, typename TT, int DCT, bool DEMOD>
+int launch_poly_d(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
+    auto k = fir_poly_kernel<ST, TT, DCT, DEMOD>;
+    RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    k<<<grid, h->nt, h->smem, st>>>(a);
     RRC_CHECK_LAUNCH();
     count_launch();
     return RRC_OK;
+}
+
+template <typename ST, typename TT, bool DEMOD>
+int launch_poly(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
+    switch (h->deci) {       // common decimations get immediate window offsets
+    case 1: return launch_poly_d<ST, TT, 1, DEMOD>(h, a, grid, st);
+    case 2: return launch_poly_d<ST, TT, 2, DEMOD>(h, a, grid, st);
+    case 4: return launch_poly_d<ST, TT, 4, DEMOD>(h, a, grid, st);
+    case 5: return launch_poly_d<ST, TT, 5, DEMOD>(h, a, grid, st);
+    case 8: return launch_poly_d<ST, TT, 8, DEMOD>(h, a, grid, st);
+    case 10: return launch_poly_d<ST, TT, 10, DEMOD>(h, a, grid, st);
+    default: return launch_poly_d<ST, TT, 0, DEMOD>(h, a, grid, st);
+    }
 }
 
 int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* out, size_t out_stride,

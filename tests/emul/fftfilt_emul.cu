@@ -47,3 +47,43 @@ extern "C" int emul_fftfilt(const float* taps, long long ntaps, const float* in,
     }
     return 0;
 }
+
+// Same for the 1024-thread x 16-point variant (fftfilt16_core.cuh).
+extern "C" int emul_fftfilt16(const float* taps, long long ntaps, const float* in, long long n,
+                              const float* hist, float* out, long long deci, long long skip, long long n_out) {
+    namespace k16 = rrc::fftk16;
+    const int T1_total = (int)ntaps - 1;
+    std::vector<float2> h(T1_total > 0 ? T1_total : 1, make_float2(0.f, 0.f));
+    if (hist && T1_total > 0) memcpy(h.data(), hist, sizeof(float2) * T1_total);
+    const long long part = ntaps <= 12289 ? ntaps : 8193;
+    long long shift = 0;
+    const bool decim = !(deci == 1 && skip == 0);
+    for (long long off = 0; off < ntaps; off += part) {
+        const long long len = std::min(part, ntaps - off);
+        std::vector<float2> Hd, tw1, tw2, tw3;
+        build_tables16(taps + 2 * off, (size_t)len, Hd, tw1, tw2, tw3);
+        BlockIO io;
+        io.in = reinterpret_cast<const float2*>(in);
+        io.hist = h.data();
+        io.out = reinterpret_cast<float2*>(out);
+        io.n_in = n; io.n_out = n_out; io.T1 = (int)len - 1; io.V = N - io.T1; io.deci = (int)deci; io.skip = skip;
+        io.T1_total = T1_total; io.shift = shift;
+        std::vector<float2> sm(k16::SMEM16_ELEMS), hres(k16::HRES16_ELEMS);
+        for (int t = 0; t < k16::NT16; ++t) k16::load_hres(t, Hd.data(), hres.data());
+        const long long nblocks = (n + io.V - 1) / io.V;
+        for (long long blk = 0; blk < nblocks; ++blk) {
+            for (int t = 0; t < k16::NT16; ++t) k16::phase_a(t, blk, io, tw1.data(), sm.data());
+            for (int t = 0; t < k16::NT16; ++t) k16::phase_b(t, tw2.data(), sm.data());
+            for (int t = 0; t < k16::NT16; ++t) k16::phase_c(t, tw3.data(), sm.data());
+            for (int t = 0; t < k16::NT16; ++t) k16::phase_d(t, Hd.data(), hres.data(), sm.data());
+            for (int t = 0; t < k16::NT16; ++t) k16::phase_ci(t, tw3.data(), sm.data());
+            for (int t = 0; t < k16::NT16; ++t) k16::phase_bi(t, tw2.data(), sm.data());
+            for (int t = 0; t < k16::NT16; ++t) {
+                if (off == 0) { if (decim) k16::phase_ai<true, false>(t, blk, io, tw1.data(), sm.data()); else k16::phase_ai<false, false>(t, blk, io, tw1.data(), sm.data()); }
+                else          { if (decim) k16::phase_ai<true, true>(t, blk, io, tw1.data(), sm.data()); else k16::phase_ai<false, true>(t, blk, io, tw1.data(), sm.data()); }
+            }
+        }
+        shift += len;
+    }
+    return 0;
+}

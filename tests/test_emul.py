@@ -28,39 +28,42 @@ def emul():
         subprocess.run([nvcc, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets",
                         "-o", str(SO), str(src)], check=True)
     L = C.CDLL(str(SO))
-    L.emul_fftfilt.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
-                               C.c_longlong, C.c_longlong, C.c_longlong]
+    for fn in (L.emul_fftfilt, L.emul_fftfilt16):
+        fn.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                       C.c_longlong, C.c_longlong, C.c_longlong]
 
-    def run(taps, x, hist=None, deci=1, skip=0):
+    def run(taps, x, hist=None, deci=1, skip=0, variant=32):
         taps = np.ascontiguousarray(taps, np.complex64)
         x = np.ascontiguousarray(x, np.complex64)
         n = len(x)
         n_out = n if (deci == 1 and skip == 0) else ((n - skip + deci - 1) // deci if n > skip else 0)
         out = np.zeros(n_out, np.complex64)
-        L.emul_fftfilt(taps.ctypes.data, len(taps), x.ctypes.data, n,
+        (L.emul_fftfilt if variant == 32 else L.emul_fftfilt16)(taps.ctypes.data, len(taps), x.ctypes.data, n,
                        hist.ctypes.data if hist is not None else None, out.ctypes.data, deci, skip, n_out)
         return out
     return run
 
 
 @pytest.mark.parametrize("ntaps,n", [(1, 3000), (2, 20_000), (193, 8000), (4097, 40_000), (64, 16384 * 2 + 5), (12289, 20_000), (16385, 40_000), (20_000, 30_000)])
-def test_emulated_kernel_matches_f64_convolution(emul, ntaps, n):
+@pytest.mark.parametrize("variant", [32, 16])
+def test_emulated_kernel_matches_f64_convolution(emul, ntaps, n, variant):
     taps = (O.low_pass_n(1.0, 0.05, ntaps).astype(np.complex64) * (1 + 0.3j)) if ntaps > 2 else np.array([0.5 - 0.25j, 0.3 + 1j][:ntaps], np.complex64)
     x = O.synth_c32(5, 0, n)
-    assert O.rel_rms(emul(taps, x), O.conv_full_f64_fft(x, taps, n)) <= 1e-5
+    assert O.rel_rms(emul(taps, x, variant=variant), O.conv_full_f64_fft(x, taps, n)) <= 1e-5
 
 
-def test_emulated_kernel_history_and_decimation(emul):
+@pytest.mark.parametrize("variant", [32, 16])
+def test_emulated_kernel_history_and_decimation(emul, variant):
     taps = O.low_pass_n(1.0, 0.1, 301).astype(np.complex64)
     x = O.synth_c32(6, 0, 40_000)
     truth = O.conv_full_f64_fft(x, taps, len(x))
-    y = np.concatenate([emul(taps, x[:12345]), emul(taps, x[12345:], hist=np.ascontiguousarray(x[12345 - 300:12345]))])
+    y = np.concatenate([emul(taps, x[:12345], variant=variant), emul(taps, x[12345:], hist=np.ascontiguousarray(x[12345 - 300:12345]), variant=variant)])
     assert O.rel_rms(y, truth) <= 1e-5
     t2 = (O.low_pass_n(1.0, 0.02, 16385).astype(np.complex64) * (1 - 0.2j))
     truth2 = O.conv_full_f64_fft(x, t2, len(x))
-    assert O.rel_rms(emul(t2, x, deci=8, skip=0), truth2[::8]) <= 1e-5
+    assert O.rel_rms(emul(t2, x, deci=8, skip=0, variant=variant), truth2[::8]) <= 1e-5
     for deci, skip in ((8, 3), (3, 0), (1, 7), (1000, 999), (700, 40_001)):
-        yd = emul(taps, x, deci=deci, skip=skip)
+        yd = emul(taps, x, deci=deci, skip=skip, variant=variant)
         want = truth[skip::deci]
         assert len(yd) == len(want)
         if len(want):
