@@ -58,7 +58,12 @@ def cfg_c4():
                 desc="RationalResampler 147/160 on 2^30 f32 samples")
 
 
-CONFIGS = {"c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4}
+def cfg_c5():
+    return dict(name="c5", op="fftfilt_decim", ntaps=16385, deci=8, n=1 << 30, cutoff=0.05, dtype="c32",
+                desc="wideband: one 2^30-sample c32 capture per GPU, 16385-tap FftFilter + decimate-by-8 fused")
+
+
+CONFIGS = {"c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4, "c5": cfg_c5}
 
 
 def low_pass_taps(ntaps: int, cutoff: float) -> np.ndarray:
@@ -84,7 +89,7 @@ def taps_for(cfg):
 
 def alg_bytes(cfg, n_in, n_out):
     """algorithmic bytes per step."""
-    if cfg["op"] in ("fir", "fftfilt"):
+    if cfg["op"] in ("fir", "fftfilt", "fftfilt_decim"):
         return 8 * n_in + 8 * n_out
     if cfg["op"] == "fir_demod":
         return 8 * n_in + 4 * n_out
@@ -166,7 +171,38 @@ def run_gpu(args):
 
     # ---- build the op and its device-resident input ----
     op = cfg["op"]
-    if op == "fftfilt":
+    scaling = "weak"
+    if op == "fftfilt" and args.shard == "time" and world > 1:
+        # ONE 2^28-sample capture split by time segment across the ranks (strong scaling): rank r
+        # filters outputs [lo, hi) and receives its left halo (ntaps-1 samples) from rank r-1 over
+        # NVLink (NCCL send/recv) every step; the halo becomes the filter's carried history.
+        from rustradio_b200 import shard as S
+        n = cfg["n"]
+        f = R.FftFilt(taps_for(cfg), device=dev)
+        seg = S.fftfilt_segment(n, cfg["ntaps"], world, rank)
+        n_in = n_out = seg.out_hi - seg.out_lo
+        T1 = cfg["ntaps"] - 1
+        din = torch.empty(2 * n_in, dtype=torch.float32, device=f"cuda:{dev}")
+        dout = torch.empty(2 * n_out, dtype=torch.float32, device=f"cuda:{dev}")
+        halo = torch.zeros(2 * T1, dtype=torch.float32, device=f"cuda:{dev}")
+        seed = SEED + int(cfg["name"][1])                  # one capture: same seed on every rank
+        R.synth_f32(din, seed, 2 * seg.out_lo, 2 * n_in, dev, stream)
+        tail = din[2 * (n_in - T1):]
+
+        def step():
+            ops = []
+            if rank + 1 < world:
+                ops.append(dist.P2POp(dist.isend, tail, rank + 1))
+            if rank > 0:
+                ops.append(dist.P2POp(dist.irecv, halo, rank - 1))
+            for w in (dist.batch_isend_irecv(ops) if ops else []):
+                w.wait()
+            f.set_history(halo, T1, stream)                # rank 0: zeros = the stream's initial state
+            f.run(din, n_in, dout, stream)
+        launches_per_step = 2
+        units = n_in
+        scaling = "strong"
+    elif op == "fftfilt":
         n = cfg["n"]
         f = R.FftFilt(taps_for(cfg), device=dev)
         n_in = (n // f.nsamples) * f.nsamples            # reference count rule (whole blocks)
@@ -178,6 +214,19 @@ def run_gpu(args):
         def step():
             f.run(din, n_in, dout, stream)
         launches_per_step = 2
+        units = n_in
+    elif op == "fftfilt_decim":
+        n = cfg["n"]
+        f = R.FftFilt(taps_for(cfg), device=dev)
+        n_in = (n // f.nsamples) * f.nsamples
+        n_out = (n_in + cfg["deci"] - 1) // cfg["deci"]
+        din = torch.empty(2 * n, dtype=torch.float32, device=f"cuda:{dev}")
+        dout = torch.empty(2 * n_out, dtype=torch.float32, device=f"cuda:{dev}")
+        R.synth_f32(din, seed, 0, 2 * n, dev, stream)
+
+        def step():
+            assert f.decim_run(din, n_in, cfg["deci"], 0, dout, stream) == n_out
+        launches_per_step = 3
         units = n_in
     elif op == "fir":
         n = cfg["n"]
@@ -252,11 +301,16 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     ms_per_step = ms_max / args.steps
-    value = units * world / (ms_per_step * 1e-3) / 1e6      # Msamples/s, whole job
+    if scaling == "strong":
+        tot = torch.tensor([float(units)], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(tot)
+        value = float(tot.item()) / (ms_per_step * 1e-3) / 1e6
+    else:
+        value = units * world / (ms_per_step * 1e-3) / 1e6      # Msamples/s, whole job
 
     # ---- end to end: host buffers through *_run_host ----
     e2e = None
-    if not args.no_e2e and op in ("fftfilt", "fir"):
+    if not args.no_e2e and op in ("fftfilt", "fir") and scaling == "weak":
         hin = R.PinnedBuffer(np.complex64, cfg["n"])
         hout = R.PinnedBuffer(np.complex64, n_out)
         R.lib().rrc_memcpy_d2h(dev, hin.ptr, din.data_ptr(), cfg["n"] * 8, stream)
@@ -303,22 +357,24 @@ def run_gpu(args):
         traffic = json.loads(traffic_path.read_text()).get(cfg["name"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
-                "kernel": {"fftfilt": "fftfilt_kernel", "fir": "fir_poly_kernel", "fir_demod": "fir_poly_kernel<DEMOD>", "resample": "resample_kernel"}[op],
+                "kernel": {"fftfilt": "fftfilt_kernel", "fir": "fir_poly_kernel", "fir_demod": "fir_poly_kernel<DEMOD>", "resample": "resample_kernel",
+                           "fftfilt_decim": "fftfilt_kernel<DECIM> x2 tap partitions"}[op],
                 "duration_ms": ms_per_step,
                 "note": "duration = CUDA-event time of the whole step on the launching stream / steps; the step is this one kernel"
                         + (" plus a <3 us history-update kernel" if op == "fftfilt" else "")}
 
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and op != "fftfilt_decim":
         cpu = cpu_baseline(cfg, threads=1, budget_s=args.cpu_budget)
 
     line = {
         "metric": "Msamples/s (c32) FIR/FftFilter/resampler at 1/2/4/8 B200; % of roofline",
         "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f32" if cfg["dtype"] == "f32" else "c32 (complex f32)", "data": "synthetic",
         "config": {"workload": cfg["desc"], "name": cfg["name"], "samples_per_gpu_per_step": int(units),
-                   "outputs_per_gpu_per_step": int(n_out), "parallelism": f"independent stream per GPU x{world}",
+                   "outputs_per_gpu_per_step": int(n_out), "parallelism": (f"independent stream per GPU x{world}" if scaling == "weak" else
+                                   f"one capture, time-segment sharded x{world}, (ntaps-1)-sample halo by NCCL P2P"),
                    "l2_policy": "inputs larger than L2 (>= 0.5 GiB per step vs 126 MB L2)" if ab > 4e8 else "input 128 MiB ~ L2 size; see DESIGN.md",
                    "timer": "torch.cuda.Event on the launching stream, max over ranks"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -364,7 +420,7 @@ def cpu_baseline(cfg, threads: int, budget_s: float):
         while True:
             list(ex.map(fn, range(threads)))
             reps += 1
-            if time.perf_counter() - t0 >= budget_s or reps >= 64:
+            if time.perf_counter() - t0 >= budget_s or reps >= 4096:
                 break
     dt = time.perf_counter() - t0
     return {"value": per * threads * reps / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
@@ -407,6 +463,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--shard", default="capture", choices=["capture", "time"],
+                    help="N>1: independent capture per GPU (weak, default) or one capture split by time segment with halo exchange (strong)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)

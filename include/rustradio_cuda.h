@@ -150,6 +150,10 @@ typedef struct rrc_fftfilt rrc_fftfilt_t;
 int rrc_fftfilt_c32_create(int device, const float* taps_c32, size_t ntaps, rrc_fftfilt_t** out);
 int rrc_fftfilt_destroy(rrc_fftfilt_t* h);
 int rrc_fftfilt_reset(rrc_fftfilt_t* h, void* stream);          /* zero the carried history */
+/* Load the carried history (the ntaps-1 samples that precede the next run's input) from a
+ * device buffer: the left halo of a time-segment shard, e.g. received from the neighbouring
+ * GPU over NVLink.  n_samples must be ntaps-1. */
+int rrc_fftfilt_set_history(rrc_fftfilt_t* h, const float* hist_dev_c32, size_t n_samples, void* stream);
 /* calc_fft_size and nsamples exactly as the reference (src/fft_filter.rs:36-42,262-263). */
 int rrc_fftfilt_ref_fft_size(size_t ntaps, size_t* fft_size, size_t* nsamples);
 /* Device-side geometry actually used (FFT size, valid outputs per block). */

@@ -78,6 +78,7 @@ _SIGS = {
     "rrc_fftfilt_c32_create": [_i, _vp, _sz, _P(_vp)],
     "rrc_fftfilt_destroy": [_vp],
     "rrc_fftfilt_reset": [_vp, _vp],
+    "rrc_fftfilt_set_history": [_vp, _vp, _sz, _vp],
     "rrc_fftfilt_ref_fft_size": [_sz, _P(_sz), _P(_sz)],
     "rrc_fftfilt_geometry": [_vp, _P(_sz), _P(_sz)],
     "rrc_fftfilt_plan": [_sz, _sz, _sz, _sz, _P(_sz), _P(_sz), _P(_sz), _P(_sz), _P(_i)],
@@ -363,6 +364,9 @@ class FftFilt:
 
     def reset(self, stream: int = 0):
         _ck(lib().rrc_fftfilt_reset(self.h, stream))
+
+    def set_history(self, d_hist, n: int, stream: int = 0):
+        _ck(lib().rrc_fftfilt_set_history(self.h, _ptr(d_hist), n, stream))
 
     def run(self, d_in, n: int, d_out, stream: int = 0):
         _ck(lib().rrc_fftfilt_run(self.h, _ptr(d_in), n, _ptr(d_out), stream))

@@ -310,6 +310,16 @@ int rrc_fftfilt_reset(rrc_fftfilt_t* h, void* stream) {
     return RRC_OK;
 }
 
+int rrc_fftfilt_set_history(rrc_fftfilt_t* h, const float* hist, size_t n, void* stream) {
+    if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
+    if (n != (size_t)h->T1) return fail(RRC_ERR_INVALID, "history must be ntaps-1 = %d samples, got %zu", h->T1, n);
+    if (n == 0) return RRC_OK;
+    if (!hist) return fail(RRC_ERR_INVALID, "hist is NULL");
+    RRC_CUDA(cudaSetDevice(h->device));
+    RRC_CUDA(cudaMemcpyAsync(h->hist[h->cur], hist, n * sizeof(float2), cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return RRC_OK;
+}
+
 int rrc_fftfilt_geometry(const rrc_fftfilt_t* h, size_t* fft_size, size_t* valid) {
     if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
     if (fft_size) *fft_size = fftk::N;

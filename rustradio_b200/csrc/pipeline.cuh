@@ -2,6 +2,8 @@
 // *_run_host entry points (the end-to-end path: host buffers in, host buffers
 // out, copies overlapped with compute on three CUDA streams).
 #pragma once
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rrc {
@@ -89,7 +91,18 @@ struct Pipe {
     }
 };
 
-// Samples per host-pipeline chunk (bytes = this * element size).
-constexpr size_t PIPE_CHUNK_SAMPLES = (size_t)1 << 23;
+// Samples per host-pipeline chunk (bytes = this * element size).  RRC_PIPE_CHUNK_LOG2 overrides
+// the default 2^23 (64 MiB of c32) for experiments.
+inline size_t pipe_chunk_samples() {
+    static const size_t v = [] {
+        const char* e = getenv("RRC_PIPE_CHUNK_LOG2");
+        int l = e ? atoi(e) : 23;
+        if (l < 12) l = 12;
+        if (l > 28) l = 28;
+        return (size_t)1 << l;
+    }();
+    return v;
+}
+#define PIPE_CHUNK_SAMPLES (::rrc::pipe_chunk_samples())
 
 }  // namespace rrc

@@ -40,6 +40,7 @@ unsafe extern "C" {
     pub fn rrc_fftfilt_ref_fft_size(ntaps: usize, fft_size: *mut usize, nsamples: *mut usize) -> c_int;
     pub fn rrc_fftfilt_plan(ntaps: usize, buffered: usize, in_len: usize, out_free: usize, blocks: *mut usize, consume: *mut usize,
                             buffered_after: *mut usize, wait_need: *mut usize, wait_on_output: *mut c_int) -> c_int;
+    pub fn rrc_fftfilt_set_history(h: *mut rrc_fftfilt_t, hist_dev_c32: *const c_float, n_samples: usize, stream: *mut c_void) -> c_int;
     pub fn rrc_fftfilt_run(h: *mut rrc_fftfilt_t, in_dev: *const c_float, n: usize, out_dev: *mut c_float, stream: *mut c_void) -> c_int;
 
     pub fn rrc_resampler_create(device: c_int, elem_size: usize, interp: usize, deci: usize, out: *mut *mut rrc_resampler_t) -> c_int;

@@ -161,6 +161,20 @@ def test_fftfilt_streaming_state_and_reset(R):
     assert O.rel_rms(f.filter(x[:5000]), truth[:5000]) <= REL_RMS_BAR
 
 
+def test_fftfilt_set_history_is_the_left_halo(R):
+    """A shard that starts mid-stream gets its ntaps-1 predecessors through set_history."""
+    taps = O.low_pass_n(1.0, 0.1, 501).astype(np.complex64)
+    x = O.synth_c32(25, 0, 50_000)
+    truth = O.conv_full_f64_fft(x, taps, len(x))
+    f = R.FftFilt(taps)
+    cut = 20_000
+    halo = R.DeviceBuffer.from_numpy(x[cut - 500:cut])
+    f.set_history(halo, 500)
+    assert O.rel_rms(f.filter(x[cut:]), truth[cut:]) <= REL_RMS_BAR
+    with pytest.raises(R.RrcError):
+        f.set_history(halo, 499)
+
+
 def test_fftfilt_run_host_reference_count_rule(R):
     """floor(N/nsamples)*nsamples outputs, trailing partial block never flushed (src/fft_filter.rs:315-327)."""
     taps = O.low_pass_complex(8000.0, 1000.0, 100.0)        # 193 taps -> fft 512, block 319
@@ -402,3 +416,26 @@ def test_time_segment_shards_equal_whole(R):
             y = xf[seg.in_lo:seg.in_hi][((k - seg.out_lo) * 160 - c0) // 147]
         parts.append(y)
     assert np.concatenate(parts).tobytes() == whole_rs.tobytes()
+
+
+# ------------------------------------------------------ empty / ragged inputs ---
+def test_empty_and_ragged_inputs(R):
+    """Zero-length and shorter-than-one-output inputs are no-ops with the reference's counts."""
+    taps = O.low_pass_n(1.0, 0.1, 33).astype(np.complex64)
+    f = R.Fir(taps, deci=4)
+    assert len(f.filter(np.empty(0, np.complex64))) == 0
+    assert len(f.filter(O.synth_c32(1, 0, 35))) == 0            # < ntaps + deci - 1 = 36
+    assert len(f.filter(O.synth_c32(1, 0, 36))) == 1
+    assert len(f.run_host(np.empty(0, np.complex64))) == 0
+    g = R.FftFilt(taps)
+    assert len(g.filter(np.empty(0, np.complex64))) == 0
+    assert len(g.run_host(O.synth_c32(1, 0, g.nsamples - 1))) == 0    # partial block is never flushed
+    assert len(g.run_host(O.synth_c32(1, 0, g.nsamples))) == g.nsamples
+    r = R.Resampler(8, 3, 7)
+    w, c, y = r.work(np.empty(0, np.complex64), 10)
+    assert (w, c, len(y)) == (0, 0, 0)                                # WaitForStream(src, 1)
+    w, c, y = r.work(O.synth_c32(1, 0, 5), 0)
+    assert (w, c, len(y)) == (1, 0, 0)                                # WaitForStream(dst, 1)
+    assert len(R.quad_demod_host(np.empty(0, np.complex64))) == 0
+    assert len(R.quad_demod_host(np.ones(1, np.complex64))) == 0
+    assert len(R.quad_demod_host(np.ones(2, np.complex64))) == 1
