@@ -23,6 +23,8 @@
 // 2*T (complex data, real taps), T (f32).  Bytes: 8*(N_in + N_out) c32.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -40,6 +42,8 @@ struct FirArgs {
     long long in_stride, out_stride;
     long long need, out_n;
     int ntaps, deci, qpad, nchunks, S, nseg;
+    int nbuf;                     // 1 or 2 input-tile buffers (2 = prefetch next tile while computing)
+    long long tiles_x, total_tiles;   // tiles per channel, tiles over all channels
     float gain;
     int translate;
     double ratio;                 // freq / samp_rate
@@ -108,21 +112,19 @@ __device__ __forceinline__ float demod_pair(float2 a, float2 b, float gain) {
     return gain * fast_atan2(im, re);
 }
 
-template <typename TT, int R>
-__device__ __forceinline__ void load_taps(const TT* tp, TT (&h)[R]);
-template <>
-__device__ __forceinline__ void load_taps<float2, FIR_R>(const float2* tp, float2 (&h)[FIR_R]) {
+template <int R>
+__device__ __forceinline__ void load_taps(const float2* tp, float2 (&h)[R]) {
 #pragma unroll
-    for (int k = 0; k < FIR_R; k += 2) {
+    for (int k = 0; k < R; k += 2) {
         float4 v = *reinterpret_cast<const float4*>(tp + k);
         h[k] = make_float2(v.x, v.y);
         h[k + 1] = make_float2(v.z, v.w);
     }
 }
-template <>
-__device__ __forceinline__ void load_taps<float, FIR_R>(const float* tp, float (&h)[FIR_R]) {
+template <int R>
+__device__ __forceinline__ void load_taps(const float* tp, float (&h)[R]) {
 #pragma unroll
-    for (int k = 0; k < FIR_R; k += 4) {
+    for (int k = 0; k < R; k += 4) {
         float4 v = *reinterpret_cast<const float4*>(tp + k);
         h[k] = v.x; h[k + 1] = v.y; h[k + 2] = v.z; h[k + 3] = v.w;
     }
@@ -131,74 +133,88 @@ __device__ __forceinline__ void load_taps<float, FIR_R>(const float* tp, float (
 // ST: sample type (float2 / float); TT: tap type; DCT: compile-time decimation (0 = run time), so
 // that every window offset u*deci is an immediate for the common decimations;
 // DEMOD: fused conj-multiply + atan2 epilogue (ST must be float2).
-template <typename ST, typename TT, int DCT, bool DEMOD>
+// R: outputs per thread = taps per chunk (8; 16 for the real-tap deci-1 case, which halves the
+// shared-memory loads per FMA).
+
+// Stage the input span of tile `id` into `s_tile` (padded: one pad element after every S).
+template <typename ST, int R>
+__device__ __forceinline__ void fir_load_tile(const FirArgs& a, ST* s_tile, long long id, int deci, int S,
+                                              int NT, int t, int bstride) {
+    const int S1 = S + 1;
+    const long long ch = id / a.tiles_x, bx = id - ch * a.tiles_x;
+    const ST* __restrict__ in = reinterpret_cast<const ST*>(a.in) + ch * a.in_stride;
+    const int L = a.nseg * S;
+    const long long g0 = bx * bstride * deci;
+    if (g0 + L <= a.need) {
+        // Interior tile: asynchronous 8/4-byte copies global -> shared (LDGSTS), all in flight
+        // at once, so the tile costs one memory latency instead of one per loop iteration.
+        const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_tile);
+        if (S >= 64) {      // one warp per thread-segment: no div/mod, constant strides
+            const int lane = t & 31, nwarp = NT >> 5;
+            for (int sg = t >> 5; sg < a.nseg; sg += nwarp) {
+                const ST* src = in + g0 + (long long)sg * S;
+                const unsigned dst = sbase + (unsigned)(sg * S1) * (unsigned)sizeof(ST);
+                for (int e = lane; e < S; e += 32) {
+                    if constexpr (sizeof(ST) == 8)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + e * 8), "l"(src + e) : "memory");
+                    else
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + e * 4), "l"(src + e) : "memory");
+                }
+            }
+        } else {            // short segments: flat element loop with incremental (segment, offset)
+            const ST* gsrc = in + g0;
+            int seg = t / S, rem = t - seg * S;
+            const int dseg = NT / S, drem = NT - dseg * S;
+            for (int e = t; e < L; e += NT) {
+                const unsigned dst = sbase + (unsigned)(seg * S1 + rem) * (unsigned)sizeof(ST);
+                if constexpr (sizeof(ST) == 8)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc + e) : "memory");
+                else
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc + e) : "memory");
+                seg += dseg; rem += drem;
+                if (rem >= S) { rem -= S; ++seg; }
+            }
+        }
+    } else {
+        int seg = t / S, rem = t - seg * S;
+        const int dseg = NT / S, drem = NT - dseg * S;
+        for (int e = t; e < L; e += NT) {
+            const long long g = g0 + e;
+            ST v; zero(v);
+            if (g < a.need) v = in[g];
+            s_tile[seg * S1 + rem] = v;
+            seg += dseg; rem += drem;
+            if (rem >= S) { rem -= S; ++seg; }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <typename ST, typename TT, int DCT, bool DEMOD, int R>
 __global__ void __launch_bounds__(FIR_MAX_NT) fir_poly_kernel(const FirArgs a) {
-    constexpr int R = FIR_R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int deci = DCT ? DCT : a.deci;
     const int S = DCT ? R * DCT : a.S;
     const int S1 = S + 1;
     const int NT = blockDim.x, t = threadIdx.x;
     const int BT = NT * R;
+    const int bstride = DEMOD ? BT - 1 : BT;
     const int ntap_tab = deci * a.qpad;
     TT* s_taps = reinterpret_cast<TT*>(smem_raw);
     ST* s_tile = reinterpret_cast<ST*>(smem_raw + (((size_t)ntap_tab * sizeof(TT) + 15) & ~(size_t)15));
 
-    const long long ob = (long long)blockIdx.x * (DEMOD ? BT - 1 : BT);
-    const ST* __restrict__ in = reinterpret_cast<const ST*>(a.in) + (long long)blockIdx.y * a.in_stride;
+    // One tile per CTA (blockIdx.x = tile in channel, blockIdx.y = channel): a persistent,
+    // double-buffered variant of this kernel measured 8-20 % slower (more registers, and the
+    // hardware CTA scheduler already overlaps one CTA's tile load with its neighbours' FMAs).
+    const long long ch = blockIdx.y;
+    const long long ob = (long long)blockIdx.x * bstride;
 
+    fir_load_tile<ST, R>(a, s_tile, ch * a.tiles_x + blockIdx.x, deci, S, NT, t, bstride);
     {   // taps -> smem (phase-major, zero padded to qpad per phase)
         const TT* __restrict__ gt = reinterpret_cast<const TT*>(a.taps);
         for (int i = t; i < ntap_tab; i += NT) s_taps[i] = gt[i];
     }
-    {   // input span -> smem, one pad element after every S elements
-        const int L = a.nseg * S;
-        const long long g0 = ob * deci;
-        if (g0 + L <= a.need) {
-            // Interior tile: asynchronous 8/4-byte copies global -> shared (LDGSTS), all in flight
-            // at once, so the tile costs one memory latency instead of one per loop iteration.
-            const unsigned sbase = (unsigned)__cvta_generic_to_shared(s_tile);
-            if (S >= 64) {      // one warp per thread-segment: no div/mod, constant strides
-                const int lane = t & 31, nwarp = NT >> 5;
-                for (int sg = t >> 5; sg < a.nseg; sg += nwarp) {
-                    const ST* src = in + g0 + (long long)sg * S;
-                    const unsigned dst = sbase + (unsigned)(sg * S1) * (unsigned)sizeof(ST);
-                    for (int e = lane; e < S; e += 32) {
-                        if constexpr (sizeof(ST) == 8)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + e * 8), "l"(src + e) : "memory");
-                        else
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + e * 4), "l"(src + e) : "memory");
-                    }
-                }
-            } else {            // short segments: flat element loop with incremental (segment, offset)
-                const ST* gsrc = in + g0;
-                int seg = t / S, rem = t - seg * S;
-                const int dseg = NT / S, drem = NT - dseg * S;
-                for (int e = t; e < L; e += NT) {
-                    const unsigned dst = sbase + (unsigned)(seg * S1 + rem) * (unsigned)sizeof(ST);
-                    if constexpr (sizeof(ST) == 8)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc + e) : "memory");
-                    else
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc + e) : "memory");
-                    seg += dseg; rem += drem;
-                    if (rem >= S) { rem -= S; ++seg; }
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        } else {
-            int seg = t / S, rem = t - seg * S;
-            const int dseg = NT / S, drem = NT - dseg * S;
-            for (int e = t; e < L; e += NT) {
-                const long long g = g0 + e;
-                ST v; zero(v);
-                if (g < a.need) v = in[g];
-                s_tile[seg * S1 + rem] = v;
-                seg += dseg; rem += drem;
-                if (rem >= S) { rem -= S; ++seg; }
-            }
-        }
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
     ST acc[R];
@@ -216,7 +232,7 @@ __global__ void __launch_bounds__(FIR_MAX_NT) fir_poly_kernel(const FirArgs a) {
 #pragma unroll
             for (int u = R - 1; u < 2 * R - 1; ++u) w[u] = bp[u * deci + (u >= R ? 1 : 0)];
             TT h[R];
-            load_taps<TT, R>(tp, h);
+            load_taps<R>(tp, h);
 #pragma unroll
             for (int k = 0; k < R; ++k)
 #pragma unroll
@@ -228,26 +244,42 @@ __global__ void __launch_bounds__(FIR_MAX_NT) fir_poly_kernel(const FirArgs a) {
         }
     }
 
-    __syncthreads();                 // everyone is done with the input tile
-    ST* s_out = s_tile;              // reuse: BT + NT entries <= tile size
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        ST y = acc[r];
-        if (a.translate) y = apply_translate(a, y, ob + (long long)t * R + r);
-        s_out[t * (R + 1) + r] = y;
-    }
-    __syncthreads();
-
     if constexpr (!DEMOD) {
-        ST* __restrict__ out = reinterpret_cast<ST*>(a.out) + (long long)blockIdx.y * a.out_stride;
+        // Each thread owns R consecutive outputs: store them straight from registers (128-bit
+        // when the destination is 16-byte aligned); the sectors a warp half-fills are completed
+        // by its own next store instruction, so L2 merges them before write-back.
+        ST* __restrict__ out = reinterpret_cast<ST*>(a.out) + ch * a.out_stride;
+        const long long gi0 = ob + (long long)t * R;
+        if (a.translate) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int o = t + r * NT;
-            const long long gi = ob + o;
-            if (gi < a.out_n) out[gi] = s_out[o + o / R];
+            for (int r = 0; r < R; ++r) acc[r] = apply_translate(a, acc[r], gi0 + r);
+        }
+        ST* dst = out + gi0;
+        if (gi0 + R <= a.out_n && (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
+            constexpr int VE = 16 / (int)sizeof(ST);
+#pragma unroll
+            for (int r = 0; r < R; r += VE) {
+                float4 v;
+                if constexpr (sizeof(ST) == 8) v = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+                else v = make_float4(acc[r], acc[r + 1], acc[r + 2], acc[r + 3]);
+                *reinterpret_cast<float4*>(dst + r) = v;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (gi0 + r < a.out_n) dst[r] = acc[r];
         }
     } else {
-        float* __restrict__ out = reinterpret_cast<float*>(a.out) + (long long)blockIdx.y * a.out_stride;
+        __syncthreads();                 // everyone is done with the input tile
+        ST* s_out = s_tile;              // reuse: BT + NT entries <= tile size
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            ST y = acc[r];
+            if (a.translate) y = apply_translate(a, y, ob + (long long)t * R + r);
+            s_out[t * (R + 1) + r] = y;
+        }
+        __syncthreads();
+        float* __restrict__ out = reinterpret_cast<float*>(a.out) + ch * a.out_stride;
         float2 ya[R], yb[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {                 // R independent demods per thread: ILP for atan2
@@ -303,7 +335,7 @@ struct rrc_fir {
     std::vector<float> taps_host;   // caller order, interleaved if cplx
     void* taps_poly = nullptr;
     void* taps_rev = nullptr;
-    int qpad = 0, nchunks = 0, nt = 0;
+    int qpad = 0, nchunks = 0, nt = 0, R = FIR_R, nbuf = 1;
     size_t smem = 0;
     bool use_poly = false;
     bool translate = false;
@@ -332,8 +364,10 @@ int upload_taps(rrc_fir* h) {
     const size_t te = h->real_taps ? 1 : 2;   // floats per tap in the device tables
 
     const size_t Q = (T + D - 1) / D;
-    h->qpad = (int)((Q + FIR_R - 1) / FIR_R * FIR_R);
-    h->nchunks = h->qpad / FIR_R;
+    // outputs per thread: 16 for the real-tap, non-decimating, >= 32-tap case (c32 or f32), else 8
+    h->R = (h->real_taps && D == 1 && T >= 32) ? 16 : FIR_R;
+    h->qpad = (int)((Q + h->R - 1) / h->R * h->R);
+    h->nchunks = h->qpad / h->R;
 
     auto tap_at = [&](size_t j, float* dst) {   // h'[j] = taps[T-1-j]
         const size_t k = T - 1 - j;
@@ -358,18 +392,23 @@ int upload_taps(rrc_fir* h) {
     // Geometry: largest CTA whose tile fits; prefer <= 100 KB so two CTAs share an SM.
     h->use_poly = false;
     if (!(h->flags & RRC_FIR_FORCE_GENERIC) && D <= (1u << 20)) {
-        const size_t S1 = FIR_R * D + 1;
+        const size_t S1 = (size_t)h->R * D + 1;
         const size_t tap_bytes = ((size_t)D * h->qpad * tap_elem(h) + 15) & ~(size_t)15;
         const size_t limit_hi = (size_t)max_smem_optin(h->device);
         // Large decimations make the staged tile big (R*deci samples per thread): prefer CTAs of
         // <= 48 KB so that >= 4 of them share an SM and their load / compute / store phases overlap.
         const size_t limits[3] = {48 * 1024, 100 * 1024, limit_hi};
         const int nt_min[3] = {64, 32, 32};
+        // Measured on config 1 (R = 16): 64-thread CTAs (1024 outputs) beat 256-thread ones by 9 %
+        // because more, smaller CTAs interleave their tile loads with their neighbours' FMAs.
+        int nt_max = h->R == 16 ? 64 : FIR_MAX_NT;
+        if (const char* e = getenv("RRC_FIR_NT")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) nt_max = v; }
         for (int pass = 0; pass < 3 && !h->use_poly; ++pass) {
-            for (int nt = FIR_MAX_NT; nt >= nt_min[pass]; nt >>= 1) {
-                const size_t bytes = tap_bytes + (size_t)(nt + h->nchunks) * S1 * samp_elem(h);
-                if (bytes <= limits[pass]) {
-                    h->nt = nt; h->smem = bytes; h->use_poly = true;
+            for (int nt = nt_max; nt >= std::min(nt_min[pass], nt_max); nt >>= 1) {
+                const size_t tile = (((size_t)(nt + h->nchunks) * S1 + 1) & ~(size_t)1) * samp_elem(h);
+                if (tap_bytes + tile <= limits[pass]) {
+                    h->nbuf = 1;
+                    h->nt = nt; h->smem = tap_bytes + h->nbuf * tile; h->use_poly = true;
                     break;
                 }
             }
@@ -378,14 +417,22 @@ int upload_taps(rrc_fir* h) {
     return RRC_OK;
 }
 
-template <typename ST, typename TT, int DCT, bool DEMOD>
-int launch_poly_d(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
-    auto k = fir_poly_kernel<ST, TT, DCT, DEMOD>;
+template <typename ST, typename TT, int DCT, bool DEMOD, int R>
+int launch_poly_r(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
+    auto k = fir_poly_kernel<ST, TT, DCT, DEMOD, R>;
     RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     k<<<grid, h->nt, h->smem, st>>>(a);
     RRC_CHECK_LAUNCH();
     count_launch();
     return RRC_OK;
+}
+
+template <typename ST, typename TT, int DCT, bool DEMOD>
+int launch_poly_d(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
+    if constexpr (DCT == 1 && std::is_same<TT, float>::value) {
+        if (h->R == 16) return launch_poly_r<ST, TT, DCT, DEMOD, 16>(h, a, grid, st);
+    }
+    return launch_poly_r<ST, TT, DCT, DEMOD, FIR_R>(h, a, grid, st);
 }
 
 template <typename ST, typename TT, bool DEMOD>
@@ -419,7 +466,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
     a.need = (long long)need; a.out_n = (long long)out_n;
     a.ntaps = (int)h->ntaps; a.deci = (int)h->deci;
     a.qpad = h->qpad; a.nchunks = h->nchunks;
-    a.S = FIR_R * (int)h->deci; a.nseg = h->nt + h->nchunks;
+    a.S = h->R * (int)h->deci; a.nseg = h->nt + h->nchunks;
     a.gain = gain;
     a.translate = h->translate ? 1 : 0;
     a.ratio = h->ratio;
@@ -427,11 +474,14 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
 
     if (h->use_poly) {
         a.taps = h->taps_poly;
-        const size_t bt = (size_t)h->nt * FIR_R;
+        const size_t bt = (size_t)h->nt * h->R;
         const size_t per = demod ? bt - 1 : bt;
         const size_t work = demod ? (out_n > 1 ? out_n - 1 : 0) : out_n;
         if (work == 0) return RRC_OK;
-        dim3 grid((unsigned)((work + per - 1) / per), (unsigned)nchan);
+        a.tiles_x = (long long)((work + per - 1) / per);
+        a.total_tiles = a.tiles_x * (long long)nchan;
+        a.nbuf = h->nbuf;
+        dim3 grid((unsigned)a.tiles_x, (unsigned)nchan);
         int s;
         if (h->cplx && !h->real_taps)
             s = demod ? launch_poly<float2, float2, true>(h, a, grid, st) : launch_poly<float2, float2, false>(h, a, grid, st);
