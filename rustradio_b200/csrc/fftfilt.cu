@@ -23,6 +23,7 @@
 #include "fftfilt_core.cuh"
 #include "fftfilt_tables.hpp"
 #include "pipeline.cuh"
+#include "fftfilt_handle.hpp"
 
 namespace rrc {
 
@@ -123,26 +124,6 @@ __global__ void fftfilt_hist_kernel(const float2* __restrict__ hist_cur, const f
 
 using namespace rrc;
 
-struct rrc_fftfilt {
-    int device = 0;
-    size_t ntaps = 0;
-    int T1 = 0;                       // ntaps - 1 (history length)
-    // Long filters are split into tap partitions of <= PART_TAPS taps; partition p filters the
-    // input delayed by p*PART_TAPS and accumulates into the output (y = sum_p h_p * x(n - p*L)).
-    std::vector<int> part_T1;         // taps of partition p, minus 1
-    std::vector<float2*> part_Hp;     // spectrum of partition p (512-thread layout)
-    std::vector<float2*> part_Hd;     // spectrum of partition p (1024-thread layout)
-    float2* Hp = nullptr;             // == part_Hp[0]
-    float2* tw1_16 = nullptr;
-    float2* tw2_16 = nullptr;
-    float2* tw3_16 = nullptr;
-    int variant = 32;                 // points per thread: 32 (512 threads) or 16 (1024 threads)
-    float2* tw1 = nullptr;
-    float2* tw2 = nullptr;
-    float2* hist[2] = {nullptr, nullptr};
-    int cur = 0;
-    Pipe pipe;
-};
 
 namespace {
 
@@ -253,6 +234,7 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
     RRC_CUDA(cudaSetDevice(device));
     auto* h = new rrc_fftfilt();
     h->device = device; h->ntaps = ntaps;
+    h->taps_host.assign(taps, taps + 2 * ntaps);
     h->T1 = (int)ntaps - 1;
     auto cleanup = [&](int s) { rrc_fftfilt_destroy(h); return s; };
     auto up = [&](float2** d, const std::vector<float2>& v) -> cudaError_t {
@@ -298,6 +280,7 @@ int rrc_fftfilt_destroy(rrc_fftfilt_t* h) {
     for (float2* p : h->part_Hd) cudaFree(p);
     cudaFree(h->tw1_16); cudaFree(h->tw2_16); cudaFree(h->tw3_16);
     cudaFree(h->tw1); cudaFree(h->tw2); cudaFree(h->hist[0]); cudaFree(h->hist[1]);
+    fold_destroy(h);
     h->pipe.destroy();
     delete h;
     return RRC_OK;
@@ -347,6 +330,19 @@ int rrc_fftfilt_decim_run(rrc_fftfilt_t* h, const float* in, size_t n, size_t de
     // deci == 1 && skip == 0 degenerates to the plain path; otherwise the store
     // predicate in phase A' keeps y[skip + k*deci].
     if (deci == 1 && skip == 0) return launch(h, in, n, out, n, 1, 0, as_stream(stream));
+    // deci == 8: folded spectrum + 8x smaller inverse transform (fftfilt_fold.cu); 65536-point
+    // cluster kernel for 12289 < ntaps <= 49153.  RRC_FFTFILT_NO_FOLD=1 forces the store-predicate path.
+    if (fold_supported(h, deci) == RRC_OK) {
+        if (cnt) RRC_TRY(fold_launch(h, in, n, out, cnt, skip, as_stream(stream)));
+        if (h->T1 > 0) {
+            fftfilt_hist_kernel<<<(h->T1 + 255) / 256, 256, 0, as_stream(stream)>>>(
+                h->hist[h->cur], reinterpret_cast<const float2*>(in), (long long)n, h->T1, h->hist[h->cur ^ 1]);
+            RRC_CHECK_LAUNCH();
+            count_launch();
+            h->cur ^= 1;
+        }
+        return RRC_OK;
+    }
     return launch(h, in, n, out, cnt, deci, skip, as_stream(stream));
 }
 

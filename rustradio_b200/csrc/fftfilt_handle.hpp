@@ -1,0 +1,50 @@
+// fftfilt_handle.hpp — the FftFilter handle shared by fftfilt.cu (plain overlap-save kernels) and
+// fftfilt_fold.cu (decimate-by-8 fused kernel with the pruned inverse transform).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "pipeline.cuh"
+
+// Tables of the decimate-by-8 fold kernel (fftfilt_fold_core.cuh), built lazily on first use.
+struct rrc_fold_tables {
+    int nc = 0;                 // CTAs per cluster: 1 (N = 16384) or 4 (N = 65536); 0 = not built
+    float2* Hc = nullptr;       // [nc][16384] spectrum rows, phase-C order
+    float2* gc = nullptr;       // [nc][512]   W_{16384 nc}^{c t}
+    float2* twc = nullptr;      // [nc][32]    W_128^{c n1}
+    float2* twm = nullptr;      // [2048]      W_{2048 nc}^{m2}
+    int max_clusters = 0;       // co-resident clusters (cudaOccupancyMaxActiveClusters)
+};
+
+struct rrc_fftfilt {
+    int device = 0;
+    size_t ntaps = 0;
+    std::vector<float> taps_host;     // interleaved c32 taps (kept for lazily built tables)
+    int T1 = 0;                       // ntaps - 1 (history length)
+    // Long filters are split into tap partitions of <= PART_TAPS taps; partition p filters the
+    // input delayed by p*PART_TAPS and accumulates into the output (y = sum_p h_p * x(n - p*L)).
+    std::vector<int> part_T1;         // taps of partition p, minus 1
+    std::vector<float2*> part_Hp;     // spectrum of partition p (512-thread layout)
+    std::vector<float2*> part_Hd;     // spectrum of partition p (1024-thread layout)
+    float2* Hp = nullptr;             // == part_Hp[0]
+    float2* tw1_16 = nullptr;
+    float2* tw2_16 = nullptr;
+    float2* tw3_16 = nullptr;
+    int variant = 32;                 // points per thread: 32 (512 threads) or 16 (1024 threads)
+    float2* tw1 = nullptr;
+    float2* tw2 = nullptr;
+    float2* hist[2] = {nullptr, nullptr};
+    int cur = 0;
+    rrc::Pipe pipe;
+    rrc_fold_tables fold;
+};
+
+namespace rrc {
+// fftfilt_fold.cu: FftFilter + decimate-by-8 with folded spectrum.  Returns RRC_ERR_UNSUPPORTED
+// (without setting the error text) when the geometry is not covered, so the caller can fall back
+// to the store-predicate path.
+int fold_supported(const rrc_fftfilt* h, size_t deci);
+int fold_launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out,
+                size_t skip, cudaStream_t st);
+void fold_destroy(rrc_fftfilt* h);
+}  // namespace rrc

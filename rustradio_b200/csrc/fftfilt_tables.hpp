@@ -9,6 +9,7 @@
 
 #include "fftfilt_core.cuh"
 #include "fftfilt16_core.cuh"
+#include "fftfilt_fold_core.cuh"
 
 namespace rrc { namespace fftk {
 
@@ -91,3 +92,36 @@ inline void build_tables16(const float* taps, size_t ntaps, std::vector<float2>&
 }
 
 }}  // namespace rrc::fftk
+
+namespace rrc { namespace fftf {
+
+// Tables of the decimate-by-8 fold kernel (fftfilt_fold_core.cuh), NBIG = nc * 16384:
+//   Hc[c*16384 + (k1*32 + k2)*16 + k3] = H_NBIG[c + nc*(k1 + 32 k2 + 1024 k3)] / NBIG
+//   gc[c*512 + t] = W_NBIG^{c t};  twc[c*32 + n1] = W_NBIG^{512 c n1};  twm[m2] = W_{2048 nc}^{m2}.
+inline void build_fold_tables(const float* taps, size_t ntaps, int nc, std::vector<float2>& Hc,
+                              std::vector<float2>& gc, std::vector<float2>& twc, std::vector<float2>& twm) {
+    const size_t NBIG = (size_t)nc * fftk::N;
+    std::vector<std::complex<double>> H(NBIG);
+    for (size_t k = 0; k < ntaps; ++k) H[k] = {(double)taps[2 * k], (double)taps[2 * k + 1]};
+    fftk::fft_host(H);
+    auto w = [](double num, double den) {
+        const double a = -2.0 * M_PI * std::fmod(num, den) / den;
+        return make_float2((float)std::cos(a), (float)std::sin(a));
+    };
+    Hc.resize(NBIG); gc.resize((size_t)nc * 512); twc.resize((size_t)nc * 32); twm.resize(LU);
+    for (int c = 0; c < nc; ++c) {
+        for (int P = 0; P < 1024; ++P) {
+            const int k1 = P >> 5, k2 = P & 31;
+            for (int k3 = 0; k3 < 16; ++k3) {
+                const size_t k = (size_t)c + (size_t)nc * (size_t)(k1 + 32 * k2 + 1024 * k3);
+                const auto v = H[k] / (double)NBIG;
+                Hc[(size_t)c * fftk::N + (size_t)P * 16 + k3] = make_float2((float)v.real(), (float)v.imag());
+            }
+        }
+        for (int t = 0; t < 512; ++t) gc[(size_t)c * 512 + t] = w((double)c * t, (double)NBIG);
+        for (int n1 = 0; n1 < 32; ++n1) twc[(size_t)c * 32 + n1] = w((double)c * 512.0 * n1, (double)NBIG);
+    }
+    for (int m2 = 0; m2 < LU; ++m2) twm[m2] = w((double)m2, (double)LU * nc);
+}
+
+}}  // namespace rrc::fftf

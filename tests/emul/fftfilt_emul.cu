@@ -87,3 +87,52 @@ extern "C" int emul_fftfilt16(const float* taps, long long ntaps, const float* i
     }
     return 0;
 }
+
+// Decimate-by-8 fold kernel (fftfilt_fold_core.cuh): nc = 1 (16384-point) or nc = 4 (65536-point,
+// the four CTAs of a cluster emulated one after the other with four shared-memory arrays).
+template <int NC>
+static int emul_fold_t(const float* taps, long long ntaps, const float* in, long long n, const float* hist,
+                       float* out, long long skip, long long n_out) {
+    namespace ff = rrc::fftf;
+    const int T1_total = (int)ntaps - 1;
+    std::vector<float2> h(T1_total > 0 ? T1_total : 1, make_float2(0.f, 0.f));
+    if (hist && T1_total > 0) memcpy(h.data(), hist, sizeof(float2) * T1_total);
+    std::vector<float2> Hp0, tw1, tw2, Hc, gc, twc, twm;
+    build_tables(taps, (size_t)std::min<long long>(ntaps, 8193), Hp0, tw1, tw2);      // tw1, tw2 only
+    ff::build_fold_tables(taps, (size_t)ntaps, NC, Hc, gc, twc, twm);
+    ff::FoldIO io;
+    io.in = reinterpret_cast<const float2*>(in); io.hist = h.data(); io.out = reinterpret_cast<float2*>(out);
+    io.n_in = n; io.n_out = n_out; io.T1_total = T1_total; io.T1eff = (T1_total + 7) & ~7;
+    io.V = NC * N - io.T1eff; io.r = (int)(skip % 8); io.jbias = skip / 8;
+    if (n <= io.r) return 0;
+    const long long nblocks = (n - io.r + io.V - 1) / io.V;
+    const int U_OFF = 4096;
+    std::vector<std::vector<float2>> sm(NC, std::vector<float2>(SMEM_ELEMS)), hres(NC, std::vector<float2>(HRES_ELEMS));
+    for (int c = 0; c < NC; ++c)
+        for (int t = 0; t < NT; ++t) load_hres(t, Hc.data() + (size_t)c * N, hres[c].data());
+    for (long long blk = 0; blk < nblocks; ++blk) {
+        for (int c = 0; c < NC; ++c) {
+            float2* s = sm[c].data();
+            const float2* Hp = Hc.data() + (size_t)c * N;
+            for (int t = 0; t < NT; ++t) ff::phase_a<NC>(t, c, blk, io, tw1.data(), gc.data() + c * 512, twc.data() + c * 32, s);
+            for (int t = 0; t < NT; ++t) phase_mid_b(t, tw2.data(), s);
+            for (int t = 0; t < NT; ++t) ff::phase_c_fold(t, Hp, hres[c].data(), s);
+            std::vector<float2> regs(64 * 32);
+            for (int t = 0; t < 64; ++t) { float2 v[32]; ff::inv1_load(t, s, v); memcpy(&regs[t * 32], v, sizeof v); }
+            for (int t = 0; t < 64; ++t) { float2 v[32]; memcpy(v, &regs[t * 32], sizeof v); ff::inv1_compute_store(t, tw1.data(), v, s); }
+            for (int t = 0; t < 64; ++t) { float2 v[32]; ff::inv2_load(t, s, v); memcpy(&regs[t * 32], v, sizeof v); }
+            for (int t = 0; t < 64; ++t) { float2 v[32]; memcpy(v, &regs[t * 32], sizeof v); ff::inv2_compute_store(t, v, s + U_OFF); }
+        }
+        const float2* uc[NC];
+        for (int c = 0; c < NC; ++c) uc[c] = sm[c].data() + U_OFF;
+        for (int c = 0; c < NC; ++c)
+            for (int t = 0; t < NT; ++t) ff::combine_store<NC>(t, c, blk, io, uc, twm.data());
+    }
+    return 0;
+}
+
+extern "C" int emul_fftfilt_fold(int nc, const float* taps, long long ntaps, const float* in, long long n,
+                                 const float* hist, float* out, long long skip, long long n_out) {
+    return nc == 1 ? emul_fold_t<1>(taps, ntaps, in, n, hist, out, skip, n_out)
+                   : emul_fold_t<4>(taps, ntaps, in, n, hist, out, skip, n_out);
+}

@@ -68,3 +68,45 @@ def test_emulated_kernel_history_and_decimation(emul, variant):
         assert len(yd) == len(want)
         if len(want):
             assert O.rel_rms(yd, want) <= 1e-5
+
+
+@pytest.fixture(scope="module")
+def emul_fold(emul):
+    L = C.CDLL(str(SO))
+    L.emul_fftfilt_fold.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                    C.c_longlong, C.c_longlong]
+
+    def run(nc, taps, x, hist=None, skip=0):
+        taps = np.ascontiguousarray(taps, np.complex64)
+        x = np.ascontiguousarray(x, np.complex64)
+        n = len(x)
+        n_out = (n - skip + 7) // 8 if n > skip else 0
+        out = np.full(n_out, np.nan + 0j, np.complex64)
+        L.emul_fftfilt_fold(nc, taps.ctypes.data, len(taps), x.ctypes.data, n,
+                            hist.ctypes.data if hist is not None else None, out.ctypes.data, skip, n_out)
+        return out
+    return run
+
+
+@pytest.mark.parametrize("nc,ntaps,n,skip", [(1, 301, 40_000, 0), (1, 4097, 50_000, 3), (1, 1, 20_000, 7), (1, 12289, 30_000, 13),
+                                             (4, 16385, 150_000, 0), (4, 16385, 70_000, 5), (4, 12290, 120_000, 9),
+                                             (4, 40_001, 100_000, 2)])
+def test_emulated_fold_kernel_matches_f64_convolution(emul_fold, nc, ntaps, n, skip):
+    """Decimate-by-8 fold kernel (pruned inverse; nc = 4: 65536-point cluster geometry)."""
+    taps = (O.low_pass_n(1.0, 0.02, ntaps).astype(np.complex64) * (1 - 0.2j)) if ntaps > 2 else np.array([0.5 - 0.25j], np.complex64)
+    x = O.synth_c32(7, 0, n)
+    want = O.conv_full_f64_fft(x, taps, n)[skip::8]
+    got = emul_fold(nc, taps, x, skip=skip)
+    assert len(got) == len(want) and not np.isnan(got).any()
+    assert O.rel_rms(got, want) <= 1e-5
+
+
+def test_emulated_fold_kernel_streaming_history(emul_fold):
+    taps = O.low_pass_n(1.0, 0.02, 16385).astype(np.complex64)
+    x = O.synth_c32(8, 0, 120_000)
+    truth = O.conv_full_f64_fft(x, taps, len(x))
+    cut = 70_001
+    a = emul_fold(4, taps, x[:cut], skip=0)
+    skip2 = (-cut) % 8                      # RationalResampler(1, 8) phase carried across the call boundary
+    b = emul_fold(4, taps, x[cut:], hist=np.ascontiguousarray(x[cut - 16384:cut]), skip=skip2)
+    assert O.rel_rms(np.concatenate([a, b]), truth[::8]) <= 1e-5

@@ -222,6 +222,52 @@ def test_fftfilt_long_taps_partitioned_streaming_and_decimation(R):
     assert O.rel_rms(dout.download(np.complex64, n), truth[::8]) <= REL_RMS_BAR
 
 
+@pytest.mark.parametrize("ntaps,n,skip", [(301, 90_000, 0), (4097, 200_000, 3), (12289, 60_000, 13),      # 16384-point fold kernel
+                                          (16385, 400_000, 0), (16385, 70_000, 5), (12290, 300_000, 9),   # 65536-point cluster kernel
+                                          (40_001, 250_000, 2), (49_153, 200_000, 7)])
+def test_fftfilt_decimate_by_8_folded_spectrum(R, ntaps, n, skip, monkeypatch):
+    """FftFilter + RationalResampler(1, 8) fused with the pruned inverse transform (fftfilt_fold.cu):
+    against f64 truth, and against the store-predicate path of the plain kernel on the same input."""
+    taps = (O.low_pass_n(1.0, 0.02, ntaps).astype(np.complex64) * (1 - 0.2j))
+    x = O.synth_c32(41, 0, n)
+    want = O.conv_full_f64_fft(x, taps, n)[skip::8]
+    din = R.DeviceBuffer.from_numpy(x)
+
+    def run():
+        f = R.FftFilt(taps)
+        dout = R.DeviceBuffer(max(1, len(want)) * 8)
+        cnt = f.decim_run(din, n, 8, skip, dout)
+        assert cnt == len(want)
+        return dout.download(np.complex64, cnt)
+    got = run()
+    assert O.rel_rms(got, want) <= REL_RMS_BAR
+    monkeypatch.setenv("RRC_FFTFILT_NO_FOLD", "1")
+    plain = run()
+    assert O.rel_rms(plain, want) <= REL_RMS_BAR
+    assert O.rel_rms(got, plain) <= REL_RMS_BAR
+
+
+def test_fftfilt_fold_streaming_carries_history_and_phase(R):
+    """Config 5 shape streamed in ragged pieces: the (ntaps-1)-sample history and the decimation phase
+    (RationalResampler's counter, src/rational_resampler.rs:101-105) carry across calls."""
+    taps = O.low_pass_n(1.0, 0.02, 16385).astype(np.complex64)
+    x = O.synth_c32(42, 0, 330_000)
+    truth = O.conv_full_f64_fft(x, taps, len(x))[::8]
+    f = R.FftFilt(taps)
+    out, pos = [], 0
+    for cut in (5, 70_001, 70_004, 200_000, 330_000):
+        piece = x[pos:cut]
+        skip = (-pos) % 8
+        din = R.DeviceBuffer.from_numpy(piece)
+        dout = R.DeviceBuffer(max(1, len(piece)) * 8)
+        cnt = f.decim_run(din, len(piece), 8, skip, dout)
+        out.append(dout.download(np.complex64, cnt))
+        pos = cut
+    y = np.concatenate(out)
+    assert len(y) == len(truth)
+    assert O.rel_rms(y, truth) <= REL_RMS_BAR
+
+
 # ------------------------------------------------------------ resampler ---
 @pytest.mark.parametrize("interp,deci", [(1, 1), (1, 2), (2, 1), (2, 3), (3, 2), (25, 64), (25, 128), (147, 160),
                                           (200000, 1024000), (1, 8), (160, 147), (7, 1000), (1000, 7)])
