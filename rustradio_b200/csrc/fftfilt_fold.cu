@@ -27,7 +27,7 @@ constexpr int FOLD_U_OFF = 4096;      // float2 offset of the u array inside the
 static_assert(fftf::P2_ELEMS <= FOLD_U_OFF && FOLD_U_OFF + fftf::LU <= fftk::SMEM_ELEMS, "fold staging layout");
 constexpr size_t FOLD_SMEM = (size_t)(fftk::SMEM_ELEMS + 512 + 512 + fftk::HRES_ELEMS + 512 + 32) * sizeof(float2);
 
-__device__ __forceinline__ void task_barrier() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+__device__ __forceinline__ void task_barrier() { asm volatile("bar.sync 3, 64;" ::: "memory"); }
 
 template <int NC>
 __global__ void __launch_bounds__(fftk::NT, 1)
@@ -61,8 +61,14 @@ fftfilt_fold_kernel(const FoldIO io, const float2* __restrict__ Hc, const float2
         uc[0] = sm + FOLD_U_OFF;
     }
     const long long cl = blockIdx.x / NC, ncl = gridDim.x / NC;
+    bool pending = false;         // a relaxed cluster-barrier arrival of the previous block is outstanding
     for (long long blk = cl; blk < nblocks; blk += ncl) {
-        fftf::phase_a<NC>(tid, c, blk, io, s_tw1, s_gc, s_twc, sm);
+        // The other CTAs of the cluster may still be reading this CTA's u array (previous block); the
+        // matching wait sits after this block's loads and DFT32, right before the first shared-memory
+        // write, so it is normally already satisfied.
+        fftf::phase_a<NC>(tid, c, blk, io, s_tw1, s_gc, s_twc, sm, [&]() {
+            if constexpr (NC > 1) { if (pending) asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+        });
         __syncthreads();
         {   // next block's segment -> L2: every CTA of the cluster pulls one quarter (16 warps x 8 KiB)
             const long long nb = blk + ncl;
@@ -87,9 +93,12 @@ fftfilt_fold_kernel(const FoldIO io, const float2* __restrict__ Hc, const float2
         }
         if constexpr (NC > 1) cg::this_cluster().sync(); else __syncthreads();
         fftf::combine_store<NC>(tid, c, blk, io, uc, twm);
-        // the next phase A overwrites the u arrays the other CTAs of the cluster are still reading
-        if constexpr (NC > 1) cg::this_cluster().sync(); else __syncthreads();
+        // The next phase A overwrites the u array other CTAs are still reading: write-after-read only,
+        // so a RELAXED arrival is enough (no release fence waiting for the global stores to drain).
+        if constexpr (NC > 1) { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); pending = true; }
+        else __syncthreads();
     }
+    if constexpr (NC > 1) { if (pending) asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 }
 
 namespace {

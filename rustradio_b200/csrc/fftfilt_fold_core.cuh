@@ -74,9 +74,13 @@ RRC_HD float2 fetch(const FoldIO& io, long long g) {
 // W_128^{c n1} input twiddle), DFT32 over n1, twiddle by gc[tid] * W_N^{tid k1}, write smem.
 //   tw1[t] = W_16384^t (t < 512); gc[t] = W_65536^{c t} (NC = 4; unused for NC = 1);
 //   twc[n1] = W_128^{c n1} (NC = 4).
-template <int NC>
+struct NoHook { RRC_HD void operator()() const {} };
+// before_store(): called after the loads and the DFT32, just before the results are written to the
+// exchange buffer (the cluster kernel waits there for the other CTAs to finish reading this CTA's
+// previous u array, which lives in the same shared memory).
+template <int NC, class Hook = NoHook>
 RRC_HD void phase_a(int tid, int c, long long blk, const FoldIO& io, const float2* tw1, const float2* gc,
-                    const float2* twc, float2* sm) {
+                    const float2* twc, float2* sm, Hook before_store = Hook()) {
     float2 v[32];
     const long long seg0 = seg_start<NC>(blk, io);
     const bool interior = seg0 >= 0 && seg0 + (long long)NC * N <= io.n_in;
@@ -94,20 +98,40 @@ RRC_HD void phase_a(int tid, int c, long long blk, const FoldIO& io, const float
         const float ur = c == 0 ? 1.f : c == 2 ? -1.f : 0.f;
         const float ui = c == 1 ? -1.f : c == 3 ? 1.f : 0.f;
         const float s2 = (c & 1) ? -1.f : 1.f;
-#pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-            float2 x0, x1, x2, x3;
-            if (interior) {
-                const float2* p = io.in + seg0 + tid + 512 * n1;
-                x0 = p[0]; x1 = p[N]; x2 = p[2 * N]; x3 = p[3 * N];
-            } else {
-                const long long g = seg0 + tid + 512 * n1;
-                x0 = fetch(io, g); x1 = fetch(io, g + N); x2 = fetch(io, g + 2 * N); x3 = fetch(io, g + 3 * N);
-            }
-            const float2 E = make_float2(fmaf(s2, x2.x, x0.x), fmaf(s2, x2.y, x0.y));
-            const float2 O = make_float2(fmaf(s2, x3.x, x1.x), fmaf(s2, x3.y, x1.y));
+        auto combine = [&](int n1, const float2 (&x)[4]) {
+            const float2 E = make_float2(fmaf(s2, x[2].x, x[0].x), fmaf(s2, x[2].y, x[0].y));
+            const float2 O = make_float2(fmaf(s2, x[3].x, x[1].x), fmaf(s2, x[3].y, x[1].y));
             const float2 a = make_float2(fmaf(-ui, O.y, fmaf(ur, O.x, E.x)), fmaf(ui, O.x, fmaf(ur, O.y, E.y)));
             v[bitrev(n1, 5)] = cmul(a, twc[n1]);
+        };
+        if (interior) {
+            // Software-pipelined: the 16 loads of batch b+1 (4 values of n1 x 4 quarters) are issued
+            // before batch b is consumed, so every thread keeps 16..32 loads in flight (the loads are
+            // L2 hits for three of the four CTAs of the cluster, ~300-800 cycles each).
+            const float2* p = io.in + seg0 + tid;
+            float2 xb[2][4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xb[0][i][j] = p[512 * i + j * N];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (b < 7) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xb[(b + 1) & 1][i][j] = p[512 * (4 * (b + 1) + i) + j * N];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) combine(4 * b + i, xb[b & 1][i]);
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {                   // edge blocks: bounds-checked, history / zero fill
+                const long long g = seg0 + tid + 512 * n1;
+                const float2 x[4] = {fetch(io, g), fetch(io, g + N), fetch(io, g + 2 * N), fetch(io, g + 3 * N)};
+                combine(n1, x);
+            }
         }
     }
     dit<32, +1>(v);
@@ -115,6 +139,7 @@ RRC_HD void phase_a(int tid, int c, long long blk, const FoldIO& io, const float
     if constexpr (NC == 1) powers32(tw1[tid], p);
     else powers32b(tw1[tid], gc[tid], p);
     float2* s = sm + (tid >> 4) * ROW_PITCH + (tid & 15);
+    before_store();
 #pragma unroll
     for (int k1 = 0; k1 < 32; ++k1) s[k1 * PLANE_PITCH] = cmul(v[k1], p[k1]);
 }
