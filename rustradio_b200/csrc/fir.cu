@@ -296,6 +296,181 @@ __global__ void __launch_bounds__(FIR_MAX_NT) fir_poly_kernel(const FirArgs a) {
     }
 }
 
+// ---- c32 samples, REAL taps: packed FP32 (FFMA2) kernel ----------------------------------------
+// low_pass_complex always produces real taps (src/fir.rs:600-603), so acc.(re,im) += h * x.(re,im)
+// is ONE Blackwell packed instruction, fma.rn.f32x2 (SASS FFMA2): sample and accumulator are the
+// 64-bit register pairs LDS.64 delivers, the tap is stored in shared memory as the pair (h, h).
+// FFMA2 retires two FMAs per issue slot (measured: 1.99 warp-instr/clk/SM = 127 lane-FMA/clk/SM,
+// tools/microbench/fp32_pipes.cu), so the window loads, tap loads and address arithmetic issue in the
+// shadow of the FP32 pipe instead of competing with it; results are bit-identical to FFMA.
+//   SPLIT = 2: two threads share one group of R outputs and take alternate polyphase branches
+//   (lanes l and l^16), then add their partial sums with one shuffle per output.  The staged input
+//   tile is R*deci samples per GROUP, so this doubles the resident warps for large decimations
+//   (config 3: 10 -> 20 warps/SM) without more shared memory.
+//   Taps per polyphase branch are NOT rounded up to a multiple of R: full chunks of R taps, then one
+//   tail chunk of (Q_p mod R) taps (config 3: 26/25 taps per branch instead of 32 -> -20 % FMAs).
+typedef unsigned long long u64;
+__device__ __forceinline__ void fma2(u64& acc, u64 hh, u64 x) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(hh), "l"(x));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float2 unpk(u64 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
+// One chunk of K <= R taps: loads the K new window elements and the K tap pairs, K*R FFMA2,
+// then slides the window by K.  bp points at the window start of this chunk (pitch S1 per R*deci).
+template <int R, int K>
+__device__ __forceinline__ void rt_chunk(u64 (&acc)[R], u64 (&w)[2 * R - 1], const u64* bp, const u64* tp, int deci) {
+#pragma unroll
+    for (int u = R - 1; u < R - 1 + K; ++u) w[u] = bp[u * deci + (u >= R ? 1 : 0)];
+    u64 h[K];
+    if constexpr (K % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(tp + k);
+            h[k] = v.x; h[k + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) h[k] = tp[k];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int r = 0; r < R; ++r) fma2(acc[r], h[k], w[r + k]);
+#pragma unroll
+    for (int u = 0; u < R - 1; ++u) w[u] = w[u + K];
+}
+
+// tail chunk of rem in [1, R) taps (rem is CTA-uniform: a short chain of uniform branches)
+template <int R, int K>
+struct RtTail {
+    static __device__ __forceinline__ void run(int rem, u64 (&acc)[R], u64 (&w)[2 * R - 1], const u64* bp, const u64* tp, int deci) {
+        if (rem == K) rt_chunk<R, K>(acc, w, bp, tp, deci);
+        else RtTail<R, K - 1>::run(rem, acc, w, bp, tp, deci);
+    }
+};
+template <int R>
+struct RtTail<R, 0> {
+    static __device__ __forceinline__ void run(int, u64 (&)[R], u64 (&)[2 * R - 1], const u64*, const u64*, int) {}
+};
+
+template <int DCT, bool DEMOD, int R, int SPLIT>
+__global__ void __launch_bounds__(FIR_MAX_NT) fir_rt_kernel(const FirArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int deci = DCT ? DCT : a.deci;
+    const int S = DCT ? R * DCT : a.S;
+    const int S1 = S + 1;
+    const int NT = blockDim.x, tid = threadIdx.x;
+    const int G = NT / SPLIT;                                   // output groups (R outputs each) per CTA
+    // half-warps keep 16 consecutive groups (conflict-free strided window reads); the partner that
+    // shares a group is lane ^ 16.
+    const int s = SPLIT == 1 ? 0 : (tid >> 4) & 1;
+    const int t = SPLIT == 1 ? tid : ((tid >> 5) << 4) | (tid & 15);
+    const int BT = G * R;
+    const int bstride = DEMOD ? BT - 1 : BT;
+    const int ntap_tab = deci * a.qpad;
+    u64* s_taps = reinterpret_cast<u64*>(smem_raw);
+    float2* s_tile = reinterpret_cast<float2*>(smem_raw + (((size_t)ntap_tab * sizeof(u64) + 15) & ~(size_t)15));
+
+    const long long ch = blockIdx.y;
+    const long long ob = (long long)blockIdx.x * bstride;
+    fir_load_tile<float2, R>(a, s_tile, ch * a.tiles_x + blockIdx.x, deci, S, NT, tid, bstride);
+    {   // taps -> smem as (h, h) pairs, phase-major, zero padded to qpad per phase
+        const float* __restrict__ gt = reinterpret_cast<const float*>(a.taps);
+        for (int i = tid; i < ntap_tab; i += NT) {
+            const float hv = gt[i];
+            float2 pr = make_float2(hv, hv);
+            s_taps[i] = *reinterpret_cast<u64*>(&pr);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    u64 acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0ull;
+
+    const u64* base_t = reinterpret_cast<const u64*>(s_tile) + t * S1;
+    for (int p = s; p < deci; p += SPLIT) {
+        const int Qp = a.ntaps > p ? (a.ntaps - p + deci - 1) / deci : 0;   // taps of polyphase branch p
+        const u64* bp = base_t + p;
+        const u64* tp = s_taps + p * a.qpad;
+        u64 w[2 * R - 1];
+#pragma unroll
+        for (int u = 0; u < R - 1; ++u) w[u] = bp[u * deci];
+        const int nfull = Qp / R, rem = Qp - nfull * R;
+        for (int c = 0; c < nfull; ++c) {
+            rt_chunk<R, R>(acc, w, bp, tp, deci);
+            bp += S1;
+            tp += R;
+        }
+        RtTail<R, R - 1>::run(rem, acc, w, bp, tp, deci);
+    }
+    if constexpr (SPLIT == 2) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const u64 o = __shfl_xor_sync(0xffffffffu, acc[r], 16);
+            acc[r] = add2(acc[r], o);
+        }
+    }
+    // each thread finishes RS of the group's R outputs: r in [r0, r0 + RS)
+    constexpr int RS = R / SPLIT;
+    const int r0 = s * RS;
+
+    if constexpr (!DEMOD) {
+        float2* __restrict__ out = reinterpret_cast<float2*>(a.out) + ch * a.out_stride;
+        const long long gi0 = ob + (long long)t * R + r0;
+        float2 y[RS];
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            y[r] = unpk(SPLIT == 2 && s ? acc[(RS + r) % R] : acc[r]);
+            if (a.translate) y[r] = apply_translate(a, y[r], gi0 + r);
+        }
+        float2* dst = out + gi0;
+        if (gi0 + RS <= a.out_n && (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
+#pragma unroll
+            for (int r = 0; r < RS; r += 2)
+                *reinterpret_cast<float4*>(dst + r) = make_float4(y[r].x, y[r].y, y[r + 1].x, y[r + 1].y);
+        } else {
+#pragma unroll
+            for (int r = 0; r < RS; ++r)
+                if (gi0 + r < a.out_n) dst[r] = y[r];
+        }
+    } else {
+        __syncthreads();                 // everyone is done with the input tile
+        float2* s_out = s_tile;          // reuse: BT + G entries <= tile size
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            float2 y = unpk(SPLIT == 2 && s ? acc[(RS + r) % R] : acc[r]);
+            if (a.translate) y = apply_translate(a, y, ob + (long long)t * R + r0 + r);
+            s_out[t * (R + 1) + r0 + r] = y;
+        }
+        __syncthreads();
+        float* __restrict__ out = reinterpret_cast<float*>(a.out) + ch * a.out_stride;
+        float2 ya[RS], yb[RS];
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {                // RS independent demods per thread: ILP for atan2
+            const int o = tid + r * NT;
+            ya[r] = s_out[o + o / R];
+            yb[r] = s_out[(o + 1) + (o + 1) / R];     // o + 1 <= BT - 1 < BT + G entries
+        }
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+            const int o = tid + r * NT;
+            const long long gi = ob + o;
+            if (o < BT - 1 && gi < a.out_n - 1) out[gi] = demod_pair(ya[r], yb[r], a.gain);
+        }
+    }
+}
+
 // Fallback for geometries whose tile does not fit shared memory (very large
 // deci*R or tap tables): one thread per output, taps and inputs through L1/L2.
 template <typename ST, typename TT>
@@ -336,6 +511,8 @@ struct rrc_fir {
     void* taps_poly = nullptr;
     void* taps_rev = nullptr;
     int qpad = 0, nchunks = 0, nt = 0, R = FIR_R, nbuf = 1;
+    int groups = 0, split = 1;   // nt = groups * split threads; split = 2: two threads per group of R outputs (fir_rt_kernel)
+    bool rt = false;             // c32 samples + real taps: packed-FP32 kernel (fir_rt_kernel)
     size_t smem = 0;
     bool use_poly = false;
     bool translate = false;
@@ -391,24 +568,32 @@ int upload_taps(rrc_fir* h) {
 
     // Geometry: largest CTA whose tile fits; prefer <= 100 KB so two CTAs share an SM.
     h->use_poly = false;
+    // Packed-FP32 kernel for decimating real-tap c32 filters.  For deci == 1 (config 1) the FFMA
+    // kernel with R = 16 measured 9 % faster (150.6 vs 137.4 Gsps), so it keeps that path
+    // (RRC_FIR_FFMA2=1 forces the packed kernel there too, =0 disables it everywhere).
+    h->rt = h->cplx && h->real_taps && D >= 2;
+    if (const char* e = getenv("RRC_FIR_FFMA2")) h->rt = h->cplx && h->real_taps && atoi(e) != 0;
+    // two threads per output group when the staged tile per group is large (R*deci*8 bytes)
+    h->split = (h->rt && D >= 4) ? 2 : 1;
+    if (const char* e = getenv("RRC_FIR_SPLIT")) { int v = atoi(e); if (h->rt && (v == 1 || (v == 2 && D >= 2))) h->split = v; }
     if (!(h->flags & RRC_FIR_FORCE_GENERIC) && D <= (1u << 20)) {
         const size_t S1 = (size_t)h->R * D + 1;
-        const size_t tap_bytes = ((size_t)D * h->qpad * tap_elem(h) + 15) & ~(size_t)15;
+        const size_t tap_bytes = ((size_t)D * h->qpad * (h->rt ? sizeof(float2) : tap_elem(h)) + 15) & ~(size_t)15;
         const size_t limit_hi = (size_t)max_smem_optin(h->device);
-        // Large decimations make the staged tile big (R*deci samples per thread): prefer CTAs of
+        // Large decimations make the staged tile big (R*deci samples per group): prefer CTAs of
         // <= 48 KB so that >= 4 of them share an SM and their load / compute / store phases overlap.
         const size_t limits[3] = {48 * 1024, 100 * 1024, limit_hi};
         const int nt_min[3] = {64, 32, 32};
         // Measured on config 1 (R = 16): 64-thread CTAs (1024 outputs) beat 256-thread ones by 9 %
         // because more, smaller CTAs interleave their tile loads with their neighbours' FMAs.
-        int nt_max = h->R == 16 ? 64 : FIR_MAX_NT;
-        if (const char* e = getenv("RRC_FIR_NT")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) nt_max = v; }
+        int nt_max = h->R == 16 ? 64 : FIR_MAX_NT / h->split;
+        if (const char* e = getenv("RRC_FIR_NT")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) nt_max = std::min(v, FIR_MAX_NT / h->split); }
         for (int pass = 0; pass < 3 && !h->use_poly; ++pass) {
-            for (int nt = nt_max; nt >= std::min(nt_min[pass], nt_max); nt >>= 1) {
-                const size_t tile = (((size_t)(nt + h->nchunks) * S1 + 1) & ~(size_t)1) * samp_elem(h);
+            for (int g = nt_max; g >= std::min(nt_min[pass], nt_max); g >>= 1) {
+                const size_t tile = (((size_t)(g + h->nchunks) * S1 + 1) & ~(size_t)1) * samp_elem(h);
                 if (tap_bytes + tile <= limits[pass]) {
                     h->nbuf = 1;
-                    h->nt = nt; h->smem = tap_bytes + h->nbuf * tile; h->use_poly = true;
+                    h->groups = g; h->nt = g * h->split; h->smem = tap_bytes + h->nbuf * tile; h->use_poly = true;
                     break;
                 }
             }
@@ -433,6 +618,36 @@ int launch_poly_d(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st
         if (h->R == 16) return launch_poly_r<ST, TT, DCT, DEMOD, 16>(h, a, grid, st);
     }
     return launch_poly_r<ST, TT, DCT, DEMOD, FIR_R>(h, a, grid, st);
+}
+
+template <int DCT, bool DEMOD, int R, int SPLIT>
+int launch_rt_k(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
+    auto k = fir_rt_kernel<DCT, DEMOD, R, SPLIT>;
+    RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    k<<<grid, h->nt, h->smem, st>>>(a);
+    RRC_CHECK_LAUNCH();
+    count_launch();
+    return RRC_OK;
+}
+template <int DCT, bool DEMOD>
+int launch_rt_d(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
+    if constexpr (DCT == 1) {
+        return h->R == 16 ? launch_rt_k<1, DEMOD, 16, 1>(h, a, grid, st) : launch_rt_k<1, DEMOD, FIR_R, 1>(h, a, grid, st);
+    } else {
+        return h->split == 2 ? launch_rt_k<DCT, DEMOD, FIR_R, 2>(h, a, grid, st) : launch_rt_k<DCT, DEMOD, FIR_R, 1>(h, a, grid, st);
+    }
+}
+template <bool DEMOD>
+int launch_rt(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
+    switch (h->deci) {
+    case 1: return launch_rt_d<1, DEMOD>(h, a, grid, st);
+    case 2: return launch_rt_d<2, DEMOD>(h, a, grid, st);
+    case 4: return launch_rt_d<4, DEMOD>(h, a, grid, st);
+    case 5: return launch_rt_d<5, DEMOD>(h, a, grid, st);
+    case 8: return launch_rt_d<8, DEMOD>(h, a, grid, st);
+    case 10: return launch_rt_d<10, DEMOD>(h, a, grid, st);
+    default: return launch_rt_d<0, DEMOD>(h, a, grid, st);
+    }
 }
 
 template <typename ST, typename TT, bool DEMOD>
@@ -466,7 +681,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
     a.need = (long long)need; a.out_n = (long long)out_n;
     a.ntaps = (int)h->ntaps; a.deci = (int)h->deci;
     a.qpad = h->qpad; a.nchunks = h->nchunks;
-    a.S = h->R * (int)h->deci; a.nseg = h->nt + h->nchunks;
+    a.S = h->R * (int)h->deci; a.nseg = h->groups + h->nchunks;
     a.gain = gain;
     a.translate = h->translate ? 1 : 0;
     a.ratio = h->ratio;
@@ -474,7 +689,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
 
     if (h->use_poly) {
         a.taps = h->taps_poly;
-        const size_t bt = (size_t)h->nt * h->R;
+        const size_t bt = (size_t)h->groups * h->R;
         const size_t per = demod ? bt - 1 : bt;
         const size_t work = demod ? (out_n > 1 ? out_n - 1 : 0) : out_n;
         if (work == 0) return RRC_OK;
@@ -485,6 +700,8 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         int s;
         if (h->cplx && !h->real_taps)
             s = demod ? launch_poly<float2, float2, true>(h, a, grid, st) : launch_poly<float2, float2, false>(h, a, grid, st);
+        else if (h->rt)
+            s = demod ? launch_rt<true>(h, a, grid, st) : launch_rt<false>(h, a, grid, st);
         else if (h->cplx)
             s = demod ? launch_poly<float2, float, true>(h, a, grid, st) : launch_poly<float2, float, false>(h, a, grid, st);
         else
