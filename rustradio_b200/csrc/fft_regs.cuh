@@ -158,4 +158,23 @@ RRC_HD void dit(float2* v) {
     }
 }
 
+// dit_g: dit with the first-level butterflies written as a +- one*b (one == 1.0f at run time, so
+// the results are bit-identical to a +- b at the same instruction count).  Every value of the
+// transform then depends on `one`; a kernel that obtains `one` from a volatile load placed after a
+// barrier thereby keeps ptxas from hoisting the arithmetic above that barrier (it otherwise does:
+// register-only FP instructions are freely scheduled across BAR.SYNC).
+template <int N, int DIR>
+RRC_HD void dit_g(float2* v, float one) {
+    static_assert(N >= 2 && N <= 64 && (N & (N - 1)) == 0, "N must be a power of two, 2..64");
+    if constexpr (N == 2) {
+        const float2 a = v[0], b = v[1];
+        v[0] = make_float2(fmaf(b.x, one, a.x), fmaf(b.y, one, a.y));
+        v[1] = make_float2(fmaf(-b.x, one, a.x), fmaf(-b.y, one, a.y));
+    } else {
+        dit_g<N / 2, DIR>(v, one);
+        dit_g<N / 2, DIR>(v + N / 2, one);
+        DitLevel<N, DIR, 0>::run(v);
+    }
+}
+
 }}  // namespace rrc::fftr

@@ -29,12 +29,25 @@ namespace rrc {
 
 using fftk::BlockIO;
 
-constexpr size_t FFTFILT_SMEM = (size_t)(fftk::SMEM_ELEMS + 512 + 512 + fftk::HRES_ELEMS) * sizeof(float2);
+constexpr size_t FFTFILT_SMEM = (size_t)(fftk::SMEM_ELEMS + 512 + 512 + fftk::HRES_ELEMS + 2) * sizeof(float2);
 
-template <bool DECIM, bool ACCUM>
+// Input prefetch: pulls the input segment of block `nb` into L2 with one 8 KiB bulk prefetch per warp
+// (16 x 8 KiB = segment; SASS UBLKPF.L2).
+__device__ __forceinline__ void prefetch_segment(const BlockIO& io, long long nb, long long nblocks, int tid) {
+    const long long seg0 = nb * (long long)io.V - io.T1 - io.shift + (long long)(tid >> 5) * 1024;
+    if ((tid & 31) == 0 && nb < nblocks && seg0 >= 0 && seg0 + 1024 <= io.n_in) {
+        const unsigned long long a = (reinterpret_cast<unsigned long long>(io.in + seg0) + 15ull) & ~15ull;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(8192 - 16) : "memory");
+    }
+}
+
+// tune: bits 0-3 = prefetch placement (0 none, 1 after barrier 1 for the next block, 2 at block start
+// for the next block, 3 at block start for the block after next); bits 8.. = CTA start stagger in
+// units of 1024 cycles times (blockIdx & 3) (experiment knobs, RRC_FFTFILT_TUNE).
+template <bool DECIM, bool ACCUM, bool TWC>
 __global__ void __launch_bounds__(fftk::NT, 1)
 fftfilt_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __restrict__ tw1g,
-               const float2* __restrict__ tw2g, long long nblocks) {
+               const float2* __restrict__ tw2g, long long nblocks, int tune) {
     extern __shared__ __align__(16) float2 sm[];
     float2* s_tw2 = sm + fftk::SMEM_ELEMS;
     float2* s_tw1 = s_tw2 + 512;
@@ -43,12 +56,79 @@ fftfilt_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __
     s_tw2[tid] = tw2g[tid];
     s_tw1[tid] = tw1g[tid];
     fftk::load_hres(tid, Hp, s_hres);
+    const int pf = tune & 15;
+    if (tune >> 8) {
+        const long long t0 = clock64(), wait = (long long)(tune >> 8) * 1024 * (blockIdx.x & 3);
+        while (clock64() - t0 < wait) { }
+    }
     __syncthreads();
+    if (pf == 3) prefetch_segment(io, blockIdx.x + gridDim.x, nblocks, tid);
     for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        if (pf == 2) prefetch_segment(io, blk + gridDim.x, nblocks, tid);
+        if (pf == 3) prefetch_segment(io, blk + 2 * gridDim.x, nblocks, tid);
         fftk::phase_a(tid, blk, io, s_tw1, sm);
         __syncthreads();
-        {   // Pull the NEXT block's input segment into L2 while this block computes, so the
-            // next phase A's loads are L2 hits: one 8 KiB bulk prefetch per warp (16 x 8 KiB = segment).
+        if (pf == 1) prefetch_segment(io, blk + gridDim.x, nblocks, tid);
+        fftk::phase_mid<TWC>(tid, s_tw2, Hp, s_hres, sm); // half-warp local exchanges: __syncwarp only
+        __syncthreads();
+        fftk::phase_ai<DECIM, ACCUM>(tid, blk, io, s_tw1, sm);
+        // no barrier: the next phase_a writes exactly the words this thread just read
+    }
+}
+
+// Staged-input variant: the next block's input is copied into the exchange buffer by cp.async while
+// phase A' of the current block computes and stores (fftfilt_core.cuh, stage_input).
+template <bool DECIM, bool ACCUM>
+__global__ void __launch_bounds__(fftk::NT, 1)
+fftfilt_st_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __restrict__ tw1g,
+                  const float2* __restrict__ tw2g, long long nblocks, int tune) {
+    extern __shared__ __align__(16) float2 sm[];
+    float2* s_tw2 = sm + fftk::SMEM_ELEMS;
+    float2* s_tw1 = s_tw2 + 512;
+    float2* s_hres = s_tw1 + 512;
+    const int tid = threadIdx.x;
+    s_tw2[tid] = tw2g[tid];
+    s_tw1[tid] = tw1g[tid];
+    fftk::load_hres(tid, Hp, s_hres);
+    const int pf = tune & 15;
+    if (blockIdx.x < nblocks) fftk::stage_input(tid, blockIdx.x, io, sm);
+    __syncthreads();
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        fftk::phase_a_staged(tid, s_tw1, sm);
+        __syncthreads();
+        if (pf) prefetch_segment(io, blk + pf * gridDim.x, nblocks, tid);
+        fftk::phase_mid(tid, s_tw2, Hp, s_hres, sm);
+        __syncthreads();
+        const long long nb = blk + gridDim.x;
+        fftk::phase_ai<DECIM, ACCUM>(tid, blk, io, s_tw1, sm, fftk::NoTurn(), [&]() {
+            __syncthreads();                                  // every thread has read the buffer
+            if (nb < nblocks) fftk::stage_input(tid, nb, io, sm);
+        });
+    }
+}
+
+// Ping-pong variant of fftfilt_kernel (PingPong policy: fftfilt_core.cuh).
+template <bool DECIM, bool ACCUM>
+__global__ void __launch_bounds__(fftk::NT, 1)
+fftfilt_pp_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __restrict__ tw1g,
+                  const float2* __restrict__ tw2g, long long nblocks, int /*tune*/) {
+    extern __shared__ __align__(16) float2 sm[];
+    float2* s_tw2 = sm + fftk::SMEM_ELEMS;
+    float2* s_tw1 = s_tw2 + 512;
+    float2* s_hres = s_tw1 + 512;
+    const int tid = threadIdx.x;
+    s_tw2[tid] = tw2g[tid];
+    s_tw1[tid] = tw1g[tid];
+    fftk::load_hres(tid, Hp, s_hres);
+    float* s_one = reinterpret_cast<float*>(s_hres + fftk::HRES_ELEMS);
+    if (tid == 0) *s_one = 1.0f;
+    __syncthreads();
+    const fftk::PingPong turn{(tid >> 7) & 1, (unsigned)__cvta_generic_to_shared(s_one)};
+    if (turn.g == 1) turn.release();                       // group 0 takes the first turn
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        fftk::phase_a(tid, blk, io, s_tw1, sm, turn);
+        __syncthreads();
+        {
             const long long nb = blk + gridDim.x;
             const long long seg0 = nb * (long long)io.V - io.T1 - io.shift + (long long)(tid >> 5) * 1024;
             if ((tid & 31) == 0 && nb < nblocks && seg0 >= 0 && seg0 + 1024 <= io.n_in) {
@@ -56,10 +136,9 @@ fftfilt_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(8192 - 16) : "memory");
             }
         }
-        fftk::phase_mid(tid, s_tw2, Hp, s_hres, sm);      // half-warp local exchanges: __syncwarp only
+        fftk::phase_mid(tid, s_tw2, Hp, s_hres, sm, turn);
         __syncthreads();
-        fftk::phase_ai<DECIM, ACCUM>(tid, blk, io, s_tw1, sm);
-        // no barrier: the next phase_a writes exactly the words this thread just read
+        fftk::phase_ai<DECIM, ACCUM>(tid, blk, io, s_tw1, sm, turn);
     }
 }
 
@@ -154,9 +233,10 @@ template <bool DECIM, bool ACCUM>
 int launch_part(rrc_fftfilt* h, const BlockIO& io, const float2* Hp, cudaStream_t st) {
     const long long nblocks = (io.n_in + io.V - 1) / io.V;
     const int grid = (int)std::min<long long>(nblocks, sm_count(h->device));
-    auto kern = fftfilt_kernel<DECIM, ACCUM>;
+    auto kern = h->variant == 33 ? fftfilt_pp_kernel<DECIM, ACCUM> : h->variant == 34 ? fftfilt_st_kernel<DECIM, ACCUM> : h->variant == 35 ? fftfilt_kernel<DECIM, ACCUM, true> : fftfilt_kernel<DECIM, ACCUM, false>;
     RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_SMEM));
-    kern<<<grid, fftk::NT, FFTFILT_SMEM, st>>>(io, Hp, h->tw1, h->tw2, nblocks);
+    static const int tune = [] { const char* e = getenv("RRC_FFTFILT_TUNE"); return e ? (int)strtol(e, nullptr, 0) : 1; }();
+    kern<<<grid, fftk::NT, FFTFILT_SMEM, st>>>(io, Hp, h->tw1, h->tw2, nblocks, tune);
     RRC_CHECK_LAUNCH();
     count_launch();
     return RRC_OK;
@@ -260,7 +340,7 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
         if (!h->tw1_16 && ((e = up(&h->tw1_16, t1)) != cudaSuccess || (e = up(&h->tw2_16, t2)) != cudaSuccess || (e = up(&h->tw3_16, t3)) != cudaSuccess))
             return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
     }
-    if (const char* v = getenv("RRC_FFTFILT_VARIANT")) h->variant = atoi(v) == 16 ? 16 : 32;
+    if (const char* v = getenv("RRC_FFTFILT_VARIANT")) h->variant = atoi(v) == 16 ? 16 : atoi(v) == 33 ? 33 : atoi(v) == 34 ? 34 : atoi(v) == 35 ? 35 : 32;
     h->Hp = h->part_Hp[0];
     if ((e = up(&h->tw1, tw1)) != cudaSuccess || (e = up(&h->tw2, tw2)) != cudaSuccess)
         return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));

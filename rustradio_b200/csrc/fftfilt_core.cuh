@@ -53,6 +53,35 @@ struct BlockIO {
 
 RRC_HD int phys(int k1, int r, int c) { return k1 * PLANE_PITCH + r * ROW_PITCH + c; }
 
+// FP-pipe "turn" policy.  Every phase below is  loads -> acquire() -> arithmetic -> release() -> stores.
+// NoTurn: no-ops (plain kernel, CPU emulator).  The ping-pong kernel (fftfilt.cu, PingPong) passes a
+// token between two groups of 8 warps so that one group's arithmetic burst runs while the other
+// group's shared-memory / global burst is in flight, instead of all 16 warps doing the same kind of
+// work in lock-step.
+// acquire() returns 1.0f: the forward phases feed it to dit_g so that their arithmetic depends on a
+// value produced after the barrier (see dit_g in fft_regs.cuh); the inverse phases start with a
+// multiplication by a twiddle that is loaded after acquire().
+struct NoTurn {
+    RRC_HD float acquire() const { return 1.0f; }
+    RRC_HD void release() const {}
+};
+
+#if defined(__CUDACC__)
+// Ping-pong: the 16 warps form two groups of 8 (two warps of each group on every SM sub-partition)
+// that pass an "FP turn" token through named barriers 1 and 2, so one group's arithmetic burst
+// overlaps the other group's shared-memory / global burst.
+struct PingPong {
+    int g;               // group 0 or 1
+    unsigned one_addr;   // shared-memory address of a float 1.0f
+    __device__ __forceinline__ float acquire() const {
+        float one;
+        asm volatile("bar.sync %1, 512;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(one) : "r"(1 + g), "r"(one_addr) : "memory");
+        return one;
+    }
+    __device__ __forceinline__ void release() const { asm volatile("bar.arrive %0, 512;" ::"r"(2 - g) : "memory"); }
+};
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define RRC_SYNCWARP() __syncwarp()
 #else
@@ -75,9 +104,26 @@ RRC_HD void powers32(float2 w, float2 (&p)[32]) {
     }
 }
 
+// Powers p[k] = w^k, k = 0..15, depth <= 4 multiplications each.
+RRC_HD void powers16(float2 w, float2 (&p)[16]) {
+    float2 wp[4];
+    wp[0] = w;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) wp[i] = csqr(wp[i - 1]);
+    p[0] = make_float2(1.f, 0.f);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+        const int low = k & (-k);
+        const int rest = k & (k - 1);
+        const int b = low == 1 ? 0 : low == 2 ? 1 : low == 4 ? 2 : 3;
+        p[k] = rest == 0 ? wp[b] : cmul(p[rest], wp[b]);
+    }
+}
+
 // Phase A: load segment of block `blk`, DFT32 over n1, twiddle, write smem.
 // tw1[t] = W_N^t = exp(-2 pi i t / N), t < 512.
-RRC_HD void phase_a(int tid, long long blk, const BlockIO& io, const float2* tw1, float2* sm) {
+template <class Turn = NoTurn>
+RRC_HD void phase_a(int tid, long long blk, const BlockIO& io, const float2* tw1, float2* sm, Turn turn = Turn()) {
     float2 v[32];
     // input index of segment element 0 (tap partition p filters the input delayed by `shift`)
     const long long seg0 = blk * (long long)io.V - io.T1 - io.shift;
@@ -96,26 +142,103 @@ RRC_HD void phase_a(int tid, long long blk, const BlockIO& io, const float2* tw1
             v[bitrev(n1, 5)] = x;
         }
     }
-    dit<32, +1>(v);                                             // bit-reversed in, natural k1 out
+    const float one = turn.acquire();
+    const float2 w1 = tw1[tid];
+    dit_g<32, +1>(v, one);                                      // bit-reversed in, natural k1 out
     float2 p[32];
-    powers32(tw1[tid], p);
+    powers32(w1, p);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) v[k1] = cmul(v[k1], p[k1]);
+    turn.release();
     float2* s = sm + (tid >> 4) * ROW_PITCH + (tid & 15);       // (k1 = 0, r = n2, c = n3)
 #pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) s[k1 * PLANE_PITCH] = cmul(v[k1], p[k1]);
+    for (int k1 = 0; k1 < 32; ++k1) s[k1 * PLANE_PITCH] = v[k1];
+}
+
+// ---- staged input (fftfilt_st_kernel) ----------------------------------------------------------
+// stage_input: thread t copies ITS 32 input samples of block `blk` (n = t + 512*n1) into the 32
+// exchange-buffer words it owns in phase A (phys(n1, t>>4, t&15) — the very words its phase-A
+// results go to), asynchronously with cp.async (SASS LDGSTS) for interior blocks.  The copy is
+// issued right after phase A' of the previous block has read the buffer, so the HBM/L2 latency of
+// the next block's input is hidden behind the arithmetic and stores of phase A' instead of being
+// exposed at the top of phase A.  No thread ever reads another thread's staged words, so the only
+// synchronisation is cp.async.wait_group by the issuing thread.
+RRC_HD void stage_input(int tid, long long blk, const BlockIO& io, float2* sm) {
+    float2* s = sm + (tid >> 4) * ROW_PITCH + (tid & 15);
+    const long long seg0 = blk * (long long)io.V - io.T1 - io.shift;
+    if (seg0 >= 0 && seg0 + N <= io.n_in) {
+        const float2* p = io.in + seg0 + tid;
+#if defined(__CUDA_ARCH__)
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(s);
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + n1 * PLANE_PITCH * 8), "l"(p + 512 * n1) : "memory");
+#else
+        for (int n1 = 0; n1 < 32; ++n1) s[n1 * PLANE_PITCH] = p[512 * n1];
+#endif
+    } else {
+        const long long g0 = seg0 + tid;
+#pragma unroll 4
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const long long g = g0 + 512 * n1;
+            float2 x = make_float2(0.f, 0.f);
+            if (g < 0) { if (g + io.T1_total >= 0) x = io.hist[g + io.T1_total]; }
+            else if (g < io.n_in) x = io.in[g];
+            s[n1 * PLANE_PITCH] = x;
+        }
+    }
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+RRC_HD void stage_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+// Phase A on staged input: the thread's own words -> DFT32 over n1 -> twiddle -> the same words.
+template <class Turn = NoTurn>
+RRC_HD void phase_a_staged(int tid, const float2* tw1, float2* sm, Turn turn = Turn()) {
+    float2* s = sm + (tid >> 4) * ROW_PITCH + (tid & 15);
+    float2 v[32];
+    stage_wait();
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = s[n1 * PLANE_PITCH];
+    const float one = turn.acquire();
+    const float2 w1 = tw1[tid];
+    dit_g<32, +1>(v, one);
+    float2 p[32];
+    powers32(w1, p);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) v[k1] = cmul(v[k1], p[k1]);
+    turn.release();
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) s[k1 * PLANE_PITCH] = v[k1];
 }
 
 // Phase MID: B, C, B' on one k1 plane per half-warp.  tw2[k2*16 + n3] = W_512^{n3*k2}.
 // Hp[(k1*32 + k2)*16 + k3] = H[k1 + 32*k2 + 1024*k3] / N.
-RRC_HD void phase_mid_b(int tid, const float2* tw2, float2* sm) {
+// TW = false: the W_512^{n3*k2} twiddle is NOT applied here but in phase C (TWC = true there), from
+// powers of one per-row value, so the arithmetic bursts of B and B' contain no shared-memory loads:
+// a table load issued inside an arithmetic burst queues behind the other warps' exchange traffic
+// and couples the FP pipe to the shared-memory pipe (no overlap between them).
+template <bool TW = true, class Turn = NoTurn>
+RRC_HD void phase_mid_b(int tid, const float2* tw2, float2* sm, Turn turn = Turn()) {
     const int k1 = tid >> 4, l = tid & 15;
     float2* col = sm + k1 * PLANE_PITCH + l;                    // (k1, r = 0, c = l)
     const float2* tw = tw2 + l;
     float2 v[32];
 #pragma unroll
     for (int n2 = 0; n2 < 32; ++n2) v[bitrev(n2, 5)] = col[n2 * ROW_PITCH];
-    dit<32, +1>(v);
+    const float one = turn.acquire();
+    dit_g<32, +1>(v, one);
+    if constexpr (TW) {
 #pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) col[k2 * ROW_PITCH] = cmul(v[k2], tw[k2 * 16]);
+        for (int k2 = 0; k2 < 32; ++k2) v[k2] = cmul(v[k2], tw[k2 * 16]);
+    }
+    turn.release();
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) col[k2 * ROW_PITCH] = v[k2];
 }
 // Spectrum residency: the row each thread multiplies first (k2 = l) lives in shared memory for
 // the whole kernel (Hres, 512 rows, pitch HRES_PITCH so the per-thread 128-bit reads are
@@ -133,7 +256,8 @@ RRC_HD void load_hres(int tid, const float2* Hp, float2* Hres) {
     for (int i = 0; i < 8; ++i) dst[i] = src[i];
 }
 
-RRC_HD void phase_mid_c(int tid, const float2* Hp, const float2* Hres, float2* sm) {
+template <bool TWC = false, class Turn = NoTurn>
+RRC_HD void phase_mid_c(int tid, const float2* Hp, const float2* Hres, float2* sm, Turn turn = Turn(), const float2* tw2 = nullptr) {
     const int k1 = tid >> 4, l = tid & 15;
     const float4* hp1 = reinterpret_cast<const float4*>(Hp + (size_t)(k1 * 32 + l + 16) * 16);
     float4 h1[8];
@@ -145,9 +269,18 @@ RRC_HD void phase_mid_c(int tid, const float2* Hp, const float2* Hres, float2* s
         const int k2 = l + 16 * half;
         float2* row = sm + k1 * PLANE_PITCH + k2 * ROW_PITCH;   // (k1, r = k2, c = 0)
         float2 v[16];
+        float2 g = make_float2(1.f, 0.f);
+        if constexpr (TWC) g = tw2[k2 * 16 + 1];                // W_512^{k2}
 #pragma unroll
         for (int n3 = 0; n3 < 16; ++n3) v[bitrev(n3, 4)] = row[n3];
-        dit<16, +1>(v);                                         // v[k3], natural order
+        const float one = turn.acquire();
+        float2 pw[16];
+        if constexpr (TWC) {
+            powers16(g, pw);                                    // W_512^{n3*k2}
+#pragma unroll
+            for (int n3 = 1; n3 < 16; ++n3) v[bitrev(n3, 4)] = cmul(v[bitrev(n3, 4)], pw[n3]);
+        }
+        dit_g<16, +1>(v, one);                                  // v[k3], natural order
         float2 u[16];
 #pragma unroll
         for (int k3 = 0; k3 < 16; k3 += 2) {
@@ -156,39 +289,64 @@ RRC_HD void phase_mid_c(int tid, const float2* Hp, const float2* Hres, float2* s
             u[bitrev(k3 + 1, 4)] = cmul(v[k3 + 1], make_float2(h.z, h.w));
         }
         dit<16, -1>(u);                                         // u[n3], natural order
+        if constexpr (TWC) {
+#pragma unroll
+            for (int n3 = 1; n3 < 16; ++n3) u[n3] = cmul_conj(u[n3], pw[n3]);
+        }
+        turn.release();
 #pragma unroll
         for (int n3 = 0; n3 < 16; ++n3) row[n3] = u[n3];
     }
 }
-RRC_HD void phase_mid_bi(int tid, const float2* tw2, float2* sm) {
+template <bool TW = true, class Turn = NoTurn>
+RRC_HD void phase_mid_bi(int tid, const float2* tw2, float2* sm, Turn turn = Turn()) {
     const int k1 = tid >> 4, l = tid & 15;
     float2* col = sm + k1 * PLANE_PITCH + l;
     const float2* tw = tw2 + l;
     float2 v[32];
 #pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) v[bitrev(k2, 5)] = cmul_conj(col[k2 * ROW_PITCH], tw[k2 * 16]);
-    dit<32, -1>(v);
+    for (int k2 = 0; k2 < 32; ++k2) v[bitrev(k2, 5)] = col[k2 * ROW_PITCH];
+    const float one = turn.acquire();
+    if constexpr (TW) {
+#pragma unroll
+        for (int k2 = 0; k2 < 32; ++k2) v[bitrev(k2, 5)] = cmul_conj(v[bitrev(k2, 5)], tw[k2 * 16]);
+        dit<32, -1>(v);
+    } else {
+        dit_g<32, -1>(v, one);
+    }
+    turn.release();
 #pragma unroll
     for (int n2 = 0; n2 < 32; ++n2) col[n2 * ROW_PITCH] = v[n2];
 }
-RRC_HD void phase_mid(int tid, const float2* tw2, const float2* Hp, const float2* Hres, float2* sm) {
-    phase_mid_b(tid, tw2, sm);
+template <bool TWC = false, class Turn = NoTurn>
+RRC_HD void phase_mid(int tid, const float2* tw2, const float2* Hp, const float2* Hres, float2* sm, Turn turn = Turn()) {
+    phase_mid_b<!TWC>(tid, tw2, sm, turn);
     RRC_SYNCWARP();
-    phase_mid_c(tid, Hp, Hres, sm);
+    phase_mid_c<TWC>(tid, Hp, Hres, sm, turn, tw2);
     RRC_SYNCWARP();
-    phase_mid_bi(tid, tw2, sm);
+    phase_mid_bi<!TWC>(tid, tw2, sm, turn);
 }
 
 // Phase A': tid = t; conj twiddle, IDFT32 over k1 -> n1; store valid outputs.
-template <bool DECIM, bool ACCUM>
-RRC_HD void phase_ai(int tid, long long blk, const BlockIO& io, const float2* tw1, const float2* sm) {
-    float2 p[32];
-    powers32(tw1[tid], p);
+struct NoHook { RRC_HD void operator()() const {} };
+// after_load() runs once the thread has read its 32 exchange-buffer words (the staged kernel puts a
+// CTA barrier and the next block's stage_input there).
+template <bool DECIM, bool ACCUM, class Turn = NoTurn, class AfterLoad = NoHook>
+RRC_HD void phase_ai(int tid, long long blk, const BlockIO& io, const float2* tw1, const float2* sm, Turn turn = Turn(),
+                     AfterLoad after_load = AfterLoad()) {
     const float2* s = sm + (tid >> 4) * ROW_PITCH + (tid & 15);
     float2 v[32];
 #pragma unroll
-    for (int k1 = 0; k1 < 32; ++k1) v[bitrev(k1, 5)] = cmul_conj(s[k1 * PLANE_PITCH], p[k1]);
+    for (int k1 = 0; k1 < 32; ++k1) v[bitrev(k1, 5)] = s[k1 * PLANE_PITCH];
+    after_load();
+    turn.acquire();
+    const float2 w1 = tw1[tid];
+    float2 p[32];
+    powers32(w1, p);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) v[bitrev(k1, 5)] = cmul_conj(v[bitrev(k1, 5)], p[k1]);
     dit<32, -1>(v);
+    turn.release();
     // v[n1] is segment element n = tid + 512*n1; elements n >= T1 are valid
     // outputs, filter output index o = o0 + n.
     const long long o0 = blk * (long long)io.V - io.T1;

@@ -4,6 +4,7 @@
 // and twiddle logic be checked against the oracle without a GPU.
 // Built by tests/test_emul.py with `nvcc -x cu` (host code only).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -33,11 +34,26 @@ extern "C" int emul_fftfilt(const float* taps, long long ntaps, const float* in,
         std::vector<float2> sm(SMEM_ELEMS), hres(HRES_ELEMS);
         for (int t = 0; t < NT; ++t) load_hres(t, Hp.data(), hres.data());
         const long long nblocks = (n + io.V - 1) / io.V;
+        // RRC_EMUL_FFTFILT_MODE: 0 = table twiddles in B/B' (default), 1 = twiddles from powers in C
+        // (TWC), 2 = TWC + staged input (stage_input / phase_a_staged).
+        const char* me = getenv("RRC_EMUL_FFTFILT_MODE");
+        const int mode = me ? atoi(me) : 0;
         for (long long blk = 0; blk < nblocks; ++blk) {
-            for (int t = 0; t < NT; ++t) phase_a(t, blk, io, tw1.data(), sm.data());
-            for (int t = 0; t < NT; ++t) phase_mid_b(t, tw2.data(), sm.data());
-            for (int t = 0; t < NT; ++t) phase_mid_c(t, Hp.data(), hres.data(), sm.data());
-            for (int t = 0; t < NT; ++t) phase_mid_bi(t, tw2.data(), sm.data());
+            if (mode == 2) {
+                for (int t = 0; t < NT; ++t) stage_input(t, blk, io, sm.data());
+                for (int t = 0; t < NT; ++t) phase_a_staged(t, tw1.data(), sm.data());
+            } else {
+                for (int t = 0; t < NT; ++t) phase_a(t, blk, io, tw1.data(), sm.data());
+            }
+            if (mode == 0) {
+                for (int t = 0; t < NT; ++t) phase_mid_b(t, tw2.data(), sm.data());
+                for (int t = 0; t < NT; ++t) phase_mid_c(t, Hp.data(), hres.data(), sm.data());
+                for (int t = 0; t < NT; ++t) phase_mid_bi(t, tw2.data(), sm.data());
+            } else {
+                for (int t = 0; t < NT; ++t) phase_mid_b<false>(t, tw2.data(), sm.data());
+                for (int t = 0; t < NT; ++t) phase_mid_c<true>(t, Hp.data(), hres.data(), sm.data(), NoTurn(), tw2.data());
+                for (int t = 0; t < NT; ++t) phase_mid_bi<false>(t, tw2.data(), sm.data());
+            }
             for (int t = 0; t < NT; ++t) {
                 if (off == 0) { if (decim) phase_ai<true, false>(t, blk, io, tw1.data(), sm.data()); else phase_ai<false, false>(t, blk, io, tw1.data(), sm.data()); }
                 else          { if (decim) phase_ai<true, true>(t, blk, io, tw1.data(), sm.data()); else phase_ai<false, true>(t, blk, io, tw1.data(), sm.data()); }

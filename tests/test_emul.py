@@ -52,6 +52,17 @@ def test_emulated_kernel_matches_f64_convolution(emul, ntaps, n, variant):
     assert O.rel_rms(emul(taps, x, variant=variant), O.conv_full_f64_fft(x, taps, n)) <= 1e-5
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("ntaps,n", [(1, 3000), (193, 8000), (4097, 40_000), (64, 16384 * 2 + 5), (16385, 40_000)])
+def test_emulated_kernel_twiddles_in_phase_c_and_staged_input(emul, monkeypatch, ntaps, n, mode):
+    """fftfilt_core.cuh TWC path (W_512 twiddles from powers inside phase C) and stage_input /
+    phase_a_staged: same index math and values as the table-twiddle kernel."""
+    monkeypatch.setenv("RRC_EMUL_FFTFILT_MODE", str(mode))
+    taps = (O.low_pass_n(1.0, 0.05, ntaps).astype(np.complex64) * (1 + 0.3j)) if ntaps > 2 else np.array([0.5 - 0.25j], np.complex64)
+    x = O.synth_c32(7, 0, n)
+    assert O.rel_rms(emul(taps, x, variant=32), O.conv_full_f64_fft(x, taps, n)) <= 1e-5
+
+
 @pytest.mark.parametrize("variant", [32, 16])
 def test_emulated_kernel_history_and_decimation(emul, variant):
     taps = O.low_pass_n(1.0, 0.1, 301).astype(np.complex64)

@@ -1,0 +1,79 @@
+// Do a shared-memory burst and an FP burst overlap across warps of one SM?  16 warps per SM, each
+// loops  [32 x LDS.64 column read] -> [DFT32 + twiddle multiply: 516 FP instr] -> [32 x STS.64] ,
+// the per-warp structure of the FftFilter kernel's phase B, with (a) all warps starting together,
+// (b) the 8 warps of group 1 delayed by half a period, (c) token ping-pong between the groups
+// (named barriers), (d) only the FP part, (e) only the shared-memory part.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../../rustradio_b200/csrc -o phase_overlap phase_overlap.cu
+#include <cstdio>
+#include "fft_regs.cuh"
+using namespace rrc::fftr;
+#define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("cuda error %s line %d\n", cudaGetErrorString(e), __LINE__); return 1;}}while(0)
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) k(float2* out, int iters, int delay) {
+    extern __shared__ __align__(16) float2 sm[];
+    __shared__ float s_one;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 32 * 544; i += 512) sm[i] = make_float2(1e-3f * i, 0.f);
+    if (tid == 0) s_one = 1.0f;
+    __syncthreads();
+    const int g = (tid >> 7) & 1;
+    float2* col = sm + (tid >> 4) * 544 + (tid & 15);
+    const unsigned one_addr = (unsigned)__cvta_generic_to_shared(&s_one);
+    if (MODE == 1 && g == 1) { const long long t0 = clock64(); while (clock64() - t0 < delay) { } }
+    if (MODE == 2 && g == 1) asm volatile("bar.arrive 1, 512;" ::: "memory");
+    float2 v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = make_float2(tid * 1e-3f, i);
+    for (int it = 0; it < iters; ++it) {
+        if (MODE != 3) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[bitrev(i, 5)] = col[i * 17];
+        }
+        float one;
+        if (MODE == 2) asm volatile("bar.sync %1, 512;\n\tld.volatile.shared.f32 %0, [%2];" : "=f"(one) : "r"(1 + g), "r"(one_addr) : "memory");
+        else asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(one) : "r"(one_addr) : "memory");
+        if (MODE != 4) {
+            dit_g<32, +1>(v, one);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = cmul(v[i], make_float2(0.999f, 0.001f * (i & 7)));
+        }
+        if (MODE == 2) asm volatile("bar.arrive %0, 512;" ::"r"(2 - g) : "memory");
+        if (MODE != 3) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) col[i * 17] = v[i];
+            __syncwarp();
+        }
+        if (MODE == 5 && (it & 3) == 3) __syncthreads();
+        if (MODE == 6 && (it & 1) == 1) __syncthreads();
+    }
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s = cadd(s, v[i]);
+    if (s.x == 123.456f) out[tid] = s;
+}
+
+int main() {
+    float2* out; CK(cudaMalloc(&out, 4096 * 8));
+    const int SMEM = 200 * 1024, iters = 2000;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const char* names[] = {"all 16 warps in phase", "group 1 delayed by half a period", "token ping-pong (named barriers)", "FP only", "shared memory only", "free-running + __syncthreads every 4 iterations", "free-running + __syncthreads every 2 iterations"};
+    float ms[7];
+    for (int mode = 0; mode < 7; ++mode) {
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(e0);
+            switch (mode) {
+                case 0: CK(cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); k<0><<<148, 512, SMEM>>>(out, iters, 0); break;
+                case 1: CK(cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); k<1><<<148, 512, SMEM>>>(out, iters, 1800); break;
+                case 2: CK(cudaFuncSetAttribute(k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); k<2><<<148, 512, SMEM>>>(out, iters, 0); break;
+                case 3: CK(cudaFuncSetAttribute(k<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); k<3><<<148, 512, SMEM>>>(out, iters, 0); break;
+                case 4: CK(cudaFuncSetAttribute(k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); k<4><<<148, 512, SMEM>>>(out, iters, 0); break;
+                case 5: CK(cudaFuncSetAttribute(k<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); k<5><<<148, 512, SMEM>>>(out, iters, 0); break;
+                case 6: CK(cudaFuncSetAttribute(k<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); k<6><<<148, 512, SMEM>>>(out, iters, 0); break;
+            }
+            cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms[mode], e0, e1);
+        }
+        printf("%-52s %8.3f ms  %7.0f cycles per iteration (16 warps x [32 LDS.64, 516 FP, 32 STS.64])\n", names[mode], ms[mode], ms[mode] * 1e-3 * 1.965e9 / iters);
+    }
+    return 0;
+}
