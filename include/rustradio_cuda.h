@@ -178,6 +178,31 @@ int rrc_fftfilt_decim_run(rrc_fftfilt_t* h, const float* in_dev, size_t n, size_
 /* Host-buffer form for a whole stream: n_in samples in, floor(n_in/nsamples)*nsamples out. */
 int rrc_fftfilt_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, float* out_host, size_t* n_out);
 
+/* ------------------------------------------------------- RtlSdrDecode --- */
+/*
+ * SURVEY 8f rank 1 — the block that feeds the hot path in the rtl_fm chain.
+ * Replaces RtlSdrDecode::work (src/rtlsdr_decode.rs:18-48): byte pairs (I, Q)
+ * -> Complex((I - 127.0) * 0.008, (Q - 127.0) * 0.008); bit-exact; tags dropped.
+ */
+/* Integer part of work() run to its WaitForStream: with in_len_bytes readable
+ * bytes and out_free output samples, consume (in_len & !1, capped by 2*out_free)
+ * bytes and produce half as many samples (:23-33); then WaitForStream(src, 2)
+ * or WaitForStream(dst, 1). */
+int rrc_rtlsdr_decode_plan(size_t in_len_bytes, size_t out_free, size_t* consume_bytes, size_t* produce,
+                           size_t* wait_need, int* wait_on_output);
+/* n_bytes/2 samples from device bytes to device c32 (any alignment). */
+int rrc_rtlsdr_decode_run(int device, const unsigned char* in_dev, size_t n_bytes, float* out_dev_c32, void* stream);
+int rrc_rtlsdr_decode_run_host(int device, const unsigned char* in_host, size_t n_bytes, float* out_host_c32, size_t* n_out);
+/* Fused form: the FIR / FftFilter kernels decode u8 I/Q pairs in their first
+ * load, so RtlSdrDecode -> FirFilter<Complex> / FftFilter chains never
+ * materialise the c32 stream (and *_run_host moves 2 B/sample over PCIe).
+ * After set_input_u8iq(h, 1) every `in` pointer of that handle's run /
+ * run_batch / decim_run / run_host calls is a 2-byte aligned array of u8 pairs;
+ * counts and strides stay in samples; outputs and carried history stay c32.
+ * Results equal RtlSdrDecode followed by the c32 filter bit for bit. */
+int rrc_fir_set_input_u8iq(rrc_fir_t* h, int on);
+int rrc_fftfilt_set_input_u8iq(rrc_fftfilt_t* h, int on);
+
 /* -------------------------------------------------- RationalResampler --- */
 /*
  * Replaces RationalResampler::new / work (src/rational_resampler.rs:125-206):
@@ -282,6 +307,9 @@ int rrb_rational_resampler_new(rrb_rstream_t* src, size_t interp, size_t deci,
                                size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
 int rrb_quadrature_demod_new(rrb_rstream_t* src, float gain,
                              size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+/* RtlSdrDecode::new(src: ReadStream<u8>) -> (Self, ReadStream<Complex>)  (src/rtlsdr_decode.rs:9-16) */
+int rrb_rtlsdr_decode_new(rrb_rstream_t* src,
+                          size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
 int rrb_block_work(rrb_block_t* b, int* kind, size_t* stream_id, size_t* need);
 int rrb_block_eof(rrb_block_t* b, int* eof);
 const char* rrb_block_name(rrb_block_t* b);

@@ -295,6 +295,29 @@ class RationalResampler:
         return (not self.r.has_pending) and self.src.eof()
 
 
+class RtlSdrDecode:
+    """src/rtlsdr_decode.rs:18-48: u8 pairs -> Complex; tags dropped; never returns Again."""
+
+    def __init__(self, src: Stream, stream_bytes=DEFAULT_STREAM_SIZE):
+        self.src = src
+        self.out = Stream(np.complex64, stream_bytes)
+
+    def work(self) -> BlockRet:
+        while True:
+            inp, _ = self.src.read_buf()
+            isamples = len(inp) & ~1
+            if isamples == 0:
+                return BlockRet(WAIT, self.src, 2)
+            out = self.out.write_buf()
+            if len(out) == 0:
+                return BlockRet(WAIT, self.out, 1)
+            isamples = min(isamples, len(out) * 2)
+            osamples = isamples // 2
+            out[:osamples] = O.rtlsdr_decode(inp[:isamples])
+            self.src.consume(isamples)
+            self.out.produce(osamples, [])
+
+
 def _uint(dt):
     return {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[np.dtype(dt).itemsize]
 

@@ -64,6 +64,7 @@ def _load(name: str) -> C.CDLL:
         "orc_resample_out_count": (i64, [i64, i64, i64]),
         "orc_quad_demod": (None, [vp, i64, f32, vp]),
         "orc_quad_demod_f64": (None, [vp, i64, f64, vp]),
+        "orc_rtlsdr_decode": (None, [vp, i64, vp]),
         "orc_signal_source_complex": (None, [f32, f32, f32, C.POINTER(f64), vp, i64]),
         "orc_synth_f32": (None, [C.c_uint64, C.c_uint64, vp, i64]),
     }
@@ -298,6 +299,22 @@ def quad_demod(x, gain: float = 1.0, *, f64: bool = False, fast: bool = False) -
         else:
             lib(fast).orc_quad_demod(_p(x), len(x), gain, _p(out))
     return out
+
+
+# -------------------------------------------------------- rtlsdr decode ----
+def rtlsdr_decode(raw) -> np.ndarray:
+    """RtlSdrDecode (src/rtlsdr_decode.rs:35-43): u8 I/Q pairs -> c32, (b - 127) * 0.008."""
+    raw = np.ascontiguousarray(raw, np.uint8)
+    out = np.empty(len(raw) // 2, np.complex64)
+    if len(out):
+        lib().orc_rtlsdr_decode(_p(raw), len(raw), _p(out))
+    return out
+
+
+def synth_u8(seed: int, first_index: int, n: int) -> np.ndarray:
+    """Deterministic u8 I/Q bytes: the top byte of the same splitmix64 stream synth_f32 uses."""
+    f = synth_f32(seed, first_index, n)
+    return np.clip(np.floor((f.astype(np.float64) + 1.0) * 128.0), 0, 255).astype(np.uint8)
 
 
 # ------------------------------------------------------------ fixtures ----

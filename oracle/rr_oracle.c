@@ -504,6 +504,21 @@ void orc_quad_demod_f64(const c32* x, int64_t n_in, double gain, double* out) {
     }
 }
 
+/* --------------------------------------------------------- RtlSdrDecode -- */
+
+/*
+ * src/rtlsdr_decode.rs:35-43: pairs of bytes (I, Q) ->
+ * Complex((I - 127.0) * 0.008, (Q - 127.0) * 0.008), all in f32, subtraction
+ * rounded before the multiplication.  n_bytes & !1 bytes are used (:23).
+ */
+void orc_rtlsdr_decode(const uint8_t* in, int64_t n_bytes, c32* out) {
+    for (int64_t i = 0; i + 1 < n_bytes; i += 2) {
+        float a = (float)in[i], b = (float)in[i + 1];
+        out[i / 2].re = (a - 127.0f) * 0.008f;
+        out[i / 2].im = (b - 127.0f) * 0.008f;
+    }
+}
+
 /* --------------------------------------------- test-fixture restatements -- */
 
 /* SignalSourceComplex iterator, src/signal_source.rs:39-51. `current` carried. */

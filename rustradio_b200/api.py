@@ -94,6 +94,11 @@ _SIGS = {
     "rrc_quad_demod_run": [_i, _vp, _sz, _f, _vp, _vp],
     "rrc_quad_demod_run_batch": [_i, _vp, _sz, _sz, _f, _vp, _sz, _sz, _vp],
     "rrc_quad_demod_run_host": [_i, _vp, _sz, _f, _vp],
+    "rrc_rtlsdr_decode_plan": [_sz, _sz, _P(_sz), _P(_sz), _P(_sz), _P(_i)],
+    "rrc_rtlsdr_decode_run": [_i, _vp, _sz, _vp, _vp],
+    "rrc_rtlsdr_decode_run_host": [_i, _vp, _sz, _vp, _P(_sz)],
+    "rrc_fir_set_input_u8iq": [_vp, _i],
+    "rrc_fftfilt_set_input_u8iq": [_vp, _i],
 }
 
 
@@ -284,6 +289,11 @@ class Fir:
     def reset(self):
         _ck(lib().rrc_fir_reset(self.h))
 
+    def set_input_u8iq(self, on: bool = True):
+        """Inputs become u8 I/Q pairs, decoded like RtlSdrDecode inside the kernel's first load."""
+        _ck(lib().rrc_fir_set_input_u8iq(self.h, int(on)))
+        self.in_u8 = bool(on)
+
     @property
     def uses_real_taps(self) -> bool:
         y = _i(0)
@@ -304,13 +314,15 @@ class Fir:
                                               out_n, nchan, stream))
 
     def run_host(self, x, out=None) -> np.ndarray:
-        """Whole-stream host->host (pipelined H2D/kernel/D2H)."""
+        """Whole-stream host->host (pipelined H2D/kernel/D2H).  In u8 I/Q mode x is the byte array."""
         dt = np.complex64 if self.cplx else np.float32
-        xa = x.array if isinstance(x, PinnedBuffer) else np.ascontiguousarray(x, dt)
-        n_out = self.out_count(len(xa))
+        u8 = getattr(self, "in_u8", False)
+        xa = x.array if isinstance(x, PinnedBuffer) else np.ascontiguousarray(x, np.uint8 if u8 else dt)
+        n_in = len(xa) // 2 if u8 else len(xa)
+        n_out = self.out_count(n_in)
         oa = out.array if isinstance(out, PinnedBuffer) else (out if out is not None else np.empty(n_out, dt))
         n = _sz(0)
-        _ck(lib().rrc_fir_run_host(self.h, xa.ctypes.data, len(xa), oa.ctypes.data, C.byref(n)))
+        _ck(lib().rrc_fir_run_host(self.h, xa.ctypes.data, n_in, oa.ctypes.data, C.byref(n)))
         return oa[: n.value]
 
     # convenience for tests: upload, run, download
@@ -365,6 +377,11 @@ class FftFilt:
     def reset(self, stream: int = 0):
         _ck(lib().rrc_fftfilt_reset(self.h, stream))
 
+    def set_input_u8iq(self, on: bool = True):
+        """Inputs become u8 I/Q pairs, decoded like RtlSdrDecode inside the kernel's first load."""
+        _ck(lib().rrc_fftfilt_set_input_u8iq(self.h, int(on)))
+        self.in_u8 = bool(on)
+
     def set_history(self, d_hist, n: int, stream: int = 0):
         _ck(lib().rrc_fftfilt_set_history(self.h, _ptr(d_hist), n, stream))
 
@@ -377,11 +394,13 @@ class FftFilt:
         return no.value
 
     def run_host(self, x, out=None) -> np.ndarray:
-        xa = x.array if isinstance(x, PinnedBuffer) else np.ascontiguousarray(x, np.complex64)
-        n_out = (len(xa) // self.nsamples) * self.nsamples
+        u8 = getattr(self, "in_u8", False)
+        xa = x.array if isinstance(x, PinnedBuffer) else np.ascontiguousarray(x, np.uint8 if u8 else np.complex64)
+        n_in = len(xa) // 2 if u8 else len(xa)
+        n_out = (n_in // self.nsamples) * self.nsamples
         oa = out.array if isinstance(out, PinnedBuffer) else (out if out is not None else np.empty(n_out, np.complex64))
         n = _sz(0)
-        _ck(lib().rrc_fftfilt_run_host(self.h, xa.ctypes.data, len(xa), oa.ctypes.data, C.byref(n)))
+        _ck(lib().rrc_fftfilt_run_host(self.h, xa.ctypes.data, n_in, oa.ctypes.data, C.byref(n)))
         return oa[: n.value]
 
     def filter(self, x: np.ndarray) -> np.ndarray:
@@ -447,6 +466,27 @@ class Resampler:
             lib().rrc_resampler_destroy(self.h)
         except Exception:
             pass
+
+
+# -------------------------------------------------------- rtlsdr decode ---
+def rtlsdr_decode_plan(in_len_bytes: int, out_free: int):
+    """(consume_bytes, produce, wait_need, wait_on_output) — src/rtlsdr_decode.rs:20-46."""
+    v = [_sz(0) for _ in range(3)]
+    w = _i(0)
+    _ck(lib().rrc_rtlsdr_decode_plan(in_len_bytes, out_free, *[C.byref(x) for x in v], C.byref(w)))
+    return v[0].value, v[1].value, v[2].value, w.value
+
+
+def rtlsdr_decode(d_in, n_bytes: int, d_out, device: int = 0, stream: int = 0):
+    _ck(lib().rrc_rtlsdr_decode_run(device, _ptr(d_in), n_bytes, _ptr(d_out), stream))
+
+
+def rtlsdr_decode_host(raw: np.ndarray, device: int = 0) -> np.ndarray:
+    raw = np.ascontiguousarray(raw, np.uint8)
+    out = np.empty(len(raw) // 2, np.complex64)
+    n = _sz(0)
+    _ck(lib().rrc_rtlsdr_decode_run_host(device, raw.ctypes.data if len(raw) else None, len(raw), out.ctypes.data if len(out) else None, C.byref(n)))
+    return out[: n.value]
 
 
 # ---------------------------------------------------------------- demod ---

@@ -550,6 +550,40 @@ int QuadratureDemod::work(BlockRet* ret) {    // src/quadrature_demod.rs:46-113
     }
 }
 
+// --------------------------------------------------------------- RtlSdrDecode -----
+int RtlSdrDecode::create(std::unique_ptr<ReadStream> src, const StreamOpts& o, std::unique_ptr<RtlSdrDecode>* out) {
+    if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    if (src->buffer().elem() != 1) return fail(RRC_ERR_INVALID, "RtlSdrDecode: stream must carry u8");
+    std::unique_ptr<RtlSdrDecode> b(new RtlSdrDecode());
+    b->device_ = o.device;
+    b->src_ = std::move(src);
+    RRC_TRY(make_output(8, o, &b->dst_, &b->out_r_));
+    *out = std::move(b);
+    return RRC_OK;
+}
+
+int RtlSdrDecode::work(BlockRet* ret) {       // src/rtlsdr_decode.rs:18-48
+    for (;;) {
+        const char* in; size_t in_len;
+        src_->buffer().read_window(&in, &in_len, nullptr);    // "TODO: handle tags" (:21): dropped
+        size_t isamples = in_len & ~(size_t)1;                // :23
+        if (isamples == 0) { *ret = BlockRet::wait(src_.get(), 2); return RRC_OK; }
+        char* outp; size_t cap;
+        dst_->buffer().write_window(&outp, &cap);
+        if (cap == 0) { *ret = BlockRet::wait(dst_.get(), 1); return RRC_OK; }
+        isamples = std::min(isamples, cap * 2);               // :32
+        const size_t osamples = isamples / 2;
+        const char* din; char* dout;
+        RRC_TRY(stage_input(src_->buffer(), in, isamples, sin_, device_, &din));
+        RRC_TRY(stage_output(dst_->buffer(), outp, osamples * 8, sout_, device_, &dout));
+        RRC_TRY(rrc_rtlsdr_decode_run(device_, (const unsigned char*)din, isamples, (float*)dout, graph_stream(device_)));
+        RRC_TRY(finish_output(dst_->buffer(), outp, osamples * 8, sout_, device_));
+        if (src_->buffer().residency() == Residency::Host) RRC_CUDA(cudaStreamSynchronize((cudaStream_t)graph_stream(device_)));
+        src_->buffer().consume(isamples);
+        dst_->buffer().produce(osamples, {});
+    }
+}
+
 // --------------------------------------------------------------- VectorSource -----
 int VectorSource::create(const void* data, size_t n, size_t elem_size, uint64_t repeat, const StreamOpts& o,
                          std::unique_ptr<VectorSource>* out) {

@@ -294,6 +294,21 @@ private:
     Scratch sin_, sout_;
 };
 
+// RtlSdrDecode (src/rtlsdr_decode.rs:9-48): ReadStream<u8> -> WriteStream<Complex>.
+class RtlSdrDecode : public Block {
+public:
+    static int create(std::unique_ptr<ReadStream> src, const StreamOpts& o, std::unique_ptr<RtlSdrDecode>* out);
+    int work(BlockRet* ret) override;
+    const char* block_name() const override { return "RtlSdrDecode"; }
+    bool eof() override { return src_->eof(); }
+private:
+    RtlSdrDecode() = default;
+    std::unique_ptr<ReadStream> src_;
+    std::unique_ptr<WriteStream> dst_;
+    int device_ = 0;
+    Scratch sin_, sout_;
+};
+
 // Test fixture: VectorSource<T> with its tags (src/vector_source.rs:97-144).
 class VectorSource : public Block {
 public:

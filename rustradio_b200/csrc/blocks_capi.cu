@@ -199,6 +199,13 @@ int rrb_quadrature_demod_new(rrb_rstream_t* src, float gain, size_t bytes, int r
     return finish(std::move(b), blk, out);
 }
 
+int rrb_rtlsdr_decode_new(rrb_rstream_t* src, size_t bytes, int res, int device, rrb_block_t** blk, rrb_rstream_t** out) {
+    if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
+    std::unique_ptr<rr::RtlSdrDecode> b;
+    RRC_TRY(rr::RtlSdrDecode::create(take(src), opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out);
+}
+
 int rrb_block_work(rrb_block_t* b, int* kind, size_t* stream_id, size_t* need) {
     if (!b || !b->b || !kind) return fail(RRC_ERR_INVALID, "NULL argument");
     rr::BlockRet r;

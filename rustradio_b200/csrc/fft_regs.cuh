@@ -46,6 +46,26 @@ RRC_HD constexpr int bitrev(int x, int bits) {
 }
 RRC_HD constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n >> 1); }
 
+// RtlSdrDecode fused into a kernel's first load (rustradio src/rtlsdr_decode.rs:35-43; SURVEY 8f
+// rank 1): one sample is two bytes (I, Q) and decodes to ((I - 127) * 0.008, (Q - 127) * 0.008),
+// the subtraction rounded before the multiplication, exactly like the reference block.
+RRC_HD float2 decode_u8iq(unsigned int lo, unsigned int hi) {
+#if defined(__CUDA_ARCH__)
+    return make_float2(__fmul_rn(__fsub_rn((float)lo, 127.0f), 0.008f), __fmul_rn(__fsub_rn((float)hi, 127.0f), 0.008f));
+#else
+    volatile float a = (float)lo - 127.0f, b = (float)hi - 127.0f;
+    return make_float2(a * 0.008f, b * 0.008f);
+#endif
+}
+// Sample g of an input stream that is either Complex<f32> (u8 == 0) or u8 I/Q pairs (2-byte aligned).
+RRC_HD float2 ld_iq(const float2* in, long long g, int u8) {
+    if (u8) {
+        const unsigned int w = reinterpret_cast<const unsigned short*>(in)[g];
+        return decode_u8iq(w & 0xffu, w >> 8);
+    }
+    return in[g];
+}
+
 RRC_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 RRC_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 RRC_HD float2 cmul(float2 a, float2 b) {

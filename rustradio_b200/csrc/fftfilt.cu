@@ -36,8 +36,9 @@ constexpr size_t FFTFILT_SMEM = (size_t)(fftk::SMEM_ELEMS + 512 + 512 + fftk::HR
 __device__ __forceinline__ void prefetch_segment(const BlockIO& io, long long nb, long long nblocks, int tid) {
     const long long seg0 = nb * (long long)io.V - io.T1 - io.shift + (long long)(tid >> 5) * 1024;
     if ((tid & 31) == 0 && nb < nblocks && seg0 >= 0 && seg0 + 1024 <= io.n_in) {
-        const unsigned long long a = (reinterpret_cast<unsigned long long>(io.in + seg0) + 15ull) & ~15ull;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(8192 - 16) : "memory");
+        const unsigned long long esz = io.in_u8 ? 2 : 8;         // bytes per input sample
+        const unsigned long long a = (reinterpret_cast<unsigned long long>(io.in) + (unsigned long long)seg0 * esz + 15ull) & ~15ull;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)(1024 * esz - 16)) : "memory");
     }
 }
 
@@ -192,10 +193,10 @@ fftfilt16_kernel(const BlockIO io, const float2* __restrict__ Hd, const float2* 
 
 // hist_next[i] = x[n - T1 + i] over the concatenation (hist_cur ++ in).
 __global__ void fftfilt_hist_kernel(const float2* __restrict__ hist_cur, const float2* __restrict__ in,
-                                    long long n, int T1, float2* __restrict__ hist_next) {
+                                    long long n, int T1, float2* __restrict__ hist_next, int in_u8) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T1; i += gridDim.x * blockDim.x) {
         const long long s = n - T1 + i;
-        hist_next[i] = s >= 0 ? in[s] : hist_cur[s + T1];
+        hist_next[i] = s >= 0 ? fftr::ld_iq(in, s, in_u8) : hist_cur[s + T1];
     }
 }
 
@@ -252,6 +253,7 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
     io.T1_total = h->T1;
     io.deci = (int)deci;
     io.skip = (long long)skip;
+    io.in_u8 = h->in_u8;
     const bool decim = !(deci == 1 && skip == 0);
     long long shift = 0;
     for (size_t p = 0; p < h->part_T1.size(); ++p) {
@@ -268,7 +270,7 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
         shift += io.T1 + 1;
     }
     if (h->T1 > 0) {
-        fftfilt_hist_kernel<<<(h->T1 + 255) / 256, 256, 0, st>>>(h->hist[h->cur], io.in, (long long)n, h->T1, h->hist[h->cur ^ 1]);
+        fftfilt_hist_kernel<<<(h->T1 + 255) / 256, 256, 0, st>>>(h->hist[h->cur], io.in, (long long)n, h->T1, h->hist[h->cur ^ 1], h->in_u8);
         RRC_CHECK_LAUNCH();
         count_launch();
         h->cur ^= 1;
@@ -383,6 +385,12 @@ int rrc_fftfilt_set_history(rrc_fftfilt_t* h, const float* hist, size_t n, void*
     return RRC_OK;
 }
 
+int rrc_fftfilt_set_input_u8iq(rrc_fftfilt_t* h, int on) {
+    if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
+    h->in_u8 = on ? 1 : 0;
+    return RRC_OK;
+}
+
 int rrc_fftfilt_geometry(const rrc_fftfilt_t* h, size_t* fft_size, size_t* valid) {
     if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
     if (fft_size) *fft_size = fftk::N;
@@ -394,6 +402,7 @@ int rrc_fftfilt_run(rrc_fftfilt_t* h, const float* in, size_t n, float* out, voi
     if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
     if (n == 0) return RRC_OK;
     if (!in || !out) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    if (h->in_u8 && (reinterpret_cast<uintptr_t>(in) & 1)) return fail(RRC_ERR_INVALID, "u8 I/Q input must be 2-byte aligned");
     RRC_CUDA(cudaSetDevice(h->device));
     return launch(h, in, n, out, n, 1, 0, as_stream(stream));
 }
@@ -406,6 +415,7 @@ int rrc_fftfilt_decim_run(rrc_fftfilt_t* h, const float* in, size_t n, size_t de
     if (n_out) *n_out = cnt;
     if (n == 0) return RRC_OK;
     if (!in || (!out && cnt)) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    if (h->in_u8 && (reinterpret_cast<uintptr_t>(in) & 1)) return fail(RRC_ERR_INVALID, "u8 I/Q input must be 2-byte aligned");
     RRC_CUDA(cudaSetDevice(h->device));
     // deci == 1 && skip == 0 degenerates to the plain path; otherwise the store
     // predicate in phase A' keeps y[skip + k*deci].
@@ -416,7 +426,7 @@ int rrc_fftfilt_decim_run(rrc_fftfilt_t* h, const float* in, size_t n, size_t de
         if (cnt) RRC_TRY(fold_launch(h, in, n, out, cnt, skip, as_stream(stream)));
         if (h->T1 > 0) {
             fftfilt_hist_kernel<<<(h->T1 + 255) / 256, 256, 0, as_stream(stream)>>>(
-                h->hist[h->cur], reinterpret_cast<const float2*>(in), (long long)n, h->T1, h->hist[h->cur ^ 1]);
+                h->hist[h->cur], reinterpret_cast<const float2*>(in), (long long)n, h->T1, h->hist[h->cur ^ 1], h->in_u8);
             RRC_CHECK_LAUNCH();
             count_launch();
             h->cur ^= 1;
@@ -436,11 +446,12 @@ int rrc_fftfilt_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, fl
     if (!in_host || !out_host) return fail(RRC_ERR_INVALID, "in/out is NULL");
     RRC_TRY(h->pipe.init(h->device));
     const size_t chunk = PIPE_CHUNK_SAMPLES;
-    RRC_TRY(h->pipe.reserve(std::min(chunk, total) * sizeof(float2), std::min(chunk, total) * sizeof(float2)));
+    const size_t esz = h->in_u8 ? 2 : sizeof(float2);           // input bytes per sample
+    RRC_TRY(h->pipe.reserve(std::min(chunk, total) * esz, std::min(chunk, total) * sizeof(float2)));
     int i = 0;
     for (size_t off = 0; off < total; off += chunk, ++i) {
         const size_t n = std::min(chunk, total - off);
-        RRC_TRY(h->pipe.stage_in(i, in_host + 2 * off, n * sizeof(float2)));
+        RRC_TRY(h->pipe.stage_in(i, reinterpret_cast<const char*>(in_host) + off * esz, n * esz));
         RRC_TRY(launch(h, (const float*)h->pipe.d_in[i & 1], n, (float*)h->pipe.d_out[i & 1], n, 1, 0, h->pipe.s_comp));
         RRC_TRY(h->pipe.drain_out(i, out_host + 2 * off, n * sizeof(float2)));
     }

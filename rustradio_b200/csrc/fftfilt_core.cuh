@@ -49,6 +49,7 @@ struct BlockIO {
     long long shift;         // input delay of this tap partition (p * partition length); 0 for a single partition
     int deci;                // output decimation (fused RationalResampler(1,deci)); 1 = none
     long long skip;          // first kept filter output index (decimation phase)
+    int in_u8 = 0;           // 1: `in` is u8 I/Q pairs (RtlSdrDecode fused into the load); hist is always c32
 };
 
 RRC_HD int phys(int k1, int r, int c) { return k1 * PLANE_PITCH + r * ROW_PITCH + c; }
@@ -128,9 +129,18 @@ RRC_HD void phase_a(int tid, long long blk, const BlockIO& io, const float2* tw1
     // input index of segment element 0 (tap partition p filters the input delayed by `shift`)
     const long long seg0 = blk * (long long)io.V - io.T1 - io.shift;
     if (seg0 >= 0 && seg0 + N <= io.n_in) {                     // interior block: no bounds checks
-        const float2* p = io.in + seg0 + tid;
+        if (io.in_u8) {
+            const unsigned short* p = reinterpret_cast<const unsigned short*>(io.in) + seg0 + tid;
+            unsigned int w[32];
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = p[512 * n1];
+            for (int n1 = 0; n1 < 32; ++n1) w[n1] = p[512 * n1];
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = decode_u8iq(w[n1] & 0xffu, w[n1] >> 8);
+        } else {
+            const float2* p = io.in + seg0 + tid;
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = p[512 * n1];
+        }
     } else {
         const long long g0 = seg0 + tid;
 #pragma unroll
@@ -138,7 +148,7 @@ RRC_HD void phase_a(int tid, long long blk, const BlockIO& io, const float2* tw1
             const long long g = g0 + 512 * n1;
             float2 x = make_float2(0.f, 0.f);
             if (g < 0) { if (g + io.T1_total >= 0) x = io.hist[g + io.T1_total]; }
-            else if (g < io.n_in) x = io.in[g];
+            else if (g < io.n_in) x = ld_iq(io.in, g, io.in_u8);
             v[bitrev(n1, 5)] = x;
         }
     }
@@ -166,7 +176,7 @@ RRC_HD void phase_a(int tid, long long blk, const BlockIO& io, const float2* tw1
 RRC_HD void stage_input(int tid, long long blk, const BlockIO& io, float2* sm) {
     float2* s = sm + (tid >> 4) * ROW_PITCH + (tid & 15);
     const long long seg0 = blk * (long long)io.V - io.T1 - io.shift;
-    if (seg0 >= 0 && seg0 + N <= io.n_in) {
+    if (seg0 >= 0 && seg0 + N <= io.n_in && !io.in_u8) {
         const float2* p = io.in + seg0 + tid;
 #if defined(__CUDA_ARCH__)
         const unsigned dst = (unsigned)__cvta_generic_to_shared(s);
@@ -183,7 +193,7 @@ RRC_HD void stage_input(int tid, long long blk, const BlockIO& io, float2* sm) {
             const long long g = g0 + 512 * n1;
             float2 x = make_float2(0.f, 0.f);
             if (g < 0) { if (g + io.T1_total >= 0) x = io.hist[g + io.T1_total]; }
-            else if (g < io.n_in) x = io.in[g];
+            else if (g < io.n_in) x = ld_iq(io.in, g, io.in_u8);
             s[n1 * PLANE_PITCH] = x;
         }
     }

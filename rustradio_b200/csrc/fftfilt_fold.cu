@@ -74,8 +74,9 @@ fftfilt_fold_kernel(const FoldIO io, const float2* __restrict__ Hc, const float2
             const long long nb = blk + ncl;
             const long long seg0 = fftf::seg_start<NC>(nb, io) + (long long)c * fftk::N + (long long)(tid >> 5) * 1024;
             if ((tid & 31) == 0 && nb < nblocks && seg0 >= 0 && seg0 + 1024 <= io.n_in) {
-                const unsigned long long a = (reinterpret_cast<unsigned long long>(io.in + seg0) + 15ull) & ~15ull;
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(8192 - 16) : "memory");
+                const unsigned long long esz = io.in_u8 ? 2 : 8;
+                const unsigned long long a = (reinterpret_cast<unsigned long long>(io.in) + (unsigned long long)seg0 * esz + 15ull) & ~15ull;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)(1024 * esz - 16)) : "memory");
             }
         }
         fftk::phase_mid_b(tid, s_tw2, sm);
@@ -178,6 +179,7 @@ int fold_launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_
     io.V = nc * fftk::N - io.T1eff;
     io.r = (int)(skip % fftf::FOLD_D);
     io.jbias = (long long)(skip / fftf::FOLD_D);
+    io.in_u8 = h->in_u8;
     if ((long long)n <= io.r) return RRC_OK;
     const long long nblocks = ((long long)n - io.r + io.V - 1) / io.V;
     return nc == 1 ? launch_fold<1>(h, io, nblocks, st) : launch_fold<4>(h, io, nblocks, st);

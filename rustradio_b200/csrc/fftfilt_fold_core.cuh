@@ -44,6 +44,7 @@ struct FoldIO {
     int T1_total;            // ntaps - 1 = length of hist
     int r;                   // skip mod 8: segment start alignment so kept outputs sit at n = 0 (mod 8)
     long long jbias;         // (skip - r) / 8
+    int in_u8 = 0;           // 1: `in` is u8 I/Q pairs (RtlSdrDecode fused into the load)
 };
 
 // p[k] = base * w^k, k = 0..31.
@@ -67,7 +68,7 @@ RRC_HD long long seg_start(long long blk, const FoldIO& io) { return blk * (long
 
 RRC_HD float2 fetch(const FoldIO& io, long long g) {
     if (g < 0) return g + io.T1_total >= 0 ? io.hist[g + io.T1_total] : make_float2(0.f, 0.f);
-    return g < io.n_in ? io.in[g] : make_float2(0.f, 0.f);
+    return g < io.n_in ? ld_iq(io.in, g, io.in_u8) : make_float2(0.f, 0.f);
 }
 
 // Phase A: load (NC = 4: with the radix-4 DIF step across the four quarters of the segment and the
@@ -83,7 +84,8 @@ RRC_HD void phase_a(int tid, int c, long long blk, const FoldIO& io, const float
                     const float2* twc, float2* sm, Hook before_store = Hook()) {
     float2 v[32];
     const long long seg0 = seg_start<NC>(blk, io);
-    const bool interior = seg0 >= 0 && seg0 + (long long)NC * N <= io.n_in;
+    // u8 I/Q input takes the bounds-checked path (fetch() decodes), c32 the pipelined one.
+    const bool interior = seg0 >= 0 && seg0 + (long long)NC * N <= io.n_in && !io.in_u8;
     if constexpr (NC == 1) {
         if (interior) {
             const float2* p = io.in + seg0 + tid;

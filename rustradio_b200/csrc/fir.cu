@@ -48,7 +48,13 @@ struct FirArgs {
     int translate;
     double ratio;                 // freq / samp_rate
     unsigned long long out_base;  // absolute index of out[0] (translate rotator)
+    int in_u8;                    // 1: `in` is u8 I/Q pairs, decoded while the tile is staged (c32 filters only)
 };
+
+// RtlSdrDecode fused into the tile load (src/rtlsdr_decode.rs:35-43).
+__device__ __forceinline__ float2 decode_iq(unsigned int w) {
+    return make_float2(__fmul_rn(__fsub_rn((float)(w & 0xffu), 127.0f), 0.008f), __fmul_rn(__fsub_rn((float)(w >> 8), 127.0f), 0.008f));
+}
 
 __device__ __forceinline__ void mac(float2& acc, float2 h, float2 x) {
     acc.x = fmaf(h.x, x.x, acc.x);
@@ -145,6 +151,23 @@ __device__ __forceinline__ void fir_load_tile(const FirArgs& a, ST* s_tile, long
     const ST* __restrict__ in = reinterpret_cast<const ST*>(a.in) + ch * a.in_stride;
     const int L = a.nseg * S;
     const long long g0 = bx * bstride * deci;
+    if constexpr (sizeof(ST) == 8) {
+        if (a.in_u8) {                                         // u8 I/Q -> c32 while staging (synchronous loads)
+            const unsigned short* __restrict__ in8 = reinterpret_cast<const unsigned short*>(a.in) + ch * a.in_stride;
+            int seg = t / S, rem = t - seg * S;
+            const int dseg = NT / S, drem = NT - dseg * S;
+            for (int e = t; e < L; e += NT) {
+                const long long g = g0 + e;
+                float2 v = make_float2(0.f, 0.f);
+                if (g < a.need) v = decode_iq(in8[g]);
+                reinterpret_cast<float2*>(s_tile)[seg * S1 + rem] = v;
+                seg += dseg; rem += drem;
+                if (rem >= S) { rem -= S; ++seg; }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            return;
+        }
+    }
     if (g0 + L <= a.need) {
         // Interior tile: asynchronous 8/4-byte copies global -> shared (LDGSTS), all in flight
         // at once, so the tile costs one memory latency instead of one per loop iteration.
@@ -482,7 +505,16 @@ __global__ void fir_generic_kernel(const FirArgs a) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.out_n; i += stride) {
         const ST* x = in + i * a.deci;
         ST acc; zero(acc);
-        for (int j = 0; j < a.ntaps; ++j) mac(acc, taps[j], x[j]);
+        if constexpr (sizeof(ST) == 8) {
+            if (a.in_u8) {
+                const unsigned short* x8 = reinterpret_cast<const unsigned short*>(a.in) + (long long)blockIdx.y * a.in_stride + i * a.deci;
+                for (int j = 0; j < a.ntaps; ++j) mac(acc, taps[j], decode_iq(x8[j]));
+            } else {
+                for (int j = 0; j < a.ntaps; ++j) mac(acc, taps[j], x[j]);
+            }
+        } else {
+            for (int j = 0; j < a.ntaps; ++j) mac(acc, taps[j], x[j]);
+        }
         if (a.translate) acc = apply_translate(a, acc, i);
         out[i] = acc;
     }
@@ -518,6 +550,7 @@ struct rrc_fir {
     bool translate = false;
     double ratio = 0.0;
     unsigned long long out_counter = 0;
+    int in_u8 = 0;               // inputs are u8 I/Q pairs (rrc_fir_set_input_u8iq; c32 filters only)
     Pipe pipe;
 };
 
@@ -686,6 +719,8 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
     a.translate = h->translate ? 1 : 0;
     a.ratio = h->ratio;
     a.out_base = h->out_counter;
+    a.in_u8 = h->in_u8;
+    if (h->in_u8 && (reinterpret_cast<uintptr_t>(in) & 1)) return fail(RRC_ERR_INVALID, "u8 I/Q input must be 2-byte aligned");
 
     if (h->use_poly) {
         a.taps = h->taps_poly;
@@ -812,6 +847,13 @@ int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes) {
     *yes = (h->cplx && h->real_taps) ? 1 : 0;
     return RRC_OK;
 }
+int rrc_fir_set_input_u8iq(rrc_fir_t* h, int on) {
+    if (!h) return fail(RRC_ERR_INVALID, "fir handle is NULL");
+    if (on && !h->cplx) return fail(RRC_ERR_INVALID, "u8 I/Q input needs a Complex FIR");
+    h->in_u8 = on ? 1 : 0;
+    return RRC_OK;
+}
+
 int rrc_fir_reset(rrc_fir_t* h) {
     if (!h) return fail(RRC_ERR_INVALID, "fir handle is NULL");
     h->out_counter = 0;
@@ -850,6 +892,7 @@ int rrc_fir_c32_demod_run_batch(rrc_fir_t* h, const void* in, size_t in_stride, 
 int rrc_fir_run_host(rrc_fir_t* h, const void* in_host, size_t n_in, void* out_host, size_t* n_out) {
     if (!h) return fail(RRC_ERR_INVALID, "fir handle is NULL");
     const size_t T = h->ntaps, D = h->deci, es = samp_elem(h);
+    const size_t ies = h->in_u8 ? 2 : es;                               // input bytes per sample
     const size_t total = n_in < T + D - 1 ? 0 : (n_in - T + 1) / D;     // src/fir.rs:496-525 to exhaustion
     if (n_out) *n_out = total;
     if (total == 0) return RRC_OK;
@@ -857,12 +900,12 @@ int rrc_fir_run_host(rrc_fir_t* h, const void* in_host, size_t n_in, void* out_h
     RRC_TRY(h->pipe.init(h->device));
     const size_t chunk_out = std::max<size_t>(1, PIPE_CHUNK_SAMPLES / D);
     const size_t max_out = std::min(chunk_out, total);
-    RRC_TRY(h->pipe.reserve(((max_out - 1) * D + T) * es, max_out * es));
+    RRC_TRY(h->pipe.reserve(((max_out - 1) * D + T) * ies, max_out * es));
     int i = 0;
     for (size_t o = 0; o < total; o += chunk_out, ++i) {
         const size_t no = std::min(chunk_out, total - o);
         const size_t need = (no - 1) * D + T;                              // halo = ntaps-1 re-copied per chunk
-        RRC_TRY(h->pipe.stage_in(i, (const char*)in_host + o * D * es, need * es));
+        RRC_TRY(h->pipe.stage_in(i, (const char*)in_host + o * D * ies, need * ies));
         RRC_TRY(run_impl(h, h->pipe.d_in[i & 1], 0, need, h->pipe.d_out[i & 1], 0, no, 1, false, 0.f, h->pipe.s_comp));
         RRC_TRY(h->pipe.drain_out(i, (char*)out_host + o * es, no * es));
     }
