@@ -63,7 +63,26 @@ def cfg_c5():
                 desc="wideband: one 2^30-sample c32 capture per GPU, 16385-tap FftFilter + decimate-by-8 fused")
 
 
-CONFIGS = {"c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4, "c5": cfg_c5}
+# SURVEY 8f rank 1 (RtlSdrDecode and u8 I/Q ingest): the same shapes fed with RTL-SDR bytes, the
+# decode fused into the kernels' first load, and the stand-alone decode block.
+def cfg_c3u8():
+    c = cfg_c3()
+    c.update(name="c3u8", in_u8=True, desc=c["desc"].replace("c32 (", "u8 I/Q (") + ", RtlSdrDecode fused into the tile load")
+    return c
+
+
+def cfg_c5u8():
+    c = cfg_c5()
+    c.update(name="c5u8", in_u8=True, desc="wideband: one 2^30-sample u8 I/Q capture per GPU, RtlSdrDecode + 16385-tap FftFilter + decimate-by-8 fused")
+    return c
+
+
+def cfg_f1():
+    return dict(name="f1", op="decode", n=1 << 29, dtype="c32",
+                desc="RtlSdrDecode u8 I/Q -> c32, 2^29 samples (1 GiB in, 4 GiB out)")
+
+
+CONFIGS = {"c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4, "c5": cfg_c5, "c3u8": cfg_c3u8, "c5u8": cfg_c5u8, "f1": cfg_f1}
 
 
 def low_pass_taps(ntaps: int, cutoff: float) -> np.ndarray:
@@ -89,10 +108,13 @@ def taps_for(cfg):
 
 def alg_bytes(cfg, n_in, n_out):
     """algorithmic bytes per step."""
+    ib = 2 if cfg.get("in_u8") else 8
     if cfg["op"] in ("fir", "fftfilt", "fftfilt_decim"):
-        return 8 * n_in + 8 * n_out
+        return ib * n_in + 8 * n_out
     if cfg["op"] == "fir_demod":
-        return 8 * n_in + 4 * n_out
+        return ib * n_in + 4 * n_out
+    if cfg["op"] == "decode":
+        return 2 * n_in + 8 * n_out
     if cfg["op"] == "resample":
         return 4 * (n_in + n_out)
     raise ValueError(cfg["op"])
@@ -167,7 +189,25 @@ def run_gpu(args):
     dev = local
     cfg = CONFIGS[args.config]()
     stream = torch.cuda.current_stream().cuda_stream
-    seed = SEED + int(cfg["name"][1]) + 1000 * rank      # every rank filters its own capture
+    seed = SEED + (int(cfg["name"][1]) if cfg["name"][1].isdigit() else 9) + 1000 * rank      # every rank filters its own capture
+    u8 = bool(cfg.get("in_u8"))
+
+    def synth_input(nsamp):
+        """Device-resident synthetic input: c32 white noise, or (u8 ingest) the same noise quantised
+        to RTL-SDR bytes by an untimed setup step."""
+        if not u8:
+            t = torch.empty(2 * nsamp, dtype=torch.float32, device=f"cuda:{dev}")
+            R.synth_f32(t, seed, 0, 2 * nsamp, dev, stream)
+            return t
+        out = torch.empty(2 * nsamp, dtype=torch.uint8, device=f"cuda:{dev}")
+        chunk = 1 << 27
+        tmp = torch.empty(min(chunk, 2 * nsamp), dtype=torch.float32, device=f"cuda:{dev}")
+        for o in range(0, 2 * nsamp, chunk):
+            m = min(chunk, 2 * nsamp - o)
+            R.synth_f32(tmp, seed, o, m, dev, stream)
+            torch.cuda.synchronize()
+            out[o:o + m] = ((tmp[:m] + 1.0) * 128.0).floor_().clamp_(0, 255).to(torch.uint8)
+        return out
 
     # ---- build the op and its device-resident input ----
     op = cfg["op"]
@@ -220,9 +260,10 @@ def run_gpu(args):
         f = R.FftFilt(taps_for(cfg), device=dev)
         n_in = (n // f.nsamples) * f.nsamples
         n_out = (n_in + cfg["deci"] - 1) // cfg["deci"]
-        din = torch.empty(2 * n, dtype=torch.float32, device=f"cuda:{dev}")
+        if u8:
+            f.set_input_u8iq(True)
+        din = synth_input(n)
         dout = torch.empty(2 * n_out, dtype=torch.float32, device=f"cuda:{dev}")
-        R.synth_f32(din, seed, 0, 2 * n, dev, stream)
 
         def step():
             assert f.decim_run(din, n_in, cfg["deci"], 0, dout, stream) == n_out
@@ -246,15 +287,26 @@ def run_gpu(args):
         f = R.Fir(taps_for(cfg), deci=cfg["deci"], device=dev)
         out_n = f.out_count(n)
         need = (out_n - 1) * cfg["deci"] + cfg["ntaps"]
-        din = torch.empty(2 * n * nchan, dtype=torch.float32, device=f"cuda:{dev}")
+        if u8:
+            f.set_input_u8iq(True)
+        din = synth_input(n * nchan)
         dout = torch.empty((out_n - 1) * nchan, dtype=torch.float32, device=f"cuda:{dev}")
-        R.synth_f32(din, seed, 0, 2 * n * nchan, dev, stream)
 
         def step():
             f.demod_run_batch(din, n, need, 1.0, dout, out_n - 1, out_n, nchan, stream)
         launches_per_step = 1
         n_in, n_out = n * nchan, (out_n - 1) * nchan
         units = n_in
+    elif op == "decode":
+        n = n_in = n_out = cfg["n"]
+        u8 = True
+        din = synth_input(n)
+        dout = torch.empty(2 * n, dtype=torch.float32, device=f"cuda:{dev}")
+
+        def step():
+            R.rtlsdr_decode(din, 2 * n, dout, dev, stream)
+        launches_per_step = 1
+        units = n
     elif op == "resample":
         n = cfg["n"]
         f = R.Resampler(4, cfg["interp"], cfg["deci"], device=dev)
@@ -310,21 +362,23 @@ def run_gpu(args):
 
     # ---- end to end: host buffers through *_run_host ----
     e2e = None
-    if not args.no_e2e and op in ("fftfilt", "fir") and scaling == "weak":
-        hin = R.PinnedBuffer(np.complex64, cfg["n"])
+    if not args.no_e2e and op in ("fftfilt", "fir", "fftfilt_decim") and scaling == "weak":
+        ib = 2 if u8 else 8
+        hin = R.PinnedBuffer(np.uint8 if u8 else np.complex64, cfg["n"] * (2 if u8 else 1))
         hout = R.PinnedBuffer(np.complex64, n_out)
-        R.lib().rrc_memcpy_d2h(dev, hin.ptr, din.data_ptr(), cfg["n"] * 8, stream)
+        R.lib().rrc_memcpy_d2h(dev, hin.ptr, din.data_ptr(), cfg["n"] * ib, stream)
         torch.cuda.synchronize()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        run_host = (lambda: f.decim_run_host(hin, cfg["deci"], hout)) if op == "fftfilt_decim" else (lambda: f.run_host(hin, hout))
         for _ in range(2):
-            f.reset() if op == "fftfilt" else None
-            f.run_host(hin, hout)
+            f.reset() if op != "fir" else None
+            run_host()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            if op == "fftfilt":
+            if op != "fir":
                 f.reset()
-            got = f.run_host(hin, hout)
+            got = run_host()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{dev}")
@@ -333,7 +387,7 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
         e2e = {"value": units * world / (dt / e2e_steps) / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": int(8 * (n_in if op == "fftfilt" else cfg["n"])), "d2h_bytes_per_step": int(8 * len(got)),
+               "h2d_bytes_per_step": int(ib * (n_in if op != "fir" else cfg["n"])), "d2h_bytes_per_step": int(8 * len(got)),
                "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3, "timer": "host wall clock around rrc_*_run_host (returns after D2H completes)"}
         hin.free(); hout.free()
 
@@ -357,14 +411,15 @@ def run_gpu(args):
         traffic = json.loads(traffic_path.read_text()).get(cfg["name"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
-                "kernel": {"fftfilt": "fftfilt_kernel", "fir": "fir_poly_kernel", "fir_demod": "fir_poly_kernel<DEMOD>", "resample": "resample_kernel",
-                           "fftfilt_decim": "fftfilt_kernel<DECIM> x2 tap partitions"}[op],
+                "kernel": {"fftfilt": "fftfilt_kernel", "fir": "fir_poly_kernel<float2,float,1,false,16>", "fir_demod": "fir_rt_kernel<10,DEMOD,8,2>",
+                           "resample": "resample_kernel", "decode": "rtlsdr_decode_kernel",
+                           "fftfilt_decim": "fftfilt_fold_kernel<4> (65536-point, 4-CTA cluster) + history update"}[op],
                 "duration_ms": ms_per_step,
                 "note": "duration = CUDA-event time of the whole step on the launching stream / steps; the step is this one kernel"
                         + (" plus a <3 us history-update kernel" if op == "fftfilt" else "")}
 
     cpu = None
-    if world == 1 and not args.no_cpu and op != "fftfilt_decim":
+    if world == 1 and not args.no_cpu:
         cpu = cpu_baseline(cfg, threads=1, budget_s=args.cpu_budget)
 
     line = {
@@ -392,7 +447,7 @@ def cpu_baseline(cfg, threads: int, budget_s: float):
 
     from oracle import oracle as O
     op = cfg["op"]
-    taps = taps_for(cfg) if op != "resample" else None
+    taps = taps_for(cfg) if op not in ("resample", "decode") else None
     if op == "fftfilt":
         per = 1 << 21
         x = O.synth_c32(SEED + 2, 0, per)
@@ -406,9 +461,26 @@ def cpu_baseline(cfg, threads: int, budget_s: float):
         sample = f"{threads} x 2^19 c32 samples per repetition"
     elif op == "fir_demod":
         per = 240_000
-        x = O.synth_c32(SEED + 3, 0, per)
-        fn = lambda i: len(O.quad_demod(O.fir(x, taps, cfg["deci"], fast=True), fast=True))
-        sample = f"{threads} channels x 240000 c32 samples per repetition"
+        if cfg.get("in_u8"):
+            raw = O.synth_u8(SEED + 3, 0, 2 * per)
+            fn = lambda i: len(O.quad_demod(O.fir(O.rtlsdr_decode(raw), taps, cfg["deci"], fast=True), fast=True))
+            sample = f"{threads} channels x 240000 u8 I/Q samples per repetition (RtlSdrDecode -> FirFilter -> QuadratureDemod)"
+        else:
+            x = O.synth_c32(SEED + 3, 0, per)
+            fn = lambda i: len(O.quad_demod(O.fir(x, taps, cfg["deci"], fast=True), fast=True))
+            sample = f"{threads} channels x 240000 c32 samples per repetition"
+    elif op == "fftfilt_decim":
+        per = 1 << 21
+        x = O.synth_u8(SEED + 5, 0, 2 * per) if cfg.get("in_u8") else O.synth_c32(SEED + 5, 0, per)
+        objs = [O.FftFilt(taps, fast=True) for _ in range(threads)]
+        dec = (lambda v: O.rtlsdr_decode(v)) if cfg.get("in_u8") else (lambda v: v)
+        fn = lambda i: len(O.resample(objs[i].run(dec(x)), 1, cfg["deci"]))
+        sample = f"{threads} x 2^21 samples per repetition, FftFilter overlap-add with F=65536 like the reference, then RationalResampler(1,8)"
+    elif op == "decode":
+        per = 1 << 24
+        raw = O.synth_u8(SEED + 6, 0, 2 * per)
+        fn = lambda i: len(O.rtlsdr_decode(raw))
+        sample = f"{threads} x 2^24 samples per repetition"
     else:
         per = 1 << 24
         x = O.synth_f32(SEED + 4, 0, per)

@@ -203,6 +203,10 @@ int rrc_rtlsdr_decode_run_host(int device, const unsigned char* in_host, size_t 
 int rrc_fir_set_input_u8iq(rrc_fir_t* h, int on);
 int rrc_fftfilt_set_input_u8iq(rrc_fftfilt_t* h, int on);
 
+/* Host-buffer form of FftFilter -> RationalResampler(1, deci) for a whole stream (config 5 end to
+ * end): floor(n_in/nsamples)*nsamples filter outputs, every deci-th kept starting with the first. */
+int rrc_fftfilt_decim_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, size_t deci, float* out_host, size_t* n_out);
+
 /* -------------------------------------------------- RationalResampler --- */
 /*
  * Replaces RationalResampler::new / work (src/rational_resampler.rs:125-206):

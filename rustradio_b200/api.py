@@ -85,6 +85,7 @@ _SIGS = {
     "rrc_fftfilt_run": [_vp, _vp, _sz, _vp, _vp],
     "rrc_fftfilt_decim_run": [_vp, _vp, _sz, _sz, _sz, _vp, _P(_sz), _vp],
     "rrc_fftfilt_run_host": [_vp, _vp, _sz, _vp, _P(_sz)],
+    "rrc_fftfilt_decim_run_host": [_vp, _vp, _sz, _sz, _vp, _P(_sz)],
     "rrc_resampler_create": [_i, _sz, _sz, _sz, _P(_vp)],
     "rrc_resampler_destroy": [_vp],
     "rrc_resampler_reset": [_vp],
@@ -401,6 +402,16 @@ class FftFilt:
         oa = out.array if isinstance(out, PinnedBuffer) else (out if out is not None else np.empty(n_out, np.complex64))
         n = _sz(0)
         _ck(lib().rrc_fftfilt_run_host(self.h, xa.ctypes.data, n_in, oa.ctypes.data, C.byref(n)))
+        return oa[: n.value]
+
+    def decim_run_host(self, x, deci: int, out=None) -> np.ndarray:
+        u8 = getattr(self, "in_u8", False)
+        xa = x.array if isinstance(x, PinnedBuffer) else np.ascontiguousarray(x, np.uint8 if u8 else np.complex64)
+        n_in = len(xa) // 2 if u8 else len(xa)
+        n_out = ((n_in // self.nsamples) * self.nsamples + deci - 1) // deci
+        oa = out.array if isinstance(out, PinnedBuffer) else (out if out is not None else np.empty(n_out, np.complex64))
+        n = _sz(0)
+        _ck(lib().rrc_fftfilt_decim_run_host(self.h, xa.ctypes.data, n_in, deci, oa.ctypes.data, C.byref(n)))
         return oa[: n.value]
 
     def filter(self, x: np.ndarray) -> np.ndarray:

@@ -458,4 +458,35 @@ int rrc_fftfilt_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, fl
     return h->pipe.finish();
 }
 
+int rrc_fftfilt_decim_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, size_t deci, float* out_host, size_t* n_out) {
+    if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
+    if (deci == 0) return fail(RRC_ERR_INVALID, "deci must be nonzero");
+    // FftFilter emits whole blocks of nsamples (src/fft_filter.rs:315-327); RationalResampler(1, deci)
+    // keeps every deci-th of them starting with the first (src/rational_resampler.rs:181-198).
+    const size_t S = ref_fft_size(h->ntaps) - h->ntaps;
+    const size_t total = (n_in / S) * S;
+    const size_t total_out = (total + deci - 1) / deci;
+    if (n_out) *n_out = total_out;
+    if (total == 0) return RRC_OK;
+    if (!in_host || !out_host) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    RRC_TRY(h->pipe.init(h->device));
+    const size_t chunk = PIPE_CHUNK_SAMPLES;
+    const size_t esz = h->in_u8 ? 2 : sizeof(float2);
+    RRC_TRY(h->pipe.reserve(std::min(chunk, total) * esz, (std::min(chunk, total) / deci + 2) * sizeof(float2)));
+    int i = 0;
+    size_t produced = 0;
+    for (size_t off = 0; off < total; off += chunk, ++i) {
+        const size_t n = std::min(chunk, total - off);
+        const size_t skip = (deci - off % deci) % deci;           // first kept output of this chunk
+        size_t cnt = 0;
+        RRC_TRY(h->pipe.stage_in(i, reinterpret_cast<const char*>(in_host) + off * esz, n * esz));
+        RRC_CUDA(cudaSetDevice(h->device));
+        RRC_TRY(rrc_fftfilt_decim_run(h, (const float*)h->pipe.d_in[i & 1], n, deci, skip, (float*)h->pipe.d_out[i & 1], &cnt, h->pipe.s_comp));
+        RRC_TRY(h->pipe.drain_out(i, out_host + 2 * produced, cnt * sizeof(float2)));
+        produced += cnt;
+    }
+    if (produced != total_out) return fail(RRC_ERR_STATE, "decim_run_host produced %zu of %zu", produced, total_out);
+    return h->pipe.finish();
+}
+
 }  // extern "C"

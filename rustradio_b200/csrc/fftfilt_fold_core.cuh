@@ -84,10 +84,16 @@ RRC_HD void phase_a(int tid, int c, long long blk, const FoldIO& io, const float
                     const float2* twc, float2* sm, Hook before_store = Hook()) {
     float2 v[32];
     const long long seg0 = seg_start<NC>(blk, io);
-    // u8 I/Q input takes the bounds-checked path (fetch() decodes), c32 the pipelined one.
-    const bool interior = seg0 >= 0 && seg0 + (long long)NC * N <= io.n_in && !io.in_u8;
+    const bool interior = seg0 >= 0 && seg0 + (long long)NC * N <= io.n_in;
     if constexpr (NC == 1) {
-        if (interior) {
+        if (interior && io.in_u8) {
+            const unsigned short* p = reinterpret_cast<const unsigned short*>(io.in) + seg0 + tid;
+            unsigned int w[32];
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) w[n1] = p[512 * n1];
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = decode_u8iq(w[n1] & 0xffu, w[n1] >> 8);
+        } else if (interior) {
             const float2* p = io.in + seg0 + tid;
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = p[512 * n1];
@@ -106,27 +112,34 @@ RRC_HD void phase_a(int tid, int c, long long blk, const FoldIO& io, const float
             const float2 a = make_float2(fmaf(-ui, O.y, fmaf(ur, O.x, E.x)), fmaf(ui, O.x, fmaf(ur, O.y, E.y)));
             v[bitrev(n1, 5)] = cmul(a, twc[n1]);
         };
-        if (interior) {
-            // Software-pipelined: the 16 loads of batch b+1 (4 values of n1 x 4 quarters) are issued
-            // before batch b is consumed, so every thread keeps 16..32 loads in flight (the loads are
-            // L2 hits for three of the four CTAs of the cluster, ~300-800 cycles each).
-            const float2* p = io.in + seg0 + tid;
+        // Software-pipelined: the 16 loads of batch b+1 (4 values of n1 x 4 quarters) are issued
+        // before batch b is consumed, so every thread keeps 16..32 loads in flight (the loads are
+        // L2 hits for three of the four CTAs of the cluster, ~300-800 cycles each).  `ld(o)` reads
+        // segment element tid + o: a c32 load, or a 16-bit load + RtlSdrDecode for u8 I/Q input.
+        auto pipelined = [&](auto ld) {
             float2 xb[2][4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) xb[0][i][j] = p[512 * i + j * N];
+                for (int j = 0; j < 4; ++j) xb[0][i][j] = ld(512 * i + j * N);
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
                 if (b < 7) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) xb[(b + 1) & 1][i][j] = p[512 * (4 * (b + 1) + i) + j * N];
+                        for (int j = 0; j < 4; ++j) xb[(b + 1) & 1][i][j] = ld(512 * (4 * (b + 1) + i) + j * N);
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) combine(4 * b + i, xb[b & 1][i]);
             }
+        };
+        if (interior && io.in_u8) {
+            const unsigned short* p = reinterpret_cast<const unsigned short*>(io.in) + seg0 + tid;
+            pipelined([&](int o) { const unsigned int w = p[o]; return decode_u8iq(w & 0xffu, w >> 8); });
+        } else if (interior) {
+            const float2* p = io.in + seg0 + tid;
+            pipelined([&](int o) { return p[o]; });
         } else {
 #pragma unroll
             for (int n1 = 0; n1 < 32; ++n1) {                   // edge blocks: bounds-checked, history / zero fill

@@ -142,6 +142,32 @@ __device__ __forceinline__ void load_taps(const float* tp, float (&h)[R]) {
 // R: outputs per thread = taps per chunk (8; 16 for the real-tap deci-1 case, which halves the
 // shared-memory loads per FMA).
 
+// u8 I/Q -> c32 while staging a tile: 16-bit loads, UB in flight per thread, then decode and store.
+// Out-of-range elements read as the byte pair (127, 127), which decodes to exactly 0.  Kept out of
+// line so that its registers do not count against the c32 kernels that share fir_load_tile.
+__device__ __noinline__ void fir_stage_u8(const unsigned short* __restrict__ in8, long long lim, float2* s_tile,
+                                          int L, int S, int NT, int t) {
+    const int S1 = S + 1;
+    int seg = t / S, rem = t - seg * S;
+    const int dseg = NT / S, drem = NT - dseg * S;
+    constexpr int UB = 8;
+    for (int e = t; e < L; e += UB * NT) {
+        unsigned int w[UB];
+        int idx[UB];
+#pragma unroll
+        for (int k = 0; k < UB; ++k) {
+            const int ee = e + k * NT;
+            idx[k] = seg * S1 + rem;
+            w[k] = (ee < L && ee < lim) ? in8[ee] : 0x7f7fu;
+            seg += dseg; rem += drem;
+            if (rem >= S) { rem -= S; ++seg; }
+        }
+#pragma unroll
+        for (int k = 0; k < UB; ++k)
+            if (e + k * NT < L) s_tile[idx[k]] = decode_iq(w[k]);
+    }
+}
+
 // Stage the input span of tile `id` into `s_tile` (padded: one pad element after every S).
 template <typename ST, int R>
 __device__ __forceinline__ void fir_load_tile(const FirArgs& a, ST* s_tile, long long id, int deci, int S,
@@ -152,18 +178,9 @@ __device__ __forceinline__ void fir_load_tile(const FirArgs& a, ST* s_tile, long
     const int L = a.nseg * S;
     const long long g0 = bx * bstride * deci;
     if constexpr (sizeof(ST) == 8) {
-        if (a.in_u8) {                                         // u8 I/Q -> c32 while staging (synchronous loads)
-            const unsigned short* __restrict__ in8 = reinterpret_cast<const unsigned short*>(a.in) + ch * a.in_stride;
-            int seg = t / S, rem = t - seg * S;
-            const int dseg = NT / S, drem = NT - dseg * S;
-            for (int e = t; e < L; e += NT) {
-                const long long g = g0 + e;
-                float2 v = make_float2(0.f, 0.f);
-                if (g < a.need) v = decode_iq(in8[g]);
-                reinterpret_cast<float2*>(s_tile)[seg * S1 + rem] = v;
-                seg += dseg; rem += drem;
-                if (rem >= S) { rem -= S; ++seg; }
-            }
+        if (a.in_u8) {
+            fir_stage_u8(reinterpret_cast<const unsigned short*>(a.in) + ch * a.in_stride + g0, a.need - g0,
+                         reinterpret_cast<float2*>(s_tile), L, S, NT, t);
             asm volatile("cp.async.commit_group;" ::: "memory");
             return;
         }

@@ -94,14 +94,11 @@ struct Pipe {
 // Samples per host-pipeline chunk (bytes = this * element size).  RRC_PIPE_CHUNK_LOG2 overrides
 // the default 2^23 (64 MiB of c32) for experiments.
 inline size_t pipe_chunk_samples() {
-    static const size_t v = [] {
-        const char* e = getenv("RRC_PIPE_CHUNK_LOG2");
-        int l = e ? atoi(e) : 23;
-        if (l < 12) l = 12;
-        if (l > 28) l = 28;
-        return (size_t)1 << l;
-    }();
-    return v;
+    const char* e = getenv("RRC_PIPE_CHUNK_LOG2");     // read per call: tests shrink it to force many chunks
+    int l = e ? atoi(e) : 23;
+    if (l < 12) l = 12;
+    if (l > 28) l = 28;
+    return (size_t)1 << l;
 }
 #define PIPE_CHUNK_SAMPLES (::rrc::pipe_chunk_samples())
 

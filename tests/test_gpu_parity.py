@@ -206,6 +206,21 @@ def test_fftfilt_fused_decimation(R):
         assert O.rel_rms(dout.download(np.complex64, n), want) <= REL_RMS_BAR
 
 
+def test_fftfilt_decim_run_host_chunked(R, monkeypatch):
+    """Host pipeline of FftFilter -> RationalResampler(1, deci): chunk boundaries carry the filter
+    history and the resampler phase (chunk forced small so several chunks run)."""
+    monkeypatch.setenv("RRC_PIPE_CHUNK_LOG2", "12")
+    for ntaps, deci, n in ((301, 8, 70_000), (4097, 8, 150_000), (193, 3, 50_001)):
+        taps = (O.low_pass_n(1.0, 0.05, ntaps) * (1 - 0.5j)).astype(np.complex64)
+        x = O.synth_c32(31, 0, n)
+        f = R.FftFilt(taps)
+        y = f.decim_run_host(x, deci)
+        nfull = (n // f.nsamples) * f.nsamples
+        want = O.conv_full_f64_fft(x, taps, n)[:nfull:deci]
+        assert len(y) == len(want)
+        assert O.rel_rms(y, want) <= REL_RMS_BAR
+
+
 def test_fftfilt_long_taps_partitioned_streaming_and_decimation(R):
     """BASELINE config 5 shape at test size: 16385 taps (two tap partitions), streamed in pieces, decimate by 8."""
     taps = O.low_pass_n(1.0, 0.02, 16385).astype(np.complex64)

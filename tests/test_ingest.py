@@ -158,6 +158,12 @@ def test_fftfilt_fused_u8_input(R, ntaps, n):
     truth = O.conv_full_f64_fft(x, taps, n)[3::8]
     assert cnt == len(truth)
     assert O.rel_rms(dd.download(np.complex64, cnt), truth) <= 1e-5
+    f4 = R.FftFilt(taps)
+    f4.set_input_u8iq(True)
+    yd = f4.decim_run_host(raw, 8)
+    nfull = (n // f4.nsamples) * f4.nsamples
+    assert len(yd) == (nfull + 7) // 8
+    assert O.rel_rms(yd, O.conv_full_f64_fft(x, taps, n)[:nfull:8]) <= 1e-5
     f3 = R.FftFilt(taps)
     f3.set_input_u8iq(True)
     yh = f3.run_host(raw)
