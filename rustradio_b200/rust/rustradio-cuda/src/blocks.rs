@@ -252,3 +252,43 @@ impl Block for CudaQuadratureDemod {
         }
     }
 }
+
+/// GPU `RtlSdrDecode`: `new(src)` like the macro-generated src/rtlsdr_decode.rs:9-16.
+pub struct CudaRtlSdrDecode {
+    dev: i32,
+    sin: Scratch,
+    sout: Scratch,
+    src: ReadStream<u8>,
+    dst: WriteStream<Complex>,
+}
+unsafe impl Send for CudaRtlSdrDecode {}
+impl CudaRtlSdrDecode {
+    pub fn new(src: ReadStream<u8>) -> (Self, ReadStream<Complex>) {
+        let (dst, dr) = rustradio::stream::new_stream();
+        (Self { dev: 0, sin: Scratch::new(0), sout: Scratch::new(0), src, dst }, dr)
+    }
+}
+impl BlockName for CudaRtlSdrDecode { fn block_name(&self) -> &str { "CudaRtlSdrDecode" } }
+impl BlockEOF for CudaRtlSdrDecode { fn eof(&mut self) -> bool { self.src.eof() } }
+impl Block for CudaRtlSdrDecode {
+    fn work(&mut self) -> Result<BlockRet<'_>> {
+        loop {
+            let (inp, _) = self.src.read_buf()?;                  // tags dropped (:21)
+            let isamples = inp.len() & !1;                        // :23
+            if isamples == 0 { return Ok(BlockRet::WaitForStream(&self.src, 2)); }
+            let mut out = self.dst.write_buf()?;
+            if out.is_empty() { return Ok(BlockRet::WaitForStream(&self.dst, 1)); }
+            let isamples = isamples.min(out.len() * 2);           // :32
+            let osamples = isamples / 2;
+            let (din, dout) = (self.sin.reserve(isamples)?, self.sout.reserve(osamples * 8)?);
+            unsafe {
+                check(ffi::rrc_memcpy_h2d(self.dev, din, inp.slice().as_ptr().cast(), isamples, ptr::null_mut()))?;
+                check(ffi::rrc_rtlsdr_decode_run(self.dev, din.cast(), isamples, dout.cast(), ptr::null_mut()))?;
+                check(ffi::rrc_memcpy_d2h(self.dev, out.slice().as_mut_ptr().cast(), dout, osamples * 8, ptr::null_mut()))?;
+                check(ffi::rrc_stream_sync(self.dev, ptr::null_mut()))?;
+            }
+            inp.consume(isamples);
+            out.produce(osamples, &[]);
+        }
+    }
+}
