@@ -50,6 +50,14 @@ unsafe extern "C" {
                              consumed: *mut usize, produced: *mut usize, wait_on_output: *mut c_int, stream: *mut c_void) -> c_int;
 
     pub fn rrc_quad_demod_run(device: c_int, in_dev_c32: *const c_float, n_in: usize, gain: c_float, out_dev: *mut c_float, stream: *mut c_void) -> c_int;
+
+    // RtlSdrDecode::work                        src/rtlsdr_decode.rs:18-48
+    pub fn rrc_rtlsdr_decode_plan(in_len_bytes: usize, out_free: usize, consume_bytes: *mut usize, produce: *mut usize,
+                                  wait_need: *mut usize, wait_on_output: *mut c_int) -> c_int;
+    pub fn rrc_rtlsdr_decode_run(device: c_int, in_dev: *const u8, n_bytes: usize, out_dev_c32: *mut c_float, stream: *mut c_void) -> c_int;
+    // RtlSdrDecode fused into the first load of the filters (u8 I/Q input mode)
+    pub fn rrc_fir_set_input_u8iq(h: *mut rrc_fir_t, on: c_int) -> c_int;
+    pub fn rrc_fftfilt_set_input_u8iq(h: *mut rrc_fftfilt_t, on: c_int) -> c_int;
 }
 
 /// Turn a status code into rustradio's `Error::DeviceError`-style error (src/lib.rs:288-294).
@@ -60,11 +68,4 @@ pub fn check(code: c_int) -> rustradio::Result<()> {
     // SAFETY: rrc_last_error returns a NUL-terminated thread-local buffer.
     let msg = unsafe { std::ffi::CStr::from_ptr(rrc_last_error()) }.to_string_lossy().into_owned();
     Err(rustradio::Error::msg(format!("rustradio-cuda error {code}: {msg}")))
-    // RtlSdrDecode::work                        src/rtlsdr_decode.rs:18-48
-    pub fn rrc_rtlsdr_decode_plan(in_len_bytes: usize, out_free: usize, consume_bytes: *mut usize, produce: *mut usize,
-                                  wait_need: *mut usize, wait_on_output: *mut c_int) -> c_int;
-    pub fn rrc_rtlsdr_decode_run(device: c_int, in_dev: *const u8, n_bytes: usize, out_dev_c32: *mut c_float, stream: *mut c_void) -> c_int;
-    // RtlSdrDecode fused into the first load of the filters (u8 I/Q input mode)
-    pub fn rrc_fir_set_input_u8iq(h: *mut rrc_fir_t, on: c_int) -> c_int;
-    pub fn rrc_fftfilt_set_input_u8iq(h: *mut rrc_fftfilt_t, on: c_int) -> c_int;
 }
