@@ -82,7 +82,12 @@ def cfg_f1():
                 desc="RtlSdrDecode u8 I/Q -> c32, 2^29 samples (1 GiB in, 4 GiB out)")
 
 
-CONFIGS = {"c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4, "c5": cfg_c5, "c3u8": cfg_c3u8, "c5u8": cfg_c5u8, "f1": cfg_f1}
+def cfg_f2():
+    return dict(name="f2", op="fft", size=1024, n=1 << 28, dtype="c32",
+                desc="FftStream forward FFT, 1024-point frames, 2^28 c32 samples")
+
+
+CONFIGS = {"f2": cfg_f2, "c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4, "c5": cfg_c5, "c3u8": cfg_c3u8, "c5u8": cfg_c5u8, "f1": cfg_f1}
 
 
 def low_pass_taps(ntaps: int, cutoff: float) -> np.ndarray:
@@ -115,6 +120,8 @@ def alg_bytes(cfg, n_in, n_out):
         return ib * n_in + 4 * n_out
     if cfg["op"] == "decode":
         return 2 * n_in + 8 * n_out
+    if cfg["op"] == "fft":
+        return 8 * n_in + 8 * n_out
     if cfg["op"] == "resample":
         return 4 * (n_in + n_out)
     raise ValueError(cfg["op"])
@@ -307,6 +314,16 @@ def run_gpu(args):
             R.rtlsdr_decode(din, 2 * n, dout, dev, stream)
         launches_per_step = 1
         units = n
+    elif op == "fft":
+        n = n_in = n_out = cfg["n"]
+        f = R.Fft(cfg["size"], device=dev)
+        din = synth_input(n)
+        dout = torch.empty(2 * n, dtype=torch.float32, device=f"cuda:{dev}")
+
+        def step():
+            f.run(din, n // cfg["size"], dout, stream)
+        launches_per_step = 1
+        units = n
     elif op == "resample":
         n = cfg["n"]
         f = R.Resampler(4, cfg["interp"], cfg["deci"], device=dev)
@@ -362,7 +379,7 @@ def run_gpu(args):
 
     # ---- end to end: host buffers through *_run_host ----
     e2e = None
-    if not args.no_e2e and op in ("fftfilt", "fir", "fftfilt_decim") and scaling == "weak":
+    if not args.no_e2e and op in ("fftfilt", "fir", "fftfilt_decim", "fft") and scaling == "weak":
         ib = 2 if u8 else 8
         hin = R.PinnedBuffer(np.uint8 if u8 else np.complex64, cfg["n"] * (2 if u8 else 1))
         hout = R.PinnedBuffer(np.complex64, n_out)
@@ -371,12 +388,12 @@ def run_gpu(args):
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         run_host = (lambda: f.decim_run_host(hin, cfg["deci"], hout)) if op == "fftfilt_decim" else (lambda: f.run_host(hin, hout))
         for _ in range(2):
-            f.reset() if op != "fir" else None
+            f.reset() if op in ("fftfilt", "fftfilt_decim") else None
             run_host()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            if op != "fir":
+            if op in ("fftfilt", "fftfilt_decim"):
                 f.reset()
             got = run_host()
         torch.cuda.synchronize()
@@ -387,7 +404,7 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
         e2e = {"value": units * world / (dt / e2e_steps) / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": int(ib * (n_in if op != "fir" else cfg["n"])), "d2h_bytes_per_step": int(8 * len(got)),
+               "h2d_bytes_per_step": int(ib * (n_in if op not in ("fir",) else cfg["n"])), "d2h_bytes_per_step": int(8 * len(got)),
                "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3, "timer": "host wall clock around rrc_*_run_host (returns after D2H completes)"}
         hin.free(); hout.free()
 
@@ -412,7 +429,7 @@ def run_gpu(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
                 "kernel": {"fftfilt": "fftfilt_kernel", "fir": "fir_poly_kernel<float2,float,1,false,16>", "fir_demod": "fir_rt_kernel<10,DEMOD,8,2>",
-                           "resample": "resample_kernel", "decode": "rtlsdr_decode_kernel",
+                           "resample": "resample_kernel", "decode": "rtlsdr_decode_kernel", "fft": "fftstream_kernel<10>",
                            "fftfilt_decim": "fftfilt_fold_kernel<4> (65536-point, 4-CTA cluster) + history update"}[op],
                 "duration_ms": ms_per_step,
                 "note": "duration = CUDA-event time of the whole step on the launching stream / steps; the step is this one kernel"
@@ -447,7 +464,7 @@ def cpu_baseline(cfg, threads: int, budget_s: float):
 
     from oracle import oracle as O
     op = cfg["op"]
-    taps = taps_for(cfg) if op not in ("resample", "decode") else None
+    taps = taps_for(cfg) if op not in ("resample", "decode", "fft") else None
     if op == "fftfilt":
         per = 1 << 21
         x = O.synth_c32(SEED + 2, 0, per)
@@ -476,6 +493,17 @@ def cpu_baseline(cfg, threads: int, budget_s: float):
         dec = (lambda v: O.rtlsdr_decode(v)) if cfg.get("in_u8") else (lambda v: v)
         fn = lambda i: len(O.resample(objs[i].run(dec(x)), 1, cfg["deci"]))
         sample = f"{threads} x 2^21 samples per repetition, FftFilter overlap-add with F=65536 like the reference, then RationalResampler(1,8)"
+    elif op == "fft":
+        per = 1 << 20
+        x = O.synth_c32(SEED + 7, 0, per)
+        sz = cfg["size"]
+
+        def fn(i):
+            y = x.copy()
+            for o in range(0, per, sz):
+                O.lib(True).orc_fft_c32(y[o:o + sz].ctypes.data, sz, 0)
+            return len(y)
+        sample = f"{threads} x 2^20 c32 samples per repetition ({sz}-point frames, the oracle's radix-4 FFT)"
     elif op == "decode":
         per = 1 << 24
         raw = O.synth_u8(SEED + 6, 0, 2 * per)

@@ -207,6 +207,24 @@ int rrc_fftfilt_set_input_u8iq(rrc_fftfilt_t* h, int on);
  * end): floor(n_in/nsamples)*nsamples filter outputs, every deci-th kept starting with the first. */
 int rrc_fftfilt_decim_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, size_t deci, float* out_host, size_t* n_out);
 
+/* ------------------------------------------------- FftStream / Fft --- */
+/*
+ * SURVEY 8f rank 2.  Replaces the compute of FftStream::work (src/fft_stream.rs:71-117: every
+ * `size` samples become their unnormalised forward DFT, rustfft process()) and Fft::process_one
+ * (src/fft.rs:31-35).  Device sizes: powers of two up to 16384 (others: RRC_ERR_UNSUPPORTED;
+ * size 0: RRC_ERR_INVALID like the reference's assert / Err, :42 / src/fft.rs:25-27).
+ */
+typedef struct rrc_fft rrc_fft_t;
+int rrc_fft_c32_create(int device, size_t size, rrc_fft_t** out);
+int rrc_fft_destroy(rrc_fft_t* h);
+int rrc_fft_size(const rrc_fft_t* h, size_t* size);
+/* nframes consecutive frames of `size` c32 samples; in place allowed. */
+int rrc_fft_run(rrc_fft_t* h, const float* in_dev_c32, size_t nframes, float* out_dev_c32, void* stream);
+/* Integer part of FftStream::work (:73-84): *len samples (a multiple of size) are transformed
+ * now, or len = 0 and WaitForStream(src|dst, size). */
+int rrc_fftstream_plan(size_t size, size_t in_len, size_t out_free, size_t* len, size_t* wait_need, int* wait_on_output);
+int rrc_fft_run_host(rrc_fft_t* h, const float* in_host, size_t n_in, float* out_host, size_t* n_out);
+
 /* -------------------------------------------------- RationalResampler --- */
 /*
  * Replaces RationalResampler::new / work (src/rational_resampler.rs:125-206):
@@ -311,6 +329,10 @@ int rrb_rational_resampler_new(rrb_rstream_t* src, size_t interp, size_t deci,
                                size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
 int rrb_quadrature_demod_new(rrb_rstream_t* src, float gain,
                              size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+/* FftStream::new(src, size) -> (Self, ReadStream<Complex>)  (src/fft_stream.rs:38-60); frame tags
+ * "FftStream::size" / "FftStream::frame" as :95-106. */
+int rrb_fft_stream_new(rrb_rstream_t* src, size_t size,
+                       size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
 /* RtlSdrDecode::new(src: ReadStream<u8>) -> (Self, ReadStream<Complex>)  (src/rtlsdr_decode.rs:9-16) */
 int rrb_rtlsdr_decode_new(rrb_rstream_t* src,
                           size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);

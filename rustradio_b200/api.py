@@ -95,6 +95,12 @@ _SIGS = {
     "rrc_quad_demod_run": [_i, _vp, _sz, _f, _vp, _vp],
     "rrc_quad_demod_run_batch": [_i, _vp, _sz, _sz, _f, _vp, _sz, _sz, _vp],
     "rrc_quad_demod_run_host": [_i, _vp, _sz, _f, _vp],
+    "rrc_fft_c32_create": [_i, _sz, _P(_vp)],
+    "rrc_fft_destroy": [_vp],
+    "rrc_fft_size": [_vp, _P(_sz)],
+    "rrc_fft_run": [_vp, _vp, _sz, _vp, _vp],
+    "rrc_fftstream_plan": [_sz, _sz, _sz, _P(_sz), _P(_sz), _P(_i)],
+    "rrc_fft_run_host": [_vp, _vp, _sz, _vp, _P(_sz)],
     "rrc_rtlsdr_decode_plan": [_sz, _sz, _P(_sz), _P(_sz), _P(_sz), _P(_i)],
     "rrc_rtlsdr_decode_run": [_i, _vp, _sz, _vp, _vp],
     "rrc_rtlsdr_decode_run_host": [_i, _vp, _sz, _vp, _P(_sz)],
@@ -475,6 +481,51 @@ class Resampler:
     def __del__(self):
         try:
             lib().rrc_resampler_destroy(self.h)
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------ FFT frames ---
+def fftstream_plan(size: int, in_len: int, out_free: int):
+    """(len, wait_need, wait_on_output) — src/fft_stream.rs:73-84."""
+    ln, need, w = _sz(0), _sz(0), _i(0)
+    _ck(lib().rrc_fftstream_plan(size, in_len, out_free, C.byref(ln), C.byref(need), C.byref(w)))
+    return ln.value, need.value, w.value
+
+
+class Fft:
+    """Forward FFT of consecutive frames (FftStream / Fft compute)."""
+
+    def __init__(self, size: int, device: int = 0):
+        self.size, self.device = size, device
+        h = C.c_void_p()
+        _ck(lib().rrc_fft_c32_create(device, size, C.byref(h)))
+        self.h = h.value
+
+    def run(self, d_in, nframes: int, d_out, stream: int = 0):
+        _ck(lib().rrc_fft_run(self.h, _ptr(d_in), nframes, _ptr(d_out), stream))
+
+    def run_host(self, x, out=None) -> np.ndarray:
+        xa = x.array if isinstance(x, PinnedBuffer) else np.ascontiguousarray(x, np.complex64)
+        n_out = (len(xa) // self.size) * self.size
+        oa = out.array if isinstance(out, PinnedBuffer) else (out if out is not None else np.empty(n_out, np.complex64))
+        n = _sz(0)
+        _ck(lib().rrc_fft_run_host(self.h, xa.ctypes.data, len(xa), oa.ctypes.data, C.byref(n)))
+        return oa[: n.value]
+
+    def transform(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.complex64)
+        nf = len(x) // self.size
+        if nf == 0:
+            return np.empty(0, np.complex64)
+        din = DeviceBuffer.from_numpy(x[: nf * self.size], self.device)
+        dout = DeviceBuffer(nf * self.size * 8, self.device)
+        self.run(din, nf, dout)
+        return dout.download(np.complex64, nf * self.size)
+
+    def __del__(self):
+        try:
+            lib().rrc_fft_destroy(self.h)
         except Exception:
             pass
 

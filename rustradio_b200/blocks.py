@@ -51,6 +51,7 @@ _SIGS = {
     "rrb_rational_resampler_new": [_vp, _sz, _sz, _sz, _i, _i, _P(_vp), _P(_vp)],
     "rrb_quadrature_demod_new": [_vp, C.c_float, _sz, _i, _i, _P(_vp), _P(_vp)],
     "rrb_rtlsdr_decode_new": [_vp, _sz, _i, _i, _P(_vp), _P(_vp)],
+    "rrb_fft_stream_new": [_vp, _sz, _sz, _i, _i, _P(_vp), _P(_vp)],
     "rrb_block_work": [_vp, _P(_i), _P(_sz), _P(_sz)],
     "rrb_block_eof": [_vp, _P(_i)],
     "rrb_block_drop": [_vp],
@@ -259,6 +260,11 @@ def RationalResampler(src: ReadStream, interp: int, deci: int, size_bytes=DEFAUL
 
 def QuadratureDemod(src: ReadStream, gain: float, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     return _mk(_L().rrb_quadrature_demod_new, np.float32, src._take(), gain, size_bytes, residency, device)
+
+
+def FftStream(src: ReadStream, size: int, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
+    """FftStream::new(src, size) (src/fft_stream.rs:38-60)."""
+    return _mk(_L().rrb_fft_stream_new, np.complex64, src._take(), size, size_bytes, residency, device)
 
 
 def RtlSdrDecode(src: ReadStream, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):

@@ -550,6 +550,55 @@ int QuadratureDemod::work(BlockRet* ret) {    // src/quadrature_demod.rs:46-113
     }
 }
 
+static Tag mk_tag_bool(size_t pos, const char* key, bool v);
+static Tag mk_tag_u64(size_t pos, const char* key, uint64_t v);
+
+// ------------------------------------------------------------------ FftStream -----
+int FftStream::create(std::unique_ptr<ReadStream> src, size_t size, const StreamOpts& o, std::unique_ptr<FftStream>* out) {
+    if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    if (src->buffer().elem() != 8) return fail(RRC_ERR_INVALID, "FftStream: stream must carry Complex<f32>");
+    if (size == 0) return fail(RRC_ERR_INVALID, "FFT size must be nonzero (src/fft_stream.rs:42)");
+    std::unique_ptr<FftStream> b(new FftStream());
+    b->device_ = o.device; b->size_ = size;
+    b->src_ = std::move(src);
+    RRC_TRY(make_output(8, o, &b->dst_, &b->out_r_));
+    char* w; size_t cap;
+    b->dst_->buffer().write_window(&w, &cap);
+    if (size > cap) return fail(RRC_ERR_INVALID, "FFT size (%zu) must be no bigger than stream size (%zu) (src/fft_stream.rs:46-50)", size, cap);
+    RRC_TRY(rrc_fft_c32_create(o.device, size, &b->h_));
+    *out = std::move(b);
+    return RRC_OK;
+}
+FftStream::~FftStream() { rrc_fft_destroy(h_); }
+
+int FftStream::work(BlockRet* ret) {          // src/fft_stream.rs:71-117 (one batch per call, then Again)
+    const char* in; size_t in_len;
+    src_->buffer().read_window(&in, &in_len, nullptr);        // input tags are not forwarded (:73)
+    if (in_len < size_) { *ret = BlockRet::wait(src_.get(), size_); return RRC_OK; }
+    char* outp; size_t cap;
+    dst_->buffer().write_window(&outp, &cap);
+    if (cap < size_) { *ret = BlockRet::wait(dst_.get(), size_); return RRC_OK; }
+    size_t len = std::min(in_len, cap);
+    len -= len % size_;
+    const char* din; char* dout;
+    RRC_TRY(stage_input(src_->buffer(), in, len * 8, sin_, device_, &din));
+    RRC_TRY(stage_output(dst_->buffer(), outp, len * 8, sout_, device_, &dout));
+    RRC_TRY(rrc_fft_run(h_, (const float*)din, len / size_, (float*)dout, graph_stream(device_)));
+    RRC_TRY(finish_output(dst_->buffer(), outp, len * 8, sout_, device_));
+    if (src_->buffer().residency() == Residency::Host) RRC_CUDA(cudaStreamSynchronize((cudaStream_t)graph_stream(device_)));
+    std::vector<Tag> tags;
+    tags.reserve(len / size_ * 3);
+    for (size_t pos = 0; pos < len; pos += size_) {           // :95-106
+        tags.push_back(mk_tag_u64(pos, "FftStream::size", (uint64_t)size_));
+        tags.push_back(mk_tag_bool(pos, "FftStream::frame", true));
+        tags.push_back(mk_tag_bool(pos + size_ - 1, "FftStream::frame", false));
+    }
+    src_->buffer().consume(len);
+    dst_->buffer().produce(len, tags);
+    *ret = BlockRet::again();
+    return RRC_OK;
+}
+
 // --------------------------------------------------------------- RtlSdrDecode -----
 int RtlSdrDecode::create(std::unique_ptr<ReadStream> src, const StreamOpts& o, std::unique_ptr<RtlSdrDecode>* out) {
     if (!src) return fail(RRC_ERR_INVALID, "src is NULL");

@@ -294,6 +294,24 @@ private:
     Scratch sin_, sout_;
 };
 
+// FftStream (src/fft_stream.rs:27-117): forward FFT of every `size` samples, frame tags.
+class FftStream : public Block {
+public:
+    static int create(std::unique_ptr<ReadStream> src, size_t size, const StreamOpts& o, std::unique_ptr<FftStream>* out);
+    ~FftStream() override;
+    int work(BlockRet* ret) override;
+    const char* block_name() const override { return "FftStream"; }
+    bool eof() override { return src_->eof(); }
+private:
+    FftStream() = default;
+    std::unique_ptr<ReadStream> src_;
+    std::unique_ptr<WriteStream> dst_;
+    rrc_fft_t* h_ = nullptr;
+    size_t size_ = 0;
+    int device_ = 0;
+    Scratch sin_, sout_;
+};
+
 // RtlSdrDecode (src/rtlsdr_decode.rs:9-48): ReadStream<u8> -> WriteStream<Complex>.
 class RtlSdrDecode : public Block {
 public:

@@ -199,6 +199,12 @@ int rrb_quadrature_demod_new(rrb_rstream_t* src, float gain, size_t bytes, int r
     return finish(std::move(b), blk, out);
 }
 
+int rrb_fft_stream_new(rrb_rstream_t* src, size_t size, size_t bytes, int res, int device, rrb_block_t** blk, rrb_rstream_t** out) {
+    if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
+    std::unique_ptr<rr::FftStream> b;
+    RRC_TRY(rr::FftStream::create(take(src), size, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out);
+}
 int rrb_rtlsdr_decode_new(rrb_rstream_t* src, size_t bytes, int res, int device, rrb_block_t** blk, rrb_rstream_t** out) {
     if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
     std::unique_ptr<rr::RtlSdrDecode> b;
