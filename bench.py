@@ -83,8 +83,9 @@ def cfg_f1():
 
 
 def cfg_f2():
-    return dict(name="f2", op="fft", size=1024, n=1 << 28, dtype="c32",
-                desc="FftStream forward FFT, 1024-point frames, 2^28 c32 samples")
+    size = int(os.environ.get("RRC_BENCH_FFT_SIZE", "1024"))     # 1024 = the spectrum-display size of the examples
+    return dict(name="f2", op="fft", size=size, n=1 << 28, dtype="c32",
+                desc=f"FftStream forward FFT, {size}-point frames, 2^28 c32 samples")
 
 
 CONFIGS = {"f2": cfg_f2, "c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4, "c5": cfg_c5, "c3u8": cfg_c3u8, "c5u8": cfg_c5u8, "f1": cfg_f1}
