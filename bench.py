@@ -82,13 +82,18 @@ def cfg_f1():
                 desc="RtlSdrDecode u8 I/Q -> c32, 2^29 samples (1 GiB in, 4 GiB out)")
 
 
+def cfg_a12():
+    return dict(name="a12", op="fftfilt_real", ntaps=4097, n=1 << 29, cutoff=0.05, dtype="f32",
+                desc="FftFilterFloat 4097 real taps, 2^29 f32 samples (real-stream kernel mode: two real blocks per transform)")
+
+
 def cfg_f2():
     size = int(os.environ.get("RRC_BENCH_FFT_SIZE", "1024"))     # 1024 = the spectrum-display size of the examples
     return dict(name="f2", op="fft", size=size, n=1 << 28, dtype="c32",
                 desc=f"FftStream forward FFT, {size}-point frames, 2^28 c32 samples")
 
 
-CONFIGS = {"f2": cfg_f2, "c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4, "c5": cfg_c5, "c3u8": cfg_c3u8, "c5u8": cfg_c5u8, "f1": cfg_f1}
+CONFIGS = {"a12": cfg_a12, "f2": cfg_f2, "c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4, "c5": cfg_c5, "c3u8": cfg_c3u8, "c5u8": cfg_c5u8, "f1": cfg_f1}
 
 
 def low_pass_taps(ntaps: int, cutoff: float) -> np.ndarray:
@@ -123,6 +128,8 @@ def alg_bytes(cfg, n_in, n_out):
         return 2 * n_in + 8 * n_out
     if cfg["op"] == "fft":
         return 8 * n_in + 8 * n_out
+    if cfg["op"] == "fftfilt_real":
+        return 4 * n_in + 4 * n_out
     if cfg["op"] == "resample":
         return 4 * (n_in + n_out)
     raise ValueError(cfg["op"])
@@ -263,6 +270,18 @@ def run_gpu(args):
             f.run(din, n_in, dout, stream)
         launches_per_step = 2
         units = n_in
+    elif op == "fftfilt_real":
+        n = cfg["n"]
+        f = R.FftFilt(taps_for(cfg).real.astype(np.float32), device=dev, real=True)
+        n_in = n_out = (n // f.nsamples) * f.nsamples
+        din = torch.empty(n, dtype=torch.float32, device=f"cuda:{dev}")
+        dout = torch.empty(n_out, dtype=torch.float32, device=f"cuda:{dev}")
+        R.synth_f32(din, seed, 0, n, dev, stream)
+
+        def step():
+            f.run(din, n_in, dout, stream)
+        launches_per_step = 2
+        units = n_in
     elif op == "fftfilt_decim":
         n = cfg["n"]
         f = R.FftFilt(taps_for(cfg), device=dev)
@@ -380,21 +399,23 @@ def run_gpu(args):
 
     # ---- end to end: host buffers through *_run_host ----
     e2e = None
-    if not args.no_e2e and op in ("fftfilt", "fir", "fftfilt_decim", "fft") and scaling == "weak":
-        ib = 2 if u8 else 8
-        hin = R.PinnedBuffer(np.uint8 if u8 else np.complex64, cfg["n"] * (2 if u8 else 1))
-        hout = R.PinnedBuffer(np.complex64, n_out)
+    if not args.no_e2e and op in ("fftfilt", "fir", "fftfilt_decim", "fft", "fftfilt_real") and scaling == "weak":
+        real = op == "fftfilt_real"
+        ib = 2 if u8 else 4 if real else 8
+        ob = 4 if real else 8
+        hin = R.PinnedBuffer(np.uint8 if u8 else np.float32 if real else np.complex64, cfg["n"] * (2 if u8 else 1))
+        hout = R.PinnedBuffer(np.float32 if real else np.complex64, n_out)
         R.lib().rrc_memcpy_d2h(dev, hin.ptr, din.data_ptr(), cfg["n"] * ib, stream)
         torch.cuda.synchronize()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         run_host = (lambda: f.decim_run_host(hin, cfg["deci"], hout)) if op == "fftfilt_decim" else (lambda: f.run_host(hin, hout))
         for _ in range(2):
-            f.reset() if op in ("fftfilt", "fftfilt_decim") else None
+            f.reset() if op in ("fftfilt", "fftfilt_decim", "fftfilt_real") else None
             run_host()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            if op in ("fftfilt", "fftfilt_decim"):
+            if op in ("fftfilt", "fftfilt_decim", "fftfilt_real"):
                 f.reset()
             got = run_host()
         torch.cuda.synchronize()
@@ -405,7 +426,7 @@ def run_gpu(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
         e2e = {"value": units * world / (dt / e2e_steps) / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": int(ib * (n_in if op not in ("fir",) else cfg["n"])), "d2h_bytes_per_step": int(8 * len(got)),
+               "h2d_bytes_per_step": int(ib * (n_in if op not in ("fir",) else cfg["n"])), "d2h_bytes_per_step": int(ob * len(got)),
                "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3, "timer": "host wall clock around rrc_*_run_host (returns after D2H completes)"}
         hin.free(); hout.free()
 
@@ -430,7 +451,7 @@ def run_gpu(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
                 "kernel": {"fftfilt": "fftfilt_kernel", "fir": "fir_poly_kernel<float2,float,1,false,16>", "fir_demod": "fir_rt_kernel<10,DEMOD,8,2>",
-                           "resample": "resample_kernel", "decode": "rtlsdr_decode_kernel", "fft": "fftstream_kernel<10>",
+                           "resample": "resample_kernel", "decode": "rtlsdr_decode_kernel", "fft": "fftstream_kernel<10>", "fftfilt_real": "fftfilt_kernel (real-stream mode)",
                            "fftfilt_decim": "fftfilt_fold_kernel<4> (65536-point, 4-CTA cluster) + history update"}[op],
                 "duration_ms": ms_per_step,
                 "note": "duration = CUDA-event time of the whole step on the launching stream / steps; the step is this one kernel"
@@ -466,7 +487,14 @@ def cpu_baseline(cfg, threads: int, budget_s: float):
     from oracle import oracle as O
     op = cfg["op"]
     taps = taps_for(cfg) if op not in ("resample", "decode", "fft") else None
-    if op == "fftfilt":
+    if op == "fftfilt_real":
+        # the reference's FftFilterFloat: widen to Complex, complex FftFilter, keep .re (src/fft_filter.rs:428-470)
+        per = 1 << 21
+        xr = O.synth_f32(SEED + 8, 0, per)
+        objs = [O.FftFilt(taps, fast=True) for _ in range(threads)]
+        fn = lambda i: len(np.ascontiguousarray(objs[i].run(xr.astype(np.complex64)).real))
+        sample = f"{threads} x 2^21 f32 samples per repetition, widen -> overlap-add FftFilter (F=16384) -> .re like the reference"
+    elif op == "fftfilt":
         per = 1 << 21
         x = O.synth_c32(SEED + 2, 0, per)
         objs = [O.FftFilt(taps, fast=True) for _ in range(threads)]

@@ -1,7 +1,9 @@
-timeout 300 python bench.py --config c2 --steps 20 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('c2 normal', round(d['ms_per_step'],4))"
-cp rustradio_b200/librustradio_cuda.so /tmp/keep.so; cp gpurun_exp_nopowers.so rustradio_b200/librustradio_cuda.so
-timeout 300 python bench.py --config c2 --steps 20 --warmup 3 --no-cpu --no-e2e 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('c2 no-powers what-if', round(d['ms_per_step'],4))"
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -12
+for c in a12; do timeout 600 python bench.py --config $c --steps 20 --warmup 3 > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; tail -2 gpurun_out/bench_$c.err; python - <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/bench_$c.json')); print('$c', round(d['ms_per_step'],4), 'ms', round(d['value']), 'Msps frac', round(d['roofline']['frac'],3), 'e2e', d['e2e'] and round(d['e2e']['value']), 'cpu', d['cpu_baseline'] and round(d['cpu_baseline']['value'],1))
+except Exception as e: print('$c failed', e)
+PY
+done

@@ -148,6 +148,12 @@ int rrc_fir_run_host(rrc_fir_t* h, const void* in_host, size_t n_in, void* out_h
 typedef struct rrc_fftfilt rrc_fftfilt_t;
 
 int rrc_fftfilt_c32_create(int device, const float* taps_c32, size_t ntaps, rrc_fftfilt_t** out);
+/* FftFilterFloat (src/fft_filter.rs:365-491): real taps on a real stream.  The handle's run /
+ * run_host / set_history then take f32 arrays (n, history length and counts in samples as before).
+ * The reference widens to Complex, runs the complex filter and keeps .re; here two consecutive real
+ * blocks ride through one complex transform as its real and imaginary parts (exact for real taps),
+ * i.e. half the transforms and no widened intermediate. */
+int rrc_fftfilt_f32_create(int device, const float* taps_f32, size_t ntaps, rrc_fftfilt_t** out);
 int rrc_fftfilt_destroy(rrc_fftfilt_t* h);
 int rrc_fftfilt_reset(rrc_fftfilt_t* h, void* stream);          /* zero the carried history */
 /* Load the carried history (the ntaps-1 samples that precede the next run's input) from a

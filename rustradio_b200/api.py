@@ -76,6 +76,7 @@ _SIGS = {
     "rrc_fir_c32_demod_run_batch": [_vp, _vp, _sz, _sz, _f, _vp, _sz, _sz, _sz, _vp],
     "rrc_fir_run_host": [_vp, _vp, _sz, _vp, _P(_sz)],
     "rrc_fftfilt_c32_create": [_i, _vp, _sz, _P(_vp)],
+    "rrc_fftfilt_f32_create": [_i, _vp, _sz, _P(_vp)],
     "rrc_fftfilt_destroy": [_vp],
     "rrc_fftfilt_reset": [_vp, _vp],
     "rrc_fftfilt_set_history": [_vp, _vp, _sz, _vp],
@@ -368,11 +369,15 @@ def fftfilt_plan(ntaps: int, buffered: int, in_len: int, out_free: int):
 
 
 class FftFilt:
-    def __init__(self, taps, device: int = 0):
-        t = np.ascontiguousarray(taps, np.complex64)
+    def __init__(self, taps, device: int = 0, real: bool = False):
+        """real=True: FftFilterFloat — f32 taps on an f32 stream (rrc_fftfilt_f32_create)."""
+        self.real = real
+        self.dtype = np.float32 if real else np.complex64
+        t = np.ascontiguousarray(taps, self.dtype)
         self.device, self.ntaps = device, len(t)
         h = C.c_void_p()
-        _ck(lib().rrc_fftfilt_c32_create(device, t.ctypes.data if len(t) else None, len(t), C.byref(h)))
+        fn = lib().rrc_fftfilt_f32_create if real else lib().rrc_fftfilt_c32_create
+        _ck(fn(device, t.ctypes.data if len(t) else None, len(t), C.byref(h)))
         self.h = h.value
         self.ref_fft_size, self.nsamples = fftfilt_ref_fft_size(len(t))
 
@@ -402,10 +407,10 @@ class FftFilt:
 
     def run_host(self, x, out=None) -> np.ndarray:
         u8 = getattr(self, "in_u8", False)
-        xa = x.array if isinstance(x, PinnedBuffer) else np.ascontiguousarray(x, np.uint8 if u8 else np.complex64)
+        xa = x.array if isinstance(x, PinnedBuffer) else np.ascontiguousarray(x, np.uint8 if u8 else self.dtype)
         n_in = len(xa) // 2 if u8 else len(xa)
         n_out = (n_in // self.nsamples) * self.nsamples
-        oa = out.array if isinstance(out, PinnedBuffer) else (out if out is not None else np.empty(n_out, np.complex64))
+        oa = out.array if isinstance(out, PinnedBuffer) else (out if out is not None else np.empty(n_out, self.dtype))
         n = _sz(0)
         _ck(lib().rrc_fftfilt_run_host(self.h, xa.ctypes.data, n_in, oa.ctypes.data, C.byref(n)))
         return oa[: n.value]
@@ -422,13 +427,13 @@ class FftFilt:
 
     def filter(self, x: np.ndarray) -> np.ndarray:
         """Upload n samples, produce n outputs of the running convolution (stateful)."""
-        x = np.ascontiguousarray(x, np.complex64)
+        x = np.ascontiguousarray(x, self.dtype)
         if len(x) == 0:
-            return np.empty(0, np.complex64)
+            return np.empty(0, self.dtype)
         din = DeviceBuffer.from_numpy(x, self.device)
         dout = DeviceBuffer(x.nbytes, self.device)
         self.run(din, len(x), dout)
-        return dout.download(np.complex64, len(x))
+        return dout.download(self.dtype, len(x))
 
     def __del__(self):
         try:

@@ -312,18 +312,19 @@ int FirFilter::work(BlockRet* ret) {          // src/fir.rs:492-550
 
 // ------------------------------------------------------------------ FftFilter -----
 int FftFilter::create(std::unique_ptr<ReadStream> src, const float* taps, size_t ntaps, const StreamOpts& o,
-                      std::unique_ptr<FftFilter>* out) {
+                      std::unique_ptr<FftFilter>* out, bool real) {
     if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
-    if (src->buffer().elem() != 8) return fail(RRC_ERR_INVALID, "FftFilter: stream must carry Complex<f32>");
+    const size_t elem = real ? 4 : 8;
+    if (src->buffer().elem() != elem) return fail(RRC_ERR_INVALID, real ? "FftFilter(real): stream must carry f32" : "FftFilter: stream must carry Complex<f32>");
     std::unique_ptr<FftFilter> b(new FftFilter());
-    b->device_ = o.device; b->ntaps_ = ntaps;
-    RRC_TRY(rrc_fftfilt_c32_create(o.device, taps, ntaps, &b->h_));
+    b->device_ = o.device; b->ntaps_ = ntaps; b->elem_ = elem;
+    RRC_TRY(real ? rrc_fftfilt_f32_create(o.device, taps, ntaps, &b->h_) : rrc_fftfilt_c32_create(o.device, taps, ntaps, &b->h_));
     size_t fft_size;
     RRC_TRY(rrc_fftfilt_ref_fft_size(ntaps, &fft_size, &b->nsamples_));
     RRC_CUDA(cudaSetDevice(o.device));
-    RRC_CUDA(cudaMalloc((void**)&b->partial_, b->nsamples_ * 8));
+    RRC_CUDA(cudaMalloc((void**)&b->partial_, b->nsamples_ * elem));
     b->src_ = std::move(src);
-    RRC_TRY(make_output(8, o, &b->dst_, &b->out_r_));
+    RRC_TRY(make_output(elem, o, &b->dst_, &b->out_r_));
     *out = std::move(b);
     return RRC_OK;
 }
@@ -333,7 +334,7 @@ FftFilter::~FftFilter() {
 }
 
 int FftFilter::work(BlockRet* ret) {          // src/fft_filter.rs:290-354, whole loop in one pass
-    const size_t S = nsamples_;
+    const size_t S = nsamples_, E = elem_;
     cudaStream_t st = (cudaStream_t)graph_stream(device_);
     char* outp; size_t out_free;
     dst_->buffer().write_window(&outp, &out_free);
@@ -345,12 +346,12 @@ int FftFilter::work(BlockRet* ret) {          // src/fft_filter.rs:290-354, whol
     const cudaMemcpyKind in_kind = host_in ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     RRC_CUDA(cudaSetDevice(device_));
     char* dout = nullptr;
-    if (blocks) RRC_TRY(stage_output(dst_->buffer(), outp, blocks * S * 8, sout_, device_, &dout));
+    if (blocks) RRC_TRY(stage_output(dst_->buffer(), outp, blocks * S * E, sout_, device_, &dout));
     size_t ipos = 0;       // input samples handed to the filter so far
     size_t done = 0;       // blocks done
     if (blocks && buffered_ > 0) {            // complete the block that was being accumulated (:306-308)
         const size_t add = S - buffered_;
-        RRC_CUDA(cudaMemcpyAsync(partial_ + buffered_ * 8, in, add * 8, in_kind, st));
+        RRC_CUDA(cudaMemcpyAsync(partial_ + buffered_ * E, in, add * E, in_kind, st));
         RRC_TRY(rrc_fftfilt_run(h_, (const float*)partial_, S, (float*)dout, st));
         ipos = add; done = 1;
     }
@@ -358,20 +359,20 @@ int FftFilter::work(BlockRet* ret) {          // src/fft_filter.rs:290-354, whol
         const size_t nb = blocks - done;
         const char* din;
         if (host_in) {
-            RRC_TRY(sin_.reserve(device_, nb * S * 8));
-            RRC_CUDA(cudaMemcpyAsync(sin_.ptr, in + ipos * 8, nb * S * 8, cudaMemcpyHostToDevice, st));
+            RRC_TRY(sin_.reserve(device_, nb * S * E));
+            RRC_CUDA(cudaMemcpyAsync(sin_.ptr, in + ipos * E, nb * S * E, cudaMemcpyHostToDevice, st));
             din = sin_.ptr;
         } else {
-            din = in + ipos * 8;
+            din = in + ipos * E;
         }
-        RRC_TRY(rrc_fftfilt_run(h_, (const float*)din, nb * S, (float*)(dout + done * S * 8), st));
+        RRC_TRY(rrc_fftfilt_run(h_, (const float*)din, nb * S, (float*)(dout + done * S * E), st));
         ipos += nb * S;
     }
     // trailing partial accumulation (:306-327): buf keeps `buffered_after` samples
     const size_t base = blocks ? 0 : buffered_;
-    if (consume > ipos) RRC_CUDA(cudaMemcpyAsync(partial_ + base * 8, in + ipos * 8, (consume - ipos) * 8, in_kind, st));
+    if (consume > ipos) RRC_CUDA(cudaMemcpyAsync(partial_ + base * E, in + ipos * E, (consume - ipos) * E, in_kind, st));
     if (host_in) RRC_CUDA(cudaStreamSynchronize(st));          // the host window is released by consume()
-    if (blocks) RRC_TRY(finish_output(dst_->buffer(), outp, blocks * S * 8, sout_, device_));
+    if (blocks) RRC_TRY(finish_output(dst_->buffer(), outp, blocks * S * E, sout_, device_));
 
     // tags (:309-313): absolute position in (buf ++ input) = buffered + pos; emitted with their block.
     std::vector<Tag> out_tags = std::move(pending_tags_);
@@ -394,14 +395,12 @@ int FftFilter::work(BlockRet* ret) {          // src/fft_filter.rs:290-354, whol
 }
 
 // ------------------------------------------------------------- FftFilterFloat -----
-__global__ void widen_kernel(const float* __restrict__ in, float2* __restrict__ out, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = make_float2(in[i], 0.f);
-}
-__global__ void real_part_kernel(const float2* __restrict__ in, float* __restrict__ out, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = in[i].x;
-}
+// The reference widens the stream to Complex, runs the complex FftFilter and keeps .re
+// (src/fft_filter.rs:428-470).  Here the inner filter runs the kernel's real-stream mode on f32 inner
+// rings (two real blocks per complex transform, rrc_fftfilt_f32_create), so the "convert" and
+// "replicate" steps are plain copies and no widened intermediate exists.  The inner rings are sized
+// for the same number of SAMPLES as the reference's Complex inner streams, so counts, BlockRets and tag
+// positions per work() call are unchanged.
 
 int FftFilterFloat::create(std::unique_ptr<ReadStream> src, const float* taps, size_t ntaps, const StreamOpts& o,
                            std::unique_ptr<FftFilterFloat>* out) {
@@ -410,16 +409,15 @@ int FftFilterFloat::create(std::unique_ptr<ReadStream> src, const float* taps, s
     if (!taps || ntaps == 0) return fail(RRC_ERR_INVALID, "FftFilterFloat needs at least one tap");
     std::unique_ptr<FftFilterFloat> b(new FftFilterFloat());
     b->device_ = o.device;
-    std::vector<float> ct(2 * ntaps, 0.f);                    // taps -> Complex::new(f, 0.0) (:404)
-    for (size_t i = 0; i < ntaps; ++i) ct[2 * i] = taps[i];
     StreamOpts inner = o;
     inner.res = Residency::Device;                            // inner streams never leave the device
+    inner.bytes = o.bytes / 2;                                // f32 ring with the sample capacity of a Complex one
     std::string err;
-    StreamPair p = new_stream(8, inner.bytes, inner.res, inner.device, &err);
+    StreamPair p = new_stream(4, inner.bytes, inner.res, inner.device, &err);
     if (!p.w) return fail(RRC_ERR_CUDA, "new_stream failed: %s", err.c_str());
     b->inner_in_ = std::move(p.w);
     b->inner_in_id_ = b->inner_in_->id();
-    RRC_TRY(FftFilter::create(std::move(p.r), ct.data(), ntaps, inner, &b->complex_));
+    RRC_TRY(FftFilter::create(std::move(p.r), taps, ntaps, inner, &b->complex_, /*real=*/true));
     b->inner_out_ = b->complex_->take_output();
     b->src_ = std::move(src);
     RRC_TRY(make_output(4, o, &b->dst_, &b->out_r_));
@@ -437,12 +435,9 @@ int FftFilterFloat::work(BlockRet* ret) {     // src/fft_filter.rs:428-490
         inner_in_->buffer().write_window(&to, &to_len);
         const size_t n = std::min(in_len, to_len);
         if (n) {
-            const char* din;
-            RRC_TRY(stage_input(src_->buffer(), in, n * 4, sin_, device_, &din));
-            widen_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, st>>>((const float*)din, (float2*)to, n);
-            RRC_CHECK_LAUNCH();
-            rrc::count_launch();
-            if (src_->buffer().residency() == Residency::Host) RRC_CUDA(cudaStreamSynchronize(st));
+            const bool host_in = src_->buffer().residency() == Residency::Host;
+            RRC_CUDA(cudaMemcpyAsync(to, in, n * 4, host_in ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+            if (host_in) RRC_CUDA(cudaStreamSynchronize(st));
         }
         tags.erase(std::remove_if(tags.begin(), tags.end(), [&](const Tag& t) { return t.pos >= n; }), tags.end());
         inner_in_->buffer().produce(n, tags);
@@ -460,9 +455,7 @@ int FftFilterFloat::work(BlockRet* ret) {     // src/fft_filter.rs:428-490
         if (n) {
             char* dout;
             RRC_TRY(stage_output(dst_->buffer(), to, n * 4, sout_, device_, &dout));
-            real_part_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, st>>>((const float2*)from, (float*)dout, n);
-            RRC_CHECK_LAUNCH();
-            rrc::count_launch();
+            RRC_CUDA(cudaMemcpyAsync(dout, from, n * 4, cudaMemcpyDeviceToDevice, st));
             RRC_TRY(finish_output(dst_->buffer(), to, n * 4, sout_, device_));
         }
         tags.erase(std::remove_if(tags.begin(), tags.end(), [&](const Tag& t) { return t.pos >= n; }), tags.end());

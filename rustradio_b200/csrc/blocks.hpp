@@ -222,8 +222,10 @@ private:
 
 class FftFilter : public Block {
 public:
-    static int create(std::unique_ptr<ReadStream> src, const float* taps_c32, size_t ntaps, const StreamOpts& o,
-                      std::unique_ptr<FftFilter>* out);
+    // real = false: FftFilter (Complex stream, Complex taps).  real = true: the inner filter of
+    // FftFilterFloat — f32 stream, `taps` are f32, the device runs the real-stream kernel mode.
+    static int create(std::unique_ptr<ReadStream> src, const float* taps, size_t ntaps, const StreamOpts& o,
+                      std::unique_ptr<FftFilter>* out, bool real = false);
     ~FftFilter() override;
     int work(BlockRet* ret) override;
     const char* block_name() const override { return "FftFilter"; }
@@ -234,7 +236,7 @@ private:
     std::unique_ptr<ReadStream> src_;
     std::unique_ptr<WriteStream> dst_;
     rrc_fftfilt_t* h_ = nullptr;
-    size_t ntaps_ = 0, nsamples_ = 0, buffered_ = 0;
+    size_t ntaps_ = 0, nsamples_ = 0, buffered_ = 0, elem_ = 8;
     char* partial_ = nullptr;                 // device: up to nsamples accumulated samples (self.buf)
     std::vector<Tag> pending_tags_;           // self.tags
     int device_ = 0;

@@ -34,6 +34,15 @@ constexpr size_t FFTFILT_SMEM = (size_t)(fftk::SMEM_ELEMS + 512 + 512 + fftk::HR
 // Input prefetch: pulls the input segment of block `nb` into L2 with one 8 KiB bulk prefetch per warp
 // (16 x 8 KiB = segment; SASS UBLKPF.L2).
 __device__ __forceinline__ void prefetch_segment(const BlockIO& io, long long nb, long long nblocks, int tid) {
+    if (io.real) {      // two real segments of N floats, V apart: warps 0-7 the first, 8-15 the second, 8 KiB each
+        const int w = tid >> 5;
+        const long long seg0 = 2 * nb * (long long)io.V - io.T1 - io.shift + (w >> 3) * (long long)io.V + (long long)(w & 7) * 2048;
+        if ((tid & 31) == 0 && nb < nblocks && seg0 >= 0 && seg0 + 2048 <= io.n_in) {
+            const unsigned long long a = (reinterpret_cast<unsigned long long>(io.in) + (unsigned long long)seg0 * 4 + 15ull) & ~15ull;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(8192 - 16) : "memory");
+        }
+        return;
+    }
     const long long seg0 = nb * (long long)io.V - io.T1 - io.shift + (long long)(tid >> 5) * 1024;
     if ((tid & 31) == 0 && nb < nblocks && seg0 >= 0 && seg0 + 1024 <= io.n_in) {
         const unsigned long long esz = io.in_u8 ? 2 : 8;         // bytes per input sample
@@ -200,6 +209,15 @@ __global__ void fftfilt_hist_kernel(const float2* __restrict__ hist_cur, const f
     }
 }
 
+// Real-stream history: T1 floats.
+__global__ void fftfilt_hist_real_kernel(const float* __restrict__ hist_cur, const float* __restrict__ in,
+                                         long long n, int T1, float* __restrict__ hist_next) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T1; i += gridDim.x * blockDim.x) {
+        const long long s = n - T1 + i;
+        hist_next[i] = s >= 0 ? in[s] : hist_cur[s + T1];
+    }
+}
+
 }  // namespace rrc
 
 using namespace rrc;
@@ -232,9 +250,10 @@ int launch_part16(rrc_fftfilt* h, const BlockIO& io, const float2* Hd, cudaStrea
 
 template <bool DECIM, bool ACCUM>
 int launch_part(rrc_fftfilt* h, const BlockIO& io, const float2* Hp, cudaStream_t st) {
-    const long long nblocks = (io.n_in + io.V - 1) / io.V;
+    long long nblocks = (io.n_in + io.V - 1) / io.V;
+    if (io.real) nblocks = (nblocks + 1) / 2;                   // two real blocks per complex transform
     const int grid = (int)std::min<long long>(nblocks, sm_count(h->device));
-    auto kern = h->variant == 33 ? fftfilt_pp_kernel<DECIM, ACCUM> : h->variant == 34 ? fftfilt_st_kernel<DECIM, ACCUM> : h->variant == 35 ? fftfilt_kernel<DECIM, ACCUM, true> : fftfilt_kernel<DECIM, ACCUM, false>;
+    auto kern = io.real ? fftfilt_kernel<DECIM, ACCUM, false> : h->variant == 33 ? fftfilt_pp_kernel<DECIM, ACCUM> : h->variant == 34 ? fftfilt_st_kernel<DECIM, ACCUM> : h->variant == 35 ? fftfilt_kernel<DECIM, ACCUM, true> : fftfilt_kernel<DECIM, ACCUM, false>;
     RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_SMEM));
     static const int tune = [] { const char* e = getenv("RRC_FFTFILT_TUNE"); return e ? (int)strtol(e, nullptr, 0) : 1; }();
     kern<<<grid, fftk::NT, FFTFILT_SMEM, st>>>(io, Hp, h->tw1, h->tw2, nblocks, tune);
@@ -254,6 +273,7 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
     io.deci = (int)deci;
     io.skip = (long long)skip;
     io.in_u8 = h->in_u8;
+    io.real = h->real;
     const bool decim = !(deci == 1 && skip == 0);
     long long shift = 0;
     for (size_t p = 0; p < h->part_T1.size(); ++p) {
@@ -261,7 +281,7 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
         io.V = fftk::N - io.T1;
         io.shift = shift;
         int s;
-        if (h->variant == 16) {
+        if (h->variant == 16 && !h->real) {
             if (p == 0) s = decim ? launch_part16<true, false>(h, io, h->part_Hd[p], st) : launch_part16<false, false>(h, io, h->part_Hd[p], st);
             else        s = decim ? launch_part16<true, true>(h, io, h->part_Hd[p], st) : launch_part16<false, true>(h, io, h->part_Hd[p], st);
         } else if (p == 0) s = decim ? launch_part<true, false>(h, io, h->part_Hp[p], st) : launch_part<false, false>(h, io, h->part_Hp[p], st);
@@ -269,7 +289,13 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
         RRC_TRY(s);
         shift += io.T1 + 1;
     }
-    if (h->T1 > 0) {
+    if (h->T1 > 0 && h->real) {
+        fftfilt_hist_real_kernel<<<(h->T1 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(h->hist[h->cur]), in, (long long)n, h->T1,
+                                                                    reinterpret_cast<float*>(h->hist[h->cur ^ 1]));
+        RRC_CHECK_LAUNCH();
+        count_launch();
+        h->cur ^= 1;
+    } else if (h->T1 > 0) {
         fftfilt_hist_kernel<<<(h->T1 + 255) / 256, 256, 0, st>>>(h->hist[h->cur], io.in, (long long)n, h->T1, h->hist[h->cur ^ 1], h->in_u8);
         RRC_CHECK_LAUNCH();
         count_launch();
@@ -355,6 +381,18 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
     return RRC_OK;
 }
 
+int rrc_fftfilt_f32_create(int device, const float* taps_f32, size_t ntaps, rrc_fftfilt_t** out) {
+    if (!out) return fail(RRC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!taps_f32 || ntaps == 0) return fail(RRC_ERR_INVALID, "FftFilterFloat needs at least one tap (src/fft_filter.rs:146)");
+    std::vector<float> ct(2 * ntaps, 0.f);                      // taps -> Complex::new(f, 0.0), src/fft_filter.rs:404
+    for (size_t i = 0; i < ntaps; ++i) ct[2 * i] = taps_f32[i];
+    RRC_TRY(rrc_fftfilt_c32_create(device, ct.data(), ntaps, out));
+    (*out)->real = 1;
+    (*out)->variant = 32;
+    return RRC_OK;
+}
+
 int rrc_fftfilt_destroy(rrc_fftfilt_t* h) {
     if (!h) return RRC_OK;
     cudaSetDevice(h->device);
@@ -381,12 +419,13 @@ int rrc_fftfilt_set_history(rrc_fftfilt_t* h, const float* hist, size_t n, void*
     if (n == 0) return RRC_OK;
     if (!hist) return fail(RRC_ERR_INVALID, "hist is NULL");
     RRC_CUDA(cudaSetDevice(h->device));
-    RRC_CUDA(cudaMemcpyAsync(h->hist[h->cur], hist, n * sizeof(float2), cudaMemcpyDeviceToDevice, as_stream(stream)));
+    RRC_CUDA(cudaMemcpyAsync(h->hist[h->cur], hist, n * (h->real ? sizeof(float) : sizeof(float2)), cudaMemcpyDeviceToDevice, as_stream(stream)));
     return RRC_OK;
 }
 
 int rrc_fftfilt_set_input_u8iq(rrc_fftfilt_t* h, int on) {
     if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
+    if (on && h->real) return fail(RRC_ERR_INVALID, "u8 I/Q input needs a Complex filter");
     h->in_u8 = on ? 1 : 0;
     return RRC_OK;
 }
@@ -420,6 +459,7 @@ int rrc_fftfilt_decim_run(rrc_fftfilt_t* h, const float* in, size_t n, size_t de
     // deci == 1 && skip == 0 degenerates to the plain path; otherwise the store
     // predicate in phase A' keeps y[skip + k*deci].
     if (deci == 1 && skip == 0) return launch(h, in, n, out, n, 1, 0, as_stream(stream));
+    if (h->real) return fail(RRC_ERR_UNSUPPORTED, "fused decimation is not implemented for real (f32) streams");
     // deci == 8: folded spectrum + 8x smaller inverse transform (fftfilt_fold.cu); 65536-point
     // cluster kernel for 12289 < ntaps <= 49153.  RRC_FFTFILT_NO_FOLD=1 forces the store-predicate path.
     if (fold_supported(h, deci) == RRC_OK) {
@@ -446,14 +486,15 @@ int rrc_fftfilt_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, fl
     if (!in_host || !out_host) return fail(RRC_ERR_INVALID, "in/out is NULL");
     RRC_TRY(h->pipe.init(h->device));
     const size_t chunk = PIPE_CHUNK_SAMPLES;
-    const size_t esz = h->in_u8 ? 2 : sizeof(float2);           // input bytes per sample
-    RRC_TRY(h->pipe.reserve(std::min(chunk, total) * esz, std::min(chunk, total) * sizeof(float2)));
+    const size_t esz = h->real ? sizeof(float) : h->in_u8 ? 2 : sizeof(float2);   // input bytes per sample
+    const size_t osz = h->real ? sizeof(float) : sizeof(float2);
+    RRC_TRY(h->pipe.reserve(std::min(chunk, total) * esz, std::min(chunk, total) * osz));
     int i = 0;
     for (size_t off = 0; off < total; off += chunk, ++i) {
         const size_t n = std::min(chunk, total - off);
         RRC_TRY(h->pipe.stage_in(i, reinterpret_cast<const char*>(in_host) + off * esz, n * esz));
         RRC_TRY(launch(h, (const float*)h->pipe.d_in[i & 1], n, (float*)h->pipe.d_out[i & 1], n, 1, 0, h->pipe.s_comp));
-        RRC_TRY(h->pipe.drain_out(i, out_host + 2 * off, n * sizeof(float2)));
+        RRC_TRY(h->pipe.drain_out(i, reinterpret_cast<char*>(out_host) + off * osz, n * osz));
     }
     return h->pipe.finish();
 }

@@ -50,7 +50,18 @@ struct BlockIO {
     int deci;                // output decimation (fused RationalResampler(1,deci)); 1 = none
     long long skip;          // first kept filter output index (decimation phase)
     int in_u8 = 0;           // 1: `in` is u8 I/Q pairs (RtlSdrDecode fused into the load); hist is always c32
+    // 1: REAL stream (FftFilterFloat, src/fft_filter.rs:365-491) with real taps: in / hist / out are f32
+    // arrays and kernel block b carries the two consecutive real blocks 2b (real part) and 2b+1
+    // (imaginary part) through ONE complex transform — h real => h*(a + ib) = h*a + i h*b — so a real
+    // stream costs half the transforms of the reference's widen -> complex filter -> .re.
+    int real = 0;
 };
+
+// Sample g of a real stream with its carried history (g < 0) and zero fill past the end.
+RRC_HD float fetch_real(const BlockIO& io, long long g) {
+    if (g < 0) return g + io.T1_total >= 0 ? reinterpret_cast<const float*>(io.hist)[g + io.T1_total] : 0.f;
+    return g < io.n_in ? reinterpret_cast<const float*>(io.in)[g] : 0.f;
+}
 
 RRC_HD int phys(int k1, int r, int c) { return k1 * PLANE_PITCH + r * ROW_PITCH + c; }
 
@@ -127,8 +138,23 @@ template <class Turn = NoTurn>
 RRC_HD void phase_a(int tid, long long blk, const BlockIO& io, const float2* tw1, float2* sm, Turn turn = Turn()) {
     float2 v[32];
     // input index of segment element 0 (tap partition p filters the input delayed by `shift`)
-    const long long seg0 = blk * (long long)io.V - io.T1 - io.shift;
-    if (seg0 >= 0 && seg0 + N <= io.n_in) {                     // interior block: no bounds checks
+    const long long seg0 = (io.real ? 2 * blk : blk) * (long long)io.V - io.T1 - io.shift;
+    if (io.real) {
+        if (seg0 >= 0 && seg0 + io.V + N <= io.n_in) {          // both real blocks interior
+            const float* p = reinterpret_cast<const float*>(io.in) + seg0 + tid;
+            float a[32], b[32];
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) { a[n1] = p[512 * n1]; b[n1] = p[512 * n1 + io.V]; }
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = make_float2(a[n1], b[n1]);
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const long long g = seg0 + tid + 512 * n1;
+                v[bitrev(n1, 5)] = make_float2(fetch_real(io, g), fetch_real(io, g + io.V));
+            }
+        }
+    } else if (seg0 >= 0 && seg0 + N <= io.n_in) {              // interior block: no bounds checks
         if (io.in_u8) {
             const unsigned short* p = reinterpret_cast<const unsigned short*>(io.in) + seg0 + tid;
             unsigned int w[32];
@@ -359,8 +385,20 @@ RRC_HD void phase_ai(int tid, long long blk, const BlockIO& io, const float2* tw
     turn.release();
     // v[n1] is segment element n = tid + 512*n1; elements n >= T1 are valid
     // outputs, filter output index o = o0 + n.
-    const long long o0 = blk * (long long)io.V - io.T1;
+    const long long o0 = (io.real ? 2 * blk : blk) * (long long)io.V - io.T1;
     const int tq = io.T1 >> 9, tr = io.T1 & 511;
+    if (io.real) {                                              // real stream: .re -> block 2b, .im -> block 2b+1
+        float* q = reinterpret_cast<float*>(io.out) + o0 + tid;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            if (n1 > tq || (n1 == tq && tid >= tr)) {
+                const long long o = o0 + tid + 512 * n1;
+                if (o < io.n_out) q[512 * n1] = ACCUM ? q[512 * n1] + v[n1].x : v[n1].x;
+                if (o + io.V < io.n_out) q[512 * n1 + io.V] = ACCUM ? q[512 * n1 + io.V] + v[n1].y : v[n1].y;
+            }
+        }
+        return;
+    }
     if constexpr (!DECIM) {
         float2* q = io.out + o0 + tid;
         if (o0 + N <= io.n_out) {                               // interior: only the n >= T1 test

@@ -30,6 +30,7 @@ struct rrc_fftfilt {
     float2* tw1_16 = nullptr;
     float2* tw2_16 = nullptr;
     float2* tw3_16 = nullptr;
+    int real = 0;                     // real stream + real taps (rrc_fftfilt_f32_create): f32 in / out / history
     int in_u8 = 0;                    // 1: run() inputs are u8 I/Q pairs (rrc_fftfilt_set_input_u8iq)
     int variant = 32;                 // points per thread: 32 (512 threads) or 16 (1024 threads)
     float2* tw1 = nullptr;

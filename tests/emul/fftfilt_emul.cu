@@ -64,6 +64,44 @@ extern "C" int emul_fftfilt(const float* taps, long long ntaps, const float* in,
     return 0;
 }
 
+// Real-stream mode (FftFilterFloat): f32 in / hist / out, two real blocks per complex transform.
+extern "C" int emul_fftfilt_real(const float* taps_f32, long long ntaps, const float* in, long long n,
+                                 const float* hist /* (ntaps-1) f32 or NULL */, float* out) {
+    const int T1_total = (int)ntaps - 1;
+    std::vector<float> h(T1_total > 0 ? T1_total : 1, 0.f);
+    if (hist && T1_total > 0) memcpy(h.data(), hist, sizeof(float) * T1_total);
+    std::vector<float> ct(2 * ntaps, 0.f);
+    for (long long i = 0; i < ntaps; ++i) ct[2 * i] = taps_f32[i];
+    const long long part = ntaps <= 12289 ? ntaps : 8193;
+    long long shift = 0;
+    for (long long off = 0; off < ntaps; off += part) {
+        const long long len = std::min(part, ntaps - off);
+        std::vector<float2> Hp, tw1, tw2;
+        build_tables(ct.data() + 2 * off, (size_t)len, Hp, tw1, tw2);
+        BlockIO io;
+        io.in = reinterpret_cast<const float2*>(in);
+        io.hist = reinterpret_cast<const float2*>(h.data());
+        io.out = reinterpret_cast<float2*>(out);
+        io.n_in = n; io.n_out = n; io.T1 = (int)len - 1; io.V = N - io.T1; io.deci = 1; io.skip = 0;
+        io.T1_total = T1_total; io.shift = shift; io.real = 1;
+        std::vector<float2> sm(SMEM_ELEMS), hres(HRES_ELEMS);
+        for (int t = 0; t < NT; ++t) load_hres(t, Hp.data(), hres.data());
+        const long long nreal = (n + io.V - 1) / io.V, nblocks = (nreal + 1) / 2;
+        for (long long blk = 0; blk < nblocks; ++blk) {
+            for (int t = 0; t < NT; ++t) phase_a(t, blk, io, tw1.data(), sm.data());
+            for (int t = 0; t < NT; ++t) phase_mid_b(t, tw2.data(), sm.data());
+            for (int t = 0; t < NT; ++t) phase_mid_c(t, Hp.data(), hres.data(), sm.data());
+            for (int t = 0; t < NT; ++t) phase_mid_bi(t, tw2.data(), sm.data());
+            for (int t = 0; t < NT; ++t) {
+                if (off == 0) phase_ai<false, false>(t, blk, io, tw1.data(), sm.data());
+                else phase_ai<false, true>(t, blk, io, tw1.data(), sm.data());
+            }
+        }
+        shift += len;
+    }
+    return 0;
+}
+
 // Same for the 1024-thread x 16-point variant (fftfilt16_core.cuh).
 extern "C" int emul_fftfilt16(const float* taps, long long ntaps, const float* in, long long n,
                               const float* hist, float* out, long long deci, long long skip, long long n_out) {

@@ -63,6 +63,32 @@ def test_emulated_kernel_twiddles_in_phase_c_and_staged_input(emul, monkeypatch,
     assert O.rel_rms(emul(taps, x, variant=32), O.conv_full_f64_fft(x, taps, n)) <= 1e-5
 
 
+@pytest.mark.parametrize("ntaps,n", [(1, 3000), (193, 30_000), (4097, 12288 * 3 + 5), (4097, 12288 * 2), (64, 16384 * 4 + 5), (16385, 70_000)])
+def test_emulated_real_stream_mode(emul, ntaps, n):
+    """FftFilterFloat mode: two consecutive real blocks per complex transform (odd and even block
+    counts, partial last block, tap partitions), with carried f32 history."""
+    import ctypes as C
+    from pathlib import Path
+    L = C.CDLL(str(Path(__file__).parent / "emul" / "_fftfilt_emul.so"))
+    L.emul_fftfilt_real.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
+    taps = O.low_pass_n(1.0, 0.05, ntaps).astype(np.float32) if ntaps > 1 else np.array([0.75], np.float32)
+    x = O.synth_f32(8, 0, n)
+    truth = O.conv_full_f64_fft(x.astype(np.complex64), taps.astype(np.complex64), n).real
+    out = np.zeros(n, np.float32)
+    L.emul_fftfilt_real(taps.ctypes.data, ntaps, x.ctypes.data, n, None, out.ctypes.data)
+    assert O.rel_rms(out, truth) <= 1e-5
+    cut = n // 3 + 1
+    o1, o2 = np.zeros(cut, np.float32), np.zeros(n - cut, np.float32)
+    L.emul_fftfilt_real(taps.ctypes.data, ntaps, x.ctypes.data, cut, None, o1.ctypes.data)
+    hist = np.zeros(max(ntaps - 1, 1), np.float32)
+    if ntaps > 1:
+        src = np.concatenate([np.zeros(ntaps - 1, np.float32), x[:cut]])
+        hist = np.ascontiguousarray(src[len(src) - (ntaps - 1):])
+    x2 = np.ascontiguousarray(x[cut:])
+    L.emul_fftfilt_real(taps.ctypes.data, ntaps, x2.ctypes.data, n - cut, hist.ctypes.data if ntaps > 1 else None, o2.ctypes.data)
+    assert O.rel_rms(np.concatenate([o1, o2]), truth) <= 1e-5
+
+
 @pytest.mark.parametrize("variant", [32, 16])
 def test_emulated_kernel_history_and_decimation(emul, variant):
     taps = O.low_pass_n(1.0, 0.1, 301).astype(np.complex64)

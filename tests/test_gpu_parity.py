@@ -206,6 +206,32 @@ def test_fftfilt_fused_decimation(R):
         assert O.rel_rms(dout.download(np.complex64, n), want) <= REL_RMS_BAR
 
 
+@pytest.mark.parametrize("ntaps,n", [(1, 5000), (193, 40_000), (4097, 12288 * 5 + 100), (4097, 12288 * 4), (12289, 50_000), (16385, 100_000)])
+def test_fftfilt_real_stream_mode(R, ntaps, n):
+    """FftFilterFloat compute (src/fft_filter.rs:365-491) with the real-stream kernel mode: two
+    consecutive real blocks per complex transform; carried f32 history across calls; host pipeline."""
+    taps = O.low_pass_n(1.0, 0.05, ntaps).astype(np.float32) if ntaps > 1 else np.array([0.75], np.float32)
+    x = O.synth_f32(33, 0, n)
+    truth = O.conv_full_f64_fft(x.astype(np.complex64), taps.astype(np.complex64), n).real
+    f = R.FftFilt(taps, real=True)
+    got = f.filter(x)
+    assert got.dtype == np.float32 and len(got) == n
+    assert O.rel_rms(got, truth) <= REL_RMS_BAR
+    f.reset()
+    cut = n // 3 + 1
+    y = np.concatenate([f.filter(x[:cut]), f.filter(x[cut:])])
+    assert O.rel_rms(y, truth) <= REL_RMS_BAR
+    # equals the reference's construction (widen -> complex filter -> .re) to rounding
+    fc = R.FftFilt(taps.astype(np.complex64))
+    assert O.rel_rms(got, fc.filter(x.astype(np.complex64)).real) <= 2e-6
+    f2 = R.FftFilt(taps, real=True)
+    yh = f2.run_host(x)
+    assert len(yh) == (n // f2.nsamples) * f2.nsamples
+    assert O.rel_rms(yh, truth[:len(yh)]) <= REL_RMS_BAR
+    with pytest.raises(R.RrcError):
+        f2.decim_run(R.DeviceBuffer(64), 8, 8, 0, R.DeviceBuffer(64))
+
+
 def test_fftfilt_decim_run_host_chunked(R, monkeypatch):
     """Host pipeline of FftFilter -> RationalResampler(1, deci): chunk boundaries carry the filter
     history and the resampler phase (chunk forced small so several chunks run)."""
