@@ -135,6 +135,30 @@ def alg_bytes(cfg, n_in, n_out):
     raise ValueError(cfg["op"])
 
 
+def alg_flops(cfg, n_in, n_out, fir=None):
+    """SURVEY 8(d) flop formulas.  FIR: 8*ntaps per output (4*ntaps when the kernel's declared real-tap
+    fast path is active); FFT filter: blocks*(2*5*F*log2 F + 6F + 2*ntaps) at the reference's F."""
+    op = cfg["op"]
+    if op in ("fir", "fir_demod"):
+        per = 4 if (fir is not None and fir.uses_real_taps) else 8
+        nout = n_out + (cfg.get("nchan", 0) if op == "fir_demod" else 0)      # FIR outputs = demod outputs + 1 per channel
+        return per * cfg["ntaps"] * nout
+    if op in ("fftfilt", "fftfilt_decim", "fftfilt_real"):
+        F = 2
+        while F < 2 * cfg["ntaps"] - 1:
+            F *= 2
+        F = max(F, 2)
+        f_ref = 1
+        while f_ref < cfg["ntaps"]:
+            f_ref *= 2
+        f_ref *= 2                                                   # calc_fft_size, src/fft_filter.rs:36-42
+        blocks = n_in / (f_ref - cfg["ntaps"])
+        return blocks * (2 * 5 * f_ref * np.log2(f_ref) + 6 * f_ref + 2 * cfg["ntaps"])
+    if op == "fft":
+        return (n_in / cfg["size"]) * 5 * cfg["size"] * np.log2(cfg["size"])
+    return 0
+
+
 # ---------------------------------------------------------------- clocks ----
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
@@ -456,6 +480,15 @@ def run_gpu(args):
                 "duration_ms": ms_per_step,
                 "note": "duration = CUDA-event time of the whole step on the launching stream / steps; the step is this one kernel"
                         + (" plus a <3 us history-update kernel" if op == "fftfilt" else "")}
+
+    # FP32 side of the roofline: algorithmic flops of the reference formulation against the
+    # FP32 FMA rate MEASURED on this pool's B200 (tools/microbench/fp32_pipes.cu: 125 lanes/clk/SM).
+    flops = alg_flops(cfg, n_in, n_out, f if op in ("fir", "fir_demod") else None)
+    if flops:
+        fp_peak = 148 * 125.0 * 2 * 1.965e9 / 1e12
+        roofline["fp32"] = {"algorithmic_flops_per_launch": flops, "achieved_tflops": flops / (ms_per_step * 1e-3) / 1e12,
+                            "peak_tflops": fp_peak, "frac": flops / (ms_per_step * 1e-3) / 1e12 / fp_peak,
+                            "peak_source": "measured FFMA issue rate (profiles/r01_microbench_fp32_pipes.txt) x 2 flop"}
 
     cpu = None
     if world == 1 and not args.no_cpu:

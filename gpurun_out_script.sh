@@ -1,9 +1,11 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -12
-for c in a12; do timeout 600 python bench.py --config $c --steps 20 --warmup 3 > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; tail -2 gpurun_out/bench_$c.err; python - <<PY
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/scale2_c2.json 2> gpurun_out/scale2_c2.err; tail -3 gpurun_out/scale2_c2.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 --shard time --no-e2e --no-cpu > gpurun_out/scale2_c2_time.json 2> gpurun_out/scale2_c2_time.err; tail -3 gpurun_out/scale2_c2_time.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 > gpurun_out/scale2_ref.json 2> gpurun_out/scale2_ref.err; tail -3 gpurun_out/scale2_ref.err
+python - <<PY
 import json
-try:
-    d=json.load(open('gpurun_out/bench_$c.json')); print('$c', round(d['ms_per_step'],4), 'ms', round(d['value']), 'Msps frac', round(d['roofline']['frac'],3), 'e2e', d['e2e'] and round(d['e2e']['value']), 'cpu', d['cpu_baseline'] and round(d['cpu_baseline']['value'],1))
-except Exception as e: print('$c failed', e)
+for f in ('scale2_c2','scale2_c2_time','scale2_ref'):
+    try:
+        d=json.loads(open(f'gpurun_out/{f}.json').read().strip().splitlines()[-1]); print(f, d.get('n_gpus'), round(d['value']), d.get('scaling'), d.get('ms_per_step'), (d.get('e2e') or {}).get('value'))
+    except Exception as e: print(f, 'failed', e)
 PY
-done
