@@ -93,7 +93,29 @@ def cfg_f2():
                 desc=f"FftStream forward FFT, {size}-point frames, 2^28 c32 samples")
 
 
-CONFIGS = {"a12": cfg_a12, "f2": cfg_f2, "c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4, "c5": cfg_c5, "c3u8": cfg_c3u8, "c5u8": cfg_c5u8, "f1": cfg_f1}
+# Hilbert and the sample-wise neighbours.
+def cfg_h1():
+    return dict(name="h1", op="hilbert", ntaps=65, n=1 << 29, dtype="f32",
+                desc="Hilbert 65 taps (Hamming), 2^29 f32 samples -> c32 (the examples' ax25/bell202 shape)")
+
+
+def cfg_e1():
+    return dict(name="e1", op="mulconst", n=1 << 29, dtype="c32", desc="MultiplyConst<Complex>, 2^29 c32 samples")
+
+
+def cfg_e2():
+    return dict(name="e2", op="mag2", n=1 << 29, dtype="c32", desc="ComplexToMag2, 2^29 c32 samples -> f32")
+
+
+def cfg_e3():
+    return dict(name="e3", op="tee", n=1 << 29, dtype="c32", desc="Tee<Complex>, 2^29 c32 samples -> two copies")
+
+
+def cfg_e4():
+    return dict(name="e4", op="iqbalance", n=1 << 29, dtype="c32", desc="IqBalance alpha=2.08e-6 (tau 0.2 s @2.4 Msps), 2^29 c32 samples")
+
+
+CONFIGS = {"h1": cfg_h1, "e1": cfg_e1, "e2": cfg_e2, "e3": cfg_e3, "e4": cfg_e4, "a12": cfg_a12, "f2": cfg_f2, "c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4, "c5": cfg_c5, "c3u8": cfg_c3u8, "c5u8": cfg_c5u8, "f1": cfg_f1}
 
 
 def low_pass_taps(ntaps: int, cutoff: float) -> np.ndarray:
@@ -132,6 +154,14 @@ def alg_bytes(cfg, n_in, n_out):
         return 4 * n_in + 4 * n_out
     if cfg["op"] == "resample":
         return 4 * (n_in + n_out)
+    if cfg["op"] == "hilbert":
+        return 4 * n_in + 8 * n_out
+    if cfg["op"] in ("mulconst", "iqbalance"):
+        return 8 * n_in + 8 * n_out
+    if cfg["op"] == "mag2":
+        return 8 * n_in + 4 * n_out
+    if cfg["op"] == "tee":
+        return 8 * n_in + 16 * n_out
     raise ValueError(cfg["op"])
 
 
@@ -156,6 +186,8 @@ def alg_flops(cfg, n_in, n_out, fir=None):
         return blocks * (2 * 5 * f_ref * np.log2(f_ref) + 6 * f_ref + 2 * cfg["ntaps"])
     if op == "fft":
         return (n_in / cfg["size"]) * 5 * cfg["size"] * np.log2(cfg["size"])
+    if op == "hilbert":
+        return 2 * cfg["ntaps"] * n_out
     return 0
 
 
@@ -368,6 +400,38 @@ def run_gpu(args):
             f.run(din, n // cfg["size"], dout, stream)
         launches_per_step = 1
         units = n
+    elif op in ("hilbert", "mulconst", "mag2", "tee", "iqbalance"):
+        n = n_in = n_out = units = cfg["n"]
+        fin = 1 if op == "hilbert" else 2                       # floats per input sample
+        fout = 1 if op == "mag2" else 2
+        din = torch.empty(fin * n, dtype=torch.float32, device=f"cuda:{dev}")
+        dout = torch.empty(fout * n, dtype=torch.float32, device=f"cuda:{dev}")
+        R.synth_f32(din, seed, 0, fin * n, dev, stream)
+        L = R.lib()
+        launches_per_step = 1
+        if op == "hilbert":
+            f = R.Hilbert(cfg["ntaps"], device=dev)
+            launches_per_step = 2
+
+            def step():
+                f.run(din, n, dout, stream)
+        elif op == "iqbalance":
+            f = R.IqBalance(R.iq_balance_alpha_from_tau(2_400_000, 0.2), device=dev)
+            launches_per_step = 3
+
+            def step():
+                f.run(din, n, dout, stream)
+        elif op == "mulconst":
+            def step():
+                assert L.rrc_multiply_const_c32_run(dev, din.data_ptr(), n, 0.3, -1.7, dout.data_ptr(), stream) == 0
+        elif op == "mag2":
+            def step():
+                assert L.rrc_complex_to_mag2_run(dev, din.data_ptr(), n, dout.data_ptr(), stream) == 0
+        else:
+            dout2 = torch.empty(2 * n, dtype=torch.float32, device=f"cuda:{dev}")
+
+            def step():
+                assert L.rrc_tee_run(dev, din.data_ptr(), 8 * n, dout.data_ptr(), dout2.data_ptr(), stream) == 0
     elif op == "resample":
         n = cfg["n"]
         f = R.Resampler(4, cfg["interp"], cfg["deci"], device=dev)
@@ -519,7 +583,7 @@ def cpu_baseline(cfg, threads: int, budget_s: float):
 
     from oracle import oracle as O
     op = cfg["op"]
-    taps = taps_for(cfg) if op not in ("resample", "decode", "fft") else None
+    taps = taps_for(cfg) if op not in ("resample", "decode", "fft", "hilbert", "mulconst", "mag2", "tee", "iqbalance") else None
     if op == "fftfilt_real":
         # the reference's FftFilterFloat: widen to Complex, complex FftFilter, keep .re (src/fft_filter.rs:428-470)
         per = 1 << 21
@@ -566,6 +630,19 @@ def cpu_baseline(cfg, threads: int, budget_s: float):
                 O.lib(True).orc_fft_c32(y[o:o + sz].ctypes.data, sz, 0)
             return len(y)
         sample = f"{threads} x 2^20 c32 samples per repetition ({sz}-point frames, the oracle's radix-4 FFT)"
+    elif op == "hilbert":
+        per = 1 << 21
+        xr = O.synth_f32(SEED + 9, 0, per)
+        objs = [O.Hilbert(cfg["ntaps"]) for _ in range(threads)]
+        fn = lambda i: len(objs[i].work(xr))
+        sample = f"{threads} x 2^21 f32 samples per repetition (faithful -O2 build: the scalar Fir::filter loop)"
+    elif op in ("mulconst", "mag2", "tee", "iqbalance"):
+        per = 1 << 23
+        x = O.synth_c32(SEED + 9, 0, per)
+        iq = [O.IqBalance(2.0833e-6) for _ in range(threads)]
+        fn = {"mulconst": lambda i: len(O.multiply_const(x, 0.3 - 1.7j)), "mag2": lambda i: len(O.complex_to_mag2(x)),
+              "tee": lambda i: len(x.copy()) + len(x.copy()), "iqbalance": lambda i: len(iq[i].work(x))}[op]
+        sample = f"{threads} x 2^23 c32 samples per repetition"
     elif op == "decode":
         per = 1 << 24
         raw = O.synth_u8(SEED + 6, 0, 2 * per)

@@ -264,6 +264,57 @@ int rrc_quad_demod_run_batch(int device, const float* in_dev_c32, size_t in_stri
                              float* out_dev, size_t out_stride, size_t nchan, void* stream);
 int rrc_quad_demod_run_host(int device, const float* in_host_c32, size_t n_in, float gain, float* out_host);
 
+/* ------------------------------------------------------------ Hilbert --- */
+/*
+ * SURVEY 8f rank 3a.  Replaces WindowType::make_window (src/window.rs:63-185), fir::hilbert
+ * (src/fir.rs:660-680) and the compute of Hilbert::work (src/hilbert.rs:72-128): with
+ * z = [0]*ntaps ++ x (the block's carried history starts as zeros, :52),
+ *   out[i] = Complex(z[i + ntaps/2], sum_j z[i+j] * taps[ntaps-1-j]),  i < n   (:106-114)
+ * n samples in -> n samples out, chunking independent; the handle carries the ntaps-sample history.
+ */
+#define RRC_WINDOW_HAMMING          0   /* a0 = 25/46 (src/window.rs:36-37) */
+#define RRC_WINDOW_BLACKMAN         1
+#define RRC_WINDOW_BLACKMAN_HARRIS  2
+#define RRC_WINDOW_HAMMING_PARM     3   /* HammingParm(parm) */
+int rrc_make_window(int window_type, float parm, size_t ntaps, float* window_out);           /* host */
+int rrc_hilbert_taps(const float* window, size_t ntaps, float* taps_out);                    /* host */
+typedef struct rrc_hilbert rrc_hilbert_t;
+/* taps in caller order (fir::hilbert output); ntaps must be odd and > 1 (RRC_ERR_INVALID, the
+ * reference asserts, :44-47); at most 8191 taps (RRC_ERR_UNSUPPORTED beyond). */
+int rrc_hilbert_create(int device, const float* taps, size_t ntaps, rrc_hilbert_t** out);
+int rrc_hilbert_destroy(rrc_hilbert_t* h);
+int rrc_hilbert_reset(rrc_hilbert_t* h, void* stream);                                       /* history <- zeros */
+int rrc_hilbert_run(rrc_hilbert_t* h, const float* in_dev, size_t n, float* out_dev_c32, void* stream);
+
+/* ------------------------------------------- sample-wise neighbours --- */
+/*
+ * the `sync` blocks that sit between the filters in real chains.  Each `n` is in
+ * samples; in place is allowed for the maps.  MultiplyConst / AddConst / ComplexToMag2 / Tee are
+ * bit-exact (separately rounded f32 operations, num-complex multiplication order).
+ *   MultiplyConst<T>::process_sync  x * val        src/multiply_const.rs:16-23
+ *   AddConst<T>::process_sync       x + val        src/add_const.rs:36-44
+ *   ComplexToMag2::process_sync     norm_sqr()     src/complex_to_mag2.rs:17-20
+ *   Tee<T>::process_sync            (s, s)         src/tee.rs:20-24
+ */
+int rrc_multiply_const_f32_run(int device, const float* in_dev, size_t n, float val, float* out_dev, void* stream);
+int rrc_multiply_const_c32_run(int device, const float* in_dev_c32, size_t n, float val_re, float val_im, float* out_dev_c32, void* stream);
+int rrc_add_const_f32_run(int device, const float* in_dev, size_t n, float val, float* out_dev, void* stream);
+int rrc_add_const_c32_run(int device, const float* in_dev_c32, size_t n, float val_re, float val_im, float* out_dev_c32, void* stream);
+int rrc_complex_to_mag2_run(int device, const float* in_dev_c32, size_t n, float* out_dev, void* stream);
+int rrc_tee_run(int device, const void* in_dev, size_t nbytes, void* out1_dev, void* out2_dev, void* stream);
+/*
+ * IqBalance (src/iq_balance.rs:12-81): mean[n] = mean[n-1]*(1-alpha) + x[n]*alpha; out = x - mean.
+ * Evaluated as a parallel affine scan (same recurrence, different association than the reference's
+ * sequential f32 loop: tolerance parity, not bit-exact).  The handle carries `mean` across calls.
+ */
+typedef struct rrc_iq_balance rrc_iq_balance_t;
+int rrc_iq_balance_alpha_from_tau(unsigned sample_rate, double tau_seconds, float* alpha);   /* with_tau, :41-57 (host) */
+int rrc_iq_balance_create(int device, float alpha, rrc_iq_balance_t** out);                  /* with_alpha, :62-73; alpha clamped to [0,1] */
+int rrc_iq_balance_destroy(rrc_iq_balance_t* h);
+int rrc_iq_balance_reset(rrc_iq_balance_t* h, void* stream);
+int rrc_iq_balance_mean(rrc_iq_balance_t* h, float* mean_re_im, void* stream);               /* D2H + sync */
+int rrc_iq_balance_run(rrc_iq_balance_t* h, const float* in_dev_c32, size_t n, float* out_dev_c32, void* stream);
+
 /* ------------------------------------------- block-level contract (rrb_) --- */
 /*
  * rustradio's Block / ReadStream / WriteStream / Tag contract (src/block.rs:12-126,
@@ -342,6 +393,24 @@ int rrb_fft_stream_new(rrb_rstream_t* src, size_t size,
 /* RtlSdrDecode::new(src: ReadStream<u8>) -> (Self, ReadStream<Complex>)  (src/rtlsdr_decode.rs:9-16) */
 int rrb_rtlsdr_decode_new(rrb_rstream_t* src,
                           size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+/* Hilbert::new(src: ReadStream<Float>, ntaps, &WindowType) -> (Self, ReadStream<Complex>)  (src/hilbert.rs:35-60) */
+int rrb_hilbert_new(rrb_rstream_t* src, size_t ntaps, int window_type, float window_parm,
+                    size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+/* `sync` blocks (rustradio_macros_code/src/lib.rs:436-514): loop { n = min(in, out space); map; consume n;
+ * produce n with the input tags at unchanged positions } until WaitForStream(src|dst, 1).
+ * cplx selects T = Complex (val = re + i im) or T = Float (val = re). */
+int rrb_multiply_const_new(rrb_rstream_t* src, int cplx, float val_re, float val_im,
+                           size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+int rrb_add_const_new(rrb_rstream_t* src, int cplx, float val_re, float val_im,
+                      size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+int rrb_complex_to_mag2_new(rrb_rstream_t* src,
+                            size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+/* Tee::new(src) -> (Self, ReadStream<T>, ReadStream<T>)  (src/tee.rs:9-18); tags go to both outputs. */
+int rrb_tee_new(rrb_rstream_t* src,
+                size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out1, rrb_rstream_t** out2);
+/* IqBalance::with_alpha(src, alpha) (src/iq_balance.rs:62-73); use rrc_iq_balance_alpha_from_tau for new()/with_tau(). */
+int rrb_iq_balance_new(rrb_rstream_t* src, float alpha,
+                       size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
 int rrb_block_work(rrb_block_t* b, int* kind, size_t* stream_id, size_t* need);
 int rrb_block_eof(rrb_block_t* b, int* eof);
 const char* rrb_block_name(rrb_block_t* b);

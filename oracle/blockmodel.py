@@ -339,3 +339,114 @@ class QuadratureDemod:
             out[:n1] = O.quad_demod(inp[:n1 + 1], self.gain)
             self.src.consume(n1)
             self.out.produce(n1, [])
+
+
+class Hilbert:
+    """Hilbert::new / work (src/hilbert.rs:35-60,72-128): f32 in, Complex out, identity tags, one
+    pass per call then Again."""
+
+    def __init__(self, src: Stream, ntaps: int, window_type: int = O.WINDOW_HAMMING, parm: float = 0.0,
+                 stream_bytes=DEFAULT_STREAM_SIZE):
+        self.eng = O.Hilbert(ntaps, window_type, parm)
+        self.ntaps, self.src = ntaps, src
+        self.out = Stream(np.complex64, stream_bytes)
+
+    def work(self) -> BlockRet:
+        i, tags = self.src.read_buf()
+        if len(i) == 0:
+            return BlockRet(WAIT, self.src, 1)
+        o = self.out.write_buf()
+        if len(o) == 0:
+            return BlockRet(WAIT, self.out, 1)
+        inout = min(len(i), len(o))
+        n = (self.ntaps + inout) - self.ntaps          # len - self.ntaps, :86-87
+        if n == 0:
+            return BlockRet(WAIT, self.src if len(i) < len(o) else self.out, 1)
+        o[:n] = self.eng.work(i[:inout])
+        self.out.produce(n, [t for t in tags if t.pos < n])
+        self.src.consume(n)
+        return BlockRet(AGAIN)
+
+
+class _Sync:
+    """The macro-generated `sync` work loop (rustradio_macros_code/src/lib.rs:458-513): one input,
+    any number of outputs, every output gets the input tags at unchanged positions."""
+
+    out_dtypes: tuple = ()
+
+    def __init__(self, src: Stream, out_dtypes, stream_bytes=DEFAULT_STREAM_SIZE):
+        self.src = src
+        self.outs = [Stream(dt, stream_bytes) for dt in out_dtypes]
+        self.out = self.outs[0]
+
+    def process(self, x):                                # -> tuple of arrays, one per output
+        raise NotImplementedError
+
+    def work(self) -> BlockRet:
+        while True:
+            i, tags = self.src.read_buf()
+            if len(i) == 0:
+                return BlockRet(WAIT, self.src, 1)
+            n = len(i)
+            ws = []
+            for o in self.outs:
+                w = o.write_buf()
+                if len(w) == 0:
+                    return BlockRet(WAIT, o, 1)
+                ws.append(w)
+            n = min([n] + [len(w) for w in ws])
+            ys = self.process(i[:n])
+            for w, y in zip(ws, ys):
+                w[:n] = y
+            keep = [t for t in tags if t.pos < n]
+            self.src.consume(n)
+            for o in self.outs:
+                o.produce(n, keep)
+
+
+class MultiplyConst(_Sync):
+    def __init__(self, src: Stream, val, stream_bytes=DEFAULT_STREAM_SIZE):
+        super().__init__(src, [src.dtype], stream_bytes)
+        self.val = val
+
+    def process(self, x):
+        return (O.multiply_const(x, self.val),)
+
+
+class AddConst(_Sync):
+    def __init__(self, src: Stream, val, stream_bytes=DEFAULT_STREAM_SIZE):
+        super().__init__(src, [src.dtype], stream_bytes)
+        self.val = val
+
+    def process(self, x):
+        return (O.add_const(x, self.val),)
+
+
+class ComplexToMag2(_Sync):
+    def __init__(self, src: Stream, stream_bytes=DEFAULT_STREAM_SIZE):
+        super().__init__(src, [np.float32], stream_bytes)
+
+    def process(self, x):
+        return (O.complex_to_mag2(x),)
+
+
+class Tee(_Sync):
+    """Tee::new(src) -> (Self, out1, out2) (src/tee.rs:9-24)."""
+
+    def __init__(self, src: Stream, stream_bytes=DEFAULT_STREAM_SIZE):
+        super().__init__(src, [src.dtype, src.dtype], stream_bytes)
+        self.out1, self.out2 = self.outs
+
+    def process(self, x):
+        return (x, x)
+
+
+class IqBalance(_Sync):
+    """IqBalance::with_alpha (src/iq_balance.rs:62-80)."""
+
+    def __init__(self, src: Stream, alpha: float, stream_bytes=DEFAULT_STREAM_SIZE):
+        super().__init__(src, [np.complex64], stream_bytes)
+        self.eng = O.IqBalance(alpha)
+
+    def process(self, x):
+        return (self.eng.work(x),)

@@ -65,6 +65,16 @@ def _load(name: str) -> C.CDLL:
         "orc_quad_demod": (None, [vp, i64, f32, vp]),
         "orc_quad_demod_f64": (None, [vp, i64, f64, vp]),
         "orc_rtlsdr_decode": (None, [vp, i64, vp]),
+        "orc_hilbert_taps": (C.c_int, [vp, i64, vp]),
+        "orc_hilbert_work": (None, [vp, vp, i64, vp, i64, vp, vp]),
+        "orc_multiply_const_f32": (None, [vp, i64, f32, vp]),
+        "orc_multiply_const_c32": (None, [vp, i64, f32, f32, vp]),
+        "orc_add_const_f32": (None, [vp, i64, f32, vp]),
+        "orc_add_const_c32": (None, [vp, i64, f32, f32, vp]),
+        "orc_complex_to_mag2": (None, [vp, i64, vp]),
+        "orc_iq_balance_alpha_from_tau": (f32, [C.c_uint32, f64]),
+        "orc_iq_balance": (None, [vp, i64, f32, vp, vp]),
+        "orc_iq_balance_f64": (None, [vp, i64, f32, vp, vp]),
         "orc_signal_source_complex": (None, [f32, f32, f32, C.POINTER(f64), vp, i64]),
         "orc_synth_f32": (None, [C.c_uint64, C.c_uint64, vp, i64]),
     }
@@ -315,6 +325,85 @@ def synth_u8(seed: int, first_index: int, n: int) -> np.ndarray:
     """Deterministic u8 I/Q bytes: the top byte of the same splitmix64 stream synth_f32 uses."""
     f = synth_f32(seed, first_index, n)
     return np.clip(np.floor((f.astype(np.float64) + 1.0) * 128.0), 0, 255).astype(np.uint8)
+
+
+# -------------------------------------------------------------- Hilbert ----
+def hilbert_taps(window) -> np.ndarray:
+    """fir::hilbert (src/fir.rs:660-680)."""
+    w = _f32(window)
+    t = np.empty(len(w), np.float32)
+    if lib().orc_hilbert_taps(_p(w), len(w), _p(t)) != 0:
+        raise ValueError("hilbert() needs a window of at least 2 taps")
+    return t
+
+
+class Hilbert:
+    """Hilbert::work compute with its carried history (src/hilbert.rs:52,86-125)."""
+
+    def __init__(self, ntaps: int, window_type: int = WINDOW_HAMMING, parm: float = 0.0):
+        assert ntaps > 1 and ntaps & 1 == 1, "hilbert filter len must be odd and greater than 1"   # :44-47
+        self.ntaps = ntaps
+        self.taps = hilbert_taps(make_window(window_type, ntaps, parm))
+        self.history = np.zeros(ntaps, np.float32)
+
+    def work(self, x, *, f64: bool = False) -> np.ndarray:
+        x = _f32(x)
+        out = np.empty(len(x), np.complex128 if f64 else np.complex64)
+        if len(x):
+            lib().orc_hilbert_work(_p(self.history), _p(self.taps), self.ntaps, _p(x), len(x),
+                                   None if f64 else _p(out), _p(out) if f64 else None)
+        return out
+
+
+# ------------------------------------------------ sample-wise neighbours ----
+def multiply_const(x, val) -> np.ndarray:
+    if np.iscomplexobj(x):
+        x = _c64(x); out = np.empty_like(x); v = complex(val)
+        lib().orc_multiply_const_c32(_p(x), len(x), v.real, v.imag, _p(out))
+    else:
+        x = _f32(x); out = np.empty_like(x)
+        lib().orc_multiply_const_f32(_p(x), len(x), float(val), _p(out))
+    return out
+
+
+def add_const(x, val) -> np.ndarray:
+    if np.iscomplexobj(x):
+        x = _c64(x); out = np.empty_like(x); v = complex(val)
+        lib().orc_add_const_c32(_p(x), len(x), v.real, v.imag, _p(out))
+    else:
+        x = _f32(x); out = np.empty_like(x)
+        lib().orc_add_const_f32(_p(x), len(x), float(val), _p(out))
+    return out
+
+
+def complex_to_mag2(x) -> np.ndarray:
+    x = _c64(x)
+    out = np.empty(len(x), np.float32)
+    lib().orc_complex_to_mag2(_p(x), len(x), _p(out))
+    return out
+
+
+def iq_balance_alpha_from_tau(sample_rate: int, tau_seconds: float = 0.2) -> float:
+    return float(lib().orc_iq_balance_alpha_from_tau(sample_rate, tau_seconds))
+
+
+class IqBalance:
+    """IqBalance::process_sync with its carried mean (src/iq_balance.rs:62-80)."""
+
+    def __init__(self, alpha: float):
+        self.alpha = float(np.float32(min(max(alpha, 0.0), 1.0)))
+        self.mean = np.zeros(1, np.complex64)
+        self.mean64 = np.zeros(1, np.complex128)
+
+    def work(self, x, *, f64: bool = False) -> np.ndarray:
+        x = _c64(x)
+        if f64:
+            out = np.empty(len(x), np.complex128)
+            lib().orc_iq_balance_f64(_p(x), len(x), self.alpha, _p(self.mean64), _p(out))
+        else:
+            out = np.empty(len(x), np.complex64)
+            lib().orc_iq_balance(_p(x), len(x), self.alpha, _p(self.mean), _p(out))
+        return out
 
 
 # ------------------------------------------------------------ fixtures ----

@@ -519,6 +519,131 @@ void orc_rtlsdr_decode(const uint8_t* in, int64_t n_bytes, c32* out) {
     }
 }
 
+/* -------------------------------------------------------------- Hilbert -- */
+
+/* fir::hilbert, src/fir.rs:660-680 (window from orc_make_window). */
+int orc_hilbert_taps(const float* window, int64_t ntaps, float* taps) {
+    if (ntaps < 2) return -1;                       /* :661-662 asserts */
+    int64_t mid = (ntaps - 1) / 2;
+    float gain = 0.0f;
+    for (int64_t i = 0; i < ntaps; i++) taps[i] = 0.0f;
+    for (int64_t i = 1; i <= mid; i++) {
+        if (i & 1) {
+            float x = 1.0f / (float)i;
+            taps[mid + i] = x * window[mid + i];
+            taps[mid - i] = -x * window[mid - i];
+            gain = taps[mid + i] - gain;
+        } else {
+            taps[mid + i] = 0.0f;
+            taps[mid - i] = 0.0f;
+        }
+    }
+    gain = 1.0f / (2.0f * fabsf(gain));
+    for (int64_t i = 0; i < ntaps; i++) taps[i] = gain * taps[i];
+    return 0;
+}
+
+/*
+ * One Hilbert::work() pass, src/hilbert.rs:86-125: iv = history ++ input[..n];
+ * out[i] = Complex(iv[i + ntaps/2], filter(iv[i..i+ntaps])) for i < n (n = len - ntaps with
+ * history.len() == ntaps); history <- iv[n..len].  `history` (ntaps floats, zeros at start, :52)
+ * is updated in place.  filter = Fir::filter (the scalar fallback of filter_float, src/fir.rs:145;
+ * its AVX / simd branches sum in a different order and are build dependent).
+ * f64_out (optional): the same sums accumulated in f64.
+ */
+void orc_hilbert_work(float* history, const float* taps, int64_t ntaps, const float* in, int64_t n,
+                      c32* out, c64* f64_out) {
+    int64_t len = ntaps + n;
+    float* iv = (float*)malloc(sizeof(float) * (size_t)len);
+    float* rev = (float*)malloc(sizeof(float) * (size_t)ntaps);
+    memcpy(iv, history, sizeof(float) * (size_t)ntaps);
+    memcpy(iv + ntaps, in, sizeof(float) * (size_t)n);
+    for (int64_t j = 0; j < ntaps; j++) rev[j] = taps[ntaps - 1 - j];   /* Fir::new, src/fir.rs:156-162 */
+    for (int64_t i = 0; i < n; i++) {
+        if (out) {
+            float acc = 0.0f;
+            for (int64_t j = 0; j < ntaps; j++) acc = acc + rev[j] * iv[i + j];
+            out[i].re = iv[i + ntaps / 2];
+            out[i].im = acc;
+        }
+        if (f64_out) {
+            double acc64 = 0.0;
+            for (int64_t j = 0; j < ntaps; j++) acc64 += (double)rev[j] * (double)iv[i + j];
+            f64_out[i].re = iv[i + ntaps / 2];
+            f64_out[i].im = acc64;
+        }
+    }
+    memcpy(history, iv + n, sizeof(float) * (size_t)ntaps);
+    free(iv);
+    free(rev);
+}
+
+/* ------------------------------------------------ sample-wise neighbours -- */
+
+/* MultiplyConst::process_sync, src/multiply_const.rs:20-22 (x * val). */
+void orc_multiply_const_f32(const float* x, int64_t n, float val, float* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = x[i] * val;
+}
+void orc_multiply_const_c32(const c32* x, int64_t n, float val_re, float val_im, c32* out) {
+    c32 val = { val_re, val_im };
+    for (int64_t i = 0; i < n; i++) out[i] = c32_mul(x[i], val);
+}
+/* AddConst::process_sync, src/add_const.rs:41-43 (a + val). */
+void orc_add_const_f32(const float* x, int64_t n, float val, float* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = x[i] + val;
+}
+void orc_add_const_c32(const c32* x, int64_t n, float val_re, float val_im, c32* out) {
+    c32 val = { val_re, val_im };
+    for (int64_t i = 0; i < n; i++) out[i] = c32_add(x[i], val);
+}
+/* ComplexToMag2::process_sync, src/complex_to_mag2.rs:17-19: norm_sqr = re*re + im*im. */
+void orc_complex_to_mag2(const c32* x, int64_t n, float* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = x[i].re * x[i].re + x[i].im * x[i].im;
+}
+
+/* IqBalance::with_tau alpha, src/iq_balance.rs:41-57. */
+float orc_iq_balance_alpha_from_tau(uint32_t sample_rate, double tau_seconds) {
+    double fs = (double)(sample_rate > 1 ? sample_rate : 1);
+    double tau = (isfinite(tau_seconds) && tau_seconds > 0.0) ? tau_seconds : 0.5;
+    double a = 1.0 - exp(-1.0 / (tau * fs));
+    if (a < 0.0) a = 0.0;
+    if (a > 1.0) a = 1.0;
+    return (float)a;
+}
+/*
+ * IqBalance::process_sync over n samples, src/iq_balance.rs:75-80:
+ *   mean = mean * one_minus_alpha + x * alpha;  out = x - mean
+ * (Complex * f32 scales both parts; every operation rounded to f32).  alpha is clamped and
+ * one_minus_alpha = 1.0 - alpha as in with_alpha (:62-73).  `mean` is carried in place.
+ */
+void orc_iq_balance(const c32* x, int64_t n, float alpha, c32* mean, c32* out) {
+    if (alpha < 0.0f) alpha = 0.0f;
+    if (alpha > 1.0f) alpha = 1.0f;
+    float oma = 1.0f - alpha;
+    c32 m = *mean;
+    for (int64_t i = 0; i < n; i++) {
+        c32 a = { m.re * oma, m.im * oma }, b = { x[i].re * alpha, x[i].im * alpha };
+        m = c32_add(a, b);
+        out[i].re = x[i].re - m.re;
+        out[i].im = x[i].im - m.im;
+    }
+    *mean = m;
+}
+/* The same recurrence in f64 (from the f32 alpha and 1 - alpha the block stores). */
+void orc_iq_balance_f64(const c32* x, int64_t n, float alpha, c64* mean, c64* out) {
+    if (alpha < 0.0f) alpha = 0.0f;
+    if (alpha > 1.0f) alpha = 1.0f;
+    double a = (double)alpha, oma = (double)(1.0f - alpha);
+    c64 m = *mean;
+    for (int64_t i = 0; i < n; i++) {
+        m.re = m.re * oma + (double)x[i].re * a;
+        m.im = m.im * oma + (double)x[i].im * a;
+        out[i].re = (double)x[i].re - m.re;
+        out[i].im = (double)x[i].im - m.im;
+    }
+    *mean = m;
+}
+
 /* --------------------------------------------- test-fixture restatements -- */
 
 /* SignalSourceComplex iterator, src/signal_source.rs:39-51. `current` carried. */

@@ -107,6 +107,24 @@ _SIGS = {
     "rrc_rtlsdr_decode_run_host": [_i, _vp, _sz, _vp, _P(_sz)],
     "rrc_fir_set_input_u8iq": [_vp, _i],
     "rrc_fftfilt_set_input_u8iq": [_vp, _i],
+    "rrc_make_window": [_i, _f, _sz, _vp],
+    "rrc_hilbert_taps": [_vp, _sz, _vp],
+    "rrc_hilbert_create": [_i, _vp, _sz, _P(_vp)],
+    "rrc_hilbert_destroy": [_vp],
+    "rrc_hilbert_reset": [_vp, _vp],
+    "rrc_hilbert_run": [_vp, _vp, _sz, _vp, _vp],
+    "rrc_multiply_const_f32_run": [_i, _vp, _sz, _f, _vp, _vp],
+    "rrc_multiply_const_c32_run": [_i, _vp, _sz, _f, _f, _vp, _vp],
+    "rrc_add_const_f32_run": [_i, _vp, _sz, _f, _vp, _vp],
+    "rrc_add_const_c32_run": [_i, _vp, _sz, _f, _f, _vp, _vp],
+    "rrc_complex_to_mag2_run": [_i, _vp, _sz, _vp, _vp],
+    "rrc_tee_run": [_i, _vp, _sz, _vp, _vp, _vp],
+    "rrc_iq_balance_alpha_from_tau": [C.c_uint, C.c_double, _P(_f)],
+    "rrc_iq_balance_create": [_i, _f, _P(_vp)],
+    "rrc_iq_balance_destroy": [_vp],
+    "rrc_iq_balance_reset": [_vp, _vp],
+    "rrc_iq_balance_mean": [_vp, _vp, _vp],
+    "rrc_iq_balance_run": [_vp, _vp, _sz, _vp, _vp],
 }
 
 
@@ -566,3 +584,141 @@ def quad_demod_host(x: np.ndarray, gain: float = 1.0, device: int = 0) -> np.nda
     out = np.empty(max(len(x) - 1, 0), np.float32)
     _ck(lib().rrc_quad_demod_run_host(device, x.ctypes.data, len(x), gain, out.ctypes.data))
     return out
+
+
+# -------------------------------------------------------------- Hilbert ---
+WINDOW_HAMMING, WINDOW_BLACKMAN, WINDOW_BLACKMAN_HARRIS, WINDOW_HAMMING_PARM = 0, 1, 2, 3
+
+
+def make_window(window_type: int, ntaps: int, parm: float = 0.0) -> np.ndarray:
+    """WindowType::make_window (src/window.rs:63-86), computed by the library on the host."""
+    w = np.empty(ntaps, np.float32)
+    _ck(lib().rrc_make_window(window_type, parm, ntaps, w.ctypes.data if ntaps else None))
+    return w
+
+
+def hilbert_taps(window: np.ndarray) -> np.ndarray:
+    """fir::hilbert (src/fir.rs:660-680)."""
+    w = np.ascontiguousarray(window, np.float32)
+    t = np.empty(len(w), np.float32)
+    _ck(lib().rrc_hilbert_taps(w.ctypes.data if len(w) else None, len(w), t.ctypes.data if len(w) else None))
+    return t
+
+
+class Hilbert:
+    """Hilbert compute (src/hilbert.rs:86-125): f32 in, Complex out, ntaps of carried history."""
+
+    def __init__(self, ntaps: int, window_type: int = WINDOW_HAMMING, parm: float = 0.0, device: int = 0, taps=None):
+        self.device = device
+        t = np.ascontiguousarray(taps, np.float32) if taps is not None else hilbert_taps(make_window(window_type, ntaps, parm))
+        self.taps, self.ntaps = t, len(t)
+        h = C.c_void_p()
+        _ck(lib().rrc_hilbert_create(device, t.ctypes.data if len(t) else None, len(t), C.byref(h)))
+        self.h = h.value
+
+    def reset(self, stream: int = 0):
+        _ck(lib().rrc_hilbert_reset(self.h, stream))
+
+    def run(self, d_in, n: int, d_out, stream: int = 0):
+        _ck(lib().rrc_hilbert_run(self.h, _ptr(d_in), n, _ptr(d_out), stream))
+
+    def process(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float32)
+        if len(x) == 0:
+            return np.empty(0, np.complex64)
+        din = DeviceBuffer.from_numpy(x, self.device)
+        dout = DeviceBuffer(len(x) * 8, self.device)
+        self.run(din, len(x), dout)
+        return dout.download(np.complex64, len(x))
+
+    def __del__(self):
+        try:
+            lib().rrc_hilbert_destroy(self.h)
+        except Exception:
+            pass
+
+
+# ------------------------------------------------- sample-wise neighbours ---
+def _map(fn, x, in_dt, out_dt, *vals, device: int = 0, offset: int = 0):
+    """Upload, run one map, download.  offset (samples) misaligns both device pointers (ring windows do)."""
+    x = np.ascontiguousarray(x, in_dt)
+    n = len(x)
+    if n == 0:
+        return np.empty(0, out_dt)
+    isz, osz = np.dtype(in_dt).itemsize, np.dtype(out_dt).itemsize
+    din = DeviceBuffer((n + offset) * isz, device)
+    din.upload(x, offset * isz)
+    dout = DeviceBuffer((n + offset) * osz, device)
+    _ck(fn(device, din.ptr + offset * isz, n, *vals, dout.ptr + offset * osz, 0))
+    return dout.download(out_dt, n, offset * osz)
+
+
+def multiply_const(x: np.ndarray, val, device: int = 0, offset: int = 0) -> np.ndarray:
+    if np.iscomplexobj(x):
+        v = complex(val)
+        return _map(lib().rrc_multiply_const_c32_run, x, np.complex64, np.complex64, v.real, v.imag, device=device, offset=offset)
+    return _map(lib().rrc_multiply_const_f32_run, x, np.float32, np.float32, float(val), device=device, offset=offset)
+
+
+def add_const(x: np.ndarray, val, device: int = 0, offset: int = 0) -> np.ndarray:
+    if np.iscomplexobj(x):
+        v = complex(val)
+        return _map(lib().rrc_add_const_c32_run, x, np.complex64, np.complex64, v.real, v.imag, device=device, offset=offset)
+    return _map(lib().rrc_add_const_f32_run, x, np.float32, np.float32, float(val), device=device, offset=offset)
+
+
+def complex_to_mag2(x: np.ndarray, device: int = 0, offset: int = 0) -> np.ndarray:
+    return _map(lib().rrc_complex_to_mag2_run, x, np.complex64, np.float32, device=device, offset=offset)
+
+
+def tee(x: np.ndarray, device: int = 0, offset_bytes: int = 0):
+    x = np.ascontiguousarray(x)
+    nb = x.nbytes
+    din = DeviceBuffer(nb + offset_bytes + 16, device)
+    din.upload(x.view(np.uint8), offset_bytes)
+    o1, o2 = DeviceBuffer(nb + offset_bytes + 16, device), DeviceBuffer(nb + offset_bytes + 16, device)
+    _ck(lib().rrc_tee_run(device, din.ptr + offset_bytes, nb, o1.ptr + offset_bytes, o2.ptr + offset_bytes, 0))
+    return (o1.download(np.uint8, nb, offset_bytes).view(x.dtype), o2.download(np.uint8, nb, offset_bytes).view(x.dtype))
+
+
+def iq_balance_alpha_from_tau(sample_rate: int, tau_seconds: float = 0.2) -> float:
+    a = _f(0)
+    _ck(lib().rrc_iq_balance_alpha_from_tau(sample_rate, tau_seconds, C.byref(a)))
+    return a.value
+
+
+class IqBalance:
+    """IqBalance compute (src/iq_balance.rs:75-80) with the carried mean."""
+
+    def __init__(self, alpha: float, device: int = 0):
+        self.device = device
+        h = C.c_void_p()
+        _ck(lib().rrc_iq_balance_create(device, alpha, C.byref(h)))
+        self.h = h.value
+
+    def reset(self, stream: int = 0):
+        _ck(lib().rrc_iq_balance_reset(self.h, stream))
+
+    @property
+    def mean(self) -> complex:
+        m = np.zeros(2, np.float32)
+        _ck(lib().rrc_iq_balance_mean(self.h, m.ctypes.data, 0))
+        return complex(m[0], m[1])
+
+    def run(self, d_in, n: int, d_out, stream: int = 0):
+        _ck(lib().rrc_iq_balance_run(self.h, _ptr(d_in), n, _ptr(d_out), stream))
+
+    def process(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.complex64)
+        if len(x) == 0:
+            return np.empty(0, np.complex64)
+        din = DeviceBuffer.from_numpy(x, self.device)
+        dout = DeviceBuffer(len(x) * 8, self.device)
+        self.run(din, len(x), dout)
+        return dout.download(np.complex64, len(x))
+
+    def __del__(self):
+        try:
+            lib().rrc_iq_balance_destroy(self.h)
+        except Exception:
+            pass

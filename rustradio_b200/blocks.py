@@ -52,6 +52,12 @@ _SIGS = {
     "rrb_quadrature_demod_new": [_vp, C.c_float, _sz, _i, _i, _P(_vp), _P(_vp)],
     "rrb_rtlsdr_decode_new": [_vp, _sz, _i, _i, _P(_vp), _P(_vp)],
     "rrb_fft_stream_new": [_vp, _sz, _sz, _i, _i, _P(_vp), _P(_vp)],
+    "rrb_hilbert_new": [_vp, _sz, _i, C.c_float, _sz, _i, _i, _P(_vp), _P(_vp)],
+    "rrb_multiply_const_new": [_vp, _i, C.c_float, C.c_float, _sz, _i, _i, _P(_vp), _P(_vp)],
+    "rrb_add_const_new": [_vp, _i, C.c_float, C.c_float, _sz, _i, _i, _P(_vp), _P(_vp)],
+    "rrb_complex_to_mag2_new": [_vp, _sz, _i, _i, _P(_vp), _P(_vp)],
+    "rrb_iq_balance_new": [_vp, C.c_float, _sz, _i, _i, _P(_vp), _P(_vp)],
+    "rrb_tee_new": [_vp, _sz, _i, _i, _P(_vp), _P(_vp), _P(_vp)],
     "rrb_block_work": [_vp, _P(_i), _P(_sz), _P(_sz)],
     "rrb_block_eof": [_vp, _P(_i)],
     "rrb_block_drop": [_vp],
@@ -270,6 +276,44 @@ def FftStream(src: ReadStream, size: int, size_bytes=DEFAULT_STREAM_SIZE, reside
 def RtlSdrDecode(src: ReadStream, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     """RtlSdrDecode::new(src) (src/rtlsdr_decode.rs:9-16): ReadStream<u8> -> ReadStream<Complex>."""
     return _mk(_L().rrb_rtlsdr_decode_new, np.complex64, src._take(), size_bytes, residency, device)
+
+
+def Hilbert(src: ReadStream, ntaps: int, window_type: int = 0, window_parm: float = 0.0, size_bytes=DEFAULT_STREAM_SIZE,
+            residency=DEVICE, device=0):
+    """Hilbert::new(src, ntaps, &window_type) (src/hilbert.rs:35-60): ReadStream<Float> -> ReadStream<Complex>."""
+    return _mk(_L().rrb_hilbert_new, np.complex64, src._take(), ntaps, window_type, window_parm, size_bytes, residency, device)
+
+
+def MultiplyConst(src: ReadStream, val, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
+    """MultiplyConst::new(src, val) (src/multiply_const.rs:5-23)."""
+    cplx = src.dtype == np.complex64
+    v = complex(val)
+    return _mk(_L().rrb_multiply_const_new, src.dtype, src._take(), int(cplx), v.real, v.imag, size_bytes, residency, device)
+
+
+def AddConst(src: ReadStream, val, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
+    """AddConst::new(src, val) (src/add_const.rs:24-44)."""
+    cplx = src.dtype == np.complex64
+    v = complex(val)
+    return _mk(_L().rrb_add_const_new, src.dtype, src._take(), int(cplx), v.real, v.imag, size_bytes, residency, device)
+
+
+def ComplexToMag2(src: ReadStream, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
+    """ComplexToMag2::new(src) (src/complex_to_mag2.rs:7-20)."""
+    return _mk(_L().rrb_complex_to_mag2_new, np.float32, src._take(), size_bytes, residency, device)
+
+
+def IqBalance(src: ReadStream, alpha: float, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
+    """IqBalance::with_alpha(src, alpha) (src/iq_balance.rs:62-73)."""
+    return _mk(_L().rrb_iq_balance_new, np.complex64, src._take(), alpha, size_bytes, residency, device)
+
+
+def Tee(src: ReadStream, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
+    """Tee::new(src) -> (block, out1, out2) (src/tee.rs:9-18)."""
+    b, o1, o2 = _vp(), _vp(), _vp()
+    dt = src.dtype
+    _ck(_L().rrb_tee_new(src._take(), size_bytes, residency, device, C.byref(b), C.byref(o1), C.byref(o2)))
+    return Block(b.value), ReadStream(o1.value, dt), ReadStream(o2.value, dt)
 
 
 def graph_run(blocks):

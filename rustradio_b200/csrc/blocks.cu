@@ -626,6 +626,144 @@ int RtlSdrDecode::work(BlockRet* ret) {       // src/rtlsdr_decode.rs:18-48
     }
 }
 
+// -------------------------------------------------------------------- Hilbert -----
+int Hilbert::create(std::unique_ptr<ReadStream> src, size_t ntaps, int window_type, float window_parm, const StreamOpts& o,
+                    std::unique_ptr<Hilbert>* out) {
+    if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    if (src->buffer().elem() != 4) return fail(RRC_ERR_INVALID, "Hilbert: stream must carry f32");
+    if (!(ntaps > 1 && (ntaps & 1) == 1)) return fail(RRC_ERR_INVALID, "hilbert filter len must be odd and greater than 1 (src/hilbert.rs:44-47)");
+    std::vector<float> win(ntaps), taps(ntaps);
+    RRC_TRY(rrc_make_window(window_type, window_parm, ntaps, win.data()));
+    RRC_TRY(rrc_hilbert_taps(win.data(), ntaps, taps.data()));
+    std::unique_ptr<Hilbert> b(new Hilbert());
+    b->device_ = o.device;
+    RRC_TRY(rrc_hilbert_create(o.device, taps.data(), ntaps, &b->h_));
+    b->src_ = std::move(src);
+    RRC_TRY(make_output(8, o, &b->dst_, &b->out_r_));
+    *out = std::move(b);
+    return RRC_OK;
+}
+Hilbert::~Hilbert() { rrc_hilbert_destroy(h_); }
+
+int Hilbert::work(BlockRet* ret) {            // src/hilbert.rs:72-128 (one pass per call, then Again)
+    const char* in; size_t in_len; std::vector<Tag> tags;
+    src_->buffer().read_window(&in, &in_len, &tags);
+    if (in_len == 0) { *ret = BlockRet::wait(src_.get(), 1); return RRC_OK; }            // :76-78
+    char* outp; size_t cap;
+    dst_->buffer().write_window(&outp, &cap);
+    if (cap == 0) { *ret = BlockRet::wait(dst_.get(), 1); return RRC_OK; }               // :81-83
+    const size_t n = std::min(in_len, cap);   // :85-87: len - ntaps with len = history.len() + inout, history.len() == ntaps
+    const char* din; char* dout;
+    RRC_TRY(stage_input(src_->buffer(), in, n * 4, sin_, device_, &din));
+    RRC_TRY(stage_output(dst_->buffer(), outp, n * 8, sout_, device_, &dout));
+    RRC_TRY(rrc_hilbert_run(h_, (const float*)din, n, (float*)dout, graph_stream(device_)));
+    RRC_TRY(finish_output(dst_->buffer(), outp, n * 8, sout_, device_));
+    if (src_->buffer().residency() == Residency::Host) RRC_CUDA(cudaStreamSynchronize((cudaStream_t)graph_stream(device_)));
+    tags.erase(std::remove_if(tags.begin(), tags.end(), [&](const Tag& t) { return t.pos >= n; }), tags.end());   // :117-120
+    dst_->buffer().produce(n, tags);
+    src_->buffer().consume(n);
+    *ret = BlockRet::again();
+    return RRC_OK;
+}
+
+// -------------------------------------------------------------------- SyncMap -----
+int SyncMap::create(std::unique_ptr<ReadStream> src, Op op, bool cplx, float val_re, float val_im, const StreamOpts& o,
+                    std::unique_ptr<SyncMap>* out) {
+    if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    std::unique_ptr<SyncMap> b(new SyncMap());
+    if (op == Op::ComplexToMag2 || op == Op::IqBalance) cplx = true;
+    b->op_ = op; b->cplx_ = cplx; b->re_ = val_re; b->im_ = val_im; b->device_ = o.device;
+    b->in_elem_ = cplx ? 8 : 4;
+    b->out_elem_ = op == Op::ComplexToMag2 ? 4 : b->in_elem_;
+    if (src->buffer().elem() != b->in_elem_) return fail(RRC_ERR_INVALID, "sync block: stream element size mismatch");
+    if (op == Op::IqBalance) RRC_TRY(rrc_iq_balance_create(o.device, val_re, &b->iq_));
+    b->src_ = std::move(src);
+    RRC_TRY(make_output(b->out_elem_, o, &b->dst_, &b->out_r_));
+    *out = std::move(b);
+    return RRC_OK;
+}
+SyncMap::~SyncMap() { rrc_iq_balance_destroy(iq_); }
+const char* SyncMap::block_name() const {
+    switch (op_) {
+    case Op::MultiplyConst: return "MultiplyConst";
+    case Op::AddConst: return "AddConst";
+    case Op::ComplexToMag2: return "ComplexToMag2";
+    default: return "IqBalance";
+    }
+}
+
+int SyncMap::work(BlockRet* ret) {            // rustradio_macros_code/src/lib.rs:458-513
+    for (;;) {
+        const char* in; size_t in_len; std::vector<Tag> tags;
+        src_->buffer().read_window(&in, &in_len, &tags);
+        if (in_len == 0) { *ret = BlockRet::wait(src_.get(), 1); return RRC_OK; }
+        char* outp; size_t cap;
+        dst_->buffer().write_window(&outp, &cap);
+        if (cap == 0) { *ret = BlockRet::wait(dst_.get(), 1); return RRC_OK; }
+        const size_t n = std::min(in_len, cap);
+        const char* din; char* dout;
+        void* st = graph_stream(device_);
+        RRC_TRY(stage_input(src_->buffer(), in, n * in_elem_, sin_, device_, &din));
+        RRC_TRY(stage_output(dst_->buffer(), outp, n * out_elem_, sout_, device_, &dout));
+        switch (op_) {
+        case Op::MultiplyConst:
+            RRC_TRY(cplx_ ? rrc_multiply_const_c32_run(device_, (const float*)din, n, re_, im_, (float*)dout, st)
+                          : rrc_multiply_const_f32_run(device_, (const float*)din, n, re_, (float*)dout, st));
+            break;
+        case Op::AddConst:
+            RRC_TRY(cplx_ ? rrc_add_const_c32_run(device_, (const float*)din, n, re_, im_, (float*)dout, st)
+                          : rrc_add_const_f32_run(device_, (const float*)din, n, re_, (float*)dout, st));
+            break;
+        case Op::ComplexToMag2: RRC_TRY(rrc_complex_to_mag2_run(device_, (const float*)din, n, (float*)dout, st)); break;
+        case Op::IqBalance: RRC_TRY(rrc_iq_balance_run(iq_, (const float*)din, n, (float*)dout, st)); break;
+        }
+        RRC_TRY(finish_output(dst_->buffer(), outp, n * out_elem_, sout_, device_));
+        if (src_->buffer().residency() == Residency::Host) RRC_CUDA(cudaStreamSynchronize((cudaStream_t)st));
+        tags.erase(std::remove_if(tags.begin(), tags.end(), [&](const Tag& t) { return t.pos >= n; }), tags.end());
+        src_->buffer().consume(n);
+        dst_->buffer().produce(n, tags);
+    }
+}
+
+// ------------------------------------------------------------------------ Tee -----
+int Tee::create(std::unique_ptr<ReadStream> src, const StreamOpts& o, std::unique_ptr<Tee>* out) {
+    if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    std::unique_ptr<Tee> b(new Tee());
+    b->device_ = o.device; b->elem_ = src->buffer().elem();
+    b->src_ = std::move(src);
+    RRC_TRY(make_output(b->elem_, o, &b->dst1_, &b->out_r_));
+    RRC_TRY(make_output(b->elem_, o, &b->dst2_, &b->out2_r_));
+    *out = std::move(b);
+    return RRC_OK;
+}
+
+int Tee::work(BlockRet* ret) {                // src/tee.rs:9-24 through the sync loop
+    for (;;) {
+        const char* in; size_t in_len; std::vector<Tag> tags;
+        src_->buffer().read_window(&in, &in_len, &tags);
+        if (in_len == 0) { *ret = BlockRet::wait(src_.get(), 1); return RRC_OK; }
+        char *o1, *o2; size_t c1, c2;
+        dst1_->buffer().write_window(&o1, &c1);
+        if (c1 == 0) { *ret = BlockRet::wait(dst1_.get(), 1); return RRC_OK; }
+        dst2_->buffer().write_window(&o2, &c2);
+        if (c2 == 0) { *ret = BlockRet::wait(dst2_.get(), 1); return RRC_OK; }
+        const size_t n = std::min(in_len, std::min(c1, c2));
+        const char* din; char *d1, *d2;
+        void* st = graph_stream(device_);
+        RRC_TRY(stage_input(src_->buffer(), in, n * elem_, sin_, device_, &din));
+        RRC_TRY(stage_output(dst1_->buffer(), o1, n * elem_, sout1_, device_, &d1));
+        RRC_TRY(stage_output(dst2_->buffer(), o2, n * elem_, sout2_, device_, &d2));
+        RRC_TRY(rrc_tee_run(device_, din, n * elem_, d1, d2, st));
+        RRC_TRY(finish_output(dst1_->buffer(), o1, n * elem_, sout1_, device_));
+        RRC_TRY(finish_output(dst2_->buffer(), o2, n * elem_, sout2_, device_));
+        if (src_->buffer().residency() == Residency::Host) RRC_CUDA(cudaStreamSynchronize((cudaStream_t)st));
+        tags.erase(std::remove_if(tags.begin(), tags.end(), [&](const Tag& t) { return t.pos >= n; }), tags.end());
+        src_->buffer().consume(n);
+        dst1_->buffer().produce(n, tags);
+        dst2_->buffer().produce(n, tags);
+    }
+}
+
 // --------------------------------------------------------------- VectorSource -----
 int VectorSource::create(const void* data, size_t n, size_t elem_size, uint64_t repeat, const StreamOpts& o,
                          std::unique_ptr<VectorSource>* out) {

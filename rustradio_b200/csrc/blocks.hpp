@@ -16,6 +16,9 @@
 //   FftFilter / FftFilterFloat          src/fft_filter.rs:210-491
 //   RationalResampler<T>                src/rational_resampler.rs:94-213
 //   QuadratureDemod                     src/quadrature_demod.rs:32-114
+//   Hilbert                             src/hilbert.rs:22-129
+//   MultiplyConst / AddConst / ComplexToMag2 / Tee / IqBalance (sync blocks)
+//                                       rustradio_macros_code/src/lib.rs:436-514
 //   VectorSource<T> (test fixture)      src/vector_source.rs:60-144
 //   Graph::run                          src/graph.rs:99-173
 //
@@ -184,8 +187,9 @@ public:
     virtual bool eof() = 0;
     // Output stream handed back by the constructor in the reference (`new() -> (Self, ReadStream)`).
     std::unique_ptr<ReadStream> take_output() { return std::move(out_r_); }
+    std::unique_ptr<ReadStream> take_output2() { return std::move(out2_r_); }   // second output (Tee)
 protected:
-    std::unique_ptr<ReadStream> out_r_;
+    std::unique_ptr<ReadStream> out_r_, out2_r_;
 };
 
 // Scratch device memory for blocks whose stream lives in host memory.
@@ -327,6 +331,66 @@ private:
     std::unique_ptr<WriteStream> dst_;
     int device_ = 0;
     Scratch sin_, sout_;
+};
+
+// Hilbert (src/hilbert.rs:22-129): ReadStream<Float> -> WriteStream<Complex>, identity tags.
+class Hilbert : public Block {
+public:
+    // Hilbert::new(src, ntaps, &window_type): taps = fir::hilbert(window_type.make_window(ntaps)).
+    static int create(std::unique_ptr<ReadStream> src, size_t ntaps, int window_type, float window_parm, const StreamOpts& o,
+                      std::unique_ptr<Hilbert>* out);
+    ~Hilbert() override;
+    int work(BlockRet* ret) override;
+    const char* block_name() const override { return "Hilbert"; }
+    bool eof() override { return src_->eof(); }
+private:
+    Hilbert() = default;
+    std::unique_ptr<ReadStream> src_;
+    std::unique_ptr<WriteStream> dst_;
+    rrc_hilbert_t* h_ = nullptr;
+    int device_ = 0;
+    Scratch sin_, sout_;
+};
+
+// The macro-generated `sync` blocks (rustradio_macros_code/src/lib.rs:436-514) next to the filters:
+// MultiplyConst<T>, AddConst<T>, ComplexToMag2, IqBalance — one input, one output, tags passed through.
+class SyncMap : public Block {
+public:
+    enum class Op : int { MultiplyConst = 0, AddConst = 1, ComplexToMag2 = 2, IqBalance = 3 };
+    // cplx: T = Complex (val = re + i*im) or Float (val = re); IqBalance: val_re = alpha.
+    static int create(std::unique_ptr<ReadStream> src, Op op, bool cplx, float val_re, float val_im, const StreamOpts& o,
+                      std::unique_ptr<SyncMap>* out);
+    ~SyncMap() override;
+    int work(BlockRet* ret) override;
+    const char* block_name() const override;
+    bool eof() override { return src_->eof(); }
+private:
+    SyncMap() = default;
+    std::unique_ptr<ReadStream> src_;
+    std::unique_ptr<WriteStream> dst_;
+    Op op_ = Op::MultiplyConst;
+    bool cplx_ = false;
+    float re_ = 0.f, im_ = 0.f;
+    size_t in_elem_ = 4, out_elem_ = 4;
+    rrc_iq_balance_t* iq_ = nullptr;
+    int device_ = 0;
+    Scratch sin_, sout_;
+};
+
+// Tee<T> (src/tee.rs:9-24): every sample and every tag goes to both outputs.
+class Tee : public Block {
+public:
+    static int create(std::unique_ptr<ReadStream> src, const StreamOpts& o, std::unique_ptr<Tee>* out);
+    int work(BlockRet* ret) override;
+    const char* block_name() const override { return "Tee"; }
+    bool eof() override { return src_->eof(); }
+private:
+    Tee() = default;
+    std::unique_ptr<ReadStream> src_;
+    std::unique_ptr<WriteStream> dst1_, dst2_;
+    size_t elem_ = 4;
+    int device_ = 0;
+    Scratch sin_, sout1_, sout2_;
 };
 
 // Test fixture: VectorSource<T> with its tags (src/vector_source.rs:97-144).

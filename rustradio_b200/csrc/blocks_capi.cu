@@ -212,6 +212,47 @@ int rrb_rtlsdr_decode_new(rrb_rstream_t* src, size_t bytes, int res, int device,
     return finish(std::move(b), blk, out);
 }
 
+int rrb_hilbert_new(rrb_rstream_t* src, size_t ntaps, int window_type, float window_parm, size_t bytes, int res, int device,
+                    rrb_block_t** blk, rrb_rstream_t** out) {
+    if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
+    // validate before taking ownership of `src` (the reference panics in new(), src/hilbert.rs:44-47)
+    if (!(ntaps > 1 && (ntaps & 1) == 1)) return fail(RRC_ERR_INVALID, "hilbert filter len must be odd and greater than 1");
+    if (window_type < RRC_WINDOW_HAMMING || window_type > RRC_WINDOW_HAMMING_PARM) return fail(RRC_ERR_INVALID, "unknown window type %d", window_type);
+    std::unique_ptr<rr::Hilbert> b;
+    RRC_TRY(rr::Hilbert::create(take(src), ntaps, window_type, window_parm, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out);
+}
+static int sync_new(rrb_rstream_t* src, rr::SyncMap::Op op, int cplx, float re, float im, size_t bytes, int res, int device,
+                    rrb_block_t** blk, rrb_rstream_t** out) {
+    if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
+    std::unique_ptr<rr::SyncMap> b;
+    RRC_TRY(rr::SyncMap::create(take(src), op, cplx != 0, re, im, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out);
+}
+int rrb_multiply_const_new(rrb_rstream_t* src, int cplx, float val_re, float val_im, size_t bytes, int res, int device,
+                           rrb_block_t** blk, rrb_rstream_t** out) {
+    return sync_new(src, rr::SyncMap::Op::MultiplyConst, cplx, val_re, val_im, bytes, res, device, blk, out);
+}
+int rrb_add_const_new(rrb_rstream_t* src, int cplx, float val_re, float val_im, size_t bytes, int res, int device,
+                      rrb_block_t** blk, rrb_rstream_t** out) {
+    return sync_new(src, rr::SyncMap::Op::AddConst, cplx, val_re, val_im, bytes, res, device, blk, out);
+}
+int rrb_complex_to_mag2_new(rrb_rstream_t* src, size_t bytes, int res, int device, rrb_block_t** blk, rrb_rstream_t** out) {
+    return sync_new(src, rr::SyncMap::Op::ComplexToMag2, 1, 0.f, 0.f, bytes, res, device, blk, out);
+}
+int rrb_iq_balance_new(rrb_rstream_t* src, float alpha, size_t bytes, int res, int device, rrb_block_t** blk, rrb_rstream_t** out) {
+    return sync_new(src, rr::SyncMap::Op::IqBalance, 1, alpha, 0.f, bytes, res, device, blk, out);
+}
+int rrb_tee_new(rrb_rstream_t* src, size_t bytes, int res, int device, rrb_block_t** blk, rrb_rstream_t** out1, rrb_rstream_t** out2) {
+    if (!src || !blk || !out1 || !out2) return fail(RRC_ERR_INVALID, "NULL argument");
+    std::unique_ptr<rr::Tee> b;
+    RRC_TRY(rr::Tee::create(take(src), opts(bytes, res, device), &b));
+    auto* r2 = new rrb_rstream();
+    r2->s = b->take_output2();
+    *out2 = r2;
+    return finish(std::move(b), blk, out1);
+}
+
 int rrb_block_work(rrb_block_t* b, int* kind, size_t* stream_id, size_t* need) {
     if (!b || !b->b || !kind) return fail(RRC_ERR_INVALID, "NULL argument");
     rr::BlockRet r;
