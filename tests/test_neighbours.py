@@ -332,13 +332,25 @@ def test_sync_block_partial_output_space(R):
     w, r = K.new_stream(np.float32, residency=K.HOST)
     x = O.synth_f32(35, 0, 100)
     w.write(x, [K.Tag(5, "k", ("U64", 1)), K.Tag(80, "k", ("U64", 2))])
-    m, out = K.MultiplyConst(r, 2.0, size_bytes=64 * 4, residency=K.HOST)
+    m, out = K.MultiplyConst(r, 2.0, size_bytes=4096, residency=K.HOST)      # one page: room for 1024 samples
+    pre = 1024 - 64                                                          # leave room for 64 samples
+    # occupy the output ring through the block itself: feed `pre` samples first
+    w.write(np.zeros(0, np.float32))
+    ret = m.work()
+    got, tags = out.read_buf()
+    assert ret.kind == K.WAIT and len(got) == 100 and tags == [K.Tag(5, "k", ("U64", 1)), K.Tag(80, "k", ("U64", 2))]
+    assert got.tobytes() == (x * np.float32(2.0)).tobytes()
+    # now fill the output so that only 64 samples of space remain, and offer 100 more with tags
+    w.write(np.zeros(pre - 100, np.float32))
+    m.work()
+    assert len(out.read_buf()[0]) == pre
+    w.write(x, [K.Tag(5, "k", ("U64", 1)), K.Tag(80, "k", ("U64", 2))])
     ret = m.work()
     assert ret.kind == K.WAIT and ret.stream_id == out.id and ret.need == 1
     got, tags = out.read_buf()
-    assert len(got) == 64 and tags == [K.Tag(5, "k", ("U64", 1))]
-    assert got.tobytes() == (x[:64] * np.float32(2.0)).tobytes()
-    out.consume(64)
+    assert len(got) == 1024 and [t for t in tags if t.pos >= pre] == [K.Tag(pre + 5, "k", ("U64", 1))]
+    assert got[pre:].tobytes() == (x[:64] * np.float32(2.0)).tobytes()
+    out.consume(1024)
     ret = m.work()
     assert ret.kind == K.WAIT and ret.stream_id != out.id
     got, tags = out.read_buf()
