@@ -117,6 +117,85 @@ fftfilt_st_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2*
     }
 }
 
+// TMA-staged variant (variant 36; fftfilt_core.cuh "linear staging"): the next block's input is
+// copied into the exchange buffer by cp.async.bulk (SASS UBLKCP) while phase A' of the current block
+// computes and stores; completion is tracked by one mbarrier (one phase per block).
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}" ::"r"(mbar), "r"(parity) : "memory");
+}
+
+template <bool DECIM, bool ACCUM>
+__global__ void __launch_bounds__(fftk::NT, 1)
+fftfilt_tma_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __restrict__ tw1g,
+                   const float2* __restrict__ tw2g, long long nblocks, int tune) {
+    extern __shared__ __align__(16) float2 sm[];
+    float2* s_tw2 = sm + fftk::SMEM_ELEMS;
+    float2* s_tw1 = s_tw2 + 512;
+    float2* s_hres = s_tw1 + 512;
+    const int tid = threadIdx.x;
+    s_tw2[tid] = tw2g[tid];
+    s_tw1[tid] = tw1g[tid];
+    fftk::load_hres(tid, Hp, s_hres);
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(s_hres + fftk::HRES_ELEMS);
+    const unsigned sm_a = (unsigned)__cvta_generic_to_shared(sm);
+    const int pf = tune & 15;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // Every thread calls stage() (the test is CTA uniform); the caller guarantees that nobody still
+    // reads the exchange buffer.
+    auto stage = [&](long long nb) {
+        if (fftk::stage_linear_bulk_ok(nb, io)) {
+            if (tid == 0) {
+                const float2* src = io.in + fftk::stage_linear_seg0(nb, io);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic accesses to the buffer before the async-proxy writes
+                asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(fftk::N * 8) : "memory");
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c)
+                    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(sm_a + c * 16384), "l"(src + c * 2048), "r"(16384), "r"(mbar) : "memory");
+            }
+        } else {
+            fftk::stage_linear_fallback(tid, nb, io, sm);
+            if (tid == 0) asm volatile("mbarrier.arrive.shared.b64 _, [%0];" ::"r"(mbar) : "memory");
+        }
+    };
+    if (tune >> 8) {      // start stagger: SMs that start together stay in lock-step and collide on HBM
+        const long long t0 = clock64(), wait = (long long)(tune >> 8) * 1024 * (blockIdx.x & 7);
+        while (clock64() - t0 < wait) { }
+    }
+    if (blockIdx.x < nblocks) stage(blockIdx.x);
+    unsigned parity = 0;
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const long long nb = blk + gridDim.x;
+        float2 v[32];
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        fftk::phase_a_linear_load(tid, sm, v);
+        fftk::phase_a_linear_compute(tid, s_tw1, v);
+        __syncthreads();                                      // every thread has read its linear words
+        fftk::phase_a_linear_store(tid, sm, v);
+        __syncthreads();
+        if (pf) prefetch_segment(io, nb, nblocks, tid);       // next block -> L2, so the bulk copy below is an L2 hit
+        fftk::phase_mid<false>(tid, s_tw2, Hp, s_hres, sm);
+        __syncthreads();
+        fftk::phase_ai<DECIM, ACCUM>(tid, blk, io, s_tw1, sm, fftk::NoTurn(), [&]() {
+            __syncthreads();                                  // every thread has read the buffer
+            if (nb < nblocks) stage(nb);
+        });
+    }
+}
+
 // Ping-pong variant of fftfilt_kernel (PingPong policy: fftfilt_core.cuh).
 template <bool DECIM, bool ACCUM>
 __global__ void __launch_bounds__(fftk::NT, 1)
@@ -253,7 +332,7 @@ int launch_part(rrc_fftfilt* h, const BlockIO& io, const float2* Hp, cudaStream_
     long long nblocks = (io.n_in + io.V - 1) / io.V;
     if (io.real) nblocks = (nblocks + 1) / 2;                   // two real blocks per complex transform
     const int grid = (int)std::min<long long>(nblocks, sm_count(h->device));
-    auto kern = io.real ? fftfilt_kernel<DECIM, ACCUM, false> : h->variant == 33 ? fftfilt_pp_kernel<DECIM, ACCUM> : h->variant == 34 ? fftfilt_st_kernel<DECIM, ACCUM> : h->variant == 35 ? fftfilt_kernel<DECIM, ACCUM, true> : fftfilt_kernel<DECIM, ACCUM, false>;
+    auto kern = io.real ? fftfilt_kernel<DECIM, ACCUM, false> : h->variant == 33 ? fftfilt_pp_kernel<DECIM, ACCUM> : h->variant == 34 ? fftfilt_st_kernel<DECIM, ACCUM> : h->variant == 35 ? fftfilt_kernel<DECIM, ACCUM, true> : (h->variant == 36 && !io.in_u8) ? fftfilt_tma_kernel<DECIM, ACCUM> : fftfilt_kernel<DECIM, ACCUM, false>;
     RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_SMEM));
     static const int tune = [] { const char* e = getenv("RRC_FFTFILT_TUNE"); return e ? (int)strtol(e, nullptr, 0) : 1; }();
     kern<<<grid, fftk::NT, FFTFILT_SMEM, st>>>(io, Hp, h->tw1, h->tw2, nblocks, tune);
@@ -368,7 +447,7 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
         if (!h->tw1_16 && ((e = up(&h->tw1_16, t1)) != cudaSuccess || (e = up(&h->tw2_16, t2)) != cudaSuccess || (e = up(&h->tw3_16, t3)) != cudaSuccess))
             return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
     }
-    if (const char* v = getenv("RRC_FFTFILT_VARIANT")) h->variant = atoi(v) == 16 ? 16 : atoi(v) == 33 ? 33 : atoi(v) == 34 ? 34 : atoi(v) == 35 ? 35 : 32;
+    if (const char* v = getenv("RRC_FFTFILT_VARIANT")) h->variant = atoi(v) == 16 ? 16 : atoi(v) == 33 ? 33 : atoi(v) == 34 ? 34 : atoi(v) == 35 ? 35 : atoi(v) == 36 ? 36 : 32;
     h->Hp = h->part_Hp[0];
     if ((e = up(&h->tw1, tw1)) != cudaSuccess || (e = up(&h->tw2, tw2)) != cudaSuccess)
         return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));

@@ -252,6 +252,54 @@ RRC_HD void phase_a_staged(int tid, const float2* tw1, float2* sm, Turn turn = T
     for (int k1 = 0; k1 < 32; ++k1) s[k1 * PLANE_PITCH] = v[k1];
 }
 
+// ---- linear staging (fftfilt_tma_kernel) --------------------------------------------------------
+// The next block's 16384 input samples land in the exchange buffer in NATURAL order, sm[n] = x[seg0+n],
+// n < N — the layout one cp.async.bulk (TMA) stream can produce: 128 KiB copied by the copy engine
+// with no LSU instructions, issued by one thread right after phase A' of the previous block has read
+// the buffer, so the HBM/L2 latency AND the per-SM load bandwidth (22-26 B/clk/SM, 5-6 K cycles for
+// 128 KiB) are hidden behind A' instead of being the first 7 K cycles of phase A.  Phase A then reads
+// sm[tid + 512*n1] (conflict free), transforms, and — after a CTA barrier, because the padded layout
+// the rest of the block uses overlaps other threads' linear words — writes phys(k1, tid>>4, tid&15).
+// stage_linear_bulk_ok(): CTA-uniform test that block `blk` is an interior block whose segment is a
+// 16-byte aligned run of c32 samples; other blocks (history at the start, zero fill at the end, odd
+// segment start) are staged by stage_linear_fallback: every thread stores the 32 elements it will
+// read back itself.
+RRC_HD long long stage_linear_seg0(long long blk, const BlockIO& io) { return blk * (long long)io.V - io.T1 - io.shift; }
+RRC_HD bool stage_linear_bulk_ok(long long blk, const BlockIO& io) {
+    const long long seg0 = stage_linear_seg0(blk, io);
+    return seg0 >= 0 && seg0 + N <= io.n_in && !io.in_u8 && !io.real &&
+           ((reinterpret_cast<unsigned long long>(io.in) + (unsigned long long)seg0 * 8ull) & 15ull) == 0;
+}
+RRC_HD void stage_linear_fallback(int tid, long long blk, const BlockIO& io, float2* sm) {
+    const long long g0 = stage_linear_seg0(blk, io) + tid;
+#pragma unroll 4
+    for (int n1 = 0; n1 < 32; ++n1) {
+        const long long g = g0 + 512 * n1;
+        float2 x = make_float2(0.f, 0.f);
+        if (g < 0) { if (g + io.T1_total >= 0) x = io.hist[g + io.T1_total]; }
+        else if (g < io.n_in) x = ld_iq(io.in, g, io.in_u8);
+        sm[tid + 512 * n1] = x;
+    }
+}
+// Phase A on linearly staged input, in two halves around the CTA barrier.
+RRC_HD void phase_a_linear_load(int tid, const float2* sm, float2 (&v)[32]) {
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) v[bitrev(n1, 5)] = sm[tid + 512 * n1];
+}
+RRC_HD void phase_a_linear_compute(int tid, const float2* tw1, float2 (&v)[32]) {
+    const float2 w1 = tw1[tid];
+    dit<32, +1>(v);
+    float2 p[32];
+    powers32(w1, p);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) v[k1] = cmul(v[k1], p[k1]);
+}
+RRC_HD void phase_a_linear_store(int tid, float2* sm, const float2 (&v)[32]) {
+    float2* s = sm + (tid >> 4) * ROW_PITCH + (tid & 15);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) s[k1 * PLANE_PITCH] = v[k1];
+}
+
 // Phase MID: B, C, B' on one k1 plane per half-warp.  tw2[k2*16 + n3] = W_512^{n3*k2}.
 // Hp[(k1*32 + k2)*16 + k3] = H[k1 + 32*k2 + 1024*k3] / N.
 // TW = false: the W_512^{n3*k2} twiddle is NOT applied here but in phase C (TWC = true there), from

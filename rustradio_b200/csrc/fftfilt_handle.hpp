@@ -32,7 +32,9 @@ struct rrc_fftfilt {
     float2* tw3_16 = nullptr;
     int real = 0;                     // real stream + real taps (rrc_fftfilt_f32_create): f32 in / out / history
     int in_u8 = 0;                    // 1: run() inputs are u8 I/Q pairs (rrc_fftfilt_set_input_u8iq)
-    int variant = 32;                 // points per thread: 32 (512 threads) or 16 (1024 threads)
+    // kernel variant (RRC_FFTFILT_VARIANT): 36 = 512 threads x 32 points with TMA-staged input (default),
+    // 32 = the same with LDG input + L2 prefetch, 16 = 1024 threads x 16 points, 33/34/35 = experiments
+    int variant = 36;
     float2* tw1 = nullptr;
     float2* tw2 = nullptr;
     float2* hist[2] = {nullptr, nullptr};

@@ -42,10 +42,16 @@ extern "C" int emul_fftfilt(const float* taps, long long ntaps, const float* in,
             if (mode == 2) {
                 for (int t = 0; t < NT; ++t) stage_input(t, blk, io, sm.data());
                 for (int t = 0; t < NT; ++t) phase_a_staged(t, tw1.data(), sm.data());
+            } else if (mode == 3) {                            // linear (TMA) staging, fftfilt_tma_kernel
+                if (stage_linear_bulk_ok(blk, io)) memcpy(sm.data(), io.in + stage_linear_seg0(blk, io), sizeof(float2) * N);   // cp.async.bulk
+                else for (int t = 0; t < NT; ++t) stage_linear_fallback(t, blk, io, sm.data());
+                std::vector<float2> regs((size_t)NT * 32);
+                for (int t = 0; t < NT; ++t) { float2 v[32]; phase_a_linear_load(t, sm.data(), v); phase_a_linear_compute(t, tw1.data(), v); memcpy(&regs[(size_t)t * 32], v, sizeof v); }
+                for (int t = 0; t < NT; ++t) { float2 v[32]; memcpy(v, &regs[(size_t)t * 32], sizeof v); phase_a_linear_store(t, sm.data(), v); }
             } else {
                 for (int t = 0; t < NT; ++t) phase_a(t, blk, io, tw1.data(), sm.data());
             }
-            if (mode == 0) {
+            if (mode == 0 || mode == 3) {
                 for (int t = 0; t < NT; ++t) phase_mid_b(t, tw2.data(), sm.data());
                 for (int t = 0; t < NT; ++t) phase_mid_c(t, Hp.data(), hres.data(), sm.data());
                 for (int t = 0; t < NT; ++t) phase_mid_bi(t, tw2.data(), sm.data());

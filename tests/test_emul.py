@@ -52,8 +52,8 @@ def test_emulated_kernel_matches_f64_convolution(emul, ntaps, n, variant):
     assert O.rel_rms(emul(taps, x, variant=variant), O.conv_full_f64_fft(x, taps, n)) <= 1e-5
 
 
-@pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("ntaps,n", [(1, 3000), (193, 8000), (4097, 40_000), (64, 16384 * 2 + 5), (16385, 40_000)])
+@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("ntaps,n", [(1, 3000), (193, 8000), (4097, 40_000), (64, 16384 * 2 + 5), (16385, 40_000), (4098, 70_000)])
 def test_emulated_kernel_twiddles_in_phase_c_and_staged_input(emul, monkeypatch, ntaps, n, mode):
     """fftfilt_core.cuh TWC path (W_512 twiddles from powers inside phase C) and stage_input /
     phase_a_staged: same index math and values as the table-twiddle kernel."""
