@@ -1,8 +1,7 @@
 mkdir -p gpurun_out
-for v in 32 36 32 36; do
-RRC_FFTFILT_VARIANT=$v timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu --e2e-steps 8 > gpurun_out/b.json 2> gpurun_out/b.err; tail -2 gpurun_out/b.err
+( timeout 600 python -m pytest tests/test_neighbours.py -m gpu -x -q -k hilbert ) > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python bench.py --config h1 --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_h1.json 2> gpurun_out/bench_h1.err; tail -2 gpurun_out/bench_h1.err
 python - <<PY
 import json
-d=json.loads(open('gpurun_out/b.json').read().strip().splitlines()[-1]); print('variant $v', round(d['value']), d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'])
+d=json.loads(open('gpurun_out/bench_h1.json').read().strip().splitlines()[-1]); print('h1', round(d['value']), d['ms_per_step'], d['roofline']['frac'])
 PY
-done

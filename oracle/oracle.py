@@ -340,10 +340,12 @@ def hilbert_taps(window) -> np.ndarray:
 class Hilbert:
     """Hilbert::work compute with its carried history (src/hilbert.rs:52,86-125)."""
 
-    def __init__(self, ntaps: int, window_type: int = WINDOW_HAMMING, parm: float = 0.0):
+    def __init__(self, ntaps: int, window_type: int = WINDOW_HAMMING, parm: float = 0.0, taps=None):
         assert ntaps > 1 and ntaps & 1 == 1, "hilbert filter len must be odd and greater than 1"   # :44-47
         self.ntaps = ntaps
-        self.taps = hilbert_taps(make_window(window_type, ntaps, parm))
+        # taps=: test hook for arbitrary (non half-band) taps; the block always uses fir::hilbert
+        self.taps = hilbert_taps(make_window(window_type, ntaps, parm)) if taps is None else _f32(taps)
+        assert len(self.taps) == ntaps
         self.history = np.zeros(ntaps, np.float32)
 
     def work(self, x, *, f64: bool = False) -> np.ndarray:

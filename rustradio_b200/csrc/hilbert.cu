@@ -14,10 +14,17 @@
 // span of its 1024 outputs in shared memory (one pad word per 8 so the thread-strided window reads
 // are conflict free), every thread slides an 8-wide register window over 8-tap chunks (64 FMA per
 // 8 window loads + 2 broadcast tap loads) and writes its 8 (re, im) pairs with four 128-bit stores.
-// Bytes 4 + 8 per sample; FMA T per sample (every other Hilbert tap is zero — a polyphase-by-2 form
-// would halve that; not done).
+// Bytes 4 + 8 per sample.
+//
+// Half-band structure: fir::hilbert only sets taps at ODD distances from the centre (src/fir.rs:667-676),
+// so h'[j] == 0 unless j = par (mod 2), par = (T/2 + 1) & 1.  hilbert_half_kernel exploits that when it
+// holds exactly for the given taps: out[i] = sum_m g[m] * z[i + par + 2m], g[m] = h'[par + 2m] — for the
+// outputs of one parity a NON-decimated FIR over every second sample.  A thread owns 16 consecutive
+// outputs as two interleaved sets of 8 (even / odd i) that share the tap registers: half the FMAs and
+// half the window loads of the dense form (T = 65: 32 instead of 72 FMA per output).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -109,6 +116,91 @@ __global__ void __launch_bounds__(HIL_NT) hilbert_kernel(const HilbertArgs a) {
     }
 }
 
+// Half-band form (see the file header).  Tile element e <-> z[ob + par + e]; padded index e + e/16, so a
+// thread's 16-element runs are 17 words apart (conflict free) and every window offset is an immediate:
+// set s in {0,1}, window slot u in [0,15): element (t+c)*16 + s + 2u  ->  (t+c)*17 + s + 2u + (u >= 8).
+constexpr int HILH_NT = 128;
+constexpr int HILH_OUT = 16;                                   // outputs per thread
+__global__ void __launch_bounds__(HILH_NT) hilbert_half_kernel(const HilbertArgs a, int par) {
+    extern __shared__ __align__(16) float hil_smem[];
+    constexpr int R = 8, P = HILH_OUT + 1, BT = HILH_NT * HILH_OUT;
+    const int t = threadIdx.x;
+    const int ntap_tab = a.nchunks * R;                        // a.nchunks: chunks of 8 taps of g
+    float* s_taps = hil_smem;
+    float* s_tile = hil_smem + ((ntap_tab + 3) & ~3);
+    const long long ob = (long long)blockIdx.x * BT;
+    const int L = (HILH_NT + a.nchunks + 1) * HILH_OUT;
+    const long long zb = ob + par;                             // z index of tile element 0
+
+    for (int i = t; i < ntap_tab; i += HILH_NT) s_taps[i] = a.taps[i];
+    if (zb >= a.T && zb - a.T + L <= a.n) {
+        const float* src = a.in + (zb - a.T);
+        for (int e = t; e < L; e += HILH_NT) s_tile[e + (e >> 4)] = src[e];
+    } else {
+        for (int e = t; e < L; e += HILH_NT) s_tile[e + (e >> 4)] = hil_z(a, zb + e);
+    }
+    __syncthreads();
+
+    float acc0[R], acc1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { acc0[r] = 0.f; acc1[r] = 0.f; }
+    const float* bp = s_tile + t * P;
+    const float* tp = s_taps;
+    float w0[2 * R - 1], w1[2 * R - 1];
+#pragma unroll
+    for (int u = 0; u < R - 1; ++u) { w0[u] = bp[2 * u]; w1[u] = bp[2 * u + 1]; }
+    for (int c = 0; c < a.nchunks; ++c) {
+#pragma unroll
+        for (int u = R - 1; u < 2 * R - 1; ++u) {
+            w0[u] = bp[2 * u + (u >= R ? 1 : 0)];
+            w1[u] = bp[2 * u + 1 + (u >= R ? 1 : 0)];
+        }
+        const float4 h0 = *reinterpret_cast<const float4*>(tp), h1 = *reinterpret_cast<const float4*>(tp + 4);
+        const float h[R] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                acc0[r] = fmaf(h[k], w0[r + k], acc0[r]);
+                acc1[r] = fmaf(h[k], w1[r + k], acc1[r]);
+            }
+#pragma unroll
+        for (int u = 0; u < R - 1; ++u) { w0[u] = w0[u + R]; w1[u] = w1[u + R]; }
+        bp += P;
+        tp += R;
+    }
+
+    const int e0 = t * HILH_OUT + a.mid - par;                 // tile element of z[i + T/2] for the thread's first output
+    float re[HILH_OUT];
+#pragma unroll
+    for (int k = 0; k < HILH_OUT; ++k) re[k] = s_tile[(e0 + k) + ((e0 + k) >> 4)];
+    // Coalesced stores through shared memory: a thread's 16 results are 128 contiguous bytes, so a direct
+    // STG.128 per thread touches 32 different lines per warp instruction (32 L1 wavefronts each — measured:
+    // the store pipe, not the FMAs, bounded the first version).  Staged with pitch 17 (conflict-free
+    // 64-bit writes), read back as consecutive 16-byte pairs: 512 contiguous bytes per warp instruction.
+    __syncthreads();                                           // everyone is done with the input tile
+    float2* s_out = reinterpret_cast<float2*>(hil_smem);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        s_out[t * P + 2 * r] = make_float2(re[2 * r], acc0[r]);
+        s_out[t * P + 2 * r + 1] = make_float2(re[2 * r + 1], acc1[r]);
+    }
+    __syncthreads();
+    float2* dst = a.out + ob;
+    const bool vec = (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        const int o = 2 * (t + k * HILH_NT);                   // even output index inside the tile
+        const float2 y0 = s_out[o + (o >> 4)], y1 = s_out[o + 1 + (o >> 4)];
+        if (vec && ob + o + 1 < a.n) {
+            *reinterpret_cast<float4*>(dst + o) = make_float4(y0.x, y0.y, y1.x, y1.y);
+        } else {
+            if (ob + o < a.n) dst[o] = y0;
+            if (ob + o + 1 < a.n) dst[o + 1] = y1;
+        }
+    }
+}
+
 // history for the next call: z[n .. n + T)  (src/hilbert.rs:123)
 __global__ void hilbert_hist_kernel(const HilbertArgs a, float* hist_next) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,6 +219,11 @@ struct rrc_hilbert {
     float* hist[2] = {nullptr, nullptr};
     int cur = 0;
     size_t smem = 0;
+    // half-band form (hilbert_half_kernel): every tap h'[j] with j != par (mod 2) is exactly zero
+    bool half = false;
+    int par = 0, half_chunks = 0;
+    float* half_taps_dev = nullptr;
+    size_t half_smem = 0;
 };
 
 namespace {
@@ -201,6 +298,19 @@ int rrc_hilbert_create(int device, const float* taps, size_t ntaps, rrc_hilbert_
     for (size_t j = 0; j < ntaps; ++j) rev[j] = taps[ntaps - 1 - j];          // Fir::new reverses (src/fir.rs:156-162)
     const size_t tap_floats = (rev.size() + 3) & ~(size_t)3;
     h->smem = (tap_floats + (size_t)(HIL_NT + h->nchunks + 1) * (HIL_R + 1)) * sizeof(float);
+    h->par = (int)((ntaps / 2 + 1) & 1);
+    h->half = !getenv("RRC_HILBERT_DENSE");
+    for (size_t j = 0; j < ntaps && h->half; ++j)
+        if ((int)(j & 1) != h->par && rev[j] != 0.0f) h->half = false;
+    std::vector<float> g;
+    if (h->half) {
+        for (size_t j = (size_t)h->par; j < ntaps; j += 2) g.push_back(rev[j]);
+        h->half_chunks = (int)((g.size() + HIL_R - 1) / HIL_R);
+        g.resize((size_t)h->half_chunks * HIL_R, 0.0f);
+        h->half_smem = std::max((((g.size() + 3) & ~(size_t)3) + (size_t)(HILH_NT + h->half_chunks + 2) * (HILH_OUT + 1)) * sizeof(float),
+                                (size_t)HILH_NT * (HILH_OUT + 1) * sizeof(float2));      // input tile, later the output staging
+        if (h->half_smem > 200 * 1024) h->half = false;
+    }
     auto bail = [&](cudaError_t e, const char* what) {
         int s = fail(RRC_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
         rrc_hilbert_destroy(h);
@@ -210,6 +320,13 @@ int rrc_hilbert_create(int device, const float* taps, size_t ntaps, rrc_hilbert_
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
     if ((e = cudaMalloc((void**)&h->taps_dev, rev.size() * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemcpy(h->taps_dev, rev.data(), rev.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
+    if (h->half) {
+        if ((e = cudaMalloc((void**)&h->half_taps_dev, g.size() * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
+        if ((e = cudaMemcpy(h->half_taps_dev, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
+        if (h->half_smem > 48 * 1024 &&
+            (e = cudaFuncSetAttribute(hilbert_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->half_smem)) != cudaSuccess)
+            return bail(e, "cudaFuncSetAttribute");
+    }
     for (int i = 0; i < 2; ++i) {
         if ((e = cudaMalloc((void**)&h->hist[i], ntaps * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
         if ((e = cudaMemset(h->hist[i], 0, ntaps * sizeof(float))) != cudaSuccess) return bail(e, "cudaMemset");   // history: vec![0.0; ntaps]
@@ -225,6 +342,7 @@ int rrc_hilbert_destroy(rrc_hilbert_t* h) {
     if (!h) return RRC_OK;
     cudaSetDevice(h->device);
     if (h->taps_dev) cudaFree(h->taps_dev);
+    if (h->half_taps_dev) cudaFree(h->half_taps_dev);
     for (int i = 0; i < 2; ++i) if (h->hist[i]) cudaFree(h->hist[i]);
     delete h;
     return RRC_OK;
@@ -246,10 +364,16 @@ int rrc_hilbert_run(rrc_hilbert_t* h, const float* in_dev, size_t n, float* out_
     HilbertArgs a{};
     a.in = in_dev; a.hist = h->hist[h->cur]; a.out = reinterpret_cast<float2*>(out_dev_c32);
     a.taps = h->taps_dev; a.n = (long long)n; a.T = (int)h->ntaps; a.nchunks = h->nchunks; a.mid = (int)(h->ntaps / 2);
-    const size_t bt = (size_t)HIL_NT * HIL_R;
+    const size_t bt = h->half ? (size_t)HILH_NT * HILH_OUT : (size_t)HIL_NT * HIL_R;
     const size_t tiles = (n + bt - 1) / bt;
     if (tiles > 0x7fffffffu) return fail(RRC_ERR_INVALID, "Hilbert: n too large for one launch");
-    hilbert_kernel<<<(unsigned)tiles, HIL_NT, h->smem, st>>>(a);
+    if (h->half) {
+        HilbertArgs b = a;
+        b.taps = h->half_taps_dev; b.nchunks = h->half_chunks;
+        hilbert_half_kernel<<<(unsigned)tiles, HILH_NT, h->half_smem, st>>>(b, h->par);
+    } else {
+        hilbert_kernel<<<(unsigned)tiles, HIL_NT, h->smem, st>>>(a);
+    }
     RRC_CHECK_LAUNCH();
     hilbert_hist_kernel<<<(unsigned)((h->ntaps + 255) / 256), 256, 0, st>>>(a, h->hist[h->cur ^ 1]);
     RRC_CHECK_LAUNCH();

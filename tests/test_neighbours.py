@@ -201,6 +201,20 @@ def test_hilbert_kernel_vs_oracle(R, ntaps, wt):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ntaps", [3, 65, 67, 129])
+def test_hilbert_dense_kernel_for_arbitrary_taps(R, ntaps):
+    """Taps that are not half-band (caller supplied through rrc_hilbert_create) take hilbert_kernel; the
+    reference's own taps take hilbert_half_kernel (both parities of T/2: 65 -> odd taps, 67 -> even)."""
+    n = 50_001
+    x = O.synth_f32(70 + ntaps, 0, n)
+    taps = O.synth_f32(71, 0, ntaps) / np.float32(ntaps)
+    got = R.Hilbert(ntaps, taps=taps).process(x)
+    assert O.rel_rms(got, O.Hilbert(ntaps, taps=taps).work(x, f64=True)) <= 1e-5
+    got = R.Hilbert(ntaps).process(x)
+    assert O.rel_rms(got, O.Hilbert(ntaps).work(x, f64=True)) <= 1e-5
+
+
+@pytest.mark.gpu
 def test_hilbert_constructor_errors(R):
     for bad in (0, 1, 64):
         with pytest.raises(R.RrcError):
