@@ -538,10 +538,10 @@ def run_gpu(args):
         traffic = json.loads(traffic_path.read_text()).get(cfg["name"])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
-                "kernel": {"fftfilt": "fftfilt_kernel", "fir": "fir_poly_kernel<float2,float,1,false,16>", "fir_demod": "fir_rt_kernel<10,DEMOD,8,2>",
+                "kernel": {"fftfilt": "fftfilt_tma_kernel (TMA-staged input; RRC_FFTFILT_VARIANT=32 selects the LDG kernel)", "fir": "fir_poly_kernel<float2,float,1,false,16>", "fir_demod": "fir_rt_kernel<10,DEMOD,8,2>",
                            "resample": "resample_kernel", "decode": "rtlsdr_decode_kernel", "fft": "fftstream_kernel<10>", "fftfilt_real": "fftfilt_kernel (real-stream mode)",
                            "fftfilt_decim": "fftfilt_fold_kernel<4> (65536-point, 4-CTA cluster) + history update",
-                           "hilbert": "hilbert_kernel + history update", "mulconst": "map_kernel<MAP_MUL_C32>", "mag2": "mag2_kernel",
+                           "hilbert": "hilbert_half_kernel + history update", "mulconst": "map_kernel<MAP_MUL_C32>", "mag2": "mag2_kernel",
                            "tee": "tee_kernel<uint4>", "iqbalance": "iq_tile_kernel<false> + iq_carry_kernel + iq_tile_kernel<true> (input read twice: 24 B/sample of traffic vs 16 algorithmic)"}[op],
                 "duration_ms": ms_per_step,
                 "note": "duration = CUDA-event time of the whole step on the launching stream / steps; the step is this one kernel"

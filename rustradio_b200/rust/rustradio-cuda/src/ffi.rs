@@ -7,6 +7,8 @@ use std::ffi::{c_char, c_float, c_int, c_uint, c_void};
 #[repr(C)] pub struct rrc_fir_t { _p: [u8; 0] }
 #[repr(C)] pub struct rrc_fftfilt_t { _p: [u8; 0] }
 #[repr(C)] pub struct rrc_resampler_t { _p: [u8; 0] }
+#[repr(C)] pub struct rrc_hilbert_t { _p: [u8; 0] }
+#[repr(C)] pub struct rrc_iq_balance_t { _p: [u8; 0] }
 
 pub const RRC_OK: c_int = 0;
 
@@ -58,6 +60,25 @@ unsafe extern "C" {
     // RtlSdrDecode fused into the first load of the filters (u8 I/Q input mode)
     pub fn rrc_fir_set_input_u8iq(h: *mut rrc_fir_t, on: c_int) -> c_int;
     pub fn rrc_fftfilt_set_input_u8iq(h: *mut rrc_fftfilt_t, on: c_int) -> c_int;
+    // WindowType::make_window / fir::hilbert / Hilbert::work     src/window.rs:63-185, src/fir.rs:660-680, src/hilbert.rs:72-128
+    pub fn rrc_make_window(window_type: c_int, parm: c_float, ntaps: usize, window_out: *mut c_float) -> c_int;
+    pub fn rrc_hilbert_taps(window: *const c_float, ntaps: usize, taps_out: *mut c_float) -> c_int;
+    pub fn rrc_hilbert_create(device: c_int, taps: *const c_float, ntaps: usize, out: *mut *mut rrc_hilbert_t) -> c_int;
+    pub fn rrc_hilbert_destroy(h: *mut rrc_hilbert_t) -> c_int;
+    pub fn rrc_hilbert_run(h: *mut rrc_hilbert_t, in_dev: *const c_float, n: usize, out_dev_c32: *mut c_float, stream: *mut c_void) -> c_int;
+    // the `sync` blocks next to the filters      src/multiply_const.rs, add_const.rs, complex_to_mag2.rs, tee.rs, iq_balance.rs
+    pub fn rrc_multiply_const_f32_run(device: c_int, in_dev: *const c_float, n: usize, val: c_float, out_dev: *mut c_float, stream: *mut c_void) -> c_int;
+    pub fn rrc_multiply_const_c32_run(device: c_int, in_dev_c32: *const c_float, n: usize, val_re: c_float, val_im: c_float,
+                                      out_dev_c32: *mut c_float, stream: *mut c_void) -> c_int;
+    pub fn rrc_add_const_f32_run(device: c_int, in_dev: *const c_float, n: usize, val: c_float, out_dev: *mut c_float, stream: *mut c_void) -> c_int;
+    pub fn rrc_add_const_c32_run(device: c_int, in_dev_c32: *const c_float, n: usize, val_re: c_float, val_im: c_float,
+                                 out_dev_c32: *mut c_float, stream: *mut c_void) -> c_int;
+    pub fn rrc_complex_to_mag2_run(device: c_int, in_dev_c32: *const c_float, n: usize, out_dev: *mut c_float, stream: *mut c_void) -> c_int;
+    pub fn rrc_tee_run(device: c_int, in_dev: *const c_void, nbytes: usize, out1_dev: *mut c_void, out2_dev: *mut c_void, stream: *mut c_void) -> c_int;
+    pub fn rrc_iq_balance_alpha_from_tau(sample_rate: c_uint, tau_seconds: f64, alpha: *mut c_float) -> c_int;
+    pub fn rrc_iq_balance_create(device: c_int, alpha: c_float, out: *mut *mut rrc_iq_balance_t) -> c_int;
+    pub fn rrc_iq_balance_destroy(h: *mut rrc_iq_balance_t) -> c_int;
+    pub fn rrc_iq_balance_run(h: *mut rrc_iq_balance_t, in_dev_c32: *const c_float, n: usize, out_dev_c32: *mut c_float, stream: *mut c_void) -> c_int;
 }
 
 /// Turn a status code into rustradio's `Error::DeviceError`-style error (src/lib.rs:288-294).
