@@ -547,6 +547,16 @@ def run_gpu(args):
                 "note": "duration = CUDA-event time of the whole step on the launching stream / steps; the step is this one kernel"
                         + (" plus a <3 us history-update kernel" if op == "fftfilt" else "")}
 
+    if op in ("fir", "fir_demod") and f.uses_tensor_cores:
+        # Declared: the real-tap c32 FIR runs as a block-scaled fp16x3 Toeplitz product on the tensor cores (fir_tc.cuh).
+        roofline["kernel"] = "fir_tc_kernel (block-scaled fp16x3 Toeplitz product, mma.m16n8k16 + ldmatrix" + (", fused demod epilogue)" if op == "fir_demod" else ")")
+        ks = (7 * cfg["deci"] + cfg["ntaps"] + 15) // 16             # k-steps of 16 at 8 outputs per block-row (lower bound)
+        nout_fir = n_out + (cfg.get("nchan", 0) if op == "fir_demod" else 0)
+        mmas = 3 * ks * nout_fir / 64                                 # three m16n8k16 per k-step per 64 complex outputs
+        mma_peak = 148 * 0.46 * 1.965e9                               # measured, profiles/r01_microbench_hmma_rate.txt
+        roofline["tensor"] = {"mma_m16n8k16_per_launch": mmas, "achieved_mma_per_s": mmas / (ms_per_step * 1e-3),
+                              "peak_mma_per_s": mma_peak, "frac": mmas / (ms_per_step * 1e-3) / mma_peak,
+                              "peak_source": "measured mma.sync m16n8k16 issue rate, 0.46 per clk per SM (tools/microbench/hmma_rate.cu)"}
     # FP32 side of the roofline: algorithmic flops of the reference formulation against the
     # FP32 FMA rate MEASURED on this pool's B200 (tools/microbench/fp32_pipes.cu: 125 lanes/clk/SM).
     flops = alg_flops(cfg, n_in, n_out, f if op in ("fir", "fir_demod") else None)

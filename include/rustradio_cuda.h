@@ -92,6 +92,7 @@ typedef struct rrc_fir rrc_fir_t;
 /* flags */
 #define RRC_FIR_NO_REAL_TAP_FASTPATH 1u  /* always do the full complex*complex MAC even if every tap has im == 0 */
 #define RRC_FIR_FORCE_GENERIC        2u  /* use the one-thread-per-output fallback kernel (testing) */
+#define RRC_FIR_NO_TENSOR            4u  /* keep the FP32 kernels: no fp16x3 tensor-core Toeplitz product */
 
 int rrc_fir_c32_create(int device, const float* taps_c32, size_t ntaps, size_t deci, unsigned flags, rrc_fir_t** out);
 int rrc_fir_f32_create(int device, const float* taps, size_t ntaps, size_t deci, unsigned flags, rrc_fir_t** out);
@@ -106,6 +107,13 @@ int rrc_fir_ntaps(const rrc_fir_t* h, size_t* ntaps);
 int rrc_fir_deci(const rrc_fir_t* h, size_t* deci);
 /* 1 if the real-tap fast path (2 FMA per tap instead of 4) is active. */
 int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes);
+/* 1 if runs go through the tensor-core Toeplitz kernel (c32 samples, real taps, >= 16 taps, c32 input,
+ * no translate): samples (per tile) and taps are scaled by powers of two and split hi + lo in fp16 (22
+ * significant bits), every product is hi*hi + hi*lo + lo*hi with FP32 accumulation.  FP32-class accuracy:
+ * rel-RMS error 1e-7..4e-7 against the f64 convolution, next to 1e-7..2e-7 for the sequential f32 loop
+ * (bar 1e-5).  Declared like the real-tap fast path; RRC_FIR_NO_TENSOR (flag) or RRC_FIR_TENSOR=0
+ * (environment) disables it. */
+int rrc_fir_uses_tensor_cores(const rrc_fir_t* h, int* yes);
 /* Restart the translate rotator's output counter (new stream). */
 int rrc_fir_reset(rrc_fir_t* h);
 

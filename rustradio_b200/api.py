@@ -13,6 +13,7 @@ _SO = _HERE / "librustradio_cuda.so"
 RRC_OK = 0
 RRC_FIR_NO_REAL_TAP_FASTPATH = 1
 RRC_FIR_FORCE_GENERIC = 2
+RRC_FIR_NO_TENSOR = 4
 
 
 class RrcError(RuntimeError):
@@ -69,6 +70,7 @@ _SIGS = {
     "rrc_fir_ntaps": [_vp, _P(_sz)],
     "rrc_fir_deci": [_vp, _P(_sz)],
     "rrc_fir_uses_real_taps": [_vp, _P(_i)],
+    "rrc_fir_uses_tensor_cores": [_vp, _P(_i)],
     "rrc_fir_reset": [_vp],
     "rrc_fir_plan": [_sz, _sz, _sz, _sz, _P(_sz), _P(_sz), _P(_sz), _P(_sz), _P(_i)],
     "rrc_fir_run": [_vp, _vp, _sz, _vp, _sz, _vp],
@@ -324,6 +326,13 @@ class Fir:
     def uses_real_taps(self) -> bool:
         y = _i(0)
         _ck(lib().rrc_fir_uses_real_taps(self.h, C.byref(y)))
+        return bool(y.value)
+
+    @property
+    def uses_tensor_cores(self) -> bool:
+        """True when runs go through the block-scaled fp16x3 tensor-core Toeplitz kernel (declared, like the real-tap path)."""
+        y = _i(0)
+        _ck(lib().rrc_fir_uses_tensor_cores(self.h, C.byref(y)))
         return bool(y.value)
 
     def out_count(self, n_in: int) -> int:

@@ -548,6 +548,8 @@ __global__ void quad_demod_kernel(const float2* __restrict__ in, long long in_st
 
 }  // namespace rrc
 
+#include "fir_tc.cuh"
+
 using namespace rrc;
 
 struct rrc_fir {
@@ -568,6 +570,15 @@ struct rrc_fir {
     double ratio = 0.0;
     unsigned long long out_counter = 0;
     int in_u8 = 0;               // inputs are u8 I/Q pairs (rrc_fir_set_input_u8iq; c32 filters only)
+    // tensor-core Toeplitz kernel (fir_tc.cuh): c32 samples, real taps, no translate, c32 input
+    bool tc = false;
+    int tc_ntile = 1, tc_nld = 9, tc_nm = 1, tc_wb = 0, tc_KS = 0, tc_RS = 0, tc_PAD = 0, tc_L = 0, tc_PL = 0;
+    unsigned tc_magic = 0;
+    bool tc1 = false;            // deci == 1, <= 121 taps: fir_tc1_kernel (A fragments loaded once per warp tile)
+    float tc_tap_inv_scale = 1.0f;
+    int tc_ctas_per_sm = 0;      // occupancy of the chosen instantiation (persistent grid), filled at first launch
+    void* tc_bfrag = nullptr;
+    size_t tc_smem = 0;
     Pipe pipe;
 };
 
@@ -575,6 +586,176 @@ namespace {
 
 size_t tap_elem(const rrc_fir* h) { return h->real_taps ? sizeof(float) : sizeof(float2); }
 size_t samp_elem(const rrc_fir* h) { return h->cplx ? sizeof(float2) : sizeof(float); }
+
+unsigned short f16_rn(float f) {           // round-to-nearest-even f32 -> fp16 (|f| < 65504)
+    unsigned x;
+    memcpy(&x, &f, 4);
+    const unsigned short sign = (unsigned short)((x >> 16) & 0x8000u);
+    x &= 0x7fffffffu;
+    if (x < 0x38800000u)                   // below 2^-14: subnormal, a multiple of 2^-24
+        return (unsigned short)(sign | (unsigned short)std::nearbyint(std::fabs((double)f) * 16777216.0));
+    unsigned h = (((x >> 23) - 112u) << 10) | ((x & 0x7fffffu) >> 13);
+    const unsigned rem = x & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+    return (unsigned short)(sign | h);
+}
+float f16_to_f32(unsigned short b) {
+    const int e = (b >> 10) & 0x1f, m = b & 0x3ff;
+    const float v = e ? std::ldexp((float)(m | 0x400), e - 25) : std::ldexp((float)m, -24);
+    return (b & 0x8000) ? -v : v;
+}
+
+// Geometry and B fragments of fir_tc_kernel for the reversed real taps w[0..T).
+int plan_tc(rrc_fir* h, const std::vector<float>& w) {
+    h->tc = false;
+    h->tc1 = false;
+    if (h->tc_bfrag) { cudaFree(h->tc_bfrag); h->tc_bfrag = nullptr; }
+    const size_t T = h->ntaps, D = h->deci;
+    if (!h->cplx || !h->real_taps || (h->flags & (RRC_FIR_NO_TENSOR | RRC_FIR_FORCE_GENERIC)) || T < 16 || D > 512) return RRC_OK;
+    if (const char* e = getenv("RRC_FIR_TENSOR")) if (atoi(e) == 0) return RRC_OK;
+    for (float v : w) if (!std::isfinite(v)) return RRC_OK;
+    auto ksteps = [&](int ntile) { return (int)(((size_t)(8 * ntile - 1) * D + T + 15) / 16); };
+    // MMAs per output are 3*KS/64 whatever NTILE is; a wider block-row only saves ldmatrix traffic,
+    // so widen while the k-range grows by less than 10 %.
+    int ntile = 1;
+    for (int c : {2, 4}) if (ksteps(c) * 10 <= ksteps(1) * 11) ntile = c;
+    if (const char* e = getenv("RRC_FIR_TC_NTILE")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4) ntile = v; }
+    const size_t limit_hi = (size_t)max_smem_optin(h->device);
+    // A warp tile = NM m-tiles of 8 block-rows; its input span must fit the lanes' registers (64 * NLD samples).
+    // The conversion to fp16 planes costs ~20 instructions per staged sample, so the path is taken when a sample
+    // feeds many taps (ntaps/deci >= 32) and the halo is at most half of the staged span.
+    bool force = false;
+    if (const char* e = getenv("RRC_FIR_TENSOR")) force = atoi(e) == 2;
+    if (!force && T < 32 * D) return RRC_OK;
+    h->tc1 = D == 1 && ksteps(1) <= 8;
+    if (const char* e = getenv("RRC_FIR_TC1")) if (atoi(e) == 0) h->tc1 = false;
+    if (h->tc1) {
+        h->tc = true;
+        h->tc_ntile = 1; h->tc_KS = ksteps(1);
+    }
+    for (int pass = 0; pass < 2 && !h->tc; ++pass)
+        for (int nt = ntile; nt >= 1 && !h->tc; nt >>= 1) {
+            const int R = 8 * nt, KS = ksteps(nt);
+            const size_t RS = (size_t)R * D;
+            const int PAD = ((RS / 8) % 2 == 0) ? 8 : 0;
+            const size_t halo = std::max<size_t>((size_t)16 * KS > RS ? (size_t)16 * KS - RS : 0, T);
+            int nld = (halo * 6 <= (size_t)64 * 9 && 8 * RS + halo <= (size_t)64 * 9) ? 9 : 14;
+            if (const char* e = getenv("RRC_FIR_TC_NLD")) { int v = atoi(e); if (v == 9 || v == 14) nld = v; }
+            const size_t lmax = (size_t)64 * nld;
+            if (RS >= 65536 || 8 * RS + halo > lmax) continue;
+            size_t nm = (lmax - halo) / (8 * RS);
+            if (!force && halo > nm * 8 * RS) continue;
+            if (const char* e = getenv("RRC_FIR_TC_NM")) { int v = atoi(e); if (v >= 1 && (size_t)v < nm) nm = (size_t)v; }
+            size_t L = nm * 8 * RS + halo;
+            L = (L + 7) & ~(size_t)7;
+            const size_t chunks = (L + RS - 1) / RS;
+            const size_t PL = (L + chunks * PAD + 7) & ~(size_t)7;
+            const size_t wb = PL * 8 + (((nm * 8 * R + 2) * 8 + 15) & ~(size_t)15);      // ytile counted for both epilogues
+            const size_t smem = (size_t)KS * nt * 512 + (FIR_TC_THREADS / 32) * wb;
+            if (smem > (pass == 0 ? (size_t)74 * 1024 : limit_hi)) continue;
+            h->tc = true;
+            h->tc_ntile = nt; h->tc_nld = nld; h->tc_nm = (int)nm; h->tc_KS = KS; h->tc_RS = (int)RS; h->tc_PAD = PAD;
+            h->tc_L = (int)L; h->tc_PL = (int)PL; h->tc_wb = (int)wb; h->tc_smem = smem;
+            h->tc_magic = (unsigned)((0x100000000ull + RS - 1) / RS);
+        }
+    if (!h->tc) return RRC_OK;
+    // B[k][n] = w[k - n*D]; per lane (g = lane >> 2, t = lane & 3): column n = 8*nt + g,
+    // register 0 = rows k0 + 2t, +1, register 1 = rows k0 + 2t + 8, +9 (lower k in the lower half).
+    const int KS = h->tc_KS;
+    ntile = h->tc_ntile;
+    // taps scaled by the power of two that puts the largest one in [2^13, 2^14), then split hi + lo in fp16
+    float wmax = 0.0f;
+    for (float v : w) wmax = std::max(wmax, std::fabs(v));
+    int we = 0;
+    if (wmax > 0.0f) std::frexp(wmax, &we);               // wmax = m * 2^we, m in [0.5, 1)
+    const int shift = wmax > 0.0f ? 14 - we : 0;
+    if (shift > 100 || shift < -100) { h->tc = false; return RRC_OK; }
+    h->tc_tap_inv_scale = std::ldexp(1.0f, -shift);
+    std::vector<unsigned> frag((size_t)KS * ntile * 32 * 4);
+    auto Bval = [&](long long k, long long n) -> float {
+        const long long j = k - n * (long long)D;
+        return (j >= 0 && j < (long long)T) ? std::ldexp(w[(size_t)j], shift) : 0.0f;
+    };
+    for (int ks = 0; ks < KS; ++ks)
+        for (int nt = 0; nt < ntile; ++nt)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t = lane & 3;
+                const long long n = 8 * nt + g, k0 = 16ll * ks + 2 * t;
+                unsigned* f = &frag[(((size_t)ks * ntile + nt) * 32 + lane) * 4];
+                for (int r = 0; r < 2; ++r) {
+                    unsigned hi = 0, lo = 0;
+                    for (int e = 0; e < 2; ++e) {
+                        const float v = Bval(k0 + 8 * r + e, n);
+                        const unsigned short vh = f16_rn(v);
+                        const unsigned short vl = f16_rn(v - f16_to_f32(vh));
+                        hi |= (unsigned)vh << (16 * e);
+                        lo |= (unsigned)vl << (16 * e);
+                    }
+                    f[r] = hi;
+                    f[2 + r] = lo;
+                }
+            }
+    RRC_CUDA(cudaMalloc(&h->tc_bfrag, frag.size() * sizeof(unsigned)));
+    RRC_CUDA(cudaMemcpy(h->tc_bfrag, frag.data(), frag.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    return RRC_OK;
+}
+
+template <int NTILE, bool DEMOD, int NLD>
+int launch_tc_k(const rrc_fir* h, const FirTcArgs& a, cudaStream_t st) {
+    auto k = fir_tc_kernel<NTILE, DEMOD, NLD>;
+    RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
+    int per_sm = 0;
+    RRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, FIR_TC_THREADS, h->tc_smem));
+    if (per_sm < 1) return fail(RRC_ERR_CUDA, "fir_tc: kernel does not fit an SM (%zu bytes of shared memory)", h->tc_smem);
+    const long long cap = (long long)sm_count(h->device) * per_sm;
+    const long long ctas = (a.total_tiles + FIR_TC_THREADS / 32 - 1) / (FIR_TC_THREADS / 32);
+    const unsigned grid = (unsigned)std::min<long long>(ctas, cap);
+    k<<<grid, FIR_TC_THREADS, h->tc_smem, st>>>(a);
+    RRC_CHECK_LAUNCH();
+    count_launch();
+    return RRC_OK;
+}
+template <bool DEMOD>
+int launch_tc(const rrc_fir* h, const FirTcArgs& a, cudaStream_t st) {
+    switch (h->tc_ntile * 100 + h->tc_nld) {
+    case 109: return launch_tc_k<1, DEMOD, 9>(h, a, st);
+    case 114: return launch_tc_k<1, DEMOD, 14>(h, a, st);
+    case 209: return launch_tc_k<2, DEMOD, 9>(h, a, st);
+    case 214: return launch_tc_k<2, DEMOD, 14>(h, a, st);
+    case 409: return launch_tc_k<4, DEMOD, 9>(h, a, st);
+    case 414: return launch_tc_k<4, DEMOD, 14>(h, a, st);
+    default: return fail(RRC_ERR_INVALID, "fir_tc: no kernel for ntile %d nld %d", h->tc_ntile, h->tc_nld);
+    }
+}
+
+template <int KS, bool DEMOD>
+int launch_tc1_k(const rrc_fir* h, const FirTc1Args& a, cudaStream_t st) {
+    auto k = fir_tc1_kernel<KS, DEMOD>;
+    const size_t smem = (size_t)(FIR_TC_THREADS / 32) * (FIR_TC1_WB + (DEMOD ? FIR_TC1_YB : 0));
+    RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    RRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, FIR_TC_THREADS, smem));
+    if (per_sm < 1) return fail(RRC_ERR_CUDA, "fir_tc1: kernel does not fit an SM");
+    const long long cap = (long long)sm_count(h->device) * per_sm;
+    const long long ctas = (a.total_tiles + FIR_TC_THREADS / 32 - 1) / (FIR_TC_THREADS / 32);
+    k<<<(unsigned)std::min<long long>(ctas, cap), FIR_TC_THREADS, smem, st>>>(a);
+    RRC_CHECK_LAUNCH();
+    count_launch();
+    return RRC_OK;
+}
+template <bool DEMOD>
+int launch_tc1(const rrc_fir* h, const FirTc1Args& a, cudaStream_t st) {
+    switch (h->tc_KS) {
+    case 2: return launch_tc1_k<2, DEMOD>(h, a, st);
+    case 3: return launch_tc1_k<3, DEMOD>(h, a, st);
+    case 4: return launch_tc1_k<4, DEMOD>(h, a, st);
+    case 5: return launch_tc1_k<5, DEMOD>(h, a, st);
+    case 6: return launch_tc1_k<6, DEMOD>(h, a, st);
+    case 7: return launch_tc1_k<7, DEMOD>(h, a, st);
+    case 8: return launch_tc1_k<8, DEMOD>(h, a, st);
+    default: return fail(RRC_ERR_INVALID, "fir_tc1: no kernel for %d k-steps", h->tc_KS);
+    }
+}
 
 // (Re)build the device tap tables from taps_host and pick the launch geometry.
 int upload_taps(rrc_fir* h) {
@@ -649,6 +830,8 @@ int upload_taps(rrc_fir* h) {
             }
         }
     }
+    if (h->real_taps && h->cplx) RRC_TRY(plan_tc(h, rev));
+    else h->tc = false;
     return RRC_OK;
 }
 
@@ -739,7 +922,36 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
     a.in_u8 = h->in_u8;
     if (h->in_u8 && (reinterpret_cast<uintptr_t>(in) & 1)) return fail(RRC_ERR_INVALID, "u8 I/Q input must be 2-byte aligned");
 
-    if (h->use_poly) {
+    if (h->tc && h->tc1 && !h->translate && !h->in_u8) {
+        const size_t work = demod ? out_n - 1 : out_n;
+        if (work == 0) return RRC_OK;
+        FirTc1Args t{};
+        t.in = reinterpret_cast<const float2*>(in); t.out = out;
+        t.bfrag = reinterpret_cast<const uint4*>(h->tc_bfrag);
+        t.taps_rev = reinterpret_cast<const float*>(h->taps_rev);
+        t.in_stride = (long long)in_stride; t.out_stride = (long long)out_stride;
+        t.need = (long long)need; t.out_n = (long long)out_n;
+        t.ntaps = (int)h->ntaps; t.gain = gain; t.tap_inv_scale = h->tc_tap_inv_scale;
+        t.tiles_x = (long long)((work + FIR_TC1_BT - 1) / FIR_TC1_BT);
+        t.total_tiles = t.tiles_x * (long long)nchan;
+        RRC_TRY(demod ? launch_tc1<true>(h, t, st) : launch_tc1<false>(h, t, st));
+    } else if (h->tc && !h->translate && !h->in_u8) {
+        const size_t work = demod ? out_n - 1 : out_n;
+        if (work == 0) return RRC_OK;
+        FirTcArgs t{};
+        t.in = reinterpret_cast<const float2*>(in); t.out = out;
+        t.bfrag = reinterpret_cast<const uint4*>(h->tc_bfrag);
+        t.taps_rev = reinterpret_cast<const float*>(h->taps_rev);
+        t.in_stride = (long long)in_stride; t.out_stride = (long long)out_stride;
+        t.need = (long long)need; t.out_n = (long long)out_n;
+        t.ntaps = (int)h->ntaps; t.deci = (int)h->deci;
+        t.RS = h->tc_RS; t.PAD = h->tc_PAD; t.magic = h->tc_magic; t.KS = h->tc_KS; t.NM = h->tc_nm; t.L = h->tc_L; t.PL = h->tc_PL; t.WB = h->tc_wb;
+        t.gain = gain; t.tap_inv_scale = h->tc_tap_inv_scale;
+        const size_t bt = (size_t)h->tc_nm * 8 * 8 * h->tc_ntile;
+        t.tiles_x = (long long)((work + bt - 1) / bt);
+        t.total_tiles = t.tiles_x * (long long)nchan;
+        RRC_TRY(demod ? launch_tc<true>(h, t, st) : launch_tc<false>(h, t, st));
+    } else if (h->use_poly) {
         a.taps = h->taps_poly;
         const size_t bt = (size_t)h->groups * h->R;
         const size_t per = demod ? bt - 1 : bt;
@@ -845,6 +1057,7 @@ int rrc_fir_destroy(rrc_fir_t* h) {
     cudaSetDevice(h->device);
     if (h->taps_poly) cudaFree(h->taps_poly);
     if (h->taps_rev) cudaFree(h->taps_rev);
+    if (h->tc_bfrag) cudaFree(h->tc_bfrag);
     h->pipe.destroy();
     delete h;
     return RRC_OK;
@@ -862,6 +1075,11 @@ int rrc_fir_deci(const rrc_fir_t* h, size_t* d) {
 int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes) {
     if (!h || !yes) return fail(RRC_ERR_INVALID, "NULL argument");
     *yes = (h->cplx && h->real_taps) ? 1 : 0;
+    return RRC_OK;
+}
+int rrc_fir_uses_tensor_cores(const rrc_fir_t* h, int* yes) {
+    if (!h || !yes) return fail(RRC_ERR_INVALID, "null argument");
+    *yes = (h->tc && !h->translate && !h->in_u8) ? 1 : 0;
     return RRC_OK;
 }
 int rrc_fir_set_input_u8iq(rrc_fir_t* h, int on) {

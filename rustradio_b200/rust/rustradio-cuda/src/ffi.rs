@@ -59,6 +59,7 @@ unsafe extern "C" {
     pub fn rrc_rtlsdr_decode_run(device: c_int, in_dev: *const u8, n_bytes: usize, out_dev_c32: *mut c_float, stream: *mut c_void) -> c_int;
     // RtlSdrDecode fused into the first load of the filters (u8 I/Q input mode)
     pub fn rrc_fir_set_input_u8iq(h: *mut rrc_fir_t, on: c_int) -> c_int;
+    pub fn rrc_fir_uses_tensor_cores(h: *const rrc_fir_t, yes: *mut c_int) -> c_int;
     pub fn rrc_fftfilt_set_input_u8iq(h: *mut rrc_fftfilt_t, on: c_int) -> c_int;
     // WindowType::make_window / fir::hilbert / Hilbert::work     src/window.rs:63-185, src/fir.rs:660-680, src/hilbert.rs:72-128
     pub fn rrc_make_window(window_type: c_int, parm: c_float, ntaps: usize, window_out: *mut c_float) -> c_int;

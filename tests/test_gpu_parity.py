@@ -60,13 +60,141 @@ def test_fir_matches_oracle(R, ntaps, deci, n, kind):
         assert e <= REL_RMS_BAR
 
 
-@pytest.mark.parametrize("flags_name", ["RRC_FIR_FORCE_GENERIC", "RRC_FIR_NO_REAL_TAP_FASTPATH"])
+@pytest.mark.parametrize("flags_name", ["RRC_FIR_FORCE_GENERIC", "RRC_FIR_NO_REAL_TAP_FASTPATH", "RRC_FIR_NO_TENSOR"])
 def test_fir_alternate_paths(R, flags_name):
     x = O.synth_c32(13, 0, 20_000)
     taps = O.low_pass_n(1.0, 0.1, 101).astype(np.complex64)
     f = R.Fir(taps, deci=3, flags=getattr(R, flags_name))
     assert not (flags_name == "RRC_FIR_NO_REAL_TAP_FASTPATH" and f.uses_real_taps)
+    assert not (flags_name != "RRC_FIR_FORCE_GENERIC" and f.uses_tensor_cores)
     assert O.rel_rms(f.filter(x), O.fir(x, taps, 3, f64=True)) <= REL_RMS_BAR
+
+
+@pytest.mark.parametrize("ntile,nld,nm", [(1, 14, 0), (2, 14, 0), (4, 14, 0), (1, 9, 0), (2, 9, 1), (4, 9, 0)])
+@pytest.mark.parametrize("ntaps,deci,n,nchan", [(64, 1, 70_001, 1), (255, 10, 61_237, 3), (31, 4, 9_000, 2), (16, 3, 40_000, 1),
+                                                (200, 2, 33_333, 2)])
+def test_fir_tensor_core_geometries(R, monkeypatch, ntile, nld, nm, ntaps, deci, n, nchan):
+    """fir_tc_kernel: every (block-row width, register-tile size) instantiation and several tile heights, ragged
+    tails, channel strides that leave odd channels 8-byte aligned only, plain and fused-demod epilogues; the FP32
+    kernels as the second opinion.  RRC_FIR_TENSOR=2 takes the tensor path for shapes the planner would leave on FP32."""
+    monkeypatch.setenv("RRC_FIR_TENSOR", "2")
+    monkeypatch.setenv("RRC_FIR_TC1", "0")             # the generic kernel also for deci == 1
+    monkeypatch.setenv("RRC_FIR_TC_NTILE", str(ntile))
+    monkeypatch.setenv("RRC_FIR_TC_NLD", str(nld))
+    if nm:
+        monkeypatch.setenv("RRC_FIR_TC_NM", str(nm))
+    taps = O.low_pass_n(1.0, 0.4 / deci, ntaps).astype(np.complex64)
+    f = R.Fir(taps, deci=deci)
+    f32 = R.Fir(taps, deci=deci, flags=R.RRC_FIR_NO_TENSOR)
+    assert f.uses_real_taps and not f32.uses_tensor_cores
+    if not f.uses_tensor_cores:
+        assert (ntaps, deci) != (64, 1)
+        pytest.skip("no warp tile of this geometry fits the register staging")
+    stride = n + 1 if n % 2 == 0 else n            # odd stride: channel 1 starts 8 bytes off a 16-byte boundary
+    xs = np.zeros((nchan, stride), np.complex64)
+    for c in range(nchan):
+        xs[c, :n] = O.synth_c32(200 + c, 0, n) * 0.5 + np.exp(2j * np.pi * 0.013 * (c + 1) * np.arange(n)).astype(np.complex64)
+    out_n = f.out_count(n)
+    need = (out_n - 1) * deci + ntaps
+    din = R.DeviceBuffer.from_numpy(xs)
+    ostride = out_n + 1 - (out_n % 2)              # odd output stride as well
+    for filt in (f, f32):
+        dy = R.DeviceBuffer(nchan * ostride * 8)
+        filt.run_batch(din, stride, need, dy, ostride, out_n, nchan)
+        y = dy.download(np.complex64, nchan * ostride).reshape(nchan, ostride)[:, :out_n]
+        dd = R.DeviceBuffer(nchan * ostride * 4)
+        filt.demod_run_batch(din, stride, need, 0.7, dd, ostride, out_n, nchan)
+        d = dd.download(np.float32, nchan * ostride).reshape(nchan, ostride)[:, :out_n - 1]
+        for c in range(nchan):
+            truth = O.fir(xs[c, :n], taps, deci, f64=True)
+            e = O.rel_rms(y[c], truth)
+            print(f"fir_tc ntile={ntile} nld={nld} nm={nm} T={ntaps} D={deci} ch{c} {'tensor' if filt is f else 'fp32'}: {e:.2e}")
+            assert e <= REL_RMS_BAR
+            want = np.angle(truth[1:] * np.conj(truth[:-1]))
+            assert O.max_angle_err(d[c] / 0.7, want) <= DEMOD_BAR
+
+
+@pytest.mark.parametrize("ntaps,n,nchan", [(16, 5_000, 2), (33, 70_001, 1), (64, 262_144, 1), (64, 1_300, 5), (100, 40_000, 3),
+                                           (121, 20_011, 2), (17, 600, 1)])
+def test_fir_tensor_core_deci1_kernel(R, monkeypatch, ntaps, n, nchan):
+    """fir_tc1_kernel (deci 1, <= 121 taps, every k-step count 2..8): plain and fused-demod epilogues, ragged last tiles,
+    tiles shorter than one warp tile, odd channel strides (8-byte aligned channels take the scalar loads/stores)."""
+    if ntaps < 32:
+        monkeypatch.setenv("RRC_FIR_TENSOR", "2")      # the planner leaves < 32 taps on the FP32 kernel
+    taps = O.low_pass_n(1.0, 0.2, ntaps).astype(np.complex64)
+    f = R.Fir(taps)
+    assert f.uses_tensor_cores
+    stride = n + 1 if n % 2 == 0 else n
+    xs = np.zeros((nchan, stride), np.complex64)
+    for c in range(nchan):
+        xs[c, :n] = O.synth_c32(300 + c, 0, n) * 0.5 + np.exp(2j * np.pi * 0.013 * (c + 1) * np.arange(n)).astype(np.complex64)
+    out_n = f.out_count(n)
+    need = (out_n - 1) + ntaps
+    din = R.DeviceBuffer.from_numpy(xs)
+    ostride = out_n + 1 - (out_n % 2)
+    dy = R.DeviceBuffer(nchan * ostride * 8)
+    f.run_batch(din, stride, need, dy, ostride, out_n, nchan)
+    y = dy.download(np.complex64, nchan * ostride).reshape(nchan, ostride)[:, :out_n]
+    dd = R.DeviceBuffer(nchan * ostride * 4)
+    f.demod_run_batch(din, stride, need, 0.7, dd, ostride, out_n, nchan)
+    d = dd.download(np.float32, nchan * ostride).reshape(nchan, ostride)[:, :out_n - 1]
+    for c in range(nchan):
+        truth = O.fir(xs[c, :n], taps, 1, f64=True)
+        e, e_ref = O.rel_rms(y[c], truth), O.rel_rms(O.fir(xs[c, :n], taps, 1), truth)
+        print(f"fir_tc1 T={ntaps} ch{c}: gpu {e:.2e}  f32-oracle {e_ref:.2e}")
+        assert e <= 2e-6
+        assert O.max_angle_err(d[c] / 0.7, np.angle(truth[1:] * np.conj(truth[:-1]))) <= DEMOD_BAR
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-20, 3e18, 0.0])
+def test_fir_tensor_core_block_scaling(R, scale):
+    """The per-tile power-of-two scaling makes the fp16 split independent of the stream's level; a tile that is one
+    loud burst next to near-silence keeps FP32-class error relative to the burst; all-zero input gives zeros."""
+    n, ntaps, deci = 50_000, 129, 4
+    taps = O.low_pass_n(1.0, 0.08, ntaps).astype(np.complex64)
+    x = (O.synth_c32(31, 0, n) * np.float32(scale)).astype(np.complex64)
+    x[20_000:20_050] *= 1000.0
+    f = R.Fir(taps, deci=deci)
+    assert f.uses_tensor_cores
+    y = f.filter(x)
+    truth = O.fir(x, taps, deci, f64=True)
+    if scale == 0.0:
+        assert not y.any()
+        return
+    e, e_ref = O.rel_rms(y, truth), O.rel_rms(O.fir(x, taps, deci), truth)
+    print(f"fir_tc scale {scale:g}: gpu {e:.2e}  f32-oracle {e_ref:.2e}")
+    assert e <= 2e-6 and e <= 8 * e_ref
+
+
+def test_fir_tensor_core_stopband_dominated_input(R, monkeypatch):
+    """A strong out-of-band tone: the error is relative to the INPUT level, so the bar is checked on the hard case."""
+    monkeypatch.setenv("RRC_FIR_TENSOR", "2")
+    n, ntaps, deci = 200_000, 255, 10
+    taps = O.low_pass_n(2.4e6, 100e3, ntaps).astype(np.complex64)
+    x = (O.synth_c32(32, 0, n) * 0.05 + 4.0 * np.exp(2j * np.pi * 0.31 * np.arange(n))).astype(np.complex64)
+    truth = O.fir(x, taps, deci, f64=True)
+    ftc = R.Fir(taps, deci=deci)
+    assert ftc.uses_tensor_cores
+    e_tc = O.rel_rms(ftc.filter(x), truth)
+    e_fp = O.rel_rms(R.Fir(taps, deci=deci, flags=R.RRC_FIR_NO_TENSOR).filter(x), truth)
+    e_ref = O.rel_rms(O.fir(x, taps, deci), truth)
+    print(f"stopband-dominated: tensor {e_tc:.2e}  fp32 kernel {e_fp:.2e}  f32-oracle {e_ref:.2e}")
+    assert e_tc <= 10 * max(e_ref, e_fp)
+
+
+def test_fir_tensor_core_falls_back(R):
+    """translate, u8 I/Q input, complex taps, < 16 taps and f32 streams stay on the FP32 kernels."""
+    lp = O.low_pass_n(1.0, 0.1, 64)
+    f = R.Fir(lp.astype(np.complex64))
+    assert f.uses_tensor_cores
+    f.set_input_u8iq(True)
+    assert not f.uses_tensor_cores
+    assert not R.Fir(lp.astype(np.float32)).uses_tensor_cores
+    assert not R.Fir(cplx_taps(64)).uses_tensor_cores
+    assert not R.Fir(O.low_pass_n(1.0, 0.1, 15).astype(np.complex64)).uses_tensor_cores
+    # the planner keeps decimating short filters (config 3: 255 taps / 10) on the packed-FP32 kernel
+    assert not R.Fir(O.low_pass_n(2.4e6, 100e3, 255).astype(np.complex64), deci=10).uses_tensor_cores
+    assert R.Fir(O.low_pass_n(1.0, 0.1, 247).astype(np.complex64)).uses_tensor_cores
 
 
 def test_fir_huge_deci_falls_back(R):
