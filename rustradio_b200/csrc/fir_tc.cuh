@@ -259,8 +259,11 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc_kernel(const FirTcAr
 // of different m-tiles are the same samples shifted by whole 8-sample units: with block-row b = j + 8*r
 // (m-tile j < 8, row r < 8) the A fragment of (m-tile j, k-step ks) is the pair of 8-sample "half fragments"
 // H(j + 2*ks), H(j + 2*ks + 1), where H(a) = rows {64*r + 8*a .. +8} of the re/im x hi/lo planes — ONE
-// ldmatrix.x4.  Walking a = 0 .. 7 + 2*(KS-1) with a two-entry window feeds all 8*KS (m-tile, k-step) pairs
-// from 8 + 2*KS loads: 17 ldmatrix per 120 mma for 64 taps instead of 80 ldmatrix + 40 B-fragment loads.
+// ldmatrix.x4.  Walking p = 0 .. 7 + 2*(KS-1) feeds all 8*KS (m-tile, k-step) pairs; each position loads its
+// A operand {H(p), H(p+1)} for the hi and for the lo planes (two ldmatrix.x4 whose destination quads are the
+// mma operands as they are — a sliding two-entry window of single half fragments would save half of these
+// loads but needs 8 register moves per position to assemble the operands): 32 ldmatrix per 120 mma for
+// 64 taps instead of 80 ldmatrix + 40 B-fragment loads.
 // The loop is fully unrolled (KS is a template parameter), so every shared-memory offset is an immediate,
 // the B fragments (4*KS registers) stay in registers for the whole kernel, and the padded plane layout
 // (8 fp16 after every 64 samples -> 144-byte row stride) needs no index arithmetic anywhere:
@@ -277,7 +280,7 @@ struct FirTc1Args {
 };
 
 constexpr int FIR_TC1_BT = 512;            // outputs per warp tile: 8 m-tiles x 8 block-rows x 8 outputs
-constexpr int FIR_TC1_NLD = 10;            // float4 per lane: up to 640 staged samples (504 + 16*KS <= 632)
+constexpr int FIR_TC1_NLD = 10;            // float4 per lane: up to 640 staged samples (512 + 16*KS <= 640)
 constexpr int FIR_TC1_PLW = 360;           // 32-bit words per plane: 10 chunks of (64 + 8) fp16
 constexpr int FIR_TC1_WB = 4 * FIR_TC1_PLW * 4;                        // plane bytes per warp (5760)
 constexpr int FIR_TC1_YB = (FIR_TC1_BT + 2) * 8;                       // ytile bytes per warp (demod only)
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = FIR_TC_THREADS / 32;
     constexpr int BT = FIR_TC1_BT;
-    constexpr int L = 504 + 16 * KS;                       // staged samples per tile
+    constexpr int L = 512 + 16 * KS;                       // staged samples per tile: 504 + 16*KS for the product, 512 + ntaps for the demod boundary output
     constexpr int NP = L / 2;                              // sample pairs
     constexpr int NLD = FIR_TC1_NLD;
     constexpr int PLW = FIR_TC1_PLW;
@@ -300,10 +303,14 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) bq[ks] = __ldg(a.bfrag + ks * 32 + lane);
 
-    // ldmatrix lane address: matrix (lane >> 3) = plane {re_hi, im_hi, re_lo, im_lo}, row r = lane & 7 at 144 bytes
+    // ldmatrix lane address for the A operand of walk position p: matrix (lane >> 3) = {re @p, im @p, re @p+1, im @p+1}
+    // of the hi planes (the lo plane of each follows it), row r = lane & 7 at 144 bytes.  Half fragment q sits at byte
+    // 16*q + 16*(q >> 3) of its row (8 fp16 of padding after every 64 samples), so lanes of the "@p+1" matrices need
+    // 16 bytes more, and 32 when p + 1 crosses a chunk (p % 8 == 7): two lane bases, every other offset an immediate.
     const int mat = lane >> 3;
-    const int plane = ((mat & 1) << 1) | (mat >> 1);       // plane index = 2*(im?) + (lo?)
-    const unsigned lane_addr = (unsigned)__cvta_generic_to_shared(s_planes) + (unsigned)plane * (PLW * 4) + (unsigned)(lane & 7) * 144u;
+    const unsigned lane_addr = (unsigned)__cvta_generic_to_shared(s_planes) + (unsigned)(mat & 1) * (2u * PLW * 4u) +
+                               (unsigned)(lane & 7) * 144u + (unsigned)(mat >> 1) * 16u;
+    const unsigned lane_addr7 = lane_addr + (unsigned)(mat >> 1) * 16u;
 
     const long long nworkers = (long long)gridDim.x * NW;
     for (long long id = (long long)blockIdx.x * NW + warp; id < a.total_tiles; id += nworkers) {
@@ -388,25 +395,24 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
         for (int j = 0; j < 8; ++j)
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
-        unsigned H[2][4];                                  // {re_hi, im_hi, re_lo, im_lo} of half fragments a, a + 1
-        ldsm4(H[0], lane_addr);
+        unsigned ah[2][4], al[2][4];                       // A operands (hi, lo) of walk positions p, p + 1
+        ldsm4(ah[0], lane_addr);
+        ldsm4(al[0], lane_addr + PLW * 4);
 #pragma unroll
         for (int p = 0; p <= 7 + 2 * (KS - 1); ++p) {
-            {   // H(p + 1): samples 64*r + 8*(p+1) -> byte 144*r + 16*(p+1) + 16*((p+1) >> 3)
+            if (p < 7 + 2 * (KS - 1)) {
                 const int q = p + 1;
-                ldsm4(H[q & 1], lane_addr + 16u * (unsigned)q + 16u * (unsigned)(q >> 3));
+                const unsigned ad = ((q & 7) == 7 ? lane_addr7 : lane_addr) + 16u * (unsigned)q + 16u * (unsigned)(q >> 3);
+                ldsm4(ah[q & 1], ad);
+                ldsm4(al[q & 1], ad + PLW * 4);
             }
-            const unsigned (&h0)[4] = H[p & 1];
-            const unsigned (&h1)[4] = H[(p + 1) & 1];
-            const unsigned ahi[4] = {h0[0], h0[1], h1[0], h1[1]};
-            const unsigned alo[4] = {h0[2], h0[3], h1[2], h1[3]};
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 const int j = p - 2 * ks;
                 if (j >= 0 && j < 8) {
-                    mma_f16(acc[j], alo, bq[ks].x, bq[ks].y);
-                    mma_f16(acc[j], ahi, bq[ks].z, bq[ks].w);
-                    mma_f16(acc[j], ahi, bq[ks].x, bq[ks].y);
+                    mma_f16(acc[j], al[p & 1], bq[ks].x, bq[ks].y);
+                    mma_f16(acc[j], ah[p & 1], bq[ks].z, bq[ks].w);
+                    mma_f16(acc[j], ah[p & 1], bq[ks].x, bq[ks].y);
                 }
             }
         }
@@ -426,16 +432,17 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
         } else {
             float2* __restrict__ outc = reinterpret_cast<float2*>(a.out) + ch * a.out_stride + ob;
             const long long left_c = a.out_n - ob;
-            const bool st16 = (reinterpret_cast<unsigned long long>(outc) & 15ull) == 0;
+            if ((reinterpret_cast<unsigned long long>(outc) & 15ull) == 0 && left_c >= BT) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int o = (j + 8 * g) * 8 + 2 * t;
-                const float4 y = make_float4(acc[j][0] * inv, acc[j][2] * inv, acc[j][1] * inv, acc[j][3] * inv);
-                if (st16 && o + 1 < left_c) {
-                    *reinterpret_cast<float4*>(outc + o) = y;
-                } else {
-                    if (o < left_c) outc[o] = make_float2(y.x, y.y);
-                    if (o + 1 < left_c) outc[o + 1] = make_float2(y.z, y.w);
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(outc + (j + 8 * g) * 8 + 2 * t) =
+                        make_float4(acc[j][0] * inv, acc[j][2] * inv, acc[j][1] * inv, acc[j][3] * inv);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int o = (j + 8 * g) * 8 + 2 * t;
+                    if (o < left_c) outc[o] = make_float2(acc[j][0] * inv, acc[j][2] * inv);
+                    if (o + 1 < left_c) outc[o + 1] = make_float2(acc[j][1] * inv, acc[j][3] * inv);
                 }
             }
         }
