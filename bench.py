@@ -549,7 +549,8 @@ def run_gpu(args):
 
     if op in ("fir", "fir_demod") and f.uses_tensor_cores:
         # Declared: the real-tap c32 FIR runs as a block-scaled fp16x3 Toeplitz product on the tensor cores (fir_tc.cuh).
-        roofline["kernel"] = "fir_tc_kernel (block-scaled fp16x3 Toeplitz product, mma.m16n8k16 + ldmatrix" + (", fused demod epilogue)" if op == "fir_demod" else ")")
+        roofline["kernel"] = ("fir_tc1_kernel<KS>" if cfg["deci"] == 1 and cfg["ntaps"] <= 121 else "fir_tc_kernel") + \
+            " (block-scaled fp16x3 Toeplitz product on the tensor cores, mma.m16n8k16 + ldmatrix" + (", fused demod epilogue)" if op == "fir_demod" else ")")
         ks = (7 * cfg["deci"] + cfg["ntaps"] + 15) // 16             # k-steps of 16 at 8 outputs per block-row (lower bound)
         nout_fir = n_out + (cfg.get("nchan", 0) if op == "fir_demod" else 0)
         mmas = 3 * ks * nout_fir / 64                                 # three m16n8k16 per k-step per 64 complex outputs

@@ -21,6 +21,10 @@
 //
 // Roofline: FP32-FMA bound.  MACs per output: 4*T FFMA (complex taps),
 // 2*T (complex data, real taps), T (f32).  Bytes: 8*(N_in + N_out) c32.
+//
+// Real-tap c32 filters with ntaps/deci >= 32 (config 1) leave these FP32 kernels for the tensor-core
+// Toeplitz-block product in fir_tc.cuh (block-scaled fp16x3, FP32-class accuracy; plan_tc below picks the
+// geometry, rrc_fir_uses_tensor_cores declares it, RRC_FIR_NO_TENSOR keeps the kernels of this file).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
