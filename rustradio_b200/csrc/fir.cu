@@ -574,7 +574,7 @@ struct rrc_fir {
     double ratio = 0.0;
     unsigned long long out_counter = 0;
     int in_u8 = 0;               // inputs are u8 I/Q pairs (rrc_fir_set_input_u8iq; c32 filters only)
-    // tensor-core Toeplitz kernel (fir_tc.cuh): c32 samples, real taps, no translate, c32 input
+    // tensor-core Toeplitz kernel (fir_tc.cuh): c32 samples (c32 or u8 I/Q input), real taps, no translate
     bool tc = false;
     int tc_ntile = 1, tc_nld = 9, tc_nm = 1, tc_wb = 0, tc_KS = 0, tc_RS = 0, tc_PAD = 0, tc_L = 0, tc_PL = 0;
     unsigned tc_magic = 0;
@@ -732,9 +732,9 @@ int launch_tc(const rrc_fir* h, const FirTcArgs& a, cudaStream_t st) {
     }
 }
 
-template <int KS, bool DEMOD>
-int launch_tc1_k(const rrc_fir* h, const FirTc1Args& a, cudaStream_t st) {
-    auto k = fir_tc1_kernel<KS, DEMOD>;
+template <int KS, bool DEMOD, bool U8>
+int launch_tc1_k2(const rrc_fir* h, const FirTc1Args& a, cudaStream_t st) {
+    auto k = fir_tc1_kernel<KS, DEMOD, U8>;
     const size_t smem = (size_t)(FIR_TC_THREADS / 32) * (FIR_TC1_WB + (DEMOD ? FIR_TC1_YB : 0));
     RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -747,13 +747,17 @@ int launch_tc1_k(const rrc_fir* h, const FirTc1Args& a, cudaStream_t st) {
     count_launch();
     return RRC_OK;
 }
+template <int KS, bool DEMOD>
+int launch_tc1_k(const rrc_fir* h, const FirTc1Args& a, cudaStream_t st) {
+    return a.in_u8 ? launch_tc1_k2<KS, DEMOD, true>(h, a, st) : launch_tc1_k2<KS, DEMOD, false>(h, a, st);
+}
 template <bool DEMOD>
 int launch_tc1(const rrc_fir* h, const FirTc1Args& a, cudaStream_t st) {
     switch (h->tc_KS) {
     case 2: return launch_tc1_k<2, DEMOD>(h, a, st);
     case 3: return launch_tc1_k<3, DEMOD>(h, a, st);
     case 4: return launch_tc1_k<4, DEMOD>(h, a, st);
-    case 5: return launch_tc1_k<5, DEMOD>(h, a, st);
+    case 5: return launch_tc1_k<5, DEMOD>(h, a, st);   // (4 CTAs per SM at 64 registers measured slower: 77.6 vs 62.8 us on config 1)
     case 6: return launch_tc1_k<6, DEMOD>(h, a, st);
     case 7: return launch_tc1_k<7, DEMOD>(h, a, st);
     case 8: return launch_tc1_k<8, DEMOD>(h, a, st);
@@ -926,7 +930,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
     a.in_u8 = h->in_u8;
     if (h->in_u8 && (reinterpret_cast<uintptr_t>(in) & 1)) return fail(RRC_ERR_INVALID, "u8 I/Q input must be 2-byte aligned");
 
-    if (h->tc && h->tc1 && !h->translate && !h->in_u8) {
+    if (h->tc && h->tc1 && !h->translate) {
         const size_t work = demod ? out_n - 1 : out_n;
         if (work == 0) return RRC_OK;
         FirTc1Args t{};
@@ -935,11 +939,11 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         t.taps_rev = reinterpret_cast<const float*>(h->taps_rev);
         t.in_stride = (long long)in_stride; t.out_stride = (long long)out_stride;
         t.need = (long long)need; t.out_n = (long long)out_n;
-        t.ntaps = (int)h->ntaps; t.gain = gain; t.tap_inv_scale = h->tc_tap_inv_scale;
+        t.ntaps = (int)h->ntaps; t.gain = gain; t.tap_inv_scale = h->tc_tap_inv_scale; t.in_u8 = h->in_u8;
         t.tiles_x = (long long)((work + FIR_TC1_BT - 1) / FIR_TC1_BT);
         t.total_tiles = t.tiles_x * (long long)nchan;
         RRC_TRY(demod ? launch_tc1<true>(h, t, st) : launch_tc1<false>(h, t, st));
-    } else if (h->tc && !h->translate && !h->in_u8) {
+    } else if (h->tc && !h->translate) {
         const size_t work = demod ? out_n - 1 : out_n;
         if (work == 0) return RRC_OK;
         FirTcArgs t{};
@@ -950,7 +954,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         t.need = (long long)need; t.out_n = (long long)out_n;
         t.ntaps = (int)h->ntaps; t.deci = (int)h->deci;
         t.RS = h->tc_RS; t.PAD = h->tc_PAD; t.magic = h->tc_magic; t.KS = h->tc_KS; t.NM = h->tc_nm; t.L = h->tc_L; t.PL = h->tc_PL; t.WB = h->tc_wb;
-        t.gain = gain; t.tap_inv_scale = h->tc_tap_inv_scale;
+        t.gain = gain; t.tap_inv_scale = h->tc_tap_inv_scale; t.in_u8 = h->in_u8;
         const size_t bt = (size_t)h->tc_nm * 8 * 8 * h->tc_ntile;
         t.tiles_x = (long long)((work + bt - 1) / bt);
         t.total_tiles = t.tiles_x * (long long)nchan;
@@ -1083,7 +1087,7 @@ int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes) {
 }
 int rrc_fir_uses_tensor_cores(const rrc_fir_t* h, int* yes) {
     if (!h || !yes) return fail(RRC_ERR_INVALID, "null argument");
-    *yes = (h->tc && !h->translate && !h->in_u8) ? 1 : 0;
+    *yes = (h->tc && !h->translate) ? 1 : 0;
     return RRC_OK;
 }
 int rrc_fir_set_input_u8iq(rrc_fir_t* h, int on) {

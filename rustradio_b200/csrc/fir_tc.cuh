@@ -56,6 +56,7 @@ struct FirTcArgs {
     int WB;                    // bytes of shared memory per warp (planes + ytile), multiple of 16
     float gain;
     float tap_inv_scale;       // 1 / (power of two the taps were multiplied by)
+    int in_u8;                 // 1: `in` is u8 I/Q pairs (RtlSdrDecode fused into the tile load; in_stride in samples)
 };
 
 constexpr int FIR_TC_THREADS = 256;
@@ -70,6 +71,32 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], const unsigned (&a)[4], u
     asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// u8 I/Q tile load (src/rtlsdr_decode.rs:35-43 fused, bit-identical to decoding first): the lane's sample pairs
+// e = lane + 32*u as one 32-bit word each (16-bit loads when the span is only 2-byte aligned or ragged); samples beyond
+// `avail` read as the byte pair (127, 127), which decodes to exactly 0.
+template <int NLD>
+__device__ __forceinline__ void tc_load_u8(const unsigned short* __restrict__ in8, long long avail, int npairs, int lane,
+                                           float4 (&v)[NLD]) {
+    const bool al4 = (reinterpret_cast<unsigned long long>(in8) & 3ull) == 0 && avail >= 2ll * npairs;
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+        const int e = lane + u * 32;
+        unsigned w = 0x7f7f7f7fu;
+        if (e < npairs) {
+            if (al4) {
+                w = __ldg(reinterpret_cast<const unsigned*>(in8) + e);
+            } else {
+                const long long s = 2ll * e;
+                const unsigned w0 = s < avail ? in8[s] : 0x7f7fu;
+                const unsigned w1 = s + 1 < avail ? in8[s + 1] : 0x7f7fu;
+                w = w0 | (w1 << 16);
+            }
+        }
+        const float2 p = decode_iq(w & 0xffffu), q = decode_iq(w >> 16);
+        v[u] = make_float4(p.x, p.y, q.x, q.y);
+    }
 }
 
 // (a, b) scaled f32 -> fp16x2 hi word and fp16x2 lo word (a in the lower half).
@@ -121,7 +148,9 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc_kernel(const FirTcAr
         {
             const float2* __restrict__ in = a.in + ch * a.in_stride + ob * a.deci;
             const long long avail = a.need - ob * a.deci;
-            if (avail >= a.L && (reinterpret_cast<unsigned long long>(in) & 15ull) == 0) {
+            if (a.in_u8) {
+                tc_load_u8<NLD>(reinterpret_cast<const unsigned short*>(a.in) + ch * a.in_stride + ob * a.deci, avail, npairs, lane, v);
+            } else if (avail >= a.L && (reinterpret_cast<unsigned long long>(in) & 15ull) == 0) {
 #pragma unroll
                 for (int u = 0; u < NLD; ++u) {
                     const int e = lane + u * 32;
@@ -277,6 +306,7 @@ struct FirTc1Args {
     long long tiles_x, total_tiles;
     int ntaps;
     float gain, tap_inv_scale;
+    int in_u8;                 // 1: `in` is u8 I/Q pairs (RtlSdrDecode fused into the tile load; in_stride in samples)
 };
 
 constexpr int FIR_TC1_BT = 512;            // outputs per warp tile: 8 m-tiles x 8 block-rows x 8 outputs
@@ -285,7 +315,7 @@ constexpr int FIR_TC1_PLW = 360;           // 32-bit words per plane: 10 chunks 
 constexpr int FIR_TC1_WB = 4 * FIR_TC1_PLW * 4;                        // plane bytes per warp (5760)
 constexpr int FIR_TC1_YB = (FIR_TC1_BT + 2) * 8;                       // ytile bytes per warp (demod only)
 
-template <int KS, bool DEMOD>
+template <int KS, bool DEMOD, bool U8>
 __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = FIR_TC_THREADS / 32;
@@ -320,7 +350,9 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
         {
             const float2* __restrict__ in = a.in + ch * a.in_stride + ob;
             const long long avail = a.need - ob;
-            if (avail >= L && (reinterpret_cast<unsigned long long>(in) & 15ull) == 0) {
+            if constexpr (U8) {
+                tc_load_u8<NLD>(reinterpret_cast<const unsigned short*>(a.in) + ch * a.in_stride + ob, avail, NP, lane, v);
+            } else if (avail >= L && (reinterpret_cast<unsigned long long>(in) & 15ull) == 0) {
 #pragma unroll
                 for (int u = 0; u < NLD; ++u) {
                     const int e = lane + u * 32;
@@ -341,7 +373,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
         }
         {   // the warp's NEXT tile -> L2 (one bulk prefetch), so that its loads are L2 hits one tile from now
             const long long nid = id + nworkers;
-            if (lane == 0 && nid < a.total_tiles) {
+            if (!U8 && lane == 0 && nid < a.total_tiles) {
                 const long long nch = nid / a.tiles_x;
                 const long long nob = (nid - nch * a.tiles_x) * BT;
                 const float2* nin = a.in + nch * a.in_stride + nob;
@@ -406,14 +438,21 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
                 ldsm4(ah[q & 1], ad);
                 ldsm4(al[q & 1], ad + PLW * 4);
             }
+            // term by term over the position's (m-tile, k-step) pairs: consecutive mma write different accumulators
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 const int j = p - 2 * ks;
-                if (j >= 0 && j < 8) {
-                    mma_f16(acc[j], al[p & 1], bq[ks].x, bq[ks].y);
-                    mma_f16(acc[j], ah[p & 1], bq[ks].z, bq[ks].w);
-                    mma_f16(acc[j], ah[p & 1], bq[ks].x, bq[ks].y);
-                }
+                if (j >= 0 && j < 8) mma_f16(acc[j], al[p & 1], bq[ks].x, bq[ks].y);
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int j = p - 2 * ks;
+                if (j >= 0 && j < 8) mma_f16(acc[j], ah[p & 1], bq[ks].z, bq[ks].w);
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int j = p - 2 * ks;
+                if (j >= 0 && j < 8) mma_f16(acc[j], ah[p & 1], bq[ks].x, bq[ks].y);
             }
         }
         // lane (g, t) of m-tile j holds (re, im) of outputs 2t, 2t+1 of block-row j + 8*g

@@ -183,11 +183,15 @@ def test_fir_tensor_core_stopband_dominated_input(R, monkeypatch):
 
 
 def test_fir_tensor_core_falls_back(R):
-    """translate, u8 I/Q input, complex taps, < 16 taps and f32 streams stay on the FP32 kernels."""
+    """translate, complex taps, short or strongly decimating filters and f32 streams stay on the FP32 kernels; u8 I/Q
+    input keeps the tensor path (decode fused into its tile load, tests/test_ingest.py)."""
     lp = O.low_pass_n(1.0, 0.1, 64)
     f = R.Fir(lp.astype(np.complex64))
     assert f.uses_tensor_cores
     f.set_input_u8iq(True)
+    assert f.uses_tensor_cores
+    f.set_input_u8iq(False)
+    f.set_translate(1.0, 0.1)
     assert not f.uses_tensor_cores
     assert not R.Fir(lp.astype(np.float32)).uses_tensor_cores
     assert not R.Fir(cplx_taps(64)).uses_tensor_cores
