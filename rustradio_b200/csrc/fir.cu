@@ -32,6 +32,8 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fir_common.cuh"
+#include "fir_tc.hpp"
 #include "pipeline.cuh"
 
 namespace rrc {
@@ -54,11 +56,6 @@ struct FirArgs {
     unsigned long long out_base;  // absolute index of out[0] (translate rotator)
     int in_u8;                    // 1: `in` is u8 I/Q pairs, decoded while the tile is staged (c32 filters only)
 };
-
-// RtlSdrDecode fused into the tile load (src/rtlsdr_decode.rs:35-43).
-__device__ __forceinline__ float2 decode_iq(unsigned int w) {
-    return make_float2(__fmul_rn(__fsub_rn((float)(w & 0xffu), 127.0f), 0.008f), __fmul_rn(__fsub_rn((float)(w >> 8), 127.0f), 0.008f));
-}
 
 __device__ __forceinline__ void mac(float2& acc, float2 h, float2 x) {
     acc.x = fmaf(h.x, x.x, acc.x);
@@ -92,35 +89,6 @@ __device__ __forceinline__ float2 apply_translate(const FirArgs& a, float2 y, lo
     return cmulf(y, rotator(a.ratio, k));
 }
 __device__ __forceinline__ float apply_translate(const FirArgs&, float y, long long) { return y; }
-
-// atan2 with |error| < 1e-6 rad over the whole plane (bar: 1e-4 rad): octant reduction to
-// q = min/max in [0,1], odd minimax polynomial of degree 15, then quadrant fix-ups.  About
-// half the instructions of libdevice's atan2f and no slow path.  atan2(0, 0) = 0 like libm.
-__device__ __forceinline__ float fast_atan2(float y, float x) {
-    const float ax = fabsf(x), ay = fabsf(y);
-    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    const float q = mx == 0.0f ? 0.0f : __fdividef(mn, mx);
-    const float s = q * q;
-    float r = -0.0040540580f;
-    r = fmaf(r, s, 0.0218612288f);
-    r = fmaf(r, s, -0.0559098861f);
-    r = fmaf(r, s, 0.0964200441f);
-    r = fmaf(r, s, -0.1390853351f);
-    r = fmaf(r, s, 0.1994653599f);
-    r = fmaf(r, s, -0.3332985605f);
-    r = fmaf(r, s, 0.9999993329f);
-    r = r * q;
-    if (ay > ax) r = 1.57079632679489662f - r;
-    if (x < 0.0f) r = 3.14159265358979324f - r;
-    return copysignf(r, y);
-}
-
-__device__ __forceinline__ float demod_pair(float2 a, float2 b, float gain) {
-    // conj(a) * b, then gain * atan2(im, re)  (src/quadrature_demod.rs:71-73,106-108)
-    float re = fmaf(a.x, b.x, a.y * b.y);
-    float im = fmaf(a.x, b.y, -(a.y * b.x));
-    return gain * fast_atan2(im, re);
-}
 
 template <int R>
 __device__ __forceinline__ void load_taps(const float2* tp, float2 (&h)[R]) {
@@ -552,8 +520,6 @@ __global__ void quad_demod_kernel(const float2* __restrict__ in, long long in_st
 
 }  // namespace rrc
 
-#include "fir_tc.cuh"
-
 using namespace rrc;
 
 struct rrc_fir {
@@ -578,7 +544,7 @@ struct rrc_fir {
     bool tc = false;
     int tc_ntile = 1, tc_nld = 9, tc_nm = 1, tc_wb = 0, tc_KS = 0, tc_RS = 0, tc_PAD = 0, tc_L = 0, tc_PL = 0;
     unsigned tc_magic = 0;
-    bool tc1 = false;            // deci == 1, <= 121 taps: fir_tc1_kernel (A fragments loaded once per warp tile)
+    bool tc1 = false;            // deci == 1, <= 249 taps: fir_tc1_kernel (A fragments loaded once per warp tile)
     float tc_tap_inv_scale = 1.0f;
     int tc_ctas_per_sm = 0;      // occupancy of the chosen instantiation (persistent grid), filled at first launch
     void* tc_bfrag = nullptr;
@@ -631,7 +597,7 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
     bool force = false;
     if (const char* e = getenv("RRC_FIR_TENSOR")) force = atoi(e) == 2;
     if (!force && T < 32 * D) return RRC_OK;
-    h->tc1 = D == 1 && ksteps(1) <= 8;
+    h->tc1 = D == 1 && ksteps(1) <= FIR_TC1_MAX_KS;
     if (const char* e = getenv("RRC_FIR_TC1")) if (atoi(e) == 0) h->tc1 = false;
     if (h->tc1) {
         h->tc = true;
@@ -702,67 +668,6 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
     RRC_CUDA(cudaMalloc(&h->tc_bfrag, frag.size() * sizeof(unsigned)));
     RRC_CUDA(cudaMemcpy(h->tc_bfrag, frag.data(), frag.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
     return RRC_OK;
-}
-
-template <int NTILE, bool DEMOD, int NLD>
-int launch_tc_k(const rrc_fir* h, const FirTcArgs& a, cudaStream_t st) {
-    auto k = fir_tc_kernel<NTILE, DEMOD, NLD>;
-    RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tc_smem));
-    int per_sm = 0;
-    RRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, FIR_TC_THREADS, h->tc_smem));
-    if (per_sm < 1) return fail(RRC_ERR_CUDA, "fir_tc: kernel does not fit an SM (%zu bytes of shared memory)", h->tc_smem);
-    const long long cap = (long long)sm_count(h->device) * per_sm;
-    const long long ctas = (a.total_tiles + FIR_TC_THREADS / 32 - 1) / (FIR_TC_THREADS / 32);
-    const unsigned grid = (unsigned)std::min<long long>(ctas, cap);
-    k<<<grid, FIR_TC_THREADS, h->tc_smem, st>>>(a);
-    RRC_CHECK_LAUNCH();
-    count_launch();
-    return RRC_OK;
-}
-template <bool DEMOD>
-int launch_tc(const rrc_fir* h, const FirTcArgs& a, cudaStream_t st) {
-    switch (h->tc_ntile * 100 + h->tc_nld) {
-    case 109: return launch_tc_k<1, DEMOD, 9>(h, a, st);
-    case 114: return launch_tc_k<1, DEMOD, 14>(h, a, st);
-    case 209: return launch_tc_k<2, DEMOD, 9>(h, a, st);
-    case 214: return launch_tc_k<2, DEMOD, 14>(h, a, st);
-    case 409: return launch_tc_k<4, DEMOD, 9>(h, a, st);
-    case 414: return launch_tc_k<4, DEMOD, 14>(h, a, st);
-    default: return fail(RRC_ERR_INVALID, "fir_tc: no kernel for ntile %d nld %d", h->tc_ntile, h->tc_nld);
-    }
-}
-
-template <int KS, bool DEMOD, bool U8>
-int launch_tc1_k2(const rrc_fir* h, const FirTc1Args& a, cudaStream_t st) {
-    auto k = fir_tc1_kernel<KS, DEMOD, U8>;
-    const size_t smem = (size_t)(FIR_TC_THREADS / 32) * (FIR_TC1_WB + (DEMOD ? FIR_TC1_YB : 0));
-    RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    RRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, FIR_TC_THREADS, smem));
-    if (per_sm < 1) return fail(RRC_ERR_CUDA, "fir_tc1: kernel does not fit an SM");
-    const long long cap = (long long)sm_count(h->device) * per_sm;
-    const long long ctas = (a.total_tiles + FIR_TC_THREADS / 32 - 1) / (FIR_TC_THREADS / 32);
-    k<<<(unsigned)std::min<long long>(ctas, cap), FIR_TC_THREADS, smem, st>>>(a);
-    RRC_CHECK_LAUNCH();
-    count_launch();
-    return RRC_OK;
-}
-template <int KS, bool DEMOD>
-int launch_tc1_k(const rrc_fir* h, const FirTc1Args& a, cudaStream_t st) {
-    return a.in_u8 ? launch_tc1_k2<KS, DEMOD, true>(h, a, st) : launch_tc1_k2<KS, DEMOD, false>(h, a, st);
-}
-template <bool DEMOD>
-int launch_tc1(const rrc_fir* h, const FirTc1Args& a, cudaStream_t st) {
-    switch (h->tc_KS) {
-    case 2: return launch_tc1_k<2, DEMOD>(h, a, st);
-    case 3: return launch_tc1_k<3, DEMOD>(h, a, st);
-    case 4: return launch_tc1_k<4, DEMOD>(h, a, st);
-    case 5: return launch_tc1_k<5, DEMOD>(h, a, st);   // (4 CTAs per SM at 64 registers measured slower: 77.6 vs 62.8 us on config 1)
-    case 6: return launch_tc1_k<6, DEMOD>(h, a, st);
-    case 7: return launch_tc1_k<7, DEMOD>(h, a, st);
-    case 8: return launch_tc1_k<8, DEMOD>(h, a, st);
-    default: return fail(RRC_ERR_INVALID, "fir_tc1: no kernel for %d k-steps", h->tc_KS);
-    }
 }
 
 // (Re)build the device tap tables from taps_host and pick the launch geometry.
@@ -942,7 +847,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         t.ntaps = (int)h->ntaps; t.gain = gain; t.tap_inv_scale = h->tc_tap_inv_scale; t.in_u8 = h->in_u8;
         t.tiles_x = (long long)((work + FIR_TC1_BT - 1) / FIR_TC1_BT);
         t.total_tiles = t.tiles_x * (long long)nchan;
-        RRC_TRY(demod ? launch_tc1<true>(h, t, st) : launch_tc1<false>(h, t, st));
+        RRC_TRY(fir_tc1_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0}, t, demod, st));
     } else if (h->tc && !h->translate) {
         const size_t work = demod ? out_n - 1 : out_n;
         if (work == 0) return RRC_OK;
@@ -958,7 +863,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         const size_t bt = (size_t)h->tc_nm * 8 * 8 * h->tc_ntile;
         t.tiles_x = (long long)((work + bt - 1) / bt);
         t.total_tiles = t.tiles_x * (long long)nchan;
-        RRC_TRY(demod ? launch_tc<true>(h, t, st) : launch_tc<false>(h, t, st));
+        RRC_TRY(fir_tc_launch(FirTcGeom{h->device, h->tc_ntile, h->tc_nld, h->tc_KS, h->tc_smem}, t, demod, st));
     } else if (h->use_poly) {
         a.taps = h->taps_poly;
         const size_t bt = (size_t)h->groups * h->R;

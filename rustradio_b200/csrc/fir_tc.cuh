@@ -35,31 +35,11 @@
 
 #include <cstdint>
 
+#include "fir_common.cuh"
+#include "fir_tc.hpp"
+
 namespace rrc {
 
-struct FirTcArgs {
-    const float2* in;
-    void* out;
-    const uint4* bfrag;        // [KS][NTILE][32] = {b_hi[0], b_hi[1], b_lo[0], b_lo[1]} per lane (scaled taps, fp16x2)
-    const float* taps_rev;     // w[j] in f32 (boundary output of the demod epilogue)
-    long long in_stride, out_stride, need, out_n;
-    long long tiles_x, total_tiles;
-    int ntaps, deci;
-    int RS;                    // samples per block-row = R * deci (a multiple of 8)
-    int PAD;                   // fp16 elements inserted after every RS staged samples (0 or 8): makes the
-                               // byte stride between block-rows an odd multiple of 16 -> conflict-free ldmatrix
-    unsigned magic;            // ceil(2^32 / RS): s / RS = umulhi(s, magic) for s < 2^16
-    int KS;                    // k-steps of 16
-    int NM;                    // m-tiles (8 block-rows each) per warp tile
-    int L;                     // staged samples per tile (multiple of 8, <= 64 * NLD)
-    int PL;                    // fp16 elements per plane (multiple of 8)
-    int WB;                    // bytes of shared memory per warp (planes + ytile), multiple of 16
-    float gain;
-    float tap_inv_scale;       // 1 / (power of two the taps were multiplied by)
-    int in_u8;                 // 1: `in` is u8 I/Q pairs (RtlSdrDecode fused into the tile load; in_stride in samples)
-};
-
-constexpr int FIR_TC_THREADS = 256;
 // NLD = float4 (two samples) a lane holds per tile: 9 -> warp tiles of <= 576 samples, 14 -> <= 896.
 
 __device__ __forceinline__ void ldsm4(unsigned (&r)[4], unsigned addr) {
@@ -293,45 +273,36 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc_kernel(const FirTcAr
 // mma operands as they are — a sliding two-entry window of single half fragments would save half of these
 // loads but needs 8 register moves per position to assemble the operands): 32 ldmatrix per 120 mma for
 // 64 taps instead of 80 ldmatrix + 40 B-fragment loads.
-// The loop is fully unrolled (KS is a template parameter), so every shared-memory offset is an immediate,
-// the B fragments (4*KS registers) stay in registers for the whole kernel, and the padded plane layout
+// The loop is fully unrolled (KS is a template parameter), so every shared-memory offset is an immediate; a B
+// fragment is alive for 8 consecutive positions, so a five-entry register window (one LDS.128 per k-step and
+// tile) holds all of them for any KS <= 16 (<= 249 taps); and the padded plane layout
 // (8 fp16 after every 64 samples -> 144-byte row stride) needs no index arithmetic anywhere:
 // the lane's sample pair u lands at word lane + 36*u.
-struct FirTc1Args {
-    const float2* in;
-    void* out;
-    const uint4* bfrag;        // [KS][32], NTILE = 1 layout
-    const float* taps_rev;
-    long long in_stride, out_stride, need, out_n;
-    long long tiles_x, total_tiles;
-    int ntaps;
-    float gain, tap_inv_scale;
-    int in_u8;                 // 1: `in` is u8 I/Q pairs (RtlSdrDecode fused into the tile load; in_stride in samples)
-};
-
-constexpr int FIR_TC1_BT = 512;            // outputs per warp tile: 8 m-tiles x 8 block-rows x 8 outputs
-constexpr int FIR_TC1_NLD = 10;            // float4 per lane: up to 640 staged samples (512 + 16*KS <= 640)
-constexpr int FIR_TC1_PLW = 360;           // 32-bit words per plane: 10 chunks of (64 + 8) fp16
-constexpr int FIR_TC1_WB = 4 * FIR_TC1_PLW * 4;                        // plane bytes per warp (5760)
-constexpr int FIR_TC1_YB = (FIR_TC1_BT + 2) * 8;                       // ytile bytes per warp (demod only)
+// Geometry of fir_tc1_kernel<KS>: staged samples, float4 per lane, 32-bit words per plane (chunks of 64 + 8 fp16),
+// bytes of planes / ytile per warp, dynamic shared memory per CTA.
+__host__ __device__ constexpr int fir_tc1_L(int KS) { return 512 + 16 * KS; }                // 504 + 16*KS for the product, 512 + ntaps for the demod boundary output
+__host__ __device__ constexpr int fir_tc1_nld(int KS) { return (fir_tc1_L(KS) / 2 + 31) / 32; }
+__host__ __device__ constexpr int fir_tc1_plw(int KS) { return (fir_tc1_L(KS) + 63) / 64 * 36; }
+constexpr int FIR_TC1_YB = (FIR_TC1_BT + 2) * 8;
+__host__ __device__ constexpr int fir_tc1_wb(int KS, bool demod) { return 4 * fir_tc1_plw(KS) * 4 + (demod ? FIR_TC1_YB : 0); }
+__host__ __device__ constexpr size_t fir_tc1_smem(int KS, bool demod) { return (size_t)KS * 512 + (size_t)(FIR_TC_THREADS / 32) * fir_tc1_wb(KS, demod); }
 
 template <int KS, bool DEMOD, bool U8>
 __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = FIR_TC_THREADS / 32;
     constexpr int BT = FIR_TC1_BT;
-    constexpr int L = 512 + 16 * KS;                       // staged samples per tile: 504 + 16*KS for the product, 512 + ntaps for the demod boundary output
+    constexpr int L = fir_tc1_L(KS);                       // staged samples per tile
     constexpr int NP = L / 2;                              // sample pairs
-    constexpr int NLD = FIR_TC1_NLD;
-    constexpr int PLW = FIR_TC1_PLW;
+    constexpr int NLD = fir_tc1_nld(KS);
+    constexpr int PLW = fir_tc1_plw(KS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* s_planes = smem_raw + (size_t)warp * (FIR_TC1_WB + (DEMOD ? FIR_TC1_YB : 0));
-    float2* s_y = reinterpret_cast<float2*>(s_planes + FIR_TC1_WB);
+    const uint4* s_b = reinterpret_cast<const uint4*>(smem_raw) + lane;    // B fragments: [KS][32] uint4, this lane's column
+    unsigned char* s_planes = smem_raw + (size_t)KS * 512 + (size_t)warp * fir_tc1_wb(KS, DEMOD);
+    float2* s_y = reinterpret_cast<float2*>(s_planes + 4 * PLW * 4);
     unsigned* pl0 = reinterpret_cast<unsigned*>(s_planes);
-
-    uint4 bq[KS];
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) bq[ks] = __ldg(a.bfrag + ks * 32 + lane);
+    for (int i = threadIdx.x; i < KS * 32; i += FIR_TC_THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = __ldg(a.bfrag + i);
+    __syncthreads();                                       // the only CTA barrier
 
     // ldmatrix lane address for the A operand of walk position p: matrix (lane >> 3) = {re @p, im @p, re @p+1, im @p+1}
     // of the hi planes (the lo plane of each follows it), row r = lane & 7 at 144 bytes.  Half fragment q sits at byte
@@ -428,8 +399,10 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
         unsigned ah[2][4], al[2][4];                       // A operands (hi, lo) of walk positions p, p + 1
+        uint4 bw[5];                                       // B fragments of the k-steps alive at p (<= 4) and the next one, slot ks % 5
         ldsm4(ah[0], lane_addr);
         ldsm4(al[0], lane_addr + PLW * 4);
+        bw[0] = s_b[0];
 #pragma unroll
         for (int p = 0; p <= 7 + 2 * (KS - 1); ++p) {
             if (p < 7 + 2 * (KS - 1)) {
@@ -438,21 +411,22 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
                 ldsm4(ah[q & 1], ad);
                 ldsm4(al[q & 1], ad + PLW * 4);
             }
+            if ((p & 1) == 0 && p / 2 + 1 < KS) bw[(p / 2 + 1) % 5] = s_b[(p / 2 + 1) * 32];   // first used at p + 2
             // term by term over the position's (m-tile, k-step) pairs: consecutive mma write different accumulators
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 const int j = p - 2 * ks;
-                if (j >= 0 && j < 8) mma_f16(acc[j], al[p & 1], bq[ks].x, bq[ks].y);
+                if (j >= 0 && j < 8) mma_f16(acc[j], al[p & 1], bw[ks % 5].x, bw[ks % 5].y);
             }
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 const int j = p - 2 * ks;
-                if (j >= 0 && j < 8) mma_f16(acc[j], ah[p & 1], bq[ks].z, bq[ks].w);
+                if (j >= 0 && j < 8) mma_f16(acc[j], ah[p & 1], bw[ks % 5].z, bw[ks % 5].w);
             }
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 const int j = p - 2 * ks;
-                if (j >= 0 && j < 8) mma_f16(acc[j], ah[p & 1], bq[ks].x, bq[ks].y);
+                if (j >= 0 && j < 8) mma_f16(acc[j], ah[p & 1], bw[ks % 5].x, bw[ks % 5].y);
             }
         }
         // lane (g, t) of m-tile j holds (re, im) of outputs 2t, 2t+1 of block-row j + 8*g

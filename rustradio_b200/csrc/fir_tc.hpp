@@ -1,0 +1,56 @@
+// fir_tc.hpp — argument structs and host entry points of the tensor-core FIR kernels (fir_tc.cuh / fir_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+namespace rrc {
+
+struct FirTcArgs {
+    const float2* in;
+    void* out;
+    const uint4* bfrag;        // [KS][NTILE][32] = {b_hi[0], b_hi[1], b_lo[0], b_lo[1]} per lane (scaled taps, fp16x2)
+    const float* taps_rev;     // w[j] in f32 (boundary output of the demod epilogue)
+    long long in_stride, out_stride, need, out_n;
+    long long tiles_x, total_tiles;
+    int ntaps, deci;
+    int RS;                    // samples per block-row = R * deci (a multiple of 8)
+    int PAD;                   // fp16 elements inserted after every RS staged samples (0 or 8): makes the
+                               // byte stride between block-rows an odd multiple of 16 -> conflict-free ldmatrix
+    unsigned magic;            // ceil(2^32 / RS): s / RS = umulhi(s, magic) for s < 2^16
+    int KS;                    // k-steps of 16
+    int NM;                    // m-tiles (8 block-rows each) per warp tile
+    int L;                     // staged samples per tile (multiple of 8, <= 64 * NLD)
+    int PL;                    // fp16 elements per plane (multiple of 8)
+    int WB;                    // bytes of shared memory per warp (planes + ytile), multiple of 16
+    float gain;
+    float tap_inv_scale;       // 1 / (power of two the taps were multiplied by)
+    int in_u8;                 // 1: `in` is u8 I/Q pairs (RtlSdrDecode fused into the tile load; in_stride in samples)
+};
+
+struct FirTc1Args {
+    const float2* in;
+    void* out;
+    const uint4* bfrag;        // [KS][32], NTILE = 1 layout
+    const float* taps_rev;
+    long long in_stride, out_stride, need, out_n;
+    long long tiles_x, total_tiles;
+    int ntaps;
+    float gain, tap_inv_scale;
+    int in_u8;                 // 1: `in` is u8 I/Q pairs (RtlSdrDecode fused into the tile load; in_stride in samples)
+};
+
+constexpr int FIR_TC_THREADS = 256;
+constexpr int FIR_TC1_BT = 512;            // outputs per warp tile of fir_tc1_kernel: 8 m-tiles x 8 block-rows x 8 outputs
+constexpr int FIR_TC1_MAX_KS = 16;         // deci == 1 kernel: up to 16 k-steps of 16 samples, i.e. <= 249 taps
+
+// What the launchers need to know about the filter (filled by plan_tc in fir.cu).
+struct FirTcGeom {
+    int device;
+    int ntile, nld, KS;
+    size_t smem;               // generic kernel: dynamic shared memory per CTA
+};
+int fir_tc_launch(const FirTcGeom& g, const FirTcArgs& a, bool demod, cudaStream_t st);
+int fir_tc1_launch(const FirTcGeom& g, const FirTc1Args& a, bool demod, cudaStream_t st);
+
+}  // namespace rrc

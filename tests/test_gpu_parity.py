@@ -115,9 +115,11 @@ def test_fir_tensor_core_geometries(R, monkeypatch, ntile, nld, nm, ntaps, deci,
 
 
 @pytest.mark.parametrize("ntaps,n,nchan", [(16, 5_000, 2), (33, 70_001, 1), (64, 262_144, 1), (64, 1_300, 5), (100, 40_000, 3),
-                                           (121, 20_011, 2), (17, 600, 1)])
+                                           (121, 20_011, 2), (17, 600, 1), (122, 9_000, 2), (137, 30_000, 1), (160, 5_555, 3),
+                                           (169, 20_000, 1), (185, 7_001, 2), (201, 12_345, 1), (217, 3_000, 2), (233, 40_001, 1),
+                                           (249, 25_000, 2)])
 def test_fir_tensor_core_deci1_kernel(R, monkeypatch, ntaps, n, nchan):
-    """fir_tc1_kernel (deci 1, <= 121 taps, every k-step count 2..8): plain and fused-demod epilogues, ragged last tiles,
+    """fir_tc1_kernel (deci 1, <= 249 taps, every k-step count 2..16): plain and fused-demod epilogues, ragged last tiles,
     tiles shorter than one warp tile, odd channel strides (8-byte aligned channels take the scalar loads/stores)."""
     if ntaps < 32:
         monkeypatch.setenv("RRC_FIR_TENSOR", "2")      # the planner leaves < 32 taps on the FP32 kernel
