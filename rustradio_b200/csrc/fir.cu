@@ -544,7 +544,7 @@ struct rrc_fir {
     bool tc = false;
     int tc_ntile = 1, tc_nld = 9, tc_nm = 1, tc_wb = 0, tc_KS = 0, tc_RS = 0, tc_PAD = 0, tc_L = 0, tc_PL = 0;
     unsigned tc_magic = 0;
-    bool tc1 = false;            // deci == 1, <= 249 taps: fir_tc1_kernel (A fragments loaded once per warp tile)
+    bool tc1 = false;            // deci 1/2/4, 7*deci + ntaps <= 320: fir_tc1_kernel (A fragments loaded once per warp tile)
     float tc_tap_inv_scale = 1.0f;
     int tc_ctas_per_sm = 0;      // occupancy of the chosen instantiation (persistent grid), filled at first launch
     void* tc_bfrag = nullptr;
@@ -597,11 +597,14 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
     bool force = false;
     if (const char* e = getenv("RRC_FIR_TENSOR")) force = atoi(e) == 2;
     if (!force && T < 32 * D) return RRC_OK;
-    h->tc1 = D == 1 && ksteps(1) <= FIR_TC1_MAX_KS;
+    // deci 1, 2, 4 and <= 16 k-steps: the walk kernel (even k-step counts only for deci 2 and 4: fewer instantiations,
+    // the extra k-step multiplies zero taps)
+    const int ks1 = (D == 1) ? ksteps(1) : ((ksteps(1) + 1) & ~1);
+    h->tc1 = (D == 1 || D == 2 || D == 4) && ks1 <= FIR_TC1_MAX_KS;
     if (const char* e = getenv("RRC_FIR_TC1")) if (atoi(e) == 0) h->tc1 = false;
     if (h->tc1) {
         h->tc = true;
-        h->tc_ntile = 1; h->tc_KS = ksteps(1);
+        h->tc_ntile = 1; h->tc_KS = ks1;
     }
     for (int pass = 0; pass < 2 && !h->tc; ++pass)
         for (int nt = ntile; nt >= 1 && !h->tc; nt >>= 1) {
@@ -845,9 +848,10 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         t.in_stride = (long long)in_stride; t.out_stride = (long long)out_stride;
         t.need = (long long)need; t.out_n = (long long)out_n;
         t.ntaps = (int)h->ntaps; t.gain = gain; t.tap_inv_scale = h->tc_tap_inv_scale; t.in_u8 = h->in_u8;
-        t.tiles_x = (long long)((work + FIR_TC1_BT - 1) / FIR_TC1_BT);
+        const size_t bt1 = FIR_TC1_BT / h->deci;
+        t.tiles_x = (long long)((work + bt1 - 1) / bt1);
         t.total_tiles = t.tiles_x * (long long)nchan;
-        RRC_TRY(fir_tc1_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0}, t, demod, st));
+        RRC_TRY(fir_tc1_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0, (int)h->deci}, t, demod, st));
     } else if (h->tc && !h->translate) {
         const size_t work = demod ? out_n - 1 : out_n;
         if (work == 0) return RRC_OK;
@@ -863,7 +867,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         const size_t bt = (size_t)h->tc_nm * 8 * 8 * h->tc_ntile;
         t.tiles_x = (long long)((work + bt - 1) / bt);
         t.total_tiles = t.tiles_x * (long long)nchan;
-        RRC_TRY(fir_tc_launch(FirTcGeom{h->device, h->tc_ntile, h->tc_nld, h->tc_KS, h->tc_smem}, t, demod, st));
+        RRC_TRY(fir_tc_launch(FirTcGeom{h->device, h->tc_ntile, h->tc_nld, h->tc_KS, h->tc_smem, (int)h->deci}, t, demod, st));
     } else if (h->use_poly) {
         a.taps = h->taps_poly;
         const size_t bt = (size_t)h->groups * h->R;

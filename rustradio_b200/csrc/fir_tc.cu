@@ -37,9 +37,9 @@ int launch_tc(const FirTcGeom& g, const FirTcArgs& a, cudaStream_t st) {
 }
 
 
-template <int KS, bool DEMOD, bool U8>
+template <int KS, bool DEMOD, bool U8, int D>
 int launch_tc1_k2(const FirTcGeom& g, const FirTc1Args& a, cudaStream_t st) {
-    auto k = fir_tc1_kernel<KS, DEMOD, U8>;
+    auto k = fir_tc1_kernel<KS, DEMOD, U8, D>;
     constexpr size_t smem = fir_tc1_smem(KS, DEMOD);
     RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -52,10 +52,26 @@ int launch_tc1_k2(const FirTcGeom& g, const FirTc1Args& a, cudaStream_t st) {
     count_launch();
     return RRC_OK;
 }
-template <int KS>
+template <int KS, int D>
 int launch_tc1_k(const FirTcGeom& g, const FirTc1Args& a, bool demod, cudaStream_t st) {
-    if (demod) return a.in_u8 ? launch_tc1_k2<KS, true, true>(g, a, st) : launch_tc1_k2<KS, true, false>(g, a, st);
-    return a.in_u8 ? launch_tc1_k2<KS, false, true>(g, a, st) : launch_tc1_k2<KS, false, false>(g, a, st);
+    if (demod) return a.in_u8 ? launch_tc1_k2<KS, true, true, D>(g, a, st) : launch_tc1_k2<KS, true, false, D>(g, a, st);
+    return a.in_u8 ? launch_tc1_k2<KS, false, true, D>(g, a, st) : launch_tc1_k2<KS, false, false, D>(g, a, st);
+}
+template <int D>
+int launch_tc1_even(const FirTcGeom& g, const FirTc1Args& a, bool demod, cudaStream_t st) {
+    switch (g.KS) {
+    case 2: return launch_tc1_k<2, D>(g, a, demod, st);
+    case 4: return launch_tc1_k<4, D>(g, a, demod, st);
+    case 6: return launch_tc1_k<6, D>(g, a, demod, st);
+    case 8: return launch_tc1_k<8, D>(g, a, demod, st);
+    case 10: return launch_tc1_k<10, D>(g, a, demod, st);
+    case 12: return launch_tc1_k<12, D>(g, a, demod, st);
+    case 14: return launch_tc1_k<14, D>(g, a, demod, st);
+    case 16: return launch_tc1_k<16, D>(g, a, demod, st);
+    case 18: return launch_tc1_k<18, D>(g, a, demod, st);
+    case 20: return launch_tc1_k<20, D>(g, a, demod, st);
+    default: return fail(RRC_ERR_INVALID, "fir_tc1: no deci-%d kernel for %d k-steps", D, g.KS);
+    }
 }
 
 }  // namespace
@@ -65,22 +81,29 @@ int fir_tc_launch(const FirTcGeom& g, const FirTcArgs& a, bool demod, cudaStream
 }
 
 int fir_tc1_launch(const FirTcGeom& g, const FirTc1Args& a, bool demod, cudaStream_t st) {
+    if (g.deci == 2) return launch_tc1_even<2>(g, a, demod, st);
+    if (g.deci == 4) return launch_tc1_even<4>(g, a, demod, st);
+    if (g.deci != 1) return fail(RRC_ERR_INVALID, "fir_tc1: deci %d", g.deci);
     switch (g.KS) {
-    case 2: return launch_tc1_k<2>(g, a, demod, st);
-    case 3: return launch_tc1_k<3>(g, a, demod, st);
-    case 4: return launch_tc1_k<4>(g, a, demod, st);
-    case 5: return launch_tc1_k<5>(g, a, demod, st);   // (4 CTAs per SM at 64 registers measured slower: 77.6 vs 62.8 us on config 1)
-    case 6: return launch_tc1_k<6>(g, a, demod, st);
-    case 7: return launch_tc1_k<7>(g, a, demod, st);
-    case 8: return launch_tc1_k<8>(g, a, demod, st);
-    case 9: return launch_tc1_k<9>(g, a, demod, st);
-    case 10: return launch_tc1_k<10>(g, a, demod, st);
-    case 11: return launch_tc1_k<11>(g, a, demod, st);
-    case 12: return launch_tc1_k<12>(g, a, demod, st);
-    case 13: return launch_tc1_k<13>(g, a, demod, st);
-    case 14: return launch_tc1_k<14>(g, a, demod, st);
-    case 15: return launch_tc1_k<15>(g, a, demod, st);
-    case 16: return launch_tc1_k<16>(g, a, demod, st);
+    case 2: return launch_tc1_k<2, 1>(g, a, demod, st);
+    case 3: return launch_tc1_k<3, 1>(g, a, demod, st);
+    case 4: return launch_tc1_k<4, 1>(g, a, demod, st);
+    case 5: return launch_tc1_k<5, 1>(g, a, demod, st);   // (4 CTAs per SM at 64 registers measured slower: 77.6 vs 62.8 us on config 1)
+    case 6: return launch_tc1_k<6, 1>(g, a, demod, st);
+    case 7: return launch_tc1_k<7, 1>(g, a, demod, st);
+    case 8: return launch_tc1_k<8, 1>(g, a, demod, st);
+    case 9: return launch_tc1_k<9, 1>(g, a, demod, st);
+    case 10: return launch_tc1_k<10, 1>(g, a, demod, st);
+    case 11: return launch_tc1_k<11, 1>(g, a, demod, st);
+    case 12: return launch_tc1_k<12, 1>(g, a, demod, st);
+    case 13: return launch_tc1_k<13, 1>(g, a, demod, st);
+    case 14: return launch_tc1_k<14, 1>(g, a, demod, st);
+    case 15: return launch_tc1_k<15, 1>(g, a, demod, st);
+    case 16: return launch_tc1_k<16, 1>(g, a, demod, st);
+    case 17: return launch_tc1_k<17, 1>(g, a, demod, st);
+    case 18: return launch_tc1_k<18, 1>(g, a, demod, st);
+    case 19: return launch_tc1_k<19, 1>(g, a, demod, st);
+    case 20: return launch_tc1_k<20, 1>(g, a, demod, st);
     default: return fail(RRC_ERR_INVALID, "fir_tc1: no kernel for %d k-steps", g.KS);
     }
 }

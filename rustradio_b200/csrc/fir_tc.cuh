@@ -261,7 +261,10 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc_kernel(const FirTcAr
     }
 }
 
-// ---- deci == 1 specialisation: every A fragment is loaded from shared memory ONCE per warp tile -------------
+// ---- deci 1, 2 and 4 specialisation: every A fragment is loaded from shared memory ONCE per warp tile -------
+// (written for deci == 1 below; for deci D in {2, 4} a warp tile has S = 8/D m-tiles, block-row b = j + S*r, so the row
+// pitch stays 64 samples and the whole layout is unchanged; the walk position of (m-tile j, k-step ks) is
+// q = D*j + 2*ks, even positions only, and a tile gives 64*S outputs from the same 512 + 16*KS staged samples)
 // The generic kernel above loads two ldmatrix.x4 (hi, lo) plus one B fragment per three mma: 12 shared-memory
 // wavefronts per 3 mma, and ncu showed the L1 data pipe at 80 % with the tensor pipe at 18 % on config 1
 // (profiles/r01_c1_tc_v4_ncu_summary.txt).  For deci == 1 (R = 8 outputs per block-row, RS = 8) the Toeplitz rows
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc_kernel(const FirTcAr
 // 64 taps instead of 80 ldmatrix + 40 B-fragment loads.
 // The loop is fully unrolled (KS is a template parameter), so every shared-memory offset is an immediate; a B
 // fragment is alive for 8 consecutive positions, so a five-entry register window (one LDS.128 per k-step and
-// tile) holds all of them for any KS <= 16 (<= 249 taps); and the padded plane layout
+// tile) holds all of them for any KS (instantiated up to 20: 7*deci + ntaps <= 320); and the padded plane layout
 // (8 fp16 after every 64 samples -> 144-byte row stride) needs no index arithmetic anywhere:
 // the lane's sample pair u lands at word lane + 36*u.
 // Geometry of fir_tc1_kernel<KS>: staged samples, float4 per lane, 32-bit words per plane (chunks of 64 + 8 fp16),
@@ -287,11 +290,15 @@ constexpr int FIR_TC1_YB = (FIR_TC1_BT + 2) * 8;
 __host__ __device__ constexpr int fir_tc1_wb(int KS, bool demod) { return 4 * fir_tc1_plw(KS) * 4 + (demod ? FIR_TC1_YB : 0); }
 __host__ __device__ constexpr size_t fir_tc1_smem(int KS, bool demod) { return (size_t)KS * 512 + (size_t)(FIR_TC_THREADS / 32) * fir_tc1_wb(KS, demod); }
 
-template <int KS, bool DEMOD, bool U8>
+template <int KS, bool DEMOD, bool U8, int D>
 __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1Args a) {
+    static_assert(D == 1 || D == 2 || D == 4, "fir_tc1_kernel: deci 1, 2 or 4");
+    constexpr int S = 8 / D;                               // m-tiles per warp tile: block-row b = j + S*r keeps the row pitch at 64 samples
+    constexpr int QL = (8 - D) + 2 * (KS - 1);             // last walk position; q = D*j + 2*ks
+    constexpr int QS = D == 1 ? 1 : 2;                     // even decimations only visit even positions
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = FIR_TC_THREADS / 32;
-    constexpr int BT = FIR_TC1_BT;
+    constexpr int BT = 64 * S;                             // outputs per warp tile (512 input samples + halo)
     constexpr int L = fir_tc1_L(KS);                       // staged samples per tile
     constexpr int NP = L / 2;                              // sample pairs
     constexpr int NLD = fir_tc1_nld(KS);
@@ -319,10 +326,10 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
         const long long ob = (id - ch * a.tiles_x) * BT;
         float4 v[NLD];
         {
-            const float2* __restrict__ in = a.in + ch * a.in_stride + ob;
-            const long long avail = a.need - ob;
+            const float2* __restrict__ in = a.in + ch * a.in_stride + ob * D;
+            const long long avail = a.need - ob * D;
             if constexpr (U8) {
-                tc_load_u8<NLD>(reinterpret_cast<const unsigned short*>(a.in) + ch * a.in_stride + ob, avail, NP, lane, v);
+                tc_load_u8<NLD>(reinterpret_cast<const unsigned short*>(a.in) + ch * a.in_stride + ob * D, avail, NP, lane, v);
             } else if (avail >= L && (reinterpret_cast<unsigned long long>(in) & 15ull) == 0) {
 #pragma unroll
                 for (int u = 0; u < NLD; ++u) {
@@ -347,8 +354,8 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
             if (!U8 && lane == 0 && nid < a.total_tiles) {
                 const long long nch = nid / a.tiles_x;
                 const long long nob = (nid - nch * a.tiles_x) * BT;
-                const float2* nin = a.in + nch * a.in_stride + nob;
-                if (a.need - nob >= L && (reinterpret_cast<unsigned long long>(nin) & 15ull) == 0)
+                const float2* nin = a.in + nch * a.in_stride + nob * D;
+                if (a.need - nob * D >= L && (reinterpret_cast<unsigned long long>(nin) & 15ull) == 0)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nin), "r"(L * 8) : "memory");
             }
         }
@@ -379,7 +386,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
             const __half* p16 = reinterpret_cast<const __half*>(s_planes);
             float re = 0.f, im = 0.f;
             for (int j = lane; j < a.ntaps; j += 32) {
-                const int s = BT + j;
+                const int s = BT * D + j;                  // = 512 + j
                 const int e = s + (s >> 6) * 8;
                 const float w = __ldg(a.taps_rev + j);
                 re = fmaf(__half2float(p16[e]) + __half2float(p16[e + 2 * PLW]), w, re);
@@ -393,9 +400,9 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
             if (lane == 0) s_y[BT] = make_float2(re * isc, im * isc);
         }
         // ---- Toeplitz product over the half-fragment walk ----
-        float acc[8][4];
+        float acc[S][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < S; ++j)
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
         unsigned ah[2][4], al[2][4];                       // A operands (hi, lo) of walk positions p, p + 1
@@ -404,37 +411,39 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
         ldsm4(al[0], lane_addr + PLW * 4);
         bw[0] = s_b[0];
 #pragma unroll
-        for (int p = 0; p <= 7 + 2 * (KS - 1); ++p) {
-            if (p < 7 + 2 * (KS - 1)) {
-                const int q = p + 1;
-                const unsigned ad = ((q & 7) == 7 ? lane_addr7 : lane_addr) + 16u * (unsigned)q + 16u * (unsigned)(q >> 3);
-                ldsm4(ah[q & 1], ad);
-                ldsm4(al[q & 1], ad + PLW * 4);
+        for (int p = 0; p <= QL; p += QS) {
+            const int cur = (p / QS) & 1;
+            if (p < QL) {
+                const int q = p + QS;
+                // second-half lanes (half fragment q + 1) cross a 64-sample chunk when (q + 1) % 8 == 0 (odd positions only)
+                const unsigned ad = (((q + 1) & 7) == 0 ? lane_addr7 : lane_addr) + 16u * (unsigned)q + 16u * (unsigned)(q >> 3);
+                ldsm4(ah[cur ^ 1], ad);
+                ldsm4(al[cur ^ 1], ad + PLW * 4);
             }
             if ((p & 1) == 0 && p / 2 + 1 < KS) bw[(p / 2 + 1) % 5] = s_b[(p / 2 + 1) * 32];   // first used at p + 2
             // term by term over the position's (m-tile, k-step) pairs: consecutive mma write different accumulators
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-                const int j = p - 2 * ks;
-                if (j >= 0 && j < 8) mma_f16(acc[j], al[p & 1], bw[ks % 5].x, bw[ks % 5].y);
+                const int dj = p - 2 * ks;
+                if (dj >= 0 && dj % D == 0 && dj / D < S) mma_f16(acc[dj / D], al[cur], bw[ks % 5].x, bw[ks % 5].y);
             }
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-                const int j = p - 2 * ks;
-                if (j >= 0 && j < 8) mma_f16(acc[j], ah[p & 1], bw[ks % 5].z, bw[ks % 5].w);
+                const int dj = p - 2 * ks;
+                if (dj >= 0 && dj % D == 0 && dj / D < S) mma_f16(acc[dj / D], ah[cur], bw[ks % 5].z, bw[ks % 5].w);
             }
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-                const int j = p - 2 * ks;
-                if (j >= 0 && j < 8) mma_f16(acc[j], ah[p & 1], bw[ks % 5].x, bw[ks % 5].y);
+                const int dj = p - 2 * ks;
+                if (dj >= 0 && dj % D == 0 && dj / D < S) mma_f16(acc[dj / D], ah[cur], bw[ks % 5].x, bw[ks % 5].y);
             }
         }
-        // lane (g, t) of m-tile j holds (re, im) of outputs 2t, 2t+1 of block-row j + 8*g
+        // lane (g, t) of m-tile j holds (re, im) of outputs 2t, 2t+1 of block-row j + S*g
         const int g = lane >> 2, t = lane & 3;
         if constexpr (DEMOD) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(s_y + (j + 8 * g) * 8 + 2 * t) =
+            for (int j = 0; j < S; ++j)
+                *reinterpret_cast<float4*>(s_y + (j + S * g) * 8 + 2 * t) =
                     make_float4(acc[j][0] * inv, acc[j][2] * inv, acc[j][1] * inv, acc[j][3] * inv);
             __syncwarp();
             float* __restrict__ out = reinterpret_cast<float*>(a.out) + ch * a.out_stride + ob;
@@ -447,13 +456,13 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
             const long long left_c = a.out_n - ob;
             if ((reinterpret_cast<unsigned long long>(outc) & 15ull) == 0 && left_c >= BT) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(outc + (j + 8 * g) * 8 + 2 * t) =
+                for (int j = 0; j < S; ++j)
+                    *reinterpret_cast<float4*>(outc + (j + S * g) * 8 + 2 * t) =
                         make_float4(acc[j][0] * inv, acc[j][2] * inv, acc[j][1] * inv, acc[j][3] * inv);
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int o = (j + 8 * g) * 8 + 2 * t;
+                for (int j = 0; j < S; ++j) {
+                    const int o = (j + S * g) * 8 + 2 * t;
                     if (o < left_c) outc[o] = make_float2(acc[j][0] * inv, acc[j][2] * inv);
                     if (o + 1 < left_c) outc[o + 1] = make_float2(acc[j][1] * inv, acc[j][3] * inv);
                 }

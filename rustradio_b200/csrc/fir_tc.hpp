@@ -41,14 +41,15 @@ struct FirTc1Args {
 };
 
 constexpr int FIR_TC_THREADS = 256;
-constexpr int FIR_TC1_BT = 512;            // outputs per warp tile of fir_tc1_kernel: 8 m-tiles x 8 block-rows x 8 outputs
-constexpr int FIR_TC1_MAX_KS = 16;         // deci == 1 kernel: up to 16 k-steps of 16 samples, i.e. <= 249 taps
+constexpr int FIR_TC1_BT = 512;            // INPUT samples a warp tile of fir_tc1_kernel advances by: 512/deci outputs
+constexpr int FIR_TC1_MAX_KS = 20;         // deci 1/2/4 kernel: up to 20 k-steps of 16 samples, i.e. 7*deci + ntaps <= 320
 
 // What the launchers need to know about the filter (filled by plan_tc in fir.cu).
 struct FirTcGeom {
     int device;
     int ntile, nld, KS;
     size_t smem;               // generic kernel: dynamic shared memory per CTA
+    int deci;                  // fir_tc1_kernel: 1, 2 or 4
 };
 int fir_tc_launch(const FirTcGeom& g, const FirTcArgs& a, bool demod, cudaStream_t st);
 int fir_tc1_launch(const FirTcGeom& g, const FirTc1Args& a, bool demod, cudaStream_t st);

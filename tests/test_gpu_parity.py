@@ -114,24 +114,28 @@ def test_fir_tensor_core_geometries(R, monkeypatch, ntile, nld, nm, ntaps, deci,
             assert O.max_angle_err(d[c] / 0.7, want) <= DEMOD_BAR
 
 
-@pytest.mark.parametrize("ntaps,n,nchan", [(16, 5_000, 2), (33, 70_001, 1), (64, 262_144, 1), (64, 1_300, 5), (100, 40_000, 3),
-                                           (121, 20_011, 2), (17, 600, 1), (122, 9_000, 2), (137, 30_000, 1), (160, 5_555, 3),
-                                           (169, 20_000, 1), (185, 7_001, 2), (201, 12_345, 1), (217, 3_000, 2), (233, 40_001, 1),
-                                           (249, 25_000, 2)])
-def test_fir_tensor_core_deci1_kernel(R, monkeypatch, ntaps, n, nchan):
-    """fir_tc1_kernel (deci 1, <= 249 taps, every k-step count 2..16): plain and fused-demod epilogues, ragged last tiles,
-    tiles shorter than one warp tile, odd channel strides (8-byte aligned channels take the scalar loads/stores)."""
-    if ntaps < 32:
-        monkeypatch.setenv("RRC_FIR_TENSOR", "2")      # the planner leaves < 32 taps on the FP32 kernel
-    taps = O.low_pass_n(1.0, 0.2, ntaps).astype(np.complex64)
-    f = R.Fir(taps)
+@pytest.mark.parametrize("ntaps,deci,n,nchan", [
+    (16, 1, 5_000, 2), (33, 1, 70_001, 1), (64, 1, 262_144, 1), (64, 1, 1_300, 5), (100, 1, 40_000, 3), (121, 1, 20_011, 2),
+    (17, 1, 600, 1), (122, 1, 9_000, 2), (137, 1, 30_000, 1), (160, 1, 5_555, 3), (169, 1, 20_000, 1), (185, 1, 7_001, 2),
+    (201, 1, 12_345, 1), (217, 1, 3_000, 2), (233, 1, 40_001, 1), (249, 1, 25_000, 2),
+    (18, 2, 4_000, 2), (64, 2, 100_001, 1), (127, 2, 33_333, 3), (180, 2, 9_999, 1), (242, 2, 50_000, 2),
+    (40, 4, 7_000, 1), (128, 4, 123_457, 1), (129, 4, 20_000, 3), (200, 4, 5_001, 2), (228, 4, 60_000, 1),
+    (255, 1, 31_000, 1), (270, 1, 8_000, 2), (290, 1, 22_222, 1), (313, 1, 10_000, 1), (255, 2, 40_000, 2), (306, 2, 9_000, 1),
+    (255, 4, 70_001, 1), (292, 4, 12_000, 2)])
+def test_fir_tensor_core_walk_kernel(R, monkeypatch, ntaps, deci, n, nchan):
+    """fir_tc1_kernel (deci 1, 2, 4; 7*deci + ntaps <= 320; every k-step count): plain and fused-demod epilogues, ragged
+    last tiles, tiles shorter than one warp tile, odd channel strides (8-byte aligned channels take the scalar loads/stores)."""
+    if ntaps < 32 * deci:
+        monkeypatch.setenv("RRC_FIR_TENSOR", "2")      # the planner leaves ntaps < 32*deci on the FP32 kernels
+    taps = O.low_pass_n(1.0, 0.2 / deci, ntaps).astype(np.complex64)
+    f = R.Fir(taps, deci=deci)
     assert f.uses_tensor_cores
     stride = n + 1 if n % 2 == 0 else n
     xs = np.zeros((nchan, stride), np.complex64)
     for c in range(nchan):
-        xs[c, :n] = O.synth_c32(300 + c, 0, n) * 0.5 + np.exp(2j * np.pi * 0.013 * (c + 1) * np.arange(n)).astype(np.complex64)
+        xs[c, :n] = O.synth_c32(300 + c, 0, n) * 0.5 + np.exp(2j * np.pi * 0.013 / deci * (c + 1) * np.arange(n)).astype(np.complex64)
     out_n = f.out_count(n)
-    need = (out_n - 1) + ntaps
+    need = (out_n - 1) * deci + ntaps
     din = R.DeviceBuffer.from_numpy(xs)
     ostride = out_n + 1 - (out_n % 2)
     dy = R.DeviceBuffer(nchan * ostride * 8)
@@ -141,9 +145,9 @@ def test_fir_tensor_core_deci1_kernel(R, monkeypatch, ntaps, n, nchan):
     f.demod_run_batch(din, stride, need, 0.7, dd, ostride, out_n, nchan)
     d = dd.download(np.float32, nchan * ostride).reshape(nchan, ostride)[:, :out_n - 1]
     for c in range(nchan):
-        truth = O.fir(xs[c, :n], taps, 1, f64=True)
-        e, e_ref = O.rel_rms(y[c], truth), O.rel_rms(O.fir(xs[c, :n], taps, 1), truth)
-        print(f"fir_tc1 T={ntaps} ch{c}: gpu {e:.2e}  f32-oracle {e_ref:.2e}")
+        truth = O.fir(xs[c, :n], taps, deci, f64=True)
+        e, e_ref = O.rel_rms(y[c], truth), O.rel_rms(O.fir(xs[c, :n], taps, deci), truth)
+        print(f"fir_tc1 T={ntaps} D={deci} ch{c}: gpu {e:.2e}  f32-oracle {e_ref:.2e}")
         assert e <= 2e-6
         assert O.max_angle_err(d[c] / 0.7, np.angle(truth[1:] * np.conj(truth[:-1]))) <= DEMOD_BAR
 
@@ -201,6 +205,7 @@ def test_fir_tensor_core_falls_back(R):
     # the planner keeps decimating short filters (config 3: 255 taps / 10) on the packed-FP32 kernel
     assert not R.Fir(O.low_pass_n(2.4e6, 100e3, 255).astype(np.complex64), deci=10).uses_tensor_cores
     assert R.Fir(O.low_pass_n(1.0, 0.1, 247).astype(np.complex64)).uses_tensor_cores
+    assert not R.Fir(O.low_pass_n(1.0, 0.1, 1025).astype(np.complex64)).uses_tensor_cores     # FftFilter territory
 
 
 def test_fir_huge_deci_falls_back(R):
