@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
 ( timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_ingest.py tests/test_blocks_gpu.py -m gpu -x -q -k "fir or Fir" -s ) > gpurun_out/pytest_fir_tc.log 2>&1; tail -2 gpurun_out/pytest_fir_tc.log
-grep "fir_tc1" gpurun_out/pytest_fir_tc.log | sort -k6 -g | tail -2
-timeout 600 python tools/fir_sweep.py 2>&1 | tail -20
+grep "fir_tcf.*tensor" gpurun_out/pytest_fir_tc.log | sort -k6 -g | tail -2
+timeout 600 python tools/fir_sweep.py --f32 2>&1 | tail -20

@@ -581,7 +581,7 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
     h->tc1 = false;
     if (h->tc_bfrag) { cudaFree(h->tc_bfrag); h->tc_bfrag = nullptr; }
     const size_t T = h->ntaps, D = h->deci;
-    if (!h->cplx || !h->real_taps || (h->flags & (RRC_FIR_NO_TENSOR | RRC_FIR_FORCE_GENERIC)) || T < 16 || D > 512) return RRC_OK;
+    if (!h->real_taps || (h->flags & (RRC_FIR_NO_TENSOR | RRC_FIR_FORCE_GENERIC)) || T < 16 || D > 512) return RRC_OK;
     if (const char* e = getenv("RRC_FIR_TENSOR")) if (atoi(e) == 0) return RRC_OK;
     for (float v : w) if (!std::isfinite(v)) return RRC_OK;
     auto ksteps = [&](int ntile) { return (int)(((size_t)(8 * ntile - 1) * D + T + 15) / 16); };
@@ -606,6 +606,7 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
         h->tc = true;
         h->tc_ntile = 1; h->tc_KS = ks1;
     }
+    if (!h->cplx && !h->tc1) return RRC_OK;               // f32 streams: walk kernel (fir_tcf_kernel) or FP32
     for (int pass = 0; pass < 2 && !h->tc; ++pass)
         for (int nt = ntile; nt >= 1 && !h->tc; nt >>= 1) {
             const int R = 8 * nt, KS = ksteps(nt);
@@ -746,7 +747,7 @@ int upload_taps(rrc_fir* h) {
             }
         }
     }
-    if (h->real_taps && h->cplx) RRC_TRY(plan_tc(h, rev));
+    if (h->real_taps) RRC_TRY(plan_tc(h, rev));
     else h->tc = false;
     return RRC_OK;
 }
@@ -838,7 +839,19 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
     a.in_u8 = h->in_u8;
     if (h->in_u8 && (reinterpret_cast<uintptr_t>(in) & 1)) return fail(RRC_ERR_INVALID, "u8 I/Q input must be 2-byte aligned");
 
-    if (h->tc && h->tc1 && !h->translate) {
+    if (h->tc && !h->cplx) {
+        if (demod) return fail(RRC_ERR_INVALID, "fused demod needs a c32 FIR");
+        FirTcfArgs t{};
+        t.in = reinterpret_cast<const float*>(in); t.out = reinterpret_cast<float*>(out);
+        t.bfrag = reinterpret_cast<const uint4*>(h->tc_bfrag);
+        t.in_stride = (long long)in_stride; t.out_stride = (long long)out_stride;
+        t.need = (long long)need; t.out_n = (long long)out_n;
+        t.tap_inv_scale = h->tc_tap_inv_scale;
+        const size_t btf = FIR_TCF_IN / h->deci;
+        t.tiles_x = (long long)((out_n + btf - 1) / btf);
+        t.total_tiles = t.tiles_x * (long long)nchan;
+        RRC_TRY(fir_tcf_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0, (int)h->deci}, t, st));
+    } else if (h->tc && h->tc1 && !h->translate) {
         const size_t work = demod ? out_n - 1 : out_n;
         if (work == 0) return RRC_OK;
         FirTc1Args t{};

@@ -74,7 +74,67 @@ int launch_tc1_even(const FirTcGeom& g, const FirTc1Args& a, bool demod, cudaStr
     }
 }
 
+template <int KS, int D>
+int launch_tcf_k(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st) {
+    auto k = fir_tcf_kernel<KS, D>;
+    constexpr size_t smem = fir_tcf_smem(KS);
+    RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    RRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, FIR_TC_THREADS, smem));
+    if (per_sm < 1) return fail(RRC_ERR_CUDA, "fir_tcf: kernel does not fit an SM");
+    const long long cap = (long long)sm_count(g.device) * per_sm;
+    const long long ctas = (a.total_tiles + FIR_TC_THREADS / 32 - 1) / (FIR_TC_THREADS / 32);
+    k<<<(unsigned)std::min<long long>(ctas, cap), FIR_TC_THREADS, smem, st>>>(a);
+    RRC_CHECK_LAUNCH();
+    count_launch();
+    return RRC_OK;
+}
+template <int D>
+int launch_tcf_even(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st) {
+    switch (g.KS) {
+    case 2: return launch_tcf_k<2, D>(g, a, st);
+    case 4: return launch_tcf_k<4, D>(g, a, st);
+    case 6: return launch_tcf_k<6, D>(g, a, st);
+    case 8: return launch_tcf_k<8, D>(g, a, st);
+    case 10: return launch_tcf_k<10, D>(g, a, st);
+    case 12: return launch_tcf_k<12, D>(g, a, st);
+    case 14: return launch_tcf_k<14, D>(g, a, st);
+    case 16: return launch_tcf_k<16, D>(g, a, st);
+    case 18: return launch_tcf_k<18, D>(g, a, st);
+    case 20: return launch_tcf_k<20, D>(g, a, st);
+    default: return fail(RRC_ERR_INVALID, "fir_tcf: no deci-%d kernel for %d k-steps", D, g.KS);
+    }
+}
+
 }  // namespace
+
+int fir_tcf_launch(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st) {
+    if (g.deci == 2) return launch_tcf_even<2>(g, a, st);
+    if (g.deci == 4) return launch_tcf_even<4>(g, a, st);
+    if (g.deci != 1) return fail(RRC_ERR_INVALID, "fir_tcf: deci %d", g.deci);
+    switch (g.KS) {
+    case 2: return launch_tcf_k<2, 1>(g, a, st);
+    case 3: return launch_tcf_k<3, 1>(g, a, st);
+    case 4: return launch_tcf_k<4, 1>(g, a, st);
+    case 5: return launch_tcf_k<5, 1>(g, a, st);
+    case 6: return launch_tcf_k<6, 1>(g, a, st);
+    case 7: return launch_tcf_k<7, 1>(g, a, st);
+    case 8: return launch_tcf_k<8, 1>(g, a, st);
+    case 9: return launch_tcf_k<9, 1>(g, a, st);
+    case 10: return launch_tcf_k<10, 1>(g, a, st);
+    case 11: return launch_tcf_k<11, 1>(g, a, st);
+    case 12: return launch_tcf_k<12, 1>(g, a, st);
+    case 13: return launch_tcf_k<13, 1>(g, a, st);
+    case 14: return launch_tcf_k<14, 1>(g, a, st);
+    case 15: return launch_tcf_k<15, 1>(g, a, st);
+    case 16: return launch_tcf_k<16, 1>(g, a, st);
+    case 17: return launch_tcf_k<17, 1>(g, a, st);
+    case 18: return launch_tcf_k<18, 1>(g, a, st);
+    case 19: return launch_tcf_k<19, 1>(g, a, st);
+    case 20: return launch_tcf_k<20, 1>(g, a, st);
+    default: return fail(RRC_ERR_INVALID, "fir_tcf: no kernel for %d k-steps", g.KS);
+    }
+}
 
 int fir_tc_launch(const FirTcGeom& g, const FirTcArgs& a, bool demod, cudaStream_t st) {
     return demod ? launch_tc<true>(g, a, st) : launch_tc<false>(g, a, st);

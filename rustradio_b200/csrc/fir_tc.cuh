@@ -472,4 +472,148 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
     }
 }
 
+// ---- f32 streams (FirFilter<Float>): the same walk with 16 block-rows per m-tile ------------------------------
+// Real samples have no re/im pairing, so the 16 rows of an mma A tile are 16 block-rows (b = j + S*r, r < 16) and a
+// warp tile gives 128*S outputs from 1024 + 16*KS staged samples; two planes (hi, lo) with the same chunk layout
+// (8 fp16 after every 64 samples, 144-byte row pitch).  The ldmatrix matrices of walk position q are
+// {rows 0-7 @q, rows 8-15 @q, rows 0-7 @q+1, rows 8-15 @q+1}; a lane's accumulators are outputs 2t, 2t+1 of
+// block-rows j + S*g and j + S*(g+8).  B fragments are the c32 kernel's (same taps, same Toeplitz matrix).
+__host__ __device__ constexpr int fir_tcf_L(int KS) { return 1024 + 16 * KS; }
+__host__ __device__ constexpr int fir_tcf_nld(int KS) { return (fir_tcf_L(KS) / 4 + 31) / 32; }
+__host__ __device__ constexpr int fir_tcf_plw(int KS) { return (fir_tcf_L(KS) + 63) / 64 * 36; }
+__host__ __device__ constexpr size_t fir_tcf_smem(int KS) { return (size_t)KS * 512 + (size_t)(FIR_TC_THREADS / 32) * 2 * fir_tcf_plw(KS) * 4; }
+
+template <int KS, int D>
+__global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tcf_kernel(const FirTcfArgs a) {
+    static_assert(D == 1 || D == 2 || D == 4, "fir_tcf_kernel: deci 1, 2 or 4");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = FIR_TC_THREADS / 32;
+    constexpr int S = 8 / D;
+    constexpr int QL = (8 - D) + 2 * (KS - 1);
+    constexpr int QS = D == 1 ? 1 : 2;
+    constexpr int BT = 128 * S;                            // outputs per warp tile (1024 input samples + halo)
+    constexpr int L = fir_tcf_L(KS);
+    constexpr int NQ = L / 4;                              // float4 units
+    constexpr int NLD = fir_tcf_nld(KS);
+    constexpr int PLW = fir_tcf_plw(KS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint4* s_b = reinterpret_cast<const uint4*>(smem_raw) + lane;
+    unsigned char* s_planes = smem_raw + (size_t)KS * 512 + (size_t)warp * (2 * PLW * 4);
+    unsigned* pl0 = reinterpret_cast<unsigned*>(s_planes);
+    for (int i = threadIdx.x; i < KS * 32; i += FIR_TC_THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = __ldg(a.bfrag + i);
+    __syncthreads();                                       // the only CTA barrier
+
+    const int mat = lane >> 3;
+    const unsigned lane_addr = (unsigned)__cvta_generic_to_shared(s_planes) + (unsigned)((lane & 7) + 8 * (mat & 1)) * 144u +
+                               (unsigned)(mat >> 1) * 16u;
+    const unsigned lane_addr7 = lane_addr + (unsigned)(mat >> 1) * 16u;
+    // the lane's four samples 4*lane + 128*u sit in chunk 2*u + (lane >> 4): word 2*lane + 4*(lane >> 4) + 72*u
+    unsigned* lane_w = pl0 + 2 * lane + 4 * (lane >> 4);
+
+    const long long nworkers = (long long)gridDim.x * NW;
+    for (long long id = (long long)blockIdx.x * NW + warp; id < a.total_tiles; id += nworkers) {
+        const long long ch = id / a.tiles_x;
+        const long long ob = (id - ch * a.tiles_x) * BT;
+        float4 v[NLD];
+        {
+            const float* __restrict__ in = a.in + ch * a.in_stride + ob * D;
+            const long long avail = a.need - ob * D;
+            if (avail >= L && (reinterpret_cast<unsigned long long>(in) & 15ull) == 0) {
+#pragma unroll
+                for (int u = 0; u < NLD; ++u) {
+                    const int e = lane + u * 32;
+                    v[u] = e < NQ ? __ldg(reinterpret_cast<const float4*>(in) + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < NLD; ++u) {
+                    const long long s = 4ll * (lane + u * 32);
+                    v[u].x = (s < L && s < avail) ? __ldg(in + s) : 0.f;
+                    v[u].y = (s + 1 < L && s + 1 < avail) ? __ldg(in + s + 1) : 0.f;
+                    v[u].z = (s + 2 < L && s + 2 < avail) ? __ldg(in + s + 2) : 0.f;
+                    v[u].w = (s + 3 < L && s + 3 < avail) ? __ldg(in + s + 3) : 0.f;
+                }
+            }
+        }
+        float mx = 0.f;
+#pragma unroll
+        for (int u = 0; u < NLD; ++u)
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+        const unsigned ex = __reduce_max_sync(0xffffffffu, __float_as_uint(mx)) >> 23;
+        const bool scaled = ex >= 14u && ex < 255u;
+        const float sc = scaled ? __uint_as_float((267u - ex) << 23) : 1.0f;
+        const float inv = (scaled ? __uint_as_float((ex - 13u) << 23) : 1.0f) * a.tap_inv_scale;
+#pragma unroll
+        for (int u = 0; u < NLD; ++u) {
+            if (lane + u * 32 < NQ) {
+                unsigned h0, l0, h1, l1;
+                split2(v[u].x * sc, v[u].y * sc, h0, l0);
+                split2(v[u].z * sc, v[u].w * sc, h1, l1);
+                unsigned* w = lane_w + 72 * u;
+                *reinterpret_cast<uint2*>(w) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(w + PLW) = make_uint2(l0, l1);
+            }
+        }
+        __syncwarp();
+        float acc[S][4];
+#pragma unroll
+        for (int j = 0; j < S; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
+        unsigned ah[2][4], al[2][4];
+        uint4 bw[5];
+        ldsm4(ah[0], lane_addr);
+        ldsm4(al[0], lane_addr + PLW * 4);
+        bw[0] = s_b[0];
+#pragma unroll
+        for (int p = 0; p <= QL; p += QS) {
+            const int cur = (p / QS) & 1;
+            if (p < QL) {
+                const int q = p + QS;
+                const unsigned ad = (((q + 1) & 7) == 0 ? lane_addr7 : lane_addr) + 16u * (unsigned)q + 16u * (unsigned)(q >> 3);
+                ldsm4(ah[cur ^ 1], ad);
+                ldsm4(al[cur ^ 1], ad + PLW * 4);
+            }
+            if ((p & 1) == 0 && p / 2 + 1 < KS) bw[(p / 2 + 1) % 5] = s_b[(p / 2 + 1) * 32];
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int dj = p - 2 * ks;
+                if (dj >= 0 && dj % D == 0 && dj / D < S) mma_f16(acc[dj / D], al[cur], bw[ks % 5].x, bw[ks % 5].y);
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int dj = p - 2 * ks;
+                if (dj >= 0 && dj % D == 0 && dj / D < S) mma_f16(acc[dj / D], ah[cur], bw[ks % 5].z, bw[ks % 5].w);
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int dj = p - 2 * ks;
+                if (dj >= 0 && dj % D == 0 && dj / D < S) mma_f16(acc[dj / D], ah[cur], bw[ks % 5].x, bw[ks % 5].y);
+            }
+        }
+        // lane (g, t) of m-tile j: outputs 2t, 2t+1 of block-rows j + S*g (c0, c1) and j + S*(g + 8) (c2, c3)
+        const int g = lane >> 2, t = lane & 3;
+        float* __restrict__ outp = a.out + ch * a.out_stride + ob;
+        const long long left = a.out_n - ob;
+        if ((reinterpret_cast<unsigned long long>(outp) & 7ull) == 0 && left >= BT) {
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const int o = (j + S * g) * 8 + 2 * t;
+                *reinterpret_cast<float2*>(outp + o) = make_float2(acc[j][0] * inv, acc[j][1] * inv);
+                *reinterpret_cast<float2*>(outp + o + 64 * S) = make_float2(acc[j][2] * inv, acc[j][3] * inv);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const int o = (j + S * g) * 8 + 2 * t;
+                if (o < left) outp[o] = acc[j][0] * inv;
+                if (o + 1 < left) outp[o + 1] = acc[j][1] * inv;
+                if (o + 64 * S < left) outp[o + 64 * S] = acc[j][2] * inv;
+                if (o + 64 * S + 1 < left) outp[o + 64 * S + 1] = acc[j][3] * inv;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace rrc

@@ -40,8 +40,18 @@ struct FirTc1Args {
     int in_u8;                 // 1: `in` is u8 I/Q pairs (RtlSdrDecode fused into the tile load; in_stride in samples)
 };
 
+struct FirTcfArgs {
+    const float* in;
+    float* out;
+    const uint4* bfrag;        // [KS][32], NTILE = 1 layout
+    long long in_stride, out_stride, need, out_n;
+    long long tiles_x, total_tiles;
+    float tap_inv_scale;
+};
+
 constexpr int FIR_TC_THREADS = 256;
 constexpr int FIR_TC1_BT = 512;            // INPUT samples a warp tile of fir_tc1_kernel advances by: 512/deci outputs
+constexpr int FIR_TCF_IN = 1024;           // INPUT samples a warp tile of fir_tcf_kernel (f32 streams) advances by
 constexpr int FIR_TC1_MAX_KS = 20;         // deci 1/2/4 kernel: up to 20 k-steps of 16 samples, i.e. 7*deci + ntaps <= 320
 
 // What the launchers need to know about the filter (filled by plan_tc in fir.cu).
@@ -53,5 +63,6 @@ struct FirTcGeom {
 };
 int fir_tc_launch(const FirTcGeom& g, const FirTcArgs& a, bool demod, cudaStream_t st);
 int fir_tc1_launch(const FirTcGeom& g, const FirTc1Args& a, bool demod, cudaStream_t st);
+int fir_tcf_launch(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st);
 
 }  // namespace rrc

@@ -152,6 +152,38 @@ def test_fir_tensor_core_walk_kernel(R, monkeypatch, ntaps, deci, n, nchan):
         assert O.max_angle_err(d[c] / 0.7, np.angle(truth[1:] * np.conj(truth[:-1]))) <= DEMOD_BAR
 
 
+@pytest.mark.parametrize("ntaps,deci,n,nchan", [
+    (32, 1, 10_000, 2), (64, 1, 300_001, 1), (65, 1, 1_500, 3), (100, 1, 2_049, 1), (247, 1, 50_000, 2), (313, 1, 70_000, 1),
+    (20, 1, 3_000, 1), (64, 2, 100_003, 1), (127, 2, 9_000, 2), (255, 2, 40_000, 1), (306, 2, 8_191, 1),
+    (128, 4, 200_000, 1), (255, 4, 33_333, 2), (292, 4, 5_000, 1), (50, 4, 6_000, 1)])
+def test_fir_tensor_core_f32_streams(R, monkeypatch, ntaps, deci, n, nchan):
+    """fir_tcf_kernel (FirFilter<Float>, deci 1/2/4, 7*deci + ntaps <= 320): against the f64 truth and the FP32 kernel,
+    ragged last tiles, odd channel strides (4-byte aligned channels take the scalar loads and stores)."""
+    if ntaps < 32 * deci:
+        monkeypatch.setenv("RRC_FIR_TENSOR", "2")
+    taps = O.low_pass_n(1.0, 0.2 / deci, ntaps)
+    f = R.Fir(taps, deci=deci)
+    f32 = R.Fir(taps, deci=deci, flags=R.RRC_FIR_NO_TENSOR)
+    assert f.uses_tensor_cores and not f32.uses_tensor_cores and not f.cplx
+    stride = n + 1 if n % 2 == 0 else n
+    xs = np.zeros((nchan, stride), np.float32)
+    for c in range(nchan):
+        xs[c, :n] = O.synth_f32(400 + c, 0, n) * 0.5 + np.cos(2 * np.pi * 0.013 / deci * (c + 1) * np.arange(n)).astype(np.float32)
+    out_n = f.out_count(n)
+    need = (out_n - 1) * deci + ntaps
+    din = R.DeviceBuffer.from_numpy(xs)
+    ostride = out_n + 1 - (out_n % 2)
+    for filt in (f, f32):
+        dy = R.DeviceBuffer(nchan * ostride * 4)
+        filt.run_batch(din, stride, need, dy, ostride, out_n, nchan)
+        y = dy.download(np.float32, nchan * ostride).reshape(nchan, ostride)[:, :out_n]
+        for c in range(nchan):
+            truth = O.fir(xs[c, :n], taps, deci, f64=True)
+            e = O.rel_rms(y[c], truth)
+            print(f"fir_tcf T={ntaps} D={deci} ch{c} {'tensor' if filt is f else 'fp32'}: {e:.2e}")
+            assert e <= 2e-6
+
+
 @pytest.mark.parametrize("scale", [1.0, 1e-20, 3e18, 0.0])
 def test_fir_tensor_core_block_scaling(R, scale):
     """The per-tile power-of-two scaling makes the fp16 split independent of the stream's level; a tile that is one
@@ -199,7 +231,8 @@ def test_fir_tensor_core_falls_back(R):
     f.set_input_u8iq(False)
     f.set_translate(1.0, 0.1)
     assert not f.uses_tensor_cores
-    assert not R.Fir(lp.astype(np.float32)).uses_tensor_cores
+    assert R.Fir(lp.astype(np.float32)).uses_tensor_cores                                    # f32 streams: fir_tcf_kernel
+    assert not R.Fir(lp.astype(np.float32), deci=3).uses_tensor_cores
     assert not R.Fir(cplx_taps(64)).uses_tensor_cores
     assert not R.Fir(O.low_pass_n(1.0, 0.1, 15).astype(np.complex64)).uses_tensor_cores
     # the planner keeps decimating short filters (config 3: 255 taps / 10) on the packed-FP32 kernel
