@@ -8,6 +8,20 @@
 namespace rrc {
 namespace {
 
+// Opt-in shared memory + occupancy of one kernel instantiation, queried once per device (the launchers run on every
+// work() call of a block).
+template <typename K>
+int ctas_per_sm(K k, size_t smem, int device, int* cache) {
+    if (device < 0 || device >= 16) device = 0;
+    if (cache[device] == 0) {
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, FIR_TC_THREADS, smem) != cudaSuccess) return -1;
+        cache[device] = per_sm > 0 ? per_sm : -1;
+    }
+    return cache[device];
+}
+
 template <int NTILE, bool DEMOD, int NLD>
 int launch_tc_k(const FirTcGeom& g, const FirTcArgs& a, cudaStream_t st) {
     auto k = fir_tc_kernel<NTILE, DEMOD, NLD>;
@@ -41,9 +55,8 @@ template <int KS, bool DEMOD, bool U8, int D>
 int launch_tc1_k2(const FirTcGeom& g, const FirTc1Args& a, cudaStream_t st) {
     auto k = fir_tc1_kernel<KS, DEMOD, U8, D>;
     constexpr size_t smem = fir_tc1_smem(KS, DEMOD);
-    RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    RRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, FIR_TC_THREADS, smem));
+    static int cache[16] = {};
+    const int per_sm = ctas_per_sm(k, smem, g.device, cache);
     if (per_sm < 1) return fail(RRC_ERR_CUDA, "fir_tc1: kernel does not fit an SM");
     const long long cap = (long long)sm_count(g.device) * per_sm;
     const long long ctas = (a.total_tiles + FIR_TC_THREADS / 32 - 1) / (FIR_TC_THREADS / 32);
@@ -78,9 +91,8 @@ template <int KS, int D>
 int launch_tcf_k(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st) {
     auto k = fir_tcf_kernel<KS, D>;
     constexpr size_t smem = fir_tcf_smem(KS);
-    RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    RRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, FIR_TC_THREADS, smem));
+    static int cache[16] = {};
+    const int per_sm = ctas_per_sm(k, smem, g.device, cache);
     if (per_sm < 1) return fail(RRC_ERR_CUDA, "fir_tcf: kernel does not fit an SM");
     const long long cap = (long long)sm_count(g.device) * per_sm;
     const long long ctas = (a.total_tiles + FIR_TC_THREADS / 32 - 1) / (FIR_TC_THREADS / 32);
