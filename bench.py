@@ -43,6 +43,16 @@ def cfg_c1():
                 desc="FirFilter c32 low-pass 64 taps, deci 1, 2^24 samples")
 
 
+def cfg_c1f():
+    return dict(name="c1f", op="fir", ntaps=64, deci=1, n=1 << 25, cutoff=0.1, dtype="f32",
+                desc="FirFilter<Float> f32 low-pass 64 taps, deci 1, 2^25 f32 samples (config 1's bytes as a real stream)")
+
+
+def cfg_c1d2():
+    return dict(name="c1d2", op="fir", ntaps=127, deci=2, n=1 << 24, cutoff=0.2, dtype="c32",
+                desc="FirFilter c32 low-pass 127 taps, deci 2, 2^24 samples (half-band decimator shape)")
+
+
 def cfg_c2():
     return dict(name="c2", op="fftfilt", ntaps=4097, n=1 << 28, cutoff=0.05, dtype="c32",
                 desc="FftFilter 4097-tap low-pass, 2^28 c32 samples, single stream per GPU")
@@ -115,7 +125,7 @@ def cfg_e4():
     return dict(name="e4", op="iqbalance", n=1 << 29, dtype="c32", desc="IqBalance alpha=2.08e-6 (tau 0.2 s @2.4 Msps), 2^29 c32 samples")
 
 
-CONFIGS = {"h1": cfg_h1, "e1": cfg_e1, "e2": cfg_e2, "e3": cfg_e3, "e4": cfg_e4, "a12": cfg_a12, "f2": cfg_f2, "c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4, "c5": cfg_c5, "c3u8": cfg_c3u8, "c5u8": cfg_c5u8, "f1": cfg_f1}
+CONFIGS = {"c1f": cfg_c1f, "c1d2": cfg_c1d2, "h1": cfg_h1, "e1": cfg_e1, "e2": cfg_e2, "e3": cfg_e3, "e4": cfg_e4, "a12": cfg_a12, "f2": cfg_f2, "c1": cfg_c1, "c2": cfg_c2, "c3": cfg_c3, "c4": cfg_c4, "c5": cfg_c5, "c3u8": cfg_c3u8, "c5u8": cfg_c5u8, "f1": cfg_f1}
 
 
 def low_pass_taps(ntaps: int, cutoff: float) -> np.ndarray:
@@ -136,12 +146,15 @@ def low_pass_taps(ntaps: int, cutoff: float) -> np.ndarray:
 def taps_for(cfg):
     if cfg["op"] == "fir_demod":
         return low_pass_taps(cfg["ntaps"], 100e3 / 2.4e6).astype(np.complex64)
-    return low_pass_taps(cfg["ntaps"], cfg["cutoff"]).astype(np.complex64)
+    t = low_pass_taps(cfg["ntaps"], cfg["cutoff"])
+    return t if (cfg["op"] == "fir" and cfg["dtype"] == "f32") else t.astype(np.complex64)
 
 
 def alg_bytes(cfg, n_in, n_out):
     """algorithmic bytes per step."""
     ib = 2 if cfg.get("in_u8") else 8
+    if cfg["op"] == "fir" and cfg["dtype"] == "f32":
+        return 4 * n_in + 4 * n_out
     if cfg["op"] in ("fir", "fftfilt", "fftfilt_decim"):
         return ib * n_in + 8 * n_out
     if cfg["op"] == "fir_demod":
@@ -170,7 +183,7 @@ def alg_flops(cfg, n_in, n_out, fir=None):
     fast path is active); FFT filter: blocks*(2*5*F*log2 F + 6F + 2*ntaps) at the reference's F."""
     op = cfg["op"]
     if op in ("fir", "fir_demod"):
-        per = 4 if (fir is not None and fir.uses_real_taps) else 8
+        per = 2 if cfg["dtype"] == "f32" else 4 if (fir is not None and fir.uses_real_taps) else 8
         nout = n_out + (cfg.get("nchan", 0) if op == "fir_demod" else 0)      # FIR outputs = demod outputs + 1 per channel
         return per * cfg["ntaps"] * nout
     if op in ("fftfilt", "fftfilt_decim", "fftfilt_real"):
@@ -357,9 +370,10 @@ def run_gpu(args):
         f = R.Fir(taps_for(cfg), deci=cfg["deci"], device=dev)
         n_out = f.out_count(n)
         n_in = n
-        din = torch.empty(2 * n, dtype=torch.float32, device=f"cuda:{dev}")
-        dout = torch.empty(2 * n_out, dtype=torch.float32, device=f"cuda:{dev}")
-        R.synth_f32(din, seed, 0, 2 * n, dev, stream)
+        fl = 1 if cfg["dtype"] == "f32" else 2                # floats per sample
+        din = torch.empty(fl * n, dtype=torch.float32, device=f"cuda:{dev}")
+        dout = torch.empty(fl * n_out, dtype=torch.float32, device=f"cuda:{dev}")
+        R.synth_f32(din, seed, 0, fl * n, dev, stream)
 
         def step():
             f.run(din, n, dout, n_out, stream)
@@ -488,7 +502,7 @@ def run_gpu(args):
     # ---- end to end: host buffers through *_run_host ----
     e2e = None
     if not args.no_e2e and op in ("fftfilt", "fir", "fftfilt_decim", "fft", "fftfilt_real") and scaling == "weak":
-        real = op == "fftfilt_real"
+        real = op == "fftfilt_real" or (op == "fir" and cfg["dtype"] == "f32")
         ib = 2 if u8 else 4 if real else 8
         ob = 4 if real else 8
         hin = R.PinnedBuffer(np.uint8 if u8 else np.float32 if real else np.complex64, cfg["n"] * (2 if u8 else 1))
@@ -549,7 +563,8 @@ def run_gpu(args):
 
     if op in ("fir", "fir_demod") and f.uses_tensor_cores:
         # Declared: the real-tap c32 FIR runs as a block-scaled fp16x3 Toeplitz product on the tensor cores (fir_tc.cuh).
-        roofline["kernel"] = ("fir_tc1_kernel<KS>" if cfg["deci"] == 1 and cfg["ntaps"] <= 121 else "fir_tc_kernel") + \
+        walk = cfg["deci"] in (1, 2, 4) and 7 * cfg["deci"] + cfg["ntaps"] <= 320
+        roofline["kernel"] = (("fir_tcf_kernel<KS,D>" if cfg["dtype"] == "f32" else "fir_tc1_kernel<KS,DEMOD,U8,D>") if walk else "fir_tc_kernel") + \
             " (block-scaled fp16x3 Toeplitz product on the tensor cores, mma.m16n8k16 + ldmatrix" + (", fused demod epilogue)" if op == "fir_demod" else ")")
         ks = (7 * cfg["deci"] + cfg["ntaps"] + 15) // 16             # k-steps of 16 at 8 outputs per block-row (lower bound)
         nout_fir = n_out + (cfg.get("nchan", 0) if op == "fir_demod" else 0)
@@ -612,9 +627,9 @@ def cpu_baseline(cfg, threads: int, budget_s: float):
         sample = f"{threads} x 2^21 c32 samples per repetition, overlap-add with F=16384 like the reference"
     elif op == "fir":
         per = 1 << 19
-        x = O.synth_c32(SEED + 1, 0, per)
+        x = O.synth_f32(SEED + 1, 0, per) if cfg["dtype"] == "f32" else O.synth_c32(SEED + 1, 0, per)
         fn = lambda i: len(O.fir(x, taps, cfg["deci"], fast=True))
-        sample = f"{threads} x 2^19 c32 samples per repetition"
+        sample = f"{threads} x 2^19 {cfg['dtype']} samples per repetition"
     elif op == "fir_demod":
         per = 240_000
         if cfg.get("in_u8"):
