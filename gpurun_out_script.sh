@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-( timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tensor_core_walk or tensor_core_f32 or tensor_core_geometries or fir_batch_and_fused" ) > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 gpurun_out/sanitizer_memcheck.log
-( timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tensor_core_walk and (64-1-1300 or 127-2 or 129-4) or tensor_core_f32 and (65-1 or 127-2) or tensor_core_geometries and 31-4" ) > gpurun_out/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 gpurun_out/sanitizer_racecheck.log
+( timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_ingest.py tests/test_blocks_gpu.py -m gpu -x -q -k "fir or Fir" -s ) > gpurun_out/pytest_fir_tc.log 2>&1; tail -3 gpurun_out/pytest_fir_tc.log
+grep "fir_tcc.*tensor" gpurun_out/pytest_fir_tc.log | sort -k6 -g | tail -2
+timeout 600 python tools/fir_sweep.py --ctaps 2>&1 | tail -20

@@ -22,9 +22,10 @@
 // Roofline: FP32-FMA bound.  MACs per output: 4*T FFMA (complex taps),
 // 2*T (complex data, real taps), T (f32).  Bytes: 8*(N_in + N_out) c32.
 //
-// Real-tap c32 filters with ntaps/deci >= 32 (config 1) leave these FP32 kernels for the tensor-core
-// Toeplitz-block product in fir_tc.cuh (block-scaled fp16x3, FP32-class accuracy; plan_tc below picks the
-// geometry, rrc_fir_uses_tensor_cores declares it, RRC_FIR_NO_TENSOR keeps the kernels of this file).
+// Filters with ntaps/deci >= 32 (config 1) leave these FP32 kernels for the tensor-core Toeplitz-block products
+// in fir_tc.cuh (real taps, c32 and f32 streams) and fir_tcc.cuh (complex taps / translate): block-scaled
+// fp16x3, FP32-class accuracy; plan_tc / plan_tc_cplx below pick the kernel, rrc_fir_uses_tensor_cores declares
+// it, RRC_FIR_NO_TENSOR keeps the kernels of this file.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -71,17 +72,6 @@ __device__ __forceinline__ void mac(float& acc, float h, float x) { acc = fmaf(h
 __device__ __forceinline__ void zero(float2& v) { v = make_float2(0.f, 0.f); }
 __device__ __forceinline__ void zero(float& v) { v = 0.f; }
 
-// exp(-j*2*pi*ratio*k) evaluated from the exact f64 angle.
-__device__ __forceinline__ float2 rotator(double ratio, unsigned long long k) {
-    double r = ratio * (double)k;
-    r -= rint(r);
-    double s, c;
-    sincospi(-2.0 * r, &s, &c);
-    return make_float2((float)c, (float)s);
-}
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
 // FirFilter translate epilogue: y[i] *= phi_i, phi_i = exp(-j*theta*((T-1) + i*D))
 // (src/fir.rs:453-462 closed form of the :464-473 recurrence).
 __device__ __forceinline__ float2 apply_translate(const FirArgs& a, float2 y, long long gi) {
@@ -544,6 +534,7 @@ struct rrc_fir {
     bool tc = false;
     int tc_ntile = 1, tc_nld = 9, tc_nm = 1, tc_wb = 0, tc_KS = 0, tc_RS = 0, tc_PAD = 0, tc_L = 0, tc_PL = 0;
     unsigned tc_magic = 0;
+    bool tc_cplx = false;        // complex taps (translate filters): fir_tcc_kernel
     bool tc1 = false;            // deci 1/2/4, 7*deci + ntaps <= 320: fir_tc1_kernel (A fragments loaded once per warp tile)
     float tc_tap_inv_scale = 1.0f;
     int tc_ctas_per_sm = 0;      // occupancy of the chosen instantiation (persistent grid), filled at first launch
@@ -579,6 +570,7 @@ float f16_to_f32(unsigned short b) {
 int plan_tc(rrc_fir* h, const std::vector<float>& w) {
     h->tc = false;
     h->tc1 = false;
+    h->tc_cplx = false;
     if (h->tc_bfrag) { cudaFree(h->tc_bfrag); h->tc_bfrag = nullptr; }
     const size_t T = h->ntaps, D = h->deci;
     if (!h->real_taps || (h->flags & (RRC_FIR_NO_TENSOR | RRC_FIR_FORCE_GENERIC)) || T < 16 || D > 512) return RRC_OK;
@@ -674,6 +666,55 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
     return RRC_OK;
 }
 
+// Complex taps (what translate() produces): B fragments of Re(w) and Im(w) for fir_tcc_kernel, one common scale.
+int plan_tc_cplx(rrc_fir* h, const std::vector<float>& w2) {       // w2: reversed taps, (re, im) interleaved
+    h->tc = false;
+    h->tc1 = false;
+    h->tc_cplx = false;
+    if (h->tc_bfrag) { cudaFree(h->tc_bfrag); h->tc_bfrag = nullptr; }
+    const size_t T = h->ntaps, D = h->deci;
+    if (!h->cplx || (h->flags & (RRC_FIR_NO_TENSOR | RRC_FIR_FORCE_GENERIC)) || T < 16) return RRC_OK;
+    bool force = false;
+    if (const char* e = getenv("RRC_FIR_TENSOR")) { if (atoi(e) == 0) return RRC_OK; force = atoi(e) == 2; }
+    if (!(D == 1 || D == 2 || D == 4) || (!force && T < 32 * D)) return RRC_OK;
+    for (float v : w2) if (!std::isfinite(v)) return RRC_OK;
+    int KS = (int)((7 * D + T + 15) / 16);
+    if (D != 1) KS = (KS + 1) & ~1;
+    if (KS > FIR_TC1_MAX_KS) return RRC_OK;
+    float wmax = 0.0f;
+    for (float v : w2) wmax = std::max(wmax, std::fabs(v));
+    int we = 0;
+    if (wmax > 0.0f) std::frexp(wmax, &we);
+    const int shift = wmax > 0.0f ? 14 - we : 0;
+    if (shift > 100 || shift < -100) return RRC_OK;
+    std::vector<unsigned> frag((size_t)KS * 2 * 32 * 4);
+    for (int ks = 0; ks < KS; ++ks)
+        for (int part = 0; part < 2; ++part)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t = lane & 3;
+                unsigned* f = &frag[(((size_t)ks * 2 + part) * 32 + lane) * 4];
+                for (int r = 0; r < 2; ++r) {
+                    unsigned hi = 0, lo = 0;
+                    for (int e = 0; e < 2; ++e) {
+                        const long long j = 16ll * ks + 2 * t + 8 * r + e - (long long)g * (long long)D;
+                        const float v = (j >= 0 && j < (long long)T) ? std::ldexp(w2[2 * (size_t)j + part], shift) : 0.0f;
+                        const unsigned short vh = f16_rn(v);
+                        const unsigned short vl = f16_rn(v - f16_to_f32(vh));
+                        hi |= (unsigned)vh << (16 * e);
+                        lo |= (unsigned)vl << (16 * e);
+                    }
+                    f[r] = hi;
+                    f[2 + r] = lo;
+                }
+            }
+    RRC_CUDA(cudaMalloc(&h->tc_bfrag, frag.size() * sizeof(unsigned)));
+    RRC_CUDA(cudaMemcpy(h->tc_bfrag, frag.data(), frag.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    h->tc = h->tc1 = h->tc_cplx = true;
+    h->tc_ntile = 1; h->tc_KS = KS;
+    h->tc_tap_inv_scale = std::ldexp(1.0f, -shift);
+    return RRC_OK;
+}
+
 // (Re)build the device tap tables from taps_host and pick the launch geometry.
 int upload_taps(rrc_fir* h) {
     const size_t T = h->ntaps, D = h->deci;
@@ -748,7 +789,7 @@ int upload_taps(rrc_fir* h) {
         }
     }
     if (h->real_taps) RRC_TRY(plan_tc(h, rev));
-    else h->tc = false;
+    else RRC_TRY(plan_tc_cplx(h, rev));
     return RRC_OK;
 }
 
@@ -839,7 +880,23 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
     a.in_u8 = h->in_u8;
     if (h->in_u8 && (reinterpret_cast<uintptr_t>(in) & 1)) return fail(RRC_ERR_INVALID, "u8 I/Q input must be 2-byte aligned");
 
-    if (h->tc && !h->cplx) {
+    const bool use_tc = h->tc && (h->tc_cplx ? !h->in_u8 : !h->translate);
+    if (use_tc && h->tc_cplx) {
+        const size_t work = demod ? out_n - 1 : out_n;
+        if (work == 0) return RRC_OK;
+        FirTccArgs t{};
+        t.in = reinterpret_cast<const float2*>(in); t.out = out;
+        t.bfrag = reinterpret_cast<const uint4*>(h->tc_bfrag);
+        t.taps_rev_c = reinterpret_cast<const float2*>(h->taps_rev);
+        t.in_stride = (long long)in_stride; t.out_stride = (long long)out_stride;
+        t.need = (long long)need; t.out_n = (long long)out_n;
+        t.ntaps = (int)h->ntaps; t.gain = gain; t.tap_inv_scale = h->tc_tap_inv_scale;
+        t.translate = h->translate ? 1 : 0; t.ratio = h->ratio; t.out_base = h->out_counter;
+        const size_t bt1 = FIR_TC1_BT / h->deci;
+        t.tiles_x = (long long)((work + bt1 - 1) / bt1);
+        t.total_tiles = t.tiles_x * (long long)nchan;
+        RRC_TRY(fir_tcc_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0, (int)h->deci}, t, demod, st));
+    } else if (use_tc && !h->cplx) {
         if (demod) return fail(RRC_ERR_INVALID, "fused demod needs a c32 FIR");
         FirTcfArgs t{};
         t.in = reinterpret_cast<const float*>(in); t.out = reinterpret_cast<float*>(out);
@@ -851,7 +908,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         t.tiles_x = (long long)((out_n + btf - 1) / btf);
         t.total_tiles = t.tiles_x * (long long)nchan;
         RRC_TRY(fir_tcf_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0, (int)h->deci}, t, st));
-    } else if (h->tc && h->tc1 && !h->translate) {
+    } else if (use_tc && h->tc1) {
         const size_t work = demod ? out_n - 1 : out_n;
         if (work == 0) return RRC_OK;
         FirTc1Args t{};
@@ -865,7 +922,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         t.tiles_x = (long long)((work + bt1 - 1) / bt1);
         t.total_tiles = t.tiles_x * (long long)nchan;
         RRC_TRY(fir_tc1_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0, (int)h->deci}, t, demod, st));
-    } else if (h->tc && !h->translate) {
+    } else if (use_tc) {
         const size_t work = demod ? out_n - 1 : out_n;
         if (work == 0) return RRC_OK;
         FirTcArgs t{};
@@ -1009,7 +1066,7 @@ int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes) {
 }
 int rrc_fir_uses_tensor_cores(const rrc_fir_t* h, int* yes) {
     if (!h || !yes) return fail(RRC_ERR_INVALID, "null argument");
-    *yes = (h->tc && !h->translate) ? 1 : 0;
+    *yes = (h->tc && (h->tc_cplx ? !h->in_u8 : !h->translate)) ? 1 : 0;
     return RRC_OK;
 }
 int rrc_fir_set_input_u8iq(rrc_fir_t* h, int on) {

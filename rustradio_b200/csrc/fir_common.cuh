@@ -38,4 +38,15 @@ __device__ __forceinline__ float demod_pair(float2 a, float2 b, float gain) {
     return gain * fast_atan2(im, re);
 }
 
+// exp(-j*2*pi*ratio*k) evaluated from the exact f64 angle.
+__device__ __forceinline__ float2 rotator(double ratio, unsigned long long k) {
+    double r = ratio * (double)k;
+    r -= rint(r);
+    double s, c;
+    sincospi(-2.0 * r, &s, &c);
+    return make_float2((float)c, (float)s);
+}
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
 }  // namespace rrc

@@ -49,6 +49,20 @@ struct FirTcfArgs {
     float tap_inv_scale;
 };
 
+struct FirTccArgs {             // fir_tcc_kernel: c32 samples, complex taps (translate filters)
+    const float2* in;
+    void* out;
+    const uint4* bfrag;        // [KS][2 = Re(w), Im(w)][32]
+    const float2* taps_rev_c;  // w[j] in f32 (boundary output of the demod epilogue)
+    long long in_stride, out_stride, need, out_n;
+    long long tiles_x, total_tiles;
+    int ntaps;
+    float gain, tap_inv_scale;
+    int translate;             // apply the per-output rotator exp(-j*2*pi*ratio*((ntaps-1) + (out_base + i)*deci))
+    double ratio;
+    unsigned long long out_base;
+};
+
 constexpr int FIR_TC_THREADS = 256;
 constexpr int FIR_TC1_BT = 512;            // INPUT samples a warp tile of fir_tc1_kernel advances by: 512/deci outputs
 constexpr int FIR_TCF_IN = 1024;           // INPUT samples a warp tile of fir_tcf_kernel (f32 streams) advances by
@@ -64,5 +78,6 @@ struct FirTcGeom {
 int fir_tc_launch(const FirTcGeom& g, const FirTcArgs& a, bool demod, cudaStream_t st);
 int fir_tc1_launch(const FirTcGeom& g, const FirTc1Args& a, bool demod, cudaStream_t st);
 int fir_tcf_launch(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st);
+int fir_tcc_launch(const FirTcGeom& g, const FirTccArgs& a, bool demod, cudaStream_t st);
 
 }  // namespace rrc

@@ -184,6 +184,64 @@ def test_fir_tensor_core_f32_streams(R, monkeypatch, ntaps, deci, n, nchan):
             assert e <= 2e-6
 
 
+@pytest.mark.parametrize("ntaps,deci,n,nchan", [
+    (32, 1, 10_000, 2), (64, 1, 200_001, 1), (100, 1, 1_500, 3), (249, 1, 40_000, 1), (313, 1, 9_000, 2), (20, 1, 3_000, 1),
+    (64, 2, 100_003, 1), (127, 2, 9_000, 3), (306, 2, 30_000, 1), (128, 4, 150_000, 1), (255, 4, 33_333, 2), (50, 4, 6_000, 1)])
+def test_fir_tensor_core_complex_taps(R, monkeypatch, ntaps, deci, n, nchan):
+    """fir_tcc_kernel (complex taps, deci 1/2/4): plain and fused-demod epilogues against the f64 truth and the FP32
+    complex-tap kernel, ragged tiles, odd channel strides."""
+    if ntaps < 32 * deci:
+        monkeypatch.setenv("RRC_FIR_TENSOR", "2")
+    taps = (O.low_pass_n(1.0, 0.2 / deci, ntaps) * np.exp(2j * np.pi * 0.07 / deci * np.arange(ntaps))).astype(np.complex64)
+    f = R.Fir(taps, deci=deci)
+    f32 = R.Fir(taps, deci=deci, flags=R.RRC_FIR_NO_TENSOR)
+    assert f.uses_tensor_cores and not f.uses_real_taps and not f32.uses_tensor_cores
+    stride = n + 1 if n % 2 == 0 else n
+    xs = np.zeros((nchan, stride), np.complex64)
+    for c in range(nchan):
+        xs[c, :n] = O.synth_c32(500 + c, 0, n) * 0.5 + np.exp(2j * np.pi * (0.07 + 0.011 * (c + 1)) / deci * np.arange(n)).astype(np.complex64)
+    out_n = f.out_count(n)
+    need = (out_n - 1) * deci + ntaps
+    din = R.DeviceBuffer.from_numpy(xs)
+    ostride = out_n + 1 - (out_n % 2)
+    for filt in (f, f32):
+        dy = R.DeviceBuffer(nchan * ostride * 8)
+        filt.run_batch(din, stride, need, dy, ostride, out_n, nchan)
+        y = dy.download(np.complex64, nchan * ostride).reshape(nchan, ostride)[:, :out_n]
+        dd = R.DeviceBuffer(nchan * ostride * 4)
+        filt.demod_run_batch(din, stride, need, 0.7, dd, ostride, out_n, nchan)
+        d = dd.download(np.float32, nchan * ostride).reshape(nchan, ostride)[:, :out_n - 1]
+        for c in range(nchan):
+            truth = O.fir(xs[c, :n], taps, deci, f64=True)
+            e = O.rel_rms(y[c], truth)
+            print(f"fir_tcc T={ntaps} D={deci} ch{c} {'tensor' if filt is f else 'fp32'}: {e:.2e}")
+            assert e <= 2e-6
+            assert O.max_angle_err(d[c] / 0.7, np.angle(truth[1:] * np.conj(truth[:-1]))) <= DEMOD_BAR
+
+
+def test_fir_tensor_core_translate(R):
+    """FirFilter::builder().translate() on the tensor path: pre-rotated (complex) taps + exact-phase rotator epilogue,
+    against the FP32 kernels with the same rotator and the reference recurrence (src/fir.rs:416-474); streaming calls keep
+    the rotator's output counter."""
+    n, deci = 60_000, 2
+    x = O.synth_c32(41, 0, n)
+    lp = O.low_pass_n(1000.0, 60.0, 101).astype(np.complex64)
+    outs = []
+    for flags in (0, R.RRC_FIR_NO_TENSOR):
+        f = R.Fir(lp, deci=deci, flags=flags)
+        f.set_translate(1000.0, 130.0)
+        assert f.uses_tensor_cores == (flags == 0)
+        first = f.filter(x[:20_000 + 100])              # 10_000 outputs
+        rest = f.filter(x[20_000:])                     # the counter carries on
+        outs.append(np.concatenate([first, rest]))
+    assert len(outs[0]) == len(outs[1])
+    assert O.rel_rms(outs[0], outs[1]) <= 2e-6
+    rt, ph, st = O.fir_new_translator(lp, 1000.0, 130.0, deci)
+    want = O.fir(x, rt, deci)
+    O.fir_translate_output(want, ph, st)
+    assert O.rel_rms(outs[0][:4000], want[:4000]) < 1e-4      # the reference's f32 rotator recurrence drifts later on (SURVEY F9)
+
+
 @pytest.mark.parametrize("scale", [1.0, 1e-20, 3e18, 0.0])
 def test_fir_tensor_core_block_scaling(R, scale):
     """The per-tile power-of-two scaling makes the fp16 split independent of the stream's level; a tile that is one
@@ -230,10 +288,13 @@ def test_fir_tensor_core_falls_back(R):
     assert f.uses_tensor_cores
     f.set_input_u8iq(False)
     f.set_translate(1.0, 0.1)
-    assert not f.uses_tensor_cores
+    assert f.uses_tensor_cores                                                                # translate: complex-tap kernel
+    f.set_input_u8iq(True)
+    assert not f.uses_tensor_cores                                                            # ... which has no u8 variant
     assert R.Fir(lp.astype(np.float32)).uses_tensor_cores                                    # f32 streams: fir_tcf_kernel
     assert not R.Fir(lp.astype(np.float32), deci=3).uses_tensor_cores
-    assert not R.Fir(cplx_taps(64)).uses_tensor_cores
+    assert R.Fir(cplx_taps(64)).uses_tensor_cores                                             # complex taps: fir_tcc_kernel
+    assert not R.Fir(cplx_taps(64), deci=3).uses_tensor_cores
     assert not R.Fir(O.low_pass_n(1.0, 0.1, 15).astype(np.complex64)).uses_tensor_cores
     # the planner keeps decimating short filters (config 3: 255 taps / 10) on the packed-FP32 kernel
     assert not R.Fir(O.low_pass_n(2.4e6, 100e3, 255).astype(np.complex64), deci=10).uses_tensor_cores

@@ -28,6 +28,8 @@ for T, D in shapes:
     taps = O.low_pass_n(1.0, 0.4 / D, T)
     if not F32:
         taps = taps.astype(np.complex64)
+        if "--ctaps" in sys.argv:                      # complex taps (what translate() produces)
+            taps = (taps * np.exp(2j * np.pi * 0.05 * np.arange(T))).astype(np.complex64)
     res = {}
     for name, env in (("fp32", "0"), ("tensor", "2")):
         os.environ["RRC_FIR_TENSOR"] = env
@@ -45,4 +47,4 @@ for T, D in shapes:
     rows.append(dict(ntaps=T, deci=D, fp32_ms=res["fp32"], tensor_ms=res["tensor"], planner_takes_tensor=auto, hbm_floor_ms=hbm_ms))
     t = res["tensor"]
     print(f"T={T:5d} D={D:3d}  fp32 {res['fp32']:.3f} ms  tensor {t if t is None else round(t, 3)} ms  planner={'tensor' if auto else 'fp32'}  hbm floor {hbm_ms:.3f}", flush=True)
-json.dump(rows, open("gpurun_out/fir_sweep_f32.json" if F32 else "gpurun_out/fir_sweep.json", "w"), indent=1)
+json.dump(rows, open("gpurun_out/fir_sweep_f32.json" if F32 else "gpurun_out/fir_sweep_ctaps.json" if "--ctaps" in sys.argv else "gpurun_out/fir_sweep.json", "w"), indent=1)
