@@ -1,4 +1,7 @@
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_ingest.py tests/test_blocks_gpu.py -m gpu -x -q -k "fir or Fir" -s ) > gpurun_out/pytest_fir_tc.log 2>&1; tail -3 gpurun_out/pytest_fir_tc.log
-grep "fir_tcc.*tensor" gpurun_out/pytest_fir_tc.log | sort -k6 -g | tail -2
-timeout 600 python tools/fir_sweep.py --ctaps 2>&1 | tail -20
+for cfg in c1 c2; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --config $cfg --steps 20 --warmup 3 --no-cpu > gpurun_out/scale2_${cfg}.json 2> gpurun_out/scale2_${cfg}.err
+python -c "
+import json
+d=json.loads([l for l in open('gpurun_out/scale2_${cfg}.json') if l.startswith('{')][-1]); print('$cfg N=2', round(d['value']), d['ms_per_step'], d['n_gpus'], d['scaling'], round(d['e2e']['value']) if d['e2e'] else None)"
+done
