@@ -109,7 +109,8 @@ int rrc_fir_deci(const rrc_fir_t* h, size_t* deci);
 int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes);
 /* 1 if runs go through a tensor-core Toeplitz kernel: ntaps >= 32 * deci and
  *  - c32 samples, real taps (also from u8 I/Q input), no translate; or
- *  - c32 samples, complex taps (translate filters included), deci 1, 2 or 4, 7*deci + ntaps <= 320, c32 input; or
+ *  - c32 samples, complex taps (translate filters included; also from u8 I/Q input), deci 1, 2 or 4,
+ *    7*deci + ntaps <= 320; or
  *  - f32 streams, deci 1, 2 or 4, 7*deci + ntaps <= 320.
  * Samples (per warp tile) and taps are scaled by powers of two and split hi + lo in fp16 (22 significant bits);
  * every product is hi*hi + hi*lo + lo*hi with FP32 accumulation.  FP32-class accuracy: rel-RMS error 1e-7..1e-6

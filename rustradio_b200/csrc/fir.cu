@@ -880,7 +880,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
     a.in_u8 = h->in_u8;
     if (h->in_u8 && (reinterpret_cast<uintptr_t>(in) & 1)) return fail(RRC_ERR_INVALID, "u8 I/Q input must be 2-byte aligned");
 
-    const bool use_tc = h->tc && (h->tc_cplx ? !h->in_u8 : !h->translate);
+    const bool use_tc = h->tc && (h->tc_cplx || !h->translate);
     if (use_tc && h->tc_cplx) {
         const size_t work = demod ? out_n - 1 : out_n;
         if (work == 0) return RRC_OK;
@@ -891,7 +891,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         t.in_stride = (long long)in_stride; t.out_stride = (long long)out_stride;
         t.need = (long long)need; t.out_n = (long long)out_n;
         t.ntaps = (int)h->ntaps; t.gain = gain; t.tap_inv_scale = h->tc_tap_inv_scale;
-        t.translate = h->translate ? 1 : 0; t.ratio = h->ratio; t.out_base = h->out_counter;
+        t.translate = h->translate ? 1 : 0; t.ratio = h->ratio; t.out_base = h->out_counter; t.in_u8 = h->in_u8;
         const size_t bt1 = FIR_TC1_BT / h->deci;
         t.tiles_x = (long long)((work + bt1 - 1) / bt1);
         t.total_tiles = t.tiles_x * (long long)nchan;
@@ -1066,7 +1066,7 @@ int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes) {
 }
 int rrc_fir_uses_tensor_cores(const rrc_fir_t* h, int* yes) {
     if (!h || !yes) return fail(RRC_ERR_INVALID, "null argument");
-    *yes = (h->tc && (h->tc_cplx ? !h->in_u8 : !h->translate)) ? 1 : 0;
+    *yes = (h->tc && (h->tc_cplx || !h->translate)) ? 1 : 0;
     return RRC_OK;
 }
 int rrc_fir_set_input_u8iq(rrc_fir_t* h, int on) {

@@ -58,6 +58,7 @@ struct FirTccArgs {             // fir_tcc_kernel: c32 samples, complex taps (tr
     long long tiles_x, total_tiles;
     int ntaps;
     float gain, tap_inv_scale;
+    int in_u8;                 // 1: `in` is u8 I/Q pairs (in_stride in samples)
     int translate;             // apply the per-output rotator exp(-j*2*pi*ratio*((ntaps-1) + (out_base + i)*deci))
     double ratio;
     unsigned long long out_base;

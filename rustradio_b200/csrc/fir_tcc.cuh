@@ -49,7 +49,9 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 2) fir_tcc_kernel(const FirTcc
         {
             const float2* __restrict__ in = a.in + ch * a.in_stride + ob * D;
             const long long avail = a.need - ob * D;
-            if (avail >= L && (reinterpret_cast<unsigned long long>(in) & 15ull) == 0) {
+            if (a.in_u8) {                                 // RtlSdrDecode fused into the tile load (bit-identical to decoding first)
+                tc_load_u8<NLD>(reinterpret_cast<const unsigned short*>(a.in) + ch * a.in_stride + ob * D, avail, NP, lane, v);
+            } else if (avail >= L && (reinterpret_cast<unsigned long long>(in) & 15ull) == 0) {
 #pragma unroll
                 for (int u = 0; u < NLD; ++u) {
                     const int e = lane + u * 32;
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 2) fir_tcc_kernel(const FirTcc
         }
         {   // the warp's NEXT tile -> L2 (one bulk prefetch), so that its loads are L2 hits one tile from now
             const long long nid = id + nworkers;
-            if (lane == 0 && nid < a.total_tiles) {
+            if (lane == 0 && nid < a.total_tiles && !a.in_u8) {
                 const long long nch = nid / a.tiles_x;
                 const long long nob = (nid - nch * a.tiles_x) * BT;
                 const float2* nin = a.in + nch * a.in_stride + nob * D;

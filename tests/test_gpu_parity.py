@@ -290,7 +290,7 @@ def test_fir_tensor_core_falls_back(R):
     f.set_translate(1.0, 0.1)
     assert f.uses_tensor_cores                                                                # translate: complex-tap kernel
     f.set_input_u8iq(True)
-    assert not f.uses_tensor_cores                                                            # ... which has no u8 variant
+    assert f.uses_tensor_cores                                                                # ... also from u8 I/Q bytes
     assert R.Fir(lp.astype(np.float32)).uses_tensor_cores                                    # f32 streams: fir_tcf_kernel
     assert not R.Fir(lp.astype(np.float32), deci=3).uses_tensor_cores
     assert R.Fir(cplx_taps(64)).uses_tensor_cores                                             # complex taps: fir_tcc_kernel

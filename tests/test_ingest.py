@@ -88,7 +88,7 @@ def test_decode_kernel_bit_exact(R, n_bytes, in_off, out_off):
 @pytest.mark.gpu
 @pytest.mark.parametrize("ntaps,deci,n,kind", [(64, 1, 50_000, "rtaps"), (255, 10, 240_000, "rtaps"), (33, 3, 20_001, "ctaps"),
                                                (7, 1, 4000, "rtaps"), (300, 1000, 10_000, "rtaps"), (64, 1, 50_001, "rtaps"),
-                                               (200, 2, 30_000, "rtaps"), (121, 1, 777, "rtaps"), (160, 4, 44_444, "rtaps")])
+                                               (200, 2, 30_000, "rtaps"), (121, 1, 777, "rtaps"), (160, 4, 44_444, "rtaps"), (64, 1, 50_001, "ctaps"), (200, 2, 30_000, "ctaps")])
 def test_fir_fused_u8_input_equals_decode_then_fir(R, ntaps, deci, n, kind):
     """RtlSdrDecode -> FirFilter<Complex> fused: bit-identical to decoding first, and within the
     FIR bar of the f64 truth."""
