@@ -21,7 +21,7 @@ F32 = "--f32" in sys.argv                      # FirFilter<Float>: f32 samples, 
 n = 1 << (26 if F32 else 25)
 x = torch.empty(n if F32 else 2 * n, dtype=torch.float32, device="cuda")
 R.synth_f32(x, 7, 0, n if F32 else 2 * n, 0, torch.cuda.current_stream().cuda_stream)
-shapes = [(32, 1), (64, 1), (121, 1), (128, 1), (247, 1), (512, 1), (1025, 1), (64, 2), (127, 2), (255, 2), (129, 4), (255, 4), (511, 4),
+shapes = [(16, 1), (24, 1), (32, 2), (48, 2), (64, 4), (96, 4), (32, 1), (64, 1), (121, 1), (128, 1), (247, 1), (512, 1), (1025, 1), (64, 2), (127, 2), (255, 2), (129, 4), (255, 4), (511, 4),
           (255, 8), (511, 8), (255, 10), (1023, 16)]
 rows = []
 for T, D in shapes:
