@@ -1,10 +1,4 @@
 mkdir -p gpurun_out
-for cfg in c3 c4 c5 f1 f2 h1 e1 e2 e3 e4 a12 c3u8 c5u8; do
-timeout 400 python bench.py --config $cfg --steps 20 --warmup 3 --cpu-budget 6 > gpurun_out/bench_${cfg}_v11.json 2> gpurun_out/bench_${cfg}_v11.err
-python -c "
-import json
-try:
-    d=json.loads(open('gpurun_out/bench_${cfg}_v11.json').read().strip().splitlines()[-1]); print('$cfg', round(d['value']), round(d['ms_per_step'],4), round(d['roofline']['frac'],3), (round(d['e2e']['value']) if d.get('e2e') else None), (round(d['cpu_baseline']['value'],1) if d.get('cpu_baseline') else None))
-except Exception as e: print('$cfg failed', e)
-"
-done
+( timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu_all.log 2>&1; tail -3 gpurun_out/pytest_gpu_all.log
+( timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" ) > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
+timeout 600 python tools/fir_sweep.py > /dev/null 2>&1; timeout 600 python tools/fir_sweep.py --f32 > /dev/null 2>&1; timeout 600 python tools/fir_sweep.py --ctaps 2>&1 | head -3

@@ -107,11 +107,10 @@ int rrc_fir_ntaps(const rrc_fir_t* h, size_t* ntaps);
 int rrc_fir_deci(const rrc_fir_t* h, size_t* deci);
 /* 1 if the real-tap fast path (2 FMA per tap instead of 4) is active. */
 int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes);
-/* 1 if runs go through a tensor-core Toeplitz kernel: ntaps >= 32 * deci and
- *  - c32 samples, real taps (also from u8 I/Q input), no translate; or
- *  - c32 samples, complex taps (translate filters included; also from u8 I/Q input), deci 1, 2 or 4,
- *    7*deci + ntaps <= 320; or
- *  - f32 streams, deci 1, 2 or 4, 7*deci + ntaps <= 320.
+/* 1 if runs go through a tensor-core Toeplitz kernel: at least 16 taps and
+ *  - deci 1, 2 or 4 with 7*deci + ntaps <= 320 (the "walk" kernels): c32 samples with real taps, c32 samples with
+ *    complex taps (translate filters included) — both also from u8 I/Q input —, or f32 streams; or
+ *  - c32 samples, real taps, ntaps >= 32 * deci, no translate (generic kernel; other decimations / longer filters).
  * Samples (per warp tile) and taps are scaled by powers of two and split hi + lo in fp16 (22 significant bits);
  * every product is hi*hi + hi*lo + lo*hi with FP32 accumulation.  FP32-class accuracy: rel-RMS error 1e-7..1e-6
  * against the f64 convolution, next to 1e-7..3e-7 for the sequential f32 loop (bar 1e-5).  Declared like the

@@ -588,8 +588,7 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
     // feeds many taps (ntaps/deci >= 32) and the halo is at most half of the staged span.
     bool force = false;
     if (const char* e = getenv("RRC_FIR_TENSOR")) force = atoi(e) == 2;
-    if (!force && T < 32 * D) return RRC_OK;
-    // deci 1, 2, 4 and <= 16 k-steps: the walk kernel (even k-step counts only for deci 2 and 4: fewer instantiations,
+    // deci 1, 2, 4 and <= 20 k-steps: the walk kernel — measured ahead of the FP32 kernels from 16 taps on (tools/fir_sweep.py) (even k-step counts only for deci 2 and 4: fewer instantiations,
     // the extra k-step multiplies zero taps)
     const int ks1 = (D == 1) ? ksteps(1) : ((ksteps(1) + 1) & ~1);
     h->tc1 = (D == 1 || D == 2 || D == 4) && ks1 <= FIR_TC1_MAX_KS;
@@ -599,6 +598,7 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
         h->tc_ntile = 1; h->tc_KS = ks1;
     }
     if (!h->cplx && !h->tc1) return RRC_OK;               // f32 streams: walk kernel (fir_tcf_kernel) or FP32
+    if (!h->tc1 && !force && T < 32 * D) return RRC_OK;   // the generic kernel only pays for ntaps/deci >= 32
     for (int pass = 0; pass < 2 && !h->tc; ++pass)
         for (int nt = ntile; nt >= 1 && !h->tc; nt >>= 1) {
             const int R = 8 * nt, KS = ksteps(nt);
@@ -676,7 +676,8 @@ int plan_tc_cplx(rrc_fir* h, const std::vector<float>& w2) {       // w2: revers
     if (!h->cplx || (h->flags & (RRC_FIR_NO_TENSOR | RRC_FIR_FORCE_GENERIC)) || T < 16) return RRC_OK;
     bool force = false;
     if (const char* e = getenv("RRC_FIR_TENSOR")) { if (atoi(e) == 0) return RRC_OK; force = atoi(e) == 2; }
-    if (!(D == 1 || D == 2 || D == 4) || (!force && T < 32 * D)) return RRC_OK;
+    (void)force;
+    if (!(D == 1 || D == 2 || D == 4)) return RRC_OK;
     for (float v : w2) if (!std::isfinite(v)) return RRC_OK;
     int KS = (int)((7 * D + T + 15) / 16);
     if (D != 1) KS = (KS + 1) & ~1;
