@@ -15,7 +15,8 @@
 // hi*hi + (hi*lo + lo*hi), FP32 accumulation in two separate accumulators; the dropped lo*lo term is
 // <= 2^-22 of the product.  That is FP32-class: measured rel-RMS against the f64 convolution 1e-7..4e-7,
 // next to the sequential f32 loop's 1e-7..2e-7 (bar 1e-5).  RRC_FIR_NO_TENSOR keeps the FP32 kernels.
-// Tiles whose largest magnitude is below 2^-113, or not finite, are not scaled.
+// Tiles whose largest magnitude is below 2^-113 are not scaled; non-finite samples are left out of the maximum, so they
+// only affect the outputs whose window contains them (tc_tile_exp).
 //
 // Pipeline: every WARP is an independent worker with its own tile, its own fp16 planes in shared memory and no
 // CTA barrier after start-up (24 warps per SM drift out of phase, so one warp's global-load wait overlaps the
@@ -77,6 +78,27 @@ __device__ __forceinline__ void tc_load_u8(const unsigned short* __restrict__ in
         const float2 p = decode_iq(w & 0xffffu), q = decode_iq(w >> 16);
         v[u] = make_float4(p.x, p.y, q.x, q.y);
     }
+}
+
+// Exponent field of the tile's largest |component| (warp-wide).  A non-finite sample must not switch the scaling off
+// for its whole tile (the other samples would overflow fp16 unscaled): then the largest FINITE magnitude is used, the
+// non-finite sample becomes an fp16 Inf/NaN and only the outputs whose window contains it are non-finite, like the reference's.
+template <int NLD>
+__device__ __forceinline__ unsigned tc_tile_exp(const float4 (&v)[NLD]) {
+    float mx = 0.f;
+#pragma unroll
+    for (int u = 0; u < NLD; ++u)
+        mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+    unsigned ex = __reduce_max_sync(0xffffffffu, __float_as_uint(mx)) >> 23;     // NaN never wins fmaxf; Inf does
+    if (ex == 255u) {
+        float m2 = 0.f;
+        auto fin = [](float c) { const float a = fabsf(c); return a <= 3.4028234e38f ? a : 0.f; };
+#pragma unroll
+        for (int u = 0; u < NLD; ++u)
+            m2 = fmaxf(fmaxf(m2, fmaxf(fin(v[u].x), fin(v[u].y))), fmaxf(fin(v[u].z), fin(v[u].w)));
+        ex = __reduce_max_sync(0xffffffffu, __float_as_uint(m2)) >> 23;
+    }
+    return ex;
 }
 
 // (a, b) scaled f32 -> fp16x2 hi word and fp16x2 lo word (a in the lower half).
@@ -150,12 +172,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc_kernel(const FirTcAr
             }
         }
         // ---- B. largest magnitude of the tile -> power-of-two scale ----
-        float mx = 0.f;
-#pragma unroll
-        for (int u = 0; u < NLD; ++u)
-            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
-        // NaN never wins fmaxf; Inf does and is caught by the exponent test
-        const unsigned ex = __reduce_max_sync(0xffffffffu, __float_as_uint(mx)) >> 23;
+        const unsigned ex = tc_tile_exp<NLD>(v);
         const bool scaled = ex >= 14u && ex < 255u;
         const float sc = scaled ? __uint_as_float((267u - ex) << 23) : 1.0f;          // 2^(13 - (ex - 127))
         const float isc = scaled ? __uint_as_float((ex - 13u) << 23) : 1.0f;
@@ -359,11 +376,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nin), "r"(L * 8) : "memory");
             }
         }
-        float mx = 0.f;
-#pragma unroll
-        for (int u = 0; u < NLD; ++u)
-            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
-        const unsigned ex = __reduce_max_sync(0xffffffffu, __float_as_uint(mx)) >> 23;
+        const unsigned ex = tc_tile_exp<NLD>(v);
         const bool scaled = ex >= 14u && ex < 255u;
         const float sc = scaled ? __uint_as_float((267u - ex) << 23) : 1.0f;
         const float isc = scaled ? __uint_as_float((ex - 13u) << 23) : 1.0f;
@@ -535,11 +548,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tcf_kernel(const FirTcf
                 }
             }
         }
-        float mx = 0.f;
-#pragma unroll
-        for (int u = 0; u < NLD; ++u)
-            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
-        const unsigned ex = __reduce_max_sync(0xffffffffu, __float_as_uint(mx)) >> 23;
+        const unsigned ex = tc_tile_exp<NLD>(v);
         const bool scaled = ex >= 14u && ex < 255u;
         const float sc = scaled ? __uint_as_float((267u - ex) << 23) : 1.0f;
         const float inv = (scaled ? __uint_as_float((ex - 13u) << 23) : 1.0f) * a.tap_inv_scale;

@@ -80,11 +80,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 2) fir_tcc_kernel(const FirTcc
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nin), "r"(L * 8) : "memory");
             }
         }
-        float mx = 0.f;
-#pragma unroll
-        for (int u = 0; u < NLD; ++u)
-            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
-        const unsigned ex = __reduce_max_sync(0xffffffffu, __float_as_uint(mx)) >> 23;
+        const unsigned ex = tc_tile_exp<NLD>(v);
         const bool scaled = ex >= 14u && ex < 255u;
         const float sc = scaled ? __uint_as_float((267u - ex) << 23) : 1.0f;
         const float isc = scaled ? __uint_as_float((ex - 13u) << 23) : 1.0f;

@@ -262,6 +262,34 @@ def test_fir_tensor_core_block_scaling(R, scale):
     assert e <= 2e-6 and e <= 8 * e_ref
 
 
+@pytest.mark.parametrize("kind", ["c32_rtaps", "c32_ctaps", "f32"])
+@pytest.mark.parametrize("bad", [np.inf, np.nan])
+def test_fir_tensor_core_non_finite_samples_stay_local(R, kind, bad):
+    """One Inf / NaN sample makes the outputs whose window contains it non-finite (like the reference's sum) — plus, at
+    most, the rest of their 8-output block-rows, whose zero-padded Toeplitz taps meet it as 0 * Inf.  Every
+    other output of the tile keeps FP32-class accuracy: the tile is still scaled, by its largest FINITE magnitude, even
+    though the finite samples would overflow fp16 unscaled."""
+    n, ntaps, pos = 30_000, 64, 12_345
+    lp = O.low_pass_n(1.0, 0.1, ntaps)
+    if kind == "f32":
+        taps, x = lp, (O.synth_f32(61, 0, n) * np.float32(3e5)).astype(np.float32)
+    else:
+        taps = lp.astype(np.complex64) if kind == "c32_rtaps" else (lp * np.exp(0.2j * np.arange(ntaps))).astype(np.complex64)
+        x = (O.synth_c32(61, 0, n) * np.float32(3e5)).astype(np.complex64)
+    f = R.Fir(taps)
+    assert f.uses_tensor_cores
+    x[pos] = bad
+    y = f.filter(x)
+    o = np.arange(len(y))
+    touched = (o > pos - ntaps) & (o <= pos)                      # y[o] uses x[o .. o + ntaps)
+    far = (o <= pos - 96) | (o > pos + 8)                         # beyond the padded k-range of any block-row that holds `pos`
+    assert not np.isfinite(y[touched]).any()
+    assert np.isfinite(y[far]).all()
+    xz = x.copy(); xz[pos] = 0
+    truth = O.fir(xz, taps, 1, f64=True)
+    assert O.rel_rms(y[far], truth[far]) <= 2e-6
+
+
 def test_fir_tensor_core_stopband_dominated_input(R, monkeypatch):
     """A strong out-of-band tone: the error is relative to the INPUT level, so the bar is checked on the hard case."""
     monkeypatch.setenv("RRC_FIR_TENSOR", "2")
