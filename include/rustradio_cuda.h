@@ -108,7 +108,7 @@ int rrc_fir_deci(const rrc_fir_t* h, size_t* deci);
 /* 1 if the real-tap fast path (2 FMA per tap instead of 4) is active. */
 int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes);
 /* 1 if runs go through a tensor-core Toeplitz kernel: at least 16 taps and
- *  - deci 1, 2 or 4 with 7*deci + ntaps <= 320 (the "walk" kernels): c32 samples with real taps, c32 samples with
+ *  - deci 1, 2, 4 or 8 with 7*deci + ntaps <= 320 (the "walk" kernels): c32 samples with real taps, c32 samples with
  *    complex taps (translate filters included) — both also from u8 I/Q input —, or f32 streams; or
  *  - c32 samples, real taps, ntaps >= 32 * deci, no translate (generic kernel; other decimations / longer filters).
  * Samples (per warp tile) and taps are scaled by powers of two and split hi + lo in fp16 (22 significant bits);

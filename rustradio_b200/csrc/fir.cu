@@ -591,7 +591,7 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
     // deci 1, 2, 4 and <= 20 k-steps: the walk kernel — measured ahead of the FP32 kernels from 16 taps on (tools/fir_sweep.py) (even k-step counts only for deci 2 and 4: fewer instantiations,
     // the extra k-step multiplies zero taps)
     const int ks1 = (D == 1) ? ksteps(1) : ((ksteps(1) + 1) & ~1);
-    h->tc1 = (D == 1 || D == 2 || D == 4) && ks1 <= FIR_TC1_MAX_KS;
+    h->tc1 = (D == 1 || D == 2 || D == 4 || D == 8) && ks1 <= FIR_TC1_MAX_KS;
     if (const char* e = getenv("RRC_FIR_TC1")) if (atoi(e) == 0) h->tc1 = false;
     if (h->tc1) {
         h->tc = true;
@@ -677,7 +677,7 @@ int plan_tc_cplx(rrc_fir* h, const std::vector<float>& w2) {       // w2: revers
     bool force = false;
     if (const char* e = getenv("RRC_FIR_TENSOR")) { if (atoi(e) == 0) return RRC_OK; force = atoi(e) == 2; }
     (void)force;
-    if (!(D == 1 || D == 2 || D == 4)) return RRC_OK;
+    if (!(D == 1 || D == 2 || D == 4 || D == 8)) return RRC_OK;
     for (float v : w2) if (!std::isfinite(v)) return RRC_OK;
     int KS = (int)((7 * D + T + 15) / 16);
     if (D != 1) KS = (KS + 1) & ~1;

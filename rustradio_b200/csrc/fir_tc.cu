@@ -123,6 +123,7 @@ int launch_tcf_even(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st) {
 int fir_tcf_launch(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st) {
     if (g.deci == 2) return launch_tcf_even<2>(g, a, st);
     if (g.deci == 4) return launch_tcf_even<4>(g, a, st);
+    if (g.deci == 8) return launch_tcf_even<8>(g, a, st);
     if (g.deci != 1) return fail(RRC_ERR_INVALID, "fir_tcf: deci %d", g.deci);
     switch (g.KS) {
     case 2: return launch_tcf_k<2, 1>(g, a, st);
@@ -155,6 +156,7 @@ int fir_tc_launch(const FirTcGeom& g, const FirTcArgs& a, bool demod, cudaStream
 int fir_tc1_launch(const FirTcGeom& g, const FirTc1Args& a, bool demod, cudaStream_t st) {
     if (g.deci == 2) return launch_tc1_even<2>(g, a, demod, st);
     if (g.deci == 4) return launch_tc1_even<4>(g, a, demod, st);
+    if (g.deci == 8) return launch_tc1_even<8>(g, a, demod, st);
     if (g.deci != 1) return fail(RRC_ERR_INVALID, "fir_tc1: deci %d", g.deci);
     switch (g.KS) {
     case 2: return launch_tc1_k<2, 1>(g, a, demod, st);

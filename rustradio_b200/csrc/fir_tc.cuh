@@ -309,7 +309,7 @@ __host__ __device__ constexpr size_t fir_tc1_smem(int KS, bool demod) { return (
 
 template <int KS, bool DEMOD, bool U8, int D>
 __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1Args a) {
-    static_assert(D == 1 || D == 2 || D == 4, "fir_tc1_kernel: deci 1, 2 or 4");
+    static_assert(D == 1 || D == 2 || D == 4 || D == 8, "fir_tc1_kernel: deci 1, 2, 4 or 8");
     constexpr int S = 8 / D;                               // m-tiles per warp tile: block-row b = j + S*r keeps the row pitch at 64 samples
     constexpr int QL = (8 - D) + 2 * (KS - 1);             // last walk position; q = D*j + 2*ks
     constexpr int QS = D == 1 ? 1 : 2;                     // even decimations only visit even positions
@@ -498,7 +498,7 @@ __host__ __device__ constexpr size_t fir_tcf_smem(int KS) { return (size_t)KS * 
 
 template <int KS, int D>
 __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tcf_kernel(const FirTcfArgs a) {
-    static_assert(D == 1 || D == 2 || D == 4, "fir_tcf_kernel: deci 1, 2 or 4");
+    static_assert(D == 1 || D == 2 || D == 4 || D == 8, "fir_tcf_kernel: deci 1, 2, 4 or 8");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = FIR_TC_THREADS / 32;
     constexpr int S = 8 / D;

@@ -53,6 +53,7 @@ int launch_tcc_even(const FirTcGeom& g, const FirTccArgs& a, bool demod, cudaStr
 int fir_tcc_launch(const FirTcGeom& g, const FirTccArgs& a, bool demod, cudaStream_t st) {
     if (g.deci == 2) return launch_tcc_even<2>(g, a, demod, st);
     if (g.deci == 4) return launch_tcc_even<4>(g, a, demod, st);
+    if (g.deci == 8) return launch_tcc_even<8>(g, a, demod, st);
     if (g.deci != 1) return fail(RRC_ERR_INVALID, "fir_tcc: deci %d", g.deci);
     switch (g.KS) {
     case 2: return launch_tcc_k<2, 1>(g, a, demod, st);

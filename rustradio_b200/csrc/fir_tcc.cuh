@@ -13,7 +13,7 @@ namespace rrc {
 
 template <int KS, bool DEMOD, int D>
 __global__ void __launch_bounds__(FIR_TC_THREADS, 2) fir_tcc_kernel(const FirTccArgs a) {
-    static_assert(D == 1 || D == 2 || D == 4, "fir_tcc_kernel: deci 1, 2 or 4");
+    static_assert(D == 1 || D == 2 || D == 4 || D == 8, "fir_tcc_kernel: deci 1, 2, 4 or 8");
     constexpr int S = 8 / D;                               // m-tiles per warp tile: block-row b = j + S*r keeps the row pitch at 64 samples
     constexpr int QL = (8 - D) + 2 * (KS - 1);             // last walk position; q = D*j + 2*ks
     constexpr int QS = D == 1 ? 1 : 2;                     // even decimations only visit even positions

@@ -121,7 +121,7 @@ def test_fir_tensor_core_geometries(R, monkeypatch, ntile, nld, nm, ntaps, deci,
     (18, 2, 4_000, 2), (64, 2, 100_001, 1), (127, 2, 33_333, 3), (180, 2, 9_999, 1), (242, 2, 50_000, 2),
     (40, 4, 7_000, 1), (128, 4, 123_457, 1), (129, 4, 20_000, 3), (200, 4, 5_001, 2), (228, 4, 60_000, 1),
     (255, 1, 31_000, 1), (270, 1, 8_000, 2), (290, 1, 22_222, 1), (313, 1, 10_000, 1), (255, 2, 40_000, 2), (306, 2, 9_000, 1),
-    (255, 4, 70_001, 1), (292, 4, 12_000, 2)])
+    (255, 4, 70_001, 1), (292, 4, 12_000, 2), (128, 8, 99_999, 1), (255, 8, 40_000, 2), (264, 8, 7_000, 1), (60, 8, 3_000, 2)])
 def test_fir_tensor_core_walk_kernel(R, monkeypatch, ntaps, deci, n, nchan):
     """fir_tc1_kernel (deci 1, 2, 4; 7*deci + ntaps <= 320; every k-step count): plain and fused-demod epilogues, ragged
     last tiles, tiles shorter than one warp tile, odd channel strides (8-byte aligned channels take the scalar loads/stores)."""
@@ -155,7 +155,7 @@ def test_fir_tensor_core_walk_kernel(R, monkeypatch, ntaps, deci, n, nchan):
 @pytest.mark.parametrize("ntaps,deci,n,nchan", [
     (32, 1, 10_000, 2), (64, 1, 300_001, 1), (65, 1, 1_500, 3), (100, 1, 2_049, 1), (247, 1, 50_000, 2), (313, 1, 70_000, 1),
     (20, 1, 3_000, 1), (64, 2, 100_003, 1), (127, 2, 9_000, 2), (255, 2, 40_000, 1), (306, 2, 8_191, 1),
-    (128, 4, 200_000, 1), (255, 4, 33_333, 2), (292, 4, 5_000, 1), (50, 4, 6_000, 1)])
+    (128, 4, 200_000, 1), (255, 4, 33_333, 2), (292, 4, 5_000, 1), (50, 4, 6_000, 1), (255, 8, 100_000, 1), (130, 8, 9_001, 2)])
 def test_fir_tensor_core_f32_streams(R, monkeypatch, ntaps, deci, n, nchan):
     """fir_tcf_kernel (FirFilter<Float>, deci 1/2/4, 7*deci + ntaps <= 320): against the f64 truth and the FP32 kernel,
     ragged last tiles, odd channel strides (4-byte aligned channels take the scalar loads and stores)."""
@@ -186,7 +186,8 @@ def test_fir_tensor_core_f32_streams(R, monkeypatch, ntaps, deci, n, nchan):
 
 @pytest.mark.parametrize("ntaps,deci,n,nchan", [
     (32, 1, 10_000, 2), (64, 1, 200_001, 1), (100, 1, 1_500, 3), (249, 1, 40_000, 1), (313, 1, 9_000, 2), (20, 1, 3_000, 1),
-    (64, 2, 100_003, 1), (127, 2, 9_000, 3), (306, 2, 30_000, 1), (128, 4, 150_000, 1), (255, 4, 33_333, 2), (50, 4, 6_000, 1)])
+    (64, 2, 100_003, 1), (127, 2, 9_000, 3), (306, 2, 30_000, 1), (128, 4, 150_000, 1), (255, 4, 33_333, 2), (50, 4, 6_000, 1),
+    (255, 8, 60_000, 1), (100, 8, 5_000, 2)])
 def test_fir_tensor_core_complex_taps(R, monkeypatch, ntaps, deci, n, nchan):
     """fir_tcc_kernel (complex taps, deci 1/2/4): plain and fused-demod epilogues against the f64 truth and the FP32
     complex-tap kernel, ragged tiles, odd channel strides."""
