@@ -896,6 +896,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         const size_t bt1 = FIR_TC1_BT / h->deci;
         t.tiles_x = (long long)((work + bt1 - 1) / bt1);
         t.total_tiles = t.tiles_x * (long long)nchan;
+        if (t.total_tiles > 0x7fffffffll) return fail(RRC_ERR_INVALID, "fir: %lld tiles in one launch (limit 2^31 - 1)", t.total_tiles);
         RRC_TRY(fir_tcc_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0, (int)h->deci}, t, demod, st));
     } else if (use_tc && !h->cplx) {
         if (demod) return fail(RRC_ERR_INVALID, "fused demod needs a c32 FIR");
@@ -908,6 +909,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         const size_t btf = FIR_TCF_IN / h->deci;
         t.tiles_x = (long long)((out_n + btf - 1) / btf);
         t.total_tiles = t.tiles_x * (long long)nchan;
+        if (t.total_tiles > 0x7fffffffll) return fail(RRC_ERR_INVALID, "fir: %lld tiles in one launch (limit 2^31 - 1)", t.total_tiles);
         RRC_TRY(fir_tcf_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0, (int)h->deci}, t, st));
     } else if (use_tc && h->tc1) {
         const size_t work = demod ? out_n - 1 : out_n;
@@ -922,6 +924,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         const size_t bt1 = FIR_TC1_BT / h->deci;
         t.tiles_x = (long long)((work + bt1 - 1) / bt1);
         t.total_tiles = t.tiles_x * (long long)nchan;
+        if (t.total_tiles > 0x7fffffffll) return fail(RRC_ERR_INVALID, "fir: %lld tiles in one launch (limit 2^31 - 1)", t.total_tiles);
         RRC_TRY(fir_tc1_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0, (int)h->deci}, t, demod, st));
     } else if (use_tc) {
         const size_t work = demod ? out_n - 1 : out_n;
@@ -938,6 +941,7 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         const size_t bt = (size_t)h->tc_nm * 8 * 8 * h->tc_ntile;
         t.tiles_x = (long long)((work + bt - 1) / bt);
         t.total_tiles = t.tiles_x * (long long)nchan;
+        if (t.total_tiles > 0x7fffffffll) return fail(RRC_ERR_INVALID, "fir: %lld tiles in one launch (limit 2^31 - 1)", t.total_tiles);
         RRC_TRY(fir_tc_launch(FirTcGeom{h->device, h->tc_ntile, h->tc_nld, h->tc_KS, h->tc_smem, (int)h->deci}, t, demod, st));
     } else if (h->use_poly) {
         a.taps = h->taps_poly;

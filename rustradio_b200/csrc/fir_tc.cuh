@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc_kernel(const FirTcAr
 
     const long long nworkers = (long long)gridDim.x * NW;
     for (long long id = (long long)blockIdx.x * NW + warp; id < a.total_tiles; id += nworkers) {
-        const long long ch = id / a.tiles_x;
+        const long long ch = (long long)((unsigned)id / (unsigned)a.tiles_x);      // total_tiles < 2^31 (checked on the host): 32-bit division
         const long long ob = (id - ch * a.tiles_x) * BT;
         // ---- A. the lane's samples 2*(lane + 32*u), +1 (zero beyond the channel's `need` samples) ----
         float4 v[NLD];
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
 
     const long long nworkers = (long long)gridDim.x * NW;
     for (long long id = (long long)blockIdx.x * NW + warp; id < a.total_tiles; id += nworkers) {
-        const long long ch = id / a.tiles_x;
+        const long long ch = (long long)((unsigned)id / (unsigned)a.tiles_x);      // total_tiles < 2^31 (checked on the host): 32-bit division
         const long long ob = (id - ch * a.tiles_x) * BT;
         float4 v[NLD];
         {
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tc1_kernel(const FirTc1
         {   // the warp's NEXT tile -> L2 (one bulk prefetch), so that its loads are L2 hits one tile from now
             const long long nid = id + nworkers;
             if (!U8 && lane == 0 && nid < a.total_tiles) {
-                const long long nch = nid / a.tiles_x;
+                const long long nch = (long long)((unsigned)nid / (unsigned)a.tiles_x);
                 const long long nob = (nid - nch * a.tiles_x) * BT;
                 const float2* nin = a.in + nch * a.in_stride + nob * D;
                 if (a.need - nob * D >= L && (reinterpret_cast<unsigned long long>(nin) & 15ull) == 0)
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 3) fir_tcf_kernel(const FirTcf
 
     const long long nworkers = (long long)gridDim.x * NW;
     for (long long id = (long long)blockIdx.x * NW + warp; id < a.total_tiles; id += nworkers) {
-        const long long ch = id / a.tiles_x;
+        const long long ch = (long long)((unsigned)id / (unsigned)a.tiles_x);      // total_tiles < 2^31 (checked on the host): 32-bit division
         const long long ob = (id - ch * a.tiles_x) * BT;
         float4 v[NLD];
         {

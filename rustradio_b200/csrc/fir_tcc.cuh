@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 2) fir_tcc_kernel(const FirTcc
 
     const long long nworkers = (long long)gridDim.x * NW;
     for (long long id = (long long)blockIdx.x * NW + warp; id < a.total_tiles; id += nworkers) {
-        const long long ch = id / a.tiles_x;
+        const long long ch = (long long)((unsigned)id / (unsigned)a.tiles_x);      // total_tiles < 2^31 (checked on the host): 32-bit division
         const long long ob = (id - ch * a.tiles_x) * BT;
         float4 v[NLD];
         {
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(FIR_TC_THREADS, 2) fir_tcc_kernel(const FirTcc
         {   // the warp's NEXT tile -> L2 (one bulk prefetch), so that its loads are L2 hits one tile from now
             const long long nid = id + nworkers;
             if (lane == 0 && nid < a.total_tiles && !a.in_u8) {
-                const long long nch = nid / a.tiles_x;
+                const long long nch = (long long)((unsigned)nid / (unsigned)a.tiles_x);
                 const long long nob = (nid - nch * a.tiles_x) * BT;
                 const float2* nin = a.in + nch * a.in_stride + nob * D;
                 if (a.need - nob * D >= L && (reinterpret_cast<unsigned long long>(nin) & 15ull) == 0)
