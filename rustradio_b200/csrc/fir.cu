@@ -130,12 +130,11 @@ __device__ __noinline__ void fir_stage_u8(const unsigned short* __restrict__ in8
     }
 }
 
-// Stage the input span of tile `id` into `s_tile` (padded: one pad element after every S).
+// Stage the input span of tile `bx` of channel `ch` into `s_tile` (padded: one pad element after every S).
 template <typename ST, int R>
-__device__ __forceinline__ void fir_load_tile(const FirArgs& a, ST* s_tile, long long id, int deci, int S,
+__device__ __forceinline__ void fir_load_tile(const FirArgs& a, ST* s_tile, long long ch, long long bx, int deci, int S,
                                               int NT, int t, int bstride) {
     const int S1 = S + 1;
-    const long long ch = id / a.tiles_x, bx = id - ch * a.tiles_x;
     const ST* __restrict__ in = reinterpret_cast<const ST*>(a.in) + ch * a.in_stride;
     const int L = a.nseg * S;
     const long long g0 = bx * bstride * deci;
@@ -211,7 +210,7 @@ __global__ void __launch_bounds__(FIR_MAX_NT) fir_poly_kernel(const FirArgs a) {
     const long long ch = blockIdx.y;
     const long long ob = (long long)blockIdx.x * bstride;
 
-    fir_load_tile<ST, R>(a, s_tile, ch * a.tiles_x + blockIdx.x, deci, S, NT, t, bstride);
+    fir_load_tile<ST, R>(a, s_tile, ch, blockIdx.x, deci, S, NT, t, bstride);
     {   // taps -> smem (phase-major, zero padded to qpad per phase)
         const TT* __restrict__ gt = reinterpret_cast<const TT*>(a.taps);
         for (int i = t; i < ntap_tab; i += NT) s_taps[i] = gt[i];
@@ -384,7 +383,7 @@ __global__ void __launch_bounds__(FIR_MAX_NT) fir_rt_kernel(const FirArgs a) {
 
     const long long ch = blockIdx.y;
     const long long ob = (long long)blockIdx.x * bstride;
-    fir_load_tile<float2, R>(a, s_tile, ch * a.tiles_x + blockIdx.x, deci, S, NT, tid, bstride);
+    fir_load_tile<float2, R>(a, s_tile, ch, blockIdx.x, deci, S, NT, tid, bstride);
     {   // taps -> smem as (h, h) pairs, phase-major, zero padded to qpad per phase
         const float* __restrict__ gt = reinterpret_cast<const float*>(a.taps);
         for (int i = tid; i < ntap_tab; i += NT) {
