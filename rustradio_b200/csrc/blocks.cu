@@ -122,7 +122,12 @@ std::shared_ptr<Buffer> Buffer::create(size_t elem_size, size_t bytes, Residency
         }
         b->base_ = (char*)va; b->map_bytes_ = sz; b->vmm_handle_ = h; b->vmm_va_ = va;
         b->cap_ = sz / elem_size;
-        cudaMemset((void*)va, 0, sz);          // zero-initialised like the reference's tempfile (Appendix B.8)
+        // zero-initialised like the reference's tempfile (Appendix B.8).  The blocks run on a non-blocking stream, which
+        // does not wait for the legacy default stream: fill on that stream and wait, or a source's first H2D copy can
+        // be overwritten by a still-running cudaMemset (seen once as an all-zero RtlSdrDecode input in the GPU suite).
+        cudaStream_t zs = (cudaStream_t)graph_stream(device);
+        cudaMemsetAsync((void*)va, 0, sz, zs);
+        cudaStreamSynchronize(zs);
     }
     return b;
 }

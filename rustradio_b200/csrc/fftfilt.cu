@@ -456,6 +456,7 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
         if ((e = cudaMalloc((void**)&h->hist[i], bytes)) != cudaSuccess || (e = cudaMemset(h->hist[i], 0, bytes)) != cudaSuccess)
             return cleanup(fail(RRC_ERR_CUDA, "FftFilter history alloc failed: %s", cudaGetErrorString(e)));
     }
+    cudaStreamSynchronize(0);      // callers run on non-blocking streams, which do not wait for the default-stream fills
     *out = h;
     return RRC_OK;
 }

@@ -331,6 +331,7 @@ int rrc_hilbert_create(int device, const float* taps, size_t ntaps, rrc_hilbert_
         if ((e = cudaMalloc((void**)&h->hist[i], ntaps * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
         if ((e = cudaMemset(h->hist[i], 0, ntaps * sizeof(float))) != cudaSuccess) return bail(e, "cudaMemset");   // history: vec![0.0; ntaps]
     }
+    if ((e = cudaStreamSynchronize(0)) != cudaSuccess) return bail(e, "cudaStreamSynchronize");   // callers run on non-blocking streams
     if (h->smem > 48 * 1024 &&
         (e = cudaFuncSetAttribute(hilbert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem)) != cudaSuccess)
         return bail(e, "cudaFuncSetAttribute");
