@@ -56,12 +56,26 @@ int rrc_malloc_device(int device, size_t bytes, void** dev_ptr);
 int rrc_free_device(int device, void* dev_ptr);
 int rrc_malloc_pinned(size_t bytes, void** host_ptr);
 int rrc_free_pinned(void* host_ptr);
+/* Pinned host memory placed on the NUMA node of `device`'s PCIe root complex (sysfs numa_node of its bus id;
+ * anonymous mapping + mbind(MPOL_PREFERRED) + cudaHostRegister); plain rrc_malloc_pinned when the platform
+ * exposes no NUMA information.  Free with rrc_free_pinned. */
+int rrc_malloc_pinned_near(int device, size_t bytes, void** host_ptr);
+int rrc_device_numa_node(int device, int* node);             /* -1: unknown */
 int rrc_host_register(void* host_ptr, size_t bytes);      /* pin caller memory */
 int rrc_host_unregister(void* host_ptr);
 int rrc_memset_device(int device, void* dev_ptr, int value, size_t bytes, void* stream);
 int rrc_memcpy_h2d(int device, void* dev_dst, const void* host_src, size_t bytes, void* stream);
 int rrc_memcpy_d2h(int device, void* host_dst, const void* dev_src, size_t bytes, void* stream);
 int rrc_memcpy_d2d(int device, void* dev_dst, const void* dev_src, size_t bytes, void* stream);
+/* Peer access for time-segment shards: halos travel GPU to GPU over NVLink with plain loads /
+ * copies, no collective.  One process driving several GPUs: rrc_peer_enable + any device pointer of `peer`
+ * is then valid in kernels and copies on `device`.  One process per GPU: export a cudaMalloc'ed buffer
+ * (rrc_malloc_device) as a 64-byte IPC handle, ship it to the neighbour by any means, open it there. */
+int rrc_peer_enable(int device, int peer);
+int rrc_memcpy_peer(int dst_device, void* dst, int src_device, const void* src, size_t bytes, void* stream);
+int rrc_ipc_export(int device, void* dev_ptr, unsigned char handle[64]);
+int rrc_ipc_open(int device, const unsigned char handle[64], void** dev_ptr);
+int rrc_ipc_close(int device, void* dev_ptr);
 int rrc_stream_create(int device, void** stream);
 int rrc_stream_destroy(int device, void* stream);
 int rrc_stream_sync(int device, void* stream);
@@ -70,6 +84,9 @@ int rrc_device_sync(int device);
 int rrc_event_create(int device, void** event);
 int rrc_event_destroy(int device, void* event);
 int rrc_event_record(int device, void* event, void* stream);
+/* Stream-ordered visibility between streams: work enqueued on `stream` after this call runs
+ * after everything recorded into `event`. */
+int rrc_event_wait(int device, void* event, void* stream);
 int rrc_event_sync(int device, void* event);
 int rrc_event_elapsed_ms(int device, void* start, void* stop, float* ms);
 /* Fill a device buffer with the deterministic synthetic signal used by the
@@ -138,6 +155,11 @@ int rrc_fir_run_batch(rrc_fir_t* h, const void* in_dev, size_t in_stride, size_t
 int rrc_fir_c32_demod_run_batch(rrc_fir_t* h, const void* in_dev, size_t in_stride, size_t need,
                                 float gain, float* out_dev, size_t out_stride, size_t out_n,
                                 size_t nchan, void* stream);
+/* Host-buffer form of the fused channelizer: nchan channels of n_in samples each, channel c at
+ * in_host + c*n_in samples (u8 I/Q pairs after rrc_fir_set_input_u8iq: 2 bytes per sample over PCIe);
+ * channel c's floor((n_in-ntaps+1)/deci) - 1 demodulated floats go to out_host + c*out_stride. */
+int rrc_fir_c32_demod_run_host_batch(rrc_fir_t* h, const void* in_host, size_t n_in, size_t nchan, float gain,
+                                     float* out_host, size_t out_stride, size_t* n_out_per_chan);
 /* Host-buffer form: H2D -> kernel -> D2H, chunked and double-buffered, for a
  * whole stream of n_in samples; writes floor((n_in-ntaps+1)/deci) outputs
  * (0 if n_in < ntaps+deci-1) and returns the count in *n_out. */
@@ -170,6 +192,10 @@ int rrc_fftfilt_reset(rrc_fftfilt_t* h, void* stream);          /* zero the carr
  * device buffer: the left halo of a time-segment shard, e.g. received from the neighbouring
  * GPU over NVLink.  n_samples must be ntaps-1. */
 int rrc_fftfilt_set_history(rrc_fftfilt_t* h, const float* hist_dev_c32, size_t n_samples, void* stream);
+/* Zero-copy form: the NEXT run / decim_run reads its ntaps-1 sample left halo through `hist_dev_c32` itself
+ * (one-shot; e.g. the IPC- or peer-mapped tail of the left neighbour's input buffer: only the kernel's first
+ * block touches it, over NVLink).  The pointer must stay valid until that run has completed. */
+int rrc_fftfilt_set_history_ptr(rrc_fftfilt_t* h, const float* hist_dev_c32, size_t n_samples);
 /* calc_fft_size and nsamples exactly as the reference (src/fft_filter.rs:36-42,262-263). */
 int rrc_fftfilt_ref_fft_size(size_t ntaps, size_t* fft_size, size_t* nsamples);
 /* Device-side geometry actually used (FFT size, valid outputs per block). */
@@ -254,6 +280,11 @@ typedef struct rrc_resampler rrc_resampler_t;
 int rrc_resampler_create(int device, size_t elem_size, size_t interp, size_t deci, rrc_resampler_t** out);
 int rrc_resampler_destroy(rrc_resampler_t* h);
 int rrc_resampler_reset(rrc_resampler_t* h);
+/* Set the carried state (src/rational_resampler.rs:101-105).  A time-segment shard that owns outputs
+ * [k_lo, k_hi) starts at input s = floor(k_lo*deci/interp) with counter = s*interp - k_lo*deci (<= 0) and no
+ * pending sample.  pending_host != NULL (elem_size bytes, host memory) makes that sample the pending one;
+ * counter must then be > 0.  interp/deci are the gcd-reduced values (rrc_resampler_state). */
+int rrc_resampler_set_state(rrc_resampler_t* h, int64_t counter, const void* pending_host);
 /* State inspection (counter <= 0 between calls unless a sample is pending). */
 int rrc_resampler_state(const rrc_resampler_t* h, int64_t* interp, int64_t* deci, int64_t* counter, int* has_pending);
 /* One work() call on an input window of n_in and an output window of out_cap
@@ -382,7 +413,9 @@ int rrb_rstream_capacity(rrb_rstream_t* r, size_t* samples);
 int rrb_rstream_eof(rrb_rstream_t* r, int* eof);
 int rrb_rstream_drop(rrb_rstream_t* r);
 
-/* Constructors: `src` is consumed.  out_bytes/out_residency/device configure the output stream. */
+/* Constructors: `src` is consumed iff the call returns RRC_OK (on any error the caller still owns it and
+ * must drop it).  out_bytes/out_residency/device configure the output stream.  A device-resident `src`
+ * ring must live on `device` (RRC_ERR_INVALID otherwise: cross-device chains need a host edge). */
 int rrb_vector_source_new(const void* data, size_t n, size_t elem_size, uint64_t repeat,
                           size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
 int rrb_fir_filter_new(rrb_rstream_t* src, int cplx, const float* taps, size_t ntaps, size_t deci,

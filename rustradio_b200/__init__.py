@@ -11,7 +11,7 @@ from .api import (  # noqa: F401
     DeviceBuffer, PinnedBuffer, Fir, FftFilt, Resampler, quad_demod, quad_demod_host,
     rtlsdr_decode, rtlsdr_decode_host, rtlsdr_decode_plan, Fft, fftstream_plan,
     synth_f32, launch_count, fir_plan, fftfilt_plan, fftfilt_ref_fft_size,
-    Event, stream_sync, device_sync,
+    Event, stream_sync, device_sync, event_wait, device_numa_node, peer_enable, ipc_export, IpcMapping,
     Hilbert, make_window, hilbert_taps, multiply_const, add_const, complex_to_mag2, tee, IqBalance,
     iq_balance_alpha_from_tau, WINDOW_HAMMING, WINDOW_BLACKMAN, WINDOW_BLACKMAN_HARRIS, WINDOW_HAMMING_PARM,
     RRC_FIR_NO_REAL_TAP_FASTPATH, RRC_FIR_FORCE_GENERIC, RRC_FIR_NO_TENSOR,

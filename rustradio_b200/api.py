@@ -46,6 +46,13 @@ _SIGS = {
     "rrc_free_device": [_i, _vp],
     "rrc_malloc_pinned": [_sz, _P(_vp)],
     "rrc_free_pinned": [_vp],
+    "rrc_malloc_pinned_near": [_i, _sz, _P(_vp)],
+    "rrc_device_numa_node": [_i, _P(_i)],
+    "rrc_peer_enable": [_i, _i],
+    "rrc_memcpy_peer": [_i, _vp, _i, _vp, _sz, _vp],
+    "rrc_ipc_export": [_i, _vp, _vp],
+    "rrc_ipc_open": [_i, _vp, _P(_vp)],
+    "rrc_ipc_close": [_i, _vp],
     "rrc_host_register": [_vp, _sz],
     "rrc_host_unregister": [_vp],
     "rrc_memset_device": [_i, _vp, _i, _sz, _vp],
@@ -59,6 +66,7 @@ _SIGS = {
     "rrc_event_create": [_i, _P(_vp)],
     "rrc_event_destroy": [_i, _vp],
     "rrc_event_record": [_i, _vp, _vp],
+    "rrc_event_wait": [_i, _vp, _vp],
     "rrc_event_sync": [_i, _vp],
     "rrc_event_elapsed_ms": [_i, _vp, _vp, _P(_f)],
     "rrc_synth_f32": [_i, _u64, _u64, _vp, _sz, _vp],
@@ -77,11 +85,13 @@ _SIGS = {
     "rrc_fir_run_batch": [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _sz, _vp],
     "rrc_fir_c32_demod_run_batch": [_vp, _vp, _sz, _sz, _f, _vp, _sz, _sz, _sz, _vp],
     "rrc_fir_run_host": [_vp, _vp, _sz, _vp, _P(_sz)],
+    "rrc_fir_c32_demod_run_host_batch": [_vp, _vp, _sz, _sz, _f, _vp, _sz, _P(_sz)],
     "rrc_fftfilt_c32_create": [_i, _vp, _sz, _P(_vp)],
     "rrc_fftfilt_f32_create": [_i, _vp, _sz, _P(_vp)],
     "rrc_fftfilt_destroy": [_vp],
     "rrc_fftfilt_reset": [_vp, _vp],
     "rrc_fftfilt_set_history": [_vp, _vp, _sz, _vp],
+    "rrc_fftfilt_set_history_ptr": [_vp, _vp, _sz],
     "rrc_fftfilt_ref_fft_size": [_sz, _P(_sz), _P(_sz)],
     "rrc_fftfilt_geometry": [_vp, _P(_sz), _P(_sz)],
     "rrc_fftfilt_plan": [_sz, _sz, _sz, _sz, _P(_sz), _P(_sz), _P(_sz), _P(_sz), _P(_i)],
@@ -92,6 +102,7 @@ _SIGS = {
     "rrc_resampler_create": [_i, _sz, _sz, _sz, _P(_vp)],
     "rrc_resampler_destroy": [_vp],
     "rrc_resampler_reset": [_vp],
+    "rrc_resampler_set_state": [_vp, C.c_int64, _vp],
     "rrc_resampler_state": [_vp, _P(C.c_int64), _P(C.c_int64), _P(C.c_int64), _P(_i)],
     "rrc_resampler_run": [_vp, _vp, _sz, _vp, _sz, _P(_sz), _P(_sz), _P(_i), _vp],
     "rrc_resampler_run_host": [_vp, _vp, _sz, _vp, _sz, _P(_sz), _P(_sz)],
@@ -216,6 +227,50 @@ class Event:
             pass
 
 
+def event_wait(event: "Event", stream: int = 0) -> None:
+    _ck(lib().rrc_event_wait(event.device, event.h, stream))
+
+
+def device_numa_node(device: int = 0) -> int:
+    n = _i(0)
+    _ck(lib().rrc_device_numa_node(device, C.byref(n)))
+    return n.value
+
+
+def peer_enable(device: int, peer: int) -> None:
+    _ck(lib().rrc_peer_enable(device, peer))
+
+
+def ipc_export(buf) -> bytes:
+    """64-byte CUDA IPC handle of a DeviceBuffer (cudaMalloc allocation) for another process on this node."""
+    h = (C.c_ubyte * 64)()
+    _ck(lib().rrc_ipc_export(buf.device, buf.ptr, h))
+    return bytes(h)
+
+
+class IpcMapping:
+    """A peer process's device buffer mapped into this process (reads/writes go over NVLink)."""
+
+    def __init__(self, handle: bytes, device: int = 0):
+        assert len(handle) == 64
+        self.device = device
+        h = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        _ck(lib().rrc_ipc_open(device, h, C.byref(p)))
+        self.ptr = p.value
+
+    def close(self):
+        if self.ptr:
+            lib().rrc_ipc_close(self.device, self.ptr)
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DeviceBuffer:
     """Raw device allocation owned by the C library."""
 
@@ -264,11 +319,13 @@ class DeviceBuffer:
 class PinnedBuffer:
     """Page-locked host memory exposed as a numpy array."""
 
-    def __init__(self, dtype, count: int):
+    def __init__(self, dtype, count: int, near_device: int | None = None):
+        """near_device: place the pages on that GPU's NUMA node (rrc_malloc_pinned_near)."""
         self.dtype = np.dtype(dtype)
         self.count = int(count)
         p = C.c_void_p()
-        _ck(lib().rrc_malloc_pinned(max(self.count * self.dtype.itemsize, 1), C.byref(p)))
+        nbytes = max(self.count * self.dtype.itemsize, 1)
+        _ck(lib().rrc_malloc_pinned(nbytes, C.byref(p)) if near_device is None else lib().rrc_malloc_pinned_near(near_device, nbytes, C.byref(p)))
         self.ptr = p.value
         buf = (C.c_char * (self.count * self.dtype.itemsize)).from_address(self.ptr)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=self.count)
@@ -348,6 +405,14 @@ class Fir:
         _ck(lib().rrc_fir_c32_demod_run_batch(self.h, _ptr(d_in), in_stride, need, gain, _ptr(d_out), out_stride,
                                               out_n, nchan, stream))
 
+    def demod_run_host_batch(self, x, n_in: int, nchan: int, gain: float, out) -> int:
+        """Host buffers through the fused FIR + demod channelizer; returns outputs per channel."""
+        xa = x.array if isinstance(x, PinnedBuffer) else x
+        oa = out.array if isinstance(out, PinnedBuffer) else out
+        per = _sz(0)
+        _ck(lib().rrc_fir_c32_demod_run_host_batch(self.h, xa.ctypes.data, n_in, nchan, gain, oa.ctypes.data, len(oa) // nchan, C.byref(per)))
+        return per.value
+
     def run_host(self, x, out=None) -> np.ndarray:
         """Whole-stream host->host (pipelined H2D/kernel/D2H).  In u8 I/Q mode x is the byte array."""
         dt = np.complex64 if self.cplx else np.float32
@@ -424,6 +489,10 @@ class FftFilt:
     def set_history(self, d_hist, n: int, stream: int = 0):
         _ck(lib().rrc_fftfilt_set_history(self.h, _ptr(d_hist), n, stream))
 
+    def set_history_ptr(self, d_hist, n: int):
+        """One-shot: the next run reads its left halo through this (possibly peer-mapped) device pointer."""
+        _ck(lib().rrc_fftfilt_set_history_ptr(self.h, _ptr(d_hist), n))
+
     def run(self, d_in, n: int, d_out, stream: int = 0):
         _ck(lib().rrc_fftfilt_run(self.h, _ptr(d_in), n, _ptr(d_out), stream))
 
@@ -486,6 +555,12 @@ class Resampler:
     def reset(self):
         _ck(lib().rrc_resampler_reset(self.h))
 
+    def set_state(self, counter: int, pending: np.ndarray | None = None):
+        """Carried state of work() (src/rational_resampler.rs:101-105); see rrc_resampler_set_state."""
+        pa = None if pending is None else np.ascontiguousarray(pending)
+        assert pa is None or pa.nbytes == self.elem
+        _ck(lib().rrc_resampler_set_state(self.h, counter, None if pa is None else pa.ctypes.data))
+
     def run(self, d_in, n_in: int, d_out, out_cap: int, stream: int = 0):
         """(consumed, produced, wait_on_output)"""
         c, p = _sz(0), _sz(0)
@@ -500,6 +575,12 @@ class Resampler:
         c, p = _sz(0), _sz(0)
         _ck(lib().rrc_resampler_run_host(self.h, xa.ctypes.data, len(xa), out.ctypes.data, out_cap, C.byref(c), C.byref(p)))
         return c.value, out[: p.value]
+
+    def run_host_into(self, xin: np.ndarray, xout: np.ndarray):
+        """run_host on caller-owned (pinned) arrays: (consumed, produced)."""
+        c, p = _sz(0), _sz(0)
+        _ck(lib().rrc_resampler_run_host(self.h, xin.ctypes.data, len(xin), xout.ctypes.data, len(xout), C.byref(c), C.byref(p)))
+        return c.value, p.value
 
     def work(self, x: np.ndarray, out_cap: int):
         """One work() call on host arrays via device buffers: (wait_on_output, consumed, out)."""

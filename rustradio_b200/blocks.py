@@ -225,8 +225,13 @@ class Block:
 
 
 def _mk(fn, out_dtype, *args):
+    """Call a constructor.  A ReadStream among `args` is the block's input: the C side consumes it iff
+    the call returns RRC_OK (include/rustradio_cuda.h), so the Python wrapper gives up its handle only then."""
     b, o = _vp(), _vp()
-    _ck(fn(*args, C.byref(b), C.byref(o)))
+    _ck(fn(*[a.h if isinstance(a, ReadStream) else a for a in args], C.byref(b), C.byref(o)))
+    for a in args:
+        if isinstance(a, ReadStream):
+            a._take()
     return Block(b.value), ReadStream(o.value, out_dtype)
 
 
@@ -242,77 +247,78 @@ def FirFilter(src: ReadStream, taps, deci: int = 1, translate=None, flags: int =
     cplx = src.dtype == np.complex64
     t = np.ascontiguousarray(taps, np.complex64 if cplx else np.float32)
     tr = translate or (0.0, 0.0)
-    return _mk(_L().rrb_fir_filter_new, src.dtype, src._take(), int(cplx), t.ctypes.data if len(t) else None, len(t), deci,
+    return _mk(_L().rrb_fir_filter_new, src.dtype, src, int(cplx), t.ctypes.data if len(t) else None, len(t), deci,
                int(translate is not None), tr[0], tr[1], flags, size_bytes, residency, device)
 
 
 def FftFilter(src: ReadStream, taps, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     t = np.ascontiguousarray(taps, np.complex64)
-    return _mk(_L().rrb_fft_filter_new, np.complex64, src._take(), t.ctypes.data if len(t) else None, len(t),
+    return _mk(_L().rrb_fft_filter_new, np.complex64, src, t.ctypes.data if len(t) else None, len(t),
                size_bytes, residency, device)
 
 
 def FftFilterFloat(src: ReadStream, taps, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     t = np.ascontiguousarray(taps, np.float32)
-    return _mk(_L().rrb_fft_filter_float_new, np.float32, src._take(), t.ctypes.data if len(t) else None, len(t),
+    return _mk(_L().rrb_fft_filter_float_new, np.float32, src, t.ctypes.data if len(t) else None, len(t),
                size_bytes, residency, device)
 
 
 def RationalResampler(src: ReadStream, interp: int, deci: int, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     if interp == 0 or deci == 0:
         raise RrcError(-1, f"RationalResampler created using {'interp' if interp == 0 else 'deci'} 0")
-    return _mk(_L().rrb_rational_resampler_new, src.dtype, src._take(), interp, deci, size_bytes, residency, device)
+    return _mk(_L().rrb_rational_resampler_new, src.dtype, src, interp, deci, size_bytes, residency, device)
 
 
 def QuadratureDemod(src: ReadStream, gain: float, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
-    return _mk(_L().rrb_quadrature_demod_new, np.float32, src._take(), gain, size_bytes, residency, device)
+    return _mk(_L().rrb_quadrature_demod_new, np.float32, src, gain, size_bytes, residency, device)
 
 
 def FftStream(src: ReadStream, size: int, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     """FftStream::new(src, size) (src/fft_stream.rs:38-60)."""
-    return _mk(_L().rrb_fft_stream_new, np.complex64, src._take(), size, size_bytes, residency, device)
+    return _mk(_L().rrb_fft_stream_new, np.complex64, src, size, size_bytes, residency, device)
 
 
 def RtlSdrDecode(src: ReadStream, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     """RtlSdrDecode::new(src) (src/rtlsdr_decode.rs:9-16): ReadStream<u8> -> ReadStream<Complex>."""
-    return _mk(_L().rrb_rtlsdr_decode_new, np.complex64, src._take(), size_bytes, residency, device)
+    return _mk(_L().rrb_rtlsdr_decode_new, np.complex64, src, size_bytes, residency, device)
 
 
 def Hilbert(src: ReadStream, ntaps: int, window_type: int = 0, window_parm: float = 0.0, size_bytes=DEFAULT_STREAM_SIZE,
             residency=DEVICE, device=0):
     """Hilbert::new(src, ntaps, &window_type) (src/hilbert.rs:35-60): ReadStream<Float> -> ReadStream<Complex>."""
-    return _mk(_L().rrb_hilbert_new, np.complex64, src._take(), ntaps, window_type, window_parm, size_bytes, residency, device)
+    return _mk(_L().rrb_hilbert_new, np.complex64, src, ntaps, window_type, window_parm, size_bytes, residency, device)
 
 
 def MultiplyConst(src: ReadStream, val, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     """MultiplyConst::new(src, val) (src/multiply_const.rs:5-23)."""
     cplx = src.dtype == np.complex64
     v = complex(val)
-    return _mk(_L().rrb_multiply_const_new, src.dtype, src._take(), int(cplx), v.real, v.imag, size_bytes, residency, device)
+    return _mk(_L().rrb_multiply_const_new, src.dtype, src, int(cplx), v.real, v.imag, size_bytes, residency, device)
 
 
 def AddConst(src: ReadStream, val, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     """AddConst::new(src, val) (src/add_const.rs:24-44)."""
     cplx = src.dtype == np.complex64
     v = complex(val)
-    return _mk(_L().rrb_add_const_new, src.dtype, src._take(), int(cplx), v.real, v.imag, size_bytes, residency, device)
+    return _mk(_L().rrb_add_const_new, src.dtype, src, int(cplx), v.real, v.imag, size_bytes, residency, device)
 
 
 def ComplexToMag2(src: ReadStream, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     """ComplexToMag2::new(src) (src/complex_to_mag2.rs:7-20)."""
-    return _mk(_L().rrb_complex_to_mag2_new, np.float32, src._take(), size_bytes, residency, device)
+    return _mk(_L().rrb_complex_to_mag2_new, np.float32, src, size_bytes, residency, device)
 
 
 def IqBalance(src: ReadStream, alpha: float, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     """IqBalance::with_alpha(src, alpha) (src/iq_balance.rs:62-73)."""
-    return _mk(_L().rrb_iq_balance_new, np.complex64, src._take(), alpha, size_bytes, residency, device)
+    return _mk(_L().rrb_iq_balance_new, np.complex64, src, alpha, size_bytes, residency, device)
 
 
 def Tee(src: ReadStream, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     """Tee::new(src) -> (block, out1, out2) (src/tee.rs:9-18)."""
     b, o1, o2 = _vp(), _vp(), _vp()
     dt = src.dtype
-    _ck(_L().rrb_tee_new(src._take(), size_bytes, residency, device, C.byref(b), C.byref(o1), C.byref(o2)))
+    _ck(_L().rrb_tee_new(src.h, size_bytes, residency, device, C.byref(b), C.byref(o1), C.byref(o2)))
+    src._take()
     return Block(b.value), ReadStream(o1.value, dt), ReadStream(o2.value, dt)
 
 

@@ -265,6 +265,15 @@ static int finish_output(Buffer& b, char* win, size_t bytes, Scratch& s, int dev
     return RRC_OK;
 }
 
+// A device-resident input ring must live on the block's own device: the VMM mapping only has
+// access rights for its device and ordering between blocks relies on the per-device graph stream.
+static int check_src_device(ReadStream& src, int device, const char* who) {
+    if (src.buffer().residency() == Residency::Device && src.buffer().device() != device)
+        return fail(RRC_ERR_INVALID, "%s: input ring lives on device %d, block runs on device %d (cross-device chains need a host edge)",
+                    who, src.buffer().device(), device);
+    return RRC_OK;
+}
+
 static int make_output(size_t elem, const StreamOpts& o, std::unique_ptr<WriteStream>* w, std::unique_ptr<ReadStream>* r) {
     std::string err;
     StreamPair p = new_stream(elem, o.bytes, o.res, o.device, &err);
@@ -274,18 +283,19 @@ static int make_output(size_t elem, const StreamOpts& o, std::unique_ptr<WriteSt
 }
 
 // ------------------------------------------------------------------ FirFilter -----
-int FirFilter::create(std::unique_ptr<ReadStream> src, bool cplx, const float* taps, size_t ntaps, size_t deci,
+int FirFilter::create(std::unique_ptr<ReadStream>& src, bool cplx, const float* taps, size_t ntaps, size_t deci,
                       bool translate, float samp_rate, float freq, unsigned flags, const StreamOpts& o,
                       std::unique_ptr<FirFilter>* out) {
     if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    RRC_TRY(check_src_device(*src, o.device, "block constructor"));
     std::unique_ptr<FirFilter> b(new FirFilter());
     b->cplx_ = cplx; b->ntaps_ = ntaps; b->deci_ = deci; b->elem_ = cplx ? 8 : 4; b->device_ = o.device;
     if (src->buffer().elem() != b->elem_) return fail(RRC_ERR_INVALID, "FirFilter: stream element size mismatch");
     RRC_TRY(cplx ? rrc_fir_c32_create(o.device, taps, ntaps, deci, flags, &b->h_)
                  : rrc_fir_f32_create(o.device, taps, ntaps, deci, flags, &b->h_));
     if (translate) RRC_TRY(rrc_fir_set_translate(b->h_, samp_rate, freq));
-    b->src_ = std::move(src);
     RRC_TRY(make_output(b->elem_, o, &b->dst_, &b->out_r_));
+    b->src_ = std::move(src);                 // last fallible step is behind us: `src` is consumed iff RRC_OK
     *out = std::move(b);
     return RRC_OK;
 }
@@ -307,6 +317,10 @@ int FirFilter::work(BlockRet* ret) {          // src/fir.rs:492-550
     RRC_TRY(stage_output(dst_->buffer(), outp, out_n * elem_, sout_, device_, &dout));
     RRC_TRY(rrc_fir_run(h_, din, need, dout, out_n, graph_stream(device_)));
     RRC_TRY(finish_output(dst_->buffer(), outp, out_n * elem_, sout_, device_));
+    // a host-resident input window was staged with an async copy: it must have left the ring before consume()
+    // hands the space back to the producer (matters once the host ring is pinned)
+    if (src_->buffer().residency() == Residency::Host && dst_->buffer().residency() == Residency::Device)
+        RRC_CUDA(cudaStreamSynchronize((cudaStream_t)graph_stream(device_)));
     tags.erase(std::remove_if(tags.begin(), tags.end(), [&](const Tag& t) { return t.pos >= n; }), tags.end());   // :536
     src_->buffer().consume(n);                                                                                   // :537
     if (deci_ != 1) for (Tag& t : tags) t.pos /= deci_;                                                          // :541-543
@@ -316,9 +330,10 @@ int FirFilter::work(BlockRet* ret) {          // src/fir.rs:492-550
 }
 
 // ------------------------------------------------------------------ FftFilter -----
-int FftFilter::create(std::unique_ptr<ReadStream> src, const float* taps, size_t ntaps, const StreamOpts& o,
+int FftFilter::create(std::unique_ptr<ReadStream>& src, const float* taps, size_t ntaps, const StreamOpts& o,
                       std::unique_ptr<FftFilter>* out, bool real) {
     if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    RRC_TRY(check_src_device(*src, o.device, "block constructor"));
     const size_t elem = real ? 4 : 8;
     if (src->buffer().elem() != elem) return fail(RRC_ERR_INVALID, real ? "FftFilter(real): stream must carry f32" : "FftFilter: stream must carry Complex<f32>");
     std::unique_ptr<FftFilter> b(new FftFilter());
@@ -328,8 +343,8 @@ int FftFilter::create(std::unique_ptr<ReadStream> src, const float* taps, size_t
     RRC_TRY(rrc_fftfilt_ref_fft_size(ntaps, &fft_size, &b->nsamples_));
     RRC_CUDA(cudaSetDevice(o.device));
     RRC_CUDA(cudaMalloc((void**)&b->partial_, b->nsamples_ * elem));
-    b->src_ = std::move(src);
     RRC_TRY(make_output(elem, o, &b->dst_, &b->out_r_));
+    b->src_ = std::move(src);                 // last fallible step is behind us: `src` is consumed iff RRC_OK
     *out = std::move(b);
     return RRC_OK;
 }
@@ -407,9 +422,10 @@ int FftFilter::work(BlockRet* ret) {          // src/fft_filter.rs:290-354, whol
 // for the same number of SAMPLES as the reference's Complex inner streams, so counts, BlockRets and tag
 // positions per work() call are unchanged.
 
-int FftFilterFloat::create(std::unique_ptr<ReadStream> src, const float* taps, size_t ntaps, const StreamOpts& o,
+int FftFilterFloat::create(std::unique_ptr<ReadStream>& src, const float* taps, size_t ntaps, const StreamOpts& o,
                            std::unique_ptr<FftFilterFloat>* out) {
     if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    RRC_TRY(check_src_device(*src, o.device, "block constructor"));
     if (src->buffer().elem() != 4) return fail(RRC_ERR_INVALID, "FftFilterFloat: stream must carry f32");
     if (!taps || ntaps == 0) return fail(RRC_ERR_INVALID, "FftFilterFloat needs at least one tap");
     std::unique_ptr<FftFilterFloat> b(new FftFilterFloat());
@@ -422,10 +438,10 @@ int FftFilterFloat::create(std::unique_ptr<ReadStream> src, const float* taps, s
     if (!p.w) return fail(RRC_ERR_CUDA, "new_stream failed: %s", err.c_str());
     b->inner_in_ = std::move(p.w);
     b->inner_in_id_ = b->inner_in_->id();
-    RRC_TRY(FftFilter::create(std::move(p.r), taps, ntaps, inner, &b->complex_, /*real=*/true));
+    RRC_TRY(FftFilter::create(p.r, taps, ntaps, inner, &b->complex_, /*real=*/true));
     b->inner_out_ = b->complex_->take_output();
-    b->src_ = std::move(src);
     RRC_TRY(make_output(4, o, &b->dst_, &b->out_r_));
+    b->src_ = std::move(src);                 // last fallible step is behind us: `src` is consumed iff RRC_OK
     *out = std::move(b);
     return RRC_OK;
 }
@@ -477,14 +493,15 @@ int FftFilterFloat::work(BlockRet* ret) {     // src/fft_filter.rs:428-490
 }
 
 // ---------------------------------------------------------- RationalResampler -----
-int RationalResampler::create(std::unique_ptr<ReadStream> src, size_t interp, size_t deci, const StreamOpts& o,
+int RationalResampler::create(std::unique_ptr<ReadStream>& src, size_t interp, size_t deci, const StreamOpts& o,
                               std::unique_ptr<RationalResampler>* out) {
     if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    RRC_TRY(check_src_device(*src, o.device, "block constructor"));
     std::unique_ptr<RationalResampler> b(new RationalResampler());
     b->device_ = o.device; b->elem_ = src->buffer().elem();
     RRC_TRY(rrc_resampler_create(o.device, b->elem_, interp, deci, &b->h_));   // Err on 0 (:130-135)
-    b->src_ = std::move(src);
     RRC_TRY(make_output(b->elem_, o, &b->dst_, &b->out_r_));
+    b->src_ = std::move(src);                 // last fallible step is behind us: `src` is consumed iff RRC_OK
     *out = std::move(b);
     return RRC_OK;
 }
@@ -516,14 +533,15 @@ int RationalResampler::work(BlockRet* ret) {  // src/rational_resampler.rs:155-2
 }
 
 // ------------------------------------------------------------ QuadratureDemod -----
-int QuadratureDemod::create(std::unique_ptr<ReadStream> src, float gain, const StreamOpts& o,
+int QuadratureDemod::create(std::unique_ptr<ReadStream>& src, float gain, const StreamOpts& o,
                             std::unique_ptr<QuadratureDemod>* out) {
     if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    RRC_TRY(check_src_device(*src, o.device, "block constructor"));
     if (src->buffer().elem() != 8) return fail(RRC_ERR_INVALID, "QuadratureDemod: stream must carry Complex<f32>");
     std::unique_ptr<QuadratureDemod> b(new QuadratureDemod());
     b->device_ = o.device; b->gain_ = gain;
-    b->src_ = std::move(src);
     RRC_TRY(make_output(4, o, &b->dst_, &b->out_r_));
+    b->src_ = std::move(src);                 // last fallible step is behind us: `src` is consumed iff RRC_OK
     *out = std::move(b);
     return RRC_OK;
 }
@@ -552,18 +570,19 @@ static Tag mk_tag_bool(size_t pos, const char* key, bool v);
 static Tag mk_tag_u64(size_t pos, const char* key, uint64_t v);
 
 // ------------------------------------------------------------------ FftStream -----
-int FftStream::create(std::unique_ptr<ReadStream> src, size_t size, const StreamOpts& o, std::unique_ptr<FftStream>* out) {
+int FftStream::create(std::unique_ptr<ReadStream>& src, size_t size, const StreamOpts& o, std::unique_ptr<FftStream>* out) {
     if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    RRC_TRY(check_src_device(*src, o.device, "block constructor"));
     if (src->buffer().elem() != 8) return fail(RRC_ERR_INVALID, "FftStream: stream must carry Complex<f32>");
     if (size == 0) return fail(RRC_ERR_INVALID, "FFT size must be nonzero (src/fft_stream.rs:42)");
     std::unique_ptr<FftStream> b(new FftStream());
     b->device_ = o.device; b->size_ = size;
-    b->src_ = std::move(src);
     RRC_TRY(make_output(8, o, &b->dst_, &b->out_r_));
     char* w; size_t cap;
     b->dst_->buffer().write_window(&w, &cap);
     if (size > cap) return fail(RRC_ERR_INVALID, "FFT size (%zu) must be no bigger than stream size (%zu) (src/fft_stream.rs:46-50)", size, cap);
     RRC_TRY(rrc_fft_c32_create(o.device, size, &b->h_));
+    b->src_ = std::move(src);                 // last fallible step is behind us: `src` is consumed iff RRC_OK
     *out = std::move(b);
     return RRC_OK;
 }
@@ -598,13 +617,14 @@ int FftStream::work(BlockRet* ret) {          // src/fft_stream.rs:71-117 (one b
 }
 
 // --------------------------------------------------------------- RtlSdrDecode -----
-int RtlSdrDecode::create(std::unique_ptr<ReadStream> src, const StreamOpts& o, std::unique_ptr<RtlSdrDecode>* out) {
+int RtlSdrDecode::create(std::unique_ptr<ReadStream>& src, const StreamOpts& o, std::unique_ptr<RtlSdrDecode>* out) {
     if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    RRC_TRY(check_src_device(*src, o.device, "block constructor"));
     if (src->buffer().elem() != 1) return fail(RRC_ERR_INVALID, "RtlSdrDecode: stream must carry u8");
     std::unique_ptr<RtlSdrDecode> b(new RtlSdrDecode());
     b->device_ = o.device;
-    b->src_ = std::move(src);
     RRC_TRY(make_output(8, o, &b->dst_, &b->out_r_));
+    b->src_ = std::move(src);                 // last fallible step is behind us: `src` is consumed iff RRC_OK
     *out = std::move(b);
     return RRC_OK;
 }
@@ -632,9 +652,10 @@ int RtlSdrDecode::work(BlockRet* ret) {       // src/rtlsdr_decode.rs:18-48
 }
 
 // -------------------------------------------------------------------- Hilbert -----
-int Hilbert::create(std::unique_ptr<ReadStream> src, size_t ntaps, int window_type, float window_parm, const StreamOpts& o,
+int Hilbert::create(std::unique_ptr<ReadStream>& src, size_t ntaps, int window_type, float window_parm, const StreamOpts& o,
                     std::unique_ptr<Hilbert>* out) {
     if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    RRC_TRY(check_src_device(*src, o.device, "block constructor"));
     if (src->buffer().elem() != 4) return fail(RRC_ERR_INVALID, "Hilbert: stream must carry f32");
     if (!(ntaps > 1 && (ntaps & 1) == 1)) return fail(RRC_ERR_INVALID, "hilbert filter len must be odd and greater than 1 (src/hilbert.rs:44-47)");
     std::vector<float> win(ntaps), taps(ntaps);
@@ -643,8 +664,8 @@ int Hilbert::create(std::unique_ptr<ReadStream> src, size_t ntaps, int window_ty
     std::unique_ptr<Hilbert> b(new Hilbert());
     b->device_ = o.device;
     RRC_TRY(rrc_hilbert_create(o.device, taps.data(), ntaps, &b->h_));
-    b->src_ = std::move(src);
     RRC_TRY(make_output(8, o, &b->dst_, &b->out_r_));
+    b->src_ = std::move(src);                 // last fallible step is behind us: `src` is consumed iff RRC_OK
     *out = std::move(b);
     return RRC_OK;
 }
@@ -672,9 +693,10 @@ int Hilbert::work(BlockRet* ret) {            // src/hilbert.rs:72-128 (one pass
 }
 
 // -------------------------------------------------------------------- SyncMap -----
-int SyncMap::create(std::unique_ptr<ReadStream> src, Op op, bool cplx, float val_re, float val_im, const StreamOpts& o,
+int SyncMap::create(std::unique_ptr<ReadStream>& src, Op op, bool cplx, float val_re, float val_im, const StreamOpts& o,
                     std::unique_ptr<SyncMap>* out) {
     if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    RRC_TRY(check_src_device(*src, o.device, "block constructor"));
     std::unique_ptr<SyncMap> b(new SyncMap());
     if (op == Op::ComplexToMag2 || op == Op::IqBalance) cplx = true;
     b->op_ = op; b->cplx_ = cplx; b->re_ = val_re; b->im_ = val_im; b->device_ = o.device;
@@ -682,8 +704,8 @@ int SyncMap::create(std::unique_ptr<ReadStream> src, Op op, bool cplx, float val
     b->out_elem_ = op == Op::ComplexToMag2 ? 4 : b->in_elem_;
     if (src->buffer().elem() != b->in_elem_) return fail(RRC_ERR_INVALID, "sync block: stream element size mismatch");
     if (op == Op::IqBalance) RRC_TRY(rrc_iq_balance_create(o.device, val_re, &b->iq_));
-    b->src_ = std::move(src);
     RRC_TRY(make_output(b->out_elem_, o, &b->dst_, &b->out_r_));
+    b->src_ = std::move(src);                 // last fallible step is behind us: `src` is consumed iff RRC_OK
     *out = std::move(b);
     return RRC_OK;
 }
@@ -731,13 +753,14 @@ int SyncMap::work(BlockRet* ret) {            // rustradio_macros_code/src/lib.r
 }
 
 // ------------------------------------------------------------------------ Tee -----
-int Tee::create(std::unique_ptr<ReadStream> src, const StreamOpts& o, std::unique_ptr<Tee>* out) {
+int Tee::create(std::unique_ptr<ReadStream>& src, const StreamOpts& o, std::unique_ptr<Tee>* out) {
     if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    RRC_TRY(check_src_device(*src, o.device, "block constructor"));
     std::unique_ptr<Tee> b(new Tee());
     b->device_ = o.device; b->elem_ = src->buffer().elem();
-    b->src_ = std::move(src);
     RRC_TRY(make_output(b->elem_, o, &b->dst1_, &b->out_r_));
     RRC_TRY(make_output(b->elem_, o, &b->dst2_, &b->out2_r_));
+    b->src_ = std::move(src);                 // last fallible step is behind us: `src` is consumed iff RRC_OK
     *out = std::move(b);
     return RRC_OK;
 }

@@ -206,7 +206,7 @@ private:
 class FirFilter : public Block {
 public:
     // FirFilter::builder(taps).deci(deci).translate(samp_rate, freq).build(src); cplx = T is Complex.
-    static int create(std::unique_ptr<ReadStream> src, bool cplx, const float* taps, size_t ntaps, size_t deci,
+    static int create(std::unique_ptr<ReadStream>& src, bool cplx, const float* taps, size_t ntaps, size_t deci,
                       bool translate, float samp_rate, float freq, unsigned flags, const StreamOpts& o,
                       std::unique_ptr<FirFilter>* out);
     ~FirFilter() override;
@@ -228,7 +228,7 @@ class FftFilter : public Block {
 public:
     // real = false: FftFilter (Complex stream, Complex taps).  real = true: the inner filter of
     // FftFilterFloat — f32 stream, `taps` are f32, the device runs the real-stream kernel mode.
-    static int create(std::unique_ptr<ReadStream> src, const float* taps, size_t ntaps, const StreamOpts& o,
+    static int create(std::unique_ptr<ReadStream>& src, const float* taps, size_t ntaps, const StreamOpts& o,
                       std::unique_ptr<FftFilter>* out, bool real = false);
     ~FftFilter() override;
     int work(BlockRet* ret) override;
@@ -249,7 +249,7 @@ private:
 
 class FftFilterFloat : public Block {
 public:
-    static int create(std::unique_ptr<ReadStream> src, const float* taps, size_t ntaps, const StreamOpts& o,
+    static int create(std::unique_ptr<ReadStream>& src, const float* taps, size_t ntaps, const StreamOpts& o,
                       std::unique_ptr<FftFilterFloat>* out);
     int work(BlockRet* ret) override;
     const char* block_name() const override { return "FftFilterFloat"; }
@@ -268,7 +268,7 @@ private:
 
 class RationalResampler : public Block {
 public:
-    static int create(std::unique_ptr<ReadStream> src, size_t interp, size_t deci, const StreamOpts& o,
+    static int create(std::unique_ptr<ReadStream>& src, size_t interp, size_t deci, const StreamOpts& o,
                       std::unique_ptr<RationalResampler>* out);
     ~RationalResampler() override;
     int work(BlockRet* ret) override;
@@ -286,7 +286,7 @@ private:
 
 class QuadratureDemod : public Block {
 public:
-    static int create(std::unique_ptr<ReadStream> src, float gain, const StreamOpts& o,
+    static int create(std::unique_ptr<ReadStream>& src, float gain, const StreamOpts& o,
                       std::unique_ptr<QuadratureDemod>* out);
     int work(BlockRet* ret) override;
     const char* block_name() const override { return "QuadratureDemod"; }
@@ -303,7 +303,7 @@ private:
 // FftStream (src/fft_stream.rs:27-117): forward FFT of every `size` samples, frame tags.
 class FftStream : public Block {
 public:
-    static int create(std::unique_ptr<ReadStream> src, size_t size, const StreamOpts& o, std::unique_ptr<FftStream>* out);
+    static int create(std::unique_ptr<ReadStream>& src, size_t size, const StreamOpts& o, std::unique_ptr<FftStream>* out);
     ~FftStream() override;
     int work(BlockRet* ret) override;
     const char* block_name() const override { return "FftStream"; }
@@ -321,7 +321,7 @@ private:
 // RtlSdrDecode (src/rtlsdr_decode.rs:9-48): ReadStream<u8> -> WriteStream<Complex>.
 class RtlSdrDecode : public Block {
 public:
-    static int create(std::unique_ptr<ReadStream> src, const StreamOpts& o, std::unique_ptr<RtlSdrDecode>* out);
+    static int create(std::unique_ptr<ReadStream>& src, const StreamOpts& o, std::unique_ptr<RtlSdrDecode>* out);
     int work(BlockRet* ret) override;
     const char* block_name() const override { return "RtlSdrDecode"; }
     bool eof() override { return src_->eof(); }
@@ -337,7 +337,7 @@ private:
 class Hilbert : public Block {
 public:
     // Hilbert::new(src, ntaps, &window_type): taps = fir::hilbert(window_type.make_window(ntaps)).
-    static int create(std::unique_ptr<ReadStream> src, size_t ntaps, int window_type, float window_parm, const StreamOpts& o,
+    static int create(std::unique_ptr<ReadStream>& src, size_t ntaps, int window_type, float window_parm, const StreamOpts& o,
                       std::unique_ptr<Hilbert>* out);
     ~Hilbert() override;
     int work(BlockRet* ret) override;
@@ -358,7 +358,7 @@ class SyncMap : public Block {
 public:
     enum class Op : int { MultiplyConst = 0, AddConst = 1, ComplexToMag2 = 2, IqBalance = 3 };
     // cplx: T = Complex (val = re + i*im) or Float (val = re); IqBalance: val_re = alpha.
-    static int create(std::unique_ptr<ReadStream> src, Op op, bool cplx, float val_re, float val_im, const StreamOpts& o,
+    static int create(std::unique_ptr<ReadStream>& src, Op op, bool cplx, float val_re, float val_im, const StreamOpts& o,
                       std::unique_ptr<SyncMap>* out);
     ~SyncMap() override;
     int work(BlockRet* ret) override;
@@ -380,7 +380,7 @@ private:
 // Tee<T> (src/tee.rs:9-24): every sample and every tag goes to both outputs.
 class Tee : public Block {
 public:
-    static int create(std::unique_ptr<ReadStream> src, const StreamOpts& o, std::unique_ptr<Tee>* out);
+    static int create(std::unique_ptr<ReadStream>& src, const StreamOpts& o, std::unique_ptr<Tee>* out);
     int work(BlockRet* ret) override;
     const char* block_name() const override { return "Tee"; }
     bool eof() override { return src_->eof(); }

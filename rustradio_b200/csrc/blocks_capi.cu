@@ -28,7 +28,8 @@ rr::StreamOpts opts(size_t bytes, int residency, int device) {
 }
 
 template <typename B>
-int finish(std::unique_ptr<B> b, rrb_block_t** blk, rrb_rstream_t** out) {
+int finish(std::unique_ptr<B> b, rrb_block_t** blk, rrb_rstream_t** out, rrb_rstream_t* src = nullptr) {
+    if (src) delete src;               // its stream has been moved into the block
     auto* r = new rrb_rstream();
     r->s = b->take_output();
     auto* h = new rrb_block();
@@ -37,11 +38,9 @@ int finish(std::unique_ptr<B> b, rrb_block_t** blk, rrb_rstream_t** out) {
     return RRC_OK;
 }
 
-std::unique_ptr<rr::ReadStream> take(rrb_rstream_t* src) {
-    std::unique_ptr<rr::ReadStream> s = std::move(src->s);
-    delete src;
-    return s;
-}
+// Ownership rule of every constructor (documented in the header): `src` is consumed iff the call
+// returns RRC_OK.  create() moves the stream out of the wrapper only after its last fallible step;
+// the wrapper itself is deleted by finish().
 
 }  // namespace
 
@@ -162,23 +161,23 @@ int rrb_fir_filter_new(rrb_rstream_t* src, int cplx, const float* taps, size_t n
                        rrb_block_t** blk, rrb_rstream_t** out) {
     if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
     std::unique_ptr<rr::FirFilter> b;
-    RRC_TRY(rr::FirFilter::create(take(src), cplx != 0, taps, ntaps, deci, translate != 0, samp_rate, freq, flags,
+    RRC_TRY(rr::FirFilter::create(src->s, cplx != 0, taps, ntaps, deci, translate != 0, samp_rate, freq, flags,
                                   opts(bytes, res, device), &b));
-    return finish(std::move(b), blk, out);
+    return finish(std::move(b), blk, out, src);
 }
 int rrb_fft_filter_new(rrb_rstream_t* src, const float* taps, size_t ntaps, size_t bytes, int res, int device,
                        rrb_block_t** blk, rrb_rstream_t** out) {
     if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
     std::unique_ptr<rr::FftFilter> b;
-    RRC_TRY(rr::FftFilter::create(take(src), taps, ntaps, opts(bytes, res, device), &b));
-    return finish(std::move(b), blk, out);
+    RRC_TRY(rr::FftFilter::create(src->s, taps, ntaps, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out, src);
 }
 int rrb_fft_filter_float_new(rrb_rstream_t* src, const float* taps, size_t ntaps, size_t bytes, int res, int device,
                              rrb_block_t** blk, rrb_rstream_t** out) {
     if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
     std::unique_ptr<rr::FftFilterFloat> b;
-    RRC_TRY(rr::FftFilterFloat::create(take(src), taps, ntaps, opts(bytes, res, device), &b));
-    return finish(std::move(b), blk, out);
+    RRC_TRY(rr::FftFilterFloat::create(src->s, taps, ntaps, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out, src);
 }
 int rrb_rational_resampler_new(rrb_rstream_t* src, size_t interp, size_t deci, size_t bytes, int res, int device,
                                rrb_block_t** blk, rrb_rstream_t** out) {
@@ -188,28 +187,28 @@ int rrb_rational_resampler_new(rrb_rstream_t* src, size_t interp, size_t deci, s
     if (deci == 0) return fail(RRC_ERR_INVALID, "RationalResampler created using deci 0");
     if (interp == 0) return fail(RRC_ERR_INVALID, "RationalResampler created using interp 0");
     std::unique_ptr<rr::RationalResampler> b;
-    RRC_TRY(rr::RationalResampler::create(take(src), interp, deci, opts(bytes, res, device), &b));
-    return finish(std::move(b), blk, out);
+    RRC_TRY(rr::RationalResampler::create(src->s, interp, deci, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out, src);
 }
 int rrb_quadrature_demod_new(rrb_rstream_t* src, float gain, size_t bytes, int res, int device,
                              rrb_block_t** blk, rrb_rstream_t** out) {
     if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
     std::unique_ptr<rr::QuadratureDemod> b;
-    RRC_TRY(rr::QuadratureDemod::create(take(src), gain, opts(bytes, res, device), &b));
-    return finish(std::move(b), blk, out);
+    RRC_TRY(rr::QuadratureDemod::create(src->s, gain, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out, src);
 }
 
 int rrb_fft_stream_new(rrb_rstream_t* src, size_t size, size_t bytes, int res, int device, rrb_block_t** blk, rrb_rstream_t** out) {
     if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
     std::unique_ptr<rr::FftStream> b;
-    RRC_TRY(rr::FftStream::create(take(src), size, opts(bytes, res, device), &b));
-    return finish(std::move(b), blk, out);
+    RRC_TRY(rr::FftStream::create(src->s, size, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out, src);
 }
 int rrb_rtlsdr_decode_new(rrb_rstream_t* src, size_t bytes, int res, int device, rrb_block_t** blk, rrb_rstream_t** out) {
     if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
     std::unique_ptr<rr::RtlSdrDecode> b;
-    RRC_TRY(rr::RtlSdrDecode::create(take(src), opts(bytes, res, device), &b));
-    return finish(std::move(b), blk, out);
+    RRC_TRY(rr::RtlSdrDecode::create(src->s, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out, src);
 }
 
 int rrb_hilbert_new(rrb_rstream_t* src, size_t ntaps, int window_type, float window_parm, size_t bytes, int res, int device,
@@ -219,15 +218,15 @@ int rrb_hilbert_new(rrb_rstream_t* src, size_t ntaps, int window_type, float win
     if (!(ntaps > 1 && (ntaps & 1) == 1)) return fail(RRC_ERR_INVALID, "hilbert filter len must be odd and greater than 1");
     if (window_type < RRC_WINDOW_HAMMING || window_type > RRC_WINDOW_HAMMING_PARM) return fail(RRC_ERR_INVALID, "unknown window type %d", window_type);
     std::unique_ptr<rr::Hilbert> b;
-    RRC_TRY(rr::Hilbert::create(take(src), ntaps, window_type, window_parm, opts(bytes, res, device), &b));
-    return finish(std::move(b), blk, out);
+    RRC_TRY(rr::Hilbert::create(src->s, ntaps, window_type, window_parm, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out, src);
 }
 static int sync_new(rrb_rstream_t* src, rr::SyncMap::Op op, int cplx, float re, float im, size_t bytes, int res, int device,
                     rrb_block_t** blk, rrb_rstream_t** out) {
     if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
     std::unique_ptr<rr::SyncMap> b;
-    RRC_TRY(rr::SyncMap::create(take(src), op, cplx != 0, re, im, opts(bytes, res, device), &b));
-    return finish(std::move(b), blk, out);
+    RRC_TRY(rr::SyncMap::create(src->s, op, cplx != 0, re, im, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out, src);
 }
 int rrb_multiply_const_new(rrb_rstream_t* src, int cplx, float val_re, float val_im, size_t bytes, int res, int device,
                            rrb_block_t** blk, rrb_rstream_t** out) {
@@ -246,11 +245,11 @@ int rrb_iq_balance_new(rrb_rstream_t* src, float alpha, size_t bytes, int res, i
 int rrb_tee_new(rrb_rstream_t* src, size_t bytes, int res, int device, rrb_block_t** blk, rrb_rstream_t** out1, rrb_rstream_t** out2) {
     if (!src || !blk || !out1 || !out2) return fail(RRC_ERR_INVALID, "NULL argument");
     std::unique_ptr<rr::Tee> b;
-    RRC_TRY(rr::Tee::create(take(src), opts(bytes, res, device), &b));
+    RRC_TRY(rr::Tee::create(src->s, opts(bytes, res, device), &b));
     auto* r2 = new rrb_rstream();
     r2->s = b->take_output2();
     *out2 = r2;
-    return finish(std::move(b), blk, out1);
+    return finish(std::move(b), blk, out1, src);
 }
 
 int rrb_block_work(rrb_block_t* b, int* kind, size_t* stream_id, size_t* need) {

@@ -43,6 +43,22 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Handle-creation uploads / fills.  cudaMemcpy from pageable host memory and cudaMemset run on the
+// legacy default stream and may return before the device has the data; every block and *_run_host
+// pipeline runs on cudaStreamNonBlocking streams, which do NOT wait for the legacy stream.  These
+// helpers therefore drain the legacy stream before they return, so a handle is complete when its
+// constructor returns, whatever stream it is used on next.
+inline cudaError_t upload_sync(void* dev, const void* host, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
+    return e;
+}
+inline cudaError_t zero_sync(void* dev, size_t bytes) {
+    cudaError_t e = cudaMemset(dev, 0, bytes);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
+    return e;
+}
+
 // Number of SMs of a device (cached).
 int sm_count(int device);
 int max_smem_optin(int device);

@@ -341,7 +341,7 @@ int rrc_iq_balance_create(int device, float alpha, rrc_iq_balance_t** out) {    
     h->tile_a = (float)std::pow((double)h->oma, (double)IQ_TILE);
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->mean, sizeof(float2));
-    if (e == cudaSuccess) e = cudaMemset(h->mean, 0, sizeof(float2));                          // mean: Complex::default()
+    if (e == cudaSuccess) e = zero_sync(h->mean, sizeof(float2));                          // mean: Complex::default()
     if (e == cudaSuccess) e = cudaStreamSynchronize(0);      // callers run on non-blocking streams, which do not wait for this fill
     if (e != cudaSuccess) {
         int s = fail(RRC_ERR_CUDA, "IqBalance create: %s", cudaGetErrorString(e));

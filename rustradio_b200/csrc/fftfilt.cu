@@ -344,7 +344,9 @@ int launch_part(rrc_fftfilt* h, const BlockIO& io, const float2* Hp, cudaStream_
 int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, size_t deci, size_t skip, cudaStream_t st) {
     BlockIO io;
     io.in = reinterpret_cast<const float2*>(in);
-    io.hist = h->hist[h->cur];
+    io.hist = h->hist_ext ? h->hist_ext : h->hist[h->cur];
+    h->hist_ext = nullptr;                                       // one-shot
+    const float2* hist_used = io.hist;
     io.out = reinterpret_cast<float2*>(out);
     io.n_in = (long long)n;
     io.n_out = (long long)n_out;
@@ -369,16 +371,31 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
         shift += io.T1 + 1;
     }
     if (h->T1 > 0 && h->real) {
-        fftfilt_hist_real_kernel<<<(h->T1 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(h->hist[h->cur]), in, (long long)n, h->T1,
+        fftfilt_hist_real_kernel<<<(h->T1 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(hist_used), in, (long long)n, h->T1,
                                                                     reinterpret_cast<float*>(h->hist[h->cur ^ 1]));
         RRC_CHECK_LAUNCH();
         count_launch();
         h->cur ^= 1;
     } else if (h->T1 > 0) {
-        fftfilt_hist_kernel<<<(h->T1 + 255) / 256, 256, 0, st>>>(h->hist[h->cur], io.in, (long long)n, h->T1, h->hist[h->cur ^ 1], h->in_u8);
+        fftfilt_hist_kernel<<<(h->T1 + 255) / 256, 256, 0, st>>>(hist_used, io.in, (long long)n, h->T1, h->hist[h->cur ^ 1], h->in_u8);
         RRC_CHECK_LAUNCH();
         count_launch();
         h->cur ^= 1;
+    }
+    return RRC_OK;
+}
+
+// reset()/set_history() wrote handle state on `st`: remember it so the host pipelines can wait for it.
+int mark_state(rrc_fftfilt* h, cudaStream_t st) {
+    if (!h->state_ev) RRC_CUDA(cudaEventCreateWithFlags(&h->state_ev, cudaEventDisableTiming));
+    RRC_CUDA(cudaEventRecord(h->state_ev, st));
+    h->state_dirty = true;
+    return RRC_OK;
+}
+int pipe_wait_state(rrc_fftfilt* h) {
+    if (h->state_dirty) {
+        RRC_CUDA(cudaStreamWaitEvent(h->pipe.s_comp, h->state_ev, 0));
+        h->state_dirty = false;
     }
     return RRC_OK;
 }
@@ -427,7 +444,7 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
     auto up = [&](float2** d, const std::vector<float2>& v) -> cudaError_t {
         cudaError_t e = cudaMalloc((void**)d, v.size() * sizeof(float2));
         if (e != cudaSuccess) return e;
-        return cudaMemcpy(*d, v.data(), v.size() * sizeof(float2), cudaMemcpyHostToDevice);
+        return upload_sync(*d, v.data(), v.size() * sizeof(float2));
     };
     cudaError_t e;
     std::vector<float2> Hp, tw1, tw2;
@@ -453,7 +470,7 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
         return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
     for (int i = 0; i < 2; ++i) {
         const size_t bytes = std::max<size_t>(1, (size_t)h->T1) * sizeof(float2);
-        if ((e = cudaMalloc((void**)&h->hist[i], bytes)) != cudaSuccess || (e = cudaMemset(h->hist[i], 0, bytes)) != cudaSuccess)
+        if ((e = cudaMalloc((void**)&h->hist[i], bytes)) != cudaSuccess || (e = zero_sync(h->hist[i], bytes)) != cudaSuccess)
             return cleanup(fail(RRC_ERR_CUDA, "FftFilter history alloc failed: %s", cudaGetErrorString(e)));
     }
     cudaStreamSynchronize(0);      // callers run on non-blocking streams, which do not wait for the default-stream fills
@@ -480,6 +497,7 @@ int rrc_fftfilt_destroy(rrc_fftfilt_t* h) {
     for (float2* p : h->part_Hd) cudaFree(p);
     cudaFree(h->tw1_16); cudaFree(h->tw2_16); cudaFree(h->tw3_16);
     cudaFree(h->tw1); cudaFree(h->tw2); cudaFree(h->hist[0]); cudaFree(h->hist[1]);
+    if (h->state_ev) cudaEventDestroy(h->state_ev);
     fold_destroy(h);
     h->pipe.destroy();
     delete h;
@@ -489,7 +507,11 @@ int rrc_fftfilt_destroy(rrc_fftfilt_t* h) {
 int rrc_fftfilt_reset(rrc_fftfilt_t* h, void* stream) {
     if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
     RRC_CUDA(cudaSetDevice(h->device));
-    if (h->T1 > 0) RRC_CUDA(cudaMemsetAsync(h->hist[h->cur], 0, (size_t)h->T1 * sizeof(float2), as_stream(stream)));
+    h->hist_ext = nullptr;
+    if (h->T1 > 0) {
+        RRC_CUDA(cudaMemsetAsync(h->hist[h->cur], 0, (size_t)h->T1 * sizeof(float2), as_stream(stream)));
+        RRC_TRY(mark_state(h, as_stream(stream)));
+    }
     return RRC_OK;
 }
 
@@ -499,7 +521,18 @@ int rrc_fftfilt_set_history(rrc_fftfilt_t* h, const float* hist, size_t n, void*
     if (n == 0) return RRC_OK;
     if (!hist) return fail(RRC_ERR_INVALID, "hist is NULL");
     RRC_CUDA(cudaSetDevice(h->device));
-    RRC_CUDA(cudaMemcpyAsync(h->hist[h->cur], hist, n * (h->real ? sizeof(float) : sizeof(float2)), cudaMemcpyDeviceToDevice, as_stream(stream)));
+    h->hist_ext = nullptr;
+    // cudaMemcpyDefault: `hist` may be a peer device's memory (IPC-mapped or peer-enabled): the copy then runs over NVLink.
+    RRC_CUDA(cudaMemcpyAsync(h->hist[h->cur], hist, n * (h->real ? sizeof(float) : sizeof(float2)), cudaMemcpyDefault, as_stream(stream)));
+    RRC_TRY(mark_state(h, as_stream(stream)));
+    return RRC_OK;
+}
+
+int rrc_fftfilt_set_history_ptr(rrc_fftfilt_t* h, const float* hist, size_t n) {
+    if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
+    if (n != (size_t)h->T1) return fail(RRC_ERR_INVALID, "history must be ntaps-1 = %d samples, got %zu", h->T1, n);
+    if (n && !hist) return fail(RRC_ERR_INVALID, "hist is NULL");
+    h->hist_ext = n ? reinterpret_cast<const float2*>(hist) : nullptr;
     return RRC_OK;
 }
 
@@ -543,10 +576,12 @@ int rrc_fftfilt_decim_run(rrc_fftfilt_t* h, const float* in, size_t n, size_t de
     // deci == 8: folded spectrum + 8x smaller inverse transform (fftfilt_fold.cu); 65536-point
     // cluster kernel for 12289 < ntaps <= 49153.  RRC_FFTFILT_NO_FOLD=1 forces the store-predicate path.
     if (fold_supported(h, deci) == RRC_OK) {
-        if (cnt) RRC_TRY(fold_launch(h, in, n, out, cnt, skip, as_stream(stream)));
+        const float2* hist_used = h->hist_ext ? h->hist_ext : h->hist[h->cur];
+        if (cnt) RRC_TRY(fold_launch(h, in, n, out, cnt, skip, as_stream(stream)));     // reads hist_ext / hist[cur] itself
+        h->hist_ext = nullptr;                                                          // one-shot
         if (h->T1 > 0) {
             fftfilt_hist_kernel<<<(h->T1 + 255) / 256, 256, 0, as_stream(stream)>>>(
-                h->hist[h->cur], reinterpret_cast<const float2*>(in), (long long)n, h->T1, h->hist[h->cur ^ 1], h->in_u8);
+                hist_used, reinterpret_cast<const float2*>(in), (long long)n, h->T1, h->hist[h->cur ^ 1], h->in_u8);
             RRC_CHECK_LAUNCH();
             count_launch();
             h->cur ^= 1;
@@ -565,6 +600,7 @@ int rrc_fftfilt_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, fl
     if (total == 0) return RRC_OK;
     if (!in_host || !out_host) return fail(RRC_ERR_INVALID, "in/out is NULL");
     RRC_TRY(h->pipe.init(h->device));
+    RRC_TRY(pipe_wait_state(h));
     const size_t chunk = PIPE_CHUNK_SAMPLES;
     const size_t esz = h->real ? sizeof(float) : h->in_u8 ? 2 : sizeof(float2);   // input bytes per sample
     const size_t osz = h->real ? sizeof(float) : sizeof(float2);
@@ -590,7 +626,11 @@ int rrc_fftfilt_decim_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_
     if (n_out) *n_out = total_out;
     if (total == 0) return RRC_OK;
     if (!in_host || !out_host) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    // real (FftFilterFloat) handles: plain path only (deci 1), f32 elements; the fused decimation is complex only.
+    if (h->real && deci != 1) return fail(RRC_ERR_UNSUPPORTED, "fused decimation is not implemented for real (f32) streams");
+    if (h->real) return rrc_fftfilt_run_host(h, in_host, n_in, out_host, n_out);
     RRC_TRY(h->pipe.init(h->device));
+    RRC_TRY(pipe_wait_state(h));
     const size_t chunk = PIPE_CHUNK_SAMPLES;
     const size_t esz = h->in_u8 ? 2 : sizeof(float2);
     RRC_TRY(h->pipe.reserve(std::min(chunk, total) * esz, (std::min(chunk, total) / deci + 2) * sizeof(float2)));

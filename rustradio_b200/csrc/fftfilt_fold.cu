@@ -141,7 +141,7 @@ int build_fold_tables(rrc_fftfilt* h, int nc) {
     auto up = [&](float2** d, const std::vector<float2>& v) -> cudaError_t {
         cudaError_t e = cudaMalloc((void**)d, v.size() * sizeof(float2));
         if (e != cudaSuccess) return e;
-        return cudaMemcpy(*d, v.data(), v.size() * sizeof(float2), cudaMemcpyHostToDevice);
+        return upload_sync(*d, v.data(), v.size() * sizeof(float2));
     };
     cudaError_t e;
     if ((e = up(&h->fold.Hc, Hc)) != cudaSuccess || (e = up(&h->fold.gc, gc)) != cudaSuccess ||
@@ -170,7 +170,7 @@ int fold_launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_
     if (h->fold.nc == 0) RRC_TRY(build_fold_tables(h, nc));
     FoldIO io;
     io.in = reinterpret_cast<const float2*>(in);
-    io.hist = h->hist[h->cur];
+    io.hist = h->hist_ext ? h->hist_ext : h->hist[h->cur];
     io.out = reinterpret_cast<float2*>(out);
     io.n_in = (long long)n;
     io.n_out = (long long)n_out;

@@ -39,6 +39,13 @@ struct rrc_fftfilt {
     float2* tw2 = nullptr;
     float2* hist[2] = {nullptr, nullptr};
     int cur = 0;
+    // One-shot external history (rrc_fftfilt_set_history_ptr): the next run reads its left halo through
+    // this pointer — e.g. the tail of the neighbouring GPU's input over NVLink — instead of hist[cur].
+    const float2* hist_ext = nullptr;
+    // reset()/set_history() enqueue on the caller's stream; the *_run_host pipelines run on their own
+    // non-blocking streams and wait for this event first.
+    cudaEvent_t state_ev = nullptr;
+    bool state_dirty = false;
     rrc::Pipe pipe;
     rrc_fold_tables fold;
 };

@@ -194,7 +194,7 @@ int rrc_fft_c32_create(int device, size_t size, rrc_fft_t** out) {
             tw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
         }
         cudaError_t e = cudaMalloc(&h->tw, size * sizeof(float2));
-        if (e == cudaSuccess) e = cudaMemcpy(h->tw, tw.data(), size * sizeof(float2), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = upload_sync(h->tw, tw.data(), size * sizeof(float2));
         if (e != cudaSuccess) { rrc_fft_destroy(h); return fail(RRC_ERR_CUDA, "fft tables: %s", cudaGetErrorString(e)); }
     }
     *out = h;

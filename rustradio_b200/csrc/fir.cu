@@ -661,7 +661,7 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
                 }
             }
     RRC_CUDA(cudaMalloc(&h->tc_bfrag, frag.size() * sizeof(unsigned)));
-    RRC_CUDA(cudaMemcpy(h->tc_bfrag, frag.data(), frag.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    RRC_CUDA(upload_sync(h->tc_bfrag, frag.data(), frag.size() * sizeof(unsigned)));
     return RRC_OK;
 }
 
@@ -708,7 +708,7 @@ int plan_tc_cplx(rrc_fir* h, const std::vector<float>& w2) {       // w2: revers
                 }
             }
     RRC_CUDA(cudaMalloc(&h->tc_bfrag, frag.size() * sizeof(unsigned)));
-    RRC_CUDA(cudaMemcpy(h->tc_bfrag, frag.data(), frag.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    RRC_CUDA(upload_sync(h->tc_bfrag, frag.data(), frag.size() * sizeof(unsigned)));
     h->tc = h->tc1 = h->tc_cplx = true;
     h->tc_ntile = 1; h->tc_KS = KS;
     h->tc_tap_inv_scale = std::ldexp(1.0f, -shift);
@@ -751,9 +751,9 @@ int upload_taps(rrc_fir* h) {
         tap_at(j, &poly[(p * h->qpad + q) * te]);
     }
     RRC_CUDA(cudaMalloc(&h->taps_rev, rev.size() * sizeof(float)));
-    RRC_CUDA(cudaMemcpy(h->taps_rev, rev.data(), rev.size() * sizeof(float), cudaMemcpyHostToDevice));
+    RRC_CUDA(upload_sync(h->taps_rev, rev.data(), rev.size() * sizeof(float)));
     RRC_CUDA(cudaMalloc(&h->taps_poly, poly.size() * sizeof(float)));
-    RRC_CUDA(cudaMemcpy(h->taps_poly, poly.data(), poly.size() * sizeof(float), cudaMemcpyHostToDevice));
+    RRC_CUDA(upload_sync(h->taps_poly, poly.data(), poly.size() * sizeof(float)));
 
     // Geometry: largest CTA whose tile fits; prefer <= 100 KB so two CTAs share an SM.
     h->use_poly = false;
@@ -1134,6 +1134,45 @@ int rrc_fir_run_host(rrc_fir_t* h, const void* in_host, size_t n_in, void* out_h
         RRC_TRY(h->pipe.stage_in(i, (const char*)in_host + o * D * ies, need * ies));
         RRC_TRY(run_impl(h, h->pipe.d_in[i & 1], 0, need, h->pipe.d_out[i & 1], 0, no, 1, false, 0.f, h->pipe.s_comp));
         RRC_TRY(h->pipe.drain_out(i, (char*)out_host + o * es, no * es));
+    }
+    return h->pipe.finish();
+}
+
+// Host-buffer form of the fused FirFilter<Complex> -> QuadratureDemod channelizer (config 3 end to end):
+// nchan channels of n_in samples each (channel c at in_host + c*n_in samples; u8 I/Q pairs after
+// rrc_fir_set_input_u8iq), whole channels staged in groups so that a chunk stays near the pipeline's
+// chunk size; every channel yields floor((n_in-ntaps+1)/deci) - 1 floats at out_host + c*out_stride.
+int rrc_fir_c32_demod_run_host_batch(rrc_fir_t* h, const void* in_host, size_t n_in, size_t nchan, float gain,
+                                     float* out_host, size_t out_stride, size_t* n_out_per_chan) {
+    if (!h) return fail(RRC_ERR_INVALID, "fir handle is NULL");
+    if (!h->cplx) return fail(RRC_ERR_INVALID, "fused demod needs a c32 FIR");
+    const size_t T = h->ntaps, D = h->deci;
+    const size_t ies = h->in_u8 ? 2 : sizeof(float2);
+    const size_t fir_n = n_in < T + D - 1 ? 0 : (n_in - T + 1) / D;       // src/fir.rs:496-525 to exhaustion
+    const size_t per = fir_n ? fir_n - 1 : 0;                             // src/quadrature_demod.rs:71-73: N -> N-1
+    if (n_out_per_chan) *n_out_per_chan = per;
+    if (per == 0 || nchan == 0) return RRC_OK;
+    if (!in_host || !out_host) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    if (out_stride < per) return fail(RRC_ERR_INVALID, "out_stride %zu < outputs per channel %zu", out_stride, per);
+    RRC_TRY(h->pipe.init(h->device));
+    const size_t need = (fir_n - 1) * D + T;
+    const size_t group = std::max<size_t>(1, std::min<size_t>(nchan, PIPE_CHUNK_SAMPLES / std::max<size_t>(n_in, 1)));
+    RRC_TRY(h->pipe.reserve(group * n_in * ies, group * per * sizeof(float)));
+    int i = 0;
+    for (size_t c = 0; c < nchan; c += group, ++i) {
+        const size_t g = std::min(group, nchan - c);
+        RRC_TRY(h->pipe.stage_in(i, (const char*)in_host + c * n_in * ies, g * n_in * ies));
+        RRC_TRY(run_impl(h, h->pipe.d_in[i & 1], n_in, need, h->pipe.d_out[i & 1], per, fir_n, g, true, gain, h->pipe.s_comp));
+        const int b = i & 1;                      // drain: contiguous when the caller's rows are packed, else row by row
+        RRC_CUDA(cudaEventRecord(h->pipe.comp_done[b], h->pipe.s_comp));
+        RRC_CUDA(cudaStreamWaitEvent(h->pipe.s_d2h, h->pipe.comp_done[b], 0));
+        if (out_stride == per) {
+            RRC_CUDA(cudaMemcpyAsync(out_host + c * per, h->pipe.d_out[b], g * per * sizeof(float), cudaMemcpyDeviceToHost, h->pipe.s_d2h));
+        } else {
+            RRC_CUDA(cudaMemcpy2DAsync(out_host + c * out_stride, out_stride * sizeof(float), h->pipe.d_out[b], per * sizeof(float),
+                                       per * sizeof(float), g, cudaMemcpyDeviceToHost, h->pipe.s_d2h));
+        }
+        RRC_CUDA(cudaEventRecord(h->pipe.d2h_done[b], h->pipe.s_d2h));
     }
     return h->pipe.finish();
 }

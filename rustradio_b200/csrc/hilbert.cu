@@ -319,17 +319,17 @@ int rrc_hilbert_create(int device, const float* taps, size_t ntaps, rrc_hilbert_
     cudaError_t e;
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
     if ((e = cudaMalloc((void**)&h->taps_dev, rev.size() * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMemcpy(h->taps_dev, rev.data(), rev.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
+    if ((e = upload_sync(h->taps_dev, rev.data(), rev.size() * sizeof(float))) != cudaSuccess) return bail(e, "cudaMemcpy");
     if (h->half) {
         if ((e = cudaMalloc((void**)&h->half_taps_dev, g.size() * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
-        if ((e = cudaMemcpy(h->half_taps_dev, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy");
+        if ((e = upload_sync(h->half_taps_dev, g.data(), g.size() * sizeof(float))) != cudaSuccess) return bail(e, "cudaMemcpy");
         if (h->half_smem > 48 * 1024 &&
             (e = cudaFuncSetAttribute(hilbert_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->half_smem)) != cudaSuccess)
             return bail(e, "cudaFuncSetAttribute");
     }
     for (int i = 0; i < 2; ++i) {
         if ((e = cudaMalloc((void**)&h->hist[i], ntaps * sizeof(float))) != cudaSuccess) return bail(e, "cudaMalloc");
-        if ((e = cudaMemset(h->hist[i], 0, ntaps * sizeof(float))) != cudaSuccess) return bail(e, "cudaMemset");   // history: vec![0.0; ntaps]
+        if ((e = zero_sync(h->hist[i], ntaps * sizeof(float))) != cudaSuccess) return bail(e, "cudaMemset");   // history: vec![0.0; ntaps]
     }
     if ((e = cudaStreamSynchronize(0)) != cudaSuccess) return bail(e, "cudaStreamSynchronize");   // callers run on non-blocking streams
     if (h->smem > 48 * 1024 &&

@@ -178,6 +178,26 @@ int rrc_resampler_reset(rrc_resampler_t* h) {
     return RRC_OK;
 }
 
+// The reference's carried state (src/rational_resampler.rs:101-105: `counter`, `pending`) made settable, so
+// that a time-segment shard can start mid-stream: the shard owning outputs [k_lo, k_hi)
+// starts at input sample s = floor(k_lo*deci/interp) with counter = s*interp - k_lo*deci (<= 0; the work()
+// loop `counter += interp; while counter > 0 { emit; counter -= deci }` is well defined for any counter).
+// pending_host != NULL: that sample is the pending one (:161-173) and counter must be > 0.
+int rrc_resampler_set_state(rrc_resampler_t* h, int64_t counter, const void* pending_host) {
+    if (!h) return fail(RRC_ERR_INVALID, "resampler handle is NULL");
+    if (pending_host) {
+        if (counter <= 0) return fail(RRC_ERR_INVALID, "a pending sample needs counter > 0 (got %lld)", (long long)counter);
+        RRC_CUDA(cudaSetDevice(h->device));
+        RRC_CUDA(cudaMemcpy(h->pending, pending_host, h->elem, cudaMemcpyHostToDevice));
+        RRC_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    } else if (counter > 0) {
+        return fail(RRC_ERR_INVALID, "counter %lld > 0 without a pending sample", (long long)counter);
+    }
+    h->counter = counter;
+    h->has_pending = pending_host != nullptr;
+    return RRC_OK;
+}
+
 int rrc_resampler_state(const rrc_resampler_t* h, int64_t* interp, int64_t* deci, int64_t* counter, int* has_pending) {
     if (!h) return fail(RRC_ERR_INVALID, "resampler handle is NULL");
     if (interp) *interp = h->interp;

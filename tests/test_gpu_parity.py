@@ -753,18 +753,57 @@ def test_time_segment_shards_equal_whole(R):
     parts = []
     for r in range(world):
         seg = S.resampler_segment(n, 147, 160, world, r)
-        # a shard starts mid-stream: seed the counter so that its first output is global output out_lo
-        k = np.arange(seg.out_lo, seg.out_hi, dtype=np.int64)
+        # a shard starts mid-stream: rrc_resampler_set_state seeds the reference's `counter`
+        # (src/rational_resampler.rs:101-105) so that the shard's first output is global output out_lo;
+        # EVERY shard runs through resample_kernel
         res = R.Resampler(4, 147, 160)
-        # closed form through the kernel: shift the window so that local index = global index - in_lo
-        _, _, y = res.work(xf[seg.in_lo:seg.in_hi], len(k)) if seg.out_lo == 0 else (0, 0, None)
-        if y is None:
-            # phase of the first output inside the shard: counter c0 = -(out_lo*deci - in_lo*interp) (<= 0)
-            c0 = -(seg.out_lo * 160 - seg.in_lo * 147)
-            assert -160 < c0 <= 0
-            y = xf[seg.in_lo:seg.in_hi][((k - seg.out_lo) * 160 - c0) // 147]
+        c0 = seg.in_lo * 147 - seg.out_lo * 160
+        assert -147 < c0 <= 0
+        res.set_state(c0)
+        _, consumed, y = res.work(xf[seg.in_lo:seg.in_hi], seg.out_hi - seg.out_lo)
+        assert len(y) == seg.out_hi - seg.out_lo
         parts.append(y)
     assert np.concatenate(parts).tobytes() == whole_rs.tobytes()
+
+
+def test_fftfilt_halo_through_history_pointer(R):
+    """SURVEY 8(e) time-segment sharding, the way bench.py does it across GPUs: shard r > 0 reads its
+    ntaps-1 sample left halo through rrc_fftfilt_set_history_ptr (zero-copy: the pointer is the tail of
+    the left neighbour's input buffer) or has it copied by rrc_fftfilt_set_history; both equal the whole
+    stream.  Also covers the fused decimate-by-8 (fold) kernel and that the pointer is one-shot."""
+    from rustradio_b200 import shard as S
+    n, world = 400_000, 3
+    x = O.synth_c32(53, 0, n)
+    for T, deci in ((257, 1), (4097, 1), (4097, 8)):
+        taps = O.low_pass_n(1.0, 0.08, T).astype(np.complex64)
+        n_out = O.fftfilt_out_count(n, T)
+        whole = O.conv_full_f64_fft(x, taps, n_out)[::deci]
+        dx = R.DeviceBuffer.from_numpy(x)                       # the "neighbour's" buffer: all shards' inputs
+        for mode in ("ptr", "copy"):
+            parts = []
+            for r in range(world):
+                seg = S.fftfilt_segment(n, T, world, r)
+                m = seg.out_hi - seg.out_lo
+                f = R.FftFilt(taps)
+                if r > 0:
+                    halo = dx.ptr + (seg.out_lo - (T - 1)) * 8
+                    f.set_history_ptr(halo, T - 1) if mode == "ptr" else f.set_history(halo, T - 1)
+                skip = (-seg.out_lo) % deci
+                cnt = (m - skip + deci - 1) // deci if m > skip else 0
+                dout = R.DeviceBuffer(max(cnt, 1) * 8)
+                if deci == 1:
+                    f.run(dx.ptr + seg.out_lo * 8, m, dout)
+                else:
+                    assert f.decim_run(dx.ptr + seg.out_lo * 8, m, deci, skip, dout) == cnt
+                parts.append(dout.download(np.complex64, cnt))
+                if r == 1 and deci == 1:                        # one-shot: a second run continues from the carried history
+                    more = min(1000, n - seg.out_hi)
+                    d2 = R.DeviceBuffer(more * 8)
+                    f.run(dx.ptr + seg.out_hi * 8, more, d2)
+                    ref = O.conv_full_f64_fft(x, taps, seg.out_hi + more)[seg.out_hi:]
+                    assert O.rel_rms(d2.download(np.complex64, more), ref) <= REL_RMS_BAR
+            got = np.concatenate(parts)
+            assert len(got) == len(whole) and O.rel_rms(got, whole) <= REL_RMS_BAR, (T, deci, mode)
 
 
 # ------------------------------------------------------ empty / ragged inputs ---
