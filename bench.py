@@ -779,6 +779,9 @@ def run_gpu(args):
     torch, R = ctx.torch, ctx.R
     rank, world = ctx.rank, ctx.world
     cfg = CONFIGS[args.config]()
+    if args.n:
+        cfg["n"] = args.n
+        cfg["desc"] += f" [EXPERIMENT: n overridden to {args.n}]"
     pool = HostPool(ctx)
     split = {"capture": "capture", "time": "time", "channel": "channel"}[args.shard] if world > 1 else "capture"
     W = build_workload(ctx, cfg, split)
@@ -1016,6 +1019,7 @@ def main():
     ap.add_argument("--shard", default="capture", choices=["capture", "time", "channel"],
                     help="N>1 headline: independent capture per GPU (weak, default), one capture split by time segment with the halo "
                          "read over NVLink peer memory (strong; c2, c4), or config 3's channels split across the GPUs (strong)")
+    ap.add_argument("--n", type=int, default=0, help="override the config's sample count (experiments only; the line's workload string says so)")
     ap.add_argument("--headline-only", action="store_true", help="skip the configs / splits sub-records")
     ap.add_argument("--no-ceiling", action="store_true", help="skip the bare-copy ceiling of the e2e leg")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back headline steps for the `sustained` sub-record (0 = off)")

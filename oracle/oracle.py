@@ -60,6 +60,7 @@ def _load(name: str) -> C.CDLL:
         "orc_resampler_free": (None, [vp]),
         "orc_resampler_has_pending": (C.c_int, [vp]),
         "orc_resampler_counter": (i64, [vp]),
+        "orc_resampler_set_counter": (None, [vp, i64]),
         "orc_resampler_work": (C.c_int, [vp, vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64)]),
         "orc_resample_out_count": (i64, [i64, i64, i64]),
         "orc_quad_demod": (None, [vp, i64, f32, vp]),
@@ -268,6 +269,10 @@ class Resampler:
         c, p = C.c_int64(0), C.c_int64(0)
         ret = lib().orc_resampler_work(self._h, _p(inp), len(inp), _p(out), out_cap, C.byref(c), C.byref(p))
         return ret, int(c.value), out[: p.value].copy()
+
+    def set_counter(self, counter: int):
+        """Preset the reference's `counter` field (mid-stream start of a time-segment shard)."""
+        lib().orc_resampler_set_counter(self._h, counter)
 
     @property
     def has_pending(self) -> bool:

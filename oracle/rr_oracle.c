@@ -432,6 +432,9 @@ orc_resampler* orc_resampler_new(int64_t elem_size, int64_t interp, int64_t deci
 void orc_resampler_free(orc_resampler* r) { free(r); }
 int orc_resampler_has_pending(const orc_resampler* r) { return r->has_pending; }
 int64_t orc_resampler_counter(const orc_resampler* r) { return r->counter; }
+/* Test hook: preset the struct field `counter` (src/rational_resampler.rs:101-105) so that the work() loop
+ * below — unchanged — starts mid-stream, the way a time-segment shard does. */
+void orc_resampler_set_counter(orc_resampler* r, int64_t counter) { r->counter = counter; r->has_pending = 0; }
 
 /*
  * One RationalResampler::work() call, src/rational_resampler.rs:155-206, on

@@ -67,6 +67,7 @@ fftfilt_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __
     s_tw1[tid] = tw1g[tid];
     fftk::load_hres(tid, Hp, s_hres);
     const int pf = tune & 15;
+    if (io.hist_next && blockIdx.x == gridDim.x - 1) fftk::update_history(io, tid, fftk::NT);
     if (tune >> 8) {
         const long long t0 = clock64(), wait = (long long)(tune >> 8) * 1024 * (blockIdx.x & 3);
         while (clock64() - t0 < wait) { }
@@ -147,6 +148,7 @@ fftfilt_tma_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2
     const unsigned mbar = (unsigned)__cvta_generic_to_shared(s_hres + fftk::HRES_ELEMS);
     const unsigned sm_a = (unsigned)__cvta_generic_to_shared(sm);
     const int pf = tune & 15;
+    if (io.hist_next && blockIdx.x == gridDim.x - 1) fftk::update_history(io, tid, fftk::NT);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -356,11 +358,14 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
     io.in_u8 = h->in_u8;
     io.real = h->real;
     const bool decim = !(deci == 1 && skip == 0);
+    // kernels that update the carried history themselves (one launch per run): the 512-thread LDG / TMA kernels
+    const bool fused_hist = h->T1 > 0 && (h->real || h->variant == 32 || h->variant == 35 || h->variant == 36);
     long long shift = 0;
     for (size_t p = 0; p < h->part_T1.size(); ++p) {
         io.T1 = h->part_T1[p];
         io.V = fftk::N - io.T1;
         io.shift = shift;
+        io.hist_next = (fused_hist && p == 0) ? h->hist[h->cur ^ 1] : nullptr;
         int s;
         if (h->variant == 16 && !h->real) {
             if (p == 0) s = decim ? launch_part16<true, false>(h, io, h->part_Hd[p], st) : launch_part16<false, false>(h, io, h->part_Hd[p], st);
@@ -370,7 +375,9 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
         RRC_TRY(s);
         shift += io.T1 + 1;
     }
-    if (h->T1 > 0 && h->real) {
+    if (fused_hist) {
+        h->cur ^= 1;
+    } else if (h->T1 > 0 && h->real) {
         fftfilt_hist_real_kernel<<<(h->T1 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float*>(hist_used), in, (long long)n, h->T1,
                                                                     reinterpret_cast<float*>(h->hist[h->cur ^ 1]));
         RRC_CHECK_LAUNCH();
@@ -577,15 +584,18 @@ int rrc_fftfilt_decim_run(rrc_fftfilt_t* h, const float* in, size_t n, size_t de
     // cluster kernel for 12289 < ntaps <= 49153.  RRC_FFTFILT_NO_FOLD=1 forces the store-predicate path.
     if (fold_supported(h, deci) == RRC_OK) {
         const float2* hist_used = h->hist_ext ? h->hist_ext : h->hist[h->cur];
-        if (cnt) RRC_TRY(fold_launch(h, in, n, out, cnt, skip, as_stream(stream)));     // reads hist_ext / hist[cur] itself
+        // the fold kernel reads hist_ext / hist[cur] and writes the next history itself (one launch);
+        // RRC_ERR_UNSUPPORTED = nothing was launched (no kept output in this call)
+        const int s = cnt ? fold_launch(h, in, n, out, cnt, skip, as_stream(stream)) : RRC_ERR_UNSUPPORTED;
         h->hist_ext = nullptr;                                                          // one-shot
-        if (h->T1 > 0) {
+        if (s != RRC_OK && s != RRC_ERR_UNSUPPORTED) return s;
+        if (s == RRC_ERR_UNSUPPORTED && h->T1 > 0) {
             fftfilt_hist_kernel<<<(h->T1 + 255) / 256, 256, 0, as_stream(stream)>>>(
                 hist_used, reinterpret_cast<const float2*>(in), (long long)n, h->T1, h->hist[h->cur ^ 1], h->in_u8);
             RRC_CHECK_LAUNCH();
             count_launch();
-            h->cur ^= 1;
         }
+        if (h->T1 > 0) h->cur ^= 1;
         return RRC_OK;
     }
     return launch(h, in, n, out, cnt, deci, skip, as_stream(stream));

@@ -55,7 +55,29 @@ struct BlockIO {
     // (imaginary part) through ONE complex transform — h real => h*(a + ib) = h*a + i h*b — so a real
     // stream costs half the transforms of the reference's widen -> complex filter -> .re.
     int real = 0;
+    // Non-NULL: the kernel itself writes the history the NEXT call starts from (the last T1_total samples of
+    // hist ++ in) into this buffer — done by the grid's last CTA before its first block, so a run() is ONE
+    // launch (matters for small work() windows and for time-segment shards, where a step is ~0.25 ms).
+    float2* hist_next = nullptr;
 };
+
+// hist_next[i] = x[n_in - T1_total + i] over the concatenation (hist ++ in), i < T1_total.
+RRC_HD void update_history(const BlockIO& io, int tid, int nthreads) {
+    if (io.real) {
+        const float* hc = reinterpret_cast<const float*>(io.hist);
+        const float* in = reinterpret_cast<const float*>(io.in);
+        float* hn = reinterpret_cast<float*>(io.hist_next);
+        for (int i = tid; i < io.T1_total; i += nthreads) {
+            const long long s = io.n_in - io.T1_total + i;
+            hn[i] = s >= 0 ? in[s] : hc[s + io.T1_total];
+        }
+        return;
+    }
+    for (int i = tid; i < io.T1_total; i += nthreads) {
+        const long long s = io.n_in - io.T1_total + i;
+        io.hist_next[i] = s >= 0 ? ld_iq(io.in, s, io.in_u8) : io.hist[s + io.T1_total];
+    }
+}
 
 // Sample g of a real stream with its carried history (g < 0) and zero fill past the end.
 RRC_HD float fetch_real(const BlockIO& io, long long g) {

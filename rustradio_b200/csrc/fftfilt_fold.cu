@@ -51,6 +51,7 @@ fftfilt_fold_kernel(const FoldIO io, const float2* __restrict__ Hc, const float2
         if (tid < 32) s_twc[tid] = twcg[c * 32 + tid];
     }
     fftk::load_hres(tid, Hp, s_hres);
+    if (io.hist_next && blockIdx.x == gridDim.x - 1) fftf::update_history(io, tid, fftk::NT);
     __syncthreads();
     const float2* uc[NC];
     if constexpr (NC > 1) {
@@ -180,7 +181,8 @@ int fold_launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_
     io.r = (int)(skip % fftf::FOLD_D);
     io.jbias = (long long)(skip / fftf::FOLD_D);
     io.in_u8 = h->in_u8;
-    if ((long long)n <= io.r) return RRC_OK;
+    io.hist_next = h->T1 > 0 ? h->hist[h->cur ^ 1] : nullptr;
+    if ((long long)n <= io.r) return RRC_ERR_UNSUPPORTED;      // nothing to launch: the caller updates the history
     const long long nblocks = ((long long)n - io.r + io.V - 1) / io.V;
     return nc == 1 ? launch_fold<1>(h, io, nblocks, st) : launch_fold<4>(h, io, nblocks, st);
 }

@@ -45,7 +45,15 @@ struct FoldIO {
     int r;                   // skip mod 8: segment start alignment so kept outputs sit at n = 0 (mod 8)
     long long jbias;         // (skip - r) / 8
     int in_u8 = 0;           // 1: `in` is u8 I/Q pairs (RtlSdrDecode fused into the load)
+    float2* hist_next = nullptr;   // non-NULL: the grid's last CTA writes the next call's history here (one launch per run)
 };
+
+RRC_HD void update_history(const FoldIO& io, int tid, int nthreads) {
+    for (int i = tid; i < io.T1_total; i += nthreads) {
+        const long long s = io.n_in - io.T1_total + i;
+        io.hist_next[i] = s >= 0 ? ld_iq(io.in, s, io.in_u8) : io.hist[s + io.T1_total];
+    }
+}
 
 // p[k] = base * w^k, k = 0..31.
 RRC_HD void powers32b(float2 w, float2 base, float2 (&p)[32]) {

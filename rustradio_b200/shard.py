@@ -67,3 +67,14 @@ def demod_segment(n_in: int, world: int, rank: int) -> Segment:
     if hi == lo:
         return Segment(lo, hi, 0, 0)
     return Segment(lo, hi, lo, hi + 1)
+
+
+def resampler_shard_counter(seg: Segment, interp: int, deci: int) -> int:
+    """The reference's `counter` state (src/rational_resampler.rs:101-105) at which a shard's work() loop
+    must start so that its first output is global output seg.out_lo: the loop adds `interp` per input and
+    emits while counter > 0, so after in_lo inputs and out_lo outputs counter = in_lo*interp - out_lo*deci,
+    always in (-interp, 0] (a value <= -deci just means the first input sample's earlier outputs belong to
+    the previous shard)."""
+    from math import gcd
+    g = gcd(interp, deci)
+    return seg.in_lo * (interp // g) - seg.out_lo * (deci // g)

@@ -41,9 +41,19 @@ def _worker(rank, world, port, q):
         rseg = S.resampler_segment(n, 147, 160, world, rank)
         k = np.arange(rseg.out_lo, rseg.out_hi, dtype=np.int64)
         yr = x[rseg.in_lo:rseg.in_hi][(k * 160) // 147 - rseg.in_lo]
+        # the same shard through the reference's work() loop started from the shard's counter state
+        # (what rrc_resampler_set_state does on the device): identical
+        orc = O.Resampler(8, 147, 160)
+        orc.set_counter(S.resampler_shard_counter(rseg, 147, 160))
+        _, consumed, yr2 = orc.work(x[rseg.in_lo:rseg.in_hi], rseg.out_hi - rseg.out_lo + 3)
+        assert consumed == rseg.in_hi - rseg.in_lo and yr2.tobytes() == yr.tobytes()
+        # --- config 3 style channel split: rank r owns channels shard_range(nchan, world, r)
+        nchan = 5
+        c_lo, c_hi = S.shard_range(nchan, world, rank)
+        ych = [O.fir(O.synth_c32(78, c * 4000, 4000), taps, 10) for c in range(c_lo, c_hi)]
         # --- gather on rank 0 (object gather: ragged shards)
         gathered = [None] * world
-        dist.all_gather_object(gathered, (y, yf, yr))
+        dist.all_gather_object(gathered, (y, yf, yr, ych))
         # --- max-over-ranks reduction used for timings
         t = torch.tensor([float(rank + 1)], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -56,6 +66,9 @@ def _worker(rank, world, port, q):
             ok_fft = len(wf) == len(ref) and O.rel_rms(wf, ref) < 1e-6
             wr = np.concatenate([g[2] for g in gathered])
             ok_rs = wr.tobytes() == O.resample(x, 147, 160).tobytes()
+            chans = [c for g in gathered for c in g[3]]
+            ok_rs = ok_rs and len(chans) == nchan and all(
+                np.array_equal(c, O.fir(O.synth_c32(78, i * 4000, 4000), taps, 10)) for i, c in enumerate(chans))
             q.put((ok_fir, ok_fft, ok_rs, float(t.item())))
     finally:
         dist.destroy_process_group()
@@ -98,3 +111,23 @@ def test_segments_cover_baseline_configs():
     f = [S.fftfilt_segment(1 << 28, 4097, 8, r) for r in range(8)]
     assert f[0].in_lo == 0 and all(s.out_lo - s.in_lo == 4096 for s in f[1:])
     assert f[-1].out_hi == 268_434_089
+
+
+@pytest.mark.parametrize("interp,deci", [(147, 160), (160, 147), (3, 1), (1, 8), (7, 3)])
+def test_resampler_shard_counter_state(interp, deci):
+    """Every shard, started from resampler_shard_counter, reproduces its slice of the whole stream through
+    the reference's own work() loop; the counter stays in (-interp, 0]."""
+    n, world = 10_007, 5
+    x = (np.arange(n) * 7919 % 65521).astype(np.uint32)
+    whole = O.resample(x, interp, deci)
+    parts = []
+    for r in range(world):
+        seg = S.resampler_segment(n, interp, deci, world, r)
+        c0 = S.resampler_shard_counter(seg, interp, deci)
+        assert -interp < c0 <= 0
+        o = O.Resampler(4, interp, deci)
+        o.set_counter(c0)
+        _, consumed, y = o.work(x[seg.in_lo:seg.in_hi], seg.out_hi - seg.out_lo)
+        assert len(y) == seg.out_hi - seg.out_lo
+        parts.append(y)
+    assert np.concatenate(parts).tobytes() == whole.tobytes()
