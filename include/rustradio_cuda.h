@@ -365,8 +365,9 @@ int rrc_iq_balance_run(rrc_iq_balance_t* h, const float* in_dev_c32, size_t n, f
  * constructors take ownership of the input ReadStream and hand back the block
  * plus the output ReadStream; work() reports Again / WaitForStream(stream, need)
  * / EOF; tags travel with the samples.  Streams are double-mapped rings in
- * pageable host memory (residency 0) or in device memory (residency 1, CUDA
- * VMM) with a configurable size (the reference's is fixed at 4,096,000 bytes).
+ * pageable host memory (residency 0), page-locked host memory (residency 2) or
+ * device memory (residency 1, CUDA VMM) with a configurable size (the
+ * reference's is fixed at 4,096,000 bytes).
  */
 typedef struct rrb_rstream rrb_rstream_t;     /* ReadStream<T> */
 typedef struct rrb_wstream rrb_wstream_t;     /* WriteStream<T> */
@@ -393,8 +394,9 @@ typedef struct {
 #define RRB_RET_WAIT    2   /* WaitForStream(stream_id, need) */
 #define RRB_RET_EOF     3
 
-#define RRB_HOST   0
-#define RRB_DEVICE 1
+#define RRB_HOST   0          /* pageable host ring (memfd double mapping, the reference's layout) */
+#define RRB_DEVICE 1          /* device ring (CUDA VMM double mapping): chained GPU blocks never touch host memory */
+#define RRB_HOST_PINNED 2     /* host ring, page-locked with cudaHostRegister: the CPU<->GPU edges of a graph are real async DMA */
 #define RRB_DEFAULT_STREAM_SIZE 4096000
 
 int rrb_stream_new(size_t elem_size, size_t bytes, int residency, int device, rrb_wstream_t** w, rrb_rstream_t** r);
@@ -418,6 +420,19 @@ int rrb_rstream_drop(rrb_rstream_t* r);
  * ring must live on `device` (RRC_ERR_INVALID otherwise: cross-device chains need a host edge). */
 int rrb_vector_source_new(const void* data, size_t n, size_t elem_size, uint64_t repeat,
                           size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+/* Capture ingest: FileSource<T>::builder(path).repeat(r).build() (src/file_source.rs:11-153) —
+ * raw little-endian samples of elem_size bytes (8 = a cf32 capture); whole samples only; work() returns Again /
+ * Pending / WaitForStream(dst,1) / EOF exactly like the reference.  repeat = number of passes (Repeat::finite),
+ * UINT64_MAX = Repeat::infinite.  With a DEVICE output ring the bytes go file -> pinned staging -> HBM. */
+int rrb_file_source_new(const char* path, size_t elem_size, uint64_t repeat,
+                        size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+/* SigMFSource<T>::builder(path).sample_rate().repeat().ignore_type_error().build() (src/sigmf.rs:229-613): a SigMF
+ * Archive (tar with X.sigmf-meta / X.sigmf-data) when `path` exists, else the Recording files path-meta / path-data.
+ * type_string = the reference's Type::type_string() ("cf32", "rf32", "ru8", "ri32", "ci32"); core:datatype must be
+ * type_string + "_le" unless ignore_type_error.  samp_rate < 0 = None; a rate in the metadata must equal it. */
+int rrb_sigmf_source_new(const char* path, size_t elem_size, const char* type_string, double samp_rate, int ignore_type_error,
+                         uint64_t repeat, size_t out_bytes, int out_residency, int device,
+                         rrb_block_t** blk, rrb_rstream_t** out, double* sample_rate_out, int* has_sample_rate);
 int rrb_fir_filter_new(rrb_rstream_t* src, int cplx, const float* taps, size_t ntaps, size_t deci,
                        int translate, float samp_rate, float freq, unsigned flags,
                        size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);

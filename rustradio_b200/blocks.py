@@ -12,7 +12,9 @@ import numpy as np
 from .api import RrcError, lib, _ck
 
 AGAIN, PENDING, WAIT, EOF = 0, 1, 2, 3
-HOST, DEVICE = 0, 1
+HOST, DEVICE, HOST_PINNED = 0, 1, 2
+REPEAT_INFINITE = 2**64 - 1
+SIGMF_TYPES = {np.dtype(np.complex64): "cf32", np.dtype(np.float32): "rf32", np.dtype(np.uint8): "ru8", np.dtype(np.int32): "ri32"}
 DEFAULT_STREAM_SIZE = 4_096_000
 _KINDS = ["String", "Float", "Bool", "U64", "I64"]
 
@@ -45,6 +47,8 @@ _SIGS = {
     "rrb_rstream_eof": [_vp, _P(_i)],
     "rrb_rstream_drop": [_vp],
     "rrb_vector_source_new": [_vp, _sz, _sz, C.c_uint64, _sz, _i, _i, _P(_vp), _P(_vp)],
+    "rrb_file_source_new": [C.c_char_p, _sz, C.c_uint64, _sz, _i, _i, _P(_vp), _P(_vp)],
+    "rrb_sigmf_source_new": [C.c_char_p, _sz, C.c_char_p, C.c_double, _i, C.c_uint64, _sz, _i, _i, _P(_vp), _P(_vp), _P(C.c_double), _P(_i)],
     "rrb_fir_filter_new": [_vp, _i, _vp, _sz, _sz, _i, C.c_float, C.c_float, C.c_uint, _sz, _i, _i, _P(_vp), _P(_vp)],
     "rrb_fft_filter_new": [_vp, _vp, _sz, _sz, _i, _i, _P(_vp), _P(_vp)],
     "rrb_fft_filter_float_new": [_vp, _vp, _sz, _sz, _i, _i, _P(_vp), _P(_vp)],
@@ -239,6 +243,23 @@ def VectorSource(data, repeat: int = 1, size_bytes=DEFAULT_STREAM_SIZE, residenc
     a = np.ascontiguousarray(data)
     return _mk(_L().rrb_vector_source_new, a.dtype, a.ctypes.data if len(a) else None, len(a), a.dtype.itemsize, repeat,
                size_bytes, residency, device)
+
+
+def FileSource(path, dtype, repeat: int = 1, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
+    """FileSource::<T>::builder(path).repeat(Repeat::finite(repeat)).build() (src/file_source.rs:11-40)."""
+    dt = np.dtype(dtype)
+    return _mk(_L().rrb_file_source_new, dt, str(path).encode(), dt.itemsize, repeat, size_bytes, residency, device)
+
+
+def SigMFSource(path, dtype, sample_rate=None, ignore_type_error=False, repeat: int = 1, size_bytes=DEFAULT_STREAM_SIZE,
+                residency=DEVICE, device=0):
+    """SigMFSource::<T>::builder(path)...build() (src/sigmf.rs:229-268) -> (block, out, sample_rate or None)."""
+    dt = np.dtype(dtype)
+    b, o = _vp(), _vp()
+    rate, has = C.c_double(0), _i(0)
+    _ck(_L().rrb_sigmf_source_new(str(path).encode(), dt.itemsize, SIGMF_TYPES[dt].encode(), -1.0 if sample_rate is None else float(sample_rate),
+                                  int(ignore_type_error), repeat, size_bytes, residency, device, C.byref(b), C.byref(o), C.byref(rate), C.byref(has)))
+    return Block(b.value), ReadStream(o.value, dt), (rate.value if has.value else None)
 
 
 def FirFilter(src: ReadStream, taps, deci: int = 1, translate=None, flags: int = 0, size_bytes=DEFAULT_STREAM_SIZE,

@@ -80,6 +80,8 @@ std::shared_ptr<Buffer> Buffer::create(size_t elem_size, size_t bytes, Residency
     if (elem_size == 0 || bytes < elem_size) return set_err("stream size too small");
     std::shared_ptr<Buffer> b(new Buffer());
     b->id_ = g_next_stream_id.fetch_add(1);
+    const bool pin = res == Residency::HostPinned;
+    if (pin) res = Residency::Host;
     b->elem_ = elem_size; b->res_ = res; b->device_ = device;
     if (res == Residency::Host) {
         const size_t page = (size_t)sysconf(_SC_PAGESIZE);
@@ -95,6 +97,28 @@ std::shared_ptr<Buffer> Buffer::create(size_t elem_size, size_t bytes, Residency
         if (m1 == MAP_FAILED || m2 == MAP_FAILED) { munmap(base, 2 * bytes); return set_err("double mmap failed"); }
         b->base_ = (char*)base; b->map_bytes_ = bytes;
         b->cap_ = bytes / elem_size;
+        if (pin) {
+            // Page-lock the ring (the analogue of the reference's double mmap, src/nowasm/circular_buffer.rs:96-128,
+            // made DMA-able): first the whole doubled range in one registration, else its two halves (both map the
+            // same memfd pages).
+            if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); munmap(base, 2 * bytes); b->base_ = nullptr; return set_err("no CUDA device for a pinned host stream"); }
+            memset(base, 0, bytes);                                          // fault the pages in before locking them
+            if (cudaHostRegister(base, 2 * bytes, cudaHostRegisterPortable) == cudaSuccess) {
+                b->pinned_parts_ = 1;
+            } else {
+                cudaGetLastError();
+                const cudaError_t e1 = cudaHostRegister(base, bytes, cudaHostRegisterPortable);
+                const cudaError_t e2 = e1 == cudaSuccess ? cudaHostRegister((char*)base + bytes, bytes, cudaHostRegisterPortable) : e1;
+                if (e1 != cudaSuccess || e2 != cudaSuccess) {
+                    cudaGetLastError();
+                    if (e1 == cudaSuccess) cudaHostUnregister(base);
+                    munmap(base, 2 * bytes); b->base_ = nullptr;
+                    return set_err(std::string("cudaHostRegister of the host ring failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+                }
+                b->pinned_parts_ = 2;
+            }
+            b->pinned_ = true;
+        }
     } else {
         const auto& d = drv::api();
         if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) return set_err("no CUDA device for a device-resident stream");
@@ -135,6 +159,12 @@ std::shared_ptr<Buffer> Buffer::create(size_t elem_size, size_t bytes, Residency
 Buffer::~Buffer() {
     if (!base_) return;
     if (res_ == Residency::Host) {
+        if (pinned_) {
+            cudaSetDevice(device_);
+            cudaStreamSynchronize((cudaStream_t)graph_stream(device_));   // no DMA may still target the ring
+            cudaHostUnregister(base_);
+            if (pinned_parts_ == 2) cudaHostUnregister(base_ + map_bytes_);
+        }
         munmap(base_, 2 * map_bytes_);
     } else {
         const auto& d = drv::api();
@@ -274,7 +304,11 @@ static int check_src_device(ReadStream& src, int device, const char* who) {
     return RRC_OK;
 }
 
+int make_output_stream(size_t elem, const StreamOpts& o, std::unique_ptr<WriteStream>* w, std::unique_ptr<ReadStream>* r);
 static int make_output(size_t elem, const StreamOpts& o, std::unique_ptr<WriteStream>* w, std::unique_ptr<ReadStream>* r) {
+    return make_output_stream(elem, o, w, r);
+}
+int make_output_stream(size_t elem, const StreamOpts& o, std::unique_ptr<WriteStream>* w, std::unique_ptr<ReadStream>* r) {
     std::string err;
     StreamPair p = new_stream(elem, o.bytes, o.res, o.device, &err);
     if (!p.w) return fail(RRC_ERR_CUDA, "new_stream failed: %s", err.c_str());

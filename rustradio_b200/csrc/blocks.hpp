@@ -63,7 +63,9 @@ struct Tag {
     TagValue val;
 };
 
-enum class Residency : int { Host = 0, Device = 1 };
+// HostPinned: a Host ring whose doubled mapping is page-locked with cudaHostRegister, so a GPU block's copies
+// from / to its windows are real asynchronous DMA (no pageable staging); residency() reports Host, pinned() true.
+enum class Residency : int { Host = 0, Device = 1, HostPinned = 2 };
 
 constexpr size_t DEFAULT_STREAM_SIZE = 4096000;   // bytes, src/stream.rs:105
 
@@ -77,6 +79,7 @@ public:
     size_t elem() const { return elem_; }
     size_t capacity() const { return cap_; }          // samples
     Residency residency() const { return res_; }
+    bool pinned() const { return pinned_; }
     int device() const { return device_; }
 
     size_t used();
@@ -115,6 +118,8 @@ private:
     size_t rpos_ = 0, wpos_ = 0, used_ = 0;
     std::map<size_t, std::vector<Tag>> tags_;
     bool writer_alive_ = true, reader_alive_ = true;
+    bool pinned_ = false;
+    int pinned_parts_ = 0;        // 1: the doubled range registered in one piece, 2: the two halves separately
 };
 
 class StreamWait {
@@ -168,6 +173,7 @@ struct BlockRet {
     size_t need = 0;
     static BlockRet again() { return {RetKind::Again, nullptr, 0}; }
     static BlockRet eof() { return {RetKind::EOF_, nullptr, 0}; }
+    static BlockRet pending() { return {RetKind::Pending, nullptr, 0}; }
     static BlockRet wait(const StreamWait* s, size_t n) { return {RetKind::WaitForStream, s, n}; }
 };
 
@@ -409,6 +415,72 @@ private:
     size_t elem_ = 1, n_ = 0, pos_ = 0;
     uint64_t repeat_ = 1, count_ = 0;
     int device_ = 0;
+};
+
+// Repeat (src/lib.rs:449-506).
+struct Repeat {
+    bool infinite = false;
+    uint64_t n = 1, count = 0;
+    static Repeat finite(uint64_t n) { Repeat r; r.n = n; return r; }
+    static Repeat forever() { Repeat r; r.infinite = true; return r; }
+    bool again();
+};
+
+// Page-locked staging buffer for file reads that go to a device ring.
+struct HostStage {
+    char* ptr = nullptr;
+    size_t cap = 0;
+    ~HostStage();
+    int reserve(size_t bytes);
+};
+
+int make_output_stream(size_t elem, const StreamOpts& o, std::unique_ptr<WriteStream>* w, std::unique_ptr<ReadStream>* r);
+
+// FileSource<T> (src/file_source.rs:11-153): raw little-endian samples from a file (a cf32 capture,
+// /dev/zero ...), whole samples only, optional repeat.  SURVEY 8f rank 1.
+class FileSource : public Block {
+public:
+    static int create(const char* path, size_t elem_size, Repeat repeat, const StreamOpts& o, std::unique_ptr<FileSource>* out);
+    ~FileSource() override;
+    int work(BlockRet* ret) override;
+    const char* block_name() const override { return "FileSource"; }
+    bool eof() override { return false; }
+private:
+    FileSource() = default;
+    std::unique_ptr<WriteStream> dst_;
+    int fd_ = -1, device_ = 0;
+    std::string path_;
+    size_t elem_ = 1;
+    Repeat repeat_;
+    std::vector<char> buf_, scratch_;      // carried partial bytes (`buf`, :50) / host read buffer
+    HostStage stage_;
+};
+
+// SigMFSource<T> (src/sigmf.rs:229-613): a SigMF Archive (tar) or separate Recording files
+// (<path>-meta / <path>-data); checks core:datatype == <type>_le and core:sample_rate.
+class SigMFSource : public Block {
+public:
+    // samp_rate < 0: no expectation (None).
+    static int create(const char* path, size_t elem_size, const char* type_string, double samp_rate, bool ignore_type_error,
+                      Repeat repeat, const StreamOpts& o, std::unique_ptr<SigMFSource>* out);
+    ~SigMFSource() override;
+    int work(BlockRet* ret) override;
+    const char* block_name() const override { return "SigMFSource"; }
+    bool eof() override { return false; }
+    bool sample_rate(double* r) const { if (has_rate_) *r = sample_rate_; return has_rate_; }   // :549-551
+    const std::string& datatype() const { return datatype_; }
+private:
+    SigMFSource() = default;
+    std::unique_ptr<WriteStream> dst_;
+    int fd_ = -1, device_ = 0;
+    std::string path_, datatype_;
+    size_t elem_ = 1;
+    uint64_t range_lo_ = 0, range_len_ = 0, left_ = 0, pos_ = 0;   // `range`, `left` (:274-279)
+    bool has_rate_ = false;
+    double sample_rate_ = 0;
+    Repeat repeat_;
+    std::vector<char> buf_;
+    HostStage stage_;
 };
 
 // Graph::run (src/graph.rs:99-173): single-threaded round robin.

@@ -22,7 +22,7 @@ namespace {
 rr::StreamOpts opts(size_t bytes, int residency, int device) {
     rr::StreamOpts o;
     o.bytes = bytes ? bytes : rr::DEFAULT_STREAM_SIZE;
-    o.res = residency == RRB_HOST ? rr::Residency::Host : rr::Residency::Device;
+    o.res = residency == RRB_HOST ? rr::Residency::Host : residency == RRB_HOST_PINNED ? rr::Residency::HostPinned : rr::Residency::Device;
     o.device = device;
     return o;
 }
@@ -154,6 +154,28 @@ int rrb_vector_source_new(const void* data, size_t n, size_t elem_size, uint64_t
     if (!blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
     std::unique_ptr<rr::VectorSource> b;
     RRC_TRY(rr::VectorSource::create(data, n, elem_size, repeat, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out);
+}
+static rr::Repeat repeat_of(uint64_t repeat) { return repeat == UINT64_MAX ? rr::Repeat::forever() : rr::Repeat::finite(repeat); }
+
+int rrb_file_source_new(const char* path, size_t elem_size, uint64_t repeat, size_t bytes, int res, int device,
+                        rrb_block_t** blk, rrb_rstream_t** out) {
+    if (!path || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
+    std::unique_ptr<rr::FileSource> b;
+    RRC_TRY(rr::FileSource::create(path, elem_size, repeat_of(repeat), opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out);
+}
+int rrb_sigmf_source_new(const char* path, size_t elem_size, const char* type_string, double samp_rate, int ignore_type_error,
+                         uint64_t repeat, size_t bytes, int res, int device, rrb_block_t** blk, rrb_rstream_t** out,
+                         double* sample_rate_out, int* has_sample_rate) {
+    if (!path || !type_string || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
+    std::unique_ptr<rr::SigMFSource> b;
+    RRC_TRY(rr::SigMFSource::create(path, elem_size, type_string, samp_rate, ignore_type_error != 0, repeat_of(repeat),
+                                    opts(bytes, res, device), &b));
+    double r = 0;
+    const bool has = b->sample_rate(&r);
+    if (sample_rate_out) *sample_rate_out = r;
+    if (has_sample_rate) *has_sample_rate = has ? 1 : 0;
     return finish(std::move(b), blk, out);
 }
 int rrb_fir_filter_new(rrb_rstream_t* src, int cplx, const float* taps, size_t ntaps, size_t deci, int translate,

@@ -3,4 +3,7 @@
 //! UNCOMPILED in this repository's environment (no Rust toolchain) — see INTEGRATION.md.
 pub mod ffi;
 pub mod blocks;
-pub use blocks::{CudaFirFilter, CudaFftFilter, CudaQuadratureDemod, CudaRationalResampler};
+pub use blocks::{
+    CudaFftFilter, CudaFftFilterFloat, CudaFirFilter, CudaFirFilterBuilder, CudaQuadratureDemod, CudaRationalResampler,
+    CudaRationalResamplerBuilder, CudaRtlSdrDecode, GpuSample,
+};

@@ -135,14 +135,45 @@ def test_fftfilt_plan_equals_restated_work(ntaps):
 
 
 def test_rust_ffi_declares_header_symbols():
-    """The (uncompiled) Rust binding only declares entry points that exist in the header, with the same arity."""
+    """The (uncompiled) Rust binding is GENERATED from the header (tools/gen_rust_ffi.py): it declares every
+    rrc_* / rrb_* entry point with the header's arity, and the committed file is not stale."""
+    import subprocess
+    import sys
     ffi = (ROOT / "rustradio_b200" / "rust" / "rustradio-cuda" / "src" / "ffi.rs").read_text()
-    decl = re.findall(r"pub fn (rrc_[a-z0-9_]+)\s*\(([^;]*?)\)\s*->", ffi, flags=re.S)
-    assert len(decl) >= 25
-    for name, args in decl:
-        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", HEADER, flags=re.S)
+    decl = dict(re.findall(r"pub fn (rr[cb]_[a-z0-9_]+)\s*\(([^;]*?)\)\s*->", ffi, flags=re.S))
+    assert set(decl) == set(declared_symbols()), set(declared_symbols()) ^ set(decl)
+    code = re.sub(r"/\*.*?\*/", " ", HEADER, flags=re.S)                 # prototypes only, no comments
+    for name, args in decl.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", code, flags=re.S)
         assert m, f"{name} in ffi.rs but not in rustradio_cuda.h"
         n_rust = 0 if not args.strip() else len([a for a in args.split(",") if a.strip()])
         c_args = m.group(1).strip()
         n_c = 0 if c_args in ("", "void") else len([a for a in c_args.split(",") if a.strip()])
         assert n_rust == n_c, f"{name}: {n_rust} args in ffi.rs vs {n_c} in the header"
+    assert subprocess.run([sys.executable, str(ROOT / "tools" / "gen_rust_ffi.py"), "--check"]).returncode == 0, \
+        "ffi.rs is stale: run python tools/gen_rust_ffi.py"
+
+
+def test_rust_blocks_cover_the_reference_constructors():
+    """The Rust side exposes the reference's constructor surface for the path:
+    builder + deci + translate, FirFilter<Float>, FftFilterFloat, the resampler's typestate builder and its
+    pending-aware eof()."""
+    rs = (ROOT / "rustradio_b200" / "rust" / "rustradio-cuda" / "src" / "blocks.rs").read_text()
+    for needle in ("pub fn builder(taps: impl Into<Vec<T>>) -> CudaFirFilterBuilder<T>", "pub fn deci(mut self, deci: usize) -> Self",
+                   "pub fn translate(mut self, samp_rate: Float, freq: Float) -> Self", "impl GpuSample for Float",
+                   "pub type CudaFftFilterFloat = CudaFftFilterT<Float>;", "pub struct CudaRationalResamplerBuilderBoth<T>",
+                   "pending == 0 && self.src.eof()", "pub struct CudaQuadratureDemod", "pub struct CudaRtlSdrDecode"):
+        assert needle in rs, needle
+    # every ffi function the blocks call exists in the generated binding
+    ffi = (ROOT / "rustradio_b200" / "rust" / "rustradio-cuda" / "src" / "ffi.rs").read_text()
+    for fn in set(re.findall(r"ffi::(rr[cb]_[a-z0-9_]+)\(", rs)):
+        assert f"pub fn {fn}(" in ffi, fn
+
+
+def test_rust_build_lists_every_source():
+    """build.rs compiles the same CUDA sources as csrc/Makefile."""
+    mk = (ROOT / "rustradio_b200" / "csrc" / "Makefile").read_text()
+    srcs = re.search(r"^SRCS := (.*)$", mk, flags=re.M).group(1).split()
+    br = (ROOT / "rustradio_b200" / "rust" / "rustradio-cuda" / "build.rs").read_text()
+    for s_ in srcs:
+        assert f'"{s_}"' in br, s_
