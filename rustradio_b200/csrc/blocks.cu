@@ -271,11 +271,26 @@ int Scratch::reserve(int device, size_t bytes) {
     return RRC_OK;
 }
 
+// cudaMemcpyAsync between a host ring window (`ring_ptr`, inside `ring`) and device memory.  A pinned ring whose
+// halves are two page-locked registrations cannot be crossed by ONE copy (invalid argument): split at the seam.
+static int ring_copy(Buffer& ring, void* dst, const void* src, const char* ring_ptr, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+    if (!bytes) return RRC_OK;
+    const char* seam = ring.dma_seam();
+    if (seam && ring_ptr < seam && ring_ptr + bytes > seam) {
+        const size_t first = (size_t)(seam - ring_ptr);
+        RRC_CUDA(cudaMemcpyAsync(dst, src, first, kind, st));
+        RRC_CUDA(cudaMemcpyAsync((char*)dst + first, (const char*)src + first, bytes - first, kind, st));
+        return RRC_OK;
+    }
+    RRC_CUDA(cudaMemcpyAsync(dst, src, bytes, kind, st));
+    return RRC_OK;
+}
+
 // Device view of an input window: the ring itself if it is device resident, else an H2D copy.
 static int stage_input(Buffer& b, const char* win, size_t bytes, Scratch& s, int device, const char** dev) {
     if (b.residency() == Residency::Device) { *dev = win; return RRC_OK; }
     RRC_TRY(s.reserve(device, std::max<size_t>(bytes, 16)));
-    RRC_CUDA(cudaMemcpyAsync(s.ptr, win, bytes, cudaMemcpyHostToDevice, (cudaStream_t)graph_stream(device)));
+    RRC_TRY(ring_copy(b, s.ptr, win, win, bytes, cudaMemcpyHostToDevice, (cudaStream_t)graph_stream(device)));
     *dev = s.ptr;
     return RRC_OK;
 }
@@ -290,7 +305,7 @@ static int stage_output(Buffer& b, char* win, size_t bytes, Scratch& s, int devi
 static int finish_output(Buffer& b, char* win, size_t bytes, Scratch& s, int device) {
     if (b.residency() == Residency::Device) return RRC_OK;
     cudaStream_t st = (cudaStream_t)graph_stream(device);
-    if (bytes) RRC_CUDA(cudaMemcpyAsync(win, s.ptr, bytes, cudaMemcpyDeviceToHost, st));
+    RRC_TRY(ring_copy(b, win, s.ptr, win, bytes, cudaMemcpyDeviceToHost, st));
     RRC_CUDA(cudaStreamSynchronize(st));
     return RRC_OK;
 }
@@ -405,7 +420,7 @@ int FftFilter::work(BlockRet* ret) {          // src/fft_filter.rs:290-354, whol
     size_t done = 0;       // blocks done
     if (blocks && buffered_ > 0) {            // complete the block that was being accumulated (:306-308)
         const size_t add = S - buffered_;
-        RRC_CUDA(cudaMemcpyAsync(partial_ + buffered_ * E, in, add * E, in_kind, st));
+        RRC_TRY(ring_copy(src_->buffer(), partial_ + buffered_ * E, in, in, add * E, in_kind, st));
         RRC_TRY(rrc_fftfilt_run(h_, (const float*)partial_, S, (float*)dout, st));
         ipos = add; done = 1;
     }
@@ -414,7 +429,7 @@ int FftFilter::work(BlockRet* ret) {          // src/fft_filter.rs:290-354, whol
         const char* din;
         if (host_in) {
             RRC_TRY(sin_.reserve(device_, nb * S * E));
-            RRC_CUDA(cudaMemcpyAsync(sin_.ptr, in + ipos * E, nb * S * E, cudaMemcpyHostToDevice, st));
+            RRC_TRY(ring_copy(src_->buffer(), sin_.ptr, in + ipos * E, in + ipos * E, nb * S * E, cudaMemcpyHostToDevice, st));
             din = sin_.ptr;
         } else {
             din = in + ipos * E;
@@ -424,7 +439,7 @@ int FftFilter::work(BlockRet* ret) {          // src/fft_filter.rs:290-354, whol
     }
     // trailing partial accumulation (:306-327): buf keeps `buffered_after` samples
     const size_t base = blocks ? 0 : buffered_;
-    if (consume > ipos) RRC_CUDA(cudaMemcpyAsync(partial_ + base * E, in + ipos * E, (consume - ipos) * E, in_kind, st));
+    if (consume > ipos) RRC_TRY(ring_copy(src_->buffer(), partial_ + base * E, in + ipos * E, in + ipos * E, (consume - ipos) * E, in_kind, st));
     if (host_in) RRC_CUDA(cudaStreamSynchronize(st));          // the host window is released by consume()
     if (blocks) RRC_TRY(finish_output(dst_->buffer(), outp, blocks * S * E, sout_, device_));
 
@@ -491,7 +506,7 @@ int FftFilterFloat::work(BlockRet* ret) {     // src/fft_filter.rs:428-490
         const size_t n = std::min(in_len, to_len);
         if (n) {
             const bool host_in = src_->buffer().residency() == Residency::Host;
-            RRC_CUDA(cudaMemcpyAsync(to, in, n * 4, host_in ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
+            RRC_TRY(ring_copy(src_->buffer(), to, in, in, n * 4, host_in ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
             if (host_in) RRC_CUDA(cudaStreamSynchronize(st));
         }
         tags.erase(std::remove_if(tags.begin(), tags.end(), [&](const Tag& t) { return t.pos >= n; }), tags.end());

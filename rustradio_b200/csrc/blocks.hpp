@@ -80,6 +80,8 @@ public:
     size_t capacity() const { return cap_; }          // samples
     Residency residency() const { return res_; }
     bool pinned() const { return pinned_; }
+    // Pinned host rings whose two halves are separate cudaHostRegister ranges: one copy must not span the seam.
+    const char* dma_seam() const { return (pinned_ && pinned_parts_ == 2) ? base_ + map_bytes_ : nullptr; }
     int device() const { return device_; }
 
     size_t used();

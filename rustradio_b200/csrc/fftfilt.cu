@@ -17,6 +17,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -198,6 +199,99 @@ fftfilt_tma_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2
     }
 }
 
+// PACKED kernel (variant 37; fftfilt_pk.cuh): the same 16384-point block with FFMA2 / FADD2 / FMUL2 lanes,
+// pair-word exchange layouts, TMA-staged input (32 bulk copies of 4 KiB, one per 512-sample row, into the
+// plane-pitched landing layout L0) and three CTA barriers per block.
+constexpr int PK_NSTAMP = 12, PK_TRACE_BLK = 6;
+constexpr size_t FFTFILT_PK_SMEM = (size_t)(fftp::SMEM_WORDS + 512 + 512 + fftp::HRES_WORDS + 2) * sizeof(float2);
+
+// MODE: 0 = plain, 1 = FP-turn ping-pong between two warp groups, 2 = staggered first load bursts (fftfilt_pk.cuh)
+template <bool DECIM, bool ACCUM, int MODE>
+__global__ void __launch_bounds__(fftk::NT, 1)
+fftfilt_pk_kernel(const BlockIO io, const float2* __restrict__ Hq, const float2* __restrict__ tw1g,
+                  const float2* __restrict__ tw2pg, long long nblocks, int tune, long long* __restrict__ trace) {
+    extern __shared__ __align__(16) float2 sm[];
+    float2* s_tw2p = sm + fftp::SMEM_WORDS;
+    float2* s_tw1 = s_tw2p + 512;
+    float2* s_hres = s_tw1 + 512;
+    const int tid = threadIdx.x;
+    s_tw2p[tid] = tw2pg[tid];
+    s_tw1[tid] = tw1g[tid];
+    fftp::load_hres(tid, Hq, s_hres);
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(s_hres + fftp::HRES_WORDS);
+    const unsigned sm_a = (unsigned)__cvta_generic_to_shared(sm);
+    const int pf = tune & 15;
+    if (io.hist_next && blockIdx.x == gridDim.x - 1) fftk::update_history(io, tid, fftk::NT);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // Every thread calls stage() (the test is CTA uniform); the caller guarantees nobody still reads the buffer.
+    auto stage = [&](long long nb) {
+        if (fftp::bulk_ok(nb, io)) {
+            if (tid == 0) {
+                const float2* src = io.in + fftp::seg0_of(nb, io);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(fftk::N * 8) : "memory");
+#pragma unroll 1
+                for (int n1 = 0; n1 < 32; ++n1)
+                    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(sm_a + n1 * (fftp::PP * 8)), "l"(src + n1 * 512), "r"(4096), "r"(mbar) : "memory");
+            }
+        } else {
+            fftp::stage_fallback(tid, nb, io, sm);
+            __syncthreads();                                  // the arrival below must follow every thread's stores
+            if (tid == 0) asm volatile("mbarrier.arrive.shared.b64 _, [%0];" ::"r"(mbar) : "memory");
+        }
+    };
+    if (blockIdx.x < nblocks) stage(blockIdx.x);
+    unsigned parity = 0;
+    // FP-turn groups: warps 0-3 and 8-11 are group 0, 4-7 and 12-15 group 1 (two warps of each per sub-partition)
+    using Turn = typename std::conditional<MODE == 1, fftp::PingPong, typename std::conditional<MODE == 2, fftp::Stagger, fftp::NoTurn>::type>::type;
+    Turn turn;
+    if constexpr (MODE == 1) {
+        turn.g = (tid >> 7) & 1;
+        if (turn.g == 1) turn.release();                      // group 0 takes the first turn
+    }
+    if constexpr (MODE == 2) turn.delay = (tid >> 5) * (tune >> 16 ? (tune >> 16) : 128);
+    // RRC_FFTFILT_TRACE (debug): every warp of CTA 3 stamps clock64 at the phase boundaries of its blocks 2..7
+    int it = 0;
+    auto stamp = [&](int i) {
+        if (trace && blockIdx.x == 3 && it >= 2 && it < 2 + PK_TRACE_BLK && (tid & 31) == 0)
+            trace[((size_t)(it - 2) * 16 + (tid >> 5)) * PK_NSTAMP + i] = clock64();
+    };
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x, ++it) {
+        const long long nb = blk + gridDim.x;
+        stamp(0);
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        stamp(1);
+        fftp::phase_a(tid, s_tw1, sm, turn);                  // in place pairwise: __syncwarp only
+        stamp(2);
+        __syncthreads();
+        stamp(3);
+        if (pf) prefetch_segment(io, nb, nblocks, tid);       // next block -> L2, so the bulk copies are L2 hits
+        fftp::phase_b(tid, s_tw2p, sm, turn);
+        __syncwarp();
+        stamp(4);
+        fftp::phase_c(tid, Hq, s_hres, sm, turn);
+        __syncwarp();
+        stamp(5);
+        fftp::phase_bi(tid, s_tw2p, sm, turn);
+        stamp(6);
+        __syncthreads();
+        stamp(7);
+        fftp::phase_ai<DECIM, ACCUM>(tid, blk, io, s_tw1, sm, [&]() {
+            stamp(8);
+            __syncthreads();                                  // every thread has read the buffer
+            if (nb < nblocks) stage(nb);
+            stamp(9);
+        }, turn);
+        stamp(10);
+    }
+}
+
 // Ping-pong variant of fftfilt_kernel (PingPong policy: fftfilt_core.cuh).
 template <bool DECIM, bool ACCUM>
 __global__ void __launch_bounds__(fftk::NT, 1)
@@ -330,10 +424,45 @@ int launch_part16(rrc_fftfilt* h, const BlockIO& io, const float2* Hd, cudaStrea
 }
 
 template <bool DECIM, bool ACCUM>
-int launch_part(rrc_fftfilt* h, const BlockIO& io, const float2* Hp, cudaStream_t st) {
+int launch_part(rrc_fftfilt* h, const BlockIO& io, const float2* Hp, const float2* Hq, cudaStream_t st) {
     long long nblocks = (io.n_in + io.V - 1) / io.V;
     if (io.real) nblocks = (nblocks + 1) / 2;                   // two real blocks per complex transform
     const int grid = (int)std::min<long long>(nblocks, sm_count(h->device));
+    if ((h->variant == 37 || h->variant == 38 || h->variant == 39) && !io.real && !io.in_u8) {
+        auto pk = h->variant == 38 ? fftfilt_pk_kernel<DECIM, ACCUM, 1> : h->variant == 39 ? fftfilt_pk_kernel<DECIM, ACCUM, 2> : fftfilt_pk_kernel<DECIM, ACCUM, 0>;
+        RRC_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_PK_SMEM));
+        static const int tune_pk = [] { const char* e = getenv("RRC_FFTFILT_TUNE"); return e ? (int)strtol(e, nullptr, 0) : 1; }();
+        static const bool want_trace = getenv("RRC_FFTFILT_TRACE") != nullptr;
+        long long* dtrace = nullptr;
+        const size_t trace_n = (size_t)PK_TRACE_BLK * 16 * PK_NSTAMP;
+        if (want_trace) { RRC_CUDA(cudaMalloc((void**)&dtrace, trace_n * 8)); RRC_CUDA(cudaMemsetAsync(dtrace, 0, trace_n * 8, st)); }
+        pk<<<grid, fftk::NT, FFTFILT_PK_SMEM, st>>>(io, Hq, h->tw1, h->tw2p, nblocks, tune_pk, dtrace);
+        RRC_CHECK_LAUNCH();
+        count_launch();
+        if (want_trace) {                                       // debug only: synchronous dump of the per-phase cycle table
+            std::vector<long long> tr(trace_n);
+            RRC_CUDA(cudaStreamSynchronize(st));
+            RRC_CUDA(cudaMemcpy(tr.data(), dtrace, trace_n * 8, cudaMemcpyDeviceToHost));
+            cudaFree(dtrace);
+            static const char* names[] = {"wait mbarrier (TMA landed)", "A (L0 read, DIF32, tw, L1 write)", "barrier 1", "B", "C", "B'", "barrier 2",
+                                          "A': loads", "barrier 3 + stage", "A': tw, IDFT32, STG"};
+            static int dumps = 0;
+            if (nblocks > 148 * 8 && dumps++ < 2) {
+                for (int b = 0; b < PK_TRACE_BLK; ++b) {
+                    long long t0 = tr[(size_t)(b * 16) * PK_NSTAMP], tend = 0;
+                    for (int w = 0; w < 16; ++w) { t0 = std::min(t0, tr[(size_t)(b * 16 + w) * PK_NSTAMP]); tend = std::max(tend, tr[(size_t)(b * 16 + w) * PK_NSTAMP + 10]); }
+                    fprintf(stderr, "pk trace (variant %d) block iter %d: total %lld cycles\n", h->variant, b + 2, tend - t0);
+                    for (int p = 0; p < 10; ++p) {
+                        std::vector<long long> d;
+                        for (int w = 0; w < 16; ++w) d.push_back(tr[(size_t)(b * 16 + w) * PK_NSTAMP + p + 1] - tr[(size_t)(b * 16 + w) * PK_NSTAMP + p]);
+                        std::sort(d.begin(), d.end());
+                        fprintf(stderr, "   %-34s min %6lld  med %6lld  max %6lld\n", names[p], d[0], d[8], d[15]);
+                    }
+                }
+            }
+        }
+        return RRC_OK;
+    }
     auto kern = io.real ? fftfilt_kernel<DECIM, ACCUM, false> : h->variant == 33 ? fftfilt_pp_kernel<DECIM, ACCUM> : h->variant == 34 ? fftfilt_st_kernel<DECIM, ACCUM> : h->variant == 35 ? fftfilt_kernel<DECIM, ACCUM, true> : (h->variant == 36 && !io.in_u8) ? fftfilt_tma_kernel<DECIM, ACCUM> : fftfilt_kernel<DECIM, ACCUM, false>;
     RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_SMEM));
     static const int tune = [] { const char* e = getenv("RRC_FFTFILT_TUNE"); return e ? (int)strtol(e, nullptr, 0) : 1; }();
@@ -359,7 +488,7 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
     io.real = h->real;
     const bool decim = !(deci == 1 && skip == 0);
     // kernels that update the carried history themselves (one launch per run): the 512-thread LDG / TMA kernels
-    const bool fused_hist = h->T1 > 0 && (h->real || h->variant == 32 || h->variant == 35 || h->variant == 36);
+    const bool fused_hist = h->T1 > 0 && (h->real || h->variant == 32 || h->variant == 35 || h->variant == 36 || h->variant == 37 || h->variant == 38 || h->variant == 39);
     long long shift = 0;
     for (size_t p = 0; p < h->part_T1.size(); ++p) {
         io.T1 = h->part_T1[p];
@@ -370,8 +499,8 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
         if (h->variant == 16 && !h->real) {
             if (p == 0) s = decim ? launch_part16<true, false>(h, io, h->part_Hd[p], st) : launch_part16<false, false>(h, io, h->part_Hd[p], st);
             else        s = decim ? launch_part16<true, true>(h, io, h->part_Hd[p], st) : launch_part16<false, true>(h, io, h->part_Hd[p], st);
-        } else if (p == 0) s = decim ? launch_part<true, false>(h, io, h->part_Hp[p], st) : launch_part<false, false>(h, io, h->part_Hp[p], st);
-        else        s = decim ? launch_part<true, true>(h, io, h->part_Hp[p], st) : launch_part<false, true>(h, io, h->part_Hp[p], st);
+        } else if (p == 0) s = decim ? launch_part<true, false>(h, io, h->part_Hp[p], h->part_Hq[p], st) : launch_part<false, false>(h, io, h->part_Hp[p], h->part_Hq[p], st);
+        else        s = decim ? launch_part<true, true>(h, io, h->part_Hp[p], h->part_Hq[p], st) : launch_part<false, true>(h, io, h->part_Hp[p], h->part_Hq[p], st);
         RRC_TRY(s);
         shift += io.T1 + 1;
     }
@@ -463,6 +592,12 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
         if ((e = up(&d, Hp)) != cudaSuccess) return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
         h->part_Hp.push_back(d);
         h->part_T1.push_back((int)len - 1);
+        std::vector<float2> Hq, tw2p;
+        fftk::build_tables_pk(taps + 2 * off, len, Hq, tw2p);
+        float2* dq = nullptr;
+        if ((e = up(&dq, Hq)) != cudaSuccess) return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
+        h->part_Hq.push_back(dq);
+        if (!h->tw2p && (e = up(&h->tw2p, tw2p)) != cudaSuccess) return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
         std::vector<float2> Hd, t1, t2, t3;
         fftk::build_tables16(taps + 2 * off, len, Hd, t1, t2, t3);
         float2* dd = nullptr;
@@ -471,7 +606,7 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
         if (!h->tw1_16 && ((e = up(&h->tw1_16, t1)) != cudaSuccess || (e = up(&h->tw2_16, t2)) != cudaSuccess || (e = up(&h->tw3_16, t3)) != cudaSuccess))
             return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
     }
-    if (const char* v = getenv("RRC_FFTFILT_VARIANT")) h->variant = atoi(v) == 16 ? 16 : atoi(v) == 33 ? 33 : atoi(v) == 34 ? 34 : atoi(v) == 35 ? 35 : atoi(v) == 36 ? 36 : 32;
+    if (const char* v = getenv("RRC_FFTFILT_VARIANT")) h->variant = atoi(v) == 16 ? 16 : atoi(v) == 33 ? 33 : atoi(v) == 34 ? 34 : atoi(v) == 35 ? 35 : atoi(v) == 36 ? 36 : atoi(v) == 37 ? 37 : atoi(v) == 38 ? 38 : atoi(v) == 39 ? 39 : 32;
     h->Hp = h->part_Hp[0];
     if ((e = up(&h->tw1, tw1)) != cudaSuccess || (e = up(&h->tw2, tw2)) != cudaSuccess)
         return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
@@ -502,6 +637,8 @@ int rrc_fftfilt_destroy(rrc_fftfilt_t* h) {
     cudaSetDevice(h->device);
     for (float2* p : h->part_Hp) cudaFree(p);
     for (float2* p : h->part_Hd) cudaFree(p);
+    for (float2* p : h->part_Hq) cudaFree(p);
+    cudaFree(h->tw2p);
     cudaFree(h->tw1_16); cudaFree(h->tw2_16); cudaFree(h->tw3_16);
     cudaFree(h->tw1); cudaFree(h->tw2); cudaFree(h->hist[0]); cudaFree(h->hist[1]);
     if (h->state_ev) cudaEventDestroy(h->state_ev);

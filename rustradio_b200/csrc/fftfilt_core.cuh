@@ -435,6 +435,57 @@ RRC_HD void phase_mid(int tid, const float2* tw2, const float2* Hp, const float2
 
 // Phase A': tid = t; conj twiddle, IDFT32 over k1 -> n1; store valid outputs.
 struct NoHook { RRC_HD void operator()() const {} };
+
+// v[n1] is segment element n = tid + 512*n1 of block `blk`; elements n >= T1 are valid outputs, filter
+// output index o = o0 + n (shared by the scalar and the packed kernels).
+template <bool DECIM, bool ACCUM>
+RRC_HD void store_outputs(int tid, long long blk, const BlockIO& io, const float2 (&v)[32]) {
+    const long long o0 = (io.real ? 2 * blk : blk) * (long long)io.V - io.T1;
+    const int tq = io.T1 >> 9, tr = io.T1 & 511;
+    const int first = tq + (tid < tr ? 1 : 0);                 // element n1 of this thread is valid iff n1 >= first
+    if (io.real) {                                              // real stream: .re -> block 2b, .im -> block 2b+1
+        float* q = reinterpret_cast<float*>(io.out) + o0 + tid;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            if (n1 >= first) {
+                const long long o = o0 + tid + 512 * n1;
+                if (o < io.n_out) q[512 * n1] = ACCUM ? q[512 * n1] + v[n1].x : v[n1].x;
+                if (o + io.V < io.n_out) q[512 * n1 + io.V] = ACCUM ? q[512 * n1 + io.V] + v[n1].y : v[n1].y;
+            }
+        }
+        return;
+    }
+    if constexpr (!DECIM) {
+        float2* q = io.out + o0 + tid;
+        if (o0 + N <= io.n_out) {                               // interior: only the n >= T1 test (one compare per element)
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1)
+                if (n1 >= first) q[512 * n1] = ACCUM ? cadd(q[512 * n1], v[n1]) : v[n1];
+        } else {
+            // last valid element of this thread: o0 + tid + 512*n1 < n_out  <=>  n1 < lim
+            const long long rem = io.n_out - o0 - tid;
+            const int lim = rem <= 0 ? 0 : (int)((rem + 511) >> 9 > 32 ? 32 : (rem + 511) >> 9);
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1)
+                if (n1 >= first && n1 < lim) q[512 * n1] = ACCUM ? cadd(q[512 * n1], v[n1]) : v[n1];
+        }
+    } else {
+        // keep outputs with (o - skip) >= 0 and (o - skip) % deci == 0, at index (o - skip)/deci.
+        const long long D = io.deci;
+        long long r = o0 + tid - io.skip;                       // for n1 = 0
+        long long qd = r >= 0 ? r / D : -((-r + D - 1) / D);    // floor division
+        long long m = r - qd * D;                               // in [0, D)
+        const long long sq = 512 / D, sm_ = 512 % D;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            if (n1 >= first && m == 0 && qd >= 0 && qd < io.n_out)
+                io.out[qd] = ACCUM ? cadd(io.out[qd], v[n1]) : v[n1];
+            qd += sq; m += sm_;
+            if (m >= D) { m -= D; ++qd; }
+        }
+    }
+}
+
 // after_load() runs once the thread has read its 32 exchange-buffer words (the staged kernel puts a
 // CTA barrier and the next block's stage_input there).
 template <bool DECIM, bool ACCUM, class Turn = NoTurn, class AfterLoad = NoHook>
@@ -453,49 +504,7 @@ RRC_HD void phase_ai(int tid, long long blk, const BlockIO& io, const float2* tw
     for (int k1 = 0; k1 < 32; ++k1) v[bitrev(k1, 5)] = cmul_conj(v[bitrev(k1, 5)], p[k1]);
     dit<32, -1>(v);
     turn.release();
-    // v[n1] is segment element n = tid + 512*n1; elements n >= T1 are valid
-    // outputs, filter output index o = o0 + n.
-    const long long o0 = (io.real ? 2 * blk : blk) * (long long)io.V - io.T1;
-    const int tq = io.T1 >> 9, tr = io.T1 & 511;
-    if (io.real) {                                              // real stream: .re -> block 2b, .im -> block 2b+1
-        float* q = reinterpret_cast<float*>(io.out) + o0 + tid;
-#pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-            if (n1 > tq || (n1 == tq && tid >= tr)) {
-                const long long o = o0 + tid + 512 * n1;
-                if (o < io.n_out) q[512 * n1] = ACCUM ? q[512 * n1] + v[n1].x : v[n1].x;
-                if (o + io.V < io.n_out) q[512 * n1 + io.V] = ACCUM ? q[512 * n1 + io.V] + v[n1].y : v[n1].y;
-            }
-        }
-        return;
-    }
-    if constexpr (!DECIM) {
-        float2* q = io.out + o0 + tid;
-        if (o0 + N <= io.n_out) {                               // interior: only the n >= T1 test
-#pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1)
-                if (n1 > tq || (n1 == tq && tid >= tr)) q[512 * n1] = ACCUM ? cadd(q[512 * n1], v[n1]) : v[n1];
-        } else {
-#pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1)
-                if ((n1 > tq || (n1 == tq && tid >= tr)) && o0 + tid + 512 * n1 < io.n_out)
-                    q[512 * n1] = ACCUM ? cadd(q[512 * n1], v[n1]) : v[n1];
-        }
-    } else {
-        // keep outputs with (o - skip) >= 0 and (o - skip) % deci == 0, at index (o - skip)/deci.
-        const long long D = io.deci;
-        long long r = o0 + tid - io.skip;                       // for n1 = 0
-        long long qd = r >= 0 ? r / D : -((-r + D - 1) / D);    // floor division
-        long long m = r - qd * D;                               // in [0, D)
-        const long long sq = 512 / D, sm_ = 512 % D;
-#pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-            if ((n1 > tq || (n1 == tq && tid >= tr)) && m == 0 && qd >= 0 && qd < io.n_out)
-                io.out[qd] = ACCUM ? cadd(io.out[qd], v[n1]) : v[n1];
-            qd += sq; m += sm_;
-            if (m >= D) { m -= D; ++qd; }
-        }
-    }
+    store_outputs<DECIM, ACCUM>(tid, blk, io, v);
 }
 
 }}  // namespace rrc::fftk

@@ -26,13 +26,16 @@ struct rrc_fftfilt {
     std::vector<int> part_T1;         // taps of partition p, minus 1
     std::vector<float2*> part_Hp;     // spectrum of partition p (512-thread layout)
     std::vector<float2*> part_Hd;     // spectrum of partition p (1024-thread layout)
+    std::vector<float2*> part_Hq;     // spectrum of partition p (packed kernel: re-pairs / im-pairs per thread, fftfilt_pk.cuh)
+    float2* tw2p = nullptr;           // packed W_512 table of the packed kernel
     float2* Hp = nullptr;             // == part_Hp[0]
     float2* tw1_16 = nullptr;
     float2* tw2_16 = nullptr;
     float2* tw3_16 = nullptr;
     int real = 0;                     // real stream + real taps (rrc_fftfilt_f32_create): f32 in / out / history
     int in_u8 = 0;                    // 1: run() inputs are u8 I/Q pairs (rrc_fftfilt_set_input_u8iq)
-    // kernel variant (RRC_FFTFILT_VARIANT): 36 = 512 threads x 32 points with TMA-staged input (default),
+    // kernel variant (RRC_FFTFILT_VARIANT): 37 = PACKED FP32 lanes + TMA-staged input (fftfilt_pk.cuh),
+    // 36 = 512 threads x 32 points with TMA-staged input (default),
     // 32 = the same with LDG input + L2 prefetch, 16 = 1024 threads x 16 points, 33/34/35 = experiments
     int variant = 36;
     float2* tw1 = nullptr;

@@ -10,6 +10,7 @@
 #include "fftfilt_core.cuh"
 #include "fftfilt16_core.cuh"
 #include "fftfilt_fold_core.cuh"
+#include "fftfilt_pk.cuh"
 
 namespace rrc { namespace fftk {
 
@@ -59,6 +60,31 @@ inline void build_tables(const float* taps, size_t ntaps, std::vector<float2>& H
         for (int n3 = 0; n3 < 16; ++n3) {
             const double a = -2.0 * M_PI * (double)(n3 * k2) / 512.0;
             tw2[k2 * 16 + n3] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+}
+
+// Tables of the packed kernel (fftfilt_pk.cuh), thread tid = k1*16 + l:
+//   Hq[tid*32 + k3]      = (Re H[k1 + 32 l + 1024 k3], Re H[k1 + 32 (l+16) + 1024 k3]) / N
+//   Hq[tid*32 + 16 + k3] = the imaginary parts
+//   tw2p[(2j + c)*16 + n3] = component c of (W_512^{n3 j}, W_512^{n3 (j+16)})
+inline void build_tables_pk(const float* taps, size_t ntaps, std::vector<float2>& Hq, std::vector<float2>& tw2p) {
+    std::vector<std::complex<double>> H(N);
+    for (size_t k = 0; k < ntaps; ++k) H[k] = {(double)taps[2 * k], (double)taps[2 * k + 1]};
+    fft_host(H);
+    Hq.resize(2 * (size_t)N); tw2p.resize(512);
+    for (int tid = 0; tid < 512; ++tid) {
+        const int k1 = tid >> 4, l = tid & 15;
+        for (int k3 = 0; k3 < 16; ++k3) {
+            const auto a = H[k1 + 32 * l + 1024 * k3] / (double)N, b = H[k1 + 32 * (l + 16) + 1024 * k3] / (double)N;
+            Hq[(size_t)tid * 32 + k3] = make_float2((float)a.real(), (float)b.real());
+            Hq[(size_t)tid * 32 + 16 + k3] = make_float2((float)a.imag(), (float)b.imag());
+        }
+    }
+    for (int j = 0; j < 16; ++j)
+        for (int n3 = 0; n3 < 16; ++n3) {
+            const double a0 = -2.0 * M_PI * (double)(n3 * j) / 512.0, a1 = -2.0 * M_PI * (double)(n3 * (j + 16)) / 512.0;
+            tw2p[(2 * j) * 16 + n3] = make_float2((float)std::cos(a0), (float)std::cos(a1));
+            tw2p[(2 * j + 1) * 16 + n3] = make_float2((float)std::sin(a0), (float)std::sin(a1));
         }
 }
 

@@ -38,6 +38,35 @@ extern "C" int emul_fftfilt(const float* taps, long long ntaps, const float* in,
         // (TWC), 2 = TWC + staged input (stage_input / phase_a_staged).
         const char* me = getenv("RRC_EMUL_FFTFILT_MODE");
         const int mode = me ? atoi(me) : 0;
+        if (mode == 4) {                                       // packed kernel (fftfilt_pk.cuh)
+            namespace pk = rrc::fftp;
+            std::vector<float2> Hq, tw2p, smp(pk::SMEM_WORDS), hresp(pk::HRES_WORDS);
+            build_tables_pk(taps + 2 * off, (size_t)len, Hq, tw2p);
+            for (int t = 0; t < NT; ++t) pk::load_hres(t, Hq.data(), hresp.data());
+            std::vector<pk::C2> regs((size_t)NT * 16);
+            auto save = [&](int t, const pk::C2 (&v)[16]) { for (int i = 0; i < 16; ++i) regs[(size_t)t * 16 + i] = v[i]; };
+            auto load = [&](int t, pk::C2 (&v)[16]) { for (int i = 0; i < 16; ++i) v[i] = regs[(size_t)t * 16 + i]; };
+            for (long long blk = 0; blk < nblocks; ++blk) {
+                if (pk::bulk_ok(blk, io)) {                        // 32 bulk copies of 4 KiB, one per row n1
+                    for (int n1 = 0; n1 < 32; ++n1) memcpy(smp.data() + n1 * pk::PP, io.in + pk::seg0_of(blk, io) + 512 * n1, sizeof(float2) * 512);
+                } else {
+                    for (int t = 0; t < NT; ++t) pk::stage_fallback(t, blk, io, smp.data());
+                }
+                for (int t = 0; t < NT; ++t) { pk::C2 v[16]; pk::phase_a_compute(t, tw1.data(), smp.data(), v); save(t, v); }
+                for (int t = 0; t < NT; ++t) { pk::C2 v[16]; load(t, v); pk::phase_a_store(t, smp.data(), v); }
+                for (int t = 0; t < NT; ++t) { pk::C2 v[16]; pk::phase_b_compute(t, tw2p.data(), smp.data(), v); save(t, v); }
+                for (int t = 0; t < NT; ++t) { pk::C2 v[16]; load(t, v); pk::phase_b_store(t, smp.data(), v); }
+                for (int t = 0; t < NT; ++t) pk::phase_c(t, Hq.data(), hresp.data(), smp.data());
+                for (int t = 0; t < NT; ++t) { pk::C2 v[16]; pk::phase_bi_compute(t, tw2p.data(), smp.data(), v); save(t, v); }
+                for (int t = 0; t < NT; ++t) { pk::C2 v[16]; load(t, v); pk::phase_bi_store(t, smp.data(), v); }
+                for (int t = 0; t < NT; ++t) {
+                    if (off == 0) { if (decim) pk::phase_ai<true, false>(t, blk, io, tw1.data(), smp.data()); else pk::phase_ai<false, false>(t, blk, io, tw1.data(), smp.data()); }
+                    else          { if (decim) pk::phase_ai<true, true>(t, blk, io, tw1.data(), smp.data()); else pk::phase_ai<false, true>(t, blk, io, tw1.data(), smp.data()); }
+                }
+            }
+            shift += len;
+            continue;
+        }
         for (long long blk = 0; blk < nblocks; ++blk) {
             if (mode == 2) {
                 for (int t = 0; t < NT; ++t) stage_input(t, blk, io, sm.data());

@@ -52,11 +52,12 @@ def test_emulated_kernel_matches_f64_convolution(emul, ntaps, n, variant):
     assert O.rel_rms(emul(taps, x, variant=variant), O.conv_full_f64_fft(x, taps, n)) <= 1e-5
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("ntaps,n", [(1, 3000), (193, 8000), (4097, 40_000), (64, 16384 * 2 + 5), (16385, 40_000), (4098, 70_000)])
 def test_emulated_kernel_twiddles_in_phase_c_and_staged_input(emul, monkeypatch, ntaps, n, mode):
-    """fftfilt_core.cuh TWC path (W_512 twiddles from powers inside phase C) and stage_input /
-    phase_a_staged: same index math and values as the table-twiddle kernel."""
+    """fftfilt_core.cuh TWC path (W_512 twiddles from powers inside phase C), stage_input /
+    phase_a_staged, linear TMA staging (mode 3) and the PACKED kernel of fftfilt_pk.cuh (mode 4: FFMA2
+    lanes, pair-word exchange layouts): same index math and values as the table-twiddle kernel."""
     monkeypatch.setenv("RRC_EMUL_FFTFILT_MODE", str(mode))
     taps = (O.low_pass_n(1.0, 0.05, ntaps).astype(np.complex64) * (1 + 0.3j)) if ntaps > 2 else np.array([0.5 - 0.25j], np.complex64)
     x = O.synth_c32(7, 0, n)
