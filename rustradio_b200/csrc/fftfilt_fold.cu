@@ -25,6 +25,7 @@ using fftf::FoldIO;
 
 constexpr int FOLD_U_OFF = 4096;      // float2 offset of the u array inside the exchange buffer (past P2)
 static_assert(fftf::P2_ELEMS <= FOLD_U_OFF && FOLD_U_OFF + fftf::LU <= fftk::SMEM_ELEMS, "fold staging layout");
+constexpr int FOLD_NSTAMP = 12, FOLD_TRACE_BLK = 6;
 constexpr size_t FOLD_SMEM = (size_t)(fftk::SMEM_ELEMS + 512 + 512 + fftk::HRES_ELEMS + 512 + 32) * sizeof(float2);
 
 __device__ __forceinline__ void task_barrier() { asm volatile("bar.sync 3, 64;" ::: "memory"); }
@@ -33,7 +34,8 @@ template <int NC>
 __global__ void __launch_bounds__(fftk::NT, 1)
 fftfilt_fold_kernel(const FoldIO io, const float2* __restrict__ Hc, const float2* __restrict__ tw1g,
                     const float2* __restrict__ tw2g, const float2* __restrict__ gcg,
-                    const float2* __restrict__ twcg, const float2* __restrict__ twm, long long nblocks) {
+                    const float2* __restrict__ twcg, const float2* __restrict__ twm, long long nblocks,
+                    long long* __restrict__ trace) {
     extern __shared__ __align__(16) float2 sm[];
     float2* s_tw2 = sm + fftk::SMEM_ELEMS;
     float2* s_tw1 = s_tw2 + 512;
@@ -63,14 +65,25 @@ fftfilt_fold_kernel(const FoldIO io, const float2* __restrict__ Hc, const float2
     }
     const long long cl = blockIdx.x / NC, ncl = gridDim.x / NC;
     bool pending = false;         // a relaxed cluster-barrier arrival of the previous block is outstanding
-    for (long long blk = cl; blk < nblocks; blk += ncl) {
+    // RRC_FFTFILT_TRACE (debug): every warp of CTA 1 of cluster 3 stamps clock64 at the phase boundaries of blocks 2..7
+    int it = 0;
+    auto stamp = [&](int i) {
+        if (trace && cl == 3 && c == 1 % NC && it >= 2 && it < 2 + FOLD_TRACE_BLK && (tid & 31) == 0)
+            trace[((size_t)(it - 2) * 16 + (tid >> 5)) * FOLD_NSTAMP + i] = clock64();
+    };
+    for (long long blk = cl; blk < nblocks; blk += ncl, ++it) {
+        stamp(0);
         // The other CTAs of the cluster may still be reading this CTA's u array (previous block); the
         // matching wait sits after this block's loads and DFT32, right before the first shared-memory
         // write, so it is normally already satisfied.
         fftf::phase_a<NC>(tid, c, blk, io, s_tw1, s_gc, s_twc, sm, [&]() {
+            stamp(1);
             if constexpr (NC > 1) { if (pending) asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
+            stamp(2);
         });
+        stamp(3);
         __syncthreads();
+        stamp(4);
         {   // next block's segment -> L2: every CTA of the cluster pulls one quarter (16 warps x 8 KiB)
             const long long nb = blk + ncl;
             const long long seg0 = fftf::seg_start<NC>(nb, io) + (long long)c * fftk::N + (long long)(tid >> 5) * 1024;
@@ -82,8 +95,11 @@ fftfilt_fold_kernel(const FoldIO io, const float2* __restrict__ Hc, const float2
         }
         fftk::phase_mid_b(tid, s_tw2, sm);
         __syncwarp();
+        stamp(5);
         fftf::phase_c_fold(tid, Hp, s_hres, sm);
+        stamp(6);
         __syncthreads();
+        stamp(7);
         if (tid < 64) {                                         // 2048-point inverse: 64 tasks x 32 points, twice
             float2 v[32];
             fftf::inv1_load(tid, sm, v);
@@ -93,8 +109,11 @@ fftfilt_fold_kernel(const FoldIO io, const float2* __restrict__ Hc, const float2
             fftf::inv2_load(tid, sm, v);
             fftf::inv2_compute_store(tid, v, sm + FOLD_U_OFF);
         }
+        stamp(8);
         if constexpr (NC > 1) cg::this_cluster().sync(); else __syncthreads();
+        stamp(9);
         fftf::combine_store<NC>(tid, c, blk, io, uc, twm);
+        stamp(10);
         // The next phase A overwrites the u array other CTAs are still reading: write-after-read only,
         // so a RELAXED arrival is enough (no release fence waiting for the global stores to drain).
         if constexpr (NC > 1) { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); pending = true; }
@@ -130,9 +149,35 @@ int launch_fold(rrc_fftfilt* h, const FoldIO& io, long long nblocks, cudaStream_
     }
     const long long ncl = std::min<long long>(nblocks, h->fold.max_clusters);
     cfg.gridDim = dim3((unsigned)(ncl * NC));
+    static const bool want_trace = getenv("RRC_FFTFILT_TRACE") != nullptr;
+    long long* dtrace = nullptr;
+    const size_t trace_n = (size_t)FOLD_TRACE_BLK * 16 * FOLD_NSTAMP;
+    if (want_trace) { RRC_CUDA(cudaMalloc((void**)&dtrace, trace_n * 8)); RRC_CUDA(cudaMemsetAsync(dtrace, 0, trace_n * 8, st)); }
     RRC_CUDA(cudaLaunchKernelEx(&cfg, kern, io, (const float2*)h->fold.Hc, (const float2*)h->tw1, (const float2*)h->tw2,
-                                (const float2*)h->fold.gc, (const float2*)h->fold.twc, (const float2*)h->fold.twm, nblocks));
+                                (const float2*)h->fold.gc, (const float2*)h->fold.twc, (const float2*)h->fold.twm, nblocks, dtrace));
     count_launch();
+    if (want_trace) {                                           // debug only: synchronous dump of the per-phase cycle table
+        std::vector<long long> tr(trace_n);
+        RRC_CUDA(cudaStreamSynchronize(st));
+        RRC_CUDA(cudaMemcpy(tr.data(), dtrace, trace_n * 8, cudaMemcpyDeviceToHost));
+        cudaFree(dtrace);
+        static const char* names[] = {"A: loads, combine, DFT32, tw", "cluster wait (prev u read)", "A: store", "barrier 1", "B", "C + fold",
+                                      "barrier 2", "inverse 2048 (warps 0-1) / idle", "cluster sync", "combine + store"};
+        static int dumps = 0;
+        if (nblocks > ncl * 8 && dumps++ < 1) {
+            for (int b = 0; b < FOLD_TRACE_BLK; ++b) {
+                long long t0 = tr[(size_t)(b * 16) * FOLD_NSTAMP], tend = 0;
+                for (int w = 0; w < 16; ++w) { t0 = std::min(t0, tr[(size_t)(b * 16 + w) * FOLD_NSTAMP]); tend = std::max(tend, tr[(size_t)(b * 16 + w) * FOLD_NSTAMP + 10]); }
+                fprintf(stderr, "fold trace block iter %d: total %lld cycles\n", b + 2, tend - t0);
+                for (int p = 0; p < 10; ++p) {
+                    std::vector<long long> d;
+                    for (int w = 0; w < 16; ++w) d.push_back(tr[(size_t)(b * 16 + w) * FOLD_NSTAMP + p + 1] - tr[(size_t)(b * 16 + w) * FOLD_NSTAMP + p]);
+                    std::sort(d.begin(), d.end());
+                    fprintf(stderr, "   %-34s min %6lld  med %6lld  max %6lld\n", names[p], d[0], d[8], d[15]);
+                }
+            }
+        }
+    }
     return RRC_OK;
 }
 

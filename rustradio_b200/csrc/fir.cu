@@ -472,6 +472,134 @@ __global__ void __launch_bounds__(FIR_MAX_NT) fir_rt_kernel(const FirArgs a) {
     }
 }
 
+// ---- c32 samples, REAL taps, taps in the UNIFORM datapath (config 3: the rtl_fm channelizer) ----
+// fir_rt_kernel spends 65 % of its issue slots on things that are not FFMA2: tap loads from shared memory
+// (one LDS.128 per two taps), window-shift moves (the chunk loop is a run-time loop), tail chunks and index
+// arithmetic.  Here the filter is a compile-time SHAPE (DCT polyphase branches x QB taps per branch, zero
+// padded) and the taps are a KERNEL PARAMETER: (h, h) pairs in the constant bank, so every FFMA2 takes its
+// tap from a uniform register (SASS: FFMA2 R, R.F32x2, UR.F32x2, R — one LDCU.128 on the uniform pipe per
+// two taps, no vector register, no shared-memory traffic), the two loops are fully unrolled (the sliding
+// window is pure register renaming, every shared-memory offset an immediate) and a thread owns all R = 8
+// outputs of its group: per tap ONE LDS.64 and eight FFMA2.  2080 FFMA2 per thread against ~330 window
+// loads and ~130 uniform loads.  Results are bit-identical to fir_rt_kernel / FFMA (same products, same
+// order: branch by branch, tap by tap).
+// Tile loader for a compile-time segment length S (c32, cp.async): a warp copies whole segments, every offset
+// an immediate, the segment loop a pointer increment — ~1/4 of the instructions of fir_load_tile's generic loop.
+template <int S>
+__device__ __forceinline__ void fir_load_tile_ct(const FirArgs& a, float2* s_tile, long long ch, long long bx, int deci,
+                                                 int NT, int t, int bstride) {
+    constexpr int S1 = S + 1;
+    const long long g0 = bx * bstride * deci;
+    const int L = a.nseg * S;
+    if (a.in_u8 || g0 + L > a.need) {           // u8 input / last tile of a channel: the generic loader
+        fir_load_tile<float2, FIR_R>(a, s_tile, ch, bx, deci, S, NT, t, bstride);
+        return;
+    }
+    const float2* __restrict__ in = reinterpret_cast<const float2*>(a.in) + ch * a.in_stride + g0;
+    const int lane = t & 31, nwarp = NT >> 5;
+    const float2* src = in + (long long)(t >> 5) * S + lane;
+    unsigned dst = (unsigned)__cvta_generic_to_shared(s_tile) + (unsigned)(((t >> 5) * S1 + lane) * 8);
+    for (int sg = t >> 5; sg < a.nseg; sg += nwarp) {
+#pragma unroll
+        for (int e = 0; e < S; e += 32)
+            if (e + 32 <= S || lane < S - e)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + e * 8), "l"(src + e) : "memory");
+        src += (long long)nwarp * S;
+        dst += (unsigned)(nwarp * S1 * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int NTAP>
+struct RtuTaps { float2 hh[NTAP]; };      // hh[p * QB + q] = (h, h), h = taps_rev[q * DCT + p] (0 beyond ntaps)
+
+template <int DCT, int QB, bool DEMOD, int R>
+__global__ void __launch_bounds__(128) fir_rtu_kernel(const FirArgs a, const __grid_constant__ RtuTaps<DCT * QB> taps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int S = R * DCT, S1 = S + 1;
+    const int NT = blockDim.x, tid = threadIdx.x;
+    const int BT = NT * R;
+    const int bstride = DEMOD ? BT - 1 : BT;
+    float2* s_tile = reinterpret_cast<float2*>(smem_raw);
+    const long long ch = blockIdx.y;
+    const long long ob = (long long)blockIdx.x * bstride;
+    fir_load_tile_ct<S>(a, s_tile, ch, blockIdx.x, DCT, NT, tid, bstride);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    u64 acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0ull;
+    const u64* base = reinterpret_cast<const u64*>(s_tile) + tid * S1;
+    // window element U of branch p (sample (r + q) * DCT + p of the thread's span, U = r + q) sits at
+    // p + (U / R) * S1 + (U % R) * DCT: one pad word after every R * DCT samples.
+    // The branch loop is NOT unrolled: one branch (QB taps x R FFMA2 + the window loads, ~4 KB of code) stays in
+    // the instruction cache; fully unrolled over the branches the kernel is 46 KB of straight-line code and
+    // stalls on instruction fetch (ncu: no_instruction 1.2 per issue).  p is warp uniform, so the tap of
+    // (p, q) is still a uniform-register operand (constant bank, uniform index).
+#pragma unroll 1
+    for (int p = 0; p < DCT; ++p) {
+        u64 w[R - 1 + QB];
+        const u64* bp = base + p;
+        const float2* tp = taps.hh + p * QB;
+#pragma unroll
+        for (int u = 0; u < R - 1; ++u) w[u] = bp[(u / R) * S1 + (u % R) * DCT];
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+            const int U = q + R - 1;
+            w[U] = bp[(U / R) * S1 + (U % R) * DCT];
+            const u64 hh = *reinterpret_cast<const u64*>(&tp[q]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) fma2(acc[r], hh, w[r + q]);
+        }
+    }
+
+    if constexpr (!DEMOD) {
+        float2* __restrict__ out = reinterpret_cast<float2*>(a.out) + ch * a.out_stride;
+        const long long gi0 = ob + (long long)tid * R;
+        float2 y[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            y[r] = unpk(acc[r]);
+            if (a.translate) y[r] = apply_translate(a, y[r], gi0 + r);
+        }
+        float2* dst = out + gi0;
+        if (gi0 + R <= a.out_n && (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
+#pragma unroll
+            for (int r = 0; r < R; r += 2)
+                *reinterpret_cast<float4*>(dst + r) = make_float4(y[r].x, y[r].y, y[r + 1].x, y[r + 1].y);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (gi0 + r < a.out_n) dst[r] = y[r];
+        }
+    } else {
+        __syncthreads();                 // everyone is done with the input tile
+        float2* s_out = s_tile;          // reuse: BT + NT entries <= tile size
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float2 y = unpk(acc[r]);
+            if (a.translate) y = apply_translate(a, y, ob + (long long)tid * R + r);
+            s_out[tid * (R + 1) + r] = y;
+        }
+        __syncthreads();
+        float* __restrict__ out = reinterpret_cast<float*>(a.out) + ch * a.out_stride;
+        float2 ya[R], yb[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {                 // R independent demods per thread: ILP for atan2
+            const int o = tid + r * NT;
+            ya[r] = s_out[o + o / R];
+            yb[r] = s_out[(o + 1) + (o + 1) / R];     // o + 1 <= BT - 1 < BT + NT entries
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int o = tid + r * NT;
+            const long long gi = ob + o;
+            if (o < BT - 1 && gi < a.out_n - 1) out[gi] = demod_pair(ya[r], yb[r], a.gain);
+        }
+    }
+}
+
 // Fallback for geometries whose tile does not fit shared memory (very large
 // deci*R or tap tables): one thread per output, taps and inputs through L1/L2.
 template <typename ST, typename TT>
@@ -523,6 +651,10 @@ struct rrc_fir {
     int qpad = 0, nchunks = 0, nt = 0, R = FIR_R, nbuf = 1;
     int groups = 0, split = 1;   // nt = groups * split threads; split = 2: two threads per group of R outputs (fir_rt_kernel)
     bool rt = false;             // c32 samples + real taps: packed-FP32 kernel (fir_rt_kernel)
+    // uniform-tap unrolled kernel (fir_rtu_kernel): shape (deci, QB taps per branch), CTA size, smem, (h, h) table
+    int rtu_qb = 0, rtu_nt = 0, rtu_r = 8;   // rtu_r: outputs per thread (8 or 16)
+    size_t rtu_smem = 0;
+    std::vector<float2> rtu_hh;
     size_t smem = 0;
     bool use_poly = false;
     bool translate = false;
@@ -765,6 +897,30 @@ int upload_taps(rrc_fir* h) {
     // two threads per output group when the staged tile per group is large (R*deci*8 bytes)
     h->split = (h->rt && D >= 4) ? 2 : 1;
     if (const char* e = getenv("RRC_FIR_SPLIT")) { int v = atoi(e); if (h->rt && (v == 1 || (v == 2 && D >= 2))) h->split = v; }
+    // Uniform-tap unrolled kernel (fir_rtu_kernel) for the instantiated shapes: c32 samples, real taps,
+    // decimation 10 or 5 with at most 26 taps per polyphase branch (config 3 is 255 taps / 10 -> 26).
+    h->rtu_qb = 0;
+    if (h->cplx && h->real_taps && !(h->flags & RRC_FIR_FORCE_GENERIC) && (D == 10 || D == 5) && Q <= 26) {
+        bool on = true;
+        if (const char* e = getenv("RRC_FIR_RTU")) on = atoi(e) != 0;
+        if (on) {
+            const int QB = Q <= 13 ? 13 : 26;
+            h->rtu_qb = QB;
+            h->rtu_hh.assign((size_t)D * QB, make_float2(0.f, 0.f));
+            for (size_t j = 0; j < T; ++j) {
+                float v; tap_at(j, &v);
+                h->rtu_hh[(j % D) * QB + j / D] = make_float2(v, v);
+            }
+            h->rtu_r = 8;
+            if (const char* e = getenv("RRC_FIR_RTU_R")) { int v = atoi(e); if (v == 8 || v == 16) h->rtu_r = v; }
+            h->rtu_nt = h->rtu_r == 16 ? 32 : 64;
+            if (const char* e = getenv("RRC_FIR_RTU_NT")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128) h->rtu_nt = v; }
+            const size_t S1u = (size_t)h->rtu_r * D + 1;
+            const size_t extra = ((size_t)QB + h->rtu_r - 2) / h->rtu_r;         // segments a thread's window reaches past its own
+            h->rtu_smem = (((size_t)(h->rtu_nt + extra) * S1u + 1) & ~(size_t)1) * sizeof(float2);
+            if (h->rtu_smem > (size_t)max_smem_optin(h->device)) h->rtu_qb = 0;
+        }
+    }
     if (!(h->flags & RRC_FIR_FORCE_GENERIC) && D <= (1u << 20)) {
         const size_t S1 = (size_t)h->R * D + 1;
         const size_t tap_bytes = ((size_t)D * h->qpad * (h->rt ? sizeof(float2) : tap_elem(h)) + 15) & ~(size_t)15;
@@ -828,6 +984,27 @@ int launch_rt_d(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) 
         return h->split == 2 ? launch_rt_k<DCT, DEMOD, FIR_R, 2>(h, a, grid, st) : launch_rt_k<DCT, DEMOD, FIR_R, 1>(h, a, grid, st);
     }
 }
+template <int DCT, int QB, bool DEMOD, int R>
+int launch_rtu_r(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
+    auto k = fir_rtu_kernel<DCT, QB, DEMOD, R>;
+    RtuTaps<DCT * QB> tp;
+    memcpy(tp.hh, h->rtu_hh.data(), sizeof(tp.hh));
+    RRC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->rtu_smem));
+    k<<<grid, h->rtu_nt, h->rtu_smem, st>>>(a, tp);
+    RRC_CHECK_LAUNCH();
+    count_launch();
+    return RRC_OK;
+}
+template <int DCT, int QB, bool DEMOD>
+int launch_rtu_k(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
+    return h->rtu_r == 16 ? launch_rtu_r<DCT, QB, DEMOD, 16>(h, a, grid, st) : launch_rtu_r<DCT, QB, DEMOD, 8>(h, a, grid, st);
+}
+template <bool DEMOD>
+int launch_rtu(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
+    if (h->deci == 10) return h->rtu_qb == 13 ? launch_rtu_k<10, 13, DEMOD>(h, a, grid, st) : launch_rtu_k<10, 26, DEMOD>(h, a, grid, st);
+    return h->rtu_qb == 13 ? launch_rtu_k<5, 13, DEMOD>(h, a, grid, st) : launch_rtu_k<5, 26, DEMOD>(h, a, grid, st);
+}
+
 template <bool DEMOD>
 int launch_rt(const rrc_fir* h, const FirArgs& a, dim3 grid, cudaStream_t st) {
     switch (h->deci) {
@@ -942,6 +1119,18 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         t.total_tiles = t.tiles_x * (long long)nchan;
         if (t.total_tiles > 0x7fffffffll) return fail(RRC_ERR_INVALID, "fir: %lld tiles in one launch (limit 2^31 - 1)", t.total_tiles);
         RRC_TRY(fir_tc_launch(FirTcGeom{h->device, h->tc_ntile, h->tc_nld, h->tc_KS, h->tc_smem, (int)h->deci}, t, demod, st));
+    } else if (h->rtu_qb) {
+        const size_t bt = (size_t)h->rtu_nt * h->rtu_r;
+        const size_t per = demod ? bt - 1 : bt;
+        const size_t work = demod ? (out_n > 1 ? out_n - 1 : 0) : out_n;
+        if (work == 0) return RRC_OK;
+        a.S = h->rtu_r * (int)h->deci;
+        a.nseg = h->rtu_nt + (h->rtu_qb + h->rtu_r - 2) / h->rtu_r;
+        a.tiles_x = (long long)((work + per - 1) / per);
+        a.total_tiles = a.tiles_x * (long long)nchan;
+        a.nbuf = 1;
+        dim3 grid((unsigned)a.tiles_x, (unsigned)nchan);
+        RRC_TRY(demod ? launch_rtu<true>(h, a, grid, st) : launch_rtu<false>(h, a, grid, st));
     } else if (h->use_poly) {
         a.taps = h->taps_poly;
         const size_t bt = (size_t)h->groups * h->R;
