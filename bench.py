@@ -707,11 +707,12 @@ def roofline_of(ctx, W, ms_per_step):
                 "kernel": KERNEL_NAMES[op], "duration_ms": ms_per_step,
                 "note": "duration = CUDA-event time of the whole step on the launching stream / steps; the step is this one kernel"
                         + (" plus a <3 us history-update kernel" if op == "fftfilt" else "")}
+    if op in ("fir", "fir_demod"):
+        roofline["kernel"] = f.kernel_name + (" + fused QuadratureDemod epilogue" if op == "fir_demod" else "")
     if op in ("fir", "fir_demod") and f.uses_tensor_cores:
         # Declared: the real-tap c32 FIR runs as a block-scaled fp16x3 Toeplitz product on the tensor cores (fir_tc.cuh).
         walk = cfg["deci"] in (1, 2, 4) and 7 * cfg["deci"] + cfg["ntaps"] <= 320
-        roofline["kernel"] = (("fir_tcf_kernel<KS,D>" if cfg["dtype"] == "f32" else "fir_tc1_kernel<KS,DEMOD,U8,D>") if walk else "fir_tc_kernel") + \
-            " (block-scaled fp16x3 Toeplitz product on the tensor cores, mma.m16n8k16 + ldmatrix" + (", fused demod epilogue)" if op == "fir_demod" else ")")
+        roofline["kernel"] += " [block-scaled fp16x3 Toeplitz product, mma.m16n8k16 + ldmatrix]"
         ks = (7 * cfg["deci"] + cfg["ntaps"] + 15) // 16             # k-steps of 16 at 8 outputs per block-row (lower bound)
         nout_fir = W.n_out + (getattr(W, "nchan", 0) if op == "fir_demod" else 0)
         mmas = 3 * ks * nout_fir / 64                                 # three m16n8k16 per k-step per 64 complex outputs

@@ -133,6 +133,23 @@ int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes);
  * against the f64 convolution, next to 1e-7..3e-7 for the sequential f32 loop (bar 1e-5).  Declared like the
  * real-tap fast path; RRC_FIR_NO_TENSOR (flag) or RRC_FIR_TENSOR=0 (environment) disables it. */
 int rrc_fir_uses_tensor_cores(const rrc_fir_t* h, int* yes);
+/* Store epilogues: the sample-wise neighbour that follows a Complex filter in the graph is
+ * applied by the filter's own output store instead of costing a block and a full HBM round trip:
+ *   RRC_EPI_MULTIPLY_CONST  y * (re + i im)   MultiplyConst<Complex>   src/multiply_const.rs:16-23
+ *   RRC_EPI_ADD_CONST       y + (re + i im)   AddConst<Complex>        src/add_const.rs:36-44
+ *   RRC_EPI_MAG2            |y|^2             ComplexToMag2            src/complex_to_mag2.rs:17-20  (out becomes f32)
+ * Same separately rounded operations as the stand-alone kernels: fused == the two blocks back to back, bit for
+ * bit.  (QuadratureDemod -> MultiplyConst<Float> is the `gain` of rrc_fir_c32_demod_run_batch.)  A FIR handle
+ * with an epilogue runs on the FP32 kernels (rrc_fir_uses_tensor_cores reports 0). */
+#define RRC_EPI_NONE           0
+#define RRC_EPI_MULTIPLY_CONST 1
+#define RRC_EPI_ADD_CONST      2
+#define RRC_EPI_MAG2           3
+int rrc_fir_set_epilogue(rrc_fir_t* h, int kind, float re, float im);
+/* Which kernel the planner chose for this handle (reports / INTEGRATION.md): e.g. "fir_tc1_kernel<KS=5,D=1> ...",
+ * "fir_rtu_kernel<D=10,QB=26,R=8> ..." (real-tap decimating filters with deci 5 or 10 and <= 26 taps per polyphase
+ * branch: taps travel as kernel parameters and reach FFMA2 as uniform-register operands), "fir_rt_kernel<...>". */
+int rrc_fir_kernel_name(const rrc_fir_t* h, char* buf, size_t buflen);
 /* Restart the translate rotator's output counter (new stream). */
 int rrc_fir_reset(rrc_fir_t* h);
 
@@ -196,6 +213,9 @@ int rrc_fftfilt_set_history(rrc_fftfilt_t* h, const float* hist_dev_c32, size_t 
  * (one-shot; e.g. the IPC- or peer-mapped tail of the left neighbour's input buffer: only the kernel's first
  * block touches it, over NVLink).  The pointer must stay valid until that run has completed. */
 int rrc_fftfilt_set_history_ptr(rrc_fftfilt_t* h, const float* hist_dev_c32, size_t n_samples);
+/* Store epilogue of rrc_fftfilt_run / decim_run / *_run_host (RRC_EPI_*, see rrc_fir_set_epilogue): Complex filters;
+ * filters split into tap partitions (ntaps > 12289) take it only through the fused decimate-by-8 kernel. */
+int rrc_fftfilt_set_epilogue(rrc_fftfilt_t* h, int kind, float re, float im);
 /* calc_fft_size and nsamples exactly as the reference (src/fft_filter.rs:36-42,262-263). */
 int rrc_fftfilt_ref_fft_size(size_t ntaps, size_t* fft_size, size_t* nsamples);
 /* Device-side geometry actually used (FFT size, valid outputs per block). */

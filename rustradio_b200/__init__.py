@@ -15,4 +15,5 @@ from .api import (  # noqa: F401
     Hilbert, make_window, hilbert_taps, multiply_const, add_const, complex_to_mag2, tee, IqBalance,
     iq_balance_alpha_from_tau, WINDOW_HAMMING, WINDOW_BLACKMAN, WINDOW_BLACKMAN_HARRIS, WINDOW_HAMMING_PARM,
     RRC_FIR_NO_REAL_TAP_FASTPATH, RRC_FIR_FORCE_GENERIC, RRC_FIR_NO_TENSOR,
+    EPI_NONE, EPI_MULTIPLY_CONST, EPI_ADD_CONST, EPI_MAG2,
 )

@@ -14,6 +14,7 @@ RRC_OK = 0
 RRC_FIR_NO_REAL_TAP_FASTPATH = 1
 RRC_FIR_FORCE_GENERIC = 2
 RRC_FIR_NO_TENSOR = 4
+EPI_NONE, EPI_MULTIPLY_CONST, EPI_ADD_CONST, EPI_MAG2 = 0, 1, 2, 3
 
 
 class RrcError(RuntimeError):
@@ -80,6 +81,9 @@ _SIGS = {
     "rrc_fir_uses_real_taps": [_vp, _P(_i)],
     "rrc_fir_uses_tensor_cores": [_vp, _P(_i)],
     "rrc_fir_reset": [_vp],
+    "rrc_fir_kernel_name": [_vp, C.c_char_p, _sz],
+    "rrc_fir_set_epilogue": [_vp, _i, _f, _f],
+    "rrc_fftfilt_set_epilogue": [_vp, _i, _f, _f],
     "rrc_fir_plan": [_sz, _sz, _sz, _sz, _P(_sz), _P(_sz), _P(_sz), _P(_sz), _P(_i)],
     "rrc_fir_run": [_vp, _vp, _sz, _vp, _sz, _vp],
     "rrc_fir_run_batch": [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _sz, _vp],
@@ -368,6 +372,11 @@ class Fir:
         _ck(fn(device, t.ctypes.data if len(t) else None, len(t), deci, flags, C.byref(h)))
         self.h = h.value
 
+    def set_epilogue(self, kind: int, val: complex = 0):
+        """Fuse the following MultiplyConst / AddConst / ComplexToMag2 into the output store (EPI_*)."""
+        v = complex(val)
+        _ck(lib().rrc_fir_set_epilogue(self.h, kind, v.real, v.imag))
+
     def set_translate(self, samp_rate: float, freq: float):
         _ck(lib().rrc_fir_set_translate(self.h, samp_rate, freq))
 
@@ -391,6 +400,12 @@ class Fir:
         y = _i(0)
         _ck(lib().rrc_fir_uses_tensor_cores(self.h, C.byref(y)))
         return bool(y.value)
+
+    @property
+    def kernel_name(self) -> str:
+        buf = C.create_string_buffer(200)
+        _ck(lib().rrc_fir_kernel_name(self.h, buf, 200))
+        return buf.value.decode()
 
     def out_count(self, n_in: int) -> int:
         return 0 if n_in < self.ntaps + self.deci - 1 else (n_in - self.ntaps + 1) // self.deci
@@ -488,6 +503,11 @@ class FftFilt:
 
     def set_history(self, d_hist, n: int, stream: int = 0):
         _ck(lib().rrc_fftfilt_set_history(self.h, _ptr(d_hist), n, stream))
+
+    def set_epilogue(self, kind: int, val: complex = 0):
+        """Fuse the following MultiplyConst / AddConst / ComplexToMag2 into the output store (EPI_*)."""
+        v = complex(val)
+        _ck(lib().rrc_fftfilt_set_epilogue(self.h, kind, v.real, v.imag))
 
     def set_history_ptr(self, d_hist, n: int):
         """One-shot: the next run reads its left halo through this (possibly peer-mapped) device pointer."""

@@ -486,10 +486,13 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
     io.skip = (long long)skip;
     io.in_u8 = h->in_u8;
     io.real = h->real;
+    io.epi = h->epi;
     const bool decim = !(deci == 1 && skip == 0);
     // kernels that update the carried history themselves (one launch per run): the 512-thread LDG / TMA kernels
     const bool fused_hist = h->T1 > 0 && (h->real || h->variant == 32 || h->variant == 35 || h->variant == 36 || h->variant == 37 || h->variant == 38 || h->variant == 39);
     long long shift = 0;
+    if (h->epi.kind != RRC_EPI_NONE && h->part_T1.size() > 1)
+        return fail(RRC_ERR_UNSUPPORTED, "store epilogues need a single tap partition (ntaps <= 12289) on this path");
     for (size_t p = 0; p < h->part_T1.size(); ++p) {
         io.T1 = h->part_T1[p];
         io.V = fftk::N - io.T1;
@@ -680,6 +683,14 @@ int rrc_fftfilt_set_history_ptr(rrc_fftfilt_t* h, const float* hist, size_t n) {
     return RRC_OK;
 }
 
+int rrc_fftfilt_set_epilogue(rrc_fftfilt_t* h, int kind, float re, float im) {
+    if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
+    if (kind < RRC_EPI_NONE || kind > RRC_EPI_MAG2) return fail(RRC_ERR_INVALID, "unknown epilogue %d", kind);
+    if (kind != RRC_EPI_NONE && h->real) return fail(RRC_ERR_INVALID, "store epilogues exist for Complex filters only");
+    h->epi.kind = kind; h->epi.re = re; h->epi.im = im;
+    return RRC_OK;
+}
+
 int rrc_fftfilt_set_input_u8iq(rrc_fftfilt_t* h, int on) {
     if (!h) return fail(RRC_ERR_INVALID, "fftfilt handle is NULL");
     if (on && h->real) return fail(RRC_ERR_INVALID, "u8 I/Q input needs a Complex filter");
@@ -750,7 +761,7 @@ int rrc_fftfilt_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, fl
     RRC_TRY(pipe_wait_state(h));
     const size_t chunk = PIPE_CHUNK_SAMPLES;
     const size_t esz = h->real ? sizeof(float) : h->in_u8 ? 2 : sizeof(float2);   // input bytes per sample
-    const size_t osz = h->real ? sizeof(float) : sizeof(float2);
+    const size_t osz = (h->real || h->epi.kind == RRC_EPI_MAG2) ? sizeof(float) : sizeof(float2);
     RRC_TRY(h->pipe.reserve(std::min(chunk, total) * esz, std::min(chunk, total) * osz));
     int i = 0;
     for (size_t off = 0; off < total; off += chunk, ++i) {
@@ -780,7 +791,8 @@ int rrc_fftfilt_decim_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_
     RRC_TRY(pipe_wait_state(h));
     const size_t chunk = PIPE_CHUNK_SAMPLES;
     const size_t esz = h->in_u8 ? 2 : sizeof(float2);
-    RRC_TRY(h->pipe.reserve(std::min(chunk, total) * esz, (std::min(chunk, total) / deci + 2) * sizeof(float2)));
+    const size_t osz = h->epi.kind == RRC_EPI_MAG2 ? sizeof(float) : sizeof(float2);
+    RRC_TRY(h->pipe.reserve(std::min(chunk, total) * esz, (std::min(chunk, total) / deci + 2) * osz));
     int i = 0;
     size_t produced = 0;
     for (size_t off = 0; off < total; off += chunk, ++i) {
@@ -790,7 +802,7 @@ int rrc_fftfilt_decim_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_
         RRC_TRY(h->pipe.stage_in(i, reinterpret_cast<const char*>(in_host) + off * esz, n * esz));
         RRC_CUDA(cudaSetDevice(h->device));
         RRC_TRY(rrc_fftfilt_decim_run(h, (const float*)h->pipe.d_in[i & 1], n, deci, skip, (float*)h->pipe.d_out[i & 1], &cnt, h->pipe.s_comp));
-        RRC_TRY(h->pipe.drain_out(i, out_host + 2 * produced, cnt * sizeof(float2)));
+        RRC_TRY(h->pipe.drain_out(i, reinterpret_cast<char*>(out_host) + produced * osz, cnt * osz));
         produced += cnt;
     }
     if (produced != total_out) return fail(RRC_ERR_STATE, "decim_run_host produced %zu of %zu", produced, total_out);

@@ -26,6 +26,7 @@
 // per block: A -> MID and MID -> A'.
 #pragma once
 #include "fft_regs.cuh"
+#include "epilogue.cuh"
 
 namespace rrc { namespace fftk {
 
@@ -59,6 +60,9 @@ struct BlockIO {
     // hist ++ in) into this buffer — done by the grid's last CTA before its first block, so a run() is ONE
     // launch (matters for small work() windows and for time-segment shards, where a step is ~0.25 ms).
     float2* hist_next = nullptr;
+    // Store epilogue (epilogue.cuh): MultiplyConst / AddConst / ComplexToMag2 fused into the output store
+    // (complex streams, single tap partition).  MAG2 makes `out` an f32 array.
+    rrc::Epi epi;
 };
 
 // hist_next[i] = x[n_in - T1_total + i] over the concatenation (hist ++ in), i < T1_total.
@@ -451,6 +455,20 @@ RRC_HD void store_outputs(int tid, long long blk, const BlockIO& io, const float
                 const long long o = o0 + tid + 512 * n1;
                 if (o < io.n_out) q[512 * n1] = ACCUM ? q[512 * n1] + v[n1].x : v[n1].x;
                 if (o + io.V < io.n_out) q[512 * n1 + io.V] = ACCUM ? q[512 * n1 + io.V] + v[n1].y : v[n1].y;
+            }
+        }
+        return;
+    }
+    if (io.epi.kind != RRC_EPI_NONE) {                          // fused neighbour (never with ACCUM: single partition only)
+        const long long D = DECIM ? io.deci : 1;
+        const long long skip = DECIM ? io.skip : 0;
+        float* qf = reinterpret_cast<float*>(io.out);
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const long long r = o0 + tid + 512 * n1 - skip;
+            if (n1 >= first && r >= 0 && r % D == 0 && r / D < io.n_out) {
+                if (io.epi.kind == RRC_EPI_MAG2) qf[r / D] = rrc::epi_mag2(v[n1]);
+                else io.out[r / D] = rrc::epi_c32(v[n1], io.epi);
             }
         }
         return;

@@ -226,6 +226,7 @@ int fold_launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_
     io.r = (int)(skip % fftf::FOLD_D);
     io.jbias = (long long)(skip / fftf::FOLD_D);
     io.in_u8 = h->in_u8;
+    io.epi = h->epi;
     io.hist_next = h->T1 > 0 ? h->hist[h->cur ^ 1] : nullptr;
     if ((long long)n <= io.r) return RRC_ERR_UNSUPPORTED;      // nothing to launch: the caller updates the history
     const long long nblocks = ((long long)n - io.r + io.V - 1) / io.V;

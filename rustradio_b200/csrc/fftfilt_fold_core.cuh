@@ -46,7 +46,12 @@ struct FoldIO {
     long long jbias;         // (skip - r) / 8
     int in_u8 = 0;           // 1: `in` is u8 I/Q pairs (RtlSdrDecode fused into the load)
     float2* hist_next = nullptr;   // non-NULL: the grid's last CTA writes the next call's history here (one launch per run)
+    rrc::Epi epi;                  // store epilogue (epilogue.cuh); MAG2 makes `out` an f32 array
 };
+RRC_HD void fold_store(const FoldIO& io, long long j, float2 z) {
+    if (io.epi.kind == RRC_EPI_MAG2) reinterpret_cast<float*>(io.out)[j] = rrc::epi_mag2(z);
+    else io.out[j] = rrc::epi_c32(z, io.epi);
+}
 
 RRC_HD void update_history(const FoldIO& io, int tid, int nthreads) {
     for (int i = tid; i < io.T1_total; i += nthreads) {
@@ -255,7 +260,7 @@ RRC_HD void combine_store(int tid, int d, long long blk, const FoldIO& io, const
         const int m2 = d * PER_CTA + tid + NT * i;
         if constexpr (NC == 1) {
             const long long j = jb + m2;
-            if (m2 >= m_first && j >= 0 && j < io.n_out) io.out[j] = uc[0][m2];
+            if (m2 >= m_first && j >= 0 && j < io.n_out) fold_store(io, j, uc[0][m2]);
         } else {
             const float2 g = twm[m2];
             const float2 g2 = csqr(g);
@@ -273,7 +278,7 @@ RRC_HD void combine_store(int tid, int d, long long blk, const FoldIO& io, const
             for (int qq = 0; qq < 4; ++qq) {
                 const int m = m2 + LU * qq;
                 const long long j = jb + m;
-                if (m >= m_first && j >= 0 && j < io.n_out) io.out[j] = z[qq];
+                if (m >= m_first && j >= 0 && j < io.n_out) fold_store(io, j, z[qq]);
             }
         }
     }

@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "pipeline.cuh"
+#include "epilogue.cuh"
 
 // Tables of the decimate-by-8 fold kernel (fftfilt_fold_core.cuh), built lazily on first use.
 struct rrc_fold_tables {
@@ -34,6 +35,7 @@ struct rrc_fftfilt {
     float2* tw3_16 = nullptr;
     int real = 0;                     // real stream + real taps (rrc_fftfilt_f32_create): f32 in / out / history
     int in_u8 = 0;                    // 1: run() inputs are u8 I/Q pairs (rrc_fftfilt_set_input_u8iq)
+    rrc::Epi epi;                     // fused store epilogue (rrc_fftfilt_set_epilogue)
     // kernel variant (RRC_FFTFILT_VARIANT): 37 = PACKED FP32 lanes + TMA-staged input (fftfilt_pk.cuh),
     // 36 = 512 threads x 32 points with TMA-staged input (default),
     // 32 = the same with LDG input + L2 prefetch, 16 = 1024 threads x 16 points, 33/34/35 = experiments

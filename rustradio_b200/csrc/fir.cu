@@ -34,6 +34,7 @@
 
 #include "common.cuh"
 #include "fir_common.cuh"
+#include "epilogue.cuh"
 #include "fir_tc.hpp"
 #include "pipeline.cuh"
 
@@ -56,7 +57,24 @@ struct FirArgs {
     double ratio;                 // freq / samp_rate
     unsigned long long out_base;  // absolute index of out[0] (translate rotator)
     int in_u8;                    // 1: `in` is u8 I/Q pairs, decoded while the tile is staged (c32 filters only)
+    Epi epi;                      // store epilogue of the non-demod c32 paths (epilogue.cuh); MAG2 makes `out` an f32 array
 };
+
+// R consecutive c32 outputs y[0..R) of one thread at output index gi0 of channel `ch`, through the epilogue.
+template <int R>
+__device__ __forceinline__ void fir_store_epi(const FirArgs& a, long long ch, long long gi0, const float2 (&y)[R]) {
+    if (a.epi.kind == RRC_EPI_MAG2) {
+        float* dst = reinterpret_cast<float*>(a.out) + ch * a.out_stride + gi0;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (gi0 + r < a.out_n) dst[r] = epi_mag2(y[r]);
+    } else {
+        float2* dst = reinterpret_cast<float2*>(a.out) + ch * a.out_stride + gi0;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (gi0 + r < a.out_n) dst[r] = epi_c32(y[r], a.epi);
+    }
+}
 
 __device__ __forceinline__ void mac(float2& acc, float2 h, float2 x) {
     acc.x = fmaf(h.x, x.x, acc.x);
@@ -255,6 +273,9 @@ __global__ void __launch_bounds__(FIR_MAX_NT) fir_poly_kernel(const FirArgs a) {
 #pragma unroll
             for (int r = 0; r < R; ++r) acc[r] = apply_translate(a, acc[r], gi0 + r);
         }
+        if constexpr (sizeof(ST) == 8) {
+            if (a.epi.kind != RRC_EPI_NONE) { fir_store_epi<R>(a, ch, gi0, acc); return; }
+        }
         ST* dst = out + gi0;
         if (gi0 + R <= a.out_n && (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
             constexpr int VE = 16 / (int)sizeof(ST);
@@ -435,6 +456,7 @@ __global__ void __launch_bounds__(FIR_MAX_NT) fir_rt_kernel(const FirArgs a) {
             y[r] = unpk(SPLIT == 2 && s ? acc[(RS + r) % R] : acc[r]);
             if (a.translate) y[r] = apply_translate(a, y[r], gi0 + r);
         }
+        if (a.epi.kind != RRC_EPI_NONE) { fir_store_epi<RS>(a, ch, gi0, y); return; }
         float2* dst = out + gi0;
         if (gi0 + RS <= a.out_n && (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
 #pragma unroll
@@ -563,6 +585,7 @@ __global__ void __launch_bounds__(128) fir_rtu_kernel(const FirArgs a, const __g
             y[r] = unpk(acc[r]);
             if (a.translate) y[r] = apply_translate(a, y[r], gi0 + r);
         }
+        if (a.epi.kind != RRC_EPI_NONE) { fir_store_epi<R>(a, ch, gi0, y); return; }
         float2* dst = out + gi0;
         if (gi0 + R <= a.out_n && (reinterpret_cast<unsigned long long>(dst) & 15ull) == 0) {
 #pragma unroll
@@ -622,6 +645,10 @@ __global__ void fir_generic_kernel(const FirArgs a) {
             for (int j = 0; j < a.ntaps; ++j) mac(acc, taps[j], x[j]);
         }
         if (a.translate) acc = apply_translate(a, acc, i);
+        if constexpr (sizeof(ST) == 8) {
+            if (a.epi.kind == RRC_EPI_MAG2) { (reinterpret_cast<float*>(a.out) + (long long)blockIdx.y * a.out_stride)[i] = epi_mag2(acc); continue; }
+            acc = epi_c32(acc, a.epi);
+        }
         out[i] = acc;
     }
 }
@@ -650,6 +677,7 @@ struct rrc_fir {
     void* taps_rev = nullptr;
     int qpad = 0, nchunks = 0, nt = 0, R = FIR_R, nbuf = 1;
     int groups = 0, split = 1;   // nt = groups * split threads; split = 2: two threads per group of R outputs (fir_rt_kernel)
+    Epi epi;                     // fused store epilogue (rrc_fir_set_epilogue); set => FP32 kernels only
     bool rt = false;             // c32 samples + real taps: packed-FP32 kernel (fir_rt_kernel)
     // uniform-tap unrolled kernel (fir_rtu_kernel): shape (deci, QB taps per branch), CTA size, smem, (h, h) table
     int rtu_qb = 0, rtu_nt = 0, rtu_r = 8;   // rtu_r: outputs per thread (8 or 16)
@@ -1055,9 +1083,11 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
     a.ratio = h->ratio;
     a.out_base = h->out_counter;
     a.in_u8 = h->in_u8;
+    a.epi = h->epi;
+    if (h->epi.kind != RRC_EPI_NONE && demod) return fail(RRC_ERR_INVALID, "a store epilogue cannot be combined with the fused demod (its gain is the MultiplyConst)");
     if (h->in_u8 && (reinterpret_cast<uintptr_t>(in) & 1)) return fail(RRC_ERR_INVALID, "u8 I/Q input must be 2-byte aligned");
 
-    const bool use_tc = h->tc && (h->tc_cplx || !h->translate);
+    const bool use_tc = h->tc && (h->tc_cplx || !h->translate) && h->epi.kind == RRC_EPI_NONE;
     if (use_tc && h->tc_cplx) {
         const size_t work = demod ? out_n - 1 : out_n;
         if (work == 0) return RRC_OK;
@@ -1259,7 +1289,29 @@ int rrc_fir_uses_real_taps(const rrc_fir_t* h, int* yes) {
 }
 int rrc_fir_uses_tensor_cores(const rrc_fir_t* h, int* yes) {
     if (!h || !yes) return fail(RRC_ERR_INVALID, "null argument");
-    *yes = (h->tc && (h->tc_cplx || !h->translate)) ? 1 : 0;
+    *yes = (h->tc && (h->tc_cplx || !h->translate) && h->epi.kind == RRC_EPI_NONE) ? 1 : 0;
+    return RRC_OK;
+}
+int rrc_fir_set_epilogue(rrc_fir_t* h, int kind, float re, float im) {
+    if (!h) return fail(RRC_ERR_INVALID, "fir handle is NULL");
+    if (kind < RRC_EPI_NONE || kind > RRC_EPI_MAG2) return fail(RRC_ERR_INVALID, "unknown epilogue %d", kind);
+    if (kind != RRC_EPI_NONE && !h->cplx) return fail(RRC_ERR_INVALID, "store epilogues exist for Complex filters only");
+    h->epi.kind = kind; h->epi.re = re; h->epi.im = im;
+    return RRC_OK;
+}
+int rrc_fir_kernel_name(const rrc_fir_t* h, char* buf, size_t buflen) {
+    if (!h || !buf || !buflen) return fail(RRC_ERR_INVALID, "null argument");
+    const bool use_tc = h->tc && (h->tc_cplx || !h->translate) && h->epi.kind == RRC_EPI_NONE;
+    char tmp[160];
+    if (use_tc && h->tc_cplx) snprintf(tmp, sizeof tmp, "fir_tcc_kernel<KS=%d,D=%zu> (tensor cores, complex taps, fp16x3)", h->tc_KS, h->deci);
+    else if (use_tc && !h->cplx) snprintf(tmp, sizeof tmp, "fir_tcf_kernel<KS=%d,D=%zu> (tensor cores, f32 stream, fp16x3)", h->tc_KS, h->deci);
+    else if (use_tc && h->tc1) snprintf(tmp, sizeof tmp, "fir_tc1_kernel<KS=%d,D=%zu> (tensor cores, real taps, fp16x3)", h->tc_KS, h->deci);
+    else if (use_tc) snprintf(tmp, sizeof tmp, "fir_tc_kernel<NTILE=%d,NLD=%d> (tensor cores, real taps, fp16x3)", h->tc_ntile, h->tc_nld);
+    else if (h->rtu_qb) snprintf(tmp, sizeof tmp, "fir_rtu_kernel<D=%zu,QB=%d,R=%d> (FFMA2, taps as uniform-register operands from the kernel parameters)", h->deci, h->rtu_qb, h->rtu_r);
+    else if (h->use_poly && h->rt) snprintf(tmp, sizeof tmp, "fir_rt_kernel<D=%zu,R=%d,SPLIT=%d> (FFMA2)", h->deci, h->R, h->split);
+    else if (h->use_poly) snprintf(tmp, sizeof tmp, "fir_poly_kernel<D=%zu,R=%d> (FP32 %s taps)", h->deci, h->R, h->real_taps ? "real" : "complex");
+    else snprintf(tmp, sizeof tmp, "fir_generic_kernel");
+    snprintf(buf, buflen, "%s", tmp);
     return RRC_OK;
 }
 int rrc_fir_set_input_u8iq(rrc_fir_t* h, int on) {
@@ -1315,14 +1367,15 @@ int rrc_fir_run_host(rrc_fir_t* h, const void* in_host, size_t n_in, void* out_h
     RRC_TRY(h->pipe.init(h->device));
     const size_t chunk_out = std::max<size_t>(1, PIPE_CHUNK_SAMPLES / D);
     const size_t max_out = std::min(chunk_out, total);
-    RRC_TRY(h->pipe.reserve(((max_out - 1) * D + T) * ies, max_out * es));
+    const size_t oes = h->epi.kind == RRC_EPI_MAG2 ? sizeof(float) : es;   // ComplexToMag2 epilogue: f32 out
+    RRC_TRY(h->pipe.reserve(((max_out - 1) * D + T) * ies, max_out * oes));
     int i = 0;
     for (size_t o = 0; o < total; o += chunk_out, ++i) {
         const size_t no = std::min(chunk_out, total - o);
         const size_t need = (no - 1) * D + T;                              // halo = ntaps-1 re-copied per chunk
         RRC_TRY(h->pipe.stage_in(i, (const char*)in_host + o * D * ies, need * ies));
         RRC_TRY(run_impl(h, h->pipe.d_in[i & 1], 0, need, h->pipe.d_out[i & 1], 0, no, 1, false, 0.f, h->pipe.s_comp));
-        RRC_TRY(h->pipe.drain_out(i, (char*)out_host + o * es, no * es));
+        RRC_TRY(h->pipe.drain_out(i, (char*)out_host + o * oes, no * oes));
     }
     return h->pipe.finish();
 }

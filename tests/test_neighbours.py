@@ -386,3 +386,73 @@ def test_graph_hilbert_chain(R):
     assert len(got) == n - 1
     y = O.Hilbert(65).work(x, f64=True)
     assert O.max_angle_err(got[200:], np.angle(y[201:] * np.conj(y[200:-1]))) <= 1e-4
+
+
+# ------------------------------------------------ neighbours as store epilogues ---
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(64, 1), (255, 10), (130, 5), (33, 4), (5, 1), (255, 3)])
+def test_fir_store_epilogues_equal_the_unfused_chain(R, shape):
+    """FirFilter -> MultiplyConst / AddConst / ComplexToMag2 fused into the filter's store equals
+    the filter followed by the stand-alone block BIT FOR BIT (same FP32 kernel, same separately rounded ops);
+    covers the uniform-tap kernel (255/10, 130/5), the packed kernel, the FP32 poly kernel and complex taps."""
+    ntaps, deci = shape
+    x = O.synth_c32(71, 0, 120_000)
+    for cplx_taps in (False, True):
+        taps = O.low_pass_n(1.0, 0.08, ntaps).astype(np.complex64) * ((1 - 0.4j) if cplx_taps else 1)
+        base = R.Fir(taps, deci=deci, flags=R.RRC_FIR_NO_TENSOR).filter(x)          # the FP32 kernels, unfused
+        for kind, val, ref in ((R.EPI_MULTIPLY_CONST, 0.3 - 1.7j, lambda y: R.multiply_const(y, 0.3 - 1.7j)),
+                               (R.EPI_ADD_CONST, -0.25 + 2j, lambda y: R.add_const(y, -0.25 + 2j)),
+                               (R.EPI_MAG2, 0, lambda y: R.complex_to_mag2(y))):
+            f = R.Fir(taps, deci=deci)
+            f.set_epilogue(kind, val)
+            assert not f.uses_tensor_cores
+            n_out = f.out_count(len(x))
+            need = (n_out - 1) * deci + ntaps
+            din = R.DeviceBuffer.from_numpy(x[:need])
+            mag = kind == R.EPI_MAG2
+            dout = R.DeviceBuffer(n_out * (4 if mag else 8))
+            f.run(din, need, dout, n_out)
+            got = dout.download(np.float32 if mag else np.complex64, n_out)
+            want = ref(base)
+            assert got.tobytes() == want.tobytes(), (shape, cplx_taps, kind)
+    f = R.Fir(taps, deci=deci)
+    f.set_epilogue(R.EPI_MULTIPLY_CONST, 2.0)
+    with pytest.raises(R.RrcError):                              # demod's gain IS the fused MultiplyConst
+        f.demod_run_batch(din, len(x), need, 1.0, dout, n_out - 1, n_out, 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ntaps", [257, 4097])
+def test_fftfilter_store_epilogues_equal_the_unfused_chain(R, ntaps):
+    """FftFilter -> MultiplyConst / ComplexToMag2 fused into phase A' / the fold kernel's combine store equals the two
+    blocks back to back bit for bit, for the plain run, the store-predicate decimation and the decimate-by-8 kernel."""
+    x = O.synth_c32(72, 0, 150_000)
+    taps = O.low_pass_n(1.0, 0.05, ntaps).astype(np.complex64)
+    dx = R.DeviceBuffer.from_numpy(x)
+    n = len(x)
+    y = R.FftFilt(taps).filter(x)
+    for kind, val, ref in ((R.EPI_MULTIPLY_CONST, 0.5 + 0.25j, lambda v: R.multiply_const(v, 0.5 + 0.25j)),
+                           (R.EPI_MAG2, 0, lambda v: R.complex_to_mag2(v))):
+        mag = kind == R.EPI_MAG2
+        dt, esz = (np.float32, 4) if mag else (np.complex64, 8)
+        f = R.FftFilt(taps)
+        f.set_epilogue(kind, val)
+        dout = R.DeviceBuffer(n * esz)
+        f.run(dx, n, dout)
+        assert dout.download(dt, n).tobytes() == ref(y).tobytes(), (ntaps, kind, "run")
+        for deci, skip in ((8, 0), (8, 5), (3, 1)):
+            plain = R.FftFilt(taps)
+            cnt = (n - skip + deci - 1) // deci
+            d0 = R.DeviceBuffer(cnt * 8)
+            assert plain.decim_run(dx, n, deci, skip, d0) == cnt
+            f = R.FftFilt(taps)
+            f.set_epilogue(kind, val)
+            d1 = R.DeviceBuffer(cnt * esz)
+            assert f.decim_run(dx, n, deci, skip, d1) == cnt
+            assert d1.download(dt, cnt).tobytes() == ref(d0.download(np.complex64, cnt)).tobytes(), (ntaps, kind, deci, skip)
+    # end to end: the MAG2 form halves the D2H bytes
+    f = R.FftFilt(taps)
+    f.set_epilogue(R.EPI_MAG2)
+    out = np.empty((n // f.nsamples) * f.nsamples, np.float32)
+    got = f.run_host(x, out)
+    assert got.tobytes() == R.complex_to_mag2(R.FftFilt(taps).run_host(x)).tobytes()
