@@ -64,7 +64,19 @@ struct FirTccArgs {             // fir_tcc_kernel: c32 samples, complex taps (tr
     unsigned long long out_base;
 };
 
+struct FirTc5Args {             // fir_tc5_kernel (tcgen05 / TMEM): c32 samples, real taps, deci 1, ntaps <= 65
+    const float2* in;
+    float2* out;
+    const uint4* bimg;         // swizzled shared-memory image of the Toeplitz tap operand (fir_tc5_bimg_offset)
+    long long in_stride, out_stride, need, out_n;
+    long long tiles_x, total_tiles;
+    int KS;                    // k-steps of 16: ceil((63 + ntaps) / 16) <= 8
+    int base_off;              // matrix-descriptor base offset of the operand advanced by one 128-byte row
+    float tap_inv_scale;
+};
+
 constexpr int FIR_TC_THREADS = 256;
+constexpr int FIR_TC5_BT = 8192;           // outputs per CTA tile of fir_tc5_kernel
 constexpr int FIR_TC1_BT = 512;            // INPUT samples a warp tile of fir_tc1_kernel advances by: 512/deci outputs
 constexpr int FIR_TCF_IN = 1024;           // INPUT samples a warp tile of fir_tcf_kernel (f32 streams) advances by
 constexpr int FIR_TC1_MAX_KS = 20;         // deci 1/2/4 kernel: up to 20 k-steps of 16 samples, i.e. 7*deci + ntaps <= 320
@@ -80,5 +92,8 @@ int fir_tc_launch(const FirTcGeom& g, const FirTcArgs& a, bool demod, cudaStream
 int fir_tc1_launch(const FirTcGeom& g, const FirTc1Args& a, bool demod, cudaStream_t st);
 int fir_tcf_launch(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st);
 int fir_tcc_launch(const FirTcGeom& g, const FirTccArgs& a, bool demod, cudaStream_t st);
+size_t fir_tc5_bimg_bytes();
+size_t fir_tc5_bimg_offset(int part, int half, int n, int kk);
+int fir_tc5_launch(int device, const FirTc5Args& a, cudaStream_t st);
 
 }  // namespace rrc

@@ -1,0 +1,298 @@
+// fir_tc5.cu — FirFilter (reference src/fir.rs:166-197, Fir::filter_n; block src/fir.rs:492-527) for c32 samples, real
+// taps, decimation 1 and ntaps <= 65 on the 5th-generation tensor cores: tcgen05.mma (kind::f16) with the accumulators
+// in tensor memory.  Same arithmetic contract as fir_tc.cuh (block-scaled fp16 hi + lo split of samples and taps, the
+// three products hi*hi + hi*lo + lo*hi accumulated in FP32), different machinery:
+//
+//   * A CTA tile is 8192 outputs = 128 block-rows of 64.  The staged fp16 plane of one component (re or im; hi or lo
+//     part) is 129 rows of 64 samples, i.e. 129 rows of 128 bytes: exactly the rows of SWIZZLE_128B K-major atoms
+//     (8 rows x 128 B, 16-byte chunk c of row r stored at chunk c ^ (r % 8)).  The Toeplitz operand
+//     A[b][k] = z[64 b + k], k < 128, is never built: for k < 64 it IS the staged plane (rows 0..127), for k >= 64 it
+//     is the same plane advanced by one row (descriptor start address + 128 B, rows 1..128).
+//   * B[n][k] = w'[k - n] (reversed, scaled taps; 64 x 128, K-major, two 64-column halves, hi and lo parts) is built
+//     once on the host in the swizzled shared-memory image and copied in at kernel start.
+//   * D = A * B^T: M = 128, N = 64, K = 16 per instruction, up to 8 k-steps x 3 products x 2 components = 48
+//     tcgen05.mma per tile, issued by one thread; completion arrives on an mbarrier (tcgen05.commit).
+//   * Epilogue: tcgen05.ld.16x256b (the mma C-fragment distribution: a lane gets two adjacent columns of one row), so
+//     the re and im accumulators of an output meet in one lane and four lanes write 64 contiguous bytes.
+//
+// Two CTAs per SM (2 x ~101 KB of shared memory, 2 x 128 TMEM columns) overlap each other's phases; inside a CTA the
+// next tile's global loads are in flight while the current tile's MMAs run and its outputs are stored.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "fir_tc.hpp"
+
+namespace rrc {
+namespace {
+
+constexpr int TC5_THREADS = 256;
+constexpr int TC5_ROWS = 129;                       // staged rows of 64 samples
+constexpr int TC5_PLANE = 17 * 1024;                // bytes per plane (129 * 128 rounded up to the 1024-byte atom)
+constexpr int TC5_BIMG = 32 * 1024;                 // B image: {hi, lo} x {k < 64, k >= 64} x 64 rows x 128 B
+constexpr int TC5_NLD = 17;                         // float4 loads per lane: rows warp, warp + 8, ...
+constexpr unsigned TC5_IDESC = 0x08100010u;         // kind::f16: D f32, A/B f16 K-major, N = 64 (>>3 at bit 17), M = 128 (>>4 at bit 24)
+constexpr size_t TC5_SMEM = 1024 + 4 * TC5_PLANE + TC5_BIMG + 64;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// Shared-memory matrix descriptor, SWIZZLE_128B K-major: start address >> 4 at [0,14), LBO (unused for a swizzled
+// K-major operand whose K extent stays inside the atom) = 1 at [16,30), SBO = 1024 B >> 4 at [32,46), version 1 at
+// [46,48), base offset at [49,52), layout type 2 at [61,64)  (cute/arch/mma_sm100_desc.hpp).
+__device__ __forceinline__ unsigned long long tc5_desc(unsigned addr, unsigned base_off) {
+    return (unsigned long long)((addr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+           ((unsigned long long)(base_off & 7u) << 49) | (2ull << 61);
+}
+
+__device__ __forceinline__ void tc5_mma(unsigned d_tmem, unsigned long long a, unsigned long long b, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(a), "l"(b), "r"(TC5_IDESC), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tc5_ld16(unsigned taddr, unsigned (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ void tc5_split2(float a, float b, unsigned& hi, unsigned& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const unsigned*>(&h);
+    lo = *reinterpret_cast<const unsigned*>(&l);
+}
+
+// Tile loads: row (warp + 8u) of the tile, samples 2*lane, 2*lane + 1 of that row.
+__device__ __forceinline__ void tc5_load(const FirTc5Args& a, long long tile, int warp, int lane, float4 (&v)[TC5_NLD]) {
+    const long long ch = tile / a.tiles_x, tx = tile - ch * a.tiles_x;
+    const long long s0 = tx * FIR_TC5_BT;
+    const float2* in = a.in + ch * a.in_stride + s0;
+    const long long avail = a.need - s0;
+    const bool fast = avail >= 64ll * TC5_ROWS && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    if (fast) {
+        const float4* p = reinterpret_cast<const float4*>(in) + lane;
+#pragma unroll
+        for (int u = 0; u < TC5_NLD; ++u) {
+            const int row = warp + 8 * u;
+            v[u] = row < TC5_ROWS ? __ldg(p + row * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < TC5_NLD; ++u) {
+            const long long s = 64ll * (warp + 8 * u) + 2 * lane;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (warp + 8 * u < TC5_ROWS) {
+                if (s < avail) { const float2 p = __ldg(in + s); v[u].x = p.x; v[u].y = p.y; }
+                if (s + 1 < avail) { const float2 q = __ldg(in + s + 1); v[u].z = q.x; v[u].w = q.y; }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TC5_THREADS, 2) fir_tc5_kernel(const FirTc5Args a) {
+    extern __shared__ unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned raw = smem_u32(smem_raw);
+    unsigned char* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);       // swizzle atoms need 1024-byte alignment
+    unsigned char* s_planes = sm;                                          // plane p = 2 * (im?) + (lo?)
+    unsigned char* s_b = sm + 4 * TC5_PLANE;
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_b + TC5_BIMG);
+    unsigned* s_tmem = reinterpret_cast<unsigned*>(s_bar + 1);
+    unsigned* s_red = s_tmem + 1;                                          // 8 words
+    const unsigned planes_u = smem_u32(s_planes), b_u = smem_u32(s_b), bar_u = smem_u32(s_bar);
+
+    {   // B image -> shared memory, zero the plane padding rows once (never written again, never read by a valid output)
+        const uint4* src = a.bimg;
+        uint4* dst = reinterpret_cast<uint4*>(s_b);
+        for (int i = tid; i < TC5_BIMG / 16; i += TC5_THREADS) dst[i] = __ldg(src + i);
+        uint4* pl = reinterpret_cast<uint4*>(s_planes);
+        for (int i = tid; i < 4 * TC5_PLANE / 16; i += TC5_THREADS) pl[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" :: "r"(smem_u32(s_tmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = *s_tmem;
+
+    float4 v[TC5_NLD];
+    long long tile = blockIdx.x;
+    if (tile < a.total_tiles) tc5_load(a, tile, warp, lane, v);
+    unsigned phase = 0;
+    for (; tile < a.total_tiles; tile += gridDim.x) {
+        // ---- A. largest finite magnitude of the tile -> power-of-two scale (CTA-wide)
+        float mx = 0.f;
+#pragma unroll
+        for (int u = 0; u < TC5_NLD; ++u)
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+        unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));          // NaN never wins fmaxf; Inf does
+        if (lane == 0) s_red[warp] = wmax;
+        __syncthreads();                    // also: every warp is past the previous tile's TMEM loads and plane use
+        unsigned ex = 0;
+#pragma unroll
+        for (int i = 0; i < TC5_THREADS / 32; ++i) ex = max(ex, s_red[i]);
+        ex >>= 23;
+        if (ex == 255u) {                   // a non-finite sample: scale by the largest finite one (block-uniform branch)
+            __syncthreads();
+            float m2 = 0.f;
+            auto fin = [](float c) { const float q = fabsf(c); return q <= 3.4028234e38f ? q : 0.f; };
+#pragma unroll
+            for (int u = 0; u < TC5_NLD; ++u)
+                m2 = fmaxf(fmaxf(m2, fmaxf(fin(v[u].x), fin(v[u].y))), fmaxf(fin(v[u].z), fin(v[u].w)));
+            wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(m2));
+            if (lane == 0) s_red[warp] = wmax;
+            __syncthreads();
+            ex = 0;
+#pragma unroll
+            for (int i = 0; i < TC5_THREADS / 32; ++i) ex = max(ex, s_red[i]);
+            ex >>= 23;
+        }
+        const bool scaled = ex >= 14u && ex < 255u;
+        const float sc = scaled ? __uint_as_float((267u - ex) << 23) : 1.0f;          // 2^(13 - (ex - 127))
+        const float isc = scaled ? __uint_as_float((ex - 13u) << 23) : 1.0f;
+        const float inv = isc * a.tap_inv_scale;
+
+        // ---- B. split into the four swizzled fp16 planes
+        {
+            const unsigned col = ((unsigned)(lane & 3)) << 2;
+#pragma unroll
+            for (int u = 0; u < TC5_NLD; ++u) {
+                const int row = warp + 8 * u;
+                if (row < TC5_ROWS) {
+                    unsigned rh, rl, ih, il;
+                    tc5_split2(v[u].x * sc, v[u].z * sc, rh, rl);
+                    tc5_split2(v[u].y * sc, v[u].w * sc, ih, il);
+                    unsigned char* p = s_planes + row * 128 + ((((unsigned)lane >> 2) ^ ((unsigned)row & 7u)) << 4) + col;
+                    *reinterpret_cast<unsigned*>(p) = rh;
+                    *reinterpret_cast<unsigned*>(p + TC5_PLANE) = rl;
+                    *reinterpret_cast<unsigned*>(p + 2 * TC5_PLANE) = ih;
+                    *reinterpret_cast<unsigned*>(p + 3 * TC5_PLANE) = il;
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core's reads
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+
+        // ---- C. one thread issues the tile's MMAs; completion -> mbarrier
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int comp = 0; comp < 2; ++comp) {
+                const unsigned d = tmem + 64u * comp;
+                const unsigned p_hi = planes_u + (2 * comp) * TC5_PLANE, p_lo = p_hi + TC5_PLANE;
+#pragma unroll 1
+                for (int s = 0; s < a.KS; ++s) {
+                    const unsigned half = (unsigned)s >> 2, ko = ((unsigned)s & 3u) * 32u;
+                    const unsigned bo = half ? (unsigned)a.base_off : 0u;
+                    const unsigned long long a_hi = tc5_desc(p_hi + half * 128u + ko, bo);
+                    const unsigned long long a_lo = tc5_desc(p_lo + half * 128u + ko, bo);
+                    const unsigned long long b_hi = tc5_desc(b_u + half * 8192u + ko, 0u);
+                    const unsigned long long b_lo = tc5_desc(b_u + 16384u + half * 8192u + ko, 0u);
+                    tc5_mma(d, a_hi, b_hi, s ? 1u : 0u);
+                    tc5_mma(d, a_hi, b_lo, 1u);
+                    tc5_mma(d, a_lo, b_hi, 1u);
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_u) : "memory");
+        }
+        __syncwarp();
+
+        // ---- D. next tile's loads go out while the tensor core works
+        const long long ch = tile / a.tiles_x, tx = tile - ch * a.tiles_x;
+        const long long next = tile + gridDim.x;
+        if (next < a.total_tiles) tc5_load(a, next, warp, lane, v);
+
+        // ---- E. wait for the accumulators, scale, store
+        {
+            unsigned done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done) : "r"(bar_u), "r"(phase) : "memory");
+            }
+            phase ^= 1u;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+            const long long o0 = tx * FIR_TC5_BT;
+            float2* out = a.out + ch * a.out_stride + o0;
+            const long long cnt = a.out_n - o0;                                    // outputs of this tile that exist (may exceed 8192)
+            const bool fast = cnt >= FIR_TC5_BT && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+            const int q = warp & 3, chalf = warp >> 2;
+            const int i = lane >> 2, t = lane & 3;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                unsigned re[16], im[16];
+                const unsigned taddr = tmem + ((unsigned)(32 * q + 16 * hh) << 16) + 32u * chalf;
+                tc5_ld16(taddr, re);
+                tc5_ld16(taddr + 64u, im);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+#pragma unroll
+                    for (int v1 = 0; v1 < 2; ++v1) {
+                        const int row = 32 * q + 16 * hh + 8 * v1 + i;
+                        const int c = 32 * chalf + 8 * g + 2 * t;
+                        const int r0 = 4 * g + 2 * v1;
+                        const float4 y = make_float4(__uint_as_float(re[r0]) * inv, __uint_as_float(im[r0]) * inv,
+                                                     __uint_as_float(re[r0 + 1]) * inv, __uint_as_float(im[r0 + 1]) * inv);
+                        const long long o = 64ll * row + c;
+                        if (fast) {
+                            *reinterpret_cast<float4*>(out + o) = y;
+                        } else {
+                            if (o < cnt) out[o] = make_float2(y.x, y.y);
+                            if (o + 1 < cnt) out[o + 1] = make_float2(y.z, y.w);
+                        }
+                    }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
+}
+
+}  // namespace
+
+size_t fir_tc5_bimg_bytes() { return TC5_BIMG; }
+
+// Shared-memory image of B for reversed taps w[0..T) already scaled (fp16 hi / lo parts given as bit patterns by the
+// callbacks): part (0 hi, 1 lo), half (k < 64, k >= 64), row n, k-local kk -> byte offset.
+size_t fir_tc5_bimg_offset(int part, int half, int n, int kk) {
+    return (size_t)part * 16384 + (size_t)half * 8192 + (size_t)n * 128 + (size_t)((((unsigned)kk >> 3) ^ ((unsigned)n & 7u)) << 4) + (size_t)(kk & 7) * 2;
+}
+
+int fir_tc5_launch(int device, const FirTc5Args& a, cudaStream_t st) {
+    static int cache[16] = {};
+    const int dv = (device < 0 || device >= 16) ? 0 : device;
+    if (cache[dv] == 0) {
+        RRC_CUDA(cudaFuncSetAttribute(fir_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC5_SMEM));
+        int per_sm = 0;
+        RRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fir_tc5_kernel, TC5_THREADS, TC5_SMEM));
+        if (per_sm < 1) return fail(RRC_ERR_CUDA, "fir_tc5: kernel does not fit an SM");
+        cache[dv] = std::min(per_sm, 4);                 // 128 TMEM columns per CTA: at most 4 CTAs can allocate
+        if (const char* e = getenv("RRC_FIR_TC5_CTAS")) { const int c = atoi(e); if (c >= 1 && c <= cache[dv]) cache[dv] = c; }
+    }
+    const long long cap = (long long)sm_count(device) * cache[dv];
+    fir_tc5_kernel<<<(unsigned)std::min<long long>(a.total_tiles, cap), TC5_THREADS, TC5_SMEM, st>>>(a);
+    RRC_CHECK_LAUNCH();
+    count_launch();
+    return RRC_OK;
+}
+
+}  // namespace rrc
