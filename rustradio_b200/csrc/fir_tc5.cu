@@ -20,6 +20,9 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "fir_tc.hpp"
@@ -37,19 +40,27 @@ constexpr size_t TC5_SMEM = 1024 + 4 * TC5_PLANE + TC5_BIMG + 64;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-// Shared-memory matrix descriptor, SWIZZLE_128B K-major: start address >> 4 at [0,14), LBO (unused for a swizzled
-// K-major operand whose K extent stays inside the atom) = 1 at [16,30), SBO = 1024 B >> 4 at [32,46), version 1 at
-// [46,48), base offset at [49,52), layout type 2 at [61,64)  (cute/arch/mma_sm100_desc.hpp).
-__device__ __forceinline__ unsigned long long tc5_desc(unsigned addr, unsigned base_off) {
-    return (unsigned long long)((addr >> 4) & 0x3fffu) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
-           ((unsigned long long)(base_off & 7u) << 49) | (2ull << 61);
+// Shared-memory matrix descriptor, SWIZZLE_128B K-major (cute/arch/mma_sm100_desc.hpp): start address >> 4 at [0,14),
+// LBO (unused for a swizzled K-major operand whose K extent stays inside the atom) = 1 at [16,30), SBO = 1024 B >> 4
+// at [32,46), version 1 at [46,48), base offset at [49,52), layout type 2 at [61,64).  Measured on B200: with base
+// offset 0 the XOR pattern follows the ABSOLUTE shared-memory address bits [7,10), so an operand that starts one
+// 128-byte row into an atom needs nothing but the advanced start address (base offset 1 shifts the pattern by one
+// row and reads the wrong chunks: tools/gpu/tc5_check.py prints the map).
+constexpr unsigned TC5_DESC_HI = 0x40004040u;          // SBO 1024 B (>>4) | version 1 | SWIZZLE_128B: bits [32,64) of every descriptor here
+__device__ __forceinline__ unsigned tc5_desc_lo(unsigned addr) { return ((addr >> 4) & 0x3fffu) | (1u << 16); }
+
+__device__ __forceinline__ void tc5_mma(unsigned d_tmem, unsigned a_lo, unsigned a_hi, unsigned b_lo, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %6};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        :: "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(TC5_IDESC), "r"(accumulate), "r"(TC5_DESC_HI) : "memory");
 }
 
-__device__ __forceinline__ void tc5_mma(unsigned d_tmem, unsigned long long a, unsigned long long b, unsigned accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :: "r"(d_tmem), "l"(a), "l"(b), "r"(TC5_IDESC), "r"(accumulate) : "memory");
+__device__ __forceinline__ unsigned tc5_elect() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred;
 }
 
 __device__ __forceinline__ void tc5_ld16(unsigned taddr, unsigned (&r)[16]) {
@@ -95,7 +106,10 @@ __device__ __forceinline__ void tc5_load(const FirTc5Args& a, long long tile, in
     }
 }
 
-__global__ void __launch_bounds__(TC5_THREADS, 2) fir_tc5_kernel(const FirTc5Args a) {
+constexpr int TC5_NSTAMP = 9, TC5_TRACE_IT = 4;
+#define TC5_STAMP(k) do { if (trace && blockIdx.x == 2 && it >= 1 && it <= TC5_TRACE_IT && lane == 0) trace[((it - 1) * 8 + warp) * TC5_NSTAMP + (k)] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(TC5_THREADS, 2) fir_tc5_kernel(const FirTc5Args a, long long* __restrict__ trace) {
     extern __shared__ unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned raw = smem_u32(smem_raw);
@@ -131,7 +145,9 @@ __global__ void __launch_bounds__(TC5_THREADS, 2) fir_tc5_kernel(const FirTc5Arg
     long long tile = blockIdx.x;
     if (tile < a.total_tiles) tc5_load(a, tile, warp, lane, v);
     unsigned phase = 0;
-    for (; tile < a.total_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (; tile < a.total_tiles; tile += gridDim.x, ++it) {
+        TC5_STAMP(0);
         // ---- A. largest finite magnitude of the tile -> power-of-two scale (CTA-wide)
         float mx = 0.f;
 #pragma unroll
@@ -163,6 +179,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 2) fir_tc5_kernel(const FirTc5Arg
         const float sc = scaled ? __uint_as_float((267u - ex) << 23) : 1.0f;          // 2^(13 - (ex - 127))
         const float isc = scaled ? __uint_as_float((ex - 13u) << 23) : 1.0f;
         const float inv = isc * a.tap_inv_scale;
+        TC5_STAMP(1);
 
         // ---- B. split into the four swizzled fp16 planes
         {
@@ -184,37 +201,45 @@ __global__ void __launch_bounds__(TC5_THREADS, 2) fir_tc5_kernel(const FirTc5Arg
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core's reads
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        TC5_STAMP(2);
         __syncthreads();
+        TC5_STAMP(3);
 
         // ---- C. one thread issues the tile's MMAs; completion -> mbarrier
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-            for (int comp = 0; comp < 2; ++comp) {
-                const unsigned d = tmem + 64u * comp;
-                const unsigned p_hi = planes_u + (2 * comp) * TC5_PLANE, p_lo = p_hi + TC5_PLANE;
-#pragma unroll 1
-                for (int s = 0; s < a.KS; ++s) {
-                    const unsigned half = (unsigned)s >> 2, ko = ((unsigned)s & 3u) * 32u;
-                    const unsigned bo = half ? (unsigned)a.base_off : 0u;
-                    const unsigned long long a_hi = tc5_desc(p_hi + half * 128u + ko, bo);
-                    const unsigned long long a_lo = tc5_desc(p_lo + half * 128u + ko, bo);
-                    const unsigned long long b_hi = tc5_desc(b_u + half * 8192u + ko, 0u);
-                    const unsigned long long b_lo = tc5_desc(b_u + 16384u + half * 8192u + ko, 0u);
-                    tc5_mma(d, a_hi, b_hi, s ? 1u : 0u);
-                    tc5_mma(d, a_hi, b_lo, 1u);
-                    tc5_mma(d, a_lo, b_hi, 1u);
+        if (warp == 0) {
+            if (tc5_elect()) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned a_hi1 = TC5_DESC_HI | (((unsigned)a.base_off & 7u) << 17);     // base offset: bits [49,52)
+                const unsigned pa = tc5_desc_lo(planes_u), pb = tc5_desc_lo(b_u);
+                constexpr unsigned PL16 = TC5_PLANE / 16;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {                   // re and im accumulators alternate: consecutive MMAs are independent
+                    if (s < a.KS) {
+                        const unsigned half = (unsigned)s >> 2, ko = ((unsigned)s & 3u) * 2u;  // all offsets in 16-byte units
+                        const unsigned ah = half ? a_hi1 : TC5_DESC_HI;
+                        const unsigned xa = pa + half * 8u + ko;
+                        const unsigned b_hi = pb + half * 512u + ko, b_lo = b_hi + 1024u;
+                        const unsigned acc = s ? 1u : 0u;
+                        tc5_mma(tmem, xa, ah, b_hi, acc);
+                        tc5_mma(tmem + 64u, xa + 2 * PL16, ah, b_hi, acc);
+                        tc5_mma(tmem, xa, ah, b_lo, 1u);
+                        tc5_mma(tmem + 64u, xa + 2 * PL16, ah, b_lo, 1u);
+                        tc5_mma(tmem, xa + PL16, ah, b_hi, 1u);
+                        tc5_mma(tmem + 64u, xa + 3 * PL16, ah, b_hi, 1u);
+                    }
                 }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_u) : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar_u) : "memory");
         }
         __syncwarp();
+        TC5_STAMP(4);
 
         // ---- D. next tile's loads go out while the tensor core works
         const long long ch = tile / a.tiles_x, tx = tile - ch * a.tiles_x;
         const long long next = tile + gridDim.x;
         if (next < a.total_tiles) tc5_load(a, next, warp, lane, v);
 
+        TC5_STAMP(5);
         // ---- E. wait for the accumulators, scale, store
         {
             unsigned done = 0;
@@ -228,6 +253,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 2) fir_tc5_kernel(const FirTc5Arg
             phase ^= 1u;
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        TC5_STAMP(6);
         {
             const long long o0 = tx * FIR_TC5_BT;
             float2* out = a.out + ch * a.out_stride + o0;
@@ -262,6 +288,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 2) fir_tc5_kernel(const FirTc5Arg
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        TC5_STAMP(7);
     }
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" :: "r"(tmem) : "memory");
@@ -279,6 +306,7 @@ size_t fir_tc5_bimg_offset(int part, int half, int n, int kk) {
 
 int fir_tc5_launch(int device, const FirTc5Args& a, cudaStream_t st) {
     static int cache[16] = {};
+    static const bool want_dbg = getenv("RRC_FIR_TC5_TRACE") != nullptr;
     const int dv = (device < 0 || device >= 16) ? 0 : device;
     if (cache[dv] == 0) {
         RRC_CUDA(cudaFuncSetAttribute(fir_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC5_SMEM));
@@ -286,12 +314,39 @@ int fir_tc5_launch(int device, const FirTc5Args& a, cudaStream_t st) {
         RRC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fir_tc5_kernel, TC5_THREADS, TC5_SMEM));
         if (per_sm < 1) return fail(RRC_ERR_CUDA, "fir_tc5: kernel does not fit an SM");
         cache[dv] = std::min(per_sm, 4);                 // 128 TMEM columns per CTA: at most 4 CTAs can allocate
-        if (const char* e = getenv("RRC_FIR_TC5_CTAS")) { const int c = atoi(e); if (c >= 1 && c <= cache[dv]) cache[dv] = c; }
+        if (want_dbg) fprintf(stderr, "tc5: occupancy API says %d CTAs/SM\n", per_sm);
+        if (const char* e = getenv("RRC_FIR_TC5_CTAS")) { const int c = atoi(e); if (c >= 1 && c <= 4) cache[dv] = c; }
     }
     const long long cap = (long long)sm_count(device) * cache[dv];
-    fir_tc5_kernel<<<(unsigned)std::min<long long>(a.total_tiles, cap), TC5_THREADS, TC5_SMEM, st>>>(a);
+    static const bool want_trace = getenv("RRC_FIR_TC5_TRACE") != nullptr;
+    if (want_trace) fprintf(stderr, "tc5: %d CTAs/SM, grid %lld, smem %zu\n", cache[dv], std::min<long long>(a.total_tiles, cap), TC5_SMEM);
+    long long* dtrace = nullptr;
+    const size_t trace_n = (size_t)TC5_TRACE_IT * 8 * TC5_NSTAMP;
+    if (want_trace) { RRC_CUDA(cudaMalloc((void**)&dtrace, trace_n * 8)); RRC_CUDA(cudaMemsetAsync(dtrace, 0, trace_n * 8, st)); }
+    fir_tc5_kernel<<<(unsigned)std::min<long long>(a.total_tiles, cap), TC5_THREADS, TC5_SMEM, st>>>(a, dtrace);
     RRC_CHECK_LAUNCH();
     count_launch();
+    if (want_trace) {                                           // debug only: synchronous dump of CTA 2's per-phase cycle table
+        std::vector<long long> tr(trace_n);
+        RRC_CUDA(cudaStreamSynchronize(st));
+        RRC_CUDA(cudaMemcpy(tr.data(), dtrace, trace_n * 8, cudaMemcpyDeviceToHost));
+        cudaFree(dtrace);
+        static const char* names[] = {"max, barrier, scale", "split + STS + proxy fence", "barrier 2", "MMA issue (thread 0) / syncwarp",
+                                      "next tile's LDG issue", "mbarrier wait (MMA done)", "TMEM ld + scale + STG"};
+        static int dumps = 0;
+        if (a.total_tiles > 148 * 2 * 5 && dumps++ < 2)
+            for (int b = 0; b < TC5_TRACE_IT; ++b) {
+                long long t0 = tr[(size_t)(b * 8) * TC5_NSTAMP], tend = 0;
+                for (int w = 0; w < 8; ++w) { t0 = std::min(t0, tr[(size_t)(b * 8 + w) * TC5_NSTAMP]); tend = std::max(tend, tr[(size_t)(b * 8 + w) * TC5_NSTAMP + 7]); }
+                fprintf(stderr, "tc5 trace tile iter %d: total %lld cycles\n", b + 1, tend - t0);
+                for (int p = 0; p < 7; ++p) {
+                    std::vector<long long> d;
+                    for (int w = 0; w < 8; ++w) d.push_back(tr[(size_t)(b * 8 + w) * TC5_NSTAMP + p + 1] - tr[(size_t)(b * 8 + w) * TC5_NSTAMP + p]);
+                    std::sort(d.begin(), d.end());
+                    fprintf(stderr, "   %-34s min %6lld  med %6lld  max %6lld\n", names[p], d[0], d[4], d[7]);
+                }
+            }
+    }
     return RRC_OK;
 }
 

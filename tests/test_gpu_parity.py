@@ -152,6 +152,69 @@ def test_fir_tensor_core_walk_kernel(R, monkeypatch, ntaps, deci, n, nchan):
         assert O.max_angle_err(d[c] / 0.7, np.angle(truth[1:] * np.conj(truth[:-1]))) <= DEMOD_BAR
 
 
+@pytest.mark.parametrize("ntaps,n,nchan", [
+    (64, 262_144, 1), (65, 8_256, 1), (64, 64, 1), (16, 5_000, 2), (33, 70_001, 1), (64, 1_300, 5), (48, 16_415, 3),
+    (65, 3 * 8192 + 64, 2), (17, 600, 1), (40, 100_000, 2)])
+def test_fir_tcgen05_kernel(R, monkeypatch, ntaps, n, nchan):
+    """fir_tc5_kernel (tcgen05.mma + TMEM; c32 samples, real taps, deci 1, ntaps <= 65), selected with RRC_FIR_TCGEN05=1:
+    ragged last tiles, tiles shorter than one 8192-output CTA tile, odd channel strides (8-byte aligned channels take the
+    scalar loads / stores), several k-step counts.  Same bar as the mma.sync kernels."""
+    monkeypatch.setenv("RRC_FIR_TCGEN05", "1")
+    taps = O.low_pass_n(1.0, 0.2, ntaps).astype(np.complex64)
+    f = R.Fir(taps)
+    assert f.uses_tensor_cores and "fir_tc5_kernel" in f.kernel_name
+    stride = n + 1 if n % 2 == 0 else n
+    xs = np.zeros((nchan, stride), np.complex64)
+    for c in range(nchan):
+        xs[c, :n] = O.synth_c32(400 + c, 0, n) * 0.5 + np.exp(2j * np.pi * 0.013 * (c + 1) * np.arange(n)).astype(np.complex64)
+    out_n = f.out_count(n)
+    need = out_n - 1 + ntaps
+    din = R.DeviceBuffer.from_numpy(xs)
+    ostride = out_n + 1 - (out_n % 2)
+    dy = R.DeviceBuffer(nchan * ostride * 8)
+    f.run_batch(din, stride, need, dy, ostride, out_n, nchan)
+    y = dy.download(np.complex64, nchan * ostride).reshape(nchan, ostride)[:, :out_n]
+    for c in range(nchan):
+        truth = O.fir(xs[c, :n], taps, 1, f64=True)
+        e, e_ref = O.rel_rms(y[c], truth), O.rel_rms(O.fir(xs[c, :n], taps, 1), truth)
+        print(f"fir_tc5 T={ntaps} ch{c}: gpu {e:.2e}  f32-oracle {e_ref:.2e}")
+        assert e <= 2e-6
+    # the fused demod is not implemented on this kernel: it must still be right (falls to fir_tc1_kernel)
+    dd = R.DeviceBuffer(nchan * ostride * 4)
+    f.demod_run_batch(din, stride, need, 0.7, dd, ostride, out_n, nchan)
+    d = dd.download(np.float32, nchan * ostride).reshape(nchan, ostride)[:, :out_n - 1]
+    truth = O.fir(xs[0, :n], taps, 1, f64=True)
+    assert O.max_angle_err(d[0] / 0.7, np.angle(truth[1:] * np.conj(truth[:-1]))) <= DEMOD_BAR
+
+
+@pytest.mark.parametrize("scale", [1e-20, 1.0, 3e18])
+@pytest.mark.parametrize("bad", [None, np.inf, np.nan])
+def test_fir_tcgen05_block_scaling_and_non_finite(R, monkeypatch, scale, bad):
+    """The CTA-tile power-of-two scale keeps FP32-class accuracy at any signal level; one Inf / NaN sample makes the
+    outputs whose window holds it non-finite plus, at most, the rest of the two 64-output block-rows whose 128-sample
+    operand rows contain it (zero-padded Toeplitz taps meet it as 0 * Inf); everything else keeps the bar."""
+    monkeypatch.setenv("RRC_FIR_TCGEN05", "1")
+    n, ntaps, pos = 30_000, 64, 12_345
+    taps = O.low_pass_n(1.0, 0.1, ntaps).astype(np.complex64)
+    x = (O.synth_c32(61, 0, n) * np.float32(scale)).astype(np.complex64)
+    f = R.Fir(taps)
+    assert "fir_tc5_kernel" in f.kernel_name
+    if bad is not None:
+        x[pos] = bad
+    y = f.filter(x)
+    o = np.arange(len(y))
+    xz = x.copy()
+    far = np.ones(len(y), bool)
+    if bad is not None:
+        xz[pos] = 0
+        touched = (o > pos - ntaps) & (o <= pos)
+        far = (o < 64 * (pos // 64 - 1)) | (o >= 64 * (pos // 64 + 1))
+        assert not np.isfinite(y[touched]).any()
+    assert np.isfinite(y[far]).all()
+    truth = O.fir(xz, taps, 1, f64=True)
+    assert O.rel_rms(y[far], truth[far]) <= 2e-6
+
+
 @pytest.mark.parametrize("ntaps,deci,n,nchan", [
     (32, 1, 10_000, 2), (64, 1, 300_001, 1), (65, 1, 1_500, 3), (100, 1, 2_049, 1), (247, 1, 50_000, 2), (313, 1, 70_000, 1),
     (20, 1, 3_000, 1), (64, 2, 100_003, 1), (127, 2, 9_000, 2), (255, 2, 40_000, 1), (306, 2, 8_191, 1),
