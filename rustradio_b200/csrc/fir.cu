@@ -829,18 +829,31 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
     int want5 = 0;
     if (const char* e = getenv("RRC_FIR_TCGEN05")) want5 = atoi(e);
     if (want5 && h->cplx && D == 1 && T <= 65) {
-        std::vector<unsigned short> img(fir_tc5_bimg_bytes() / 2, 0);
-        for (int half = 0; half < 2; ++half)
-            for (int n = 0; n < 64; ++n)
-                for (int kk = 0; kk < 64; ++kk) {
-                    const float v = Bval(64 * half + kk, n);
-                    const unsigned short vh = f16_rn(v);
-                    img[fir_tc5_bimg_offset(0, half, n, kk) / 2] = vh;
-                    img[fir_tc5_bimg_offset(1, half, n, kk) / 2] = f16_rn(v - f16_to_f32(vh));
-                }
+        std::vector<unsigned short> img;
+        if (want5 == 1 || want5 == 2) {                    // samples as the A operand: swizzled Toeplitz image of the taps
+            img.assign(fir_tc5_bimg_bytes() / 2, 0);
+            for (int half = 0; half < 2; ++half)
+                for (int n = 0; n < 64; ++n)
+                    for (int kk = 0; kk < 64; ++kk) {
+                        const float v = Bval(64 * half + kk, n);
+                        const unsigned short vh = f16_rn(v);
+                        img[fir_tc5_bimg_offset(0, half, n, kk) / 2] = vh;
+                        img[fir_tc5_bimg_offset(1, half, n, kk) / 2] = f16_rn(v - f16_to_f32(vh));
+                    }
+            h->tc5_KS = (int)((63 + T + 15) / 16);
+        } else {                                           // taps in TMEM: table of the scaled taps' fp16 parts at index j + 128
+            const size_t tab = fir_tc5_tab_entries();
+            img.assign(2 * tab, 0);
+            for (size_t j = 0; j < T; ++j) {
+                const float v = Bval((long long)j, 0);
+                const unsigned short vh = f16_rn(v);
+                img[128 + j] = vh;
+                img[tab + 128 + j] = f16_rn(v - f16_to_f32(vh));
+            }
+            h->tc5_KS = (int)((127 + T + 15) / 16);
+        }
         RRC_CUDA(cudaMalloc(&h->tc5_bimg, img.size() * 2));
         RRC_CUDA(upload_sync(h->tc5_bimg, img.data(), img.size() * 2));
-        h->tc5_KS = (int)((63 + T + 15) / 16);
         h->tc5_base_off = 0;
         if (const char* e = getenv("RRC_FIR_TC5_BASE_OFF")) h->tc5_base_off = atoi(e) & 7;
     }

@@ -70,7 +70,7 @@ struct FirTc5Args {             // fir_tc5_kernel (tcgen05 / TMEM): c32 samples,
     const uint4* bimg;         // swizzled shared-memory image of the Toeplitz tap operand (fir_tc5_bimg_offset)
     long long in_stride, out_stride, need, out_n;
     long long tiles_x, total_tiles;
-    int KS;                    // k-steps of 16: ceil((63 + ntaps) / 16) <= 8
+    int KS;                    // k-steps of 16: ceil((63 + ntaps) / 16) <= 8 (samples as A), ceil((127 + ntaps) / 16) <= 12 (taps in TMEM)
     int base_off;              // matrix-descriptor base offset of the operand advanced by one 128-byte row
     float tap_inv_scale;
 };
@@ -93,6 +93,7 @@ int fir_tc1_launch(const FirTcGeom& g, const FirTc1Args& a, bool demod, cudaStre
 int fir_tcf_launch(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st);
 int fir_tcc_launch(const FirTcGeom& g, const FirTccArgs& a, bool demod, cudaStream_t st);
 size_t fir_tc5_bimg_bytes();
+size_t fir_tc5_tab_entries();     // tap-stationary kernel: fp16 tap table entries per part, index (k - m) + 128
 size_t fir_tc5_bimg_offset(int part, int half, int n, int kk);
 int fir_tc5_launch(int device, const FirTc5Args& a, cudaStream_t st);
 

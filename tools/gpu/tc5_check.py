@@ -4,7 +4,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.getcwd())
-os.environ["RRC_FIR_TCGEN05"] = "1"
+os.environ.setdefault("RRC_FIR_TCGEN05", "1")
 from oracle import oracle as O
 import rustradio_b200 as R
 
