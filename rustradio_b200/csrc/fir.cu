@@ -842,14 +842,23 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
                     }
             h->tc5_KS = (int)((63 + T + 15) / 16);
         } else {                                           // taps in TMEM: table of the scaled taps' fp16 parts at index j + 128
+            // fp16x2 words of the scaled taps: [part hi / lo][alignment even / odd][q + 64], E[q] = (w[2q], w[2q + 1]),
+            // O[q] = (w[2q + 1], w[2q + 2]), zero outside the taps: lane m of the TMEM operand reads 96 consecutive words
             const size_t tab = fir_tc5_tab_entries();
-            img.assign(2 * tab, 0);
-            for (size_t j = 0; j < T; ++j) {
-                const float v = Bval((long long)j, 0);
+            img.assign(2 * 2 * tab * 2, 0);
+            auto part16 = [&](long long j, int part) -> unsigned short {
+                if (j < 0 || j >= (long long)T) return 0;
+                const float v = Bval(j, 0);
                 const unsigned short vh = f16_rn(v);
-                img[128 + j] = vh;
-                img[tab + 128 + j] = f16_rn(v - f16_to_f32(vh));
-            }
+                return part == 0 ? vh : f16_rn(v - f16_to_f32(vh));
+            };
+            for (int part = 0; part < 2; ++part)
+                for (int odd = 0; odd < 2; ++odd)
+                    for (size_t i = 0; i < tab; ++i) {
+                        const long long q = (long long)i - 64;
+                        img[2 * ((part * 2 + odd) * tab + i)] = part16(2 * q + odd, part);
+                        img[2 * ((part * 2 + odd) * tab + i) + 1] = part16(2 * q + odd + 1, part);
+                    }
             h->tc5_KS = (int)((127 + T + 15) / 16);
         }
         RRC_CUDA(cudaMalloc(&h->tc5_bimg, img.size() * 2));

@@ -554,9 +554,12 @@ __global__ void __launch_bounds__(TC5P_THREADS, 1) fir_tc5p_kernel(const FirTc5A
 // lane one output of 16 consecutive block-rows, a warp stores 256 contiguous bytes per block-row.
 constexpr int TC5T_REGION = 9 * 1024;               // 65 rows x 128 B, rounded up to the 1024-byte atom
 constexpr int TC5T_PLANE = 2 * TC5T_REGION;
-constexpr size_t TC5T_SMEM = 1024 + 8 * TC5T_PLANE + 512;
-constexpr int TC5T_THREADS = (2 * 8 + 4) * 32;       // two producer groups of 8 warps (warp 0 of a group also issues its MMAs), 4 epilogue warps
-constexpr int TC5T_TAB = 320;                       // tap table entries per part: index (k - m) + 128
+constexpr size_t TC5T_SMEM = 1024 + 8 * TC5T_PLANE + 4096;
+constexpr int TC5T_NPW = 9;                         // warps per producer group
+constexpr int TC5T_NLD = (TC5_ROWS + TC5T_NPW - 1) / TC5T_NPW;   // half-rows (float4 loads) per producer lane
+constexpr int TC5T_EPI0 = 2 * TC5T_NPW, TC5T_MMAW = TC5T_EPI0 + 4;
+constexpr int TC5T_THREADS = (TC5T_MMAW + 1) * 32;  // two producer groups, 4 epilogue warps (one per TMEM lane quarter), 1 MMA warp
+constexpr int TC5T_TAB = 160;                       // fp16x2 words per tap table (even / odd alignment, hi / lo part)
 
 __device__ __forceinline__ void tc5_mma_ts(unsigned d_tmem, unsigned a_tmem, unsigned b_lo, unsigned accumulate) {
     asm volatile(
@@ -577,87 +580,128 @@ __device__ __forceinline__ void tc5_st8(unsigned taddr, const unsigned (&r)[8]) 
                  :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 
+__device__ __forceinline__ void tc5t_load(const FirTc5Args& a, long long tile, int pw, int lane, float4 (&v)[TC5T_NLD]) {
+    const long long ch = tile / a.tiles_x, tx = tile - ch * a.tiles_x;
+    const long long s0 = tx * FIR_TC5_BT;
+    const float2* in = a.in + ch * a.in_stride + s0;
+    const long long avail = a.need - s0;
+    const bool fast = avail >= 64ll * TC5_ROWS && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    if (fast) {
+        const float4* p = reinterpret_cast<const float4*>(in) + lane;
+#pragma unroll
+        for (int u = 0; u < TC5T_NLD; ++u) {
+            const int hr = pw + TC5T_NPW * u;
+            v[u] = hr < TC5_ROWS ? ldg_stream(p + hr * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < TC5T_NLD; ++u) {
+            const long long s = 64ll * (pw + TC5T_NPW * u) + 2 * lane;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pw + TC5T_NPW * u < TC5_ROWS) {
+                if (s < avail) { const float2 p = __ldg(in + s); v[u].x = p.x; v[u].y = p.y; }
+                if (s + 1 < avail) { const float2 q = __ldg(in + s + 1); v[u].z = q.x; v[u].w = q.y; }
+            }
+        }
+    }
+}
+
 #define TC5T_STAMP(role, k) do { if (trace && blockIdx.x == 2 && j >= 2 && j < 2 + TC5P_TRACE_IT && lane == 0) trace[((j - 2) * 4 + (role)) * TC5P_NSTAMP + (k)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(TC5T_THREADS, 1) fir_tc5t_kernel(const FirTc5Args a, long long* __restrict__ trace) {
     extern __shared__ unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long* const ktr = (trace && blockIdx.x == 2) ? trace + TC5P_TRACE_IT * 4 * TC5P_NSTAMP : nullptr;   // whole-kernel stamps
+    if (ktr && tid == 0) ktr[0] = clock64();
     const unsigned raw = smem_u32(smem_raw);
     unsigned char* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
     unsigned char* s_planes = sm;                                          // [2 sets][4 planes][2 regions]
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm + 8 * TC5T_PLANE);   // (unused)[2], done[2], accfree[2]
-    unsigned* s_tmem = reinterpret_cast<unsigned*>(s_bar + 6);
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm + 8 * TC5T_PLANE);   // full[2], done[2], accfree[2], taps
+    unsigned* s_tmem = reinterpret_cast<unsigned*>(s_bar + 7);
     float* s_inv = reinterpret_cast<float*>(s_tmem + 1);                   // [4]
-    unsigned* s_red = reinterpret_cast<unsigned*>(s_inv + 4);              // [2 groups][3][8]
+    unsigned* s_red = reinterpret_cast<unsigned*>(s_inv + 4);              // [2 groups][3][16]
+    unsigned* s_tab = s_red + 96;                                          // [hi, lo][even, odd][TC5T_TAB]
     const unsigned planes_u = smem_u32(s_planes), bar_u = smem_u32(s_bar);
-    const unsigned done_u = bar_u + 16, accfree_u = bar_u + 32;
+    const unsigned full_u = bar_u, done_u = bar_u + 16, accfree_u = bar_u + 32, taps_u = bar_u + 48;
 
+    const long long first = blockIdx.x;
+    const int njobs = first < a.total_tiles ? (int)((a.total_tiles - first + gridDim.x - 1) / gridDim.x) : 0;
     if (tid == 0) {
-        for (unsigned g = 0; g < 2; ++g) { mbar_init(done_u + 8 * g, 1); mbar_init(accfree_u + 8 * g, 128); }
+        for (unsigned g = 0; g < 2; ++g) { mbar_init(full_u + 8 * g, 32 * TC5T_NPW); mbar_init(done_u + 8 * g, 1); mbar_init(accfree_u + 8 * g, 128); }
+        mbar_init(taps_u, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 16) {
+    __syncthreads();                        // the only CTA-wide barrier before the tail: the mbarriers exist
+    if (ktr && tid == 0) ktr[1] = clock64();
+    // Set-up off the producers' path: the MMA warp allocates tensor memory while the epilogue warps stage the tap words in
+    // shared memory; those 160 threads meet on named barrier 3, the epilogue warps write the tap operand into TMEM and
+    // arrive on `taps`, which the MMA warp waits for before its first MMA.  The producers go straight to their first tile.
+    unsigned tmem = 0;
+    if (warp == TC5T_MMAW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(s_tmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (ktr && lane == 0) ktr[9] = clock64();
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const unsigned tmem = *s_tmem;
-    if (warp >= 16 && warp < 20) {          // the tap operand: lane m, column c of part p holds (w'[2c - m], w'[2c + 1 - m]) as fp16x2
+    if (warp >= TC5T_EPI0) {
+        if (warp < TC5T_MMAW)
+            for (int i = tid - 32 * TC5T_EPI0; i < 4 * TC5T_TAB; i += 128) s_tab[i] = __ldg(reinterpret_cast<const unsigned*>(a.bimg) + i);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 3, 160;" ::: "memory");
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem = *s_tmem;
+        if (ktr && warp == TC5T_EPI0 && lane == 0) ktr[10] = clock64();
+    }
+    if (warp >= TC5T_EPI0 && warp < TC5T_MMAW) {          // the tap operand: lane m, column c of part p holds (w'[2c - m], w'[2c + 1 - m]) as fp16x2
         const int m = 32 * (warp & 3) + lane;
-        const unsigned short* tab = reinterpret_cast<const unsigned short*>(a.bimg);
+        // host tables of fp16x2 words: E[q] = (w'[2q], w'[2q + 1]), O[q] = (w'[2q + 1], w'[2q + 2]), q + 64 in [0, 160)
+        const unsigned* tab = s_tab + (m & 1) * TC5T_TAB - ((m + 1) >> 1) + 64;
         for (int part = 0; part < 2; ++part)
             for (int c8 = 0; c8 < 12; ++c8) {
                 unsigned r[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int idx = 2 * (8 * c8 + i) - m + 128;
-                    r[i] = (unsigned)__ldg(tab + part * TC5T_TAB + idx) | ((unsigned)__ldg(tab + part * TC5T_TAB + idx + 1) << 16);
-                }
+                for (int i = 0; i < 8; ++i) r[i] = tab[part * 2 * TC5T_TAB + 8 * c8 + i];
                 tc5_st8(tmem + ((unsigned)(32 * (warp & 3)) << 16) + 96u * part + 8u * c8, r);
             }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(taps_u);
+        if (ktr && warp == TC5T_EPI0 && lane == 0) ktr[11] = clock64();
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const long long first = blockIdx.x;
-    const int njobs = first < a.total_tiles ? (int)((a.total_tiles - first + gridDim.x - 1) / gridDim.x) : 0;
 
-    if (warp < 16) {
+    if (warp < TC5T_EPI0) {
         // ================= producers: group g stages tiles j = g, g + 2, ... into plane set g
-        const int g = warp >> 3, pw = warp & 7;
+        const int g = warp >= TC5T_NPW ? 1 : 0, pw = warp - g * TC5T_NPW;
+        float4 v[TC5T_NLD];
+        if (g < njobs) tc5t_load(a, first + (long long)g * gridDim.x, pw, lane, v);
+        if (ktr && warp == 0 && lane == 0) ktr[8] = clock64();
         unsigned char* planes = s_planes + g * 4 * TC5T_PLANE;
-        unsigned* red = s_red + g * 24;
-        float4 v[TC5_NLD];
-        if (g < njobs) tc5p_load(a, first + (long long)g * gridDim.x, pw, lane, v);
+        unsigned* red = s_red + g * 48;
         for (int j = g, u = 0; j < njobs; j += 2, ++u) {
             TC5T_STAMP(g, 0);
             float mx = 0.f;
 #pragma unroll
-            for (int i = 0; i < TC5_NLD; ++i)
+            for (int i = 0; i < TC5T_NLD; ++i)
                 mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[i].x), fabsf(v[i].y))), fmaxf(fabsf(v[i].z), fabsf(v[i].w)));
             unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));      // NaN never wins fmaxf; Inf does
-            unsigned* rb = red + 8 * (u & 1);
+            unsigned* rb = red + 16 * (u & 1);
             if (lane == 0) rb[pw] = wmax;
-            asm volatile("bar.sync %0, 256;" :: "r"(1 + g) : "memory");
+            asm volatile("bar.sync %0, %1;" :: "r"(1 + g), "n"(32 * TC5T_NPW) : "memory");
             unsigned ex = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ex = max(ex, rb[i]);
+            for (int i = 0; i < TC5T_NPW; ++i) ex = max(ex, rb[i]);
             ex >>= 23;
             if (ex == 255u) {               // a non-finite sample: scale by the largest finite one (group-uniform branch)
                 float m2 = 0.f;
                 auto fin = [](float c) { const float q = fabsf(c); return q <= 3.4028234e38f ? q : 0.f; };
 #pragma unroll
-                for (int i = 0; i < TC5_NLD; ++i)
+                for (int i = 0; i < TC5T_NLD; ++i)
                     m2 = fmaxf(fmaxf(m2, fmaxf(fin(v[i].x), fin(v[i].y))), fmaxf(fin(v[i].z), fin(v[i].w)));
                 wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(m2));
-                if (lane == 0) red[16 + pw] = wmax;
-                asm volatile("bar.sync %0, 256;" :: "r"(1 + g) : "memory");
+                if (lane == 0) red[32 + pw] = wmax;
+                asm volatile("bar.sync %0, %1;" :: "r"(1 + g), "n"(32 * TC5T_NPW) : "memory");
                 ex = 0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) ex = max(ex, red[16 + i]);
+                for (int i = 0; i < TC5T_NPW; ++i) ex = max(ex, red[32 + i]);
                 ex >>= 23;
             }
             const bool scaled = ex >= 14u && ex < 255u;
@@ -667,18 +711,16 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) fir_tc5t_kernel(const FirTc5A
             if (u >= 1) mbar_wait(done_u + 8 * g, (unsigned)(u - 1) & 1u);            // the MMAs of tile j - 2 have read plane set g
             TC5T_STAMP(g, 2);
             {
-                // half-row hr = pw + 8 i  ->  region hr & 1 = pw & 1, block-row n = (pw >> 1) + 4 i, n & 7 = (pw >> 1) + 4 (i & 1):
-                // two base addresses, everything else is an immediate offset of the stores
-                const unsigned col = ((unsigned)(lane & 3)) << 2, n0 = (unsigned)pw >> 1, c8 = (unsigned)lane >> 2;
-                unsigned char* pe = planes + (pw & 1) * TC5T_REGION + n0 * 128 + ((c8 ^ n0) << 4) + col;
-                unsigned char* po = planes + (pw & 1) * TC5T_REGION + (n0 + 4) * 128 + ((c8 ^ (n0 + 4)) << 4) + col;
+                const unsigned col = ((unsigned)(lane & 3)) << 2, c8 = (unsigned)lane >> 2;
 #pragma unroll
-                for (int i = 0; i < TC5_NLD; ++i) {
-                    if (i < 16 || pw == 0) {                                            // half-row 128 belongs to warp 0
+                for (int i = 0; i < TC5T_NLD; ++i) {
+                    const unsigned hr = (unsigned)(pw + TC5T_NPW * i);                 // half-row: 64 samples
+                    if (hr < (unsigned)TC5_ROWS) {
                         unsigned rh, rl, ih, il;
                         tc5_split2(v[i].x * sc, v[i].z * sc, rh, rl);
                         tc5_split2(v[i].y * sc, v[i].w * sc, ih, il);
-                        unsigned char* p = ((i & 1) ? po : pe) + (i >> 1) * 1024;
+                        const unsigned n = hr >> 1;
+                        unsigned char* p = planes + (hr & 1u) * TC5T_REGION + n * 128u + ((c8 ^ (n & 7u)) << 4) + col;
                         *reinterpret_cast<unsigned*>(p) = rh;
                         *reinterpret_cast<unsigned*>(p + TC5T_PLANE) = rl;
                         *reinterpret_cast<unsigned*>(p + 2 * TC5T_PLANE) = ih;
@@ -688,43 +730,13 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) fir_tc5t_kernel(const FirTc5A
             }
             if (pw == 0 && lane == 0) s_inv[j & 3] = isc * a.tap_inv_scale;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.sync %0, 256;" :: "r"(1 + g) : "memory");               // the group's planes are complete
+            mbar_arrive(full_u + 8 * g);
             TC5T_STAMP(g, 3);
-            if (j + 2 < njobs) tc5p_load(a, first + (long long)(j + 2) * gridDim.x, pw, lane, v);
+            if (j + 2 < njobs) tc5t_load(a, first + (long long)(j + 2) * gridDim.x, pw, lane, v);
             TC5T_STAMP(g, 4);
-            if (pw == 0) {
-                // ---- this warp issues the tile's MMAs (its next loads are already in flight)
-                if (u >= 1) mbar_wait(accfree_u + 8 * g, (unsigned)(u - 1) & 1u);      // tile j - 2 has left accumulator set g
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                TC5T_STAMP(g, 5);
-                if (tc5_elect()) {
-                    constexpr unsigned PL16 = TC5T_PLANE / 16, RG16 = TC5T_REGION / 16;
-                    const unsigned pb = tc5_desc_lo(planes_u + (unsigned)g * 4u * TC5T_PLANE);
-                    const unsigned d = tmem + 256u + 128u * (unsigned)g;
-#pragma unroll
-                    for (int s = 0; s < 12; ++s) {
-                        if (s < a.KS) {
-                            // k-block 0: region 0; 1: region 1; 2: region 0 advanced by one 128-byte row (offsets in 16-byte units)
-                            const unsigned kb = (unsigned)s >> 2;
-                            const unsigned xb = pb + (kb == 1 ? RG16 : 0u) + (kb == 2 ? 8u : 0u) + ((unsigned)s & 3u) * 2u;
-                            const unsigned a_hi = tmem + 8u * s, a_lo = a_hi + 96u;
-                            const unsigned acc = s ? 1u : 0u;
-                            tc5_mma_ts(d, a_hi, xb, acc);                       // re: hi * hi
-                            tc5_mma_ts(d + 64u, a_hi, xb + 2 * PL16, acc);      // im: hi * hi
-                            tc5_mma_ts(d, a_hi, xb + PL16, 1u);                 // taps hi * samples lo
-                            tc5_mma_ts(d + 64u, a_hi, xb + 3 * PL16, 1u);
-                            tc5_mma_ts(d, a_lo, xb, 1u);                        // taps lo * samples hi
-                            tc5_mma_ts(d + 64u, a_lo, xb + 2 * PL16, 1u);
-                        }
-                    }
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(done_u + 8 * g) : "memory");
-                }
-                __syncwarp();
-                TC5T_STAMP(g, 6);
-            }
         }
-    } else {
+        if (ktr && lane == 0 && pw == 0) ktr[2 + g] = clock64();
+    } else if (warp < TC5T_MMAW) {
         // ================= epilogue: warp q holds outputs 32 q + lane of every block-row
         const int q = warp & 3;
         for (int j = 0; j < njobs; ++j) {
@@ -756,11 +768,50 @@ __global__ void __launch_bounds__(TC5T_THREADS, 1) fir_tc5t_kernel(const FirTc5A
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(accfree_u + 8 * g);
             if (q == 0) TC5T_STAMP(3, 2);
+            if (ktr && q == 0 && lane == 0 && j < 2) ktr[6 + j] = clock64();
+        }
+        if (ktr && q == 0 && lane == 0) ktr[4] = clock64();
+    } else {
+        // ================= MMA warp
+        constexpr unsigned PL16 = TC5T_PLANE / 16, RG16 = TC5T_REGION / 16;
+        mbar_wait(taps_u, 0u);
+        for (int j = 0; j < njobs; ++j) {
+            const int g = j & 1, u = j >> 1;
+            TC5T_STAMP(2, 0);
+            mbar_wait(full_u + 8 * g, (unsigned)u & 1u);
+            TC5T_STAMP(2, 1);
+            if (u >= 1) mbar_wait(accfree_u + 8 * g, (unsigned)(u - 1) & 1u);          // tile j - 2 has left accumulator set g
+            TC5T_STAMP(2, 2);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tc5_elect()) {
+                const unsigned pb = tc5_desc_lo(planes_u + (unsigned)g * 4u * TC5T_PLANE);
+                const unsigned d = tmem + 256u + 128u * (unsigned)g;
+#pragma unroll
+                for (int s = 0; s < 12; ++s) {
+                    if (s < a.KS) {
+                        // k-block 0: region 0; 1: region 1; 2: region 0 advanced by one 128-byte row (offsets in 16-byte units)
+                        const unsigned kb = (unsigned)s >> 2;
+                        const unsigned xb = pb + (kb == 1 ? RG16 : 0u) + (kb == 2 ? 8u : 0u) + ((unsigned)s & 3u) * 2u;
+                        const unsigned a_hi = tmem + 8u * s, a_lo = a_hi + 96u;
+                        const unsigned acc = s ? 1u : 0u;
+                        tc5_mma_ts(d, a_hi, xb, acc);                       // re: hi * hi
+                        tc5_mma_ts(d + 64u, a_hi, xb + 2 * PL16, acc);      // im: hi * hi
+                        tc5_mma_ts(d, a_hi, xb + PL16, 1u);                 // taps hi * samples lo
+                        tc5_mma_ts(d + 64u, a_hi, xb + 3 * PL16, 1u);
+                        tc5_mma_ts(d, a_lo, xb, 1u);                        // taps lo * samples hi
+                        tc5_mma_ts(d + 64u, a_lo, xb + 2 * PL16, 1u);
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(done_u + 8 * g) : "memory");
+            }
+            __syncwarp();
+            TC5T_STAMP(2, 3);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+    if (warp == TC5T_MMAW) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+    if (ktr && tid == 0) ktr[5] = clock64();
 }
 
 }  // namespace
@@ -785,7 +836,7 @@ int fir_tc5p_launch(int device, const FirTc5Args& a, cudaStream_t st, bool ts) {
     }
     static const bool want_trace = getenv("RRC_FIR_TC5_TRACE") != nullptr;
     long long* dtrace = nullptr;
-    const size_t trace_n = (size_t)TC5P_TRACE_IT * 4 * TC5P_NSTAMP;
+    const size_t trace_n = (size_t)TC5P_TRACE_IT * 4 * TC5P_NSTAMP + 16;
     if (want_trace) { RRC_CUDA(cudaMalloc((void**)&dtrace, trace_n * 8)); RRC_CUDA(cudaMemsetAsync(dtrace, 0, trace_n * 8, st)); }
     const unsigned grid = (unsigned)std::min<long long>(a.total_tiles, sm_count(device));
     if (ts) fir_tc5t_kernel<<<grid, TC5T_THREADS, TC5T_SMEM, st>>>(a, dtrace);
@@ -813,6 +864,10 @@ int fir_tc5p_launch(int device, const FirTc5Args& a, cudaStream_t st, bool ts) {
                     fprintf(stderr, "\n");
                 }
             for (int r = 0; r < 4; ++r) fprintf(stderr, "   %s\n", role[r]);
+            const long long* kt = &tr[(size_t)TC5P_TRACE_IT * 4 * TC5P_NSTAMP];
+            if (kt[0]) fprintf(stderr, "tc5p kernel (CTA 2, %lld tiles in all): start %lld, prologue done %lld, first two tiles stored %lld %lld, producers done %lld %lld, epilogue done %lld, exit %lld\n",
+                               (long long)a.total_tiles, kt[0] - t0, kt[1] - t0, kt[6] - t0, kt[7] - t0, kt[2] - t0, kt[3] - t0, kt[4] - t0, kt[5] - t0);
+            if (kt[0]) fprintf(stderr, "tc5p prologue: first loads issued (warp 0) %lld, TMEM allocated %lld, barrier 1 passed %lld, taps in TMEM %lld\n", kt[8] - t0, kt[9] - t0, kt[10] - t0, kt[11] - t0);
         }
     }
     return RRC_OK;
