@@ -711,15 +711,23 @@ def roofline_of(ctx, W, ms_per_step):
         roofline["kernel"] = f.kernel_name + (" + fused QuadratureDemod epilogue" if op == "fir_demod" else "")
     if op in ("fir", "fir_demod") and f.uses_tensor_cores:
         # Declared: the real-tap c32 FIR runs as a block-scaled fp16x3 Toeplitz product on the tensor cores (fir_tc.cuh).
-        walk = cfg["deci"] in (1, 2, 4) and 7 * cfg["deci"] + cfg["ntaps"] <= 320
-        roofline["kernel"] += " [block-scaled fp16x3 Toeplitz product, mma.m16n8k16 + ldmatrix]"
-        ks = (7 * cfg["deci"] + cfg["ntaps"] + 15) // 16             # k-steps of 16 at 8 outputs per block-row (lower bound)
         nout_fir = W.n_out + (getattr(W, "nchan", 0) if op == "fir_demod" else 0)
-        mmas = 3 * ks * nout_fir / 64                                 # three m16n8k16 per k-step per 64 complex outputs
-        mma_peak = 148 * 0.46 * 1.965e9                               # measured, profiles/r01_microbench_hmma_rate.txt
-        roofline["tensor"] = {"mma_m16n8k16_per_launch": mmas, "achieved_mma_per_s": mmas / (ms_per_step * 1e-3),
-                              "peak_mma_per_s": mma_peak, "frac": mmas / (ms_per_step * 1e-3) / mma_peak,
-                              "peak_source": "measured mma.sync m16n8k16 issue rate, 0.46 per clk per SM (tools/microbench/hmma_rate.cu)"}
+        if "fir_tc5_kernel" in roofline["kernel"]:
+            # tcgen05 path (fir_tc5.cu): 6 MMAs (M128 N64 K16) per k-step per 8192-output tile, K = 127 + ntaps padded to 16
+            ks = (127 + cfg["ntaps"] + 15) // 16
+            mmas = 6 * ks * nout_fir / 8192
+            mma_peak = 148 * 1.965e9 / 32                             # tensor-pipe floor of the shape: 128 * 64 / 256 cycles per MMA
+            roofline["tensor"] = {"tcgen05_mma_m128n64k16_per_launch": mmas, "achieved_mma_per_s": mmas / (ms_per_step * 1e-3),
+                                  "peak_mma_per_s": mma_peak, "frac": mmas / (ms_per_step * 1e-3) / mma_peak,
+                                  "peak_source": "tcgen05 floor max(M,128)*N/256 = 32 cycles per MMA (measured 32.4 in the kernel's trace)"}
+        else:
+            roofline["kernel"] += " [block-scaled fp16x3 Toeplitz product, mma.m16n8k16 + ldmatrix]"
+            ks = (7 * cfg["deci"] + cfg["ntaps"] + 15) // 16         # k-steps of 16 at 8 outputs per block-row (lower bound)
+            mmas = 3 * ks * nout_fir / 64                             # three m16n8k16 per k-step per 64 complex outputs
+            mma_peak = 148 * 0.46 * 1.965e9                           # measured, profiles/r01_microbench_hmma_rate.txt
+            roofline["tensor"] = {"mma_m16n8k16_per_launch": mmas, "achieved_mma_per_s": mmas / (ms_per_step * 1e-3),
+                                  "peak_mma_per_s": mma_peak, "frac": mmas / (ms_per_step * 1e-3) / mma_peak,
+                                  "peak_source": "measured mma.sync m16n8k16 issue rate, 0.46 per clk per SM (tools/microbench/hmma_rate.cu)"}
     # FP32 side of the roofline: algorithmic flops of the reference formulation against the
     # FP32 FMA rate MEASURED on this pool's B200 (tools/microbench/fp32_pipes.cu: 125 lanes/clk/SM).
     if op == "fir_demod":

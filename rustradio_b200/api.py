@@ -403,8 +403,8 @@ class Fir:
 
     @property
     def kernel_name(self) -> str:
-        buf = C.create_string_buffer(200)
-        _ck(lib().rrc_fir_kernel_name(self.h, buf, 200))
+        buf = C.create_string_buffer(320)
+        _ck(lib().rrc_fir_kernel_name(self.h, buf, 320))
         return buf.value.decode()
 
     def out_count(self, n_in: int) -> int:

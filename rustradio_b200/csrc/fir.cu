@@ -699,8 +699,10 @@ struct rrc_fir {
     int tc_ctas_per_sm = 0;      // occupancy of the chosen instantiation (persistent grid), filled at first launch
     void* tc_bfrag = nullptr;
     size_t tc_smem = 0;
-    void* tc5_bimg = nullptr;    // tcgen05 kernel (fir_tc5.cu): swizzled tap operand; set when the filter qualifies
-    int tc5_KS = 0, tc5_base_off = 0;
+    std::vector<unsigned> tc5_tab;   // tcgen05 kernel (fir_tc5.cu): tap words of its TMEM operand; non-empty when the filter qualifies
+    int tc5_KS = 0;
+    long long tc5_min_tiles = 0;     // launches with fewer 8192-output tiles stay on fir_tc1_kernel (pipeline fill, see plan_tc)
+    int last_tc5 = -1;               // what the last launch used: rrc_fir_kernel_name reports it
     Pipe pipe;
 };
 
@@ -733,7 +735,7 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
     h->tc1 = false;
     h->tc_cplx = false;
     if (h->tc_bfrag) { cudaFree(h->tc_bfrag); h->tc_bfrag = nullptr; }
-    if (h->tc5_bimg) { cudaFree(h->tc5_bimg); h->tc5_bimg = nullptr; }
+    h->tc5_tab.clear();
     const size_t T = h->ntaps, D = h->deci;
     if (!h->real_taps || (h->flags & (RRC_FIR_NO_TENSOR | RRC_FIR_FORCE_GENERIC)) || T < 16 || D > 512) return RRC_OK;
     if (const char* e = getenv("RRC_FIR_TENSOR")) if (atoi(e) == 0) return RRC_OK;
@@ -825,46 +827,23 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
             }
     RRC_CUDA(cudaMalloc(&h->tc_bfrag, frag.size() * sizeof(unsigned)));
     RRC_CUDA(upload_sync(h->tc_bfrag, frag.data(), frag.size() * sizeof(unsigned)));
-    // tcgen05 kernel: c32 samples, deci 1, ntaps <= 65 (K = 64 + 64 covers k = n + j <= 63 + 64)
-    int want5 = 0;
+    // tcgen05 kernel (fir_tc5.cu): c32 samples, deci 1, ntaps <= 65 (k = m + j <= 127 + 64 < 192).  One persistent CTA per SM
+    // works through 8192-output tiles behind a three-stage pipeline whose fill costs about two tile times, so it is taken
+    // when a launch gives every SM at least 4 tiles (measured against fir_tc1_kernel: a tie at 3.5, 14 % ahead at 6.9; config 1 has 13.8).
+    // RRC_FIR_TCGEN05: 0 never, 2 always (tests), default by size.
+    int want5 = 1;
     if (const char* e = getenv("RRC_FIR_TCGEN05")) want5 = atoi(e);
     if (want5 && h->cplx && D == 1 && T <= 65) {
-        std::vector<unsigned short> img;
-        if (want5 == 1 || want5 == 2) {                    // samples as the A operand: swizzled Toeplitz image of the taps
-            img.assign(fir_tc5_bimg_bytes() / 2, 0);
-            for (int half = 0; half < 2; ++half)
-                for (int n = 0; n < 64; ++n)
-                    for (int kk = 0; kk < 64; ++kk) {
-                        const float v = Bval(64 * half + kk, n);
-                        const unsigned short vh = f16_rn(v);
-                        img[fir_tc5_bimg_offset(0, half, n, kk) / 2] = vh;
-                        img[fir_tc5_bimg_offset(1, half, n, kk) / 2] = f16_rn(v - f16_to_f32(vh));
-                    }
-            h->tc5_KS = (int)((63 + T + 15) / 16);
-        } else {                                           // taps in TMEM: table of the scaled taps' fp16 parts at index j + 128
-            // fp16x2 words of the scaled taps: [part hi / lo][alignment even / odd][q + 64], E[q] = (w[2q], w[2q + 1]),
-            // O[q] = (w[2q + 1], w[2q + 2]), zero outside the taps: lane m of the TMEM operand reads 96 consecutive words
-            const size_t tab = fir_tc5_tab_entries();
-            img.assign(2 * 2 * tab * 2, 0);
-            auto part16 = [&](long long j, int part) -> unsigned short {
-                if (j < 0 || j >= (long long)T) return 0;
-                const float v = Bval(j, 0);
-                const unsigned short vh = f16_rn(v);
-                return part == 0 ? vh : f16_rn(v - f16_to_f32(vh));
-            };
-            for (int part = 0; part < 2; ++part)
-                for (int odd = 0; odd < 2; ++odd)
-                    for (size_t i = 0; i < tab; ++i) {
-                        const long long q = (long long)i - 64;
-                        img[2 * ((part * 2 + odd) * tab + i)] = part16(2 * q + odd, part);
-                        img[2 * ((part * 2 + odd) * tab + i) + 1] = part16(2 * q + odd + 1, part);
-                    }
-            h->tc5_KS = (int)((127 + T + 15) / 16);
+        std::vector<unsigned short> hi(T), lo(T);
+        for (size_t j = 0; j < T; ++j) {
+            const float v = Bval((long long)j, 0);
+            hi[j] = f16_rn(v);
+            lo[j] = f16_rn(v - f16_to_f32(hi[j]));
         }
-        RRC_CUDA(cudaMalloc(&h->tc5_bimg, img.size() * 2));
-        RRC_CUDA(upload_sync(h->tc5_bimg, img.data(), img.size() * 2));
-        h->tc5_base_off = 0;
-        if (const char* e = getenv("RRC_FIR_TC5_BASE_OFF")) h->tc5_base_off = atoi(e) & 7;
+        h->tc5_tab.assign(fir_tc5_tab_words(), 0u);
+        fir_tc5_build_tab(hi.data(), lo.data(), T, h->tc5_tab.data());
+        h->tc5_KS = (int)((127 + T + 15) / 16);
+        h->tc5_min_tiles = want5 == 2 ? 0 : 4ll * sm_count(h->device);
     }
     return RRC_OK;
 }
@@ -1161,19 +1140,21 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         t.total_tiles = t.tiles_x * (long long)nchan;
         if (t.total_tiles > 0x7fffffffll) return fail(RRC_ERR_INVALID, "fir: %lld tiles in one launch (limit 2^31 - 1)", t.total_tiles);
         RRC_TRY(fir_tcf_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0, (int)h->deci}, t, st));
-    } else if (use_tc && h->tc5_bimg && !demod && !h->in_u8) {
+    } else if (use_tc && !h->tc5_tab.empty() && !demod && !h->in_u8 &&
+               (long long)((out_n + FIR_TC5_BT - 1) / FIR_TC5_BT) * (long long)nchan >= h->tc5_min_tiles) {
         FirTc5Args t{};
         t.in = reinterpret_cast<const float2*>(in); t.out = reinterpret_cast<float2*>(out);
-        t.bimg = reinterpret_cast<const uint4*>(h->tc5_bimg);
         t.in_stride = (long long)in_stride; t.out_stride = (long long)out_stride;
         t.need = (long long)need; t.out_n = (long long)out_n;
-        t.KS = h->tc5_KS; t.base_off = h->tc5_base_off; t.tap_inv_scale = h->tc_tap_inv_scale;
+        t.KS = h->tc5_KS; t.tap_inv_scale = h->tc_tap_inv_scale;
         t.tiles_x = (long long)((out_n + FIR_TC5_BT - 1) / FIR_TC5_BT);
         t.total_tiles = t.tiles_x * (long long)nchan;
-        RRC_TRY(fir_tc5_launch(h->device, t, st));
+        RRC_TRY(fir_tc5_launch(h->device, t, h->tc5_tab.data(), st));
+        h->last_tc5 = 1;
     } else if (use_tc && h->tc1) {
         const size_t work = demod ? out_n - 1 : out_n;
         if (work == 0) return RRC_OK;
+        h->last_tc5 = 0;
         FirTc1Args t{};
         t.in = reinterpret_cast<const float2*>(in); t.out = out;
         t.bfrag = reinterpret_cast<const uint4*>(h->tc_bfrag);
@@ -1322,7 +1303,6 @@ int rrc_fir_destroy(rrc_fir_t* h) {
     if (h->taps_poly) cudaFree(h->taps_poly);
     if (h->taps_rev) cudaFree(h->taps_rev);
     if (h->tc_bfrag) cudaFree(h->tc_bfrag);
-    if (h->tc5_bimg) cudaFree(h->tc5_bimg);
     h->pipe.destroy();
     delete h;
     return RRC_OK;
@@ -1357,10 +1337,12 @@ int rrc_fir_set_epilogue(rrc_fir_t* h, int kind, float re, float im) {
 int rrc_fir_kernel_name(const rrc_fir_t* h, char* buf, size_t buflen) {
     if (!h || !buf || !buflen) return fail(RRC_ERR_INVALID, "null argument");
     const bool use_tc = h->tc && (h->tc_cplx || !h->translate) && h->epi.kind == RRC_EPI_NONE;
-    char tmp[160];
+    char tmp[320];
     if (use_tc && h->tc_cplx) snprintf(tmp, sizeof tmp, "fir_tcc_kernel<KS=%d,D=%zu> (tensor cores, complex taps, fp16x3)", h->tc_KS, h->deci);
     else if (use_tc && !h->cplx) snprintf(tmp, sizeof tmp, "fir_tcf_kernel<KS=%d,D=%zu> (tensor cores, f32 stream, fp16x3)", h->tc_KS, h->deci);
-    else if (use_tc && h->tc5_bimg && !h->in_u8) snprintf(tmp, sizeof tmp, "fir_tc5_kernel<KS=%d> (tcgen05.mma kind::f16, TMEM accumulators, real taps, fp16x3; fused demod falls to fir_tc1_kernel)", h->tc5_KS);
+    else if (use_tc && !h->tc5_tab.empty() && !h->in_u8 && h->last_tc5 != 0)
+        snprintf(tmp, sizeof tmp, "fir_tc5_kernel<KS=%d> (tcgen05.mma kind::f16 M128 N64 K16, taps and accumulators in TMEM, fp16x3)%s", h->tc5_KS,
+                 h->last_tc5 == 1 ? "" : "; launches below 4 tiles of 8192 outputs per SM and the fused demod use fir_tc1_kernel (mma.sync)");
     else if (use_tc && h->tc1) snprintf(tmp, sizeof tmp, "fir_tc1_kernel<KS=%d,D=%zu> (tensor cores, real taps, fp16x3)", h->tc_KS, h->deci);
     else if (use_tc) snprintf(tmp, sizeof tmp, "fir_tc_kernel<NTILE=%d,NLD=%d> (tensor cores, real taps, fp16x3)", h->tc_ntile, h->tc_nld);
     else if (h->rtu_qb) snprintf(tmp, sizeof tmp, "fir_rtu_kernel<D=%zu,QB=%d,R=%d> (FFMA2, taps as uniform-register operands from the kernel parameters)", h->deci, h->rtu_qb, h->rtu_r);

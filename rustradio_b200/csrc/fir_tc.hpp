@@ -64,14 +64,12 @@ struct FirTccArgs {             // fir_tcc_kernel: c32 samples, complex taps (tr
     unsigned long long out_base;
 };
 
-struct FirTc5Args {             // fir_tc5_kernel (tcgen05 / TMEM): c32 samples, real taps, deci 1, ntaps <= 65
+struct FirTc5Args {             // fir_tc5_kernel (tcgen05 / TMEM, fir_tc5.cu): c32 samples, real taps, deci 1, ntaps <= 65
     const float2* in;
     float2* out;
-    const uint4* bimg;         // swizzled shared-memory image of the Toeplitz tap operand (fir_tc5_bimg_offset)
     long long in_stride, out_stride, need, out_n;
     long long tiles_x, total_tiles;
-    int KS;                    // k-steps of 16: ceil((63 + ntaps) / 16) <= 8 (samples as A), ceil((127 + ntaps) / 16) <= 12 (taps in TMEM)
-    int base_off;              // matrix-descriptor base offset of the operand advanced by one 128-byte row
+    int KS;                    // k-steps of 16: ceil((127 + ntaps) / 16) <= 12
     float tap_inv_scale;
 };
 
@@ -92,9 +90,8 @@ int fir_tc_launch(const FirTcGeom& g, const FirTcArgs& a, bool demod, cudaStream
 int fir_tc1_launch(const FirTcGeom& g, const FirTc1Args& a, bool demod, cudaStream_t st);
 int fir_tcf_launch(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st);
 int fir_tcc_launch(const FirTcGeom& g, const FirTccArgs& a, bool demod, cudaStream_t st);
-size_t fir_tc5_bimg_bytes();
-size_t fir_tc5_tab_entries();     // tap-stationary kernel: fp16 tap table entries per part, index (k - m) + 128
-size_t fir_tc5_bimg_offset(int part, int half, int n, int kk);
-int fir_tc5_launch(int device, const FirTc5Args& a, cudaStream_t st);
+size_t fir_tc5_tab_words();       // words of the tap table fir_tc5_build_tab fills (kernel parameter of fir_tc5_kernel)
+void fir_tc5_build_tab(const unsigned short* hi, const unsigned short* lo, size_t ntaps, unsigned* tab);
+int fir_tc5_launch(int device, const FirTc5Args& a, const unsigned* tab_host, cudaStream_t st);
 
 }  // namespace rrc

@@ -154,12 +154,13 @@ def test_fir_tensor_core_walk_kernel(R, monkeypatch, ntaps, deci, n, nchan):
 
 @pytest.mark.parametrize("ntaps,n,nchan", [
     (64, 262_144, 1), (65, 8_256, 1), (64, 64, 1), (16, 5_000, 2), (33, 70_001, 1), (64, 1_300, 5), (48, 16_415, 3),
-    (65, 3 * 8192 + 64, 2), (17, 600, 1), (40, 100_000, 2)])
+    (65, 3 * 8192 + 64, 2), (17, 600, 1), (40, 100_000, 2), (64, 8192 * 171 + 77, 2), (33, 8192 * 300 + 5000, 1)])
 def test_fir_tcgen05_kernel(R, monkeypatch, ntaps, n, nchan):
-    """fir_tc5_kernel (tcgen05.mma + TMEM; c32 samples, real taps, deci 1, ntaps <= 65), selected with RRC_FIR_TCGEN05=1:
+    """fir_tc5_kernel (tcgen05.mma, taps and accumulators in TMEM; c32 samples, real taps, deci 1, ntaps <= 65), forced
+    for every launch size with RRC_FIR_TCGEN05=2 (by default launches below 4 tiles per SM stay on fir_tc1_kernel):
     ragged last tiles, tiles shorter than one 8192-output CTA tile, odd channel strides (8-byte aligned channels take the
-    scalar loads / stores), several k-step counts.  Same bar as the mma.sync kernels."""
-    monkeypatch.setenv("RRC_FIR_TCGEN05", "1")
+    scalar loads), several k-step counts, more and fewer tiles than CTAs.  Same bar as the mma.sync kernels."""
+    monkeypatch.setenv("RRC_FIR_TCGEN05", "2")
     taps = O.low_pass_n(1.0, 0.2, ntaps).astype(np.complex64)
     f = R.Fir(taps)
     assert f.uses_tensor_cores and "fir_tc5_kernel" in f.kernel_name
@@ -173,6 +174,7 @@ def test_fir_tcgen05_kernel(R, monkeypatch, ntaps, n, nchan):
     ostride = out_n + 1 - (out_n % 2)
     dy = R.DeviceBuffer(nchan * ostride * 8)
     f.run_batch(din, stride, need, dy, ostride, out_n, nchan)
+    assert f.kernel_name.startswith("fir_tc5_kernel") and "fir_tc1" not in f.kernel_name    # the launch took the tcgen05 kernel
     y = dy.download(np.complex64, nchan * ostride).reshape(nchan, ostride)[:, :out_n]
     for c in range(nchan):
         truth = O.fir(xs[c, :n], taps, 1, f64=True)
@@ -181,19 +183,21 @@ def test_fir_tcgen05_kernel(R, monkeypatch, ntaps, n, nchan):
         assert e <= 2e-6
     # the fused demod is not implemented on this kernel: it must still be right (falls to fir_tc1_kernel)
     dd = R.DeviceBuffer(nchan * ostride * 4)
-    f.demod_run_batch(din, stride, need, 0.7, dd, ostride, out_n, nchan)
-    d = dd.download(np.float32, nchan * ostride).reshape(nchan, ostride)[:, :out_n - 1]
-    truth = O.fir(xs[0, :n], taps, 1, f64=True)
-    assert O.max_angle_err(d[0] / 0.7, np.angle(truth[1:] * np.conj(truth[:-1]))) <= DEMOD_BAR
+    if out_n > 1:
+        f.demod_run_batch(din, stride, need, 0.7, dd, ostride, out_n, nchan)
+        assert f.kernel_name.startswith("fir_tc1_kernel")
+        d = dd.download(np.float32, nchan * ostride).reshape(nchan, ostride)[:, :out_n - 1]
+        truth = O.fir(xs[0, :n], taps, 1, f64=True)
+        assert O.max_angle_err(d[0] / 0.7, np.angle(truth[1:] * np.conj(truth[:-1]))) <= DEMOD_BAR
 
 
 @pytest.mark.parametrize("scale", [1e-20, 1.0, 3e18])
 @pytest.mark.parametrize("bad", [None, np.inf, np.nan])
 def test_fir_tcgen05_block_scaling_and_non_finite(R, monkeypatch, scale, bad):
     """The CTA-tile power-of-two scale keeps FP32-class accuracy at any signal level; one Inf / NaN sample makes the
-    outputs whose window holds it non-finite plus, at most, the rest of the two 64-output block-rows whose 128-sample
+    outputs whose window holds it non-finite plus, at most, the rest of the two 128-output block-rows whose 192-sample
     operand rows contain it (zero-padded Toeplitz taps meet it as 0 * Inf); everything else keeps the bar."""
-    monkeypatch.setenv("RRC_FIR_TCGEN05", "1")
+    monkeypatch.setenv("RRC_FIR_TCGEN05", "2")
     n, ntaps, pos = 30_000, 64, 12_345
     taps = O.low_pass_n(1.0, 0.1, ntaps).astype(np.complex64)
     x = (O.synth_c32(61, 0, n) * np.float32(scale)).astype(np.complex64)
@@ -208,7 +212,7 @@ def test_fir_tcgen05_block_scaling_and_non_finite(R, monkeypatch, scale, bad):
     if bad is not None:
         xz[pos] = 0
         touched = (o > pos - ntaps) & (o <= pos)
-        far = (o < 64 * (pos // 64 - 1)) | (o >= 64 * (pos // 64 + 1))
+        far = (o < 128 * (pos // 128 - 1)) | (o >= 128 * (pos // 128 + 1))       # block-rows of 128 outputs read 192 samples
         assert not np.isfinite(y[touched]).any()
     assert np.isfinite(y[far]).all()
     truth = O.fir(xz, taps, 1, f64=True)
@@ -756,7 +760,11 @@ def test_fir_config1_full_size(R):
     assert n_out == 16_777_153
     dout = R.DeviceBuffer(n_out * 8)
     f.run(din, n, dout, n_out)
+    assert f.kernel_name.startswith("fir_tc5_kernel")          # 2048 tiles >= 4 per SM: the tcgen05 kernel by default
     assert _spot_check_fir(R, din, dout, n_out, taps, 1, seed, n) <= REL_RMS_BAR
+    small = R.Fir(taps)
+    small.filter(O.synth_c32(3, 0, 100_000))
+    assert small.kernel_name.startswith("fir_tc1_kernel")      # 13 tiles: the mma.sync walk kernel
     # the device generator and the oracle generator are the same function
     h = din.download(np.complex64, 4096)
     assert np.array_equal(h, O.synth_c32(seed, 0, 4096))
