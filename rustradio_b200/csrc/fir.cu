@@ -829,7 +829,8 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
     RRC_CUDA(upload_sync(h->tc_bfrag, frag.data(), frag.size() * sizeof(unsigned)));
     // tcgen05 kernel (fir_tc5.cu): c32 samples, deci 1, ntaps <= 65 (k = m + j <= 127 + 64 < 192).  One persistent CTA per SM
     // works through 8192-output tiles behind a three-stage pipeline whose fill costs about two tile times, so it is taken
-    // when a launch gives every SM at least 4 tiles (measured against fir_tc1_kernel: a tie at 3.5, 14 % ahead at 6.9; config 1 has 13.8).
+    // when a launch gives every SM at least 3 tiles of 8192 outputs (measured against fir_tc1_kernel: 13 % ahead at 3.5, 16 % at 6.9,
+    // 10 % at config 1's 13.8); below about 12 per SM the tiles are 4096 outputs (fir_tc5_rows).
     // RRC_FIR_TCGEN05: 0 never, 2 always (tests), default by size.
     int want5 = 1;
     if (const char* e = getenv("RRC_FIR_TCGEN05")) want5 = atoi(e);
@@ -843,7 +844,7 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
         h->tc5_tab.assign(fir_tc5_tab_words(), 0u);
         fir_tc5_build_tab(hi.data(), lo.data(), T, h->tc5_tab.data());
         h->tc5_KS = (int)((127 + T + 15) / 16);
-        h->tc5_min_tiles = want5 == 2 ? 0 : 4ll * sm_count(h->device);
+        h->tc5_min_tiles = want5 == 2 ? 0 : 3ll * sm_count(h->device);
     }
     return RRC_OK;
 }
@@ -1141,13 +1142,15 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         if (t.total_tiles > 0x7fffffffll) return fail(RRC_ERR_INVALID, "fir: %lld tiles in one launch (limit 2^31 - 1)", t.total_tiles);
         RRC_TRY(fir_tcf_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0, (int)h->deci}, t, st));
     } else if (use_tc && !h->tc5_tab.empty() && !demod && !h->in_u8 &&
-               (long long)((out_n + FIR_TC5_BT - 1) / FIR_TC5_BT) * (long long)nchan >= h->tc5_min_tiles) {
+               (long long)((out_n + 8191) / 8192) * (long long)nchan >= h->tc5_min_tiles) {
         FirTc5Args t{};
         t.in = reinterpret_cast<const float2*>(in); t.out = reinterpret_cast<float2*>(out);
         t.in_stride = (long long)in_stride; t.out_stride = (long long)out_stride;
         t.need = (long long)need; t.out_n = (long long)out_n;
         t.KS = h->tc5_KS; t.tap_inv_scale = h->tc_tap_inv_scale;
-        t.tiles_x = (long long)((out_n + FIR_TC5_BT - 1) / FIR_TC5_BT);
+        t.nr = fir_tc5_rows((long long)((out_n + 8191) / 8192) * (long long)nchan, h->device);
+        const size_t bt5 = (size_t)128 * t.nr;
+        t.tiles_x = (long long)((out_n + bt5 - 1) / bt5);
         t.total_tiles = t.tiles_x * (long long)nchan;
         RRC_TRY(fir_tc5_launch(h->device, t, h->tc5_tab.data(), st));
         h->last_tc5 = 1;
@@ -1342,7 +1345,7 @@ int rrc_fir_kernel_name(const rrc_fir_t* h, char* buf, size_t buflen) {
     else if (use_tc && !h->cplx) snprintf(tmp, sizeof tmp, "fir_tcf_kernel<KS=%d,D=%zu> (tensor cores, f32 stream, fp16x3)", h->tc_KS, h->deci);
     else if (use_tc && !h->tc5_tab.empty() && !h->in_u8 && h->last_tc5 != 0)
         snprintf(tmp, sizeof tmp, "fir_tc5_kernel<KS=%d> (tcgen05.mma kind::f16 M128 N64 K16, taps and accumulators in TMEM, fp16x3)%s", h->tc5_KS,
-                 h->last_tc5 == 1 ? "" : "; launches below 4 tiles of 8192 outputs per SM and the fused demod use fir_tc1_kernel (mma.sync)");
+                 h->last_tc5 == 1 ? "" : "; launches below 3 tiles of 8192 outputs per SM and the fused demod use fir_tc1_kernel (mma.sync)");
     else if (use_tc && h->tc1) snprintf(tmp, sizeof tmp, "fir_tc1_kernel<KS=%d,D=%zu> (tensor cores, real taps, fp16x3)", h->tc_KS, h->deci);
     else if (use_tc) snprintf(tmp, sizeof tmp, "fir_tc_kernel<NTILE=%d,NLD=%d> (tensor cores, real taps, fp16x3)", h->tc_ntile, h->tc_nld);
     else if (h->rtu_qb) snprintf(tmp, sizeof tmp, "fir_rtu_kernel<D=%zu,QB=%d,R=%d> (FFMA2, taps as uniform-register operands from the kernel parameters)", h->deci, h->rtu_qb, h->rtu_r);

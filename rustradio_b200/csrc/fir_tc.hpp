@@ -68,13 +68,13 @@ struct FirTc5Args {             // fir_tc5_kernel (tcgen05 / TMEM, fir_tc5.cu): 
     const float2* in;
     float2* out;
     long long in_stride, out_stride, need, out_n;
-    long long tiles_x, total_tiles;
+    long long tiles_x, total_tiles;   // tiles of 128 * nr outputs per channel / in the launch
+    int nr;                    // block-rows per tile: 32 or 64 (fir_tc5_rows)
     int KS;                    // k-steps of 16: ceil((127 + ntaps) / 16) <= 12
     float tap_inv_scale;
 };
 
 constexpr int FIR_TC_THREADS = 256;
-constexpr int FIR_TC5_BT = 8192;           // outputs per CTA tile of fir_tc5_kernel
 constexpr int FIR_TC1_BT = 512;            // INPUT samples a warp tile of fir_tc1_kernel advances by: 512/deci outputs
 constexpr int FIR_TCF_IN = 1024;           // INPUT samples a warp tile of fir_tcf_kernel (f32 streams) advances by
 constexpr int FIR_TC1_MAX_KS = 20;         // deci 1/2/4 kernel: up to 20 k-steps of 16 samples, i.e. 7*deci + ntaps <= 320
@@ -92,6 +92,7 @@ int fir_tcf_launch(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st);
 int fir_tcc_launch(const FirTcGeom& g, const FirTccArgs& a, bool demod, cudaStream_t st);
 size_t fir_tc5_tab_words();       // words of the tap table fir_tc5_build_tab fills (kernel parameter of fir_tc5_kernel)
 void fir_tc5_build_tab(const unsigned short* hi, const unsigned short* lo, size_t ntaps, unsigned* tab);
+int fir_tc5_rows(long long tiles8192, int device);   // block-rows of 128 outputs per CTA tile for a launch of that size: 32 or 64
 int fir_tc5_launch(int device, const FirTc5Args& a, const unsigned* tab_host, cudaStream_t st);
 
 }  // namespace rrc

@@ -39,16 +39,20 @@
 namespace rrc {
 namespace {
 
-constexpr int TC5_HROWS = 129;                      // staged half-rows of 64 samples: 8192 + 64
-constexpr int TC5_REGION = 9 * 1024;                // 65 rows x 128 B, rounded up to the 1024-byte atom
-constexpr int TC5_PLANE = 2 * TC5_REGION;           // one component (re / im), one part (hi / lo)
+// NR = block-rows (of 128 outputs) per CTA tile: 64 (8192 outputs) or 32 (4096: half the pipeline fill)
 constexpr int TC5_NPW = 9;                          // warps per producer group
-constexpr int TC5_NLD = (TC5_HROWS + TC5_NPW - 1) / TC5_NPW;     // half-rows (float4 loads) per producer lane
+template <int NR> struct Tc5Geom {
+    static constexpr int BT = 128 * NR;             // outputs per tile
+    static constexpr int HROWS = 2 * NR + 1;        // staged half-rows of 64 samples: BT + 64
+    static constexpr int REGION = ((NR + 1) * 128 + 1023) / 1024 * 1024;      // NR + 1 rows x 128 B, rounded up to the atom
+    static constexpr int PLANE = 2 * REGION;        // one component (re / im), one part (hi / lo)
+    static constexpr int NLD = (HROWS + TC5_NPW - 1) / TC5_NPW;               // half-rows (float4 loads) per producer lane
+    static constexpr size_t SMEM = 1024 + 8 * PLANE + 4096;
+    static constexpr unsigned IDESC = 0x08000010u | ((unsigned)(NR >> 3) << 17);   // kind::f16: D f32, A/B f16 K-major, N = NR, M = 128
+};
 constexpr int TC5_EPI0 = 2 * TC5_NPW, TC5_MMAW = TC5_EPI0 + 4;
 constexpr int TC5_THREADS = (TC5_MMAW + 1) * 32;    // two producer groups, 4 epilogue warps, 1 MMA warp
 constexpr int TC5_TAB = 160;                        // fp16x2 words per tap table (even / odd alignment, hi / lo part)
-constexpr size_t TC5_SMEM = 1024 + 8 * TC5_PLANE + 4096;
-constexpr unsigned TC5_IDESC = 0x08100010u;         // kind::f16: D f32, A/B f16 K-major, N = 64 (>>3 at bit 17), M = 128 (>>4 at bit 24)
 // Shared-memory matrix descriptor, SWIZZLE_128B K-major (cute/arch/mma_sm100_desc.hpp): start address >> 4 at [0,14),
 // LBO (unused: the K extent of an MMA stays inside the atom) = 1 at [16,30), SBO = 1024 B >> 4 at [32,46), version 1 at
 // [46,48), base offset 0 at [49,52), layout type 2 at [61,64).
@@ -63,12 +67,12 @@ struct alignas(16) Tc5Params {                      // kernel parameters: the ta
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned tc5_desc_lo(unsigned addr) { return ((addr >> 4) & 0x3fffu) | (1u << 16); }
 
-__device__ __forceinline__ void tc5_mma_ts(unsigned d_tmem, unsigned a_tmem, unsigned b_lo, unsigned accumulate) {
+__device__ __forceinline__ void tc5_mma_ts(unsigned d_tmem, unsigned a_tmem, unsigned b_lo, unsigned accumulate, unsigned idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "mov.b64 db, {%2, %5};\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
-        :: "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(TC5_IDESC), "r"(accumulate), "r"(TC5_DESC_HI) : "memory");
+        :: "r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(TC5_DESC_HI) : "memory");
 }
 __device__ __forceinline__ void tc5_ld32(unsigned taddr, unsigned (&r)[16]) {
     asm volatile(
@@ -113,9 +117,11 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {      // read onc
 }
 
 // Tile loads: half-row (pw + 9 u) of the tile, samples 2*lane, 2*lane + 1 of it.  Samples at or past `need` are zeros.
-__device__ __forceinline__ void tc5_load(const FirTc5Args& a, long long tile, int pw, int lane, float4 (&v)[TC5_NLD]) {
+template <int NR>
+__device__ __forceinline__ void tc5_load(const FirTc5Args& a, long long tile, int pw, int lane, float4 (&v)[Tc5Geom<NR>::NLD]) {
+    constexpr int TC5_HROWS = Tc5Geom<NR>::HROWS, TC5_NLD = Tc5Geom<NR>::NLD;
     const long long ch = tile / a.tiles_x, tx = tile - ch * a.tiles_x;
-    const long long s0 = tx * FIR_TC5_BT;
+    const long long s0 = tx * Tc5Geom<NR>::BT;
     const float2* in = a.in + ch * a.in_stride + s0;
     const long long avail = a.need - s0;
     const bool fast = avail >= 64ll * TC5_HROWS && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
@@ -142,7 +148,10 @@ __device__ __forceinline__ void tc5_load(const FirTc5Args& a, long long tile, in
 // RRC_FIR_TC5_TRACE (debug): CTA 2 stamps clock64 per role for its tiles 2..7, plus whole-kernel stamps
 #define TC5_STAMP(role, k) do { if (trace && blockIdx.x == 2 && j >= 2 && j < 2 + TC5_TRACE_IT && lane == 0) trace[((j - 2) * 4 + (role)) * TC5_NSTAMP + (k)] = clock64(); } while (0)
 
+template <int NR>
 __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_constant__ Tc5Params prm, long long* __restrict__ trace) {
+    constexpr int TC5_HROWS = Tc5Geom<NR>::HROWS, TC5_NLD = Tc5Geom<NR>::NLD, TC5_REGION = Tc5Geom<NR>::REGION, TC5_PLANE = Tc5Geom<NR>::PLANE;
+    constexpr int FIR_TC5_BT = Tc5Geom<NR>::BT;
     extern __shared__ unsigned char smem_raw[];
     const FirTc5Args& a = prm.a;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -216,7 +225,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
         const int g = warp >= TC5_NPW ? 1 : 0, pw = warp - g * TC5_NPW;
         float4 v[TC5_NLD];
         if (g == 1) mbar_wait(lead_u, 0u);              // the CTA's first tile is requested first: it heads the pipeline
-        if (g < njobs) tc5_load(a, first + (long long)g * gridDim.x, pw, lane, v);
+        if (g < njobs) tc5_load<NR>(a, first + (long long)g * gridDim.x, pw, lane, v);
         if (g == 0) mbar_arrive(lead_u);
         if (ktr && warp == 0 && lane == 0) ktr[8] = clock64();
         unsigned char* planes = s_planes + g * 4 * TC5_PLANE;
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");              // generic-proxy stores -> visible to the tensor core's reads
             mbar_arrive(full_u + 8 * g);
             TC5_STAMP(g, 3);
-            if (j + 2 < njobs) tc5_load(a, first + (long long)(j + 2) * gridDim.x, pw, lane, v);
+            if (j + 2 < njobs) tc5_load<NR>(a, first + (long long)(j + 2) * gridDim.x, pw, lane, v);
             TC5_STAMP(g, 4);
         }
         if (ktr && lane == 0 && pw == 0) ktr[2 + g] = clock64();
@@ -300,11 +309,11 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
             const long long cnt = a.out_n - o0 - (32 * q + lane);                   // this lane's output of block-row n exists for 128 n < cnt
             const bool fast = a.out_n - o0 >= FIR_TC5_BT;
 #pragma unroll 1
-            for (int part = 0; part < 4; ++part) {
+            for (int part = 0; part < NR / 16; ++part) {
                 unsigned re[16], im[16];
-                const unsigned taddr = tmem + 256u + 128u * g + ((unsigned)(32 * q) << 16) + 16u * part;
+                const unsigned taddr = tmem + 256u + 2u * NR * g + ((unsigned)(32 * q) << 16) + 16u * part;
                 tc5_ld32(taddr, re);
-                tc5_ld32(taddr + 64u, im);
+                tc5_ld32(taddr + NR, im);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
@@ -332,7 +341,8 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tc5_elect()) {
                 const unsigned pb = tc5_desc_lo(planes_u + (unsigned)g * 4u * TC5_PLANE);
-                const unsigned d = tmem + 256u + 128u * (unsigned)g;
+                const unsigned d = tmem + 256u + 2u * NR * (unsigned)g;
+                constexpr unsigned idesc = Tc5Geom<NR>::IDESC;
 #pragma unroll
                 for (int s = 0; s < 12; ++s) {
                     if (s < a.KS) {
@@ -341,12 +351,12 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
                         const unsigned xb = pb + (kb == 1 ? RG16 : 0u) + (kb == 2 ? 8u : 0u) + ((unsigned)s & 3u) * 2u;
                         const unsigned a_hi = tmem + 8u * s, a_lo = a_hi + 96u;
                         const unsigned acc = s ? 1u : 0u;
-                        tc5_mma_ts(d, a_hi, xb, acc);                       // re: taps hi * samples hi
-                        tc5_mma_ts(d + 64u, a_hi, xb + 2 * PL16, acc);      // im
-                        tc5_mma_ts(d, a_hi, xb + PL16, 1u);                 // taps hi * samples lo
-                        tc5_mma_ts(d + 64u, a_hi, xb + 3 * PL16, 1u);
-                        tc5_mma_ts(d, a_lo, xb, 1u);                        // taps lo * samples hi
-                        tc5_mma_ts(d + 64u, a_lo, xb + 2 * PL16, 1u);
+                        tc5_mma_ts(d, a_hi, xb, acc, idesc);                       // re: taps hi * samples hi
+                        tc5_mma_ts(d + NR, a_hi, xb + 2 * PL16, acc, idesc);       // im
+                        tc5_mma_ts(d, a_hi, xb + PL16, 1u, idesc);                 // taps hi * samples lo
+                        tc5_mma_ts(d + NR, a_hi, xb + 3 * PL16, 1u, idesc);
+                        tc5_mma_ts(d, a_lo, xb, 1u, idesc);                        // taps lo * samples hi
+                        tc5_mma_ts(d + NR, a_lo, xb + 2 * PL16, 1u, idesc);
                     }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(done_u + 8 * g) : "memory");
@@ -378,11 +388,21 @@ void fir_tc5_build_tab(const unsigned short* hi, const unsigned short* lo, size_
             }
 }
 
+// Block-rows per CTA tile for a launch of `tiles8192` tiles of 8192 outputs: 32-row tiles (4096 outputs) halve the pipeline
+// fill (first tile stored after 10 K instead of 17 K cycles) and cost 4 % in the steady state (measured):
+// ahead below about 12 tiles per SM, behind above.  RRC_FIR_TC5_NR = 32 / 64 overrides (experiments).
+int fir_tc5_rows(long long tiles8192, int device) {
+    if (const char* e = getenv("RRC_FIR_TC5_NR")) { const int v = atoi(e); if (v == 32 || v == 64) return v; }
+    return tiles8192 < 12ll * sm_count(device) ? 32 : 64;
+}
+
 int fir_tc5_launch(int device, const FirTc5Args& a, const unsigned* tab_host, cudaStream_t st) {
     static bool ready[16] = {};
     const int dv = (device < 0 || device >= 16) ? 0 : device;
+    const bool nr32 = a.nr == 32;
     if (!ready[dv]) {
-        RRC_CUDA(cudaFuncSetAttribute(fir_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC5_SMEM));
+        RRC_CUDA(cudaFuncSetAttribute(fir_tc5_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Geom<64>::SMEM));
+        RRC_CUDA(cudaFuncSetAttribute(fir_tc5_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Geom<32>::SMEM));
         ready[dv] = true;
     }
     Tc5Params prm;
@@ -392,7 +412,8 @@ int fir_tc5_launch(int device, const FirTc5Args& a, const unsigned* tab_host, cu
     long long* dtrace = nullptr;
     if (want_trace) { RRC_CUDA(cudaMalloc((void**)&dtrace, TC5_TRACE_WORDS * 8)); RRC_CUDA(cudaMemsetAsync(dtrace, 0, TC5_TRACE_WORDS * 8, st)); }
     const unsigned grid = (unsigned)std::min<long long>(a.total_tiles, sm_count(device));
-    fir_tc5_kernel<<<grid, TC5_THREADS, TC5_SMEM, st>>>(prm, dtrace);
+    if (nr32) fir_tc5_kernel<32><<<grid, TC5_THREADS, Tc5Geom<32>::SMEM, st>>>(prm, dtrace);
+    else fir_tc5_kernel<64><<<grid, TC5_THREADS, Tc5Geom<64>::SMEM, st>>>(prm, dtrace);
     RRC_CHECK_LAUNCH();
     count_launch();
     if (want_trace) {                                           // debug only: CTA 2's stamps, cycles relative to the earliest one

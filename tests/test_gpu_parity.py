@@ -155,12 +155,14 @@ def test_fir_tensor_core_walk_kernel(R, monkeypatch, ntaps, deci, n, nchan):
 @pytest.mark.parametrize("ntaps,n,nchan", [
     (64, 262_144, 1), (65, 8_256, 1), (64, 64, 1), (16, 5_000, 2), (33, 70_001, 1), (64, 1_300, 5), (48, 16_415, 3),
     (65, 3 * 8192 + 64, 2), (17, 600, 1), (40, 100_000, 2), (64, 8192 * 171 + 77, 2), (33, 8192 * 300 + 5000, 1)])
-def test_fir_tcgen05_kernel(R, monkeypatch, ntaps, n, nchan):
+@pytest.mark.parametrize("rows", [32, 64])
+def test_fir_tcgen05_kernel(R, monkeypatch, ntaps, n, nchan, rows):
     """fir_tc5_kernel (tcgen05.mma, taps and accumulators in TMEM; c32 samples, real taps, deci 1, ntaps <= 65), forced
-    for every launch size with RRC_FIR_TCGEN05=2 (by default launches below 4 tiles per SM stay on fir_tc1_kernel):
+    for every launch size with RRC_FIR_TCGEN05=2 (by default launches below 3 tiles of 8192 outputs per SM stay on fir_tc1_kernel; tiles are 4096 outputs below 12 per SM, 8192 above):
     ragged last tiles, tiles shorter than one 8192-output CTA tile, odd channel strides (8-byte aligned channels take the
     scalar loads), several k-step counts, more and fewer tiles than CTAs.  Same bar as the mma.sync kernels."""
     monkeypatch.setenv("RRC_FIR_TCGEN05", "2")
+    monkeypatch.setenv("RRC_FIR_TC5_NR", str(rows))                # both tile heights at every size (default: by launch size)
     taps = O.low_pass_n(1.0, 0.2, ntaps).astype(np.complex64)
     f = R.Fir(taps)
     assert f.uses_tensor_cores and "fir_tc5_kernel" in f.kernel_name
@@ -193,11 +195,13 @@ def test_fir_tcgen05_kernel(R, monkeypatch, ntaps, n, nchan):
 
 @pytest.mark.parametrize("scale", [1e-20, 1.0, 3e18])
 @pytest.mark.parametrize("bad", [None, np.inf, np.nan])
-def test_fir_tcgen05_block_scaling_and_non_finite(R, monkeypatch, scale, bad):
+@pytest.mark.parametrize("rows", [32, 64])
+def test_fir_tcgen05_block_scaling_and_non_finite(R, monkeypatch, scale, bad, rows):
     """The CTA-tile power-of-two scale keeps FP32-class accuracy at any signal level; one Inf / NaN sample makes the
     outputs whose window holds it non-finite plus, at most, the rest of the two 128-output block-rows whose 192-sample
     operand rows contain it (zero-padded Toeplitz taps meet it as 0 * Inf); everything else keeps the bar."""
     monkeypatch.setenv("RRC_FIR_TCGEN05", "2")
+    monkeypatch.setenv("RRC_FIR_TC5_NR", str(rows))
     n, ntaps, pos = 30_000, 64, 12_345
     taps = O.low_pass_n(1.0, 0.1, ntaps).astype(np.complex64)
     x = (O.synth_c32(61, 0, n) * np.float32(scale)).astype(np.complex64)
@@ -760,7 +764,7 @@ def test_fir_config1_full_size(R):
     assert n_out == 16_777_153
     dout = R.DeviceBuffer(n_out * 8)
     f.run(din, n, dout, n_out)
-    assert f.kernel_name.startswith("fir_tc5_kernel")          # 2048 tiles >= 4 per SM: the tcgen05 kernel by default
+    assert f.kernel_name.startswith("fir_tc5_kernel")          # 2048 tiles >= 3 per SM: the tcgen05 kernel by default
     assert _spot_check_fir(R, din, dout, n_out, taps, 1, seed, n) <= REL_RMS_BAR
     small = R.Fir(taps)
     small.filter(O.synth_c32(3, 0, 100_000))
