@@ -148,7 +148,11 @@ int rrc_fir_uses_tensor_cores(const rrc_fir_t* h, int* yes);
 int rrc_fir_set_epilogue(rrc_fir_t* h, int kind, float re, float im);
 /* Which kernel the planner chose for this handle (reports / INTEGRATION.md): e.g. "fir_tc1_kernel<KS=5,D=1> ...",
  * "fir_rtu_kernel<D=10,QB=26,R=8> ..." (real-tap decimating filters with deci 5 or 10 and <= 26 taps per polyphase
- * branch: taps travel as kernel parameters and reach FFMA2 as uniform-register operands), "fir_rt_kernel<...>". */
+ * branch: taps travel as kernel parameters and reach FFMA2 as uniform-register operands), "fir_rt_kernel<...>".
+ * c32 filters with real taps, deci 1 and <= 65 taps have two kernels and pick per launch: "fir_tc5_kernel<KS=..>"
+ * (tcgen05.mma, taps and accumulators in tensor memory) for launches of at least 3 tiles of 8192 outputs per SM,
+ * "fir_tc1_kernel" (mma.sync) below that and for the fused demod; after a launch the name is the one that ran.
+ * RRC_FIR_TCGEN05=0 (environment) keeps such filters on mma.sync. */
 int rrc_fir_kernel_name(const rrc_fir_t* h, char* buf, size_t buflen);
 /* Restart the translate rotator's output counter (new stream). */
 int rrc_fir_reset(rrc_fir_t* h);

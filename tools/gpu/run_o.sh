@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "tcgen05 or config1_full" -x 2>&1 | tail -3 | tee gpurun_out/o_pytest.txt
-for n in 1048576 2097152 3145728 4194304 8388608 12582912 16777216 25165824 33554432 67108864; do
-for v in 1 0; do
-RRC_FIR_TCGEN05=$v timeout 300 python bench.py --config c1 --n $n --steps 20 --warmup 3 --headline-only --no-e2e --no-cpu --sustain 0 > gpurun_out/o_tmp.json 2> gpurun_out/o_c1_tc5.err; python -c "import json;d=json.load(open('gpurun_out/o_tmp.json'));print('n $n RRC_FIR_TCGEN05=$v', round(d['ms_per_step']*1000,2),'us', round(d['roofline']['frac'],3), d['roofline']['kernel'][:16])"
-done; done 2>&1 | tee gpurun_out/o_c1_tc5_sizes.txt
+for tool in memcheck racecheck synccheck; do
+  timeout 900 compute-sanitizer --tool $tool --kernel-regex kns=fir_tc5 python tools/gpu/tc5_sanitize.py > gpurun_out/o_sanitize_$tool.txt 2>&1; echo "$tool rc=$?"; grep -i "error summary\|hazard\|Invalid\|done\|========= [A-Z]" gpurun_out/o_sanitize_$tool.txt | sort | uniq -c | head -12
+done
+for i in 1 2 3 4 5; do timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "tcgen05 or config1_full" -x 2>&1 | tail -1; done
