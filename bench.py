@@ -446,14 +446,17 @@ def build_workload(ctx, cfg, split="capture"):
             t = dev_f32(fl * n)
             R.synth_f32(t, seed + 17 * b, 0, fl * n, dev, stream)
             dins.append(t)
-        dout = dev_f32(fl * n_out)
+        # ... and over NBUF distinct output buffers, so that a step's stores are not absorbed by lines the previous
+        # step left dirty in L2 at the same addresses: in the steady state every output byte is written back to HBM
+        douts = [dev_f32(fl * n_out) for _ in range(nbuf)]
+        dout = douts[0]
         state = {"i": 0}
 
         def step():
-            f.run(dins[state["i"] % nbuf], n, dout, n_out, stream)
+            f.run(dins[state["i"] % nbuf], n, douts[state["i"] % nbuf], n_out, stream)
             state["i"] += 1
         W.__dict__.update(f=f, step=step, n_in=n, n_out=n_out, units=n, din=dins[0], n_host=n)
-        W.keep += dins + [dout]
+        W.keep += dins + douts
     elif op == "fir_demod":
         from rustradio_b200 import shard as S
         n = cfg["n"]
@@ -748,7 +751,7 @@ def config_block(cfg, W, world):
     return {"workload": cfg["desc"], "name": cfg["name"], "samples_per_gpu_per_step": int(W.units),
             "outputs_per_gpu_per_step": int(W.n_out), "parallelism": W.parallelism,
             "l2_policy": ("inputs larger than L2 (>= 0.5 GiB per step vs 126 MB L2)" if ab > 4e8 else
-                          f"input 128 MiB ~ L2 size: the steps rotate over {cfg.get('rotate', 1)} distinct input buffers ({cfg.get('rotate', 1) * 128} MiB) so no step finds its input in L2")}
+                          f"input 128 MiB ~ L2 size: the steps rotate over {cfg.get('rotate', 1)} distinct input and output buffers ({cfg.get('rotate', 1) * 128} MiB each way) so no step finds its input in L2 or overwrites lines it left dirty there")}
 
 
 def run_sub(ctx, name, split, args, pool, want_e2e=True, want_cpu=True, steps=None):
