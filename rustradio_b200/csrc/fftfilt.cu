@@ -759,7 +759,7 @@ int rrc_fftfilt_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, fl
     if (!in_host || !out_host) return fail(RRC_ERR_INVALID, "in/out is NULL");
     RRC_TRY(h->pipe.init(h->device));
     RRC_TRY(pipe_wait_state(h));
-    const size_t chunk = PIPE_CHUNK_SAMPLES;
+    const size_t chunk = pipe_chunk_samples_for(total);
     const size_t esz = h->real ? sizeof(float) : h->in_u8 ? 2 : sizeof(float2);   // input bytes per sample
     const size_t osz = (h->real || h->epi.kind == RRC_EPI_MAG2) ? sizeof(float) : sizeof(float2);
     RRC_TRY(h->pipe.reserve(std::min(chunk, total) * esz, std::min(chunk, total) * osz));
@@ -789,7 +789,7 @@ int rrc_fftfilt_decim_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_
     if (h->real) return rrc_fftfilt_run_host(h, in_host, n_in, out_host, n_out);
     RRC_TRY(h->pipe.init(h->device));
     RRC_TRY(pipe_wait_state(h));
-    const size_t chunk = PIPE_CHUNK_SAMPLES;
+    const size_t chunk = pipe_chunk_samples_for(total);
     const size_t esz = h->in_u8 ? 2 : sizeof(float2);
     const size_t osz = h->epi.kind == RRC_EPI_MAG2 ? sizeof(float) : sizeof(float2);
     RRC_TRY(h->pipe.reserve(std::min(chunk, total) * esz, (std::min(chunk, total) / deci + 2) * osz));

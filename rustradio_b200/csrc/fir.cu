@@ -1406,7 +1406,7 @@ int rrc_fir_run_host(rrc_fir_t* h, const void* in_host, size_t n_in, void* out_h
     if (total == 0) return RRC_OK;
     if (!in_host || !out_host) return fail(RRC_ERR_INVALID, "in/out is NULL");
     RRC_TRY(h->pipe.init(h->device));
-    const size_t chunk_out = std::max<size_t>(1, PIPE_CHUNK_SAMPLES / D);
+    const size_t chunk_out = std::max<size_t>(1, pipe_chunk_samples_for(n_in) / D);
     const size_t max_out = std::min(chunk_out, total);
     const size_t oes = h->epi.kind == RRC_EPI_MAG2 ? sizeof(float) : es;   // ComplexToMag2 epilogue: f32 out
     RRC_TRY(h->pipe.reserve(((max_out - 1) * D + T) * ies, max_out * oes));
@@ -1466,7 +1466,7 @@ int rrc_quad_demod_run_host(int device, const float* in_host, size_t n_in, float
     RRC_CUDA(cudaSetDevice(device));
     Pipe pipe;
     RRC_TRY(pipe.init(device));
-    const size_t chunk = PIPE_CHUNK_SAMPLES;
+    const size_t chunk = pipe_chunk_samples_for(n_in);
     int s = pipe.reserve((std::min(chunk, n_in - 1) + 1) * sizeof(float2), std::min(chunk, n_in - 1) * sizeof(float));
     int i = 0;
     for (size_t o = 0; s == RRC_OK && o < n_in - 1; o += chunk, ++i) {

@@ -101,5 +101,15 @@ inline size_t pipe_chunk_samples() {
     return (size_t)1 << l;
 }
 #define PIPE_CHUNK_SAMPLES (::rrc::pipe_chunk_samples())
+// Chunk for a call that moves `total` samples: the first chunk's H2D and the last chunk's D2H are not overlapped, so a
+// call of only a few default chunks loses a large part of the copy time (config 1, 2^24 samples = 2 chunks: 0.72 of
+// the bare-copy ceiling; with 2^21-sample chunks 0.89), while chunks below 2^21 samples cost more per copy than they
+// hide (config 2: 0.94 at 2^23, 0.88 at 2^21; profiles/r02_e2e_chunk_sweep.txt).  Aim for 8 chunks inside [2^21, 2^23].
+inline size_t pipe_chunk_samples_for(size_t total) {
+    if (getenv("RRC_PIPE_CHUNK_LOG2")) return pipe_chunk_samples();
+    size_t c = (size_t)1 << 23;
+    while (c > ((size_t)1 << 21) && c * 8 > total) c >>= 1;
+    return c;
+}
 
 }  // namespace rrc

@@ -263,7 +263,7 @@ int rrc_resampler_run_host(rrc_resampler_t* h, const void* in_host, size_t n_in,
     *consumed = 0; *produced = 0;
     RRC_TRY(h->pipe.init(h->device));
     const size_t es = h->elem;
-    const size_t chunk_in = PIPE_CHUNK_SAMPLES;
+    const size_t chunk_in = pipe_chunk_samples_for(n_in);
     // worst-case outputs of one chunk (+ pending flush)
     const size_t chunk_out = (size_t)(((__int128)chunk_in * h->interp) / h->deci) + (size_t)((h->interp + h->deci - 1) / h->deci) + 2;
     RRC_TRY(h->pipe.reserve(chunk_in * es, chunk_out * es));
