@@ -764,8 +764,8 @@ int rrc_fftfilt_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_in, fl
     const size_t osz = (h->real || h->epi.kind == RRC_EPI_MAG2) ? sizeof(float) : sizeof(float2);
     RRC_TRY(h->pipe.reserve(std::min(chunk, total) * esz, std::min(chunk, total) * osz));
     int i = 0;
-    for (size_t off = 0; off < total; off += chunk, ++i) {
-        const size_t n = std::min(chunk, total - off);
+    for (size_t off = 0, n = 0; off < total; off += n, ++i) {
+        n = pipe_next_chunk((size_t)i, total - off, chunk);
         RRC_TRY(h->pipe.stage_in(i, reinterpret_cast<const char*>(in_host) + off * esz, n * esz));
         RRC_TRY(launch(h, (const float*)h->pipe.d_in[i & 1], n, (float*)h->pipe.d_out[i & 1], n, 1, 0, h->pipe.s_comp));
         RRC_TRY(h->pipe.drain_out(i, reinterpret_cast<char*>(out_host) + off * osz, n * osz));
@@ -795,8 +795,8 @@ int rrc_fftfilt_decim_run_host(rrc_fftfilt_t* h, const float* in_host, size_t n_
     RRC_TRY(h->pipe.reserve(std::min(chunk, total) * esz, (std::min(chunk, total) / deci + 2) * osz));
     int i = 0;
     size_t produced = 0;
-    for (size_t off = 0; off < total; off += chunk, ++i) {
-        const size_t n = std::min(chunk, total - off);
+    for (size_t off = 0, n = 0; off < total; off += n, ++i) {
+        n = pipe_next_chunk((size_t)i, total - off, chunk);
         const size_t skip = (deci - off % deci) % deci;           // first kept output of this chunk
         size_t cnt = 0;
         RRC_TRY(h->pipe.stage_in(i, reinterpret_cast<const char*>(in_host) + off * esz, n * esz));

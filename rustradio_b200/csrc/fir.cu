@@ -1411,8 +1411,8 @@ int rrc_fir_run_host(rrc_fir_t* h, const void* in_host, size_t n_in, void* out_h
     const size_t oes = h->epi.kind == RRC_EPI_MAG2 ? sizeof(float) : es;   // ComplexToMag2 epilogue: f32 out
     RRC_TRY(h->pipe.reserve(((max_out - 1) * D + T) * ies, max_out * oes));
     int i = 0;
-    for (size_t o = 0; o < total; o += chunk_out, ++i) {
-        const size_t no = std::min(chunk_out, total - o);
+    for (size_t o = 0, no = 0; o < total; o += no, ++i) {
+        no = pipe_next_chunk((size_t)i, total - o, chunk_out);
         const size_t need = (no - 1) * D + T;                              // halo = ntaps-1 re-copied per chunk
         RRC_TRY(h->pipe.stage_in(i, (const char*)in_host + o * D * ies, need * ies));
         RRC_TRY(run_impl(h, h->pipe.d_in[i & 1], 0, need, h->pipe.d_out[i & 1], 0, no, 1, false, 0.f, h->pipe.s_comp));

@@ -2,6 +2,7 @@
 // *_run_host entry points (the end-to-end path: host buffers in, host buffers
 // out, copies overlapped with compute on three CUDA streams).
 #pragma once
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -110,6 +111,18 @@ inline size_t pipe_chunk_samples_for(size_t total) {
     size_t c = (size_t)1 << 23;
     while (c > ((size_t)1 << 21) && c * 8 > total) c >>= 1;
     return c;
+}
+
+// Tapered schedule: the first chunk's H2D copy and the last chunk's D2H copy have nothing to overlap with, so the
+// chunks ramp up from maxc/8 (x2 per chunk) and ramp down again at the end: the exposed copies shrink 8x for four extra
+// chunks at each end.  `k` = chunks already issued, `remaining` = units left; returns the size of the next chunk.
+inline size_t pipe_next_chunk(size_t k, size_t remaining, size_t maxc) {
+    if (getenv("RRC_PIPE_CHUNK_LOG2")) return std::min(maxc, remaining);       // tests: fixed chunks
+    const size_t minc = std::max<size_t>(1, maxc >> 3);
+    size_t c = k < 3 ? std::min(maxc, minc << k) : maxc;                       // ramp up
+    while (c > minc && c * 2 > remaining) c >>= 1;                             // ramp down: at most half of what is left
+    if (remaining <= minc + minc / 2) c = remaining;                           // no crumbs
+    return std::min(c, remaining);
 }
 
 }  // namespace rrc

@@ -270,7 +270,7 @@ int rrc_resampler_run_host(rrc_resampler_t* h, const void* in_host, size_t n_in,
     size_t ipos = 0, opos = 0;
     int i = 0;
     for (;; ++i) {
-        const size_t ni = std::min(chunk_in, n_in - ipos);
+        const size_t ni = n_in > ipos ? pipe_next_chunk((size_t)i, n_in - ipos, chunk_in) : 0;
         const size_t cap = std::min(chunk_out, out_cap - opos);
         if (cap == 0) break;
         RRC_TRY(h->pipe.stage_in(i, (const char*)in_host + ipos * es, ni * es));
