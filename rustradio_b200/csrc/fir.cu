@@ -834,7 +834,7 @@ int plan_tc(rrc_fir* h, const std::vector<float>& w) {
     // RRC_FIR_TCGEN05: 0 never, 2 always (tests), default by size.
     int want5 = 1;
     if (const char* e = getenv("RRC_FIR_TCGEN05")) want5 = atoi(e);
-    if (want5 && h->cplx && D == 1 && T <= 65) {
+    if (want5 && D == 1 && T <= 65) {
         std::vector<unsigned short> hi(T), lo(T);
         for (size_t j = 0; j < T; ++j) {
             const float v = Bval((long long)j, 0);
@@ -1128,8 +1128,22 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         t.total_tiles = t.tiles_x * (long long)nchan;
         if (t.total_tiles > 0x7fffffffll) return fail(RRC_ERR_INVALID, "fir: %lld tiles in one launch (limit 2^31 - 1)", t.total_tiles);
         RRC_TRY(fir_tcc_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0, (int)h->deci}, t, demod, st));
+    } else if (use_tc && !h->tc5_tab.empty() && !demod && !h->in_u8 &&
+               (long long)((out_n + 8191) / 8192) * (long long)nchan >= h->tc5_min_tiles) {
+        FirTc5Args t{};
+        t.in = reinterpret_cast<const float2*>(in); t.out = reinterpret_cast<float2*>(out);
+        t.in_stride = (long long)in_stride; t.out_stride = (long long)out_stride;
+        t.need = (long long)need; t.out_n = (long long)out_n;
+        t.KS = h->tc5_KS; t.tap_inv_scale = h->tc_tap_inv_scale; t.real_stream = h->cplx ? 0 : 1;
+        t.nr = fir_tc5_rows((long long)((out_n + 8191) / 8192) * (long long)nchan, h->device, !h->cplx);
+        const size_t bt5 = (size_t)128 * t.nr;
+        t.tiles_x = (long long)((out_n + bt5 - 1) / bt5);
+        t.total_tiles = t.tiles_x * (long long)nchan;
+        RRC_TRY(fir_tc5_launch(h->device, t, h->tc5_tab.data(), st));
+        h->last_tc5 = 1;
     } else if (use_tc && !h->cplx) {
         if (demod) return fail(RRC_ERR_INVALID, "fused demod needs a c32 FIR");
+        h->last_tc5 = 0;
         FirTcfArgs t{};
         t.in = reinterpret_cast<const float*>(in); t.out = reinterpret_cast<float*>(out);
         t.bfrag = reinterpret_cast<const uint4*>(h->tc_bfrag);
@@ -1141,19 +1155,6 @@ int run_impl(rrc_fir* h, const void* in, size_t in_stride, size_t need, void* ou
         t.total_tiles = t.tiles_x * (long long)nchan;
         if (t.total_tiles > 0x7fffffffll) return fail(RRC_ERR_INVALID, "fir: %lld tiles in one launch (limit 2^31 - 1)", t.total_tiles);
         RRC_TRY(fir_tcf_launch(FirTcGeom{h->device, 1, 0, h->tc_KS, 0, (int)h->deci}, t, st));
-    } else if (use_tc && !h->tc5_tab.empty() && !demod && !h->in_u8 &&
-               (long long)((out_n + 8191) / 8192) * (long long)nchan >= h->tc5_min_tiles) {
-        FirTc5Args t{};
-        t.in = reinterpret_cast<const float2*>(in); t.out = reinterpret_cast<float2*>(out);
-        t.in_stride = (long long)in_stride; t.out_stride = (long long)out_stride;
-        t.need = (long long)need; t.out_n = (long long)out_n;
-        t.KS = h->tc5_KS; t.tap_inv_scale = h->tc_tap_inv_scale;
-        t.nr = fir_tc5_rows((long long)((out_n + 8191) / 8192) * (long long)nchan, h->device);
-        const size_t bt5 = (size_t)128 * t.nr;
-        t.tiles_x = (long long)((out_n + bt5 - 1) / bt5);
-        t.total_tiles = t.tiles_x * (long long)nchan;
-        RRC_TRY(fir_tc5_launch(h->device, t, h->tc5_tab.data(), st));
-        h->last_tc5 = 1;
     } else if (use_tc && h->tc1) {
         const size_t work = demod ? out_n - 1 : out_n;
         if (work == 0) return RRC_OK;
@@ -1342,10 +1343,10 @@ int rrc_fir_kernel_name(const rrc_fir_t* h, char* buf, size_t buflen) {
     const bool use_tc = h->tc && (h->tc_cplx || !h->translate) && h->epi.kind == RRC_EPI_NONE;
     char tmp[320];
     if (use_tc && h->tc_cplx) snprintf(tmp, sizeof tmp, "fir_tcc_kernel<KS=%d,D=%zu> (tensor cores, complex taps, fp16x3)", h->tc_KS, h->deci);
-    else if (use_tc && !h->cplx) snprintf(tmp, sizeof tmp, "fir_tcf_kernel<KS=%d,D=%zu> (tensor cores, f32 stream, fp16x3)", h->tc_KS, h->deci);
+    else if (use_tc && !h->cplx && (h->tc5_tab.empty() || h->last_tc5 == 0)) snprintf(tmp, sizeof tmp, "fir_tcf_kernel<KS=%d,D=%zu> (tensor cores, f32 stream, fp16x3)", h->tc_KS, h->deci);
     else if (use_tc && !h->tc5_tab.empty() && !h->in_u8 && h->last_tc5 != 0)
         snprintf(tmp, sizeof tmp, "fir_tc5_kernel<KS=%d> (tcgen05.mma kind::f16 M128 N64 K16, taps and accumulators in TMEM, fp16x3)%s", h->tc5_KS,
-                 h->last_tc5 == 1 ? "" : "; launches below 3 tiles of 8192 outputs per SM and the fused demod use fir_tc1_kernel (mma.sync)");
+                 h->last_tc5 == 1 ? "" : "; launches below 3 tiles of 8192 outputs per SM and the fused demod use the mma.sync kernel (fir_tc1_kernel / fir_tcf_kernel)");
     else if (use_tc && h->tc1) snprintf(tmp, sizeof tmp, "fir_tc1_kernel<KS=%d,D=%zu> (tensor cores, real taps, fp16x3)", h->tc_KS, h->deci);
     else if (use_tc) snprintf(tmp, sizeof tmp, "fir_tc_kernel<NTILE=%d,NLD=%d> (tensor cores, real taps, fp16x3)", h->tc_ntile, h->tc_nld);
     else if (h->rtu_qb) snprintf(tmp, sizeof tmp, "fir_rtu_kernel<D=%zu,QB=%d,R=%d> (FFMA2, taps as uniform-register operands from the kernel parameters)", h->deci, h->rtu_qb, h->rtu_r);

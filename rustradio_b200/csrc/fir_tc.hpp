@@ -64,12 +64,13 @@ struct FirTccArgs {             // fir_tcc_kernel: c32 samples, complex taps (tr
     unsigned long long out_base;
 };
 
-struct FirTc5Args {             // fir_tc5_kernel (tcgen05 / TMEM, fir_tc5.cu): c32 samples, real taps, deci 1, ntaps <= 65
-    const float2* in;
+struct FirTc5Args {             // fir_tc5_kernel (tcgen05 / TMEM, fir_tc5.cu): c32 or f32 samples, real taps, deci 1, ntaps <= 65
+    const float2* in;          // f32 streams: float arrays behind these pointers (real_stream = 1), strides in samples
     float2* out;
     long long in_stride, out_stride, need, out_n;
+    int real_stream;
     long long tiles_x, total_tiles;   // tiles of 128 * nr outputs per channel / in the launch
-    int nr;                    // block-rows per tile: 32 or 64 (fir_tc5_rows)
+    int nr;                    // block-rows per tile (fir_tc5_rows)
     int KS;                    // k-steps of 16: ceil((127 + ntaps) / 16) <= 12
     float tap_inv_scale;
 };
@@ -92,7 +93,7 @@ int fir_tcf_launch(const FirTcGeom& g, const FirTcfArgs& a, cudaStream_t st);
 int fir_tcc_launch(const FirTcGeom& g, const FirTccArgs& a, bool demod, cudaStream_t st);
 size_t fir_tc5_tab_words();       // words of the tap table fir_tc5_build_tab fills (kernel parameter of fir_tc5_kernel)
 void fir_tc5_build_tab(const unsigned short* hi, const unsigned short* lo, size_t ntaps, unsigned* tab);
-int fir_tc5_rows(long long tiles8192, int device);   // block-rows of 128 outputs per CTA tile for a launch of that size: 32 or 64
+int fir_tc5_rows(long long tiles8192, int device, bool real_stream);   // block-rows of 128 outputs per CTA tile: 32 / 64 (c32), 64 (f32)
 int fir_tc5_launch(int device, const FirTc5Args& a, const unsigned* tab_host, cudaStream_t st);
 
 }  // namespace rrc

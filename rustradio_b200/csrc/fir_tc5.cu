@@ -1,4 +1,4 @@
-// fir_tc5.cu — FirFilter (reference src/fir.rs:166-197, Fir::filter_n; block src/fir.rs:492-527) for c32 samples, real
+// fir_tc5.cu — FirFilter (reference src/fir.rs:166-197, Fir::filter_n; block src/fir.rs:492-527) for c32 or f32 samples, real
 // taps, decimation 1 and ntaps <= 65 on the 5th-generation tensor cores: tcgen05.mma (kind::f16), the tap operand and
 // the accumulators in tensor memory.  Same arithmetic contract as fir_tc.cuh (block-scaled fp16 hi + lo split of
 // samples and taps, the three products hi*hi + hi*lo + lo*hi accumulated in FP32), different machinery:
@@ -47,7 +47,7 @@ template <int NR> struct Tc5Geom {
     static constexpr int REGION = ((NR + 1) * 128 + 1023) / 1024 * 1024;      // NR + 1 rows x 128 B, rounded up to the atom
     static constexpr int PLANE = 2 * REGION;        // one component (re / im), one part (hi / lo)
     static constexpr int NLD = (HROWS + TC5_NPW - 1) / TC5_NPW;               // half-rows (float4 loads) per producer lane
-    static constexpr size_t SMEM = 1024 + 8 * PLANE + 4096;
+    static constexpr size_t smem(bool cplx) { return 1024 + (size_t)(cplx ? 8 : 4) * PLANE + 4096; }   // 2 sets x (4 | 2) planes
     static constexpr unsigned IDESC = 0x08000010u | ((unsigned)(NR >> 3) << 17);   // kind::f16: D f32, A/B f16 K-major, N = NR, M = 128
 };
 constexpr int TC5_EPI0 = 2 * TC5_NPW, TC5_MMAW = TC5_EPI0 + 4;
@@ -117,13 +117,29 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {      // read onc
 }
 
 // Tile loads: half-row (pw + 9 u) of the tile, samples 2*lane, 2*lane + 1 of it.  Samples at or past `need` are zeros.
-template <int NR>
-__device__ __forceinline__ void tc5_load(const FirTc5Args& a, long long tile, int pw, int lane, float4 (&v)[Tc5Geom<NR>::NLD]) {
+template <bool CPLX> struct Tc5Val { using T = float4; };       // what a producer lane holds of one half-row: two samples
+template <> struct Tc5Val<false> { using T = float2; };
+template <int NR, bool CPLX>
+__device__ __forceinline__ void tc5_load(const FirTc5Args& a, long long tile, int pw, int lane, typename Tc5Val<CPLX>::T (&v)[Tc5Geom<NR>::NLD]) {
     constexpr int TC5_HROWS = Tc5Geom<NR>::HROWS, TC5_NLD = Tc5Geom<NR>::NLD;
     const long long ch = tile / a.tiles_x, tx = tile - ch * a.tiles_x;
     const long long s0 = tx * Tc5Geom<NR>::BT;
-    const float2* in = a.in + ch * a.in_stride + s0;
     const long long avail = a.need - s0;
+    if constexpr (!CPLX) {                                 // f32 stream: samples 2*lane, 2*lane + 1 in v.x, v.y
+        const float* in = reinterpret_cast<const float*>(a.in) + ch * a.in_stride + s0;
+        const bool fast = avail >= 64ll * TC5_HROWS && (reinterpret_cast<uintptr_t>(in) & 7) == 0;
+#pragma unroll
+        for (int u = 0; u < TC5_NLD; ++u) {
+            const int hr = pw + TC5_NPW * u;
+            const long long s = 64ll * hr + 2 * lane;
+            v[u] = make_float2(0.f, 0.f);
+            if (hr < TC5_HROWS) {
+                if (fast) { v[u] = __ldg(reinterpret_cast<const float2*>(in + s)); }
+                else { if (s < avail) v[u].x = __ldg(in + s); if (s + 1 < avail) v[u].y = __ldg(in + s + 1); }
+            }
+        }
+    } else {
+    const float2* in = a.in + ch * a.in_stride + s0;
     const bool fast = avail >= 64ll * TC5_HROWS && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
     if (fast) {
         const float4* p = reinterpret_cast<const float4*>(in) + lane;
@@ -143,12 +159,13 @@ __device__ __forceinline__ void tc5_load(const FirTc5Args& a, long long tile, in
             }
         }
     }
+    }
 }
 
 // RRC_FIR_TC5_TRACE (debug): CTA 2 stamps clock64 per role for its tiles 2..7, plus whole-kernel stamps
 #define TC5_STAMP(role, k) do { if (trace && blockIdx.x == 2 && j >= 2 && j < 2 + TC5_TRACE_IT && lane == 0) trace[((j - 2) * 4 + (role)) * TC5_NSTAMP + (k)] = clock64(); } while (0)
 
-template <int NR>
+template <int NR, bool CPLX>
 __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_constant__ Tc5Params prm, long long* __restrict__ trace) {
     constexpr int TC5_HROWS = Tc5Geom<NR>::HROWS, TC5_NLD = Tc5Geom<NR>::NLD, TC5_REGION = Tc5Geom<NR>::REGION, TC5_PLANE = Tc5Geom<NR>::PLANE;
     constexpr int FIR_TC5_BT = Tc5Geom<NR>::BT;
@@ -160,11 +177,13 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
     const unsigned raw = smem_u32(smem_raw);
     unsigned char* sm = smem_raw + ((1024u - (raw & 1023u)) & 1023u);      // swizzle atoms need 1024-byte alignment
     unsigned char* s_planes = sm;                                          // [2 sets][4 planes = re hi, re lo, im hi, im lo][2 regions]
-    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm + 8 * TC5_PLANE);   // full[2], done[2], accfree[2], taps, lead
+    constexpr int NPL = CPLX ? 4 : 2;                                      // planes per set: (re, im) x (hi, lo) | (hi, lo)
+    constexpr unsigned DSET = CPLX ? 2u * NR : (unsigned)NR;               // accumulator columns per set
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(sm + 2 * NPL * TC5_PLANE);   // full[2], done[2], accfree[2], taps, lead
     unsigned* s_tmem = reinterpret_cast<unsigned*>(s_bar + 8);
     float* s_inv = reinterpret_cast<float*>(s_tmem + 1);                   // [4]: 1 / (tile scale * tap scale) of tile j & 3
     unsigned* s_red = reinterpret_cast<unsigned*>(s_inv + 4);              // [2 groups][3][16]
-    unsigned* s_tab = reinterpret_cast<unsigned*>(sm + 8 * TC5_PLANE + 512);    // the tap words, staged for per-lane indexing (16-byte aligned)
+    unsigned* s_tab = reinterpret_cast<unsigned*>(sm + 2 * NPL * TC5_PLANE + 512);    // the tap words, staged for per-lane indexing (16-byte aligned)
     const unsigned planes_u = smem_u32(s_planes), bar_u = smem_u32(s_bar);
     const unsigned full_u = bar_u, done_u = bar_u + 16, accfree_u = bar_u + 32, taps_u = bar_u + 48, lead_u = bar_u + 56;
 
@@ -223,20 +242,22 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
     if (warp < TC5_EPI0) {
         // ================= producers: group g stages tiles j = g, g + 2, ... into plane set g
         const int g = warp >= TC5_NPW ? 1 : 0, pw = warp - g * TC5_NPW;
-        float4 v[TC5_NLD];
+        typename Tc5Val<CPLX>::T v[TC5_NLD];
         if (g == 1) mbar_wait(lead_u, 0u);              // the CTA's first tile is requested first: it heads the pipeline
-        if (g < njobs) tc5_load<NR>(a, first + (long long)g * gridDim.x, pw, lane, v);
+        if (g < njobs) tc5_load<NR, CPLX>(a, first + (long long)g * gridDim.x, pw, lane, v);
         if (g == 0) mbar_arrive(lead_u);
         if (ktr && warp == 0 && lane == 0) ktr[8] = clock64();
-        unsigned char* planes = s_planes + g * 4 * TC5_PLANE;
+        unsigned char* planes = s_planes + g * NPL * TC5_PLANE;
         unsigned* red = s_red + g * 48;
         for (int j = g, u = 0; j < njobs; j += 2, ++u) {
             TC5_STAMP(g, 0);
             // ---- largest finite magnitude of the tile -> power-of-two scale (group-wide)
             float mx = 0.f;
 #pragma unroll
-            for (int i = 0; i < TC5_NLD; ++i)
-                mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v[i].x), fabsf(v[i].y))), fmaxf(fabsf(v[i].z), fabsf(v[i].w)));
+            for (int i = 0; i < TC5_NLD; ++i) {
+                mx = fmaxf(mx, fmaxf(fabsf(v[i].x), fabsf(v[i].y)));
+                if constexpr (CPLX) mx = fmaxf(mx, fmaxf(fabsf(v[i].z), fabsf(v[i].w)));
+            }
             unsigned wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));      // NaN never wins fmaxf; Inf does
             unsigned* rb = red + 16 * (u & 1);
             if (lane == 0) rb[pw] = wmax;
@@ -249,8 +270,10 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
                 float m2 = 0.f;
                 auto fin = [](float c) { const float q = fabsf(c); return q <= 3.4028234e38f ? q : 0.f; };
 #pragma unroll
-                for (int i = 0; i < TC5_NLD; ++i)
-                    m2 = fmaxf(fmaxf(m2, fmaxf(fin(v[i].x), fin(v[i].y))), fmaxf(fin(v[i].z), fin(v[i].w)));
+                for (int i = 0; i < TC5_NLD; ++i) {
+                    m2 = fmaxf(m2, fmaxf(fin(v[i].x), fin(v[i].y)));
+                    if constexpr (CPLX) m2 = fmaxf(m2, fmaxf(fin(v[i].z), fin(v[i].w)));
+                }
                 wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(m2));
                 if (lane == 0) red[32 + pw] = wmax;
                 asm volatile("bar.sync %0, %1;" :: "r"(1 + g), "n"(32 * TC5_NPW) : "memory");
@@ -272,15 +295,20 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
                 for (int i = 0; i < TC5_NLD; ++i) {
                     const unsigned hr = (unsigned)(pw + TC5_NPW * i);
                     if (hr < (unsigned)TC5_HROWS) {
-                        unsigned rh, rl, ih, il;
-                        tc5_split2(v[i].x * sc, v[i].z * sc, rh, rl);
-                        tc5_split2(v[i].y * sc, v[i].w * sc, ih, il);
                         const unsigned n = hr >> 1;
                         unsigned char* p = planes + (hr & 1u) * TC5_REGION + n * 128u + ((c8 ^ (n & 7u)) << 4) + col;
+                        unsigned rh, rl;
+                        if constexpr (CPLX) {
+                            unsigned ih, il;
+                            tc5_split2(v[i].x * sc, v[i].z * sc, rh, rl);
+                            tc5_split2(v[i].y * sc, v[i].w * sc, ih, il);
+                            *reinterpret_cast<unsigned*>(p + 2 * TC5_PLANE) = ih;
+                            *reinterpret_cast<unsigned*>(p + 3 * TC5_PLANE) = il;
+                        } else {
+                            tc5_split2(v[i].x * sc, v[i].y * sc, rh, rl);
+                        }
                         *reinterpret_cast<unsigned*>(p) = rh;
                         *reinterpret_cast<unsigned*>(p + TC5_PLANE) = rl;
-                        *reinterpret_cast<unsigned*>(p + 2 * TC5_PLANE) = ih;
-                        *reinterpret_cast<unsigned*>(p + 3 * TC5_PLANE) = il;
                     }
                 }
             }
@@ -288,7 +316,7 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");              // generic-proxy stores -> visible to the tensor core's reads
             mbar_arrive(full_u + 8 * g);
             TC5_STAMP(g, 3);
-            if (j + 2 < njobs) tc5_load<NR>(a, first + (long long)(j + 2) * gridDim.x, pw, lane, v);
+            if (j + 2 < njobs) tc5_load<NR, CPLX>(a, first + (long long)(j + 2) * gridDim.x, pw, lane, v);
             TC5_STAMP(g, 4);
         }
         if (ktr && lane == 0 && pw == 0) ktr[2 + g] = clock64();
@@ -305,20 +333,31 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
             const long long tile = first + (long long)j * gridDim.x;
             const long long ch = tile / a.tiles_x, tx = tile - ch * a.tiles_x;
             const long long o0 = tx * FIR_TC5_BT;
-            float2* out = a.out + ch * a.out_stride + o0 + 32 * q + lane;
             const long long cnt = a.out_n - o0 - (32 * q + lane);                   // this lane's output of block-row n exists for 128 n < cnt
             const bool fast = a.out_n - o0 >= FIR_TC5_BT;
 #pragma unroll 1
             for (int part = 0; part < NR / 16; ++part) {
-                unsigned re[16], im[16];
-                const unsigned taddr = tmem + 256u + 2u * NR * g + ((unsigned)(32 * q) << 16) + 16u * part;
+                unsigned re[16];
+                const unsigned taddr = tmem + 256u + DSET * g + ((unsigned)(32 * q) << 16) + 16u * part;
                 tc5_ld32(taddr, re);
-                tc5_ld32(taddr + NR, im);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if constexpr (CPLX) {
+                    unsigned im[16];
+                    tc5_ld32(taddr + NR, im);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float2* out = a.out + ch * a.out_stride + o0 + 32 * q + lane;
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const long long o = 128ll * (16 * part + r);
-                    if (fast || o < cnt) out[o] = make_float2(__uint_as_float(re[r]) * inv, __uint_as_float(im[r]) * inv);
+                    for (int r = 0; r < 16; ++r) {
+                        const long long o = 128ll * (16 * part + r);
+                        if (fast || o < cnt) out[o] = make_float2(__uint_as_float(re[r]) * inv, __uint_as_float(im[r]) * inv);
+                    }
+                } else {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float* out = reinterpret_cast<float*>(a.out) + ch * a.out_stride + o0 + 32 * q + lane;
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const long long o = 128ll * (16 * part + r);
+                        if (fast || o < cnt) out[o] = __uint_as_float(re[r]) * inv;
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -340,8 +379,8 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
             TC5_STAMP(2, 2);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tc5_elect()) {
-                const unsigned pb = tc5_desc_lo(planes_u + (unsigned)g * 4u * TC5_PLANE);
-                const unsigned d = tmem + 256u + 2u * NR * (unsigned)g;
+                const unsigned pb = tc5_desc_lo(planes_u + (unsigned)g * NPL * TC5_PLANE);
+                const unsigned d = tmem + 256u + DSET * (unsigned)g;
                 constexpr unsigned idesc = Tc5Geom<NR>::IDESC;
 #pragma unroll
                 for (int s = 0; s < 12; ++s) {
@@ -352,11 +391,11 @@ __global__ void __launch_bounds__(TC5_THREADS, 1) fir_tc5_kernel(const __grid_co
                         const unsigned a_hi = tmem + 8u * s, a_lo = a_hi + 96u;
                         const unsigned acc = s ? 1u : 0u;
                         tc5_mma_ts(d, a_hi, xb, acc, idesc);                       // re: taps hi * samples hi
-                        tc5_mma_ts(d + NR, a_hi, xb + 2 * PL16, acc, idesc);       // im
+                        if constexpr (CPLX) tc5_mma_ts(d + NR, a_hi, xb + 2 * PL16, acc, idesc);       // im
                         tc5_mma_ts(d, a_hi, xb + PL16, 1u, idesc);                 // taps hi * samples lo
-                        tc5_mma_ts(d + NR, a_hi, xb + 3 * PL16, 1u, idesc);
+                        if constexpr (CPLX) tc5_mma_ts(d + NR, a_hi, xb + 3 * PL16, 1u, idesc);
                         tc5_mma_ts(d, a_lo, xb, 1u, idesc);                        // taps lo * samples hi
-                        tc5_mma_ts(d + NR, a_lo, xb + 2 * PL16, 1u, idesc);
+                        if constexpr (CPLX) tc5_mma_ts(d + NR, a_lo, xb + 2 * PL16, 1u, idesc);
                     }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(done_u + 8 * g) : "memory");
@@ -391,7 +430,8 @@ void fir_tc5_build_tab(const unsigned short* hi, const unsigned short* lo, size_
 // Block-rows per CTA tile for a launch of `tiles8192` tiles of 8192 outputs: 32-row tiles (4096 outputs) halve the pipeline
 // fill (first tile stored after 10 K instead of 17 K cycles) and cost 4 % in the steady state (measured):
 // ahead below about 12 tiles per SM, behind above.  RRC_FIR_TC5_NR = 32 / 64 overrides (experiments).
-int fir_tc5_rows(long long tiles8192, int device) {
+int fir_tc5_rows(long long tiles8192, int device, bool real_stream) {
+    if (real_stream) return 64;                         // f32 streams: 128-row tiles (the same bytes per tile) measured 5-8 % slower
     if (const char* e = getenv("RRC_FIR_TC5_NR")) { const int v = atoi(e); if (v == 32 || v == 64) return v; }
     return tiles8192 < 12ll * sm_count(device) ? 32 : 64;
 }
@@ -399,10 +439,10 @@ int fir_tc5_rows(long long tiles8192, int device) {
 int fir_tc5_launch(int device, const FirTc5Args& a, const unsigned* tab_host, cudaStream_t st) {
     static bool ready[16] = {};
     const int dv = (device < 0 || device >= 16) ? 0 : device;
-    const bool nr32 = a.nr == 32;
     if (!ready[dv]) {
-        RRC_CUDA(cudaFuncSetAttribute(fir_tc5_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Geom<64>::SMEM));
-        RRC_CUDA(cudaFuncSetAttribute(fir_tc5_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Geom<32>::SMEM));
+        RRC_CUDA(cudaFuncSetAttribute(fir_tc5_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Geom<64>::smem(true)));
+        RRC_CUDA(cudaFuncSetAttribute(fir_tc5_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Geom<32>::smem(true)));
+        RRC_CUDA(cudaFuncSetAttribute(fir_tc5_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tc5Geom<64>::smem(false)));
         ready[dv] = true;
     }
     Tc5Params prm;
@@ -412,8 +452,14 @@ int fir_tc5_launch(int device, const FirTc5Args& a, const unsigned* tab_host, cu
     long long* dtrace = nullptr;
     if (want_trace) { RRC_CUDA(cudaMalloc((void**)&dtrace, TC5_TRACE_WORDS * 8)); RRC_CUDA(cudaMemsetAsync(dtrace, 0, TC5_TRACE_WORDS * 8, st)); }
     const unsigned grid = (unsigned)std::min<long long>(a.total_tiles, sm_count(device));
-    if (nr32) fir_tc5_kernel<32><<<grid, TC5_THREADS, Tc5Geom<32>::SMEM, st>>>(prm, dtrace);
-    else fir_tc5_kernel<64><<<grid, TC5_THREADS, Tc5Geom<64>::SMEM, st>>>(prm, dtrace);
+    if (a.real_stream) {
+        if (a.nr == 64) fir_tc5_kernel<64, false><<<grid, TC5_THREADS, Tc5Geom<64>::smem(false), st>>>(prm, dtrace);
+        else return fail(RRC_ERR_INVALID, "fir_tc5: %d block-rows per tile (f32 streams: 64)", a.nr);
+    } else {
+        if (a.nr == 32) fir_tc5_kernel<32, true><<<grid, TC5_THREADS, Tc5Geom<32>::smem(true), st>>>(prm, dtrace);
+        else if (a.nr == 64) fir_tc5_kernel<64, true><<<grid, TC5_THREADS, Tc5Geom<64>::smem(true), st>>>(prm, dtrace);
+        else return fail(RRC_ERR_INVALID, "fir_tc5: %d block-rows per tile (c32 streams: 32 or 64)", a.nr);
+    }
     RRC_CHECK_LAUNCH();
     count_launch();
     if (want_trace) {                                           // debug only: CTA 2's stamps, cycles relative to the earliest one

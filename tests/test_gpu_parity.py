@@ -193,6 +193,32 @@ def test_fir_tcgen05_kernel(R, monkeypatch, ntaps, n, nchan, rows):
         assert O.max_angle_err(d[0] / 0.7, np.angle(truth[1:] * np.conj(truth[:-1]))) <= DEMOD_BAR
 
 
+@pytest.mark.parametrize("ntaps,n,nchan", [
+    (64, 262_144, 1), (65, 8_256, 1), (16, 5_001, 2), (33, 70_001, 1), (64, 1_301, 5), (48, 16_415, 3), (64, 8192 * 150 + 77, 2)])
+def test_fir_tcgen05_kernel_f32_streams(R, monkeypatch, ntaps, n, nchan):
+    """fir_tc5_kernel on FirFilter<Float> streams (one component: three MMAs per k-step, f32 loads and stores): ragged
+    tiles, odd channel strides (4-byte aligned channels take the scalar loads); 64-row tiles."""
+    monkeypatch.setenv("RRC_FIR_TCGEN05", "2")
+    taps = O.low_pass_n(1.0, 0.2, ntaps)
+    f = R.Fir(taps)
+    assert f.uses_tensor_cores and not f.cplx and "fir_tc5_kernel" in f.kernel_name
+    stride = n + 1 if n % 2 == 0 else n
+    xs = np.zeros((nchan, stride), np.float32)
+    for c in range(nchan):
+        xs[c, :n] = O.synth_f32(500 + c, 0, n) * 0.5 + np.cos(2 * np.pi * 0.013 * (c + 1) * np.arange(n)).astype(np.float32)
+    out_n = f.out_count(n)
+    din = R.DeviceBuffer.from_numpy(xs)
+    ostride = out_n + 1 - (out_n % 2)
+    dy = R.DeviceBuffer(nchan * ostride * 4)
+    f.run_batch(din, stride, out_n - 1 + ntaps, dy, ostride, out_n, nchan)
+    assert f.kernel_name.startswith("fir_tc5_kernel")
+    y = dy.download(np.float32, nchan * ostride).reshape(nchan, ostride)[:, :out_n]
+    for c in range(nchan):
+        e = O.rel_rms(y[c], O.fir(xs[c, :n], taps, 1, f64=True))
+        print(f"fir_tc5 f32 T={ntaps} ch{c}: {e:.2e}")
+        assert e <= 2e-6
+
+
 @pytest.mark.parametrize("scale", [1e-20, 1.0, 3e18])
 @pytest.mark.parametrize("bad", [None, np.inf, np.nan])
 @pytest.mark.parametrize("rows", [32, 64])
