@@ -259,6 +259,15 @@ int rrc_rtlsdr_decode_plan(size_t in_len_bytes, size_t out_free, size_t* consume
 /* n_bytes/2 samples from device bytes to device c32 (any alignment). */
 int rrc_rtlsdr_decode_run(int device, const unsigned char* in_dev, size_t n_bytes, float* out_dev_c32, void* stream);
 int rrc_rtlsdr_decode_run_host(int device, const unsigned char* in_host, size_t n_bytes, float* out_host_c32, size_t* n_out);
+/* RtlSdrEncode::work (src/rtlsdr_encode.rs:22-52), the inverse wire format: Complex -> (u8 I, u8 Q) with
+ * ((s / 0.008) + 127).round().clamp(0, 255) as u8 — bit-exact (f32 division and addition, round half away from
+ * zero, NaN -> 0 like the saturating cast).  _plan: the reference loop run to its WaitForStream for `in_len`
+ * readable samples and `out_free_bytes` writable bytes: consume samples, produce 2 bytes each; then
+ * wait_on_output = 0: WaitForStream(src, 1), = 1: WaitForStream(dst, 2). */
+int rrc_rtlsdr_encode_plan(size_t in_len, size_t out_free_bytes, size_t* consume, size_t* produce_bytes,
+                           size_t* wait_need, int* wait_on_output);
+int rrc_rtlsdr_encode_run(int device, const float* in_dev_c32, size_t n, unsigned char* out_dev, void* stream);
+int rrc_rtlsdr_encode_run_host(int device, const float* in_host_c32, size_t n, unsigned char* out_host, size_t* n_out_bytes);
 /* Fused form: the FIR / FftFilter kernels decode u8 I/Q pairs in their first
  * load, so RtlSdrDecode -> FirFilter<Complex> / FftFilter chains never
  * materialise the c32 stream (and *_run_host moves 2 B/sample over PCIe).
@@ -475,6 +484,17 @@ int rrb_fft_stream_new(rrb_rstream_t* src, size_t size,
 /* RtlSdrDecode::new(src: ReadStream<u8>) -> (Self, ReadStream<Complex>)  (src/rtlsdr_decode.rs:9-16) */
 int rrb_rtlsdr_decode_new(rrb_rstream_t* src,
                           size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+/* RtlSdrEncode::new(src: ReadStream<Complex>) -> (Self, ReadStream<u8>)  (src/rtlsdr_encode.rs:12-20) */
+int rrb_rtlsdr_encode_new(rrb_rstream_t* src,
+                          size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);
+/* Capture egress: FileSink<T>::builder(path).mode(m).flush(f).build(src) (src/file_sink.rs:11-160) — raw little-endian
+ * samples of the stream's element size.  mode: RRB_FILE_CREATE fails when the file exists, RRB_FILE_OVERWRITE truncates,
+ * RRB_FILE_APPEND appends.  work(): everything readable is written, Again; WaitForStream(src, 1) on an empty stream.
+ * A DEVICE input ring is read through a pinned staging buffer.  A sink has no output stream. */
+#define RRB_FILE_CREATE    0
+#define RRB_FILE_OVERWRITE 1
+#define RRB_FILE_APPEND    2
+int rrb_file_sink_new(rrb_rstream_t* src, const char* path, int mode, int flush, int device, rrb_block_t** blk);
 /* Hilbert::new(src: ReadStream<Float>, ntaps, &WindowType) -> (Self, ReadStream<Complex>)  (src/hilbert.rs:35-60) */
 int rrb_hilbert_new(rrb_rstream_t* src, size_t ntaps, int window_type, float window_parm,
                     size_t out_bytes, int out_residency, int device, rrb_block_t** blk, rrb_rstream_t** out);

@@ -66,6 +66,7 @@ def _load(name: str) -> C.CDLL:
         "orc_quad_demod": (None, [vp, i64, f32, vp]),
         "orc_quad_demod_f64": (None, [vp, i64, f64, vp]),
         "orc_rtlsdr_decode": (None, [vp, i64, vp]),
+        "orc_rtlsdr_encode": (None, [vp, i64, vp]),
         "orc_hilbert_taps": (C.c_int, [vp, i64, vp]),
         "orc_hilbert_work": (None, [vp, vp, i64, vp, i64, vp, vp]),
         "orc_multiply_const_f32": (None, [vp, i64, f32, vp]),
@@ -323,6 +324,15 @@ def rtlsdr_decode(raw) -> np.ndarray:
     out = np.empty(len(raw) // 2, np.complex64)
     if len(out):
         lib().orc_rtlsdr_decode(_p(raw), len(raw), _p(out))
+    return out
+
+
+def rtlsdr_encode(x) -> np.ndarray:
+    """RtlSdrEncode (src/rtlsdr_encode.rs:22-26): c32 -> u8 I/Q pairs, round((s / 0.008) + 127) clamped to 0..255."""
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.empty(2 * len(x), np.uint8)
+    if len(x):
+        lib().orc_rtlsdr_encode(_p(x), len(x), _p(out))
     return out
 
 

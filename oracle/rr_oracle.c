@@ -522,6 +522,28 @@ void orc_rtlsdr_decode(const uint8_t* in, int64_t n_bytes, c32* out) {
     }
 }
 
+/* --------------------------------------------------------- RtlSdrEncode -- */
+
+/*
+ * src/rtlsdr_encode.rs:22-26,45-46: Complex -> (u8 I, u8 Q),
+ * ((sample / 0.008) + 127.0).round().clamp(0.0, 255.0) as u8 in f32; f32::round is
+ * half away from zero (roundf); clamp keeps NaN, the saturating `as u8` maps it to 0.
+ */
+static uint8_t orc_encode_sample(float s) {
+    volatile float q = s / 0.008f;                  /* volatile: keep the two roundings apart (no contraction) */
+    float v = roundf(q + 127.0f);
+    if (v != v) return 0;
+    if (v < 0.0f) v = 0.0f;
+    if (v > 255.0f) v = 255.0f;
+    return (uint8_t)v;
+}
+void orc_rtlsdr_encode(const c32* in, int64_t n, uint8_t* out) {
+    for (int64_t i = 0; i < n; ++i) {
+        out[2 * i] = orc_encode_sample(in[i].re);
+        out[2 * i + 1] = orc_encode_sample(in[i].im);
+    }
+}
+
 /* -------------------------------------------------------------- Hilbert -- */
 
 /* fir::hilbert, src/fir.rs:660-680 (window from orc_make_window). */

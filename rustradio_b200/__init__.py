@@ -9,7 +9,7 @@ library and raises `RrcError` if the library or a CUDA device is missing.
 from .api import (  # noqa: F401
     RrcError, lib, library_path, build_library, device_count,
     DeviceBuffer, PinnedBuffer, Fir, FftFilt, Resampler, quad_demod, quad_demod_host,
-    rtlsdr_decode, rtlsdr_decode_host, rtlsdr_decode_plan, Fft, fftstream_plan,
+    rtlsdr_decode, rtlsdr_decode_host, rtlsdr_decode_plan, rtlsdr_encode, rtlsdr_encode_host, rtlsdr_encode_plan, Fft, fftstream_plan,
     synth_f32, launch_count, fir_plan, fftfilt_plan, fftfilt_ref_fft_size,
     Event, stream_sync, device_sync, event_wait, device_numa_node, peer_enable, ipc_export, IpcMapping,
     Hilbert, make_window, hilbert_taps, multiply_const, add_const, complex_to_mag2, tee, IqBalance,

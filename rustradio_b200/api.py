@@ -122,6 +122,9 @@ _SIGS = {
     "rrc_rtlsdr_decode_plan": [_sz, _sz, _P(_sz), _P(_sz), _P(_sz), _P(_i)],
     "rrc_rtlsdr_decode_run": [_i, _vp, _sz, _vp, _vp],
     "rrc_rtlsdr_decode_run_host": [_i, _vp, _sz, _vp, _P(_sz)],
+    "rrc_rtlsdr_encode_plan": [_sz, _sz, _P(_sz), _P(_sz), _P(_sz), _P(_i)],
+    "rrc_rtlsdr_encode_run": [_i, _vp, _sz, _vp, _vp],
+    "rrc_rtlsdr_encode_run_host": [_i, _vp, _sz, _vp, _P(_sz)],
     "rrc_fir_set_input_u8iq": [_vp, _i],
     "rrc_fftfilt_set_input_u8iq": [_vp, _i],
     "rrc_make_window": [_i, _f, _sz, _vp],
@@ -674,6 +677,28 @@ def rtlsdr_decode_plan(in_len_bytes: int, out_free: int):
 
 def rtlsdr_decode(d_in, n_bytes: int, d_out, device: int = 0, stream: int = 0):
     _ck(lib().rrc_rtlsdr_decode_run(device, _ptr(d_in), n_bytes, _ptr(d_out), stream))
+
+
+def rtlsdr_encode_plan(in_len: int, out_free_bytes: int):
+    """(consume, produce_bytes, wait_need, wait_on_output) — src/rtlsdr_encode.rs:30-51."""
+    v = [_sz(0) for _ in range(3)]
+    w = _i(0)
+    _ck(lib().rrc_rtlsdr_encode_plan(in_len, out_free_bytes, *[C.byref(x) for x in v], C.byref(w)))
+    return v[0].value, v[1].value, v[2].value, w.value
+
+
+def rtlsdr_encode(d_in, n: int, d_out, device: int = 0, stream: int = 0):
+    _ck(lib().rrc_rtlsdr_encode_run(device, _ptr(d_in), n, _ptr(d_out), stream))
+
+
+def rtlsdr_encode_host(x: np.ndarray, device: int = 0) -> np.ndarray:
+    """RtlSdrEncode over a host buffer (pipelined H2D / kernel / D2H): c32 -> u8 I/Q bytes."""
+    x = np.ascontiguousarray(x, np.complex64)
+    out = np.empty(2 * len(x), np.uint8)
+    n = _sz(0)
+    _ck(lib().rrc_rtlsdr_encode_run_host(device, x.ctypes.data if len(x) else None, len(x), out.ctypes.data if len(out) else None, C.byref(n)))
+    assert n.value == len(out)
+    return out
 
 
 def rtlsdr_decode_host(raw: np.ndarray, device: int = 0) -> np.ndarray:

@@ -55,6 +55,8 @@ _SIGS = {
     "rrb_rational_resampler_new": [_vp, _sz, _sz, _sz, _i, _i, _P(_vp), _P(_vp)],
     "rrb_quadrature_demod_new": [_vp, C.c_float, _sz, _i, _i, _P(_vp), _P(_vp)],
     "rrb_rtlsdr_decode_new": [_vp, _sz, _i, _i, _P(_vp), _P(_vp)],
+    "rrb_rtlsdr_encode_new": [_vp, _sz, _i, _i, _P(_vp), _P(_vp)],
+    "rrb_file_sink_new": [_vp, C.c_char_p, _i, _i, _i, _P(_vp)],
     "rrb_fft_stream_new": [_vp, _sz, _sz, _i, _i, _P(_vp), _P(_vp)],
     "rrb_hilbert_new": [_vp, _sz, _i, C.c_float, _sz, _i, _i, _P(_vp), _P(_vp)],
     "rrb_multiply_const_new": [_vp, _i, C.c_float, C.c_float, _sz, _i, _i, _P(_vp), _P(_vp)],
@@ -302,6 +304,22 @@ def FftStream(src: ReadStream, size: int, size_bytes=DEFAULT_STREAM_SIZE, reside
 def RtlSdrDecode(src: ReadStream, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
     """RtlSdrDecode::new(src) (src/rtlsdr_decode.rs:9-16): ReadStream<u8> -> ReadStream<Complex>."""
     return _mk(_L().rrb_rtlsdr_decode_new, np.complex64, src, size_bytes, residency, device)
+
+
+def RtlSdrEncode(src: ReadStream, size_bytes=DEFAULT_STREAM_SIZE, residency=DEVICE, device=0):
+    """RtlSdrEncode::new(src) (src/rtlsdr_encode.rs:12-20): ReadStream<Complex> -> ReadStream<u8>."""
+    return _mk(_L().rrb_rtlsdr_encode_new, np.uint8, src, size_bytes, residency, device)
+
+
+FILE_CREATE, FILE_OVERWRITE, FILE_APPEND = 0, 1, 2
+
+
+def FileSink(src: ReadStream, path, mode: int = FILE_CREATE, flush: bool = False, device=0):
+    """FileSink::<T>::builder(path).mode(mode).flush(flush).build(src) (src/file_sink.rs:24-115); a sink: returns the block only."""
+    b = _vp()
+    _ck(_L().rrb_file_sink_new(src.h, str(path).encode(), mode, int(flush), device, C.byref(b)))
+    src._take()
+    return Block(b.value)
 
 
 def Hilbert(src: ReadStream, ntaps: int, window_type: int = 0, window_parm: float = 0.0, size_bytes=DEFAULT_STREAM_SIZE,

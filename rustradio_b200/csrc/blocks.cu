@@ -312,7 +312,7 @@ static int finish_output(Buffer& b, char* win, size_t bytes, Scratch& s, int dev
 
 // A device-resident input ring must live on the block's own device: the VMM mapping only has
 // access rights for its device and ordering between blocks relies on the per-device graph stream.
-static int check_src_device(ReadStream& src, int device, const char* who) {
+int check_src_device(ReadStream& src, int device, const char* who) {
     if (src.buffer().residency() == Residency::Device && src.buffer().device() != device)
         return fail(RRC_ERR_INVALID, "%s: input ring lives on device %d, block runs on device %d (cross-device chains need a host edge)",
                     who, src.buffer().device(), device);
@@ -697,6 +697,40 @@ int RtlSdrDecode::work(BlockRet* ret) {       // src/rtlsdr_decode.rs:18-48
         if (src_->buffer().residency() == Residency::Host) RRC_CUDA(cudaStreamSynchronize((cudaStream_t)graph_stream(device_)));
         src_->buffer().consume(isamples);
         dst_->buffer().produce(osamples, {});
+    }
+}
+
+// --------------------------------------------------------------- RtlSdrEncode -----
+int RtlSdrEncode::create(std::unique_ptr<ReadStream>& src, const StreamOpts& o, std::unique_ptr<RtlSdrEncode>* out) {
+    if (!src) return fail(RRC_ERR_INVALID, "src is NULL");
+    RRC_TRY(check_src_device(*src, o.device, "block constructor"));
+    if (src->buffer().elem() != 8) return fail(RRC_ERR_INVALID, "RtlSdrEncode: stream must carry Complex");
+    std::unique_ptr<RtlSdrEncode> b(new RtlSdrEncode());
+    b->device_ = o.device;
+    RRC_TRY(make_output(1, o, &b->dst_, &b->out_r_));
+    b->src_ = std::move(src);                 // last fallible step is behind us: `src` is consumed iff RRC_OK
+    *out = std::move(b);
+    return RRC_OK;
+}
+
+int RtlSdrEncode::work(BlockRet* ret) {       // src/rtlsdr_encode.rs:28-52
+    for (;;) {
+        const char* in; size_t in_len;
+        src_->buffer().read_window(&in, &in_len, nullptr);    // "TODO: handle tags" (:31): dropped
+        if (in_len == 0) { *ret = BlockRet::wait(src_.get(), 1); return RRC_OK; }            // :33-35
+        char* outp; size_t cap;
+        dst_->buffer().write_window(&outp, &cap);
+        if (cap < 2) { *ret = BlockRet::wait(dst_.get(), 2); return RRC_OK; }                // :37-39
+        const size_t isamples = std::min(in_len, cap / 2);    // :41
+        const size_t obytes = isamples * 2;
+        const char* din; char* dout;
+        RRC_TRY(stage_input(src_->buffer(), in, isamples * 8, sin_, device_, &din));
+        RRC_TRY(stage_output(dst_->buffer(), outp, obytes, sout_, device_, &dout));
+        RRC_TRY(rrc_rtlsdr_encode_run(device_, (const float*)din, isamples, (unsigned char*)dout, graph_stream(device_)));
+        RRC_TRY(finish_output(dst_->buffer(), outp, obytes, sout_, device_));
+        if (src_->buffer().residency() == Residency::Host) RRC_CUDA(cudaStreamSynchronize((cudaStream_t)graph_stream(device_)));
+        src_->buffer().consume(isamples);
+        dst_->buffer().produce(obytes, {});
     }
 }
 

@@ -341,6 +341,21 @@ private:
     Scratch sin_, sout_;
 };
 
+// RtlSdrEncode (src/rtlsdr_encode.rs:12-52): ReadStream<Complex> -> WriteStream<u8>, tags dropped.
+class RtlSdrEncode : public Block {
+public:
+    static int create(std::unique_ptr<ReadStream>& src, const StreamOpts& o, std::unique_ptr<RtlSdrEncode>* out);
+    int work(BlockRet* ret) override;
+    const char* block_name() const override { return "RtlSdrEncode"; }
+    bool eof() override { return src_->eof(); }
+private:
+    RtlSdrEncode() = default;
+    std::unique_ptr<ReadStream> src_;
+    std::unique_ptr<WriteStream> dst_;
+    int device_ = 0;
+    Scratch sin_, sout_;
+};
+
 // Hilbert (src/hilbert.rs:22-129): ReadStream<Float> -> WriteStream<Complex>, identity tags.
 class Hilbert : public Block {
 public:
@@ -437,6 +452,7 @@ struct HostStage {
 };
 
 int make_output_stream(size_t elem, const StreamOpts& o, std::unique_ptr<WriteStream>* w, std::unique_ptr<ReadStream>* r);
+int check_src_device(ReadStream& src, int device, const char* who);   // a device-resident src ring must live on `device`
 
 // FileSource<T> (src/file_source.rs:11-153): raw little-endian samples from a file (a cf32 capture,
 // /dev/zero ...), whole samples only, optional repeat.  SURVEY 8f rank 1.
@@ -455,6 +471,26 @@ private:
     size_t elem_ = 1;
     Repeat repeat_;
     std::vector<char> buf_, scratch_;      // carried partial bytes (`buf`, :50) / host read buffer
+    HostStage stage_;
+};
+
+// FileSink<T> (src/file_sink.rs:11-160): raw little-endian samples to a file; Mode Create (fails if the file exists) /
+// Overwrite / Append; work() writes everything readable and returns Again, WaitForStream(src, 1) on an empty stream.
+// A DEVICE input ring is read through a pinned staging buffer (one D2H copy per work() on the blocks' stream).
+class FileSink : public Block {
+public:
+    enum Mode { Create = 0, Overwrite = 1, Append = 2 };
+    static int create(std::unique_ptr<ReadStream>& src, const char* path, int mode, bool flush, int device, std::unique_ptr<FileSink>* out);
+    ~FileSink() override;
+    int work(BlockRet* ret) override;
+    const char* block_name() const override { return "FileSink"; }
+    bool eof() override { return src_->eof(); }
+private:
+    FileSink() = default;
+    std::unique_ptr<ReadStream> src_;
+    int fd_ = -1, device_ = 0;
+    bool flush_ = false;
+    std::string path_;
     HostStage stage_;
 };
 

@@ -233,6 +233,23 @@ int rrb_rtlsdr_decode_new(rrb_rstream_t* src, size_t bytes, int res, int device,
     return finish(std::move(b), blk, out, src);
 }
 
+int rrb_rtlsdr_encode_new(rrb_rstream_t* src, size_t bytes, int res, int device, rrb_block_t** blk, rrb_rstream_t** out) {
+    if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");
+    std::unique_ptr<rr::RtlSdrEncode> b;
+    RRC_TRY(rr::RtlSdrEncode::create(src->s, opts(bytes, res, device), &b));
+    return finish(std::move(b), blk, out, src);
+}
+int rrb_file_sink_new(rrb_rstream_t* src, const char* path, int mode, int flush, int device, rrb_block_t** blk) {
+    if (!src || !path || !blk) return fail(RRC_ERR_INVALID, "NULL argument");
+    std::unique_ptr<rr::FileSink> b;
+    RRC_TRY(rr::FileSink::create(src->s, path, mode, flush != 0, device, &b));
+    delete src;                        // its stream has been moved into the block
+    auto* h = new rrb_block();
+    h->b = std::move(b);
+    *blk = h;
+    return RRC_OK;
+}
+
 int rrb_hilbert_new(rrb_rstream_t* src, size_t ntaps, int window_type, float window_parm, size_t bytes, int res, int device,
                     rrb_block_t** blk, rrb_rstream_t** out) {
     if (!src || !blk || !out) return fail(RRC_ERR_INVALID, "NULL argument");

@@ -1,4 +1,4 @@
-// ingest.cu — RtlSdrDecode: RTL-SDR's byte format (u8 I, u8 Q) -> Complex<f32> on sm_100a.
+// ingest.cu — RtlSdrDecode / RtlSdrEncode: RTL-SDR's byte format (u8 I, u8 Q) <-> Complex<f32> on sm_100a.
 //
 // Replaces RtlSdrDecode::work (rustradio src/rtlsdr_decode.rs:18-48):
 //   out[k] = Complex((in[2k] - 127.0) * 0.008, (in[2k+1] - 127.0) * 0.008)   (f32, sub then mul)
@@ -44,6 +44,40 @@ __global__ void __launch_bounds__(256) rtlsdr_decode_bytes_kernel(const unsigned
     const long long nthreads = (long long)gridDim.x * blockDim.x;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += nthreads)
         out[k] = make_float2(dec1(in[2 * k]), dec1(in[2 * k + 1]));
+}
+
+// ---- RtlSdrEncode (src/rtlsdr_encode.rs:22-26): ((s / 0.008) + 127).round().clamp(0, 255) as u8.  Single correctly rounded
+// f32 division and addition (never a multiply by the reciprocal, never contracted), round half away from zero, NaN -> 0
+// like Rust's saturating float -> int cast (fmaxf(NaN, 0) = 0).
+__device__ __forceinline__ unsigned int enc1(float s) {
+    const float v = roundf(__fadd_rn(__fdiv_rn(s, 0.008f), 127.0f));
+    return (unsigned int)fminf(fmaxf(v, 0.0f), 255.0f);
+}
+// Fast path: `in` 16-byte aligned, `out` 4-byte aligned: 2 samples per thread-iteration (128-bit load, 32-bit store).
+__global__ void __launch_bounds__(256) rtlsdr_encode_kernel(const float4* __restrict__ in, unsigned int* __restrict__ out, long long npairs) {
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * nthreads < npairs; i += 4 * nthreads) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldcs(in + i + k * nthreads);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            __stcs(out + i + k * nthreads, enc1(v[k].x) | (enc1(v[k].y) << 8) | (enc1(v[k].z) << 16) | (enc1(v[k].w) << 24));
+    }
+    for (; i < npairs; i += nthreads) {
+        const float4 v = in[i];
+        out[i] = enc1(v.x) | (enc1(v.y) << 8) | (enc1(v.z) << 16) | (enc1(v.w) << 24);
+    }
+}
+// Any alignment: one sample per thread-iteration (64-bit load, two byte stores).
+__global__ void __launch_bounds__(256) rtlsdr_encode_bytes_kernel(const float2* __restrict__ in, unsigned char* __restrict__ out, long long n) {
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += nthreads) {
+        const float2 v = in[k];
+        out[2 * k] = (unsigned char)enc1(v.x);
+        out[2 * k + 1] = (unsigned char)enc1(v.y);
+    }
 }
 
 }  // namespace rrc
@@ -122,6 +156,79 @@ int rrc_rtlsdr_decode_run_host(int device, const unsigned char* in_host, size_t 
             s = pipe.stage_in(i, in_host + 2 * off, n * 2);
             if (s == RRC_OK) s = rrc_rtlsdr_decode_run(device, (const unsigned char*)pipe.d_in[i & 1], n * 2, (float*)pipe.d_out[i & 1], pipe.s_comp);
             if (s == RRC_OK) s = pipe.drain_out(i, out_host + 2 * off, n * sizeof(float2));
+        }
+        if (s == RRC_OK) s = pipe.finish();
+    }
+    pipe.destroy();
+    return s;
+}
+
+int rrc_rtlsdr_encode_plan(size_t in_len, size_t out_free_bytes, size_t* consume, size_t* produce_bytes,
+                           size_t* wait_need, int* wait_on_output) {
+    if (!consume || !produce_bytes || !wait_need || !wait_on_output) return fail(RRC_ERR_INVALID, "NULL argument");
+    // The loop of src/rtlsdr_encode.rs:30-51 run to its WaitForStream.
+    const size_t take = std::min(in_len, out_free_bytes / 2);             // :41
+    *consume = take;
+    *produce_bytes = 2 * take;
+    if (in_len - take == 0) { *wait_on_output = 0; *wait_need = 1; }      // :33-35
+    else { *wait_on_output = 1; *wait_need = 2; }                         // :37-39
+    return RRC_OK;
+}
+
+int rrc_rtlsdr_encode_run(int device, const float* in_dev_c32, size_t n, unsigned char* out_dev, void* stream) {
+    if (n == 0) return RRC_OK;
+    if (!in_dev_c32 || !out_dev) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    RRC_CUDA(cudaSetDevice(device));
+    cudaStream_t st = as_stream(stream);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(in_dev_c32), o = reinterpret_cast<uintptr_t>(out_dev);
+    const float2* in = reinterpret_cast<const float2*>(in_dev_c32);
+    const int max_grid = sm_count(device) * 8;
+    // head: 0 or 1 samples so that the body's input is 16-byte and its output 4-byte aligned
+    const bool in_odd = (a & 15) == 8, out_odd = (o & 3) == 2;
+    const bool fast = (a & 7) == 0 && (o & 1) == 0 && in_odd == out_odd;
+    size_t done = 0;
+    if (fast) {
+        const size_t head = in_odd ? 1 : 0;
+        const size_t npairs = (n - std::min(n, head)) / 2;
+        if (npairs) {
+            const unsigned grid = (unsigned)std::min<size_t>((npairs + 256 * 4 - 1) / (256 * 4), (size_t)max_grid);
+            rtlsdr_encode_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(in + head),
+                                                       reinterpret_cast<unsigned int*>(out_dev + 2 * head), (long long)npairs);
+            RRC_CHECK_LAUNCH();
+            count_launch();
+        }
+        if (head && n) {
+            rtlsdr_encode_bytes_kernel<<<1, 32, 0, st>>>(in, out_dev, 1);
+            RRC_CHECK_LAUNCH();
+            count_launch();
+        }
+        done = std::min(n, head + 2 * npairs);
+    }
+    if (done < n) {                                             // tail sample, or everything when unaligned
+        const size_t rest = n - done;
+        const unsigned grid = (unsigned)std::min<size_t>((rest + 255) / 256, (size_t)max_grid * 4);
+        rtlsdr_encode_bytes_kernel<<<grid, 256, 0, st>>>(in + done, out_dev + 2 * done, (long long)rest);
+        RRC_CHECK_LAUNCH();
+        count_launch();
+    }
+    return RRC_OK;
+}
+
+int rrc_rtlsdr_encode_run_host(int device, const float* in_host_c32, size_t n, unsigned char* out_host, size_t* n_out_bytes) {
+    if (n_out_bytes) *n_out_bytes = 2 * n;
+    if (n == 0) return RRC_OK;
+    if (!in_host_c32 || !out_host) return fail(RRC_ERR_INVALID, "in/out is NULL");
+    Pipe pipe;
+    int s = pipe.init(device);
+    if (s == RRC_OK) {
+        const size_t chunk = pipe_chunk_samples_for(n);
+        s = pipe.reserve(std::min(chunk, n) * sizeof(float2), std::min(chunk, n) * 2);
+        int i = 0;
+        for (size_t off = 0, m = 0; s == RRC_OK && off < n; off += m, ++i) {
+            m = pipe_next_chunk((size_t)i, n - off, chunk);
+            s = pipe.stage_in(i, reinterpret_cast<const char*>(in_host_c32) + off * sizeof(float2), m * sizeof(float2));
+            if (s == RRC_OK) s = rrc_rtlsdr_encode_run(device, (const float*)pipe.d_in[i & 1], m, (unsigned char*)pipe.d_out[i & 1], pipe.s_comp);
+            if (s == RRC_OK) s = pipe.drain_out(i, out_host + 2 * off, m * 2);
         }
         if (s == RRC_OK) s = pipe.finish();
     }

@@ -1,9 +1,10 @@
-// sources.cu — capture ingest for the hot path (second half): raw sample files
+// sources.cu — capture ingest and egress for the hot path (second half): raw sample files
 // (cf32 / rf32 / u8 ...) and SigMF recordings / archives streamed into a host, pinned-host or DEVICE
 // ring.  Restates
 //   FileSource<T>::new / builder().repeat() / work()      rustradio src/file_source.rs:11-153
 //   SigMFSource<T>::new2 / from_recording / from_archive / work()   src/sigmf.rs:229-613
 //   Repeat::again                                          src/lib.rs:449-506
+//   FileSink<T>::new / builder().mode().flush() / work()   src/file_sink.rs:11-160
 // Samples on disk are little-endian (Sample::parse, src/lib.rs:724-800), which on this platform is the
 // in-memory layout, so "parsing" is a byte copy; whole samples only (a partial tail is never produced).
 // The file I/O itself is host work: a read lands in a page-locked staging buffer and goes to a device
@@ -300,6 +301,53 @@ int SigMFSource::work(BlockRet* ret) {        // src/sigmf.rs:563-612
     dst_->buffer().produce(samples, {});
     buf_.erase(buf_.begin(), buf_.begin() + (ptrdiff_t)(samples * elem_));                    // :608
     *ret = BlockRet::wait(dst_.get(), 1);                                                     // :609
+    return RRC_OK;
+}
+
+// ------------------------------------------------------------------- FileSink -----
+int FileSink::create(std::unique_ptr<ReadStream>& src, const char* path, int mode, bool flush, int device, std::unique_ptr<FileSink>* out) {
+    if (!src || !path) return fail(RRC_ERR_INVALID, "FileSink: bad arguments");
+    RRC_TRY(check_src_device(*src, device, "block constructor"));
+    int flags = O_WRONLY | O_CLOEXEC;
+    switch (mode) {                                                        // src/file_sink.rs:93-105
+    case Create: flags |= O_CREAT | O_EXCL; break;
+    case Overwrite: flags |= O_CREAT | O_TRUNC; break;
+    case Append: flags |= O_CREAT | O_APPEND; break;
+    default: return fail(RRC_ERR_INVALID, "FileSink: unknown mode %d", mode);
+    }
+    const int fd = open(path, flags, 0666);
+    if (fd < 0) return fail(RRC_ERR_INVALID, "file io on %s: %s", path, strerror(errno));      // Error::file_io, :107
+    std::unique_ptr<FileSink> b(new FileSink());
+    b->fd_ = fd; b->path_ = path; b->flush_ = flush; b->device_ = device;
+    b->src_ = std::move(src);                 // `src` is consumed iff RRC_OK
+    *out = std::move(b);
+    return RRC_OK;
+}
+FileSink::~FileSink() { if (fd_ >= 0) close(fd_); }     // writes are unbuffered here: nothing left to flush (Drop, :124-133)
+
+int FileSink::work(BlockRet* ret) {           // src/file_sink.rs:139-159
+    const char* in; size_t n;
+    src_->buffer().read_window(&in, &n, nullptr);
+    if (n == 0) { *ret = BlockRet::wait(src_.get(), 1); return RRC_OK; }
+    const size_t bytes = n * src_->buffer().elem();
+    const char* from = in;
+    if (src_->buffer().residency() == Residency::Device) {
+        RRC_CUDA(cudaSetDevice(device_));
+        cudaStream_t st = (cudaStream_t)graph_stream(device_);
+        RRC_TRY(stage_.reserve(bytes));
+        RRC_CUDA(cudaMemcpyAsync(stage_.ptr, in, bytes, cudaMemcpyDeviceToHost, st));
+        RRC_CUDA(cudaStreamSynchronize(st));
+        from = stage_.ptr;
+    }                                         // host rings: a producing block has synchronised before produce() (finish_output)
+    size_t off = 0;
+    while (off < bytes) {                     // write_all
+        const ssize_t w = write(fd_, from + off, bytes - off);
+        if (w < 0) { if (errno == EINTR) continue; return fail(RRC_ERR_INVALID, "file io on %s: %s", path_.c_str(), strerror(errno)); }
+        off += (size_t)w;
+    }
+    if (flush_ && fsync(fd_) < 0 && errno != EINVAL && errno != EROFS) return fail(RRC_ERR_INVALID, "flush of %s: %s", path_.c_str(), strerror(errno));
+    src_->buffer().consume(n);
+    *ret = BlockRet::again();
     return RRC_OK;
 }
 

@@ -1,6 +1,6 @@
 //! The GPU blocks behind rustradio's `Block` trait (src/block.rs:115-126): `CudaFirFilter<T>` with its builder
 //! (`deci`, `translate`), `CudaFftFilter` / `CudaFftFilterFloat`, `CudaRationalResampler<T>` with its typestate
-//! builder, `CudaQuadratureDemod`, `CudaRtlSdrDecode`.
+//! builder, `CudaQuadratureDemod`, `CudaRtlSdrDecode`, `CudaRtlSdrEncode`.
 //!
 //! This variant keeps rustradio's own host-resident streams (`ReadStream`/`WriteStream`,
 //! src/stream.rs:180-327) and stages each `work()` window through device scratch, which needs no
@@ -424,6 +424,45 @@ impl Block for CudaRtlSdrDecode {
             }
             inp.consume(isamples);
             out.produce(osamples, &[]);
+        }
+    }
+}
+
+/// GPU `RtlSdrEncode`: `new(src)` like the macro-generated src/rtlsdr_encode.rs:12-20.
+pub struct CudaRtlSdrEncode {
+    dev: i32,
+    sin: Scratch,
+    sout: Scratch,
+    src: ReadStream<Complex>,
+    dst: WriteStream<u8>,
+}
+unsafe impl Send for CudaRtlSdrEncode {}
+impl CudaRtlSdrEncode {
+    pub fn new(src: ReadStream<Complex>) -> (Self, ReadStream<u8>) {
+        let (dst, dr) = rustradio::stream::new_stream();
+        (Self { dev: 0, sin: Scratch::new(0), sout: Scratch::new(0), src, dst }, dr)
+    }
+}
+impl BlockName for CudaRtlSdrEncode { fn block_name(&self) -> &str { "CudaRtlSdrEncode" } }
+impl BlockEOF for CudaRtlSdrEncode { fn eof(&mut self) -> bool { self.src.eof() } }
+impl Block for CudaRtlSdrEncode {
+    fn work(&mut self) -> Result<BlockRet<'_>> {
+        loop {
+            let (inp, _) = self.src.read_buf()?;                  // tags dropped (:31)
+            if inp.is_empty() { return Ok(BlockRet::WaitForStream(&self.src, 1)); }
+            let mut out = self.dst.write_buf()?;
+            if out.len() < 2 { return Ok(BlockRet::WaitForStream(&self.dst, 2)); }
+            let isamples = inp.len().min(out.len() / 2);          // :41
+            let obytes = isamples * 2;
+            let (din, dout) = (self.sin.reserve(isamples * 8)?, self.sout.reserve(obytes)?);
+            unsafe {
+                check(ffi::rrc_memcpy_h2d(self.dev, din, inp.slice().as_ptr().cast(), isamples * 8, ptr::null_mut()))?;
+                check(ffi::rrc_rtlsdr_encode_run(self.dev, din.cast(), isamples, dout.cast(), ptr::null_mut()))?;
+                check(ffi::rrc_memcpy_d2h(self.dev, out.slice().as_mut_ptr().cast(), dout, obytes, ptr::null_mut()))?;
+                check(ffi::rrc_stream_sync(self.dev, ptr::null_mut()))?;
+            }
+            inp.consume(isamples);
+            out.produce(obytes, &[]);
         }
     }
 }

@@ -162,7 +162,8 @@ def test_rust_blocks_cover_the_reference_constructors():
     for needle in ("pub fn builder(taps: impl Into<Vec<T>>) -> CudaFirFilterBuilder<T>", "pub fn deci(mut self, deci: usize) -> Self",
                    "pub fn translate(mut self, samp_rate: Float, freq: Float) -> Self", "impl GpuSample for Float",
                    "pub type CudaFftFilterFloat = CudaFftFilterT<Float>;", "pub struct CudaRationalResamplerBuilderBoth<T>",
-                   "pending == 0 && self.src.eof()", "pub struct CudaQuadratureDemod", "pub struct CudaRtlSdrDecode"):
+                   "pending == 0 && self.src.eof()", "pub struct CudaQuadratureDemod", "pub struct CudaRtlSdrDecode",
+                   "pub struct CudaRtlSdrEncode"):
         assert needle in rs, needle
     # every ffi function the blocks call exists in the generated binding
     ffi = (ROOT / "rustradio_b200" / "rust" / "rustradio-cuda" / "src" / "ffi.rs").read_text()

@@ -1,7 +1,19 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "tcgen05 or config1_full or f32_streams" -x 2>&1 | tail -4 | tee gpurun_out/o_pytest.txt
-for n in 8388608 33554432 134217728; do
-for v in 1 0; do
-RRC_FIR_TCGEN05=$v timeout 300 python bench.py --config c1f --n $n --steps 20 --warmup 3 --headline-only --no-e2e --no-cpu --sustain 0 > gpurun_out/o_tmp.json 2> gpurun_out/o_c1_tc5.err; python -c "import json;d=json.load(open('gpurun_out/o_tmp.json'));print('c1f n $n RRC_FIR_TCGEN05=$v', round(d['ms_per_step']*1000,2),'us', round(d['roofline']['frac'],3), d['roofline']['kernel'][:16])" || tail -3 gpurun_out/o_c1_tc5.err
-done; done 2>&1 | tee gpurun_out/o_c1f_sizes.txt
+timeout 900 python -m pytest tests/test_egress.py -q -m gpu 2>&1 | tail -15 | tee gpurun_out/o_pytest.txt
+python - <<'PY'
+import numpy as np, time, torch
+import rustradio_b200 as R
+n = 1 << 28
+din = R.DeviceBuffer(n * 8); R.synth_f32(din, 5, 0, 2 * n)
+dout = R.DeviceBuffer(2 * n)
+for _ in range(3): R.rtlsdr_encode(din, n, dout)
+R.device_sync()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s = torch.cuda.current_stream()
+ev0.record(s)
+for _ in range(10): R.rtlsdr_encode(din, n, dout, 0, s.cuda_stream)
+ev1.record(s); ev1.synchronize()
+ms = ev0.elapsed_time(ev1) / 10
+print(f"rtlsdr_encode 2^28 samples: {ms:.3f} ms, {n * 10 / ms / 1e6:.0f} GB/s algorithmic (8 B in + 2 B out per sample)")
+PY
