@@ -646,6 +646,7 @@ int rrc_fftfilt_destroy(rrc_fftfilt_t* h) {
     cudaFree(h->tw1); cudaFree(h->tw2); cudaFree(h->hist[0]); cudaFree(h->hist[1]);
     if (h->state_ev) cudaEventDestroy(h->state_ev);
     fold_destroy(h);
+    poly_destroy(h);
     h->pipe.destroy();
     delete h;
     return RRC_OK;
@@ -730,11 +731,16 @@ int rrc_fftfilt_decim_run(rrc_fftfilt_t* h, const float* in, size_t n, size_t de
     if (h->real) return fail(RRC_ERR_UNSUPPORTED, "fused decimation is not implemented for real (f32) streams");
     // deci == 8: folded spectrum + 8x smaller inverse transform (fftfilt_fold.cu); 65536-point
     // cluster kernel for 12289 < ntaps <= 49153.  RRC_FFTFILT_NO_FOLD=1 forces the store-predicate path.
-    if (fold_supported(h, deci) == RRC_OK) {
+    // 2 <= deci <= 16: polyphase form (fftfilt_poly.cu: deci forward transforms on the deci-times slower branch streams, one
+    // inverse per block).  RRC_FFTFILT_NO_POLY=1 falls through to the fold kernel / the store predicate.
+    const bool poly = poly_supported(h, deci) == RRC_OK;
+    if (poly || fold_supported(h, deci) == RRC_OK) {
         const float2* hist_used = h->hist_ext ? h->hist_ext : h->hist[h->cur];
-        // the fold kernel reads hist_ext / hist[cur] and writes the next history itself (one launch);
+        // both kernels read hist_ext / hist[cur] and write the next history themselves (one launch);
         // RRC_ERR_UNSUPPORTED = nothing was launched (no kept output in this call)
-        const int s = cnt ? fold_launch(h, in, n, out, cnt, skip, as_stream(stream)) : RRC_ERR_UNSUPPORTED;
+        const int s = !cnt ? RRC_ERR_UNSUPPORTED
+                    : poly ? poly_launch(h, in, n, out, cnt, deci, skip, as_stream(stream))
+                           : fold_launch(h, in, n, out, cnt, skip, as_stream(stream));
         h->hist_ext = nullptr;                                                          // one-shot
         if (s != RRC_OK && s != RRC_ERR_UNSUPPORTED) return s;
         if (s == RRC_ERR_UNSUPPORTED && h->T1 > 0) {

@@ -17,6 +17,15 @@ struct rrc_fold_tables {
     int max_clusters = 0;       // co-resident clusters (cudaOccupancyMaxActiveClusters)
 };
 
+// Tables of the polyphase decimating kernel (fftfilt_poly_core.cuh), built lazily for the decimation of the first call.
+struct rrc_poly_tables {
+    int D = 0;                  // decimation the tables were built for; 0 = not built
+    float2* Hph[16] = {};       // by skip mod D: [D][16384] spectra of the polyphase branches, phase-C order
+    float4* scratch = nullptr;  // [clusters][C][4][8192] partial sums on their way to the block's finisher CTA
+    size_t scratch_bytes = 0;
+    int max_clusters[3] = {0, 0, 0};   // co-resident clusters for C = 1, 2, 4
+};
+
 struct rrc_fftfilt {
     int device = 0;
     size_t ntaps = 0;
@@ -53,6 +62,7 @@ struct rrc_fftfilt {
     bool state_dirty = false;
     rrc::Pipe pipe;
     rrc_fold_tables fold;
+    rrc_poly_tables poly;
 };
 
 namespace rrc {
@@ -63,4 +73,10 @@ int fold_supported(const rrc_fftfilt* h, size_t deci);
 int fold_launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out,
                 size_t skip, cudaStream_t st);
 void fold_destroy(rrc_fftfilt* h);
+// fftfilt_poly.cu: FftFilter + decimate-by-D as a polyphase filter (D forward transforms, one inverse per block).
+// Same convention: RRC_ERR_UNSUPPORTED = not covered / nothing launched.
+int poly_supported(const rrc_fftfilt* h, size_t deci);
+int poly_launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, size_t deci,
+                size_t skip, cudaStream_t st);
+void poly_destroy(rrc_fftfilt* h);
 }  // namespace rrc

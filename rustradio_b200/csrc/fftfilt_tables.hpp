@@ -11,6 +11,7 @@
 #include "fftfilt16_core.cuh"
 #include "fftfilt_fold_core.cuh"
 #include "fftfilt_pk.cuh"
+#include "fftfilt_poly_core.cuh"
 
 namespace rrc { namespace fftk {
 
@@ -151,3 +152,33 @@ inline void build_fold_tables(const float* taps, size_t ntaps, int nc, std::vect
 }
 
 }}  // namespace rrc::fftf
+
+namespace rrc { namespace fftp {
+
+// Spectra of the D polyphase branches h_r[q] = h[D q + smod - r] (fftfilt_poly_core.cuh; smod = skip mod D), each in phase
+// C's row order:  Hph[r*16384 + (k1*32 + k2)*16 + k3] = FFT_16384(h_r)[k1 + 32 k2 + 1024 k3] / 16384.
+// Followed by the rows k2 = l of every branch in the padded shared-memory layout of fftk::load_hres (one bulk copy per
+// branch):  Hph[D*16384 + r*HRES_ELEMS + tid*HRES_PITCH + k3].
+inline void build_poly_tables(const float* taps, size_t ntaps, int D, int smod, std::vector<float2>& Hph) {
+    Hph.assign((size_t)D * (fftk::N + fftk::HRES_ELEMS), make_float2(0.f, 0.f));
+    std::vector<std::complex<double>> H(fftk::N);
+    for (int r = 0; r < D; ++r) {
+        std::fill(H.begin(), H.end(), std::complex<double>(0.0, 0.0));
+        for (long long q = 0; q < fftk::N; ++q) {
+            const long long j = (long long)D * q + smod - r;
+            if (j >= 0 && j < (long long)ntaps) H[q] = {(double)taps[2 * j], (double)taps[2 * j + 1]};
+        }
+        fftk::fft_host(H);
+        for (int P = 0; P < 1024; ++P) {
+            const int k1 = P >> 5, k2 = P & 31;
+            for (int k3 = 0; k3 < 16; ++k3) {
+                const auto v = H[k1 + 32 * k2 + 1024 * k3] / (double)fftk::N;
+                Hph[(size_t)r * fftk::N + (size_t)P * 16 + k3] = make_float2((float)v.real(), (float)v.imag());
+            }
+        }
+        for (int t = 0; t < fftk::NT; ++t)
+            fftk::load_hres(t, Hph.data() + (size_t)r * fftk::N, Hph.data() + (size_t)D * fftk::N + (size_t)r * fftk::HRES_ELEMS);
+    }
+}
+
+}}  // namespace rrc::fftp

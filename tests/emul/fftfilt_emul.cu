@@ -225,3 +225,48 @@ extern "C" int emul_fftfilt_fold(int nc, const float* taps, long long ntaps, con
     return nc == 1 ? emul_fold_t<1>(taps, ntaps, in, n, hist, out, skip, n_out)
                    : emul_fold_t<4>(taps, ntaps, in, n, hist, out, skip, n_out);
 }
+
+// Polyphase decimating kernel (fftfilt_poly_core.cuh): D forward transforms, the running sum over the
+// branches in a per-thread accumulator array (tensor memory on the GPU), one inverse transform.  Pairs of branches are
+// fetched with 128-bit loads where the alignment allows, the second one parked in the stash.
+extern "C" int emul_fftfilt_poly(const float* taps, long long ntaps, const float* in, long long n, const float* hist,
+                                 float* out, long long deci, long long skip, long long n_out) {
+    namespace fp = rrc::fftp;
+    const int T1_total = (int)ntaps - 1;
+    std::vector<float2> h(T1_total > 0 ? T1_total : 1, make_float2(0.f, 0.f));
+    if (hist && T1_total > 0) memcpy(h.data(), hist, sizeof(float2) * T1_total);
+    std::vector<float2> Hp0, tw1, tw2, Hph;
+    build_tables(taps, (size_t)std::min<long long>(ntaps, 8193), Hp0, tw1, tw2);      // tw1, tw2 only
+    const int smod = (int)(skip % deci);
+    fp::build_poly_tables(taps, (size_t)ntaps, (int)deci, smod, Hph);
+    fp::PolyIO io;
+    io.b.in = reinterpret_cast<const float2*>(in); io.b.hist = h.data(); io.b.out = reinterpret_cast<float2*>(out);
+    io.b.n_in = n; io.b.n_out = n_out; io.b.T1_total = T1_total;
+    io.b.T1 = fp::poly_T1(ntaps, (int)deci, smod); io.b.V = N - io.b.T1; io.b.shift = 0; io.b.deci = 1; io.b.skip = 0;
+    io.D = (int)deci; io.sbase = skip - smod;
+    if (n_out <= 0) return 0;
+    const long long nblocks = (n_out + io.b.V - 1) / io.b.V;
+    std::vector<float2> sm(SMEM_ELEMS), accv(512 * 32), stashv(512 * 32), regs(512 * 32);
+    fp::HostAcc acc{accv.data()}, stash{stashv.data()};
+    for (long long blk = 0; blk < nblocks; ++blk) {
+        bool stashed = false;
+        for (int r = 0; r < io.D; ++r) {
+            const bool pair = !stashed && fp::poly_pair_ok(io, blk, r);
+            for (int t = 0; t < NT; ++t) {
+                float2 v[32];
+                if (stashed) fp::poly_load_stash(t, v, stash);
+                else if (pair) fp::poly_load_pair(t, blk, r, io, v, stash);
+                else fp::poly_load(t, blk, r, io, v);
+                phase_a_linear_compute(t, tw1.data(), v);
+                memcpy(&regs[t * 32], v, sizeof v);
+            }
+            stashed = pair;
+            for (int t = 0; t < NT; ++t) { float2 v[32]; memcpy(v, &regs[t * 32], sizeof v); phase_a_linear_store(t, sm.data(), v); }
+            for (int t = 0; t < NT; ++t) phase_mid_b(t, tw2.data(), sm.data());
+            for (int t = 0; t < NT; ++t) fp::phase_c_acc(t, Hph.data() + (size_t)r * N, Hph.data() + (size_t)io.D * N + (size_t)r * HRES_ELEMS, sm.data(), acc, r == 0, r == io.D - 1);
+        }
+        for (int t = 0; t < NT; ++t) phase_mid_bi(t, tw2.data(), sm.data());
+        for (int t = 0; t < NT; ++t) phase_ai<false, false>(t, blk, io.b, tw1.data(), sm.data());
+    }
+    return 0;
+}

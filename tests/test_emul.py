@@ -148,3 +148,46 @@ def test_emulated_fold_kernel_streaming_history(emul_fold):
     skip2 = (-cut) % 8                      # RationalResampler(1, 8) phase carried across the call boundary
     b = emul_fold(4, taps, x[cut:], hist=np.ascontiguousarray(x[cut - 16384:cut]), skip=skip2)
     assert O.rel_rms(np.concatenate([a, b]), truth[::8]) <= 1e-5
+
+
+@pytest.fixture(scope="module")
+def emul_poly(emul):
+    L = C.CDLL(str(SO))
+    L.emul_fftfilt_poly.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                    C.c_longlong, C.c_longlong, C.c_longlong]
+
+    def run(taps, x, deci, hist=None, skip=0):
+        taps = np.ascontiguousarray(taps, np.complex64)
+        x = np.ascontiguousarray(x, np.complex64)
+        n = len(x)
+        n_out = (n - skip + deci - 1) // deci if n > skip else 0
+        out = np.full(n_out, np.nan + 0j, np.complex64)
+        L.emul_fftfilt_poly(taps.ctypes.data, len(taps), x.ctypes.data, n,
+                            hist.ctypes.data if hist is not None else None, out.ctypes.data, deci, skip, n_out)
+        return out
+    return run
+
+
+@pytest.mark.parametrize("ntaps,n,deci,skip", [(16385, 300_000, 8, 0), (16385, 70_000, 8, 5), (301, 40_000, 8, 0), (4097, 50_000, 8, 3),
+                                               (5, 20_000, 8, 7), (40_001, 200_000, 8, 2), (4097, 60_000, 3, 1), (64, 50_000, 2, 0),
+                                               (16385, 90_000, 16, 9), (12289, 60_000, 5, 13)])
+def test_emulated_poly_kernel_matches_f64_convolution(emul_poly, ntaps, n, deci, skip):
+    """Polyphase decimating kernel (fftfilt_poly_core.cuh): deci forward transforms per block, the sum over the branches in
+    the per-thread accumulator, one inverse transform."""
+    taps = O.low_pass_n(1.0, 0.02, ntaps).astype(np.complex64) * (1 - 0.2j)
+    x = O.synth_c32(7, 0, n)
+    want = O.conv_full_f64_fft(x, taps, n)[skip::deci]
+    got = emul_poly(taps, x, deci, skip=skip)
+    assert len(got) == len(want) and not np.isnan(got).any()
+    assert O.rel_rms(got, want) <= 1e-5
+
+
+def test_emulated_poly_kernel_streaming_history(emul_poly):
+    taps = O.low_pass_n(1.0, 0.02, 16385).astype(np.complex64)
+    x = O.synth_c32(8, 0, 150_000)
+    truth = O.conv_full_f64_fft(x, taps, len(x))
+    cut = 70_001
+    a = emul_poly(taps, x[:cut], 8, skip=0)
+    skip2 = (-cut) % 8                      # RationalResampler(1, 8) phase carried across the call boundary
+    b = emul_poly(taps, x[cut:], 8, hist=np.ascontiguousarray(x[cut - 16384:cut]), skip=skip2)
+    assert O.rel_rms(np.concatenate([a, b]), truth[::8]) <= 1e-5

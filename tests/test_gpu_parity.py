@@ -628,6 +628,7 @@ def test_fftfilt_long_taps_partitioned_streaming_and_decimation(R):
 def test_fftfilt_decimate_by_8_folded_spectrum(R, ntaps, n, skip, monkeypatch):
     """FftFilter + RationalResampler(1, 8) fused with the pruned inverse transform (fftfilt_fold.cu):
     against f64 truth, and against the store-predicate path of the plain kernel on the same input."""
+    monkeypatch.setenv("RRC_FFTFILT_NO_POLY", "1")              # the polyphase kernel (next test) is the default for deci 8
     taps = (O.low_pass_n(1.0, 0.02, ntaps).astype(np.complex64) * (1 - 0.2j))
     x = O.synth_c32(41, 0, n)
     want = O.conv_full_f64_fft(x, taps, n)[skip::8]
@@ -645,6 +646,74 @@ def test_fftfilt_decimate_by_8_folded_spectrum(R, ntaps, n, skip, monkeypatch):
     plain = run()
     assert O.rel_rms(plain, want) <= REL_RMS_BAR
     assert O.rel_rms(got, plain) <= REL_RMS_BAR
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C", [0, 4, 2, 1])
+@pytest.mark.parametrize("ntaps,n,deci,skip", [(16385, 2_000_000, 8, 0), (16385, 70_000, 8, 5), (301, 90_000, 8, 0), (4097, 200_000, 8, 3),
+                                               (5, 20_000, 8, 7), (40_001, 250_000, 8, 2), (4097, 60_000, 3, 1), (64, 50_000, 2, 0),
+                                               (16385, 190_000, 16, 9), (12289, 60_000, 5, 13), (1000, 300_000, 4, 2), (5, 5, 8, 0),
+                                               (16385, 1_000_001, 8, 20_003)])
+def test_fftfilt_polyphase_decimation(R, ntaps, n, deci, skip, C, monkeypatch):
+    """FftFilter + RationalResampler(1, deci) as a polyphase filter (fftfilt_poly.cu: deci forward transforms, the sum over the
+    branches in tensor memory, one inverse): every cluster width, 128-bit pair gathers and the unaligned fallback, against f64
+    truth and against the store-predicate path of the plain kernel."""
+    if C and deci % C:
+        pytest.skip("cluster width does not divide the decimation")
+    monkeypatch.setenv("RRC_FFTFILT_POLY_C", str(C))
+    taps = (O.low_pass_n(1.0, 0.02, ntaps).astype(np.complex64) * (1 - 0.2j))
+    x = O.synth_c32(43, 0, n)
+    want = O.conv_full_f64_fft(x, taps, n)[skip::deci]
+    din = R.DeviceBuffer.from_numpy(x)
+
+    def run():
+        f = R.FftFilt(taps)
+        dout = R.DeviceBuffer(max(1, len(want)) * 8)
+        k0 = R.launch_count()
+        cnt = f.decim_run(din, n, deci, skip, dout)
+        assert cnt == len(want)
+        return dout.download(np.complex64, cnt), R.launch_count() - k0
+    got, launches = run()
+    assert launches == 1                                          # the kernel writes the next history itself
+    assert O.rel_rms(got, want) <= REL_RMS_BAR
+    monkeypatch.setenv("RRC_FFTFILT_NO_POLY", "1")
+    monkeypatch.setenv("RRC_FFTFILT_NO_FOLD", "1")
+    plain, _ = run()
+    assert O.rel_rms(got, plain) <= REL_RMS_BAR
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("u8", [0, 1])
+def test_fftfilt_polyphase_streaming_history_epilogue_and_u8(R, u8):
+    """Config 5 shape streamed in ragged pieces through the polyphase kernel: the (ntaps-1)-sample history and the decimation
+    phase carry across calls; u8 I/Q input (RtlSdrDecode fused into the gather) and a fused ComplexToMag2 store."""
+    taps = O.low_pass_n(1.0, 0.02, 16385).astype(np.complex64)
+    n = 700_000
+    if u8:
+        raw = np.frombuffer(np.random.default_rng(5).bytes(2 * n), np.uint8)
+        x = O.rtlsdr_decode(raw)
+    else:
+        x = O.synth_c32(44, 0, n)
+    truth = O.conv_full_f64_fft(x, taps, n)[::8]
+    for epi in (False, True):
+        f = R.FftFilt(taps)
+        if u8:
+            f.set_input_u8iq(True)
+        if epi:
+            f.set_epilogue(R.EPI_MAG2)
+        pieces, off, got = [300_001, 7, 250_000, 3, 149_989], 0, []
+        for m in pieces:
+            skip = (-off) % 8
+            src = raw[2 * off:2 * (off + m)] if u8 else x[off:off + m]
+            din = R.DeviceBuffer.from_numpy(np.ascontiguousarray(src))
+            dout = R.DeviceBuffer(max(1, m // 8 + 2) * 8)
+            cnt = f.decim_run(din, m, 8, skip, dout)
+            got.append(dout.download(np.float32 if epi else np.complex64, cnt))
+            off += m
+        got = np.concatenate(got)
+        want = (truth.real.astype(np.float64) ** 2 + truth.imag.astype(np.float64) ** 2) if epi else truth
+        assert len(got) == len(want)
+        assert O.rel_rms(got, want) <= (3e-5 if epi else REL_RMS_BAR)
 
 
 def test_fftfilt_fold_streaming_carries_history_and_phase(R):
