@@ -260,7 +260,7 @@ KERNEL_NAMES = {
     "fir": "fir_poly_kernel<float2,float,1,false,16>", "fir_demod": "fir_rt_kernel<10,DEMOD,8,2>",
     "resample": "resample_kernel", "decode": "rtlsdr_decode_kernel", "fft": "fftstream_kernel<10>",
     "fftfilt_real": "fftfilt_kernel (real-stream mode)",
-    "fftfilt_decim": "fftfilt_fold_kernel<4> (65536-point, 4-CTA cluster) + history update",
+    "fftfilt_decim": "fftfilt_poly_kernel<4,false> (polyphase: 8 forward 16384-point transforms + 1 inverse per block, sum in TMEM, 4-CTA cluster; RRC_FFTFILT_NO_POLY=1 selects fftfilt_fold_kernel<4>)",
     "hilbert": "hilbert_half_kernel + history update", "mulconst": "map_kernel<MAP_MUL_C32>", "mag2": "mag2_kernel",
     "tee": "tee_kernel<uint4>",
     "iqbalance": "iq_tile_kernel<false> + iq_carry_kernel + iq_tile_kernel<true> (input read twice: 24 B/sample of traffic vs 16 algorithmic)",

@@ -8,19 +8,25 @@
 // Work split (template parameter C = CTAs per cluster, 1, 2 or 4):
 //   * A block reads D * 16384 consecutive input samples (1 MiB for D = 8); every branch touches every 128-byte line of
 //     it, so the region has to stay in L2 for the whole block.  With one block per SM that is 148 MiB of live lines —
-//     more than the 126 MB L2 (measured: 15-20 K cycles per branch load, 310 K cycles per block).  The C CTAs of a
+//     more than the 126 MB L2 (measured: 15-20 K cycles per branch gather, 310 K cycles per block).  The C CTAs of a
 //     cluster therefore share ONE block: CTA c transforms branches c*D/C .. (c+1)*D/C - 1 (D = 8, C = 4: the two
 //     branches that live in the same aligned 16 bytes, fetched with ONE 128-bit load per k — half the sectors and half
-//     the LSU time of two 64-bit gathers; the second branch waits in a 128 KiB TMEM stash), 37 MiB of lines live.
-//   * Every CTA writes its partial sum to an L2-resident scratch slot (coalesced 128-bit rows; 4 slots per CTA, indexed
-//     by the iteration) and arrives on the cluster barrier (release).  The block's FINISHER (rotating: iteration it ->
-//     CTA it % C) runs the inverse transform ONE ITERATION LATER, after its forward transforms of the next block: its own
+//     the LSU time of two 64-bit gathers; the second branch waits in a 128 KiB TMEM stash).  A hardware cluster, not a
+//     software group: co-scheduled CTAs ask for the same lines at the same time (same code on cooperative groups with a
+//     global-memory barrier and all 148 SMs: gather 25 K cycles instead of 10 K; 33 four-CTA clusters = 132 SMs fit).
+//   * Every CTA writes its partial sum to an L2 scratch slot (coalesced 128-bit rows; 4 slots per CTA, indexed by the
+//     iteration) and arrives on the cluster barrier (release).  The block's FINISHER (rotating: iteration it -> CTA
+//     it % C) runs the inverse transform ONE ITERATION LATER, after its forward transforms of the next block: its own
 //     next partial sum is then never late, so no CTA ever waits for a finisher (with immediate finishing the barrier
 //     chain serialised forward + inverse: measured 166 K cycles per finisher iteration against 61 K).  Over C blocks every
 //     CTA does D forward transforms and one inverse: balanced.
-//   * Rejected by measurement (profiles/r02_c5_poly_v1_trace.txt): four LOADER warps (setmaxnreg 104 / 64) gathering the
-//     next branch into the TMEM stash while the 16 transform warps compute — the gather's LSU time then lands on the
-//     transform warps' shared-memory exchanges (phase B 3.5 K -> 9 K cycles, phase C 8.6 K -> 12 K): same total.
+//   * HRES (off by default): the spectrum rows k2 = l of the branch in shared memory (one 72 KiB bulk copy per branch,
+//     as fftfilt_tma_kernel keeps them resident).  Phase C drops from 8.8 K to 5.4 K cycles — and the gather rises from
+//     10 K to 18-28 K: shared memory is taken from L1, and the L1 size bounds the sector-sparse gather's misses in flight.
+//   * Rejected by measurement (profiles/r02_c5_poly_*): four LOADER warps (setmaxnreg 104 / 64) gathering the next branch
+//     into the TMEM stash while the 16 transform warps compute — the gather's LSU time then lands on the transform warps'
+//     shared-memory exchanges (phase B 3.5 K -> 9 K cycles, phase C 8.6 K -> 12 K): same total; an evict-first hint on the
+//     gather (the CTAs of a cluster share sectors); prefetching two blocks ahead.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -35,7 +41,10 @@ namespace rrc {
 
 using fftp::PolyIO;
 
-constexpr size_t POLY_SMEM = (size_t)(fftk::SMEM_ELEMS + 512 + 512 + fftk::HRES_ELEMS + 4) * sizeof(float2);
+// Shared memory: exchange buffer + twiddles (+ the resident spectrum rows).  What is not shared memory is L1, and the L1
+// size bounds the sector-sparse gather's misses in flight: with the 72 KiB of resident rows the gather of a branch pair
+// takes 18-28 K cycles instead of 10-13 K — more than the rows save in phase C.  Hence HRES = false by default.
+constexpr size_t poly_smem(bool hres) { return (size_t)(fftk::SMEM_ELEMS + 512 + 512 + (hres ? fftk::HRES_ELEMS : 0) + 4) * sizeof(float2); }
 constexpr int POLY_SLOTS = 4;                                  // scratch slots per CTA (see the kernel for why four)
 constexpr int POLY_NSTAMP = 16, POLY_TRACE_IT = 6;
 
@@ -60,6 +69,14 @@ __device__ __forceinline__ void tm_st32(unsigned taddr, const float2 (&x)[16]) {
            "f"(x[4].x), "f"(x[4].y), "f"(x[5].x), "f"(x[5].y), "f"(x[6].x), "f"(x[6].y), "f"(x[7].x), "f"(x[7].y),
            "f"(x[8].x), "f"(x[8].y), "f"(x[9].x), "f"(x[9].y), "f"(x[10].x), "f"(x[10].y), "f"(x[11].x), "f"(x[11].y),
            "f"(x[12].x), "f"(x[12].y), "f"(x[13].x), "f"(x[13].y), "f"(x[14].x), "f"(x[14].y), "f"(x[15].x), "f"(x[15].y)
+        : "memory");
+}
+__device__ __forceinline__ void tm_st16(unsigned taddr, const float2 (&x)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :: "r"(taddr),
+           "f"(x[0].x), "f"(x[0].y), "f"(x[1].x), "f"(x[1].y), "f"(x[2].x), "f"(x[2].y), "f"(x[3].x), "f"(x[3].y),
+           "f"(x[4].x), "f"(x[4].y), "f"(x[5].x), "f"(x[5].y), "f"(x[6].x), "f"(x[6].y), "f"(x[7].x), "f"(x[7].y)
         : "memory");
 }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -97,6 +114,7 @@ struct TmemStash {
     unsigned base;
     __device__ __forceinline__ void load(int, int half, float2 (&x)[16]) const { tm_ld32(base + 32u * half, x); }
     __device__ __forceinline__ void store(int, int half, const float2 (&x)[16]) const { tm_st32(base + 32u * half, x); }
+    __device__ __forceinline__ void store8(int, int quarter, const float2 (&x)[8]) const { tm_st16(base + 16u * quarter, x); }
 };
 
 __device__ __forceinline__ void poly_load_pair_dev(int tid, long long blk, int r, const PolyIO& io, float2 (&v)[32], const TmemStash& stash,
@@ -104,33 +122,41 @@ __device__ __forceinline__ void poly_load_pair_dev(int tid, long long blk, int r
     const float2* q = io.b.in + fftp::poly_g(io, blk, r, tid);
     const long long step = 512ll * io.D;
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        float4 w[16];
+    for (int b = 0; b < 4; ++b) {
+        float4 w[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
+        for (int e = 0; e < 8; ++e)
             asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-                         : "=f"(w[e].x), "=f"(w[e].y), "=f"(w[e].z), "=f"(w[e].w) : "l"(q + step * fftr::bitrev(16 * b + e, 5)), "l"(pol));
-        float2 x[16];
+                         : "=f"(w[e].x), "=f"(w[e].y), "=f"(w[e].z), "=f"(w[e].w) : "l"(q + step * fftr::bitrev(8 * b + e, 5)), "l"(pol));
+        float2 x[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) { v[16 * b + e] = make_float2(w[e].x, w[e].y); x[e] = make_float2(w[e].z, w[e].w); }
-        stash.store(tid, b, x);
+        for (int e = 0; e < 8; ++e) { v[8 * b + e] = make_float2(w[e].x, w[e].y); x[e] = make_float2(w[e].z, w[e].w); }
+        stash.store8(tid, b, x);
     }
 }
 
 // Last phase C of a CTA's branches in a cluster: the partial sum goes to this CTA's scratch slot as 16 coalesced
 // 128-bit rows per thread, slot[(half*8 + j)*512 + tid].
+template <bool HRES>
 __device__ __forceinline__ void phase_c_partial(int tid, const float2* Hp, const float2* Hres, const float2* sm, const TmemAcc& acc, bool first, float4* slot) {
     const int k1 = tid >> 4, l = tid & 15;
     const float4* hp1 = reinterpret_cast<const float4*>(Hp + (size_t)(k1 * 32 + l + 16) * 16);
     float4 h1[8];
+    if constexpr (HRES) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h1[i] = hp1[i];
+        for (int i = 0; i < 8; ++i) h1[i] = hp1[i];
+    }
     const float4* hres = reinterpret_cast<const float4*>(Hres + tid * fftk::HRES_PITCH);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         const float2* row = sm + k1 * fftk::PLANE_PITCH + (l + 16 * half) * fftk::ROW_PITCH;
         float2 u[16];
-        fftp::poly_c_row(tid, half, half == 0 ? hres : h1, row, acc, first, u);
+        if constexpr (!HRES) {
+            const float4* hp = reinterpret_cast<const float4*>(Hp + (size_t)(k1 * 32 + l + 16 * half) * 16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h1[i] = hp[i];
+        }
+        fftp::poly_c_row(tid, half, (HRES && half == 0) ? hres : h1, row, acc, first, u);
 #pragma unroll
         for (int j = 0; j < 8; ++j) __stcg(slot + (half * 8 + j) * 512 + tid, make_float4(u[2 * j].x, u[2 * j].y, u[2 * j + 1].x, u[2 * j + 1].y));
     }
@@ -169,7 +195,7 @@ __device__ __forceinline__ void phase_c_finish(int tid, float2* sm, const float4
     }
 }
 
-template <int C>
+template <int C, bool HRES>
 __global__ void __launch_bounds__(512, 1)
 fftfilt_poly_kernel(const PolyIO io, const float2* __restrict__ Hph, const float2* __restrict__ tw1g,
                     const float2* __restrict__ tw2g, float4* __restrict__ scratch, long long nblocks, int tune,
@@ -178,8 +204,9 @@ fftfilt_poly_kernel(const PolyIO io, const float2* __restrict__ Hph, const float
     float2* s_tw2 = sm + fftk::SMEM_ELEMS;
     float2* s_tw1 = s_tw2 + 512;
     float2* s_hres = s_tw1 + 512;
-    unsigned* s_tmem = reinterpret_cast<unsigned*>(s_hres + fftk::HRES_ELEMS + 2);
-    const unsigned mbar = (unsigned)__cvta_generic_to_shared(s_hres + fftk::HRES_ELEMS);
+    constexpr int HRES_N = HRES ? fftk::HRES_ELEMS : 0;
+    unsigned* s_tmem = reinterpret_cast<unsigned*>(s_hres + HRES_N + 2);
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(s_hres + HRES_N);
     const unsigned hres_a = (unsigned)__cvta_generic_to_shared(s_hres);
     const float2* Hresg = Hph + (size_t)io.D * fftk::N;       // [D][HRES_ELEMS]: rows k2 = l of every branch, shared-memory layout
     unsigned hpar = 0;
@@ -262,7 +289,7 @@ fftfilt_poly_kernel(const PolyIO io, const float2* __restrict__ Hph, const float
             fftk::phase_a_linear_compute(tid, s_tw1, v);
             if (i < 2) stamp(2 + 6 * i);
             __syncthreads();                                    // phase C / A' of the previous transform has read the buffer
-            if (tid == 0 && !(tune & 4)) {                      // ... and the previous branch's spectrum rows: this branch's -> shared memory
+            if (HRES && tid == 0) {                             // ... and the previous branch's spectrum rows: this branch's -> shared memory
                 const float2* src = Hresg + (size_t)r * fftk::HRES_ELEMS;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(fftk::HRES_ELEMS * 8) : "memory");
@@ -276,18 +303,15 @@ fftfilt_poly_kernel(const PolyIO io, const float2* __restrict__ Hph, const float
             __syncthreads();
             if (i < 2) stamp(4 + 6 * i);
             if (!(tune & 18)) prefetch(blk, 2 * i);
+            const float2* Hp = Hph + (size_t)r * fftk::N;
             fftk::phase_mid_b(tid, s_tw2, sm);
             __syncwarp();
             if (i < 2) stamp(5 + 6 * i);
             if (!(tune & 18)) prefetch(blk, 2 * i + 1);
-            const float2* Hp = Hph + (size_t)r * fftk::N;
-            // tune bit 2 (experiment): both spectrum rows straight from L2 (generic loads), no bulk copy
-            const float2* hres_p = s_hres;
-            if (tune & 4) hres_p = Hp + (size_t)((tid >> 4) * 32 + (tid & 15)) * 16 - tid * fftk::HRES_PITCH;
-            else { poly_mbar_wait(mbar, hpar); hpar ^= 1u; }
-            if (i < PP - 1) fftp::phase_c_acc(tid, Hp, hres_p, sm, acc, i == 0, false);
-            else if constexpr (C == 1) fftp::phase_c_acc(tid, Hp, hres_p, sm, acc, i == 0, true);
-            else phase_c_partial(tid, Hp, hres_p, sm, acc, i == 0, my_slots + (size_t)(c * POLY_SLOTS + (it & 3)) * 8192);
+            if constexpr (HRES) { poly_mbar_wait(mbar, hpar); hpar ^= 1u; }
+            if (i < PP - 1) fftp::phase_c_acc<HRES>(tid, Hp, s_hres, sm, acc, i == 0, false);
+            else if constexpr (C == 1) fftp::phase_c_acc<HRES>(tid, Hp, s_hres, sm, acc, i == 0, true);
+            else phase_c_partial<HRES>(tid, Hp, s_hres, sm, acc, i == 0, my_slots + (size_t)(c * POLY_SLOTS + (it & 3)) * 8192);
             if (i < 2) stamp(6 + 6 * i);
         }
         if constexpr (C == 1) {
@@ -324,13 +348,13 @@ int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-template <int C>
+template <int C, bool HRES>
 int launch_poly(rrc_fftfilt* h, const PolyIO& io, const float2* Hph, long long nblocks, cudaStream_t st) {
-    auto kern = fftfilt_poly_kernel<C>;
-    RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POLY_SMEM));
+    auto kern = fftfilt_poly_kernel<C, HRES>;
+    RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)poly_smem(HRES)));
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(512);
-    cfg.dynamicSmemBytes = POLY_SMEM;
+    cfg.dynamicSmemBytes = poly_smem(HRES);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -437,9 +461,10 @@ int poly_launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_
     const int want = env_int("RRC_FFTFILT_POLY_C", 0);
     if ((want == 1 || want == 2 || want == 4) && deci % want == 0) C = want;
     const float2* Hph = h->poly.Hph[smod];
-    if (C == 4) return launch_poly<4>(h, io, Hph, nblocks, st);
-    if (C == 2) return launch_poly<2>(h, io, Hph, nblocks, st);
-    return launch_poly<1>(h, io, Hph, nblocks, st);
+    const bool hres = env_int("RRC_FFTFILT_POLY_HRES", 0) != 0;
+    if (C == 4) return hres ? launch_poly<4, true>(h, io, Hph, nblocks, st) : launch_poly<4, false>(h, io, Hph, nblocks, st);
+    if (C == 2) return hres ? launch_poly<2, true>(h, io, Hph, nblocks, st) : launch_poly<2, false>(h, io, Hph, nblocks, st);
+    return hres ? launch_poly<1, true>(h, io, Hph, nblocks, st) : launch_poly<1, false>(h, io, Hph, nblocks, st);
 }
 
 void poly_destroy(rrc_fftfilt* h) {

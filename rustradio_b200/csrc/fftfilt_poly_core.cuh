@@ -89,20 +89,20 @@ RRC_HD void poly_load(int tid, long long blk, int r, const PolyIO& io, float2 (&
 }
 
 // Branches r (-> v) and r + 1 (-> the stash, in the order phase A wants them) with 32 aligned 128-bit loads per thread,
-// two batches of 16 so that at most 64 load registers are in flight.  Requires poly_pair_ok().
+// four batches of 8 so that at most 32 load registers are in flight beside v (batches of 16 spilled).  Requires poly_pair_ok().
 template <class Stash>
 RRC_HD void poly_load_pair(int tid, long long blk, int r, const PolyIO& io, float2 (&v)[32], const Stash& stash) {
     const float2* q = io.b.in + poly_g(io, blk, r, tid);
     const long long step = 512ll * io.D;
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        float4 w[16];
+    for (int b = 0; b < 4; ++b) {
+        float4 w[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) w[e] = *reinterpret_cast<const float4*>(q + step * bitrev(16 * b + e, 5));
-        float2 x[16];
+        for (int e = 0; e < 8; ++e) w[e] = *reinterpret_cast<const float4*>(q + step * bitrev(8 * b + e, 5));
+        float2 x[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) { v[16 * b + e] = make_float2(w[e].x, w[e].y); x[e] = make_float2(w[e].z, w[e].w); }
-        stash.store(tid, b, x);
+        for (int e = 0; e < 8; ++e) { v[8 * b + e] = make_float2(w[e].x, w[e].y); x[e] = make_float2(w[e].z, w[e].w); }
+        stash.store8(tid, b, x);
     }
 }
 template <class Stash>
@@ -116,6 +116,7 @@ struct HostAcc {
     float2* a;               // [512][32]
     void load(int tid, int half, float2 (&x)[16]) const { for (int i = 0; i < 16; ++i) x[i] = a[tid * 32 + half * 16 + i]; }
     void store(int tid, int half, const float2 (&x)[16]) const { for (int i = 0; i < 16; ++i) a[tid * 32 + half * 16 + i] = x[i]; }
+    void store8(int tid, int quarter, const float2 (&x)[8]) const { for (int i = 0; i < 8; ++i) a[tid * 32 + quarter * 8 + i] = x[i]; }
 };
 
 // One row (k2 = l + 16 half) of phase C of one branch: DFT16 over n3 -> x H_r -> running sum over the branches in u.
@@ -143,19 +144,27 @@ RRC_HD void poly_c_row(int tid, int half, const float4* h, const float2* row, co
 // memory; the rows k2 = l of it also in shared memory (Hres, the padded layout of fftk::load_hres — on the GPU a bulk
 // copy per branch puts them there while phases A and B run): the row each thread multiplies first comes from shared
 // memory, the second one from L2 into registers at the top of the phase, as in fftk::phase_mid_c.
-template <class Acc>
+// HRES = false: both rows from L2, each at the top of its half (no shared-memory rows, fewer live registers).
+template <bool HRES = true, class Acc>
 RRC_HD void phase_c_acc(int tid, const float2* Hp, const float2* Hres, float2* sm, const Acc& acc, bool first, bool last) {
     const int k1 = tid >> 4, l = tid & 15;
     const float4* hp1 = reinterpret_cast<const float4*>(Hp + (size_t)(k1 * 32 + l + 16) * 16);
     float4 h1[8];
+    if constexpr (HRES) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h1[i] = hp1[i];
+        for (int i = 0; i < 8; ++i) h1[i] = hp1[i];
+    }
     const float4* hres = reinterpret_cast<const float4*>(Hres + tid * HRES_PITCH);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
         float2* row = sm + k1 * PLANE_PITCH + (l + 16 * half) * ROW_PITCH;   // (k1, r = k2, c = 0)
         float2 u[16];
-        poly_c_row(tid, half, half == 0 ? hres : h1, row, acc, first, u);
+        if constexpr (!HRES) {
+            const float4* hp = reinterpret_cast<const float4*>(Hp + (size_t)(k1 * 32 + l + 16 * half) * 16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h1[i] = hp[i];
+        }
+        poly_c_row(tid, half, (HRES && half == 0) ? hres : h1, row, acc, first, u);
         if (!last) {
             acc.store(tid, half, u);
         } else {
