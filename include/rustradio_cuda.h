@@ -238,7 +238,12 @@ int rrc_fftfilt_run(rrc_fftfilt_t* h, const float* in_dev, size_t n, float* out_
  * y[k*deci - phase] style decimated output without materialising y.
  * `skip` = number of filter outputs to drop before the first kept one
  * (carries the resampler counter between calls); produces
- * ceil((n - skip)/deci) outputs for n > skip. */
+ * ceil((n - skip)/deci) outputs for n > skip.
+ * Kernel selection: 2 <= deci <= 16 on a Complex filter of at most 8193 * deci taps runs as a POLYPHASE filter
+ * (fftfilt_poly_kernel: deci forward transforms on the deci-times slower branch streams, one inverse per block, the sum
+ * over the branches in tensor memory; clusters of 4 / 2 / 1 CTAs by what divides deci) — RRC_FFTFILT_NO_POLY=1 disables
+ * it; then deci == 8 takes the folded-spectrum kernel (RRC_FFTFILT_NO_FOLD=1 disables) and everything else the plain
+ * kernel with a store predicate.  Same outputs within the FftFilter tolerance on every path; one launch per call. */
 int rrc_fftfilt_decim_run(rrc_fftfilt_t* h, const float* in_dev, size_t n, size_t deci, size_t skip,
                           float* out_dev, size_t* n_out, void* stream);
 /* Host-buffer form for a whole stream: n_in samples in, floor(n_in/nsamples)*nsamples out. */

@@ -9,7 +9,7 @@ fn main() {
     let out = PathBuf::from(std::env::var("OUT_DIR").unwrap());
     let nvcc = std::env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     // keep in step with SRCS in rustradio_b200/csrc/Makefile (tests/test_abi.py::test_rust_build_lists_every_source)
-    let srcs = ["runtime.cu", "fir.cu", "fir_tc.cu", "fir_tc5.cu", "fir_tcc.cu", "fftfilt.cu", "fftfilt_fold.cu", "resample.cu", "ingest.cu",
+    let srcs = ["runtime.cu", "fir.cu", "fir_tc.cu", "fir_tc5.cu", "fir_tcc.cu", "fftfilt.cu", "fftfilt_fold.cu", "fftfilt_poly.cu", "resample.cu", "ingest.cu",
                 "fftstream.cu", "hilbert.cu", "elementwise.cu", "blocks.cu", "blocks_capi.cu", "sources.cu"];
     let mut objs = vec![];
     for s in srcs {
