@@ -24,6 +24,8 @@ struct rrc_poly_tables {
     float4* scratch = nullptr;  // [clusters][C][4][8192] partial sums on their way to the block's finisher CTA
     size_t scratch_bytes = 0;
     int max_clusters[3] = {0, 0, 0};   // co-resident clusters for C = 1, 2, 4
+    cudaStream_t side = nullptr;       // second launch (two-CTA clusters on the SMs the four-CTA clusters leave idle)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 struct rrc_fftfilt {

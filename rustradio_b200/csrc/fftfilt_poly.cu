@@ -198,7 +198,7 @@ __device__ __forceinline__ void phase_c_finish(int tid, float2* sm, const float4
 template <int C, bool HRES>
 __global__ void __launch_bounds__(512, 1)
 fftfilt_poly_kernel(const PolyIO io, const float2* __restrict__ Hph, const float2* __restrict__ tw1g,
-                    const float2* __restrict__ tw2g, float4* __restrict__ scratch, long long nblocks, int tune,
+                    const float2* __restrict__ tw2g, float4* __restrict__ scratch, long long blk0, long long nblocks, int tune,
                     long long* __restrict__ trace) {
     extern __shared__ __align__(16) float2 sm[];
     float2* s_tw2 = sm + fftk::SMEM_ELEMS;
@@ -267,7 +267,7 @@ fftfilt_poly_kernel(const PolyIO io, const float2* __restrict__ Hph, const float
         }
     };
     long long prev_blk = -1;
-    for (long long blk = cl; blk < nblocks; blk += ncl, ++it) {
+    for (long long blk = blk0 + cl; blk < nblocks; blk += ncl, ++it) {          // this launch's blocks: [blk0, nblocks)
         stamp(0);
         bool stashed = false;
         for (int i = 0; i < PP; ++i) {
@@ -348,8 +348,36 @@ int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
+// Co-resident clusters of the C-CTA kernel (cudaOccupancyMaxActiveClusters; B200: 33 four-CTA clusters, 74 two-CTA ones).
 template <int C, bool HRES>
-int launch_poly(rrc_fftfilt* h, const PolyIO& io, const float2* Hph, long long nblocks, cudaStream_t st) {
+int poly_clusters(rrc_fftfilt* h, int* out) {
+    int& mc = h->poly.max_clusters[C == 1 ? 0 : C == 2 ? 1 : 2];
+    if (mc == 0) {
+        if (C > 1) {
+            auto kern = fftfilt_poly_kernel<C, HRES>;
+            RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)poly_smem(HRES)));
+            cudaLaunchConfig_t cfg = {};
+            cfg.blockDim = dim3(512);
+            cfg.dynamicSmemBytes = poly_smem(HRES);
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cfg.gridDim = dim3(sm_count(h->device) / C * C);
+            RRC_CUDA(cudaOccupancyMaxActiveClusters(&mc, kern, &cfg));
+            if (mc < 1) return fail(RRC_ERR_CUDA, "no %d-CTA cluster of the polyphase kernel fits on device %d", C, h->device);
+        } else {
+            mc = sm_count(h->device);
+        }
+    }
+    *out = mc;
+    return RRC_OK;
+}
+
+// One launch over the blocks [blk0, nblocks) on at most `ncl` clusters, partial sums in `scratch` (ncl * C * POLY_SLOTS slots).
+template <int C, bool HRES>
+int launch_poly(rrc_fftfilt* h, const PolyIO& io, const float2* Hph, long long blk0, long long nblocks, long long ncl, float4* scratch,
+                cudaStream_t st) {
     auto kern = fftfilt_poly_kernel<C, HRES>;
     RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)poly_smem(HRES)));
     cudaLaunchConfig_t cfg = {};
@@ -360,32 +388,14 @@ int launch_poly(rrc_fftfilt* h, const PolyIO& io, const float2* Hph, long long n
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    int& mc = h->poly.max_clusters[C == 1 ? 0 : C == 2 ? 1 : 2];
-    if (mc == 0) {
-        cfg.gridDim = dim3(sm_count(h->device) / C * C);
-        if (C > 1) {
-            RRC_CUDA(cudaOccupancyMaxActiveClusters(&mc, kern, &cfg));
-            if (mc < 1) return fail(RRC_ERR_CUDA, "no %d-CTA cluster of the polyphase kernel fits on device %d", C, h->device);
-        } else {
-            mc = sm_count(h->device);
-        }
-    }
-    long long ncl = std::min<long long>(nblocks, mc);
-    if (const int cap = env_int("RRC_FFTFILT_POLY_GROUPS", 0)) ncl = std::min<long long>(ncl, cap);   // experiment: fewer resident groups
-    const size_t need = (size_t)ncl * C * POLY_SLOTS * 8192 * sizeof(float4);
-    if (C > 1 && h->poly.scratch_bytes < need) {
-        cudaFree(h->poly.scratch);
-        h->poly.scratch = nullptr; h->poly.scratch_bytes = 0;
-        RRC_CUDA(cudaMalloc((void**)&h->poly.scratch, need));
-        h->poly.scratch_bytes = need;
-    }
     cfg.gridDim = dim3((unsigned)(ncl * C));
-    static const bool want_trace = getenv("RRC_FFTFILT_TRACE") != nullptr;
+    static const bool trace_env = getenv("RRC_FFTFILT_TRACE") != nullptr;
+    const bool want_trace = trace_env && blk0 == 0;
     long long* dtrace = nullptr;
     const size_t trace_n = (size_t)POLY_TRACE_IT * 16 * POLY_NSTAMP;
     if (want_trace) { RRC_CUDA(cudaMalloc((void**)&dtrace, trace_n * 8)); RRC_CUDA(cudaMemsetAsync(dtrace, 0, trace_n * 8, st)); }
     RRC_CUDA(cudaLaunchKernelEx(&cfg, kern, io, Hph, (const float2*)h->tw1, (const float2*)h->tw2,
-                                (float4*)h->poly.scratch, nblocks, env_int("RRC_FFTFILT_POLY_TUNE", 0), dtrace));
+                                scratch, blk0, nblocks, env_int("RRC_FFTFILT_POLY_TUNE", 0), dtrace));
     count_launch();
     if (want_trace) {                                           // debug only: synchronous dump of the per-phase cycle table
         std::vector<long long> tr(trace_n);
@@ -396,7 +406,7 @@ int launch_poly(rrc_fftfilt* h, const PolyIO& io, const float2* Hph, long long n
                                       "br1 load / stash", "br1 A compute", "br1 barrier", "br1 A store + barrier", "br1 B", "br1 C",
                                       "other branches, barrier, finish, B'", "A' + store"};
         static int dumps = 0;
-        if (nblocks > ncl * 8 && dumps++ < 1) {
+        if (nblocks - blk0 > ncl * 8 && dumps++ < 1) {
             for (int b = 0; b < POLY_TRACE_IT; ++b) {
                 auto at = [&](int w, int i) { return tr[((size_t)b * 16 + w) * POLY_NSTAMP + i]; };
                 long long t0 = at(0, 0), tend = 0;
@@ -460,16 +470,63 @@ int poly_launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_
     int C = deci % 4 == 0 ? 4 : deci % 2 == 0 ? 2 : 1;
     const int want = env_int("RRC_FFTFILT_POLY_C", 0);
     if ((want == 1 || want == 2 || want == 4) && deci % want == 0) C = want;
-    const float2* Hph = h->poly.Hph[smod];
     const bool hres = env_int("RRC_FFTFILT_POLY_HRES", 0) != 0;
-    if (C == 4) return hres ? launch_poly<4, true>(h, io, Hph, nblocks, st) : launch_poly<4, false>(h, io, Hph, nblocks, st);
-    if (C == 2) return hres ? launch_poly<2, true>(h, io, Hph, nblocks, st) : launch_poly<2, false>(h, io, Hph, nblocks, st);
-    return hres ? launch_poly<1, true>(h, io, Hph, nblocks, st) : launch_poly<1, false>(h, io, Hph, nblocks, st);
+    const float2* Hph = h->poly.Hph[smod];
+    int mc = 0;
+    if (C == 4) RRC_TRY((hres ? poly_clusters<4, true> : poly_clusters<4, false>)(h, &mc));
+    else if (C == 2) RRC_TRY((hres ? poly_clusters<2, true> : poly_clusters<2, false>)(h, &mc));
+    else RRC_TRY((hres ? poly_clusters<1, true> : poly_clusters<1, false>)(h, &mc));
+    long long ncl = std::min<long long>(nblocks, mc);
+    if (const int cap = env_int("RRC_FFTFILT_POLY_GROUPS", 0)) ncl = std::min<long long>(ncl, cap);   // experiment: fewer resident clusters
+    // Experiment (RRC_FFTFILT_POLY_SPLIT=1, off by default): the SMs the four-CTA clusters leave idle (B200: 148 - 4 * 33 = 16)
+    // run a SECOND launch of two-CTA clusters on their share of the blocks, on a side stream forked from and joined to the
+    // caller's.  Measured on config 5: 8.45 ms for every share between 5 % and 8 % against 8.10 ms without — the second
+    // launch slows the first one down by more than it takes off it (profiles/r02_c5_poly_split_rejected.txt).
+    long long nclB = 0, nA = nblocks;
+    if (C == 4 && !hres && ncl == mc && env_int("RRC_FFTFILT_POLY_SPLIT", 0) != 0) {
+        int mc2 = 0;
+        RRC_TRY((poly_clusters<2, false>)(h, &mc2));
+        nclB = std::min<long long>((sm_count(h->device) - 4 * mc) / 2, mc2);
+        const double w = 0.01 * env_int("RRC_FFTFILT_POLY_SPLIT_W", 85);           // per-SM speed of the two-CTA clusters relative to the four-CTA ones
+        const long long nB = nclB > 0 ? (long long)((double)nblocks * (2.0 * nclB * w) / (4.0 * mc + 2.0 * nclB * w)) : 0;
+        if (nB >= 4 * nclB && nblocks - nB >= 8 * ncl) nA = nblocks - nB; else nclB = 0;
+    }
+    const size_t slot_f4 = (size_t)POLY_SLOTS * 8192;
+    const size_t need = ((size_t)ncl * C + (size_t)nclB * 2) * slot_f4 * sizeof(float4);
+    if (C > 1 && h->poly.scratch_bytes < need) {
+        cudaFree(h->poly.scratch);
+        h->poly.scratch = nullptr; h->poly.scratch_bytes = 0;
+        RRC_CUDA(cudaMalloc((void**)&h->poly.scratch, need));
+        h->poly.scratch_bytes = need;
+    }
+    if (nclB > 0) {
+        if (!h->poly.side) {
+            RRC_CUDA(cudaStreamCreateWithFlags(&h->poly.side, cudaStreamNonBlocking));
+            RRC_CUDA(cudaEventCreateWithFlags(&h->poly.ev_fork, cudaEventDisableTiming));
+            RRC_CUDA(cudaEventCreateWithFlags(&h->poly.ev_join, cudaEventDisableTiming));
+        }
+        RRC_CUDA(cudaEventRecord(h->poly.ev_fork, st));
+        RRC_CUDA(cudaStreamWaitEvent(h->poly.side, h->poly.ev_fork, 0));
+    }
+    int rc;
+    if (C == 4) rc = hres ? launch_poly<4, true>(h, io, Hph, 0, nA, ncl, h->poly.scratch, st) : launch_poly<4, false>(h, io, Hph, 0, nA, ncl, h->poly.scratch, st);
+    else if (C == 2) rc = hres ? launch_poly<2, true>(h, io, Hph, 0, nA, ncl, h->poly.scratch, st) : launch_poly<2, false>(h, io, Hph, 0, nA, ncl, h->poly.scratch, st);
+    else rc = hres ? launch_poly<1, true>(h, io, Hph, 0, nA, ncl, h->poly.scratch, st) : launch_poly<1, false>(h, io, Hph, 0, nA, ncl, h->poly.scratch, st);
+    if (rc != RRC_OK) return rc;
+    if (nclB > 0) {
+        PolyIO iob = io;
+        iob.b.hist_next = nullptr;                              // the first launch writes the next history
+        RRC_TRY((launch_poly<2, false>)(h, iob, Hph, nA, nblocks, nclB, h->poly.scratch + (size_t)ncl * C * slot_f4, h->poly.side));
+        RRC_CUDA(cudaEventRecord(h->poly.ev_join, h->poly.side));
+        RRC_CUDA(cudaStreamWaitEvent(st, h->poly.ev_join, 0));
+    }
+    return RRC_OK;
 }
 
 void poly_destroy(rrc_fftfilt* h) {
     for (auto& t : h->poly.Hph) cudaFree(t);
     cudaFree(h->poly.scratch);
+    if (h->poly.side) { cudaStreamDestroy(h->poly.side); cudaEventDestroy(h->poly.ev_fork); cudaEventDestroy(h->poly.ev_join); }
     h->poly = rrc_poly_tables();
 }
 
