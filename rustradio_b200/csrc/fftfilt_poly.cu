@@ -125,9 +125,14 @@ __device__ __forceinline__ void poly_load_pair_dev(int tid, long long blk, int r
     for (int b = 0; b < 4; ++b) {
         float4 w[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-            asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-                         : "=f"(w[e].x), "=f"(w[e].y), "=f"(w[e].z), "=f"(w[e].w) : "l"(q + step * fftr::bitrev(8 * b + e, 5)), "l"(pol));
+        for (int e = 0; e < 8; ++e) {
+            if (pol == 1ull)                                    // tune bit 32: no L1 allocation only
+                asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(w[e].x), "=f"(w[e].y), "=f"(w[e].z), "=f"(w[e].w) : "l"(q + step * fftr::bitrev(8 * b + e, 5)));
+            else
+                asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                             : "=f"(w[e].x), "=f"(w[e].y), "=f"(w[e].z), "=f"(w[e].w) : "l"(q + step * fftr::bitrev(8 * b + e, 5)), "l"(pol));
+        }
         float2 x[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) { v[8 * b + e] = make_float2(w[e].x, w[e].y); x[e] = make_float2(w[e].z, w[e].w); }
@@ -253,6 +258,7 @@ fftfilt_poly_kernel(const PolyIO io, const float2* __restrict__ Hph, const float
     // share sectors: the first reader demotes the line the second one still needs)
     unsigned long long pol_first = 0;
     if (tune & 1) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+    if (tune & 32) pol_first = 1ull;                            // experiment: L1::no_allocate on the gather, default L2 policy
     // Next block's region -> L2 in 2 * PP slices, issued before and after phase B of every branch: while the transforms run
     // the memory system is idle; issued together with the gather, the prefetch traffic queues in front of the demand loads
     // (a gather that misses L2 runs at the SM's 22 B/clk DRAM rate: 24 K cycles instead of 8-10 K).
