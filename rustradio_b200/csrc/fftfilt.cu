@@ -25,6 +25,7 @@
 #include "fftfilt_tables.hpp"
 #include "pipeline.cuh"
 #include "fftfilt_handle.hpp"
+#include "tmem.cuh"
 
 namespace rrc {
 
@@ -197,6 +198,115 @@ fftfilt_tma_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2
             if (nb < nblocks) stage(nb);
         });
     }
+}
+
+// Variant 40: fftfilt_tma_kernel with the WHOLE spectrum in tensor memory.  Thread tid multiplies rows k2 = l, l + 16 of plane
+// k1 in every block: 32 spectrum values = 64 columns of its own TMEM lane, written once at kernel start (tcgen05.st), read at
+// the top of each half of phase C (tcgen05.ld.32x32b.x32).  No spectrum rows in shared memory (72 KiB less), no 64 KiB per
+// block from L2 through the 28 KiB of L1 that 216 KiB of shared memory leave, 8 LDS.128 per thread and block fewer.
+constexpr size_t FFTFILT_TMH_SMEM = (size_t)(fftk::SMEM_ELEMS + 512 + 512 + 4) * sizeof(float2);
+
+__device__ __forceinline__ void phase_mid_c_tm(int tid, unsigned hbase, float2* sm) {
+    const int k1 = tid >> 4, l = tid & 15;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float2* row = sm + k1 * fftk::PLANE_PITCH + (l + 16 * half) * fftk::ROW_PITCH;
+        float2 hh[16];
+        tm_ld32_issue(hbase + 32u * half, hh);                  // in flight behind the row loads and the forward DFT16
+        float2 v[16];
+#pragma unroll
+        for (int n3 = 0; n3 < 16; ++n3) v[fftr::bitrev(n3, 4)] = row[n3];
+        fftr::dit<16, +1>(v);
+        tm_ld32_wait(hh);
+        float2 u[16];
+#pragma unroll
+        for (int k3 = 0; k3 < 16; ++k3) u[fftr::bitrev(k3, 4)] = fftr::cmul(v[k3], hh[k3]);
+        fftr::dit<16, -1>(u);
+#pragma unroll
+        for (int n3 = 0; n3 < 16; ++n3) row[n3] = u[n3];
+    }
+}
+
+template <bool DECIM, bool ACCUM>
+__global__ void __launch_bounds__(fftk::NT, 1)
+fftfilt_tmh_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __restrict__ tw1g,
+                   const float2* __restrict__ tw2g, long long nblocks, int tune) {
+    extern __shared__ __align__(16) float2 sm[];
+    float2* s_tw2 = sm + fftk::SMEM_ELEMS;
+    float2* s_tw1 = s_tw2 + 512;
+    unsigned* s_tmem = reinterpret_cast<unsigned*>(s_tw1 + 512 + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    s_tw2[tid] = tw2g[tid];
+    s_tw1[tid] = tw1g[tid];
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(s_tw1 + 512);
+    const unsigned sm_a = (unsigned)__cvta_generic_to_shared(sm);
+    const int pf = tune & 15;
+    if (io.hist_next && blockIdx.x == gridDim.x - 1) fftk::update_history(io, tid, fftk::NT);
+    if (warp == 0) tm_alloc_all(s_tmem);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tm_fence_before();
+    __syncthreads();
+    tm_fence_after();
+    const unsigned tmem = *s_tmem;
+    const unsigned hbase = tm_strip64(tmem, warp);
+    {   // this thread's two spectrum rows -> its TMEM strip
+        const int k1 = tid >> 4, l = tid & 15;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const float4* hp = reinterpret_cast<const float4*>(Hp + (size_t)(k1 * 32 + l + 16 * half) * 16);
+            float2 x[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float4 h4 = hp[i]; x[2 * i] = make_float2(h4.x, h4.y); x[2 * i + 1] = make_float2(h4.z, h4.w); }
+            tm_st32(hbase + 32u * half, x);
+        }
+        tm_wait_st();
+    }
+    auto stage = [&](long long nb) {
+        if (fftk::stage_linear_bulk_ok(nb, io)) {
+            if (tid == 0) {
+                const float2* src = io.in + fftk::stage_linear_seg0(nb, io);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"(mbar), "r"(fftk::N * 8) : "memory");
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c)
+                    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(sm_a + c * 16384), "l"(src + c * 2048), "r"(16384), "r"(mbar) : "memory");
+            }
+        } else {
+            fftk::stage_linear_fallback(tid, nb, io, sm);
+            if (tid == 0) asm volatile("mbarrier.arrive.shared.b64 _, [%0];" ::"r"(mbar) : "memory");
+        }
+    };
+    if (blockIdx.x < nblocks) stage(blockIdx.x);
+    unsigned parity = 0;
+    for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const long long nb = blk + gridDim.x;
+        float2 v[32];
+        mbar_wait(mbar, parity);
+        parity ^= 1;
+        fftk::phase_a_linear_load(tid, sm, v);
+        fftk::phase_a_linear_compute(tid, s_tw1, v);
+        __syncthreads();
+        fftk::phase_a_linear_store(tid, sm, v);
+        __syncthreads();
+        if (pf) prefetch_segment(io, nb, nblocks, tid);
+        fftk::phase_mid_b<true>(tid, s_tw2, sm);
+        __syncwarp();
+        phase_mid_c_tm(tid, hbase, sm);
+        __syncwarp();
+        fftk::phase_mid_bi<true>(tid, s_tw2, sm);
+        __syncthreads();
+        fftk::phase_ai<DECIM, ACCUM>(tid, blk, io, s_tw1, sm, fftk::NoTurn(), [&]() {
+            __syncthreads();
+            if (nb < nblocks) stage(nb);
+        });
+    }
+    tm_fence_before();
+    __syncthreads();
+    if (warp == 0) tm_dealloc_all(tmem);
 }
 
 // PACKED kernel (variant 37; fftfilt_pk.cuh): the same 16384-point block with FFMA2 / FADD2 / FMUL2 lanes,
@@ -463,6 +573,15 @@ int launch_part(rrc_fftfilt* h, const BlockIO& io, const float2* Hp, const float
         }
         return RRC_OK;
     }
+    if (h->variant == 40 && !io.real && !io.in_u8) {
+        auto tk = fftfilt_tmh_kernel<DECIM, ACCUM>;
+        RRC_CUDA(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_TMH_SMEM));
+        static const int tune = [] { const char* e = getenv("RRC_FFTFILT_TUNE"); return e ? (int)strtol(e, nullptr, 0) : 1; }();
+        tk<<<grid, fftk::NT, FFTFILT_TMH_SMEM, st>>>(io, Hp, h->tw1, h->tw2, nblocks, tune);
+        RRC_CHECK_LAUNCH();
+        count_launch();
+        return RRC_OK;
+    }
     auto kern = io.real ? fftfilt_kernel<DECIM, ACCUM, false> : h->variant == 33 ? fftfilt_pp_kernel<DECIM, ACCUM> : h->variant == 34 ? fftfilt_st_kernel<DECIM, ACCUM> : h->variant == 35 ? fftfilt_kernel<DECIM, ACCUM, true> : (h->variant == 36 && !io.in_u8) ? fftfilt_tma_kernel<DECIM, ACCUM> : fftfilt_kernel<DECIM, ACCUM, false>;
     RRC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_SMEM));
     static const int tune = [] { const char* e = getenv("RRC_FFTFILT_TUNE"); return e ? (int)strtol(e, nullptr, 0) : 1; }();
@@ -489,7 +608,7 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
     io.epi = h->epi;
     const bool decim = !(deci == 1 && skip == 0);
     // kernels that update the carried history themselves (one launch per run): the 512-thread LDG / TMA kernels
-    const bool fused_hist = h->T1 > 0 && (h->real || h->variant == 32 || h->variant == 35 || h->variant == 36 || h->variant == 37 || h->variant == 38 || h->variant == 39);
+    const bool fused_hist = h->T1 > 0 && (h->real || h->variant == 32 || h->variant == 35 || h->variant == 36 || h->variant == 37 || h->variant == 38 || h->variant == 39 || h->variant == 40);
     long long shift = 0;
     if (h->epi.kind != RRC_EPI_NONE && h->part_T1.size() > 1)
         return fail(RRC_ERR_UNSUPPORTED, "store epilogues need a single tap partition (ntaps <= 12289) on this path");
@@ -609,7 +728,7 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
         if (!h->tw1_16 && ((e = up(&h->tw1_16, t1)) != cudaSuccess || (e = up(&h->tw2_16, t2)) != cudaSuccess || (e = up(&h->tw3_16, t3)) != cudaSuccess))
             return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
     }
-    if (const char* v = getenv("RRC_FFTFILT_VARIANT")) h->variant = atoi(v) == 16 ? 16 : atoi(v) == 33 ? 33 : atoi(v) == 34 ? 34 : atoi(v) == 35 ? 35 : atoi(v) == 36 ? 36 : atoi(v) == 37 ? 37 : atoi(v) == 38 ? 38 : atoi(v) == 39 ? 39 : 32;
+    if (const char* v = getenv("RRC_FFTFILT_VARIANT")) h->variant = atoi(v) == 16 ? 16 : atoi(v) == 33 ? 33 : atoi(v) == 34 ? 34 : atoi(v) == 35 ? 35 : atoi(v) == 36 ? 36 : atoi(v) == 37 ? 37 : atoi(v) == 38 ? 38 : atoi(v) == 39 ? 39 : atoi(v) == 40 ? 40 : 32;
     h->Hp = h->part_Hp[0];
     if ((e = up(&h->tw1, tw1)) != cudaSuccess || (e = up(&h->tw2, tw2)) != cudaSuccess)
         return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));

@@ -35,6 +35,7 @@
 #include "common.cuh"
 #include "fftfilt_handle.hpp"
 #include "fftfilt_poly_core.cuh"
+#include "tmem.cuh"
 #include "fftfilt_tables.hpp"
 
 namespace rrc {
@@ -48,40 +49,6 @@ constexpr size_t poly_smem(bool hres) { return (size_t)(fftk::SMEM_ELEMS + 512 +
 constexpr int POLY_SLOTS = 4;                                  // scratch slots per CTA (see the kernel for why four)
 constexpr int POLY_NSTAMP = 16, POLY_TRACE_IT = 6;
 
-// 32 consecutive 32-bit columns of the thread's own TMEM lane <-> 16 float2
-__device__ __forceinline__ void tm_ld32(unsigned taddr, float2 (&x)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=f"(x[0].x), "=f"(x[0].y), "=f"(x[1].x), "=f"(x[1].y), "=f"(x[2].x), "=f"(x[2].y), "=f"(x[3].x), "=f"(x[3].y),
-          "=f"(x[4].x), "=f"(x[4].y), "=f"(x[5].x), "=f"(x[5].y), "=f"(x[6].x), "=f"(x[6].y), "=f"(x[7].x), "=f"(x[7].y),
-          "=f"(x[8].x), "=f"(x[8].y), "=f"(x[9].x), "=f"(x[9].y), "=f"(x[10].x), "=f"(x[10].y), "=f"(x[11].x), "=f"(x[11].y),
-          "=f"(x[12].x), "=f"(x[12].y), "=f"(x[13].x), "=f"(x[13].y), "=f"(x[14].x), "=f"(x[14].y), "=f"(x[15].x), "=f"(x[15].y)
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tm_st32(unsigned taddr, const float2 (&x)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        :: "r"(taddr),
-           "f"(x[0].x), "f"(x[0].y), "f"(x[1].x), "f"(x[1].y), "f"(x[2].x), "f"(x[2].y), "f"(x[3].x), "f"(x[3].y),
-           "f"(x[4].x), "f"(x[4].y), "f"(x[5].x), "f"(x[5].y), "f"(x[6].x), "f"(x[6].y), "f"(x[7].x), "f"(x[7].y),
-           "f"(x[8].x), "f"(x[8].y), "f"(x[9].x), "f"(x[9].y), "f"(x[10].x), "f"(x[10].y), "f"(x[11].x), "f"(x[11].y),
-           "f"(x[12].x), "f"(x[12].y), "f"(x[13].x), "f"(x[13].y), "f"(x[14].x), "f"(x[14].y), "f"(x[15].x), "f"(x[15].y)
-        : "memory");
-}
-__device__ __forceinline__ void tm_st16(unsigned taddr, const float2 (&x)[8]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        :: "r"(taddr),
-           "f"(x[0].x), "f"(x[0].y), "f"(x[1].x), "f"(x[1].y), "f"(x[2].x), "f"(x[2].y), "f"(x[3].x), "f"(x[3].y),
-           "f"(x[4].x), "f"(x[4].y), "f"(x[5].x), "f"(x[5].y), "f"(x[6].x), "f"(x[6].y), "f"(x[7].x), "f"(x[7].y)
-        : "memory");
-}
-__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
