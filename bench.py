@@ -256,7 +256,7 @@ class ClockSampler:
 
 # ------------------------------------------------------------ GPU arm -------
 KERNEL_NAMES = {
-    "fftfilt": "fftfilt_tma_kernel (TMA-staged input; RRC_FFTFILT_VARIANT=32 selects the LDG kernel)",
+    "fftfilt": "fftfilt_tmh_kernel<.,.,false,true> (TMA-staged input; spectrum and phase-B twiddles in tensor memory; RRC_FFTFILT_VARIANT=36 selects fftfilt_tma_kernel, 32 the LDG kernel)",
     "fir": "fir_poly_kernel<float2,float,1,false,16>", "fir_demod": "fir_rt_kernel<10,DEMOD,8,2>",
     "resample": "resample_kernel", "decode": "rtlsdr_decode_kernel", "fft": "fftstream_kernel<10>",
     "fftfilt_real": "fftfilt_kernel (real-stream mode)",

@@ -227,7 +227,74 @@ __device__ __forceinline__ void phase_mid_c_tm(int tid, unsigned hbase, float2* 
     }
 }
 
-template <bool DECIM, bool ACCUM>
+// TWP (variant 41): the 32 powers W_N^{t k1} of phases A and A' also live in the thread's TMEM strip (columns 256..), written once,
+// instead of being rebuilt from tw1[tid] with 31 complex multiplications twice per block.  Same values, bit-identical output.
+__device__ __forceinline__ void phase_a_compute_tm(unsigned pbase, float2 (&v)[32]) {
+    fftr::dit<32, +1>(v);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float2 p[16];
+        tm_ld32(pbase + 32u * half, p);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 * half + j] = fftr::cmul(v[16 * half + j], p[j]);
+    }
+}
+template <bool DECIM, bool ACCUM, class AfterLoad>
+__device__ __forceinline__ void phase_ai_tm(int tid, long long blk, const BlockIO& io, unsigned pbase, const float2* sm, AfterLoad after_load) {
+    const float2* s = sm + (tid >> 4) * fftk::ROW_PITCH + (tid & 15);
+    float2 v[32];
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) v[fftr::bitrev(k1, 5)] = s[k1 * fftk::PLANE_PITCH];
+    after_load();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float2 p[16];
+        tm_ld32(pbase + 32u * half, p);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[fftr::bitrev(16 * half + j, 5)] = fftr::cmul_conj(v[fftr::bitrev(16 * half + j, 5)], p[j]);
+    }
+    fftr::dit<32, -1>(v);
+    fftk::store_outputs<DECIM, ACCUM>(tid, blk, io, v);
+}
+
+// TWB (variant 42): instead of the phase-A powers, the 32 twiddles W_512^{l k2} of phases B and B' (64 LDS.64 per thread and
+// block out of ~330 shared-memory instructions) live in columns 256.. of the strip.
+__device__ __forceinline__ void phase_mid_b_tm(int tid, unsigned wbase, float2* sm) {
+    const int k1 = tid >> 4, l = tid & 15;
+    float2* col = sm + k1 * fftk::PLANE_PITCH + l;
+    float2 v[32];
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) v[fftr::bitrev(n2, 5)] = col[n2 * fftk::ROW_PITCH];
+    fftr::dit<32, +1>(v);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float2 w[16];
+        tm_ld32(wbase + 32u * half, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 * half + j] = fftr::cmul(v[16 * half + j], w[j]);
+    }
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) col[k2 * fftk::ROW_PITCH] = v[k2];
+}
+__device__ __forceinline__ void phase_mid_bi_tm(int tid, unsigned wbase, float2* sm) {
+    const int k1 = tid >> 4, l = tid & 15;
+    float2* col = sm + k1 * fftk::PLANE_PITCH + l;
+    float2 v[32];
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) v[fftr::bitrev(k2, 5)] = col[k2 * fftk::ROW_PITCH];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float2 w[16];
+        tm_ld32(wbase + 32u * half, w);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[fftr::bitrev(16 * half + j, 5)] = fftr::cmul_conj(v[fftr::bitrev(16 * half + j, 5)], w[j]);
+    }
+    fftr::dit<32, -1>(v);
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) col[n2 * fftk::ROW_PITCH] = v[n2];
+}
+
+template <bool DECIM, bool ACCUM, bool TWP, bool TWB = false>
 __global__ void __launch_bounds__(fftk::NT, 1)
 fftfilt_tmh_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2* __restrict__ tw1g,
                    const float2* __restrict__ tw2g, long long nblocks, int tune) {
@@ -262,6 +329,19 @@ fftfilt_tmh_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2
             for (int i = 0; i < 8; ++i) { const float4 h4 = hp[i]; x[2 * i] = make_float2(h4.x, h4.y); x[2 * i + 1] = make_float2(h4.z, h4.w); }
             tm_st32(hbase + 32u * half, x);
         }
+        if constexpr (TWB) {
+            float2 p[32];
+#pragma unroll
+            for (int k2 = 0; k2 < 32; ++k2) p[k2] = tw2g[k2 * 16 + (tid & 15)];
+            tm_st32(hbase + 256u, *reinterpret_cast<float2(*)[16]>(&p[0]));
+            tm_st32(hbase + 288u, *reinterpret_cast<float2(*)[16]>(&p[16]));
+        }
+        if constexpr (TWP) {
+            float2 p[32];
+            fftk::powers32(s_tw1[tid], p);
+            tm_st32(hbase + 256u, *reinterpret_cast<float2(*)[16]>(&p[0]));
+            tm_st32(hbase + 288u, *reinterpret_cast<float2(*)[16]>(&p[16]));
+        }
         tm_wait_st();
     }
     auto stage = [&](long long nb) {
@@ -288,21 +368,24 @@ fftfilt_tmh_kernel(const BlockIO io, const float2* __restrict__ Hp, const float2
         mbar_wait(mbar, parity);
         parity ^= 1;
         fftk::phase_a_linear_load(tid, sm, v);
-        fftk::phase_a_linear_compute(tid, s_tw1, v);
+        if constexpr (TWP) phase_a_compute_tm(hbase + 256u, v);
+        else fftk::phase_a_linear_compute(tid, s_tw1, v);
         __syncthreads();
         fftk::phase_a_linear_store(tid, sm, v);
         __syncthreads();
         if (pf) prefetch_segment(io, nb, nblocks, tid);
-        fftk::phase_mid_b<true>(tid, s_tw2, sm);
+        if constexpr (TWB) phase_mid_b_tm(tid, hbase + 256u, sm); else fftk::phase_mid_b<true>(tid, s_tw2, sm);
         __syncwarp();
         phase_mid_c_tm(tid, hbase, sm);
         __syncwarp();
-        fftk::phase_mid_bi<true>(tid, s_tw2, sm);
+        if constexpr (TWB) phase_mid_bi_tm(tid, hbase + 256u, sm); else fftk::phase_mid_bi<true>(tid, s_tw2, sm);
         __syncthreads();
-        fftk::phase_ai<DECIM, ACCUM>(tid, blk, io, s_tw1, sm, fftk::NoTurn(), [&]() {
+        auto after = [&]() {
             __syncthreads();
             if (nb < nblocks) stage(nb);
-        });
+        };
+        if constexpr (TWP) phase_ai_tm<DECIM, ACCUM>(tid, blk, io, hbase + 256u, sm, after);
+        else fftk::phase_ai<DECIM, ACCUM>(tid, blk, io, s_tw1, sm, fftk::NoTurn(), after);
     }
     tm_fence_before();
     __syncthreads();
@@ -573,8 +656,8 @@ int launch_part(rrc_fftfilt* h, const BlockIO& io, const float2* Hp, const float
         }
         return RRC_OK;
     }
-    if (h->variant == 40 && !io.real && !io.in_u8) {
-        auto tk = fftfilt_tmh_kernel<DECIM, ACCUM>;
+    if ((h->variant == 40 || h->variant == 41 || h->variant == 42) && !io.real && !io.in_u8) {
+        auto tk = h->variant == 42 ? fftfilt_tmh_kernel<DECIM, ACCUM, false, true> : h->variant == 41 ? fftfilt_tmh_kernel<DECIM, ACCUM, true> : fftfilt_tmh_kernel<DECIM, ACCUM, false>;
         RRC_CUDA(cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FFTFILT_TMH_SMEM));
         static const int tune = [] { const char* e = getenv("RRC_FFTFILT_TUNE"); return e ? (int)strtol(e, nullptr, 0) : 1; }();
         tk<<<grid, fftk::NT, FFTFILT_TMH_SMEM, st>>>(io, Hp, h->tw1, h->tw2, nblocks, tune);
@@ -608,7 +691,7 @@ int launch(rrc_fftfilt* h, const float* in, size_t n, float* out, size_t n_out, 
     io.epi = h->epi;
     const bool decim = !(deci == 1 && skip == 0);
     // kernels that update the carried history themselves (one launch per run): the 512-thread LDG / TMA kernels
-    const bool fused_hist = h->T1 > 0 && (h->real || h->variant == 32 || h->variant == 35 || h->variant == 36 || h->variant == 37 || h->variant == 38 || h->variant == 39 || h->variant == 40);
+    const bool fused_hist = h->T1 > 0 && (h->real || h->variant == 32 || h->variant == 35 || h->variant == 36 || h->variant == 37 || h->variant == 38 || h->variant == 39 || h->variant == 40 || h->variant == 41 || h->variant == 42);
     long long shift = 0;
     if (h->epi.kind != RRC_EPI_NONE && h->part_T1.size() > 1)
         return fail(RRC_ERR_UNSUPPORTED, "store epilogues need a single tap partition (ntaps <= 12289) on this path");
@@ -728,7 +811,7 @@ int rrc_fftfilt_c32_create(int device, const float* taps, size_t ntaps, rrc_fftf
         if (!h->tw1_16 && ((e = up(&h->tw1_16, t1)) != cudaSuccess || (e = up(&h->tw2_16, t2)) != cudaSuccess || (e = up(&h->tw3_16, t3)) != cudaSuccess))
             return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));
     }
-    if (const char* v = getenv("RRC_FFTFILT_VARIANT")) h->variant = atoi(v) == 16 ? 16 : atoi(v) == 33 ? 33 : atoi(v) == 34 ? 34 : atoi(v) == 35 ? 35 : atoi(v) == 36 ? 36 : atoi(v) == 37 ? 37 : atoi(v) == 38 ? 38 : atoi(v) == 39 ? 39 : atoi(v) == 40 ? 40 : 32;
+    if (const char* v = getenv("RRC_FFTFILT_VARIANT")) h->variant = atoi(v) == 16 ? 16 : atoi(v) == 33 ? 33 : atoi(v) == 34 ? 34 : atoi(v) == 35 ? 35 : atoi(v) == 36 ? 36 : atoi(v) == 37 ? 37 : atoi(v) == 38 ? 38 : atoi(v) == 39 ? 39 : atoi(v) == 40 ? 40 : atoi(v) == 41 ? 41 : atoi(v) == 42 ? 42 : 32;
     h->Hp = h->part_Hp[0];
     if ((e = up(&h->tw1, tw1)) != cudaSuccess || (e = up(&h->tw2, tw2)) != cudaSuccess)
         return cleanup(fail(RRC_ERR_CUDA, "FftFilter table upload failed: %s", cudaGetErrorString(e)));

@@ -47,11 +47,12 @@ struct rrc_fftfilt {
     int real = 0;                     // real stream + real taps (rrc_fftfilt_f32_create): f32 in / out / history
     int in_u8 = 0;                    // 1: run() inputs are u8 I/Q pairs (rrc_fftfilt_set_input_u8iq)
     rrc::Epi epi;                     // fused store epilogue (rrc_fftfilt_set_epilogue)
-    // kernel variant (RRC_FFTFILT_VARIANT): 40 = 36 with the whole spectrum in tensor memory (default: fftfilt_tmh_kernel),
+    // kernel variant (RRC_FFTFILT_VARIANT): fftfilt_tmh_kernel = 36 with per-thread constants in tensor memory: 40 = the whole
+    // spectrum, 41 = spectrum + the phase-A / A' twiddle powers, 42 = spectrum + the phase-B / B' twiddles (default),
     // 37 = PACKED FP32 lanes + TMA-staged input (fftfilt_pk.cuh),
     // 36 = 512 threads x 32 points with TMA-staged input, half the spectrum in shared memory, half from L2,
     // 32 = the same with LDG input + L2 prefetch, 16 = 1024 threads x 16 points, 33/34/35 = experiments
-    int variant = 40;
+    int variant = 42;
     float2* tw1 = nullptr;
     float2* tw2 = nullptr;
     float2* hist[2] = {nullptr, nullptr};
