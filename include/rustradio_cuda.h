@@ -197,6 +197,10 @@ int rrc_fir_run_host(rrc_fir_t* h, const void* in_host, size_t n_in, void* out_h
  * rule (whole blocks of nsamples = 2*nextpow2(ntaps) - ntaps, trailing
  * partial block never flushed, :306-327) is applied by the caller / by
  * rrc_fftfilt_plan.
+ * Kernel selection of run(): Complex c32 streams take fftfilt_tmh_kernel (TMA-staged input; the filter spectrum and the
+ * phase-B twiddles are thread-private tables in tensor memory: RRC_FFTFILT_VARIANT=42, the default; 40 / 41 = other table
+ * choices, 36 = fftfilt_tma_kernel with the spectrum half in shared memory, half from L2, 32 = the LDG kernel); u8 I/Q input
+ * and real (f32) streams take fftfilt_kernel.  Every variant computes the same values (same tables, same arithmetic).
  */
 typedef struct rrc_fftfilt rrc_fftfilt_t;
 
